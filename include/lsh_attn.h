@@ -1,0 +1,152 @@
+/*
+ * lsh_attn.h — C ABI of the B200-native Reformer LSH-attention path (liblsh_attn_b200.so).
+ *
+ * The reference (google/trax) has NO native code and no FFI for this path: the hot path is
+ * `trax/layers/research/efficient_attention.py` ("EA") class LSHSelfAttention, pure Python over
+ * jax.numpy.  These entry points are what a `jax.ffi` custom call (or the ctypes binding shipped
+ * in trax_b200/_lib.py) binds in place of the XLA ops that EA lowers to; each declaration cites the
+ * reference lines it replaces.  See INTEGRATION.md for the reference-side stub.
+ *
+ * Conventions
+ *   - plain C, device pointers only (unless a name ends in _host), no allocation inside, no
+ *     synchronisation inside: every call is asynchronous on the caller-supplied CUDA stream
+ *     (`stream` is a cudaStream_t passed as void*).
+ *   - scratch memory comes from the caller: query `*_workspace_bytes`, pass `ws`/`ws_bytes`.
+ *   - return value 0 = OK; non-zero = error, message in lsh_attn_last_error() (thread-local).
+ *   - a "unit" is one (example b, head h) pair, unit index u = b*H + h (EA:2406-2407).
+ *   - N = nh*L is the sorted length of one unit; "ticker" index = round*L + position (EA:1946).
+ *
+ * Device layouts (all row-major, innermost last)
+ *   x, out, dout, dx : (B, L, D)            act_dtype (f32 or bf16)
+ *   w_q              : (H, D, dq) f32       w_v : (H, D, dv) f32       w_o : (H, dv, D) f32   (EA:1845-1868)
+ *   wqv (packed)     : (D, H, dq+dv) bf16   — columns [h][0:dq]=w_q[h], [h][dq:dq+dv]=w_v[h]
+ *   wo  (packed)     : (H*dv, D) bf16
+ *   qv               : (B, L, H, dq+dv) bf16 — q then v of head h for token (b,t)
+ *   rotations        : (B*H, dq, nh, R) f32 (EA:91, one draw per unit because the hash rng lives in
+ *                      per-unit state, EA:1927-1929); R = sum(factors)/2
+ *   mask             : (B, L) uint8, 1 = valid token (only when dims.masked)
+ *   buckets          : (B*H, buckets_stride) int32, first nh*L entries of each row used (EA:1913-1916, 1930-1941)
+ *   sticker, undo    : (B*H, nh*L) int32 (EA:1951-1953)
+ *   o_rounds         : (B*H, nh*L, dv) bf16 in TICKER order (= EA:1985 `o` before the combine)
+ *   logits           : (B*H, nh*L) f32 in ticker order (EA:1986)
+ *   o_comb           : (B, L, H, dv) bf16 (EA:1992 `o`, heads side by side so that w_o sums heads, EA:2426)
+ */
+#ifndef LSH_ATTN_H_
+#define LSH_ATTN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LSH_ATTN_ABI_VERSION 1
+
+enum { LSH_DTYPE_F32 = 0, LSH_DTYPE_BF16 = 1 };
+
+/* Hyper-parameters of one call: the constructor arguments of EA:1732-1748 that the train path uses,
+ * plus the input shape.  `factors` is the hash factor list after EA:1893-1902 resolved n_buckets. */
+typedef struct LshAttnDims {
+  int32_t B, H, L, D;      /* batch, n_heads, seqlen, d_model */
+  int32_t dq, dv;          /* d_qk, d_v */
+  int32_t C, nb, na, nh;   /* chunk_len, n_chunks_before, n_chunks_after, n_hashes */
+  int32_t n_factors;       /* 1..4 */
+  int32_t factors[4];      /* even ints; n_buckets = prod(factors) (+1 when masked, EA:1908) */
+  int32_t causal, masked;  /* bools */
+  int32_t act_dtype;       /* LSH_DTYPE_* of x/out/dout/dx */
+  int32_t reserved[3];
+} LshAttnDims;
+
+int lsh_attn_abi_version(void);
+const char *lsh_attn_last_error(void);
+
+/* 0 when the shape is supported by the sm_100a kernels; otherwise non-zero + message.  There is no
+ * CPU or generic fallback: unsupported shapes are rejected. */
+int lsh_attn_check_dims(const LshAttnDims *dims);
+
+/* ---- stage-level entry points ---------------------------------------------------------------- */
+
+/* Weight layout change + f32→bf16 (replaces nothing in EA; prepares operands for EA:1923-1924, 1995). */
+int lsh_pack_weights(const LshAttnDims *dims, const float *w_q, const float *w_v, const float *w_o,
+                     void *wqv_bf16, void *wo_bf16, void *stream);
+
+/* EA:1923-1924  q = x·w_q ; v = x·w_v for every unit at once.  x_bf16 (B,L,D) bf16. */
+int lsh_project_qv(const LshAttnDims *dims, const void *x_bf16, const void *wqv_bf16, void *qv_bf16,
+                   void *ws, size_t ws_bytes, void *stream);
+
+/* EA:1889-1916 hash_vectors + EA:60-119 hash_vecs: fp32 sequential-fmaf rotation, argmax over
+ * [x,-x] per factor (first max wins), factor combine, mask bucket, per-round offsets. */
+int lsh_hash(const LshAttnDims *dims, const void *qv_bf16, const float *rotations,
+             const uint8_t *mask, int32_t *buckets, int64_t buckets_stride, void *stream);
+
+/* Same hash on caller-supplied fp32 vectors (BH, L, dq) — the `hash_vecs`-granularity entry. */
+int lsh_hash_f32(const LshAttnDims *dims, const float *vecs, const float *rotations,
+                 const uint8_t *mask, int32_t *buckets, int64_t buckets_stride, void *stream);
+
+/* EA:1946-1956 the two sort_key_val calls: stable sort of key = L*bucket + position per unit.
+ * Emits sticker and (if non-null) undo_sort. */
+size_t lsh_sort_workspace_bytes(const LshAttnDims *dims);
+int lsh_sort(const LshAttnDims *dims, const int32_t *buckets, int64_t buckets_stride,
+             int32_t *sticker, int32_t *undo_sort, void *ws, size_t ws_bytes, void *stream);
+
+/* EA:1958-1986: gather by sticker, `attend` (EA:163-268) with look-back window, masks
+ * (EA:145-160), per-row log-sum-exp, and the un-sort of EA:1985-1986 (rows are written straight to
+ * their ticker slot).  o_rounds may alias o_comb's layout when nh==1 via lsh_attend_fwd_strided. */
+int lsh_attend_fwd(const LshAttnDims *dims, const void *qv_bf16, const int32_t *sticker,
+                   const uint8_t *mask, void *o_rounds_bf16, float *logits, void *stream);
+
+/* EA:1988-1992 multi-round combine; also emits lse_tot = logsumexp_h(logits) (BH, L) when non-null. */
+int lsh_combine_fwd(const LshAttnDims *dims, const void *o_rounds_bf16, const float *logits,
+                    void *o_comb_bf16, float *lse_tot, void *stream);
+
+/* EA:1995 out = o·w_o summed over heads (EA:2426).  out dtype = dims->act_dtype. */
+int lsh_project_out(const LshAttnDims *dims, const void *o_comb_bf16, const void *wo_bf16, void *out,
+                    void *ws, size_t ws_bytes, void *stream);
+
+/* VJP of EA:1958-1992 with the permutation fixed (jax.vjp at EA:2418-2421; formulas in SURVEY.md
+ * App. B): recomputes S and P per chunk from qv + sticker; do_comb is the cotangent of o_comb
+ * (B,L,H,dv) bf16.  Writes dqv (B,L,H,dq+dv) bf16, the cotangent of qv. */
+size_t lsh_attend_bwd_workspace_bytes(const LshAttnDims *dims);
+int lsh_attend_bwd(const LshAttnDims *dims, const void *qv_bf16, const int32_t *sticker,
+                   const uint8_t *mask, const void *o_comb_bf16, const float *lse_tot,
+                   const void *do_comb_bf16, void *dqv_bf16, void *ws, size_t ws_bytes,
+                   void *stream);
+
+/* ---- layer-level entry points (EA:2261-2561 forward_and_or_backward) -------------------------- */
+
+size_t lsh_layer_workspace_bytes(const LshAttnDims *dims, int with_grad);
+
+/* compute_output=True.  update_state=True when `rotations` != NULL: buckets are computed and
+ * written (EA:1926-1937); otherwise buckets are read (EA:1939-1941). */
+int lsh_layer_fwd(const LshAttnDims *dims, const void *x, const float *w_q, const float *w_v,
+                  const float *w_o, const float *rotations, const uint8_t *mask, int32_t *buckets,
+                  int64_t buckets_stride, void *out, void *ws, size_t ws_bytes, void *stream);
+
+/* output_grad given, update_state=False: recomputes the forward from the stored buckets, then the
+ * backward.  `out` may be NULL (compute_output=False, EA:2256-2258) or a buffer
+ * (compute_output=True, the call ReversibleHalfResidual makes, reversible.py:374-378).
+ * dw_q/dw_v/dw_o are fully overwritten with the sum over examples (EA:2431); dx (B,L,D) with the
+ * sum over heads (EA:2430). */
+int lsh_layer_bwd(const LshAttnDims *dims, const void *x, const float *w_q, const float *w_v,
+                  const float *w_o, const uint8_t *mask, const int32_t *buckets,
+                  int64_t buckets_stride, const void *dout, void *out, void *dx, float *dw_q,
+                  float *dw_v, float *dw_o, void *ws, size_t ws_bytes, void *stream);
+
+/* ---- helpers ---------------------------------------------------------------------------------- */
+
+/* Counter-based N(0,1) draws for the rotations (stands in for fastmath.random.normal at EA:92;
+ * NOT bit-compatible with jax.random — a JAX host passes its own rotations instead).
+ * keys: (B*H, 2) uint32 per-unit hash keys (EA:1870-1882 state rng); new_keys (B*H,2) receives the
+ * advanced key (EA:1928 split). */
+int lsh_make_rotations(const LshAttnDims *dims, const uint32_t *keys, uint32_t *new_keys,
+                       float *rotations, void *stream);
+
+/* Number of kernels this library has launched on this thread since the last reset (bench.py's
+ * gpu_launches claim). */
+int64_t lsh_attn_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* LSH_ATTN_H_ */

@@ -1,0 +1,236 @@
+"""GPU parity tests of the layer (`trax_b200.LSHSelfAttention`) against the CPU oracle, modelled on
+`trax/layers/research/efficient_attention_test.py` (:63-73, :136-156, :210-284, :322-328, :376-440).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import lsh_oracle as O
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _layer(cfg, **kw):
+  import trax_b200
+  return trax_b200.LSHSelfAttention(
+      n_heads=cfg.n_heads, d_qk=64, d_v=64, causal=cfg.causal, masked=cfg.masked, chunk_len=cfg.chunk_len,
+      n_chunks_before=cfg.n_chunks_before, n_chunks_after=cfg.n_chunks_after, n_hashes=cfg.n_hashes,
+      n_buckets=cfg.n_buckets, max_length_for_buckets=cfg.max_length_for_buckets, **kw)
+
+
+def _case(seed, B, L, D, cfg, dtype):
+  rng = np.random.default_rng(seed)
+  x = rng.standard_normal((B, L, D)).astype(np.float32)
+  if dtype == torch.bfloat16:
+    x = util.bf16_round(x)
+  weights = O.init_weights(cfg.n_heads, D, 64, 64, seed=seed + 1)
+  factors = O.bucket_factors(cfg.n_buckets, L, cfg.chunk_len)
+  rot = rng.standard_normal((B * cfg.n_heads, 64, cfg.n_hashes, sum(factors) // 2)).astype(np.float32)
+  dout = rng.standard_normal((B, L, D)).astype(np.float32)
+  if dtype == torch.bfloat16:
+    dout = util.bf16_round(dout)
+  mask = (rng.random((B, L)) > 0.2) if cfg.masked else None
+  return x, weights, rot, dout, mask
+
+
+LAYER_CASES = [
+    # (B, L, D, dtype, cfg)
+    (1, 1024, 256, torch.float32, util.make_cfg(H=2, C=64, nh=1, n_buckets=32)),                  # BASELINE config 1
+    (2, 512, 128, torch.bfloat16, util.make_cfg(H=4, C=128, nh=4, n_buckets=None)),               # config-2 style
+    (1, 768, 256, torch.bfloat16, util.make_cfg(H=2, C=128, nh=2, n_buckets=12)),                 # int n_buckets, nh=2
+    (2, 256, 64, torch.float32, util.make_cfg(H=2, C=64, nb=1, na=1, nh=2, n_buckets=8, causal=False, masked=True)),
+]
+
+
+@pytest.mark.parametrize('B,L,D,dtype,cfg', LAYER_CASES)
+def test_layer_fwd_bwd_shared_buckets(B, L, D, dtype, cfg):
+  """T3 + T4: update_state=False with the oracle's buckets in `state` (reversible.py:374-378)."""
+  x, weights, rot, dout, mask = _case(21, B, L, D, cfg, dtype)
+  want_out, buckets, _, _ = O.forward_and_or_backward(cfg, x, weights, rotations=rot, mask=mask, update_state=True)
+  _, _, want_dx, want_dw = O.forward_and_or_backward(cfg, x, weights, buckets=buckets, mask=mask, output_grad=dout,
+                                                     update_state=False)
+  layer = _layer(cfg)
+  w_d = tuple(torch.from_numpy(w).cuda() for w in weights)
+  x_d = torch.from_numpy(x).cuda().to(dtype)
+  inputs = x_d if mask is None else (x_d, torch.from_numpy(mask).cuda())
+  state = (torch.from_numpy(buckets).cuda(), torch.zeros((B * cfg.n_heads, 2), dtype=torch.int32, device='cuda'))
+  out, new_state, dx, dw = layer.forward_and_or_backward(
+      inputs, w_d, state, None, output_grad=torch.from_numpy(dout).cuda().to(dtype), compute_output=True,
+      update_state=False)
+  assert new_state is None and out.dtype == dtype and out.shape == x_d.shape
+  util.assert_close(out.float().cpu().numpy(), want_out, 'out')
+  dx0 = dx if mask is None else dx[0]
+  util.assert_close(dx0.float().cpu().numpy(), want_dx, 'dx')
+  for name, g, w in zip(('dw_q', 'dw_v', 'dw_o'), dw, want_dw):
+    assert g.dtype == torch.float32
+    util.assert_close(g.cpu().numpy(), w, name)
+  # cotangent = ones, as the reference test does (efficient_attention_test.py:81)
+  ones = np.ones_like(dout)
+  _, _, want_dx1, want_dw1 = O.forward_and_or_backward(cfg, x, weights, buckets=buckets, mask=mask, output_grad=ones,
+                                                       update_state=False)
+  out2, _, dx1, dw1 = layer.forward_and_or_backward(
+      inputs, w_d, state, None, output_grad=torch.ones_like(x_d), compute_output=False, update_state=False)
+  assert out2 is None
+  util.assert_close((dx1 if mask is None else dx1[0]).float().cpu().numpy(), want_dx1, 'dx(ones)')
+  for name, g, w in zip(('dw_q', 'dw_v', 'dw_o'), dw1, want_dw1):
+    util.assert_close(g.cpu().numpy(), w, name + '(ones)')
+
+
+@pytest.mark.parametrize('B,L,D,dtype,cfg', LAYER_CASES[:3])
+def test_layer_forward_update_state(B, L, D, dtype, cfg):
+  """update_state=True: buckets bit-exact vs the oracle hashing the DEVICE q (hash_vecs granularity), state shapes
+  as efficient_attention_test.py:322-328, output within tolerance of the oracle run on those buckets."""
+  from trax_b200 import ops, _lib
+  x, weights, rot, _, mask = _case(22, B, L, D, cfg, dtype)
+  layer = _layer(cfg)
+  layer._rotations_override = torch.from_numpy(rot).cuda()
+  w_d = tuple(torch.from_numpy(w).cuda() for w in weights)
+  x_d = torch.from_numpy(x).cuda().to(dtype)
+  layer.init(__import__('trax_b200').ShapeDtype((B, L, D)))
+  layer.weights = w_d
+  out = layer.forward(x_d)
+  buckets, rng_state = layer.state
+  assert tuple(buckets.shape) == (B * cfg.n_heads, cfg.n_hashes * L) and buckets.dtype == torch.int32
+  assert tuple(rng_state.shape) == (B * cfg.n_heads, 2)
+  # device q (bf16) -> oracle hash
+  factors = O.bucket_factors(cfg.n_buckets, L, cfg.chunk_len)
+  dims = _lib.make_dims(B, cfg.n_heads, L, D, 64, 64, cfg.chunk_len, 1, 0, cfg.n_hashes, factors, True, False, 1)
+  wqv, _ = ops.pack_weights(dims, *w_d)
+  qv = ops.project_qv(dims, x_d.to(torch.bfloat16).contiguous(), wqv).float().cpu().numpy()
+  got_b = buckets.cpu().numpy()
+  for u in range(B * cfg.n_heads):
+    b, h = divmod(u, cfg.n_heads)
+    want_b = O.hash_vectors(cfg, np.ascontiguousarray(qv[b, :, h, :64]), rot[u])
+    np.testing.assert_array_equal(got_b[u], want_b)
+  want_out, _, _, _ = O.forward_and_or_backward(cfg, x, weights, buckets=got_b, update_state=False)
+  util.assert_close(out.float().cpu().numpy(), want_out, 'out')
+  # how far the device q is from the fp32 q: fraction of bucket ids that differ from hashing the oracle's own q
+  b_ref = O.forward_and_or_backward(cfg, x, weights, rotations=rot, update_state=True)[1]
+  print('bucket-id mismatch vs oracle-q hashing: %.4f' % float((b_ref != got_b).mean()))
+
+
+def test_determinism_and_rng_advance():
+  """efficient_attention_test.py:210-236: same seeds -> same output; the state's rng advances (EA:1928)."""
+  import trax_b200
+  cfg = util.make_cfg(H=2, C=64, nh=2, n_buckets=16)
+  x = torch.randn(2, 256, 64, device='cuda', generator=torch.Generator('cuda').manual_seed(0))
+  outs = []
+  for _ in range(3):
+    layer = _layer(cfg)
+    layer.init(trax_b200.ShapeDtype((2, 256, 64)), rng=np.array([1, 2], np.uint32))
+    s0 = layer.state[1].clone()
+    outs.append(layer.forward(x))
+    assert not torch.equal(layer.state[1].view(torch.int32), s0.view(torch.int32))
+  assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+  out_b = layer.forward(x)                       # second step: new rotations from the advanced key
+  assert not torch.equal(out_b, outs[0])
+
+
+def test_unit_batching_invariance():
+  """Analogue of n_parallel_heads ∈ {1,3,6,12} (efficient_attention_test.py:136-156): examples processed together
+  equal examples processed one at a time."""
+  cfg = util.make_cfg(H=2, C=64, nh=2, n_buckets=8)
+  B, L, D = 3, 256, 64
+  x, weights, rot, dout, _ = _case(23, B, L, D, cfg, torch.bfloat16)
+  buckets = O.forward_and_or_backward(cfg, x, weights, rotations=rot, update_state=True)[1]
+  layer = _layer(cfg)
+  w_d = tuple(torch.from_numpy(w).cuda() for w in weights)
+  x_d, g_d = torch.from_numpy(x).cuda().bfloat16(), torch.from_numpy(dout).cuda().bfloat16()
+  b_d = torch.from_numpy(buckets).cuda()
+  rng0 = torch.zeros((B * 2, 2), dtype=torch.int32, device='cuda')
+  out, _, dx, dw = layer.forward_and_or_backward(x_d, w_d, (b_d, rng0), None, output_grad=g_d, update_state=False)
+  dw_sum = [torch.zeros_like(g) for g in dw]
+  for b in range(B):
+    o1, _, dx1, dw1 = layer.forward_and_or_backward(
+        x_d[b:b + 1].contiguous(), w_d, (b_d[2 * b:2 * b + 2].contiguous(), rng0[:2]), None,
+        output_grad=g_d[b:b + 1].contiguous(), update_state=False)
+    assert torch.equal(o1[0], out[b]) and torch.equal(dx1[0], dx[b])
+    for acc, g in zip(dw_sum, dw1):
+      acc += g
+  for a, g in zip(dw_sum, dw):
+    torch.testing.assert_close(a, g, rtol=1e-3, atol=1e-3)
+
+
+def test_masked_invariance():
+  """efficient_attention_test.py:238-284: changing masked-out inputs leaves unmasked outputs unchanged."""
+  cfg = util.make_cfg(H=2, C=64, nb=1, na=1, nh=2, n_buckets=8, causal=False, masked=True)
+  B, L, D = 1, 256, 64
+  x, weights, rot, _, _ = _case(24, B, L, D, cfg, torch.float32)
+  mask = np.ones((B, L), bool)
+  mask[:, L // 2:] = False
+  layer = _layer(cfg)
+  layer._rotations_override = torch.from_numpy(rot).cuda()
+  w_d = tuple(torch.from_numpy(w).cuda() for w in weights)
+  st = (torch.zeros((2, 2 * L), dtype=torch.int32, device='cuda'), torch.zeros((2, 2), dtype=torch.int32, device='cuda'))
+  x1 = torch.from_numpy(x).cuda()
+  x2 = x1.clone()
+  x2[:, L // 2:] = torch.randn_like(x2[:, L // 2:])
+  m = torch.from_numpy(mask).cuda()
+  o1 = layer.forward_and_or_backward((x1, m), w_d, st, None)[0]
+  o2 = layer.forward_and_or_backward((x2, m), w_d, st, None)[0]
+  torch.testing.assert_close(o1[:, :L // 2], o2[:, :L // 2], rtol=1e-5, atol=1e-5)
+
+
+def test_autograd_through_pure_fn():
+  """base.py:585-590, 644-673: pure_fn routes through the custom backward; torch autograd sees it."""
+  import trax_b200
+  cfg = util.make_cfg(H=2, C=64, nh=2, n_buckets=8)
+  B, L, D = 1, 256, 64
+  x, weights, rot, dout, _ = _case(25, B, L, D, cfg, torch.float32)
+  layer = _layer(cfg)
+  layer._rotations_override = torch.from_numpy(rot).cuda()
+  layer.init(trax_b200.ShapeDtype((B, L, D)))
+  w_d = tuple(torch.from_numpy(w).cuda().requires_grad_() for w in weights)
+  x_d = torch.from_numpy(x).cuda().requires_grad_()
+  out, new_state = layer.pure_fn(x_d, w_d, layer.state, None)
+  (out * torch.from_numpy(dout).cuda()).sum().backward()
+  buckets = new_state[0].cpu().numpy()
+  _, _, want_dx, want_dw = O.forward_and_or_backward(cfg, x, weights, buckets=buckets, output_grad=dout, update_state=False)
+  util.assert_close(x_d.grad.cpu().numpy(), want_dx, 'dx')
+  for name, w, g in zip(('dw_q', 'dw_v', 'dw_o'), w_d, want_dw):
+    util.assert_close(w.grad.cpu().numpy(), g, name)
+
+
+def test_max_length_for_buckets_state_layout():
+  """EA:1880, 1930-1941: state is padded to n_hashes*max_length_for_buckets and only the prefix is used."""
+  import trax_b200
+  cfg = util.make_cfg(H=2, C=64, nh=2, n_buckets=8, max_len=512)
+  layer = _layer(cfg)
+  layer.init(trax_b200.ShapeDtype((1, 256, 64)))
+  assert tuple(layer.state[0].shape) == (2, 2 * 512)
+  x = torch.randn(1, 256, 64, device='cuda')
+  out = layer.forward(x)
+  assert tuple(layer.state[0].shape) == (2, 2 * 512)
+  assert (layer.state[0][:, 2 * 256:] == 0).all()
+  out2 = layer.forward_and_or_backward(x, layer.weights, layer.state, None, update_state=False)[0]
+  assert torch.equal(out, out2)
+
+
+def test_unsupported_shapes_are_rejected():
+  """no fallback — the reference's odd test shapes (d_qk=7, d_v=17, chunk_len=5) raise."""
+  import trax_b200
+  from trax_b200 import _lib
+  layer = trax_b200.LSHSelfAttention(n_heads=6, d_qk=7, d_v=17, chunk_len=5, n_hashes=2, n_buckets=4, causal=True)
+  layer.init(trax_b200.ShapeDtype((2, 10, 13)))
+  with pytest.raises(_lib.LshAttnError):
+    layer.forward(torch.zeros(2, 10, 13, device='cuda'))
+  with pytest.raises(NotImplementedError):
+    trax_b200.LSHSelfAttention(mode='predict', causal=True)
+  with pytest.raises(NotImplementedError):
+    trax_b200.LSHSelfAttention(attention_dropout=0.1)
+  with pytest.raises(ValueError):
+    trax_b200.LSHSelfAttention(n_heads=6, n_parallel_heads=4)
+
+
+def test_host_buffers_roundtrip():
+  """Host (pinned) tensors in -> host tensors out: the e2e path bench.py times."""
+  import trax_b200
+  cfg = util.make_cfg(H=2, C=64, nh=1, n_buckets=8)
+  layer = _layer(cfg)
+  layer.init(trax_b200.ShapeDtype((1, 256, 64)))
+  x = torch.randn(1, 256, 64).pin_memory()
+  out = layer.forward(x)
+  assert not out.is_cuda and out.shape == x.shape
+  out_d = layer.forward_and_or_backward(x.cuda(), layer.weights, layer.state, None, update_state=False)[0]
+  torch.testing.assert_close(out, out_d.cpu(), rtol=0, atol=0)

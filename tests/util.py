@@ -1,0 +1,53 @@
+"""Shared helpers for the parity tests: seeded cases, oracle adapters, tolerance checks."""
+import numpy as np
+import torch
+
+from oracle import lsh_oracle as O
+
+# north_star tolerance for floating-point results: 2e-2 relative / 1e-3 absolute, applied as
+# |got - want| <= ATOL * scale + RTOL * |want| with scale = max(1, rms(want)) so that the absolute
+# term follows the tensor's magnitude (gradient tensors are O(10..100)).
+RTOL, ATOL = 2e-2, 1e-3
+
+
+def bf16_round(a):
+  """fp32/fp64 numpy -> values representable in bf16 (as float32 numpy)."""
+  return torch.from_numpy(np.asarray(a, np.float32)).to(torch.bfloat16).to(torch.float32).numpy()
+
+
+def close_report(got, want, rtol=RTOL, atol=ATOL):
+  got = np.asarray(got, np.float64)
+  want = np.asarray(want, np.float64)
+  scale = max(1.0, float(np.sqrt(np.mean(want ** 2))))
+  err = np.abs(got - want)
+  tol = atol * scale + rtol * np.abs(want)
+  bad = err > tol
+  return dict(max_abs=float(err.max()), max_ref=float(np.abs(want).max()), rms_ref=float(np.sqrt(np.mean(want ** 2))),
+              n_bad=int(bad.sum()), frac_bad=float(bad.mean()), worst_ratio=float((err / tol).max()))
+
+
+def assert_close(got, want, name, rtol=RTOL, atol=ATOL):
+  assert np.isfinite(np.asarray(got, np.float64)).all(), '%s has non-finite values' % name
+  r = close_report(got, want, rtol, atol)
+  assert r['n_bad'] == 0, '%s outside %g rel / %g abs: %s' % (name, rtol, atol, r)
+  return r
+
+
+def make_cfg(H=2, C=64, nb=1, na=0, nh=1, n_buckets=None, causal=True, masked=False, max_len=None):
+  return O.LSHConfig(n_heads=H, d_qk=64, d_v=64, causal=causal, masked=masked, chunk_len=C,
+                     n_chunks_before=nb, n_chunks_after=na, n_hashes=nh, n_buckets=n_buckets,
+                     max_length_for_buckets=max_len)
+
+
+def random_valid_buckets(rng, BH, nh, L, n_buckets):
+  b = rng.integers(0, n_buckets, size=(BH, nh, L)).astype(np.int32)
+  b += (np.arange(nh, dtype=np.int32) * n_buckets)[None, :, None]
+  return b.reshape(BH, nh * L)
+
+
+def core_identity_weights():
+  """x = [q|v] (D=128), w_q=[I;0], w_v=[0;I], w_o=I: the oracle's unit then reduces to the attention core."""
+  w_q = np.zeros((128, 64)); w_q[:64] = np.eye(64)
+  w_v = np.zeros((128, 64)); w_v[64:] = np.eye(64)
+  w_o = np.eye(64)
+  return w_q, w_v, w_o

@@ -1,0 +1,10 @@
+"""trax_b200 — B200-native (sm_100a) implementation of ONE hot path of google/trax:
+`trax.layers.research.efficient_attention.LSHSelfAttention` forward + backward.
+
+Layout: csrc/ (CUDA kernels + C ABI, built to liblsh_attn_b200.so), _lib.py (ctypes binding),
+ops.py (stage-level wrappers), lsh_attention.py (the layer with the reference's interface).
+Importing the package does not need a GPU; calling anything does, and raises otherwise.
+"""
+from trax_b200.lsh_attention import LSHSelfAttention, ShapeDtype  # noqa: F401
+
+__all__ = ['LSHSelfAttention', 'ShapeDtype']

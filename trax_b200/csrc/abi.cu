@@ -1,0 +1,337 @@
+// extern "C" surface of liblsh_attn_b200.so (see include/lsh_attn.h) + the layer-level orchestration
+// that mirrors LSHSelfAttention.forward_and_or_backward (EA:2261-2561) for every unit at once.
+//
+// The D-contractions (x·w_q|w_v EA:1923-1924, o·w_o EA:1995 and their VJPs) are plain dense GEMMs and
+// go to cuBLAS (bf16 operands, fp32 accumulation); everything between them is hand-written CUDA.
+#include <cublas_v2.h>
+#include <stdarg.h>
+#include <stdio.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace lsh {
+
+// ---- error + launch bookkeeping --------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static thread_local int64_t g_launches = 0;
+
+int set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+void count_launch(int n) { g_launches += n; }
+
+// ---- kernels implemented in the other translation units --------------------------------------------
+int hash_bf16_qv(const LshAttnDims &, const void *, const float *, const uint8_t *, int32_t *, int64_t, cudaStream_t);
+int hash_f32_vecs(const LshAttnDims &, const float *, const float *, const uint8_t *, int32_t *, int64_t, cudaStream_t);
+size_t sort_workspace_bytes(const LshAttnDims &);
+int sort_run(const LshAttnDims &, const int32_t *, int64_t, int32_t *, int32_t *, void *, size_t, cudaStream_t);
+int attend_fwd_run(const LshAttnDims &, const void *, const int32_t *, const uint8_t *, void *, int64_t, int64_t,
+                   int64_t, int64_t, float *, cudaStream_t);
+int combine_fwd_run(const LshAttnDims &, const void *, const float *, void *, float *, cudaStream_t);
+size_t attend_bwd_workspace_bytes(const LshAttnDims &);
+int attend_bwd_run(const LshAttnDims &, const void *, const int32_t *, const uint8_t *, const void *, const float *,
+                   const void *, void *, void *, size_t, cudaStream_t);
+int pack_weights_run(const LshAttnDims &, const float *, const float *, const float *, void *, void *, cudaStream_t);
+int f32_to_bf16_run(const float *, void *, int64_t, cudaStream_t);
+int unpack_dwqv_run(const LshAttnDims &, const float *, float *, float *, cudaStream_t);
+int make_rotations_run(const LshAttnDims &, const uint32_t *, uint32_t *, float *, cudaStream_t);
+
+// ---- dims ------------------------------------------------------------------------------------------
+static int check_dims(const LshAttnDims *dp, bool need_bwd) {
+  if (!dp) return set_error("dims == NULL");
+  const LshAttnDims &d = *dp;
+  if (d.B < 1 || d.H < 1 || d.L < 1 || d.D < 1) return set_error("B, H, L, D must be >= 1");
+  if (d.dq != 64 || d.dv != 64)
+    return set_error("unsupported head size d_qk=%d d_v=%d: the sm_100a kernels are specialised for 64/64", d.dq, d.dv);
+  if (d.C != 32 && d.C != 64 && d.C != 128 && d.C != 256)
+    return set_error("unsupported chunk_len=%d (supported: 32, 64, 128, 256)", d.C);
+  if (need_bwd && d.C == 32) return set_error("chunk_len=32 has no backward kernel (supported: 64, 128, 256)");
+  if (d.nb < 0 || d.na < 0 || 1 + d.nb + d.na > 8) return set_error("n_chunks_before/after out of range");
+  if (d.nh < 1 || d.nh > 64) return set_error("n_hashes=%d out of range", d.nh);
+  Derived dr = derive(d);
+  if (dr.N % d.C != 0) return set_error("n_hashes*seqlen=%d not divisible by chunk_len=%d (EA:210)", dr.N, d.C);
+  if (dr.W % 64 != 0) return set_error("window of %d keys must be a multiple of 64", dr.W);
+  if (d.n_factors < 1 || d.n_factors > 4) return set_error("n_factors=%d out of range (1..4)", d.n_factors);
+  for (int i = 0; i < d.n_factors; ++i)
+    if (d.factors[i] < 2 || (d.factors[i] & 1)) return set_error("hash factor %d must be even (EA:80, 87)", d.factors[i]);
+  if (d.D % 8 != 0) return set_error("d_model=%d must be a multiple of 8", d.D);
+  if (d.act_dtype != LSH_DTYPE_F32 && d.act_dtype != LSH_DTYPE_BF16) return set_error("bad act_dtype");
+  // int32 sort key of EA:1947 must not wrap: max key = L*(nh*n_buckets - 1) + L - 1
+  const int64_t maxkey = static_cast<int64_t>(d.L) * d.nh * dr.n_buckets - 1;
+  if (maxkey >= (1ll << 31))
+    return set_error("int32 sort key would wrap: seqlen*n_hashes*n_buckets = %lld >= 2^31 (EA:1947); "
+                     "pass a smaller n_buckets", static_cast<long long>(maxkey + 1));
+  return 0;
+}
+
+// ---- cuBLAS ----------------------------------------------------------------------------------------
+static constexpr size_t kCublasWs = 32ull << 20;
+
+static cublasHandle_t get_handle() {
+  static thread_local cublasHandle_t h = nullptr;
+  static thread_local int dev = -1;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  if (h == nullptr || dev != cur) {
+    if (cublasCreate(&h) != CUBLAS_STATUS_SUCCESS) return nullptr;
+    dev = cur;
+  }
+  return h;
+}
+
+// Row-major C[M,N] = op(A)·op(B); A/B bf16, C bf16 or f32; fp32 accumulation.
+static int gemm_rm(bool ta, bool tb, int64_t M, int64_t N, int64_t K, const void *A, int64_t lda, const void *B,
+                   int64_t ldb, void *C, int64_t ldc, bool c_f32, void *cws, cudaStream_t stream) {
+  cublasHandle_t h = get_handle();
+  if (!h) return set_error("cublasCreate failed");
+  cublasSetStream(h, stream);
+  if (cws) cublasSetWorkspace(h, cws, kCublasWs);
+  const float alpha = 1.f, beta = 0.f;
+  cublasStatus_t st = cublasGemmEx(h, tb ? CUBLAS_OP_T : CUBLAS_OP_N, ta ? CUBLAS_OP_T : CUBLAS_OP_N, (int)N, (int)M,
+                                   (int)K, &alpha, B, CUDA_R_16BF, (int)ldb, A, CUDA_R_16BF, (int)lda, &beta, C,
+                                   c_f32 ? CUDA_R_32F : CUDA_R_16BF, (int)ldc, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT);
+  if (st != CUBLAS_STATUS_SUCCESS) return set_error("cublasGemmEx failed with status %d", (int)st);
+  return 0;
+}
+
+// ---- workspace carving -----------------------------------------------------------------------------
+struct Bump {
+  char *base; size_t off;
+  explicit Bump(void *b) : base(static_cast<char *>(b)), off(0) {}
+  void *take(size_t bytes) {
+    off = (off + 255) / 256 * 256;
+    void *p = base ? base + off : nullptr;
+    off += bytes;
+    return p;
+  }
+};
+
+struct LayerWs {
+  void *cublas, *xb, *wqv, *wo, *qv, *o_rounds, *o_comb, *sort_ws, *doutb, *do_comb, *dqv, *bwd_ws;
+  int32_t *sticker;
+  float *logits, *lse_tot, *dwqv;
+  size_t sort_bytes, bwd_bytes, total;
+};
+
+static LayerWs carve(const LshAttnDims &d, void *ws, bool with_grad) {
+  Derived dr = derive(d);
+  LayerWs w{};
+  Bump b(ws);
+  const size_t BL = static_cast<size_t>(d.B) * d.L, rows = static_cast<size_t>(dr.BH) * dr.N;
+  w.cublas = b.take(kCublasWs);
+  w.xb = d.act_dtype == LSH_DTYPE_F32 ? b.take(BL * d.D * 2) : nullptr;
+  w.wqv = b.take(static_cast<size_t>(d.D) * d.H * dr.QV * 2);
+  w.wo = b.take(static_cast<size_t>(d.H) * d.dv * d.D * 2);
+  w.qv = b.take(BL * d.H * dr.QV * 2);
+  w.sticker = static_cast<int32_t *>(b.take(rows * 4));
+  w.sort_bytes = sort_workspace_bytes(d);
+  w.sort_ws = b.take(w.sort_bytes);
+  w.o_rounds = d.nh > 1 ? b.take(rows * d.dv * 2) : nullptr;
+  w.logits = static_cast<float *>(b.take(rows * 4));
+  w.o_comb = b.take(BL * d.H * d.dv * 2);
+  w.lse_tot = d.nh > 1 ? static_cast<float *>(b.take(static_cast<size_t>(dr.BH) * d.L * 4)) : w.logits;
+  if (with_grad) {
+    w.doutb = d.act_dtype == LSH_DTYPE_F32 ? b.take(BL * d.D * 2) : nullptr;
+    w.do_comb = b.take(BL * d.H * d.dv * 2);
+    w.dqv = b.take(BL * d.H * dr.QV * 2);
+    w.dwqv = static_cast<float *>(b.take(static_cast<size_t>(d.D) * d.H * dr.QV * 4));
+    w.bwd_bytes = attend_bwd_workspace_bytes(d);
+    w.bwd_ws = b.take(w.bwd_bytes);
+  }
+  w.total = b.off + 256;
+  return w;
+}
+
+// Forward up to o_comb (EA:1923-1992 for all units).  Returns xb (bf16 view of x).
+static int forward_core(const LshAttnDims &d, const LayerWs &w, const void *x, const float *w_q, const float *w_v,
+                        const float *w_o, const float *rotations, const uint8_t *mask, int32_t *buckets,
+                        int64_t bstride, bool need_lse_tot, const void **xb_out, cudaStream_t s) {
+  Derived dr = derive(d);
+  const int64_t BL = static_cast<int64_t>(d.B) * d.L;
+  int rc;
+  const void *xb = x;
+  if (d.act_dtype == LSH_DTYPE_F32) {
+    if ((rc = f32_to_bf16_run(static_cast<const float *>(x), w.xb, BL * d.D, s))) return rc;
+    xb = w.xb;
+  }
+  *xb_out = xb;
+  if ((rc = pack_weights_run(d, w_q, w_v, w_o, w.wqv, w.wo, s))) return rc;
+  const int64_t NQV = static_cast<int64_t>(d.H) * dr.QV;
+  if ((rc = gemm_rm(false, false, BL, NQV, d.D, xb, d.D, w.wqv, NQV, w.qv, NQV, false, w.cublas, s))) return rc;
+  if (rotations) {
+    if ((rc = hash_bf16_qv(d, w.qv, rotations, mask, buckets, bstride, s))) return rc;
+  }
+  if ((rc = sort_run(d, buckets, bstride, w.sticker, nullptr, w.sort_ws, w.sort_bytes, s))) return rc;
+  if (d.nh > 1) {
+    if ((rc = attend_fwd_run(d, w.qv, w.sticker, mask, w.o_rounds, static_cast<int64_t>(d.H) * dr.N * 64,
+                             static_cast<int64_t>(dr.N) * 64, static_cast<int64_t>(d.L) * 64, 64, w.logits, s)))
+      return rc;
+    if ((rc = combine_fwd_run(d, w.o_rounds, w.logits, w.o_comb, need_lse_tot ? w.lse_tot : nullptr, s))) return rc;
+  } else {
+    // single round: rows land directly in the (B, L, H, dv) layout, logits == lse_tot
+    if ((rc = attend_fwd_run(d, w.qv, w.sticker, mask, w.o_comb, static_cast<int64_t>(d.L) * d.H * 64, 64, 0,
+                             static_cast<int64_t>(d.H) * 64, w.logits, s)))
+      return rc;
+  }
+  return 0;
+}
+
+}  // namespace lsh
+
+using namespace lsh;
+
+extern "C" {
+
+int lsh_attn_abi_version(void) { return LSH_ATTN_ABI_VERSION; }
+const char *lsh_attn_last_error(void) { return g_err; }
+int64_t lsh_attn_launch_count(int reset) {
+  int64_t v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
+int lsh_attn_check_dims(const LshAttnDims *dims) { return check_dims(dims, false); }
+
+int lsh_pack_weights(const LshAttnDims *dims, const float *w_q, const float *w_v, const float *w_o, void *wqv,
+                     void *wo, void *stream) {
+  if (int rc = check_dims(dims, false)) return rc;
+  return pack_weights_run(*dims, w_q, w_v, w_o, wqv, wo, static_cast<cudaStream_t>(stream));
+}
+
+int lsh_project_qv(const LshAttnDims *dims, const void *x_bf16, const void *wqv, void *qv, void *ws, size_t ws_bytes,
+                   void *stream) {
+  if (int rc = check_dims(dims, false)) return rc;
+  const LshAttnDims &d = *dims;
+  const int64_t BL = static_cast<int64_t>(d.B) * d.L, NQV = static_cast<int64_t>(d.H) * (d.dq + d.dv);
+  return gemm_rm(false, false, BL, NQV, d.D, x_bf16, d.D, wqv, NQV, qv, NQV, false,
+                 ws_bytes >= kCublasWs ? ws : nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int lsh_hash(const LshAttnDims *dims, const void *qv, const float *rotations, const uint8_t *mask, int32_t *buckets,
+             int64_t buckets_stride, void *stream) {
+  if (int rc = check_dims(dims, false)) return rc;
+  return hash_bf16_qv(*dims, qv, rotations, mask, buckets, buckets_stride, static_cast<cudaStream_t>(stream));
+}
+
+int lsh_hash_f32(const LshAttnDims *dims, const float *vecs, const float *rotations, const uint8_t *mask,
+                 int32_t *buckets, int64_t buckets_stride, void *stream) {
+  if (int rc = check_dims(dims, false)) return rc;
+  return hash_f32_vecs(*dims, vecs, rotations, mask, buckets, buckets_stride, static_cast<cudaStream_t>(stream));
+}
+
+size_t lsh_sort_workspace_bytes(const LshAttnDims *dims) { return dims ? sort_workspace_bytes(*dims) : 0; }
+
+int lsh_sort(const LshAttnDims *dims, const int32_t *buckets, int64_t buckets_stride, int32_t *sticker,
+             int32_t *undo_sort, void *ws, size_t ws_bytes, void *stream) {
+  if (int rc = check_dims(dims, false)) return rc;
+  return sort_run(*dims, buckets, buckets_stride, sticker, undo_sort, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int lsh_attend_fwd(const LshAttnDims *dims, const void *qv, const int32_t *sticker, const uint8_t *mask,
+                   void *o_rounds, float *logits, void *stream) {
+  if (int rc = check_dims(dims, false)) return rc;
+  const LshAttnDims &d = *dims;
+  Derived dr = derive(d);
+  return attend_fwd_run(d, qv, sticker, mask, o_rounds, static_cast<int64_t>(d.H) * dr.N * 64,
+                        static_cast<int64_t>(dr.N) * 64, static_cast<int64_t>(d.L) * 64, 64, logits,
+                        static_cast<cudaStream_t>(stream));
+}
+
+int lsh_combine_fwd(const LshAttnDims *dims, const void *o_rounds, const float *logits, void *o_comb, float *lse_tot,
+                    void *stream) {
+  if (int rc = check_dims(dims, false)) return rc;
+  return combine_fwd_run(*dims, o_rounds, logits, o_comb, lse_tot, static_cast<cudaStream_t>(stream));
+}
+
+int lsh_project_out(const LshAttnDims *dims, const void *o_comb, const void *wo, void *out, void *ws, size_t ws_bytes,
+                    void *stream) {
+  if (int rc = check_dims(dims, false)) return rc;
+  const LshAttnDims &d = *dims;
+  const int64_t BL = static_cast<int64_t>(d.B) * d.L, KO = static_cast<int64_t>(d.H) * d.dv;
+  return gemm_rm(false, false, BL, d.D, KO, o_comb, KO, wo, d.D, out, d.D, d.act_dtype == LSH_DTYPE_F32,
+                 ws_bytes >= kCublasWs ? ws : nullptr, static_cast<cudaStream_t>(stream));
+}
+
+size_t lsh_attend_bwd_workspace_bytes(const LshAttnDims *dims) { return dims ? attend_bwd_workspace_bytes(*dims) : 0; }
+
+int lsh_attend_bwd(const LshAttnDims *dims, const void *qv, const int32_t *sticker, const uint8_t *mask,
+                   const void *o_comb, const float *lse_tot, const void *do_comb, void *dqv, void *ws, size_t ws_bytes,
+                   void *stream) {
+  if (int rc = check_dims(dims, true)) return rc;
+  return attend_bwd_run(*dims, qv, sticker, mask, o_comb, lse_tot, do_comb, dqv, ws, ws_bytes,
+                        static_cast<cudaStream_t>(stream));
+}
+
+size_t lsh_layer_workspace_bytes(const LshAttnDims *dims, int with_grad) {
+  if (check_dims(dims, with_grad != 0)) return 0;
+  return carve(*dims, nullptr, with_grad != 0).total;
+}
+
+int lsh_layer_fwd(const LshAttnDims *dims, const void *x, const float *w_q, const float *w_v, const float *w_o,
+                  const float *rotations, const uint8_t *mask, int32_t *buckets, int64_t buckets_stride, void *out,
+                  void *ws, size_t ws_bytes, void *stream) {
+  if (int rc = check_dims(dims, false)) return rc;
+  const LshAttnDims &d = *dims;
+  if (!x || !w_q || !w_v || !w_o || !buckets || !out || !ws) return set_error("lsh_layer_fwd: NULL argument");
+  LayerWs w = carve(d, ws, false);
+  if (ws_bytes < w.total) return set_error("lsh_layer_fwd: workspace too small (%zu < %zu)", ws_bytes, w.total);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const void *xb;
+  if (int rc = forward_core(d, w, x, w_q, w_v, w_o, rotations, mask, buckets, buckets_stride, false, &xb, s)) return rc;
+  const int64_t BL = static_cast<int64_t>(d.B) * d.L, KO = static_cast<int64_t>(d.H) * d.dv;
+  return gemm_rm(false, false, BL, d.D, KO, w.o_comb, KO, w.wo, d.D, out, d.D, d.act_dtype == LSH_DTYPE_F32, w.cublas, s);
+}
+
+int lsh_layer_bwd(const LshAttnDims *dims, const void *x, const float *w_q, const float *w_v, const float *w_o,
+                  const uint8_t *mask, const int32_t *buckets, int64_t buckets_stride, const void *dout, void *out,
+                  void *dx, float *dw_q, float *dw_v, float *dw_o, void *ws, size_t ws_bytes, void *stream) {
+  if (int rc = check_dims(dims, true)) return rc;
+  const LshAttnDims &d = *dims;
+  if (!x || !w_q || !w_v || !w_o || !buckets || !dout || !dx || !dw_q || !dw_v || !dw_o || !ws)
+    return set_error("lsh_layer_bwd: NULL argument");
+  Derived dr = derive(d);
+  LayerWs w = carve(d, ws, true);
+  if (ws_bytes < w.total) return set_error("lsh_layer_bwd: workspace too small (%zu < %zu)", ws_bytes, w.total);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const void *xb;
+  int rc;
+  if ((rc = forward_core(d, w, x, w_q, w_v, w_o, nullptr, mask, const_cast<int32_t *>(buckets), buckets_stride, true,
+                         &xb, s)))
+    return rc;
+  const int64_t BL = static_cast<int64_t>(d.B) * d.L, KO = static_cast<int64_t>(d.H) * d.dv;
+  const int64_t NQV = static_cast<int64_t>(d.H) * dr.QV;
+  const bool f32 = d.act_dtype == LSH_DTYPE_F32;
+  if (out) {
+    if ((rc = gemm_rm(false, false, BL, d.D, KO, w.o_comb, KO, w.wo, d.D, out, d.D, f32, w.cublas, s))) return rc;
+  }
+  const void *doutb = dout;
+  if (f32) {
+    if ((rc = f32_to_bf16_run(static_cast<const float *>(dout), w.doutb, BL * d.D, s))) return rc;
+    doutb = w.doutb;
+  }
+  // B1: do = dout·w_o^T ; dW_o = o^T·dout
+  if ((rc = gemm_rm(false, true, BL, KO, d.D, doutb, d.D, w.wo, d.D, w.do_comb, KO, false, w.cublas, s))) return rc;
+  if ((rc = gemm_rm(true, false, KO, d.D, BL, w.o_comb, KO, doutb, d.D, dw_o, d.D, true, w.cublas, s))) return rc;
+  // B2-B6
+  if ((rc = attend_bwd_run(d, w.qv, w.sticker, mask, w.o_comb, w.lse_tot, w.do_comb, w.dqv, w.bwd_ws, w.bwd_bytes, s)))
+    return rc;
+  // B7: dW_q|dW_v = x^T·dqv ; dx = dqv·wqv^T
+  if ((rc = gemm_rm(true, false, d.D, NQV, BL, xb, d.D, w.dqv, NQV, w.dwqv, NQV, true, w.cublas, s))) return rc;
+  if ((rc = unpack_dwqv_run(d, w.dwqv, dw_q, dw_v, s))) return rc;
+  return gemm_rm(false, true, BL, d.D, NQV, w.dqv, NQV, w.wqv, NQV, dx, d.D, f32, w.cublas, s);
+}
+
+int lsh_make_rotations(const LshAttnDims *dims, const uint32_t *keys, uint32_t *new_keys, float *rotations,
+                       void *stream) {
+  if (int rc = check_dims(dims, false)) return rc;
+  if (keys == new_keys) return set_error("lsh_make_rotations: new_keys must not alias keys");
+  return make_rotations_run(*dims, keys, new_keys, rotations, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,145 @@
+// HBM-bound row kernels around the chunk attention:
+//   combine_fwd : EA:1988-1992  o = sum_r o_r * exp(logit_r - logsumexp_r(logit))      (+ lse_tot)
+//   bwd_prep    : D[u][t] = do[t]·o[t]   (-Delta + dlse collapses to -w_r * (do·o))
+//   sum_rounds  : App. B6: dq[t] = sum over the nh copies (and partial kinds) of each token
+// One 64-wide bf16 row = 128 bytes = 8 lanes x 16 bytes; a warp moves 4 rows per step.
+#include "common.cuh"
+
+namespace lsh {
+
+constexpr int ROW_THREADS = 256;
+
+__device__ __forceinline__ void bf16x8_to_f32(const uint4 &v, float (&f)[8]) {
+  float2 a = unpack_bf16(v.x), b = unpack_bf16(v.y), c = unpack_bf16(v.z), d = unpack_bf16(v.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 f32_to_bf16x8(const float (&f)[8]) {
+  uint4 v;
+  v.x = pack_bf16(f[0], f[1]); v.y = pack_bf16(f[2], f[3]);
+  v.z = pack_bf16(f[4], f[5]); v.w = pack_bf16(f[6], f[7]);
+  return v;
+}
+
+// o_rounds (BH, nh, L, 64) bf16, logits (BH, nh, L) f32 -> o_comb (B, L, H, 64) bf16, lse_tot (BH, L)
+__global__ void __launch_bounds__(ROW_THREADS) combine_fwd_kernel(
+    const __nv_bfloat16 *__restrict__ o_rounds, const float *__restrict__ logits,
+    __nv_bfloat16 *__restrict__ o_comb, float *__restrict__ lse_tot, int L, int H, int nh,
+    int64_t total_rows) {
+  const int64_t row = (static_cast<int64_t>(blockIdx.x) * ROW_THREADS + threadIdx.x) >> 3;   // (u, t)
+  const int ch = threadIdx.x & 7;
+  if (row >= total_rows) return;
+  const int64_t u = row / L;
+  const int t = static_cast<int>(row - u * L);
+  const int64_t b = u / H, h = u % H;
+  const float *lg = logits + u * nh * L + t;
+  float mx = -INFINITY;
+  for (int r = 0; r < nh; ++r) mx = fmaxf(mx, __ldg(lg + static_cast<int64_t>(r) * L));
+  float den = 0.f;
+  for (int r = 0; r < nh; ++r) den += expf(__ldg(lg + static_cast<int64_t>(r) * L) - mx);
+  const float lse = mx + logf(den);                                   // logsumexp over rounds (EA:1991)
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int r = 0; r < nh; ++r) {
+    const float w = expf(__ldg(lg + static_cast<int64_t>(r) * L) - lse);
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(o_rounds + ((u * nh + r) * L + t) * 64) + ch);
+    float f[8];
+    bf16x8_to_f32(v, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = fmaf(w, f[i], acc[i]);
+  }
+  *(reinterpret_cast<uint4 *>(o_comb + ((b * L + t) * H + h) * 64) + ch) = f32_to_bf16x8(acc);
+  if (lse_tot != nullptr && ch == 0) lse_tot[u * L + t] = lse;
+}
+
+int combine_fwd_run(const LshAttnDims &d, const void *o_rounds, const float *logits, void *o_comb,
+                    float *lse_tot, cudaStream_t stream) {
+  Derived dr = derive(d);
+  const int64_t rows = static_cast<int64_t>(dr.BH) * d.L;
+  const int64_t blocks = (rows * 8 + ROW_THREADS - 1) / ROW_THREADS;
+  combine_fwd_kernel<<<static_cast<unsigned>(blocks), ROW_THREADS, 0, stream>>>(
+      static_cast<const __nv_bfloat16 *>(o_rounds), logits, static_cast<__nv_bfloat16 *>(o_comb),
+      lse_tot, d.L, d.H, d.nh, rows);
+  LSH_CHECK_LAUNCH("combine_fwd_kernel");
+  return 0;
+}
+
+// D[u][t] = sum_d do[b,t,h,d] * o[b,t,h,d]; both (B, L, H, 64) bf16
+__global__ void __launch_bounds__(ROW_THREADS) bwd_prep_kernel(
+    const __nv_bfloat16 *__restrict__ do_comb, const __nv_bfloat16 *__restrict__ o_comb,
+    float *__restrict__ dvec, int L, int H, int64_t total_rows) {
+  const int64_t row = (static_cast<int64_t>(blockIdx.x) * ROW_THREADS + threadIdx.x) >> 3;   // (b,t,h)
+  const int ch = threadIdx.x & 7;
+  const bool ok = row < total_rows;
+  float s = 0.f;
+  if (ok) {
+    float a[8], c[8];
+    bf16x8_to_f32(__ldg(reinterpret_cast<const uint4 *>(do_comb + row * 64) + ch), a);
+    bf16x8_to_f32(__ldg(reinterpret_cast<const uint4 *>(o_comb + row * 64) + ch), c);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s = fmaf(a[i], c[i], s);
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  if (ok && ch == 0) {
+    const int64_t h = row % H, bt = row / H;
+    const int64_t b = bt / L, t = bt % L;
+    dvec[(b * H + h) * L + t] = s;
+  }
+}
+
+int bwd_prep_run(const LshAttnDims &d, const void *do_comb, const void *o_comb, float *dvec,
+                 cudaStream_t stream) {
+  Derived dr = derive(d);
+  const int64_t rows = static_cast<int64_t>(dr.BH) * d.L;
+  const int64_t blocks = (rows * 8 + ROW_THREADS - 1) / ROW_THREADS;
+  bwd_prep_kernel<<<static_cast<unsigned>(blocks), ROW_THREADS, 0, stream>>>(
+      static_cast<const __nv_bfloat16 *>(do_comb), static_cast<const __nv_bfloat16 *>(o_comb), dvec,
+      d.L, d.H, rows);
+  LSH_CHECK_LAUNCH("bwd_prep_kernel");
+  return 0;
+}
+
+// dqv[b,t,h,0:64]   = sum_r sum_kind dq_part[kind][u][r*L+t][:]
+// dqv[b,t,h,64:128] = sum_r dv_part[u][r*L+t][:]
+__global__ void __launch_bounds__(ROW_THREADS) sum_rounds_kernel(
+    const __nv_bfloat16 *__restrict__ dq_part, const __nv_bfloat16 *__restrict__ dv_part,
+    __nv_bfloat16 *__restrict__ dqv, int L, int H, int nh, int n_kinds, int64_t kind_stride,
+    int64_t total_rows) {
+  const int64_t row = (static_cast<int64_t>(blockIdx.x) * ROW_THREADS + threadIdx.x) >> 3;   // (u, t)
+  const int ch = threadIdx.x & 7;
+  if (row >= total_rows) return;
+  const int64_t u = row / L;
+  const int t = static_cast<int>(row - u * L);
+  const int64_t b = u / H, h = u % H;
+  float aq[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, av[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int r = 0; r < nh; ++r) {
+    const int64_t off = ((u * nh + r) * L + t) * 64;
+    float f[8];
+    for (int k = 0; k < n_kinds; ++k) {
+      bf16x8_to_f32(__ldg(reinterpret_cast<const uint4 *>(dq_part + k * kind_stride + off) + ch), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) aq[i] += f[i];
+    }
+    bf16x8_to_f32(__ldg(reinterpret_cast<const uint4 *>(dv_part + off) + ch), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) av[i] += f[i];
+  }
+  __nv_bfloat16 *dst = dqv + ((b * L + t) * H + h) * 128;
+  *(reinterpret_cast<uint4 *>(dst) + ch) = f32_to_bf16x8(aq);
+  *(reinterpret_cast<uint4 *>(dst + 64) + ch) = f32_to_bf16x8(av);
+}
+
+int sum_rounds_run(const LshAttnDims &d, const void *dq_part, const void *dv_part, void *dqv,
+                   int n_kinds, cudaStream_t stream) {
+  Derived dr = derive(d);
+  const int64_t rows = static_cast<int64_t>(dr.BH) * d.L;
+  const int64_t blocks = (rows * 8 + ROW_THREADS - 1) / ROW_THREADS;
+  sum_rounds_kernel<<<static_cast<unsigned>(blocks), ROW_THREADS, 0, stream>>>(
+      static_cast<const __nv_bfloat16 *>(dq_part), static_cast<const __nv_bfloat16 *>(dv_part),
+      static_cast<__nv_bfloat16 *>(dqv), d.L, d.H, d.nh, n_kinds,
+      static_cast<int64_t>(dr.BH) * dr.N * 64, rows);
+  LSH_CHECK_LAUNCH("sum_rounds_kernel");
+  return 0;
+}
+
+}  // namespace lsh

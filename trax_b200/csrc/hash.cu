@@ -1,0 +1,172 @@
+// LSH bucket hashing — replaces EA:1889-1916 (hash_vectors) + EA:60-119 (hash_vecs).
+//
+// Contract (bit-exact with oracle/hash_oracle.c): every rotated coordinate is ONE fp32 accumulator,
+// updated with __fmaf_rn over the contraction index f = 0..dq-1 in ascending order, starting from
+// +0.0f.  argmax over concat([rv, -rv]) takes the first maximum.  CUDA-core fp32 work by design:
+// tensor-core (bf16/tf32) products would change bucket ids.
+//
+// One thread owns one token: its dq-vector lives in registers, the rotation columns of one hash
+// round are staged in shared memory and read as warp-wide broadcasts (LDS.128 feeds 4 FFMA/lane).
+#include "common.cuh"
+
+namespace lsh {
+
+constexpr int HASH_THREADS = 128;
+constexpr int HASH_COLS = 8;   // rotation columns processed together per thread
+
+struct HashParams {
+  const void *vecs;        // bf16 or f32
+  int64_t stride_b, stride_h, stride_t;   // element strides of vecs for (example, head, token)
+  const float *rot;        // (BH, dq, nh, R)
+  const uint8_t *mask;     // (B, L) or null
+  int32_t *buckets;
+  int64_t buckets_stride;
+  int L, H, nh, R, Rpad, n_factors, n_buckets;
+  int factors[4];
+};
+
+template <typename T>
+__device__ __forceinline__ void load_vec64(const T *p, float (&q)[64]);
+
+template <>
+__device__ __forceinline__ void load_vec64<float>(const float *p, float (&q)[64]) {
+  const float4 *p4 = reinterpret_cast<const float4 *>(p);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float4 v = __ldg(p4 + i);
+    q[4 * i] = v.x; q[4 * i + 1] = v.y; q[4 * i + 2] = v.z; q[4 * i + 3] = v.w;
+  }
+}
+template <>
+__device__ __forceinline__ void load_vec64<__nv_bfloat16>(const __nv_bfloat16 *p, float (&q)[64]) {
+  const uint4 *p4 = reinterpret_cast<const uint4 *>(p);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    uint4 v = __ldg(p4 + i);
+    float2 a = unpack_bf16(v.x), b = unpack_bf16(v.y), c = unpack_bf16(v.z), d = unpack_bf16(v.w);
+    q[8 * i] = a.x; q[8 * i + 1] = a.y; q[8 * i + 2] = b.x; q[8 * i + 3] = b.y;
+    q[8 * i + 4] = c.x; q[8 * i + 5] = c.y; q[8 * i + 6] = d.x; q[8 * i + 7] = d.y;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(HASH_THREADS) hash_kernel(const HashParams p) {
+  constexpr int DQ = 64;
+  extern __shared__ __align__(16) float s_rot[];   // [DQ][Rpad]
+  const int u = blockIdx.y;
+  const int b = u / p.H, h = u % p.H;
+  const int t = blockIdx.x * HASH_THREADS + threadIdx.x;
+  const bool active = t < p.L;
+
+  float q[DQ];
+  if (active) {
+    const T *src = reinterpret_cast<const T *>(p.vecs) + b * p.stride_b + h * p.stride_h +
+                   static_cast<int64_t>(t) * p.stride_t;
+    load_vec64<T>(src, q);
+  } else {
+#pragma unroll
+    for (int i = 0; i < DQ; ++i) q[i] = 0.f;
+  }
+  bool valid_tok = true;
+  if (p.mask != nullptr && active) valid_tok = p.mask[static_cast<int64_t>(b) * p.L + t] != 0;
+
+  const float *rot_u = p.rot + static_cast<int64_t>(u) * DQ * p.nh * p.R;
+  for (int round = 0; round < p.nh; ++round) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < DQ * p.Rpad; i += HASH_THREADS) {
+      int f = i / p.Rpad, c = i % p.Rpad;
+      s_rot[i] = (c < p.R) ? __ldg(rot_u + (static_cast<int64_t>(f) * p.nh + round) * p.R + c) : 0.f;
+    }
+    __syncthreads();
+
+    // argmax state machine over the factor list
+    int fi = 0, pos = 0, half = p.factors[0] >> 1;
+    float best_pos = -INFINITY, best_neg = INFINITY;   // max of rv, min of rv
+    int idx_pos = 0, idx_neg = 0;
+    int bucket = 0, prod = 1;
+    for (int c0 = 0; c0 < p.Rpad; c0 += HASH_COLS) {
+      float acc[HASH_COLS];
+#pragma unroll
+      for (int j = 0; j < HASH_COLS; ++j) acc[j] = 0.f;
+      const float *sr = s_rot + c0;
+#pragma unroll
+      for (int f = 0; f < DQ; ++f) {
+        const float4 r0 = *reinterpret_cast<const float4 *>(sr + f * p.Rpad);
+        const float4 r1 = *reinterpret_cast<const float4 *>(sr + f * p.Rpad + 4);
+        acc[0] = __fmaf_rn(q[f], r0.x, acc[0]);
+        acc[1] = __fmaf_rn(q[f], r0.y, acc[1]);
+        acc[2] = __fmaf_rn(q[f], r0.z, acc[2]);
+        acc[3] = __fmaf_rn(q[f], r0.w, acc[3]);
+        acc[4] = __fmaf_rn(q[f], r1.x, acc[4]);
+        acc[5] = __fmaf_rn(q[f], r1.y, acc[5]);
+        acc[6] = __fmaf_rn(q[f], r1.z, acc[6]);
+        acc[7] = __fmaf_rn(q[f], r1.w, acc[7]);
+      }
+#pragma unroll
+      for (int j = 0; j < HASH_COLS; ++j) {
+        if (c0 + j < p.R) {
+          const float x = acc[j];
+          if (x > best_pos) { best_pos = x; idx_pos = pos; }
+          if (x < best_neg) { best_neg = x; idx_neg = pos; }
+          ++pos;
+          if (pos == half) {
+            // concat([rv, -rv]): the +half wins ties (lower index), EA:104-105 / 112-116
+            const int am = (best_pos >= -best_neg) ? idx_pos : half + idx_neg;
+            bucket += prod * am;
+            prod *= p.factors[fi];
+            ++fi;
+            half = (fi < p.n_factors) ? (p.factors[fi] >> 1) : 0x7fffffff;
+            pos = 0; best_pos = -INFINITY; best_neg = INFINITY; idx_pos = 0; idx_neg = 0;
+          }
+        }
+      }
+    }
+    if (active) {
+      if (!valid_tok) bucket = p.n_buckets - 1;                      // EA:1908-1909
+      p.buckets[static_cast<int64_t>(u) * p.buckets_stride + static_cast<int64_t>(round) * p.L + t] =
+          bucket + round * p.n_buckets;                              // EA:1913-1915
+    }
+  }
+}
+
+template <typename T>
+static int launch_hash(const LshAttnDims &d, const void *vecs, int64_t sb, int64_t sh, int64_t st,
+                       const float *rot, const uint8_t *mask, int32_t *buckets, int64_t bstride,
+                       cudaStream_t stream) {
+  Derived dr = derive(d);
+  HashParams p;
+  p.vecs = vecs; p.stride_b = sb; p.stride_h = sh; p.stride_t = st;
+  p.rot = rot; p.mask = d.masked ? mask : nullptr; p.buckets = buckets; p.buckets_stride = bstride;
+  p.L = d.L; p.H = d.H; p.nh = d.nh; p.R = dr.R; p.Rpad = (dr.R + HASH_COLS - 1) / HASH_COLS * HASH_COLS;
+  p.n_factors = d.n_factors; p.n_buckets = dr.n_buckets;
+  for (int i = 0; i < 4; ++i) p.factors[i] = i < d.n_factors ? d.factors[i] : 2;
+  size_t smem = static_cast<size_t>(64) * p.Rpad * sizeof(float);
+  if (smem > 200 * 1024) return set_error("lsh_hash: sum(factors)/2 = %d too large for shared memory", dr.R);
+  if (d.masked && mask == nullptr) return set_error("lsh_hash: dims.masked set but mask == NULL");
+  static thread_local size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaFuncSetAttribute(hash_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  dim3 grid((d.L + HASH_THREADS - 1) / HASH_THREADS, dr.BH);
+  hash_kernel<T><<<grid, HASH_THREADS, smem, stream>>>(p);
+  LSH_CHECK_LAUNCH("hash_kernel");
+  return 0;
+}
+
+int hash_bf16_qv(const LshAttnDims &d, const void *qv, const float *rot, const uint8_t *mask,
+                 int32_t *buckets, int64_t bstride, cudaStream_t stream) {
+  Derived dr = derive(d);
+  return launch_hash<__nv_bfloat16>(d, qv, static_cast<int64_t>(d.L) * d.H * dr.QV, dr.QV,
+                                    static_cast<int64_t>(d.H) * dr.QV, rot, mask, buckets, bstride,
+                                    stream);
+}
+
+int hash_f32_vecs(const LshAttnDims &d, const float *vecs, const float *rot, const uint8_t *mask,
+                  int32_t *buckets, int64_t bstride, cudaStream_t stream) {
+  return launch_hash<float>(d, vecs, static_cast<int64_t>(d.H) * d.L * d.dq,
+                            static_cast<int64_t>(d.L) * d.dq, d.dq, rot, mask, buckets, bstride,
+                            stream);
+}
+
+}  // namespace lsh

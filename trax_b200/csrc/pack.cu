@@ -1,0 +1,138 @@
+// Layout / dtype plumbing around the projection GEMMs (EA:1923-1924, 1995 and their VJPs).
+#include "common.cuh"
+
+namespace lsh {
+
+// w_q (H, D, dq) f32, w_v (H, D, dv) f32 -> wqv (D, H, dq+dv) bf16 ; w_o (H, dv, D) f32 -> bf16 same layout
+__global__ void pack_wqv_kernel(const float *__restrict__ w_q, const float *__restrict__ w_v,
+                                __nv_bfloat16 *__restrict__ wqv, int H, int D, int dq, int dv) {
+  const int QV = dq + dv;
+  const int64_t n = static_cast<int64_t>(D) * H * QV;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % QV);
+    const int h = static_cast<int>((i / QV) % H);
+    const int dm = static_cast<int>(i / (static_cast<int64_t>(QV) * H));
+    const float v = (c < dq) ? w_q[(static_cast<int64_t>(h) * D + dm) * dq + c]
+                             : w_v[(static_cast<int64_t>(h) * D + dm) * dv + (c - dq)];
+    wqv[i] = __float2bfloat16_rn(v);
+  }
+}
+
+__global__ void f32_to_bf16_kernel(const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst, int64_t n) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int64_t n4 = n >> 2;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(src) + i);
+    uint2 o;
+    o.x = pack_bf16(v.x, v.y); o.y = pack_bf16(v.z, v.w);
+    reinterpret_cast<uint2 *>(dst)[i] = o;
+  }
+  for (int64_t i = (n4 << 2) + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+// dwqv (D, H, dq+dv) f32 -> dw_q (H, D, dq), dw_v (H, D, dv) f32
+__global__ void unpack_dwqv_kernel(const float *__restrict__ dwqv, float *__restrict__ dw_q,
+                                   float *__restrict__ dw_v, int H, int D, int dq, int dv) {
+  const int QV = dq + dv;
+  const int64_t n = static_cast<int64_t>(D) * H * QV;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % QV);
+    const int h = static_cast<int>((i / QV) % H);
+    const int dm = static_cast<int>(i / (static_cast<int64_t>(QV) * H));
+    if (c < dq) dw_q[(static_cast<int64_t>(h) * D + dm) * dq + c] = dwqv[i];
+    else dw_v[(static_cast<int64_t>(h) * D + dm) * dv + (c - dq)] = dwqv[i];
+  }
+}
+
+static unsigned grid_for(int64_t n, int threads) {
+  int64_t b = (n + threads - 1) / threads;
+  if (b > 148 * 16) b = 148 * 16;
+  if (b < 1) b = 1;
+  return static_cast<unsigned>(b);
+}
+
+int pack_weights_run(const LshAttnDims &d, const float *w_q, const float *w_v, const float *w_o,
+                     void *wqv, void *wo, cudaStream_t stream) {
+  const int64_t n = static_cast<int64_t>(d.D) * d.H * (d.dq + d.dv);
+  pack_wqv_kernel<<<grid_for(n, 256), 256, 0, stream>>>(w_q, w_v, static_cast<__nv_bfloat16 *>(wqv), d.H,
+                                                        d.D, d.dq, d.dv);
+  LSH_CHECK_LAUNCH("pack_wqv_kernel");
+  const int64_t no = static_cast<int64_t>(d.H) * d.dv * d.D;
+  f32_to_bf16_kernel<<<grid_for(no / 4 + 1, 256), 256, 0, stream>>>(w_o, static_cast<__nv_bfloat16 *>(wo), no);
+  LSH_CHECK_LAUNCH("f32_to_bf16_kernel");
+  return 0;
+}
+
+int f32_to_bf16_run(const float *src, void *dst, int64_t n, cudaStream_t stream) {
+  f32_to_bf16_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, stream>>>(src, static_cast<__nv_bfloat16 *>(dst), n);
+  LSH_CHECK_LAUNCH("f32_to_bf16_kernel");
+  return 0;
+}
+
+int unpack_dwqv_run(const LshAttnDims &d, const float *dwqv, float *dw_q, float *dw_v, cudaStream_t stream) {
+  const int64_t n = static_cast<int64_t>(d.D) * d.H * (d.dq + d.dv);
+  unpack_dwqv_kernel<<<grid_for(n, 256), 256, 0, stream>>>(dwqv, dw_q, dw_v, d.H, d.D, d.dq, d.dv);
+  LSH_CHECK_LAUNCH("unpack_dwqv_kernel");
+  return 0;
+}
+
+// ---- rotations: counter-based N(0,1) (stands in for jax.random.normal at EA:92) ---------------------
+__device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+
+// Threefry-2x32, 20 rounds (Salmon et al. 2011), the generator family JAX uses; bit-compatibility with
+// jax.random is NOT claimed (not verifiable offline).
+__device__ __forceinline__ void threefry2x32(uint32_t k0, uint32_t k1, uint32_t &x0, uint32_t &x1) {
+  const uint32_t ks[3] = {k0, k1, 0x1BD11BDAu ^ k0 ^ k1};
+  const int rot[8] = {13, 15, 26, 6, 17, 29, 16, 24};
+  x0 += ks[0]; x1 += ks[1];
+#pragma unroll
+  for (int r = 0; r < 5; ++r) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      x0 += x1; x1 = rotl32(x1, rot[(r & 1) * 4 + i]); x1 ^= x0;
+    }
+    x0 += ks[(r + 1) % 3]; x1 += ks[(r + 2) % 3] + static_cast<uint32_t>(r + 1);
+  }
+}
+
+__global__ void make_rotations_kernel(const uint32_t *__restrict__ keys, uint32_t *__restrict__ new_keys,
+                                      float *__restrict__ rot, int per_unit) {
+  const int u = blockIdx.y;
+  const uint32_t k0 = keys[2 * u], k1 = keys[2 * u + 1];
+  // split (EA:1928): child 0 = next state key, child 1 = key for this draw
+  uint32_t a0 = 0, a1 = 0, b0 = 0, b1 = 1;
+  threefry2x32(k0, k1, a0, a1);
+  threefry2x32(k0, k1, b0, b1);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // pair index
+  if (2 * i < per_unit) {
+    uint32_t x0 = static_cast<uint32_t>(i), x1 = 0x9E3779B9u;
+    threefry2x32(b0, b1, x0, x1);
+    // Box-Muller on two uniforms in (0,1]
+    const float u1 = (static_cast<float>(x0 >> 8) + 1.0f) * (1.0f / 16777216.0f);
+    const float u2 = static_cast<float>(x1 >> 8) * (1.0f / 16777216.0f);
+    const float rad = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincospif(2.0f * u2, &sn, &cs);
+    float *dst = rot + static_cast<int64_t>(u) * per_unit;
+    dst[2 * i] = rad * cs;
+    if (2 * i + 1 < per_unit) dst[2 * i + 1] = rad * sn;
+  }
+  if (new_keys != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+    new_keys[2 * u] = a0; new_keys[2 * u + 1] = a1;
+  }
+}
+
+int make_rotations_run(const LshAttnDims &d, const uint32_t *keys, uint32_t *new_keys, float *rot,
+                       cudaStream_t stream) {
+  Derived dr = derive(d);
+  const int per_unit = d.dq * d.nh * dr.R;
+  dim3 grid((per_unit / 2 + 1 + 127) / 128, dr.BH);
+  make_rotations_kernel<<<grid, 128, 0, stream>>>(keys, new_keys, rot, per_unit);
+  LSH_CHECK_LAUNCH("make_rotations_kernel");
+  return 0;
+}
+
+}  // namespace lsh

@@ -1,0 +1,213 @@
+// Stable bucket sort — replaces the two `sort_key_val` calls of EA:1946-1956.
+//
+// The reference sorts the int32 key  seqlen*bucket + position.  Bucket ids carry a per-round offset
+// (EA:1913-1915), so hash round r owns sorted slots [r*L, (r+1)*L) and, inside a round, the order is
+// "by bucket, then by position" = a STABLE sort of positions 0..L-1 by (bucket - r*n_buckets).  The
+// permutation is unique (keys are unique as long as the int32 key does not wrap, which
+// lsh_attn_check_dims enforces), so a stable counting sort reproduces jnp.argsort bit for bit.
+//
+// Each (unit, round) segment is an LSD radix sort with <= 11-bit digits (one pass when
+// n_buckets <= 2048):   histogram per tile  ->  exclusive scan over (digit, tile)  ->  stable scatter
+// (per-warp digit counters in shared memory + __match_any_sync ranks).  sticker[slot] = ticker of the
+// element in that slot; undo_sort = inverse permutation (EA:1953).
+#include "common.cuh"
+
+namespace lsh {
+
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int SORT_TILE = 2048;                       // positions per CTA
+constexpr int SORT_PER_WARP = SORT_TILE / SORT_WARPS; // contiguous positions per warp
+constexpr int SORT_MAX_BITS = 11;
+
+struct SortParams {
+  const int32_t *buckets; int64_t buckets_stride;
+  const int32_t *perm_in;   // (BH, N) ticker values, or null = identity (first pass)
+  int32_t *perm_out;        // (BH, N)
+  int32_t *undo;            // (BH, N) or null; written on the last pass only
+  int32_t *hist;            // (n_seg, n_digits, n_tiles)
+  int L, nh, N, n_buckets, n_tiles, shift, n_digits, last_pass;
+};
+
+__device__ __forceinline__ int sort_digit(const SortParams &p, int u, int round, int idx, int &pos) {
+  // idx: index inside the segment in the CURRENT order
+  if (p.perm_in) pos = p.perm_in[static_cast<int64_t>(u) * p.N + round * p.L + idx] - round * p.L;
+  else pos = idx;
+  int b = p.buckets[static_cast<int64_t>(u) * p.buckets_stride + static_cast<int64_t>(round) * p.L + pos] -
+          round * p.n_buckets;
+  b = min(max(b, 0), p.n_buckets - 1);   // a corrupt state must not index outside shared memory
+  return (b >> p.shift) & (p.n_digits - 1);
+}
+
+__global__ void __launch_bounds__(SORT_THREADS) sort_hist_kernel(const SortParams p) {
+  extern __shared__ int s_hist[];   // [n_digits]
+  const int tile = blockIdx.x, seg = blockIdx.y;
+  const int u = seg / p.nh, round = seg % p.nh;
+  for (int i = threadIdx.x; i < p.n_digits; i += SORT_THREADS) s_hist[i] = 0;
+  __syncthreads();
+  const int base = tile * SORT_TILE;
+  for (int i = threadIdx.x; i < SORT_TILE; i += SORT_THREADS) {
+    int idx = base + i;
+    if (idx < p.L) {
+      int pos;
+      int dgt = sort_digit(p, u, round, idx, pos);
+      atomicAdd(&s_hist[dgt], 1);
+    }
+  }
+  __syncthreads();
+  int32_t *out = p.hist + static_cast<int64_t>(seg) * p.n_digits * p.n_tiles;
+  for (int i = threadIdx.x; i < p.n_digits; i += SORT_THREADS)
+    out[static_cast<int64_t>(i) * p.n_tiles + tile] = s_hist[i];
+}
+
+// Exclusive scan of one segment's (digit-major, tile-minor) histogram, in place.
+__global__ void __launch_bounds__(1024) sort_scan_kernel(int32_t *hist, int entries) {
+  __shared__ int s_warp[32];
+  int32_t *h = hist + static_cast<int64_t>(blockIdx.x) * entries;
+  const int per = (entries + 1023) / 1024;
+  const int lo = threadIdx.x * per, hi = min(lo + per, entries);
+  int sum = 0;
+  for (int i = lo; i < hi; ++i) sum += h[i];
+  // block exclusive scan of `sum`
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = s_warp[lane];
+    int wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int v = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += v;
+    }
+    s_warp[lane] = wi - w;   // exclusive
+  }
+  __syncthreads();
+  int run = s_warp[warp] + incl - sum;
+  for (int i = lo; i < hi; ++i) {
+    int v = h[i];
+    h[i] = run;
+    run += v;
+  }
+}
+
+__global__ void __launch_bounds__(SORT_THREADS) sort_scatter_kernel(const SortParams p) {
+  extern __shared__ int s_cnt[];   // [SORT_WARPS][n_digits]
+  const int tile = blockIdx.x, seg = blockIdx.y;
+  const int u = seg / p.nh, round = seg % p.nh;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < SORT_WARPS * p.n_digits; i += SORT_THREADS) s_cnt[i] = 0;
+  __syncthreads();
+  int *my_cnt = s_cnt + warp * p.n_digits;
+  const int wbase = tile * SORT_TILE + warp * SORT_PER_WARP;
+  // phase A: per-warp digit counts
+  for (int i = lane; i < SORT_PER_WARP; i += 32) {
+    int idx = wbase + i;
+    if (idx < p.L) {
+      int pos;
+      atomicAdd(&my_cnt[sort_digit(p, u, round, idx, pos)], 1);
+    }
+  }
+  __syncthreads();
+  // phase B: counts -> starting offsets (tile base from the scanned histogram, then warps in order)
+  const int32_t *hs = p.hist + static_cast<int64_t>(seg) * p.n_digits * p.n_tiles;
+  for (int dgt = threadIdx.x; dgt < p.n_digits; dgt += SORT_THREADS) {
+    int run = hs[static_cast<int64_t>(dgt) * p.n_tiles + tile];
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; ++w) {
+      int c = s_cnt[w * p.n_digits + dgt];
+      s_cnt[w * p.n_digits + dgt] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+  // phase C: stable scatter, 32 elements of the warp's range at a time, in order
+  const int64_t row = static_cast<int64_t>(u) * p.N + static_cast<int64_t>(round) * p.L;
+  for (int i0 = 0; i0 < SORT_PER_WARP; i0 += 32) {
+    const int idx = wbase + i0 + lane;
+    const bool valid = idx < p.L;
+    int pos = 0;
+    unsigned dgt = valid ? static_cast<unsigned>(sort_digit(p, u, round, idx, pos)) : 0xffffffffu;
+    const unsigned peers = __match_any_sync(0xffffffffu, dgt);
+    const int rank = __popc(peers & ((1u << lane) - 1u));
+    int off = 0;
+    if (valid) off = my_cnt[dgt];
+    __syncwarp();
+    if (valid && rank == 0) my_cnt[dgt] = off + __popc(peers);
+    __syncwarp();
+    if (valid) {
+      const int dst = off + rank;                       // slot inside the round
+      p.perm_out[row + dst] = round * p.L + pos;        // ticker value (EA:1946)
+      if (p.last_pass && p.undo) p.undo[row + pos] = round * p.L + dst;
+    }
+  }
+}
+
+static int ceil_log2(int x) { int b = 0; while ((1 << b) < x) ++b; return b; }
+
+struct SortPlan { int passes, bits, n_digits, n_tiles; size_t hist_bytes, perm_bytes; };
+
+static SortPlan plan_sort(const LshAttnDims &d) {
+  Derived dr = derive(d);
+  SortPlan s;
+  int total_bits = ceil_log2(dr.n_buckets);
+  if (total_bits < 1) total_bits = 1;
+  s.passes = (total_bits + SORT_MAX_BITS - 1) / SORT_MAX_BITS;
+  s.bits = (total_bits + s.passes - 1) / s.passes;
+  s.n_digits = 1 << s.bits;
+  s.n_tiles = (d.L + SORT_TILE - 1) / SORT_TILE;
+  s.hist_bytes = static_cast<size_t>(dr.BH) * d.nh * s.n_digits * s.n_tiles * sizeof(int32_t);
+  s.hist_bytes = (s.hist_bytes + 255) / 256 * 256;
+  s.perm_bytes = s.passes > 1 ? static_cast<size_t>(dr.BH) * dr.N * sizeof(int32_t) : 0;
+  s.perm_bytes = (s.perm_bytes + 255) / 256 * 256;
+  return s;
+}
+
+size_t sort_workspace_bytes(const LshAttnDims &d) {
+  SortPlan s = plan_sort(d);
+  return s.hist_bytes + s.perm_bytes;
+}
+
+int sort_run(const LshAttnDims &d, const int32_t *buckets, int64_t bstride, int32_t *sticker,
+             int32_t *undo, void *ws, size_t ws_bytes, cudaStream_t stream) {
+  Derived dr = derive(d);
+  SortPlan s = plan_sort(d);
+  if (ws_bytes < s.hist_bytes + s.perm_bytes)
+    return set_error("lsh_sort: workspace too small (%zu < %zu)", ws_bytes, s.hist_bytes + s.perm_bytes);
+  int32_t *hist = static_cast<int32_t *>(ws);
+  int32_t *tmp = reinterpret_cast<int32_t *>(static_cast<char *>(ws) + s.hist_bytes);
+  size_t smem_sc = static_cast<size_t>(SORT_WARPS) * s.n_digits * sizeof(int);
+  static thread_local bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(sort_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         SORT_WARPS * (1 << SORT_MAX_BITS) * (int)sizeof(int));
+    configured = true;
+  }
+  // ping-pong so that the last pass lands in `sticker`
+  const int32_t *in = nullptr;
+  for (int pass = 0; pass < s.passes; ++pass) {
+    const bool last = pass == s.passes - 1;
+    int32_t *out = ((s.passes - 1 - pass) % 2 == 0) ? sticker : tmp;
+    SortParams p;
+    p.buckets = buckets; p.buckets_stride = bstride; p.perm_in = in; p.perm_out = out;
+    p.undo = undo; p.hist = hist; p.L = d.L; p.nh = d.nh; p.N = dr.N; p.n_buckets = dr.n_buckets;
+    p.n_tiles = s.n_tiles; p.shift = pass * s.bits; p.n_digits = s.n_digits; p.last_pass = last;
+    dim3 grid(s.n_tiles, dr.BH * d.nh);
+    sort_hist_kernel<<<grid, SORT_THREADS, s.n_digits * sizeof(int), stream>>>(p);
+    LSH_CHECK_LAUNCH("sort_hist_kernel");
+    sort_scan_kernel<<<dr.BH * d.nh, 1024, 0, stream>>>(hist, s.n_digits * s.n_tiles);
+    LSH_CHECK_LAUNCH("sort_scan_kernel");
+    sort_scatter_kernel<<<grid, SORT_THREADS, smem_sc, stream>>>(p);
+    LSH_CHECK_LAUNCH("sort_scatter_kernel");
+    in = out;
+  }
+  return 0;
+}
+
+}  // namespace lsh

@@ -1,0 +1,379 @@
+"""`LSHSelfAttention` — drop-in for `trax.layers.research.efficient_attention.LSHSelfAttention`
+(EA:1729-2561) on the train path, hosted on torch tensors, computed by hand-written sm_100a CUDA
+through the C ABI in include/lsh_attn.h.
+
+Kept from the reference (names, argument meaning, error behaviour):
+  * the 21 constructor keywords (EA:1732-1748); `share_qk` is forced on (EA:1782); dropouts are
+    zeroed unless mode == 'train' (EA:1790-1795); `n_in = 2 if masked else 1` (EA:1750).
+  * `weights = (w_q (H,D,dq), w_v (H,D,dv), w_o (H,dv,D))` fp32 (EA:1845-1868, stacked EA:1829-1830).
+  * `state = (buckets int32 (B*H, nh*max(L, max_length_for_buckets)), rng uint32 (B*H, 2))`
+    (EA:1870-1887, stacked EA:1831).
+  * `init`, `init_weights_and_state`, `forward`, `has_backward`, `backward`,
+    `forward_and_or_backward`, `pure_fn`, `__call__` with the semantics of `trax/layers/base.py:265`,
+    `:541`, `:644` and EA:2111-2126, 2246-2561; only `weights`, `state`, `rng` are settable public
+    attributes (base.py:675-706).
+Not provided (raise, never silently differ): mode='predict' (EA:1999-2109, out of scope for this
+tier), `use_reference_code=True` (would be a CPU path), `bias=True` (broken in the reference too:
+EA:1921 unpacks exactly three weights), dropout rates > 0 (keep-masks need jax.random's bits).
+
+torch plays the role JAX plays for the reference: device memory, streams, autograd glue
+(`torch.autograd.Function` ≙ `fastmath.custom_vjp` in base.py:644-673).
+"""
+import ctypes
+from typing import NamedTuple
+
+import numpy as np
+import torch
+
+from trax_b200 import _lib
+from trax_b200 import ops
+
+
+class ShapeDtype(NamedTuple):
+  """Stand-in for `trax.shapes.ShapeDtype` (shapes.py:23): what `init` receives."""
+  shape: tuple
+  dtype: object = torch.float32
+
+
+def _to_int32_bits(rng):
+  """uint32 key material → int32 tensor with the same bits (torch has no general uint32 kernels)."""
+  if isinstance(rng, torch.Tensor):
+    if rng.dtype == torch.int32:
+      return rng
+    if hasattr(torch, 'uint32') and rng.dtype == torch.uint32:
+      return rng.view(torch.int32)
+    rng = rng.cpu().numpy()
+  arr = np.asarray(rng).astype(np.uint32)
+  return torch.from_numpy(arr.view(np.int32).copy())
+
+
+def _split_host(key, n):
+  """Host-side key derivation used at init time only (EA:1819, 1824 call fastmath.random.split).
+
+  Not threefry-compatible with JAX (documented): a NumPy Philox stream keyed by the parent key.
+  """
+  key = np.asarray(key, dtype=np.uint32).reshape(-1)[:2]
+  gen = np.random.Generator(np.random.Philox(key=int(key[0]) << 32 | int(key[1])))
+  return gen.integers(0, 2 ** 32, size=(n, 2), dtype=np.uint64).astype(np.uint32)
+
+
+class LSHSelfAttention:
+  """LSH self-attention (see module docstring)."""
+
+  def __init__(self,
+               n_heads=2, d_qk=64, d_v=64, share_qk='unused',
+               causal=False,
+               masked=False,
+               chunk_len=128, n_chunks_before=1, n_chunks_after=0,
+               n_hashes=1,
+               n_buckets=None,
+               mode='train',
+               predict_mem_len=2048, predict_drop_len=256,
+               attention_dropout=0.0,
+               output_dropout=0.0,
+               max_length_for_buckets=None,
+               bias=False,
+               n_parallel_heads=1,
+               use_python_loop=False,
+               use_reference_code=False,
+              ):
+    del share_qk, predict_mem_len, predict_drop_len
+    self._n_in = 2 if masked else 1                                 # EA:1750
+    self._n_out = 1
+    self._n_heads = n_heads
+    if n_parallel_heads:                                            # EA:1753-1760
+      if ((n_parallel_heads > n_heads and n_parallel_heads % n_heads != 0)
+          or (n_parallel_heads < n_heads and n_heads % n_parallel_heads != 0)):
+        raise ValueError('n_parallel_heads must be a multiple or fraction of n_heads')
+    # All units run in one batched launch; n_parallel_heads / use_python_loop only shaped the
+    # reference's memory use (EA:2297-2321) and do not change results.
+    self._n_parallel_heads = n_parallel_heads or None
+    self._use_python_loop = use_python_loop
+    if mode == 'predict':
+      raise NotImplementedError(
+          "LSHSelfAttention(mode='predict') (EA:1999-2109, 2174-2244) is outside this build's scope")
+    if use_reference_code:
+      raise NotImplementedError('use_reference_code=True is a CPU loop in the reference; this build has no CPU path')
+    if bias:
+      raise NotImplementedError('bias=True is not supported (the reference unpacks 3 weights, EA:1921)')
+    self._d_qk, self._d_v = d_qk, d_v
+    self._share_qk = True                                           # EA:1782
+    self._causal, self._masked = causal, masked
+    self._chunk_len = chunk_len
+    self._n_chunks_before, self._n_chunks_after = n_chunks_before, n_chunks_after
+    self._bias = bias
+    self._mode = mode
+    if mode == 'train':                                             # EA:1790-1795
+      self._attention_dropout, self._output_dropout = attention_dropout, output_dropout
+    else:
+      self._attention_dropout = self._output_dropout = 0.0
+    if self._attention_dropout or self._output_dropout:
+      raise NotImplementedError(
+          'attention_dropout/output_dropout > 0 need jax.random keep-masks (EA:254-262, 271-280); not supported')
+    self._n_hashes = n_hashes
+    self._n_buckets = n_buckets
+    self._max_length_for_buckets = max_length_for_buckets
+    self._weights = ()
+    self._state = ()
+    self._rng = None
+    self._rotations_override = None     # tests / a JAX host inject explicit rotations here
+
+  # ---- attribute discipline (base.py:675-706) -----------------------------------------------------
+  def __setattr__(self, attr, value):
+    if attr[0] != '_' and attr not in ('weights', 'state', 'rng'):
+      raise ValueError("Trax layers only allow to set ('weights', 'state', 'rng') as public "
+                       f'attribues, not {attr}.')
+    super().__setattr__(attr, value)
+
+  @property
+  def n_in(self):
+    return self._n_in
+
+  @property
+  def n_out(self):
+    return self._n_out
+
+  @property
+  def weights(self):
+    return self._weights
+
+  @weights.setter
+  def weights(self, w):
+    self._weights = tuple(w) if isinstance(w, (list, tuple)) else w
+
+  @property
+  def state(self):
+    return self._state
+
+  @state.setter
+  def state(self, s):
+    self._state = tuple(s) if isinstance(s, (list, tuple)) else s
+
+  @property
+  def rng(self):
+    if self._rng is None:
+      self._rng = np.array([0, 0], dtype=np.uint32)                 # base.py: default key from seed 0
+    return self._rng
+
+  @rng.setter
+  def rng(self, rng):
+    self._rng = rng
+
+  @property
+  def has_backward(self):                                           # EA:2246-2249
+    return True
+
+  # ---- init (base.py:265-311, EA:1810-1887) -------------------------------------------------------
+  def init(self, input_signature, rng=None, use_cache=False):
+    del use_cache
+    if rng is not None:
+      self.rng = rng
+    self.init_weights_and_state(input_signature)
+    return self.weights, self.state
+
+  def _kernel_initializer(self, shape, gen):                        # EA:1801-1808
+    lim = np.sqrt(6.0 / (shape[0] + shape[1] * self._n_heads))
+    return gen.uniform(-lim, lim, size=shape).astype(np.float32)
+
+  def init_weights_and_state(self, input_signature, device=None):
+    if not isinstance(input_signature, (tuple, list)) or isinstance(input_signature, ShapeDtype):
+      input_signature = (input_signature,)
+    shape = tuple(input_signature[0].shape)
+    batch_size, seqlen, d_model = int(shape[0]), int(shape[1]), int(shape[2])
+    device = device or ('cuda' if torch.cuda.is_available() else 'cpu')
+    w_q, w_v, w_o = [], [], []
+    weight_rngs = _split_host(self.rng, self._n_heads)              # EA:1819
+    for i in range(self._n_heads):                                  # EA:1845-1868
+      g = np.random.Generator(np.random.Philox(key=int(weight_rngs[i][0]) << 32 | int(weight_rngs[i][1])))
+      w_q.append(self._kernel_initializer((d_model, self._d_qk), g))
+      w_v.append(self._kernel_initializer((d_model, self._d_v), g))
+      w_o.append(np.transpose(self._kernel_initializer((d_model, self._d_v), g)))
+    state_rngs = _split_host(self.rng, self._n_heads * batch_size)  # EA:1824
+    length = self._max_length_for_buckets or seqlen                 # EA:1880
+    buckets = torch.zeros((self._n_heads * batch_size, self._n_hashes * length), dtype=torch.int32,
+                          device=device)                            # EA:1881
+    rng_state = _to_int32_bits(state_rngs).to(device)
+    if hasattr(torch, 'uint32'):
+      rng_state = rng_state.view(torch.uint32)
+    self.weights = tuple(torch.from_numpy(np.ascontiguousarray(np.stack(w))).to(device) for w in (w_q, w_v, w_o))
+    self.state = (buckets, rng_state)
+
+  # ---- forward / backward (EA:2111-2126, 2251-2259) ------------------------------------------------
+  def forward(self, inputs):
+    weights, state, rng = self.weights, self.state, self.rng
+    output, new_state, _, _ = self.forward_and_or_backward(
+        inputs, weights, state, rng, compute_output=True, update_state=True)
+    self.state = new_state
+    return output
+
+  def backward(self, inputs, output, grad, weights, state, new_state, rng=None, **kwargs):
+    del output, state, kwargs
+    _, _, inputs_grad, weights_grad = self.forward_and_or_backward(
+        inputs, weights, new_state, rng, output_grad=grad, compute_output=False, update_state=False)
+    return inputs_grad, weights_grad
+
+  def pure_fn(self, x, weights, state, rng, use_cache=False):       # base.py:541-600
+    old_weights, old_state, old_rng = self.weights, self.state, self._rng
+    self._rng = rng
+    self.weights, self.state = weights, state
+    try:
+      outputs, s = self._do_custom_gradients(x)
+    finally:
+      self._rng = old_rng
+      if not use_cache:
+        self.weights, self.state = old_weights, old_state
+    if use_cache:
+      self.state = s
+    return outputs, s
+
+  def __call__(self, x, weights=None, state=None, rng=None):        # base.py:158-196
+    weights = self.weights if weights is None else weights
+    if state is not None:
+      self.state = state
+    outputs, new_state = self.pure_fn(x, weights, self.state, self.rng if rng is None else rng)
+    self.state = new_state
+    return outputs
+
+  def _do_custom_gradients(self, x):
+    """base.py:644-673 with torch.autograd.Function standing in for fastmath.custom_vjp."""
+    layer = self
+    have_single_input = not isinstance(x, (tuple, list))
+    xs = (x,) if have_single_input else tuple(x)
+    state, rng, weights = self.state, self._rng, self.weights
+
+    holder = {}
+
+    class _Fn(torch.autograd.Function):
+
+      @staticmethod
+      def forward(ctx, x0, w_q, w_v, w_o):
+        inputs = x0 if have_single_input else (x0,) + xs[1:]
+        out, new_state, _, _ = layer.forward_and_or_backward(
+            inputs, (w_q, w_v, w_o), state, rng, compute_output=True, update_state=True)
+        ctx.save_for_backward(x0, w_q, w_v, w_o)
+        holder['new_state'] = new_state                             # residual (base.py:659)
+        return out
+
+      @staticmethod
+      def backward(ctx, grad):
+        x0, w_q, w_v, w_o = ctx.saved_tensors
+        inputs = x0 if have_single_input else (x0,) + xs[1:]
+        inputs_grad, weights_grad = layer.backward(
+            inputs, None, grad.contiguous(), (w_q, w_v, w_o), state, holder['new_state'], rng)
+        gx = inputs_grad if have_single_input else inputs_grad[0]
+        return (gx,) + tuple(weights_grad)
+
+    out = _Fn.apply(xs[0], *weights)
+    return out, holder['new_state']
+
+  # ---- the batched driver (EA:2261-2561) -----------------------------------------------------------
+  def _dims(self, batch_size, seqlen, d_model, act_dtype):
+    factors = ops.bucket_factors(self._n_buckets, seqlen, self._chunk_len)     # EA:1890-1902
+    return _lib.make_dims(batch_size, self._n_heads, seqlen, d_model, self._d_qk, self._d_v,
+                          self._chunk_len, self._n_chunks_before, self._n_chunks_after, self._n_hashes,
+                          factors, self._causal, self._masked, act_dtype)
+
+  def forward_and_or_backward(self, inputs, weights, state, rng, output_grad=None,
+                              compute_output=True, update_state=True):
+    """Performs batched forward and/or backward passes (EA:2261-2289).
+
+    Returns (output, new_state, inputs_grad, weights_grad):
+      output is not None iff compute_output; new_state iff update_state; grads iff output_grad given.
+    Tensors may live on the GPU (no copies) or on the host (pinned or pageable): host inputs are
+    copied to cuda:current, results copied back — the e2e path bench.py times.
+    """
+    del rng   # only dropout consumes it (EA:1920) and dropout is rejected at construction
+    have_single_input = not isinstance(inputs, (tuple, list))
+    if have_single_input:
+      inputs = (inputs,)
+    if len(inputs) != self._n_in:
+      raise ValueError('LSHSelfAttention(masked=%s) takes %d inputs, got %d' % (self._masked, self._n_in, len(inputs)))
+    x = inputs[0]
+    compute_grad = output_grad is not None
+    assert compute_output or compute_grad, 'No work to perform!'    # EA:2331
+    if x.dim() != 3:
+      raise ValueError('inputs[0] must have shape (batch, seqlen, d_model)')
+    if not torch.cuda.is_available():
+      raise _lib.LshAttnError('trax_b200.LSHSelfAttention needs a CUDA device (no CPU fallback)')
+    lib = _lib.load()
+    host_io = not x.is_cuda
+    dev = torch.device('cuda', torch.cuda.current_device()) if host_io else x.device
+
+    def to_dev(t):
+      if t is None or t.is_cuda:
+        return t
+      return t.to(dev, non_blocking=True)
+    x_d = to_dev(x).contiguous()
+    mask_d = None
+    if self._masked:
+      mask_d = to_dev(inputs[1]).to(torch.uint8).contiguous()
+    w_q, w_v, w_o = (to_dev(w).to(torch.float32).contiguous() for w in weights)
+    buckets, hash_rng = state
+    batch_size, seqlen, d_model = (int(s) for s in x_d.shape)
+    if tuple(w_q.shape) != (self._n_heads, d_model, self._d_qk) or tuple(w_o.shape) != (self._n_heads, self._d_v, d_model):
+      raise ValueError('weights do not match (n_heads, d_model, d_head) layout: %s %s %s'
+                       % (tuple(w_q.shape), tuple(w_v.shape), tuple(w_o.shape)))
+    dims = self._dims(batch_size, seqlen, d_model, ops._act_dtype(x_d))
+    _lib.check(lib.lsh_attn_check_dims(ctypes.byref(dims)), 'LSHSelfAttention')
+    bh = batch_size * self._n_heads
+    length = self._n_hashes * (self._max_length_for_buckets or seqlen)
+    stream = ops._stream()
+
+    new_state = None
+    rotations = None
+    if update_state:                                                # EA:1926-1937
+      if self._rotations_override is not None:
+        rotations = to_dev(self._rotations_override).to(torch.float32).contiguous()
+        new_rng = hash_rng
+      else:
+        keys = to_dev(_to_int32_bits(hash_rng)).contiguous()
+        rotations, new_keys = ops.make_rotations(dims, keys)        # split + normal (EA:1928, 92)
+        new_rng = new_keys.view(torch.uint32) if hasattr(torch, 'uint32') else new_keys
+      buckets_d = torch.zeros((bh, max(length, self._n_hashes * seqlen)), dtype=torch.int32, device=dev)
+    else:                                                           # EA:1939-1941
+      buckets_d = to_dev(buckets)
+      if buckets_d.dtype != torch.int32 or buckets_d.dim() != 2 or buckets_d.shape[0] != bh \
+          or buckets_d.shape[1] < self._n_hashes * seqlen or buckets_d.stride(1) != 1:
+        raise ValueError('state buckets must be int32 of shape (B*H, >= n_hashes*seqlen), got %s %s'
+                         % (tuple(buckets_d.shape), buckets_d.dtype))
+
+    nbytes = lib.lsh_layer_workspace_bytes(ctypes.byref(dims), 1 if compute_grad else 0)
+    if nbytes == 0:
+      _lib.check(1, 'lsh_layer_workspace_bytes')
+    ws = ops.workspace(dev, nbytes)
+
+    out_d = None
+    if compute_output:
+      out_d = torch.empty_like(x_d)                                 # dtype of inputs[0], EA:2529-2530
+    inputs_grad = weights_grad = None
+    if not compute_grad:
+      _lib.check(lib.lsh_layer_fwd(
+          ctypes.byref(dims), ops._ptr(x_d), ops._ptr(w_q), ops._ptr(w_v), ops._ptr(w_o), ops._ptr(rotations),
+          ops._ptr(mask_d), ops._ptr(buckets_d), buckets_d.stride(0), ops._ptr(out_d), ops._ptr(ws), ws.numel(),
+          stream), 'lsh_layer_fwd')
+    else:
+      if update_state:
+        # EA allows update_state together with output_grad; the hash must then run first.
+        _lib.check(lib.lsh_layer_fwd(
+            ctypes.byref(dims), ops._ptr(x_d), ops._ptr(w_q), ops._ptr(w_v), ops._ptr(w_o), ops._ptr(rotations),
+            ops._ptr(mask_d), ops._ptr(buckets_d), buckets_d.stride(0),
+            ops._ptr(out_d if out_d is not None else torch.empty_like(x_d)), ops._ptr(ws), ws.numel(), stream),
+            'lsh_layer_fwd')
+      g_d = to_dev(output_grad).to(x_d.dtype).contiguous()
+      if g_d.shape != x_d.shape:
+        raise ValueError('output_grad shape %s != input shape %s' % (tuple(g_d.shape), tuple(x_d.shape)))
+      dx = torch.empty_like(x_d)
+      dw_q, dw_v, dw_o = torch.empty_like(w_q), torch.empty_like(w_v), torch.empty_like(w_o)
+      _lib.check(lib.lsh_layer_bwd(
+          ctypes.byref(dims), ops._ptr(x_d), ops._ptr(w_q), ops._ptr(w_v), ops._ptr(w_o), ops._ptr(mask_d),
+          ops._ptr(buckets_d), buckets_d.stride(0), ops._ptr(g_d), ops._ptr(out_d), ops._ptr(dx), ops._ptr(dw_q),
+          ops._ptr(dw_v), ops._ptr(dw_o), ops._ptr(ws), ws.numel(), stream), 'lsh_layer_bwd')
+      if host_io:
+        dx, dw_q, dw_v, dw_o = (t.cpu() for t in (dx, dw_q, dw_v, dw_o))
+      inputs_grad = dx if have_single_input else (dx,) + (None,) * (len(inputs) - 1)
+      weights_grad = (dw_q, dw_v, dw_o)
+    if update_state:
+      new_state = (buckets_d, new_rng)    # state stays on the device, like a jitted Trax layer's
+    if compute_output and host_io:
+      out_d = out_d.cpu()
+    return out_d, new_state, inputs_grad, weights_grad
