@@ -31,6 +31,8 @@ def _case(seed, B, L, D, cfg, dtype):
   if dtype == torch.bfloat16:
     dout = util.bf16_round(dout)
   mask = (rng.random((B, L)) > 0.2) if cfg.masked else None
+  if mask is not None:
+    dout = dout * mask[:, :, None]     # no gradient flows into padding outputs (see test_attend_bwd)
   return x, weights, rot, dout, mask
 
 

@@ -37,11 +37,11 @@ __global__ void __launch_bounds__(2 * C, 1) attend_bwd_kernel(const AttendBwdPar
   constexpr int NSPLIT = NWARP / 4;            // how many warps share one 16-row dQ stripe
   constexpr int NTW = 8 / NSPLIT;              // n-tiles of dQ per warp
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t *Ks = smem;                          // [C][64] bf16  normalised keys
+  uint8_t *Ks = smem;                          // [C][64] bf16  raw q rows of the key chunk
   uint8_t *Vs = Ks + C * 128;                  // [C][64] bf16
   uint8_t *Qs = Vs + C * 128;                  // [QB][64] bf16 raw queries of the sub-block
   uint8_t *Ds = Qs + QB * 128;                 // [QB][64] bf16 do rows
-  uint8_t *Ts = Ds + QB * 128;                 // [C][QB] bf16 dS^T   (also reused for raw keys at the end)
+  uint8_t *Ts = Ds + QB * 128;                 // [C][QB] bf16 (dS ∘ kscale)^T staged for dQ
   float *rnorm = reinterpret_cast<float *>(Ts + C * 128);   // [C]
   int *kpos = reinterpret_cast<int *>(rnorm + C);           // [C] 0-based key positions
   int *ktk = kpos + C;                                      // [C] key tickers
@@ -78,21 +78,14 @@ __global__ void __launch_bounds__(2 * C, 1) attend_bwd_kernel(const AttendBwdPar
   __syncthreads();
   for (int j = tid >> 3; j < C; j += NT / 8) {
     const int ch = tid & 7;
-    uint4 *ptr = reinterpret_cast<uint4 *>(Ks + swz(j, ch));
-    uint4 raw = *ptr;
+    const uint4 raw = *reinterpret_cast<const uint4 *>(Ks + swz(j, ch));
     float2 f0 = unpack_bf16(raw.x), f1 = unpack_bf16(raw.y), f2 = unpack_bf16(raw.z), f3 = unpack_bf16(raw.w);
     float ss = f0.x * f0.x + f0.y * f0.y + f1.x * f1.x + f1.y * f1.y + f2.x * f2.x + f2.y * f2.y +
                f3.x * f3.x + f3.y * f3.y;
     ss += __shfl_xor_sync(0xffffffffu, ss, 1);
     ss += __shfl_xor_sync(0xffffffffu, ss, 2);
     ss += __shfl_xor_sync(0xffffffffu, ss, 4);
-    const float r = sqrtf(ss * (1.0f / 64) + 1e-6f);
-    raw.x = pack_bf16(f0.x / r * 0.125f, f0.y / r * 0.125f);
-    raw.y = pack_bf16(f1.x / r * 0.125f, f1.y / r * 0.125f);
-    raw.z = pack_bf16(f2.x / r * 0.125f, f2.y / r * 0.125f);
-    raw.w = pack_bf16(f3.x / r * 0.125f, f3.y / r * 0.125f);
-    *ptr = raw;
-    if (ch == 0) rnorm[j] = r;
+    if (ch == 0) rnorm[j] = sqrtf(ss * (1.0f / 64) + 1e-6f);
   }
   __syncthreads();
 
@@ -108,6 +101,8 @@ __global__ void __launch_bounds__(2 * C, 1) attend_bwd_kernel(const AttendBwdPar
     }
   }
   const float ki0 = static_cast<float>(kinfo[krow0 + g]), ki1 = static_cast<float>(kinfo[krow0 + g + 8]);
+  // k^ = q / (r * sqrt(dq)) is never materialised: the per-key factor scales the fp32 score row (and dS below)
+  const float ksc0 = 0.125f / rnorm[krow0 + g], ksc1 = 0.125f / rnorm[krow0 + g + 8];
 
   float dk[8][4], dv[8][4];
 #pragma unroll
@@ -172,7 +167,7 @@ __global__ void __launch_bounds__(2 * C, 1) attend_bwd_kernel(const AttendBwdPar
           const int col = nt * 8 + 2 * t + (e & 1);
           const float qi = static_cast<float>(qpos[col] + 1);
           const float ki = (e < 2) ? ki0 : ki1;
-          float v = s[nt][e];
+          float v = s[nt][e] * ((e < 2) ? ksc0 : ksc1);
           if (p.causal && qi < ki) v = v - 1e9f;
           if (qi == ki) v = v - 1e5f;
           if (p.masked && ki < 0.f) v = v - 1e9f;
@@ -183,8 +178,9 @@ __global__ void __launch_bounds__(2 * C, 1) attend_bwd_kernel(const AttendBwdPar
         const int kk = nt >> 1, hi = (nt & 1) * 2;
         pa[kk][hi] = pack_bf16(pv[0], pv[1]);   pa[kk][hi + 1] = pack_bf16(pv[2], pv[3]);
         dsa[kk][hi] = pack_bf16(dsv[0], dsv[1]); dsa[kk][hi + 1] = pack_bf16(dsv[2], dsv[3]);
-        *reinterpret_cast<uint32_t *>(Ts + swz(krow0 + g, nt) + 4 * t) = dsa[kk][hi];
-        *reinterpret_cast<uint32_t *>(Ts + swz(krow0 + g + 8, nt) + 4 * t) = dsa[kk][hi + 1];
+        // dQ = dS·k^ = (dS ∘ kscale_j)·q_raw: the staged copy carries the key factor
+        *reinterpret_cast<uint32_t *>(Ts + swz(krow0 + g, nt) + 4 * t) = pack_bf16(dsv[0] * ksc0, dsv[1] * ksc0);
+        *reinterpret_cast<uint32_t *>(Ts + swz(krow0 + g + 8, nt) + 4 * t) = pack_bf16(dsv[2] * ksc1, dsv[3] * ksc1);
       }
       // dV += P^T·do ; dK^ += dS^T·q   (contraction over the 64 queries)
 #pragma unroll
@@ -238,23 +234,14 @@ __global__ void __launch_bounds__(2 * C, 1) attend_bwd_kernel(const AttendBwdPar
   }
 
   // ---- key side: length-normalisation VJP (App. B5) and row stores ---------------------------------
-  __syncthreads();
-  for (int i = tid; i < C * 8; i += NT) {       // raw q rows of the key chunk -> Ts
-    const int j = i >> 3, ch = i & 7;
-    const __nv_bfloat16 *src = p.qv + ((static_cast<int64_t>(b) * p.L + kpos[j]) * p.H + h) * 128 + ch * 8;
-    cp_async16(ts_base + swz(j, ch), src);
-  }
-  cp_async_commit();
-  cp_async_wait<0>();
-  __syncthreads();
   {
     const int r0 = krow0 + g, r1 = r0 + 8;
     float qraw[8][4];
     float dot0 = 0.f, dot1 = 0.f;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      const float2 a = unpack_bf16(*reinterpret_cast<const uint32_t *>(Ts + swz(r0, nt) + 4 * t));
-      const float2 c = unpack_bf16(*reinterpret_cast<const uint32_t *>(Ts + swz(r1, nt) + 4 * t));
+      const float2 a = unpack_bf16(*reinterpret_cast<const uint32_t *>(Ks + swz(r0, nt) + 4 * t));
+      const float2 c = unpack_bf16(*reinterpret_cast<const uint32_t *>(Ks + swz(r1, nt) + 4 * t));
       qraw[nt][0] = a.x; qraw[nt][1] = a.y; qraw[nt][2] = c.x; qraw[nt][3] = c.y;
       dot0 += dk[nt][0] * a.x + dk[nt][1] * a.y;
       dot1 += dk[nt][2] * c.x + dk[nt][3] * c.y;
@@ -283,11 +270,7 @@ __global__ void __launch_bounds__(2 * C, 1) attend_bwd_kernel(const AttendBwdPar
 template <int C>
 static int launch_attend_bwd(const AttendBwdParams &p, int BH, cudaStream_t stream) {
   size_t smem = static_cast<size_t>(C) * 128 * 3 + QB * 128 * 2 + C * 16 + QB * 16;
-  static thread_local bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(attend_bwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = true;
-  }
+  LSH_OPT_IN_SMEM(attend_bwd_kernel<C>);
   attend_bwd_kernel<C><<<BH * p.n_chunks, 2 * C, smem, stream>>>(p);
   LSH_CHECK_LAUNCH("attend_bwd_kernel");
   return 0;

@@ -27,11 +27,12 @@ __global__ void __launch_bounds__(2 * C) attend_fwd_kernel(const AttendFwdParams
   constexpr int QVROW = 128;           // elements per (token, head) row of qv
   extern __shared__ __align__(1024) uint8_t smem[];
   const int W = C * p.nwin;
-  uint8_t *Ks = smem;                                  // [W][64] bf16 swizzled (q rows → k-hat)
+  uint8_t *Ks = smem;                                  // [W][64] bf16 swizzled (raw q rows: queries AND keys)
   uint8_t *Vs = smem + static_cast<size_t>(W) * 128;   // [W][64] bf16 swizzled
   int *kinfo = reinterpret_cast<int *>(Vs + static_cast<size_t>(W) * 128);   // [W] kv_info (+1 applied)
   int *spos = kinfo + W;                               // [W] 0-based positions
   int *tkq = spos + W;                                 // [C] ticker of the query rows
+  float *kscale = reinterpret_cast<float *>(tkq + C);  // [W] 1 / (sqrt(mean(q^2)+eps) * sqrt(dq)) per key row
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int u = blockIdx.x / p.n_chunks, c = blockIdx.x % p.n_chunks;
@@ -79,26 +80,20 @@ __global__ void __launch_bounds__(2 * C) attend_fwd_kernel(const AttendFwdParams
     for (int ks = 0; ks < 4; ++ks)
       ldmatrix_x4(ks_base + swz(row, ks * 2 + (mi >> 1)), qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
   }
-  __syncthreads();
 
-  // ---- keys: k = q / sqrt(mean(q^2) + 1e-6) / sqrt(dq)  (EA:54-57, 229-231), in place -------------
+  // ---- keys: k = q / sqrt(mean(q^2) + 1e-6) / sqrt(dq)  (EA:54-57, 229-231) -------------------------
+  // The rows stay un-normalised in shared memory (exact bf16 operands); the per-key factor is applied
+  // to the fp32 score column instead, which saves one bf16 rounding of every key.
   for (int j = tid >> 3; j < W; j += NT / 8) {
     const int ch = tid & 7;
-    uint4 *ptr = reinterpret_cast<uint4 *>(Ks + swz(j, ch));
-    uint4 raw = *ptr;
+    const uint4 raw = *reinterpret_cast<const uint4 *>(Ks + swz(j, ch));
     float2 f0 = unpack_bf16(raw.x), f1 = unpack_bf16(raw.y), f2 = unpack_bf16(raw.z), f3 = unpack_bf16(raw.w);
     float ss = f0.x * f0.x + f0.y * f0.y + f1.x * f1.x + f1.y * f1.y + f2.x * f2.x + f2.y * f2.y +
                f3.x * f3.x + f3.y * f3.y;
     ss += __shfl_xor_sync(0xffffffffu, ss, 1);
     ss += __shfl_xor_sync(0xffffffffu, ss, 2);
     ss += __shfl_xor_sync(0xffffffffu, ss, 4);
-    const float r = sqrtf(ss * (1.0f / D) + 1e-6f);
-    const float inv = 0.125f;   // 1/sqrt(64)
-    raw.x = pack_bf16(f0.x / r * inv, f0.y / r * inv);
-    raw.y = pack_bf16(f1.x / r * inv, f1.y / r * inv);
-    raw.z = pack_bf16(f2.x / r * inv, f2.y / r * inv);
-    raw.w = pack_bf16(f3.x / r * inv, f3.y / r * inv);
-    *ptr = raw;
+    if (ch == 0) kscale[j] = 0.125f / sqrtf(ss * (1.0f / D) + 1e-6f);   // 1/sqrt(64) = 0.125
   }
   __syncthreads();
 
@@ -137,7 +132,7 @@ __global__ void __launch_bounds__(2 * C) attend_fwd_kernel(const AttendFwdParams
         const int col = kb * 64 + nt * 8 + 2 * t + (e & 1);
         const float ki = static_cast<float>(kinfo[col]);
         const float qi = (e < 2) ? qi0 : qi1;
-        float v = s[nt][e];
+        float v = s[nt][e] * kscale[col];
         if (p.causal && qi < ki) v = v - 1e9f;
         if (qi == ki) v = v - 1e5f;
         if (p.masked && ki < 0.f) v = v - 1e9f;
@@ -209,13 +204,9 @@ __global__ void __launch_bounds__(2 * C) attend_fwd_kernel(const AttendFwdParams
 template <int C>
 static int launch_attend_fwd(const AttendFwdParams &p, int BH, cudaStream_t stream) {
   const int W = C * p.nwin;
-  size_t smem = static_cast<size_t>(W) * 256 + static_cast<size_t>(W) * 8 + C * 4;
+  size_t smem = static_cast<size_t>(W) * 256 + static_cast<size_t>(W) * 12 + C * 4;
   if (smem > 227 * 1024) return set_error("attend_fwd: window of %d keys needs %zu B shared memory", W, smem);
-  static thread_local size_t configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(attend_fwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
+  LSH_OPT_IN_SMEM(attend_fwd_kernel<C>);
   attend_fwd_kernel<C><<<BH * p.n_chunks, 2 * C, smem, stream>>>(p);
   LSH_CHECK_LAUNCH("attend_fwd_kernel");
   return 0;

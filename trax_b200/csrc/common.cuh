@@ -34,6 +34,19 @@ inline Derived derive(const LshAttnDims &d) {
   return r;
 }
 
+// Opt a kernel in to the full 227 KB of dynamic shared memory once per (thread, kernel).
+#define LSH_OPT_IN_SMEM(kernel)                                                                      \
+  do {                                                                                               \
+    static thread_local int done_dev_ = -1;                                                          \
+    int dev_ = 0;                                                                                    \
+    cudaGetDevice(&dev_);                                                                            \
+    if (done_dev_ != dev_) {                                                                         \
+      cudaError_t e_ = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
+      if (e_ != cudaSuccess) return lsh::set_error("cudaFuncSetAttribute(%s): %s", #kernel, cudaGetErrorString(e_)); \
+      done_dev_ = dev_;                                                                              \
+    }                                                                                                \
+  } while (0)
+
 #define LSH_CHECK_LAUNCH(name)                                                      \
   do {                                                                              \
     cudaError_t e_ = cudaGetLastError();                                            \

@@ -143,11 +143,7 @@ static int launch_hash(const LshAttnDims &d, const void *vecs, int64_t sb, int64
   size_t smem = static_cast<size_t>(64) * p.Rpad * sizeof(float);
   if (smem > 200 * 1024) return set_error("lsh_hash: sum(factors)/2 = %d too large for shared memory", dr.R);
   if (d.masked && mask == nullptr) return set_error("lsh_hash: dims.masked set but mask == NULL");
-  static thread_local size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaFuncSetAttribute(hash_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
+  LSH_OPT_IN_SMEM(hash_kernel<T>);
   dim3 grid((d.L + HASH_THREADS - 1) / HASH_THREADS, dr.BH);
   hash_kernel<T><<<grid, HASH_THREADS, smem, stream>>>(p);
   LSH_CHECK_LAUNCH("hash_kernel");

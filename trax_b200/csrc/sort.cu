@@ -183,12 +183,7 @@ int sort_run(const LshAttnDims &d, const int32_t *buckets, int64_t bstride, int3
   int32_t *hist = static_cast<int32_t *>(ws);
   int32_t *tmp = reinterpret_cast<int32_t *>(static_cast<char *>(ws) + s.hist_bytes);
   size_t smem_sc = static_cast<size_t>(SORT_WARPS) * s.n_digits * sizeof(int);
-  static thread_local bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(sort_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         SORT_WARPS * (1 << SORT_MAX_BITS) * (int)sizeof(int));
-    configured = true;
-  }
+  LSH_OPT_IN_SMEM(sort_scatter_kernel);
   // ping-pong so that the last pass lands in `sticker`
   const int32_t *in = nullptr;
   for (int pass = 0; pass < s.passes; ++pass) {
