@@ -6,19 +6,12 @@
 // v1 compute path: bf16 mma.sync m16n8k16 with fp32 accumulation, one CTA per query chunk
 // (chunk_len/16 warps, one 16-row stripe each), K/V window staged once in swizzled shared memory
 // by cp.async row gathers, flash-style online softmax over 64-key blocks.
-#include "common.cuh"
+#include <stdlib.h>
+#include <string.h>
+
+#include "attend_params.cuh"
 
 namespace lsh {
-
-struct AttendFwdParams {
-  const __nv_bfloat16 *qv;      // (B, L, H, 128)
-  const int32_t *sticker;       // (BH, N)
-  const uint8_t *mask;          // (B, L) or null
-  __nv_bfloat16 *o;             // rows addressed as b*o_sb + h*o_sh + round*o_sr + pos*o_sp
-  int64_t o_sb, o_sh, o_sr, o_sp;
-  float *lse;                   // (BH, N) ticker order
-  int L, H, N, n_chunks, nb, nwin, causal, masked;
-};
 
 template <int C>
 __global__ void __launch_bounds__(2 * C) attend_fwd_kernel(const AttendFwdParams p) {
@@ -223,6 +216,9 @@ int attend_fwd_run(const LshAttnDims &d, const void *qv, const int32_t *sticker,
   p.L = d.L; p.H = d.H; p.N = dr.N; p.n_chunks = dr.n_chunks; p.nb = d.nb; p.nwin = dr.nwin;
   p.causal = d.causal; p.masked = d.masked;
   if (d.masked && !mask) return set_error("attend_fwd: dims.masked set but mask == NULL");
+  // tcgen05 path for the long-sequence shape (chunk 128, 2-chunk window); LSH_ATTN_FWD=mma forces the mma.sync path
+  static const bool force_mma = [] { const char *e = getenv("LSH_ATTN_FWD"); return e && strcmp(e, "mma") == 0; }();
+  if (d.C == 128 && dr.nwin == 2 && !force_mma) return attend_fwd_tc_run(p, dr.BH, stream);
   switch (d.C) {
     case 32: return launch_attend_fwd<32>(p, dr.BH, stream);
     case 64: return launch_attend_fwd<64>(p, dr.BH, stream);
