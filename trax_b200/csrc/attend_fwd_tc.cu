@@ -2,215 +2,322 @@
 // Same contract as attend_fwd.cu (EA:1958-1986); specialised for chunk_len 128 with a 2-chunk window
 // (n_chunks_before + n_chunks_after == 1), dq = dv = 64 — the shape of every long-sequence config.
 //
-// One CTA = one query chunk; two CTAs share an SM (256 TMEM columns each), so one CTA's softmax
-// overlaps the other's MMAs and gathers.
-//   smem : window rows [256][64] bf16 for q (queries AND keys, un-normalised) and v, SWIZZLE_128B
-//          (cp.async row gathers with the chunk ^= row&7 pattern = the UMMA canonical K-major /
-//          MN-major SW128 layouts)
-//   TMEM : S = Q·K^T  128 lanes x 256 fp32 columns [0,256)           (tcgen05.mma SS, M128 N256 K16 x4)
-//          P (bf16, 2 per column) written back in place to columns [0,128) by the softmax warps
-//          O = P·V    128 x 64 fp32 at columns [128,192)              (tcgen05.mma TS, M128 N64 K16 x16)
-//   warps 0-3: one query row per thread (TMEM lane = row): key scale + masks + 2-pass softmax, epilogue
-//   warp  4  : TMEM allocation, MMA issue (one lane), commit -> mbarriers
-//   warp  5  : helps with the gathers
+// Persistent, warp-specialised: one CTA per SM walks a contiguous range of (unit, chunk) work items.
+//   warps 0-1  producers : sticker -> positions -> cp.async row gathers of q|v into a ring of chunk
+//                          tiles (each tile = 128 rows x (64 q + 64 v) bf16, SWIZZLE_128B atoms).  A tile
+//                          is loaded ONCE and serves as "own chunk" for chunk c and as look-back for c+1.
+//   warp  2    MMA issuer: S = Q·K^T  (tcgen05.mma SS, M128 N128 K16, 4 k-steps x 2 tiles) -> TMEM,
+//                          O = P·V    (tcgen05.mma TS, P from TMEM, V MN-major, 16 k-steps) -> TMEM,
+//                          completion via tcgen05.commit -> mbarriers; S(k+1) is issued before PV(k).
+//   warp  3    TMEM allocation / idle
+//   warps 4-7, 8-11  two softmax warpgroups, ping-pong on two 256-column TMEM regions: thread = query
+//                          row = TMEM lane.  One pass: t = s*kscale_j*log2e - m_i + masks, p = exp2(t),
+//                          P (bf16) written back in place over S; then O/l -> bf16 row -> ticker slot.
+// The softmax shift m_i is the analytic bound |q_i| (the un-masked self score, Cauchy-Schwarz), so no
+// max pass is needed; rows whose only visible key is themselves (EA "-1e5" class) shift by that class.
 #include "attend_params.cuh"
 #include "tc_common.cuh"
 
 namespace lsh {
 
-constexpr int TC_C = 128, TC_W = 256, TC_THREADS = 192;
-constexpr uint32_t TC_TMEM_COLS = 256;
-constexpr uint32_t TC_IDESC_S = make_idesc_bf16(128, 256, 0, 0);    // Q (K-major) x K (K-major)
-constexpr uint32_t TC_IDESC_O = make_idesc_bf16(128, 64, 0, 1);     // P (TMEM)    x V (MN-major)
+constexpr int TC_C = 128;
+constexpr int TC_NST = 5;                    // tile ring depth
+constexpr int TC_THREADS = 384;
+constexpr int TC_TILE_BYTES = 2 * TC_C * 128;   // K rows then V rows
+constexpr uint32_t TC_IDESC_S = make_idesc_bf16(128, 128, 0, 0);   // Q (K-major) x K (K-major)
+constexpr uint32_t TC_IDESC_O = make_idesc_bf16(128, 64, 0, 1);    // P (TMEM)    x V (MN-major)
+
+struct __align__(16) TcTileMeta {
+  float kinfo[TC_C];    // kv_info (+1 applied; negative = padding), fp32 like EA:148-149
+  int pos[TC_C];        // 0-based positions
+  int tk[TC_C];         // ticker values
+  float vmin[2], vmax[2];   // min / max of the valid kinfo per producer warp (visibility test)
+};
 
 struct __align__(16) TcShared {
-  float kinfo[TC_W];     // kv_info (+1 applied, negative = padding) as fp32 (EA:148-149 compares in fp32)
-  float kscl[TC_W];      // kscale * log2(e)
-  int spos[TC_W];
-  int tkq[TC_C];
-  uint64_t bar_s, bar_p, bar_o;
+  TcTileMeta meta[TC_NST];
+  float kscl[2][2 * TC_C];          // per softmax warpgroup: kscale * log2(e) of the 256 window rows
+  uint64_t full[TC_NST], empty[TC_NST];
+  uint64_t s_full[2], p_full[2], o_full[2], s_free[2];
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 2) attend_fwd_tc_kernel(const AttendFwdParams p) {
+// Enumerates the work items of one CTA and the tile sequence numbers they use.
+struct Walker {
+  int g, g_end, n_chunks, k, n;     // global chunk id, end, chunks per unit, index in range, seq of the 2nd window tile
+  int u, c;
+  bool reuse;
+  __device__ Walker(int g0, int g1, int nc) : g(g0), g_end(g1), n_chunks(nc), k(0), n(1) {
+    u = g / nc; c = g - u * nc; reuse = false;
+  }
+  __device__ bool valid() const { return g < g_end; }
+  __device__ bool next_reuses() const { return (g + 1 < g_end) && (c + 1 < n_chunks); }
+  __device__ void next() {
+    ++g; ++k; ++c;
+    if (c == n_chunks) { c = 0; ++u; reuse = false; } else { reuse = true; }
+    n += reuse ? 1 : 2;
+  }
+};
+
+__device__ __forceinline__ uint32_t slot_of(int n) { return static_cast<uint32_t>(n % TC_NST); }
+__device__ __forceinline__ uint32_t phase_of(int n) { return static_cast<uint32_t>((n / TC_NST) & 1); }
+
+__global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const AttendFwdParams p, int total_chunks) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // dynamic smem base is only guaranteed 16-byte aligned: round up to the 1024-byte swizzle atom
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t *Ks = smem;                       // [256][128 B]
-  uint8_t *Vs = smem + TC_W * 128;          // [256][128 B]
-  TcShared &sh = *reinterpret_cast<TcShared *>(smem + 2 * TC_W * 128);
+  uint8_t *tiles = smem;                                    // [TC_NST][K 16 KB | V 16 KB]
+  TcShared &sh = *reinterpret_cast<TcShared *>(smem + TC_NST * TC_TILE_BYTES);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int u = blockIdx.x / p.n_chunks, c = blockIdx.x % p.n_chunks;
-  const int b = u / p.H, h = u % p.H;
-  const int32_t *stk = p.sticker + static_cast<int64_t>(u) * p.N;
+  // contiguous, balanced range of chunks for this CTA
+  const int g0 = static_cast<int>(static_cast<int64_t>(total_chunks) * blockIdx.x / gridDim.x);
+  const int g1 = static_cast<int>(static_cast<int64_t>(total_chunks) * (blockIdx.x + 1) / gridDim.x);
 
-  if (warp == 4) tmem_alloc(&sh.tmem_base, TC_TMEM_COLS);
+  if (warp == 3) tmem_alloc(&sh.tmem_base, 512);
   if (tid == 0) {
-    mbar_init(&sh.bar_s, 1);
-    mbar_init(&sh.bar_p, 128);
-    mbar_init(&sh.bar_o, 1);
+    for (int i = 0; i < TC_NST; ++i) { mbar_init(&sh.full[i], 64); mbar_init(&sh.empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sh.s_full[i], 1); mbar_init(&sh.p_full[i], 128);
+      mbar_init(&sh.o_full[i], 1); mbar_init(&sh.s_free[i], 128);
+    }
     fence_mbar_init();
-  }
-  // ---- window metadata ------------------------------------------------------------------------------
-  for (int j = tid; j < TC_W; j += TC_THREADS) {
-    const int blk = j >> 7;
-    int src_chunk = c + blk - p.nb;
-    src_chunk = (src_chunk % p.n_chunks + p.n_chunks) % p.n_chunks;
-    const int tk = stk[src_chunk * TC_C + (j & 127)];
-    const int pos = tk % p.L;
-    bool valid = true;
-    if (p.masked) valid = p.mask[static_cast<int64_t>(b) * p.L + pos] != 0;
-    sh.kinfo[j] = static_cast<float>((valid ? pos : -pos) + 1);
-    sh.spos[j] = pos;
-    if (blk == p.nb) sh.tkq[j & 127] = tk;
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sh.tmem_base;
+  const uint32_t tiles_u32 = smem_u32(tiles);
 
-  // ---- gather q|v rows -------------------------------------------------------------------------------
-  const uint32_t ks_base = smem_u32(Ks), vs_base = smem_u32(Vs);
-  for (int i = tid; i < TC_W * 16; i += TC_THREADS) {
-    const int j = i >> 4, ch = i & 15;
-    const __nv_bfloat16 *src = p.qv + ((static_cast<int64_t>(b) * p.L + sh.spos[j]) * p.H + h) * 128 + ch * 8;
-    cp_async16((ch < 8) ? ks_base + swz(j, ch) : vs_base + swz(j, ch - 8), src);
-  }
-  cp_async_commit();
-  cp_async_wait<0>();
-  fence_proxy_async();          // this thread's gathered bytes -> async proxy (UMMA operand reads)
-  __syncthreads();
-
-  if (warp == 4) {
-    // ---- MMA issuer --------------------------------------------------------------------------------
+  if (warp < 2) {
+    // ================================ producers ======================================================
+    const int pw = warp;                                  // rows [64*pw, 64*pw + 64) of every tile
+    int issued = 0;                                       // tiles issued by this thread
+    int prev_slot = -1;
+    auto load_tile = [&](int n, int u, int cc) {
+      const uint32_t slot = slot_of(n);
+      mbar_wait(&sh.empty[slot], phase_of(n) ^ 1);
+      const int b = u / p.H, h = u - b * p.H;
+      const int32_t *stk = p.sticker + static_cast<int64_t>(u) * p.N + cc * TC_C + 64 * pw;
+      const int tka = __ldg(stk + lane), tkb = __ldg(stk + 32 + lane);
+      const int pa = tka % p.L, pb = tkb % p.L;
+      bool va = true, vb = true;
+      if (p.masked) {
+        va = p.mask[static_cast<int64_t>(b) * p.L + pa] != 0;
+        vb = p.mask[static_cast<int64_t>(b) * p.L + pb] != 0;
+      }
+      TcTileMeta &mt = sh.meta[slot];
+      const float kia = static_cast<float>((va ? pa : -pa) + 1), kib = static_cast<float>((vb ? pb : -pb) + 1);
+      mt.kinfo[64 * pw + lane] = kia; mt.kinfo[64 * pw + 32 + lane] = kib;
+      mt.pos[64 * pw + lane] = pa;    mt.pos[64 * pw + 32 + lane] = pb;
+      mt.tk[64 * pw + lane] = tka;    mt.tk[64 * pw + 32 + lane] = tkb;
+      float mn = fminf(kia > 0.f ? kia : INFINITY, kib > 0.f ? kib : INFINITY);
+      float mx = fmaxf(kia > 0.f ? kia : -INFINITY, kib > 0.f ? kib : -INFINITY);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      }
+      if (lane == 0) { mt.vmin[pw] = mn; mt.vmax[pw] = mx; }
+      const uint32_t kt = tiles_u32 + slot * TC_TILE_BYTES, vt = kt + TC_C * 128;
+      const int ch = lane & 15, hi = lane >> 4;
+      const __nv_bfloat16 *base = p.qv + (static_cast<int64_t>(b) * p.L * p.H + h) * 128 + ch * 8;
+#pragma unroll 4
+      for (int i = 0; i < 32; ++i) {
+        const int rel = 2 * i + hi;                                      // row within this warp's 64
+        const int pr = __shfl_sync(0xffffffffu, (i < 16) ? pa : pb, rel & 31);
+        const int row = 64 * pw + rel;
+        const __nv_bfloat16 *src = base + static_cast<int64_t>(pr) * p.H * 128;
+        cp_async16((ch < 8 ? kt : vt) + swz(row, ch & 7), src);
+      }
+      cp_async_commit();
+      if (prev_slot >= 0) {
+        cp_async_wait<1>();               // the previous tile of this thread has landed
+        fence_proxy_async();
+        mbar_arrive(&sh.full[prev_slot]);
+      }
+      prev_slot = static_cast<int>(slot);
+      ++issued;
+    };
+    for (Walker w(g0, g1, p.n_chunks); w.valid(); w.next()) {
+      const int c0 = ((w.c - p.nb) % p.n_chunks + p.n_chunks) % p.n_chunks;   // first window chunk (EA:137-141)
+      if (!w.reuse) load_tile(w.n - 1, w.u, c0);
+      load_tile(w.n, w.u, (c0 + 1) % p.n_chunks);
+    }
+    if (prev_slot >= 0) {
+      cp_async_wait<0>();
+      fence_proxy_async();
+      mbar_arrive(&sh.full[prev_slot]);
+    }
+  } else if (warp == 2) {
+    // ================================ MMA issuer =====================================================
     if (lane == 0) {
-      // S[128 x 256] = Q (window rows 128 * nb .. +127) x K^T (all 256 rows); K = 64 = 4 x UMMA_K
-      const uint32_t q_addr = ks_base + p.nb * TC_C * 128;
+      Walker ws(g0, g1, p.n_chunks);      // walker for the S products
+      Walker wo(g0, g1, p.n_chunks);      // walker for the PV products (one chunk behind)
+      while (wo.valid()) {
+        if (ws.valid()) {
+          const int k = ws.k, n = ws.n;
+          const uint32_t w = k & 1, j = k >> 1;
+          mbar_wait(&sh.full[slot_of(n - 1)], phase_of(n - 1));
+          mbar_wait(&sh.full[slot_of(n)], phase_of(n));
+          mbar_wait(&sh.s_free[w], (j & 1) ^ 1);
+          fence_proxy_async();
+          tc_fence_after();
+          const uint32_t k0 = tiles_u32 + slot_of(n - 1) * TC_TILE_BYTES, k1 = tiles_u32 + slot_of(n) * TC_TILE_BYTES;
+          const uint32_t qa = p.nb ? k1 : k0;
+          const uint32_t s_t = tmem + w * 256;
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        const uint64_t a_desc = make_smem_desc(q_addr + ks * 32, 16, 1024);
-        const uint64_t b_desc = make_smem_desc(ks_base + ks * 32, 16, 1024);
-        umma_ss(tmem, a_desc, b_desc, TC_IDESC_S, ks > 0);
-      }
-      umma_commit(&sh.bar_s);
-      // O[128 x 64] = P (TMEM cols [0,128), 8 columns per K=16 step) x V (MN-major, 16 key rows per step)
-      mbar_wait(&sh.bar_p, 0);
-      tc_fence_after();
+          for (int ks = 0; ks < 4; ++ks)
+            umma_ss(s_t, make_smem_desc(qa + ks * 32, 16, 1024), make_smem_desc(k0 + ks * 32, 16, 1024), TC_IDESC_S, ks > 0);
 #pragma unroll
-      for (int kk = 0; kk < 16; ++kk) {
-        const uint64_t b_desc = make_smem_desc(vs_base + kk * 2048, 1024, 1024);
-        umma_ts(tmem + 128, tmem + kk * 8, b_desc, TC_IDESC_O, kk > 0);
+          for (int ks = 0; ks < 4; ++ks)
+            umma_ss(s_t + 128, make_smem_desc(qa + ks * 32, 16, 1024), make_smem_desc(k1 + ks * 32, 16, 1024), TC_IDESC_S, ks > 0);
+          umma_commit(&sh.s_full[w]);
+          ws.next();
+        }
+        if (ws.k > wo.k + 1 || !ws.valid()) {
+          const int k = wo.k, n = wo.n;
+          const uint32_t w = k & 1, j = k >> 1;
+          mbar_wait(&sh.p_full[w], j & 1);
+          tc_fence_after();
+          const uint32_t v0 = tiles_u32 + slot_of(n - 1) * TC_TILE_BYTES + TC_C * 128;
+          const uint32_t v1 = tiles_u32 + slot_of(n) * TC_TILE_BYTES + TC_C * 128;
+          const uint32_t p_t = tmem + w * 256, o_t = p_t + 128;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            umma_ts(o_t, p_t + i * 8, make_smem_desc(v0 + i * 2048, 1024, 1024), TC_IDESC_O, i > 0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            umma_ts(o_t, p_t + 64 + i * 8, make_smem_desc(v1 + i * 2048, 1024, 1024), TC_IDESC_O, 1);
+          umma_commit(&sh.o_full[w]);
+          umma_commit(&sh.empty[slot_of(n - 1)]);                 // look-back tile is done
+          if (!wo.next_reuses()) umma_commit(&sh.empty[slot_of(n)]);   // nobody will reuse the own tile
+          wo.next();
+        }
       }
-      umma_commit(&sh.bar_o);
     }
     __syncwarp();
-  } else if (warp < 4) {
-    // ---- key scale 1/(sqrt(mean(q^2)+eps)*sqrt(dq)) * log2(e), 2 rows per thread -------------------------
-    for (int j = tid; j < TC_W; j += 128) {
-      float ss = 0.f;
+  } else if (warp >= 4) {
+    // ================================ softmax warpgroups ==============================================
+    const uint32_t w = (warp - 4) >> 2;                    // warpgroup 0 / 1 <-> TMEM region
+    const int row = ((warp - 4) & 3) * 32 + lane;          // query row == TMEM lane
+    const uint32_t t_lane = tmem + w * 256 + (static_cast<uint32_t>(((warp - 4) & 3) * 32) << 16);
+    float *kscl = sh.kscl[w];
+    constexpr float kBig = 1e9f * kLog2e, kSelf = 1e5f * kLog2e;   // EA:152-159 masks, log2 domain
+    for (Walker wk(g0, g1, p.n_chunks); wk.valid(); wk.next()) {
+      if ((wk.k & 1) != static_cast<int>(w)) continue;
+      const int n = wk.n;
+      const uint32_t j = wk.k >> 1;
+      const uint32_t sl0 = slot_of(n - 1), sl1 = slot_of(n);
+      mbar_wait(&sh.full[sl0], phase_of(n - 1));
+      mbar_wait(&sh.full[sl1], phase_of(n));
+      // key scale of window rows `row` (tile 0) and 128 + `row` (tile 1): 1/(sqrt(mean(q^2)+eps)*sqrt(dq)) * log2e
+      float ss[2];
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
-        const uint4 raw = *reinterpret_cast<const uint4 *>(Ks + swz(j, ch));
-        const float2 f0 = unpack_bf16(raw.x), f1 = unpack_bf16(raw.y), f2 = unpack_bf16(raw.z), f3 = unpack_bf16(raw.w);
-        ss += f0.x * f0.x + f0.y * f0.y + f1.x * f1.x + f1.y * f1.y + f2.x * f2.x + f2.y * f2.y + f3.x * f3.x + f3.y * f3.y;
-      }
-      sh.kscl[j] = 0.125f * kLog2e / sqrtf(ss * (1.0f / 64) + 1e-6f);
-    }
-    asm volatile("bar.sync 1, 128;\n" ::: "memory");   // kscl visible to the 4 softmax warps
-
-    const int row = warp * 32 + lane;                      // query row == TMEM lane
-    const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-    const float qi = static_cast<float>(sh.spos[p.nb * TC_C + row] + 1);
-    constexpr float kBig = 1e9f * kLog2e, kSelf = 1e5f * kLog2e;   // masks in the log2 domain
-    mbar_wait(&sh.bar_s, 0);
-    tc_fence_after();
-    // pass 1: row maximum of the scaled + masked scores
-    float m = -INFINITY;
-    for (int k = 0; k < 8; ++k) {
-      uint32_t r[32];
-      tmem_ld32(t_lane + k * 32, r);
-      tmem_ld_wait();
+      for (int t = 0; t < 2; ++t) {
+        const uint8_t *kt = tiles + (t ? sl1 : sl0) * TC_TILE_BYTES;
+        float s = 0.f;
 #pragma unroll
-      for (int c4 = 0; c4 < 32; c4 += 4) {
-        const float4 ki4 = *reinterpret_cast<const float4 *>(&sh.kinfo[k * 32 + c4]);
-        const float4 sc4 = *reinterpret_cast<const float4 *>(&sh.kscl[k * 32 + c4]);
-        const float kis[4] = {ki4.x, ki4.y, ki4.z, ki4.w}, scs[4] = {sc4.x, sc4.y, sc4.z, sc4.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float v = __uint_as_float(r[c4 + e]) * scs[e];
-          if (p.causal && qi < kis[e]) v -= kBig;
-          if (qi == kis[e]) v -= kSelf;
-          if (p.masked && kis[e] < 0.f) v -= kBig;
-          m = fmaxf(m, v);
+        for (int ch = 0; ch < 8; ++ch) {
+          const uint4 raw = *reinterpret_cast<const uint4 *>(kt + swz(row, ch));
+          const float2 f0 = unpack_bf16(raw.x), f1 = unpack_bf16(raw.y), f2 = unpack_bf16(raw.z), f3 = unpack_bf16(raw.w);
+          s += f0.x * f0.x + f0.y * f0.y + f1.x * f1.x + f1.y * f1.y + f2.x * f2.x + f2.y * f2.y + f3.x * f3.x + f3.y * f3.y;
         }
+        ss[t] = s;
+        kscl[t * TC_C + row] = 0.125f * kLog2e / sqrtf(s * (1.0f / 64) + 1e-6f);
       }
-    }
-    // pass 2: P = exp2(t - m) -> bf16, written in place (columns [16k, 16k+16) after reading [32k, 32k+32))
-    float l = 0.f;
-    for (int k = 0; k < 8; ++k) {
-      uint32_t r[32];
-      tmem_ld32(t_lane + k * 32, r);
-      tmem_ld_wait();
-      uint32_t pk[16];
+      const TcTileMeta &m0 = sh.meta[sl0], &m1 = sh.meta[sl1];
+      const TcTileMeta &mq = p.nb ? m1 : m0;
+      const float qi = static_cast<float>(mq.pos[row] + 1);          // q_info = pos + 1 (EA:201)
+      const float own_ki = mq.kinfo[row];
+      const int tk = mq.tk[row];
+      const float wmin = fminf(fminf(m0.vmin[0], m0.vmin[1]), fminf(m1.vmin[0], m1.vmin[1]));
+      const float wmax = fmaxf(fmaxf(m0.vmax[0], m0.vmax[1]), fmaxf(m1.vmax[0], m1.vmax[1]));
+      asm volatile("bar.sync %0, 128;\n" ::"r"(1 + w) : "memory");   // kscl of this warpgroup complete
+      // softmax shift (log2 domain): the un-masked self score bounds every score of the row
+      const float self2 = ss[p.nb] * kscl[p.nb * TC_C + row];
+      const bool visible = p.causal ? (wmin < qi) : !(wmin == qi && wmax == qi);
+      float m2 = visible ? self2 : self2 - kSelf;
+      if (p.masked && own_ki < 0.f) m2 = -kBig;                       // padding query: any finite result
+      mbar_wait(&sh.s_full[w], j & 1);
+      tc_fence_after();
+      float l = 0.f;
+#pragma unroll 1
+      for (int kc = 0; kc < 8; ++kc) {
+        uint32_t r[32];
+        tmem_ld32(t_lane + kc * 32, r);
+        const float *kin = (kc < 4 ? m0.kinfo : m1.kinfo) + (kc & 3) * 32;
+        const float *ksc = kscl + kc * 32;
+        tmem_ld_wait();
+        uint32_t pk[16];
 #pragma unroll
-      for (int c4 = 0; c4 < 32; c4 += 4) {
-        const float4 ki4 = *reinterpret_cast<const float4 *>(&sh.kinfo[k * 32 + c4]);
-        const float4 sc4 = *reinterpret_cast<const float4 *>(&sh.kscl[k * 32 + c4]);
-        const float kis[4] = {ki4.x, ki4.y, ki4.z, ki4.w}, scs[4] = {sc4.x, sc4.y, sc4.z, sc4.w};
-        float pv[4];
+        for (int c4 = 0; c4 < 32; c4 += 4) {
+          const float4 ki4 = *reinterpret_cast<const float4 *>(kin + c4);
+          const float4 sc4 = *reinterpret_cast<const float4 *>(ksc + c4);
+          const float kis[4] = {ki4.x, ki4.y, ki4.z, ki4.w}, scs[4] = {sc4.x, sc4.y, sc4.z, sc4.w};
+          float pv[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float v = __uint_as_float(r[c4 + e]) * scs[e];
-          if (p.causal && qi < kis[e]) v -= kBig;
-          if (qi == kis[e]) v -= kSelf;
-          if (p.masked && kis[e] < 0.f) v -= kBig;
-          pv[e] = exp2f(v - m);
+          for (int e = 0; e < 4; ++e) {
+            float t = fmaf(__uint_as_float(r[c4 + e]), scs[e], -m2);
+            if (p.causal && qi < kis[e]) t -= kBig;
+            if (qi == kis[e]) t -= kSelf;
+            if (p.masked && kis[e] < 0.f) t -= kBig;
+            pv[e] = fast_exp2(t);
+          }
+          l += (pv[0] + pv[1]) + (pv[2] + pv[3]);
+          pk[c4 >> 1] = pack_bf16(pv[0], pv[1]);
+          pk[(c4 >> 1) + 1] = pack_bf16(pv[2], pv[3]);
         }
-        l += (pv[0] + pv[1]) + (pv[2] + pv[3]);
-        pk[c4 >> 1] = pack_bf16(pv[0], pv[1]);
-        pk[(c4 >> 1) + 1] = pack_bf16(pv[2], pv[3]);
+        tmem_st16(t_lane + kc * 16, pk);
       }
-      tmem_st16(t_lane + k * 16, pk);
-    }
-    tmem_st_wait();
-    tc_fence_before();
-    mbar_arrive(&sh.bar_p);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&sh.p_full[w]);
 
-    // ---- epilogue: O / l -> bf16 row, written straight to its ticker slot (EA:1985-1986) ---------------
-    mbar_wait(&sh.bar_o, 0);
-    tc_fence_after();
-    const float il = 1.f / l;
-    const int tk = sh.tkq[row];
-    const int round = tk / p.L, pos = tk - round * p.L;
-    __nv_bfloat16 *dst = p.o + b * p.o_sb + h * p.o_sh + round * p.o_sr + pos * p.o_sp;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      uint32_t r[32];
-      tmem_ld32(t_lane + 128 + half * 32, r);
+      // ---- epilogue ----------------------------------------------------------------------------------
+      const int u = wk.u, b = u / p.H, h = u - b * p.H;
+      const int round = tk / p.L, pos = tk - round * p.L;
+      __nv_bfloat16 *dst = p.o + b * p.o_sb + h * p.o_sh + round * p.o_sr + pos * p.o_sp;
+      const float il = l > 0.f ? 1.f / l : 0.f;
+      const float lse = l > 0.f ? (m2 + log2f(l)) * kLn2 : -3e9f;
+      mbar_wait(&sh.o_full[w], j & 1);
+      tc_fence_after();
+      uint32_t r0[32], r1[32];
+      tmem_ld32(t_lane + 128, r0);
+      tmem_ld32(t_lane + 160, r1);
       tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&sh.s_free[w]);                           // region w may be overwritten by the next S
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
         uint4 v;
-        v.x = pack_bf16(__uint_as_float(r[8 * q4 + 0]) * il, __uint_as_float(r[8 * q4 + 1]) * il);
-        v.y = pack_bf16(__uint_as_float(r[8 * q4 + 2]) * il, __uint_as_float(r[8 * q4 + 3]) * il);
-        v.z = pack_bf16(__uint_as_float(r[8 * q4 + 4]) * il, __uint_as_float(r[8 * q4 + 5]) * il);
-        v.w = pack_bf16(__uint_as_float(r[8 * q4 + 6]) * il, __uint_as_float(r[8 * q4 + 7]) * il);
-        *reinterpret_cast<uint4 *>(dst + half * 32 + q4 * 8) = v;
+        v.x = pack_bf16(__uint_as_float(r0[8 * q4 + 0]) * il, __uint_as_float(r0[8 * q4 + 1]) * il);
+        v.y = pack_bf16(__uint_as_float(r0[8 * q4 + 2]) * il, __uint_as_float(r0[8 * q4 + 3]) * il);
+        v.z = pack_bf16(__uint_as_float(r0[8 * q4 + 4]) * il, __uint_as_float(r0[8 * q4 + 5]) * il);
+        v.w = pack_bf16(__uint_as_float(r0[8 * q4 + 6]) * il, __uint_as_float(r0[8 * q4 + 7]) * il);
+        *reinterpret_cast<uint4 *>(dst + q4 * 8) = v;
+        v.x = pack_bf16(__uint_as_float(r1[8 * q4 + 0]) * il, __uint_as_float(r1[8 * q4 + 1]) * il);
+        v.y = pack_bf16(__uint_as_float(r1[8 * q4 + 2]) * il, __uint_as_float(r1[8 * q4 + 3]) * il);
+        v.z = pack_bf16(__uint_as_float(r1[8 * q4 + 4]) * il, __uint_as_float(r1[8 * q4 + 5]) * il);
+        v.w = pack_bf16(__uint_as_float(r1[8 * q4 + 6]) * il, __uint_as_float(r1[8 * q4 + 7]) * il);
+        *reinterpret_cast<uint4 *>(dst + 32 + q4 * 8) = v;
       }
+      p.lse[static_cast<int64_t>(u) * p.N + tk] = lse;
     }
-    p.lse[static_cast<int64_t>(u) * p.N + tk] = (m + log2f(l)) * kLn2;
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, TC_TMEM_COLS);
+  if (warp == 3) tmem_dealloc(tmem, 512);
 }
 
 int attend_fwd_tc_run(const AttendFwdParams &p, int BH, cudaStream_t stream) {
-  // > 76 KB so that at most two CTAs (2 x 256 TMEM columns) are resident per SM
-  const size_t smem = 2 * TC_W * 128 + sizeof(TcShared) + 1024 + 12 * 1024;
+  const size_t smem = static_cast<size_t>(TC_NST) * TC_TILE_BYTES + sizeof(TcShared) + 1024;
   LSH_OPT_IN_SMEM(attend_fwd_tc_kernel);
-  attend_fwd_tc_kernel<<<BH * p.n_chunks, TC_THREADS, smem, stream>>>(p);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int total = BH * p.n_chunks;
+  const int grid = total < sms ? total : sms;
+  attend_fwd_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(p, total);
   LSH_CHECK_LAUNCH("attend_fwd_tc_kernel");
   return 0;
 }
