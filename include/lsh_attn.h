@@ -93,8 +93,10 @@ int lsh_sort(const LshAttnDims *dims, const int32_t *buckets, int64_t buckets_st
 /* EA:1958-1986: gather by sticker, `attend` (EA:163-268) with look-back window, masks
  * (EA:145-160), per-row log-sum-exp, and the un-sort of EA:1985-1986 (rows are written straight to
  * their ticker slot).  o_rounds may alias o_comb's layout when nh==1 via lsh_attend_fwd_strided. */
+size_t lsh_attend_fwd_workspace_bytes(const LshAttnDims *dims);
 int lsh_attend_fwd(const LshAttnDims *dims, const void *qv_bf16, const int32_t *sticker,
-                   const uint8_t *mask, void *o_rounds_bf16, float *logits, void *stream);
+                   const uint8_t *mask, void *o_rounds_bf16, float *logits, void *ws, size_t ws_bytes,
+                   void *stream);
 
 /* EA:1988-1992 multi-round combine; also emits lse_tot = logsumexp_h(logits) (BH, L) when non-null. */
 int lsh_combine_fwd(const LshAttnDims *dims, const void *o_rounds_bf16, const float *logits,

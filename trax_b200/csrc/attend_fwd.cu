@@ -13,6 +13,8 @@
 
 namespace lsh {
 
+long long *g_fwd_trace = nullptr;   // set through lsh_debug_set_trace (profiling aid)
+
 template <int C>
 __global__ void __launch_bounds__(2 * C) attend_fwd_kernel(const AttendFwdParams p) {
   constexpr int NT = 2 * C;            // threads
@@ -207,18 +209,21 @@ static int launch_attend_fwd(const AttendFwdParams &p, int BH, cudaStream_t stre
 
 int attend_fwd_run(const LshAttnDims &d, const void *qv, const int32_t *sticker, const uint8_t *mask,
                    void *o, int64_t o_sb, int64_t o_sh, int64_t o_sr, int64_t o_sp, float *lse,
-                   cudaStream_t stream) {
+                   const float *qscale, cudaStream_t stream) {
   Derived dr = derive(d);
   AttendFwdParams p;
   p.qv = static_cast<const __nv_bfloat16 *>(qv); p.sticker = sticker;
   p.mask = d.masked ? mask : nullptr; p.o = static_cast<__nv_bfloat16 *>(o);
-  p.o_sb = o_sb; p.o_sh = o_sh; p.o_sr = o_sr; p.o_sp = o_sp; p.lse = lse;
+  p.o_sb = o_sb; p.o_sh = o_sh; p.o_sr = o_sr; p.o_sp = o_sp; p.lse = lse; p.qscale = qscale; p.trace = g_fwd_trace;
   p.L = d.L; p.H = d.H; p.N = dr.N; p.n_chunks = dr.n_chunks; p.nb = d.nb; p.nwin = dr.nwin;
   p.causal = d.causal; p.masked = d.masked;
   if (d.masked && !mask) return set_error("attend_fwd: dims.masked set but mask == NULL");
   // tcgen05 path for the long-sequence shape (chunk 128, 2-chunk window); LSH_ATTN_FWD=mma forces the mma.sync path
   static const bool force_mma = [] { const char *e = getenv("LSH_ATTN_FWD"); return e && strcmp(e, "mma") == 0; }();
-  if (d.C == 128 && dr.nwin == 2 && !force_mma) return attend_fwd_tc_run(p, dr.BH, stream);
+  if (d.C == 128 && dr.nwin == 2 && !force_mma) {
+    if (!qscale) return set_error("attend_fwd: the tcgen05 path needs the qscale workspace");
+    return attend_fwd_tc_run(p, dr.BH, stream);
+  }
   switch (d.C) {
     case 32: return launch_attend_fwd<32>(p, dr.BH, stream);
     case 64: return launch_attend_fwd<64>(p, dr.BH, stream);

@@ -11,6 +11,8 @@ struct AttendFwdParams {
   __nv_bfloat16 *o;             // rows addressed as b*o_sb + h*o_sh + round*o_sr + pos*o_sp
   int64_t o_sb, o_sh, o_sr, o_sp;
   float *lse;                   // (BH, N) ticker order
+  const float *qscale;          // (BH, L) per-token key scale (tcgen05 path only)
+  long long *trace;             // debug: per-phase clock64 stamps of CTA 0 (null = off)
   int L, H, N, n_chunks, nb, nwin, causal, masked;
 };
 

@@ -99,6 +99,41 @@ int bwd_prep_run(const LshAttnDims &d, const void *do_comb, const void *o_comb, 
   return 0;
 }
 
+// qscale[u][t] = log2(e) / (sqrt(mean(q^2) + 1e-6) * sqrt(dq))  — the per-key factor of EA:54-57, 229-231 folded with
+// the exp2 conversion; one value per (unit, token), consumed by the tcgen05 attention kernels.
+__global__ void __launch_bounds__(ROW_THREADS) qscale_kernel(const __nv_bfloat16 *__restrict__ qv,
+                                                            float *__restrict__ qscale, int L, int H,
+                                                            int64_t total_rows) {
+  const int64_t row = (static_cast<int64_t>(blockIdx.x) * ROW_THREADS + threadIdx.x) >> 3;   // (b, t, h)
+  const int ch = threadIdx.x & 7;
+  const bool ok = row < total_rows;
+  float s = 0.f;
+  if (ok) {
+    float a[8];
+    bf16x8_to_f32(__ldg(reinterpret_cast<const uint4 *>(qv + row * 128) + ch), a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s = fmaf(a[i], a[i], s);
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  if (ok && ch == 0) {
+    const int64_t h = row % H, bt = row / H;
+    const int64_t b = bt / L, t = bt % L;
+    qscale[(b * H + h) * L + t] = 0.125f * kLog2e / sqrtf(s * (1.0f / 64) + 1e-6f);
+  }
+}
+
+int qscale_run(const LshAttnDims &d, const void *qv, float *qscale, cudaStream_t stream) {
+  Derived dr = derive(d);
+  const int64_t rows = static_cast<int64_t>(dr.BH) * d.L;
+  const int64_t blocks = (rows * 8 + ROW_THREADS - 1) / ROW_THREADS;
+  qscale_kernel<<<static_cast<unsigned>(blocks), ROW_THREADS, 0, stream>>>(static_cast<const __nv_bfloat16 *>(qv), qscale,
+                                                                          d.L, d.H, rows);
+  LSH_CHECK_LAUNCH("qscale_kernel");
+  return 0;
+}
+
 // dqv[b,t,h,0:64]   = sum_r sum_kind dq_part[kind][u][r*L+t][:]
 // dqv[b,t,h,64:128] = sum_r dv_part[u][r*L+t][:]
 __global__ void __launch_bounds__(ROW_THREADS) sum_rounds_kernel(

@@ -41,7 +41,11 @@ inline Derived derive(const LshAttnDims &d) {
     int dev_ = 0;                                                                                    \
     cudaGetDevice(&dev_);                                                                            \
     if (done_dev_ != dev_) {                                                                         \
-      cudaError_t e_ = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
+      cudaFuncAttributes fa_;                                                                        \
+      cudaError_t e_ = cudaFuncGetAttributes(&fa_, kernel);                                          \
+      if (e_ == cudaSuccess)                                                                         \
+        e_ = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,               \
+                                  227 * 1024 - static_cast<int>(fa_.sharedSizeBytes));               \
       if (e_ != cudaSuccess) return lsh::set_error("cudaFuncSetAttribute(%s): %s", #kernel, cudaGetErrorString(e_)); \
       done_dev_ = dev_;                                                                              \
     }                                                                                                \
@@ -63,6 +67,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) {
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src));
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(src));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>

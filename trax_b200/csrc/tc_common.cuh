@@ -16,12 +16,28 @@ __device__ __forceinline__ void fence_mbar_init() {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+// Potentially-blocking probe: the hardware suspends the thread until the phase completes or `hint_ns` expires
+// (wake-up on completion is immediate), so a waiting warp neither burns issue slots nor oversleeps.
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity, uint32_t hint_ns = 20000) {
   uint32_t ok;
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
+// non-blocking probe
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t"
       "}\n"
       : "=r"(ok)
@@ -29,11 +45,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+template <int SLEEP_NS = 0>
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  // bounded spin: a protocol bug becomes a trap (launch failure) instead of a hung GPU
+#ifdef LSH_DEBUG_SPIN
   uint32_t spins = 0;
+#endif
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) __trap();
+    if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
+#ifdef LSH_DEBUG_SPIN
+    if (++spins > (1u << 22)) __trap();   // a protocol bug becomes a trap instead of a hung GPU
+#endif
   }
 }
 // generic-proxy writes (st.shared / cp.async) -> visible to the async proxy (tcgen05.mma operand reads)
@@ -111,6 +132,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+// Same wait, but data-dependent on the destination registers of an earlier (prefetched) tcgen05.ld so that
+// the compiler cannot hoist their uses above the wait.
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n" ::"r"(taddr),

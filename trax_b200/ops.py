@@ -112,8 +112,9 @@ def attend_fwd(dims, qv, sticker, mask=None):
   bh, n = dims.B * dims.H, dims.nh * dims.L
   o = torch.empty((bh, n, dims.dv), dtype=torch.bfloat16, device=qv.device)
   logits = torch.empty((bh, n), dtype=torch.float32, device=qv.device)
+  ws = workspace(qv.device, lib.lsh_attend_fwd_workspace_bytes(ctypes.byref(dims)))
   _lib.check(lib.lsh_attend_fwd(ctypes.byref(dims), _ptr(qv), _ptr(sticker), _ptr(mask), _ptr(o), _ptr(logits),
-                                _stream()), 'lsh_attend_fwd')
+                                _ptr(ws), ws.numel(), _stream()), 'lsh_attend_fwd')
   return o, logits
 
 
