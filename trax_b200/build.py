@@ -10,6 +10,8 @@ LIB = os.path.join(HERE, 'liblsh_attn_b200.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 FLAGS = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC', '--use_fast_math=false']
+if os.environ.get('LSH_DEBUG_SPIN'):
+  FLAGS.append('-DLSH_DEBUG_SPIN')   # barrier waits trap instead of hanging (kernel bring-up)
 
 
 def _cublas_dirs():

@@ -11,7 +11,10 @@
 // P^T / dS^T are already A-operand fragments for the dV / dK^ products.  dS^T goes through shared
 // memory once for dQ = dS·k^.  dQ partials are written per window slot ("kind"); sum_rounds_kernel
 // adds kinds and hash rounds (App. B6) — deterministic, no atomics.
-#include "common.cuh"
+#include <stdlib.h>
+#include <string.h>
+
+#include "attend_bwd_params.cuh"
 
 namespace lsh {
 
@@ -280,7 +283,7 @@ size_t attend_bwd_workspace_bytes(const LshAttnDims &d) {
   Derived dr = derive(d);
   size_t rows = static_cast<size_t>(dr.BH) * dr.N;
   size_t b = rows * 64 * 2 * (dr.nwin + 2);       // dq kinds (nwin+1) + dv
-  b += static_cast<size_t>(dr.BH) * d.L * 4;      // dvec
+  b += static_cast<size_t>(dr.BH) * d.L * 4 * 4 + 1024;   // dvec, lse2, qcmp, qscale
   return (b + 255) / 256 * 256 + 512;
 }
 
@@ -288,10 +291,13 @@ int bwd_prep_run(const LshAttnDims &d, const void *do_comb, const void *o_comb, 
                  cudaStream_t stream);
 int sum_rounds_run(const LshAttnDims &d, const void *dq_part, const void *dv_part, void *dqv,
                    int n_kinds, cudaStream_t stream);
+int bwd_prep_tc_run(const LshAttnDims &d, const void *do_comb, const void *o_comb, const float *lse_tot, float *dvec,
+                    float *lse2, float *qcmp, cudaStream_t stream);
+int qscale_run(const LshAttnDims &d, const void *qv, float *qscale, cudaStream_t stream);
 
 int attend_bwd_run(const LshAttnDims &d, const void *qv, const int32_t *sticker, const uint8_t *mask,
-                   const void *o_comb, const float *lse_tot, const void *do_comb, void *dqv, void *ws,
-                   size_t ws_bytes, cudaStream_t stream) {
+                   const void *o_comb, const float *lse_tot, const void *do_comb, const float *qscale_in, void *dqv,
+                   void *ws, size_t ws_bytes, cudaStream_t stream) {
   Derived dr = derive(d);
   if (ws_bytes < attend_bwd_workspace_bytes(d))
     return set_error("lsh_attend_bwd: workspace too small (%zu < %zu)", ws_bytes, attend_bwd_workspace_bytes(d));
@@ -304,7 +310,27 @@ int attend_bwd_run(const LshAttnDims &d, const void *qv, const int32_t *sticker,
   w += rows * 64 * 2;
   w = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(w) + 255) / 256 * 256);
   float *dvec = reinterpret_cast<float *>(w);
-  int rc = bwd_prep_run(d, do_comb, o_comb, dvec, stream);
+  const size_t tok = (static_cast<size_t>(dr.BH) * d.L * 4 + 255) / 256 * 256;
+  float *lse2 = reinterpret_cast<float *>(w + tok), *qcmp = reinterpret_cast<float *>(w + 2 * tok);
+  float *qscale_ws = reinterpret_cast<float *>(w + 3 * tok);
+  int rc;
+  // tcgen05 path for the long-sequence shape; LSH_ATTN_BWD=mma forces the mma.sync path
+  static const bool force_mma = [] { const char *e = getenv("LSH_ATTN_BWD"); return e && strcmp(e, "mma") == 0; }();
+  if (d.C == 128 && d.nb == 1 && d.na == 0 && d.causal && !d.masked && !force_mma) {
+    const float *qscale = qscale_in;
+    if (!qscale) {
+      if ((rc = qscale_run(d, qv, qscale_ws, stream))) return rc;
+      qscale = qscale_ws;
+    }
+    if ((rc = bwd_prep_tc_run(d, do_comb, o_comb, lse_tot, dvec, lse2, qcmp, stream))) return rc;
+    AttendBwdTcParams t;
+    t.qv = static_cast<const __nv_bfloat16 *>(qv); t.sticker = sticker;
+    t.do_comb = static_cast<const __nv_bfloat16 *>(do_comb); t.qscale = qscale; t.lse2 = lse2; t.dvec = dvec; t.qcmp = qcmp;
+    t.dq_out = dq_part; t.dv_out = dv_part; t.L = d.L; t.H = d.H; t.N = dr.N; t.n_chunks = dr.n_chunks;
+    if ((rc = attend_bwd_tc_run(t, dr.BH, stream))) return rc;
+    return sum_rounds_run(d, dq_part, dv_part, dqv, 1, stream);
+  }
+  rc = bwd_prep_run(d, do_comb, o_comb, dvec, stream);
   if (rc) return rc;
   AttendBwdParams p;
   p.qv = static_cast<const __nv_bfloat16 *>(qv); p.sticker = sticker; p.mask = d.masked ? mask : nullptr;

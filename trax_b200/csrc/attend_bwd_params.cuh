@@ -1,0 +1,22 @@
+// Parameter block of the tcgen05 backward attention kernel.
+#pragma once
+#include "common.cuh"
+
+namespace lsh {
+
+struct AttendBwdTcParams {
+  const __nv_bfloat16 *qv;        // (B, L, H, 128)
+  const int32_t *sticker;         // (BH, N)
+  const __nv_bfloat16 *do_comb;   // (B, L, H, 64)
+  const float *qscale;            // (BH, L)  log2e / (sqrt(mean(q^2)+eps) sqrt(dq))
+  const float *lse2;              // (BH, L)  log2e * lse_tot (+ log2e*1e5 for self-only rows)
+  const float *dvec;              // (BH, L)  do . o
+  const float *qcmp;              // (BH, L)  pos + 1 (+ 0.5 for self-only rows)
+  __nv_bfloat16 *dq_out;          // (BH, N, 64) ticker order: dq_query + dq_key of every token copy
+  __nv_bfloat16 *dv_out;          // (BH, N, 64)
+  int L, H, N, n_chunks;
+};
+
+int attend_bwd_tc_run(const AttendBwdTcParams &p, int BH, cudaStream_t stream);
+
+}  // namespace lsh

@@ -1,0 +1,443 @@
+// Chunked look-back attention, backward, on tcgen05 + TMEM.  Same math as attend_bwd.cu (SURVEY App. B with
+// the multi-round combine folded in); specialised for chunk_len 128, n_chunks_before = 1, n_chunks_after = 0,
+// causal, no padding mask, dq = dv = 64 (every long-sequence config).
+//
+// KEY-centric persistent walk: one CTA per SM owns a contiguous range of key chunks.  For key chunk t it visits
+// the two query chunks that see it (t itself and t+1), 64 queries ("half") at a time, in the transposed
+// orientation so that the softmax threads own KEY rows (TMEM lane = key row):
+//     S^T  = K_t Q^T           dP^T = V_t dO^T                       (tcgen05.mma SS, M128 N64 K64)
+//     P^T  = [k_j < q_i] exp2(S^T ksc_j - lse2_i) ;  dS^T = P^T (dP^T - D_i)     (softmax warpgroups, in place)
+//     dV  += P^T dO   ;  dK^ += dS^T Q                                (tcgen05.mma TS, A from TMEM)
+//     dQ  += (dS ksc) K_t      (A = dS staged in shared memory, MN-major)         (tcgen05.mma SS)
+// dK^ / dV of chunk t are complete after its two query chunks (no atomics, no partial buffers); dQ of chunk t
+// collects keys t-1 (previous iteration) and t (this iteration) in one of two TMEM slots.  Because queries
+// and keys are the same tokens (shared-QK), thread j ends up holding dq_query, dq_key and dv of ONE token and
+// writes single rows.  Range / unit boundaries replay one "pre" item (keys t-1 x queries t, dQ only).
+//
+// TMEM (512 columns): region h (h = query half): S^T [128h,+64) -> P^T bf16 [128h,+32); dP^T [128h+64,+64) ->
+// dS^T bf16 [128h+64,+32); dK^ [256,320); dV [320,384); dQ slots [384,448), [448,512).
+// Warps: 0-3 softmax warpgroup 0 (half 0), 4-7 warpgroup 1 (half 1), 8-11 producers, 12 MMA issuer.
+#include "attend_bwd_params.cuh"
+#include "tc_common.cuh"
+
+namespace lsh {
+
+constexpr int BT_C = 128;
+constexpr int BT_NST = 3;                         // tile ring depth
+constexpr int BT_THREADS = 416;
+constexpr int BT_TILE_BYTES = 3 * BT_C * 128;     // K(=Q) rows | V rows | dO rows
+constexpr int BT_DS_BYTES = 2 * BT_C * 128;       // one dS staging buffer: two 64-query blocks of [128 keys][128 B]
+constexpr uint32_t BT_IDESC_ST = make_idesc_bf16(128, 64, 0, 0);   // S^T, dP^T
+constexpr uint32_t BT_IDESC_KV = make_idesc_bf16(128, 64, 0, 1);   // dV, dK^ (B MN-major)
+constexpr uint32_t BT_IDESC_DQ = make_idesc_bf16(128, 64, 1, 1);   // dQ (A and B MN-major)
+
+struct __align__(16) BtTileMeta {
+  float kinfo[BT_C];    // pos + 1 as fp32 (key side of the causal compare)
+  float qcmp[BT_C];     // pos + 1, or pos + 1.5 for rows whose only visible key is their own "-1e5" class
+  float lse2[BT_C];     // log2(e) * lse_tot (+ the -1e5 class shift for those rows)
+  float dvec[BT_C];     // D_i = do_i . o_i
+  float kscl[BT_C];     // log2(e) / (sqrt(mean(q^2)+eps) * sqrt(dq))
+  int tk[BT_C];         // ticker
+};
+
+struct __align__(16) BtShared {
+  BtTileMeta meta[BT_NST];
+  uint64_t full[BT_NST], empty[BT_NST];
+  uint64_t st_full[2], pds_full[2], dsm_free[2], dq_full[2];
+  uint64_t kv_full, kv_free;
+  uint32_t tmem_base;
+};
+
+// One (key tile, query tile) product group.
+struct BtItem {
+  int seq_k, seq_q;       // tile sequence numbers
+  int u;                  // unit of the key chunk
+  int n;                  // global item index (barrier phases)
+  int rit;                // index of the real iteration this item belongs to (or the upcoming one for a pre item)
+  bool real, first, iter_end, last_seg;   // first = first item of its iteration
+  bool do_kv, kv_first, do_dq, dq_fresh;
+  int dq_slot;
+};
+
+// Enumerates iterations / items / tiles of one CTA's range of key chunks [g0, g1).
+struct BtWalk {
+  int g, g_end, nc, seq, rit, n;
+  bool need_pre, second;      // second = item B of a real iteration comes next
+  __device__ BtWalk(int g0, int g1, int nchunks)
+      : g(g0), g_end(g1), nc(nchunks), seq(0), rit(0), n(0), need_pre(true), second(false) {}
+  __device__ bool valid() const { return g < g_end; }
+  __device__ bool seg_last() const { const int c = g % nc; return g == g_end - 1 || c == nc - 1; }
+  __device__ BtItem item() const {
+    BtItem it;
+    it.u = g / nc; it.n = n; it.rit = rit; it.seq_k = seq;
+    if (need_pre) {
+      it.seq_q = seq + 1; it.real = false; it.first = true; it.iter_end = true; it.last_seg = false;
+      it.do_kv = false; it.kv_first = false; it.do_dq = true; it.dq_fresh = true; it.dq_slot = rit & 1;
+    } else if (!second) {
+      it.seq_q = seq; it.real = true; it.first = true; it.iter_end = false; it.last_seg = seg_last();
+      it.do_kv = true; it.kv_first = true; it.do_dq = true; it.dq_fresh = false; it.dq_slot = rit & 1;
+    } else {
+      it.seq_q = seq + 1; it.real = true; it.first = false; it.iter_end = true; it.last_seg = seg_last();
+      it.do_kv = true; it.kv_first = false; it.do_dq = !it.last_seg; it.dq_fresh = true; it.dq_slot = (rit + 1) & 1;
+    }
+    return it;
+  }
+  __device__ void next() {
+    ++n;
+    if (need_pre) { need_pre = false; seq += 1; return; }
+    if (!second) { second = true; return; }
+    second = false;
+    const bool last = seg_last();
+    seq += last ? 2 : 1;
+    need_pre = last;
+    ++rit; ++g;
+  }
+  // chunk ids (within the unit) of the key tile and of the next tile of the current iteration
+  __device__ void chunks(int &c_key, int &c_next) const {
+    const int c = g % nc;
+    if (need_pre) { c_key = (c + nc - 1) % nc; c_next = c; } else { c_key = c; c_next = (c + 1) % nc; }
+  }
+};
+
+__device__ __forceinline__ uint32_t bt_slot(int seq) { return static_cast<uint32_t>(seq % BT_NST); }
+__device__ __forceinline__ uint32_t bt_phase(int seq) { return static_cast<uint32_t>((seq / BT_NST) & 1); }
+
+__global__ void __launch_bounds__(BT_THREADS, 1) attend_bwd_tc_kernel(const AttendBwdTcParams p, int total_chunks) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t *tiles = smem;                                   // [BT_NST][K | V | dO]
+  uint8_t *dsbuf = smem + BT_NST * BT_TILE_BYTES;          // [2][BT_DS_BYTES]
+  __shared__ BtShared sh;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g0 = static_cast<int>(static_cast<int64_t>(total_chunks) * blockIdx.x / gridDim.x);
+  const int g1 = static_cast<int>(static_cast<int64_t>(total_chunks) * (blockIdx.x + 1) / gridDim.x);
+
+  if (warp == 12) tmem_alloc(&sh.tmem_base, 512);
+  if (tid == 0) {
+    for (int i = 0; i < BT_NST; ++i) { mbar_init(&sh.full[i], 128); mbar_init(&sh.empty[i], 257); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sh.st_full[i], 1); mbar_init(&sh.pds_full[i], 128);
+      mbar_init(&sh.dsm_free[i], 1); mbar_init(&sh.dq_full[i], 1);
+    }
+    mbar_init(&sh.kv_full, 1); mbar_init(&sh.kv_free, 256);
+    fence_mbar_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sh.tmem_base;
+  const uint32_t tiles_u32 = smem_u32(tiles), ds_u32 = smem_u32(dsbuf);
+
+  if (warp >= 8 && warp < 12) {
+    // ================================ producers ========================================================
+    const int pw = warp - 8;                               // rows [32*pw, 32*pw + 32) of every tile
+    int prev_slot = -1;
+    auto load_tile = [&](int seq, int u, int cc) {
+      const uint32_t slot = bt_slot(seq);
+      const int b = u / p.H, h = u - b * p.H;
+      const int row = 32 * pw + lane;
+      const int tk = __ldg(p.sticker + static_cast<int64_t>(u) * p.N + cc * BT_C + row);
+      const int pos = tk % p.L;
+      mbar_wait<128>(&sh.empty[slot], bt_phase(seq) ^ 1);
+      BtTileMeta &mt = sh.meta[slot];
+      mt.kinfo[row] = static_cast<float>(pos + 1);
+      mt.tk[row] = tk;
+      const int64_t tokoff = static_cast<int64_t>(u) * p.L + pos;
+      cp_async4(smem_u32(&mt.kscl[row]), p.qscale + tokoff);
+      cp_async4(smem_u32(&mt.lse2[row]), p.lse2 + tokoff);
+      cp_async4(smem_u32(&mt.dvec[row]), p.dvec + tokoff);
+      cp_async4(smem_u32(&mt.qcmp[row]), p.qcmp + tokoff);
+      const uint32_t kt = tiles_u32 + slot * BT_TILE_BYTES, vt = kt + BT_C * 128, dt = vt + BT_C * 128;
+      {   // q|v rows: 16 lanes per 256-byte row, 2 rows per instruction
+        const int ch = lane & 15, hi = lane >> 4;
+        const __nv_bfloat16 *base = p.qv + (static_cast<int64_t>(b) * p.L * p.H + h) * 128 + ch * 8;
+#pragma unroll 4
+        for (int i = 0; i < 16; ++i) {
+          const int rel = 2 * i + hi;
+          const int pr = __shfl_sync(0xffffffffu, pos, rel);
+          cp_async16((ch < 8 ? kt : vt) + swz(32 * pw + rel, ch & 7), base + static_cast<int64_t>(pr) * p.H * 128);
+        }
+      }
+      {   // do rows: 8 lanes per 128-byte row, 4 rows per instruction
+        const int ch = lane & 7, hi = lane >> 3;
+        const __nv_bfloat16 *base = p.do_comb + (static_cast<int64_t>(b) * p.L * p.H + h) * 64 + ch * 8;
+#pragma unroll 4
+        for (int i = 0; i < 8; ++i) {
+          const int rel = 4 * i + hi;
+          const int pr = __shfl_sync(0xffffffffu, pos, rel);
+          cp_async16(dt + swz(32 * pw + rel, ch), base + static_cast<int64_t>(pr) * p.H * 64);
+        }
+      }
+      cp_async_commit();
+      if (prev_slot >= 0) {
+        cp_async_wait<1>();
+        fence_proxy_async();
+        mbar_arrive(&sh.full[prev_slot]);
+      }
+      prev_slot = static_cast<int>(slot);
+    };
+    for (BtWalk w(g0, g1, p.n_chunks); w.valid();) {
+      const BtItem it = w.item();
+      if (it.first) {               // one visit per iteration: a pre iteration brings two tiles, a real one brings one
+        int c_key, c_next;
+        w.chunks(c_key, c_next);
+        if (!it.real) load_tile(it.seq_k, it.u, c_key);
+        load_tile(it.seq_k + 1, it.u, c_next);
+      }
+      w.next();
+    }
+    if (prev_slot >= 0) {
+      cp_async_wait<0>();
+      fence_proxy_async();
+      mbar_arrive(&sh.full[prev_slot]);
+    }
+  } else if (warp == 12) {
+    // ================================ MMA issuer =======================================================
+    if (lane == 0) {
+      auto tile_addr = [&](int seq) { return tiles_u32 + bt_slot(seq) * BT_TILE_BYTES; };
+      // S^T and dP^T of one half of an item
+      auto issue_st = [&](const BtItem &it, int h) {
+        const uint32_t kt = tile_addr(it.seq_k), qt = tile_addr(it.seq_q);
+        const uint32_t r = tmem + 128 * h;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_ss(r, make_smem_desc(kt + ks * 32, 16, 1024), make_smem_desc(qt + h * 8192 + ks * 32, 16, 1024), BT_IDESC_ST, ks > 0);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_ss(r + 64, make_smem_desc(kt + BT_C * 128 + ks * 32, 16, 1024),
+                  make_smem_desc(qt + 2 * BT_C * 128 + h * 8192 + ks * 32, 16, 1024), BT_IDESC_ST, ks > 0);
+        umma_commit(&sh.st_full[h]);
+      };
+      auto wait_tiles = [&](const BtItem &it) {
+        mbar_wait(&sh.full[bt_slot(it.seq_k)], bt_phase(it.seq_k));
+        mbar_wait(&sh.full[bt_slot(it.seq_q)], bt_phase(it.seq_q));
+        fence_proxy_async();
+        tc_fence_after();
+      };
+      BtWalk w(g0, g1, p.n_chunks);
+      BtItem cur = w.item();
+      wait_tiles(cur);
+      issue_st(cur, 0);
+      issue_st(cur, 1);
+      while (true) {
+        w.next();
+        const bool have_next = w.valid();
+        BtItem nxt = cur;
+        if (have_next) nxt = w.item();
+        const uint32_t qt = tile_addr(cur.seq_q), kt = tile_addr(cur.seq_k);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(&sh.pds_full[h], cur.n & 1);
+          tc_fence_after();
+          if (cur.do_kv) {
+            if (cur.kv_first && h == 0) mbar_wait(&sh.kv_free, (cur.rit & 1) ^ 1);   // previous epilogue has drained dK^/dV/dQ
+            const uint32_t r = tmem + 128 * h;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_ts(tmem + 320, r + kk * 8, make_smem_desc(qt + 2 * BT_C * 128 + h * 8192 + kk * 2048, 1024, 1024), BT_IDESC_KV,
+                      !(cur.kv_first && h == 0 && kk == 0));
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_ts(tmem + 256, r + 64 + kk * 8, make_smem_desc(qt + h * 8192 + kk * 2048, 1024, 1024), BT_IDESC_KV,
+                      !(cur.kv_first && h == 0 && kk == 0));
+          }
+          if (have_next) {      // next item's S^T / dP^T for this half: the region is free once the MMAs above have read it
+            if (h == 0) wait_tiles(nxt);
+            issue_st(nxt, h);
+          }
+        }
+        if (cur.do_kv && cur.iter_end) umma_commit(&sh.kv_full);
+        if (cur.do_dq) {
+          fence_proxy_async();
+          const uint32_t a0 = ds_u32 + (cur.n & 1) * BT_DS_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_ss(tmem + 384 + 64 * cur.dq_slot, make_smem_desc(a0 + kk * 2048, 16384, 1024),
+                    make_smem_desc(kt + kk * 2048, 1024, 1024), BT_IDESC_DQ, !(cur.dq_fresh && kk == 0));
+        }
+        umma_commit(&sh.dsm_free[cur.n & 1]);
+        if (cur.real && !cur.iter_end) umma_commit(&sh.dq_full[cur.rit & 1]);     // dQ of this key chunk is final after item A
+        if (cur.iter_end) {
+          umma_commit(&sh.empty[bt_slot(cur.seq_k)]);
+          if (cur.real && cur.last_seg) umma_commit(&sh.empty[bt_slot(cur.seq_k + 1)]);
+        }
+        if (!have_next) break;
+        cur = nxt;
+      }
+    }
+    __syncwarp();
+  } else if (warp < 8) {
+    // ================================ softmax warpgroups ===============================================
+    const int h = warp >> 2;                               // query half handled by this warpgroup
+    const int row = (warp & 3) * 32 + lane;                // key row == TMEM lane
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    const uint32_t r_st = t_lane + 128 * h;
+    float ksc_j = 0.f, ki_j = 0.f;
+    for (BtWalk w(g0, g1, p.n_chunks); w.valid(); w.next()) {
+      const BtItem it = w.item();
+      const uint32_t slk = bt_slot(it.seq_k), slq = bt_slot(it.seq_q);
+      if (it.first) {
+        mbar_wait(&sh.full[slk], bt_phase(it.seq_k));
+        ksc_j = sh.meta[slk].kscl[row];
+        ki_j = sh.meta[slk].kinfo[row];
+      }
+      mbar_wait(&sh.full[slq], bt_phase(it.seq_q));
+      const BtTileMeta &mq = sh.meta[slq];
+      const float kst_j = ksc_j * kLn2;                    // true key scale 1/(r*sqrt(dq)) for the dQ operand
+      uint8_t *dsrow = dsbuf + (it.n & 1) * BT_DS_BYTES + h * (BT_C * 128);
+      mbar_wait(&sh.st_full[h], it.n & 1);
+      mbar_wait(&sh.dsm_free[it.n & 1], ((it.n >> 1) & 1) ^ 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < 64; cc += 32) {
+        uint32_t s[32], dp[32];
+        tmem_ld32(r_st + cc, s);
+        tmem_ld32(r_st + 64 + cc, dp);
+        tmem_ld_wait_dep(s);
+        tmem_ld_wait_dep(dp);
+        uint32_t pk_p[16], pk_ds[16];
+#pragma unroll
+        for (int c4 = 0; c4 < 32; c4 += 4) {
+          const int i0 = 64 * h + cc + c4;
+          const float4 qc = *reinterpret_cast<const float4 *>(&mq.qcmp[i0]);
+          const float4 ls = *reinterpret_cast<const float4 *>(&mq.lse2[i0]);
+          const float4 dv = *reinterpret_cast<const float4 *>(&mq.dvec[i0]);
+          const float p0 = ki_j < qc.x ? fast_exp2(fmaf(__uint_as_float(s[c4 + 0]), ksc_j, -ls.x)) : 0.f;
+          const float p1 = ki_j < qc.y ? fast_exp2(fmaf(__uint_as_float(s[c4 + 1]), ksc_j, -ls.y)) : 0.f;
+          const float p2 = ki_j < qc.z ? fast_exp2(fmaf(__uint_as_float(s[c4 + 2]), ksc_j, -ls.z)) : 0.f;
+          const float p3 = ki_j < qc.w ? fast_exp2(fmaf(__uint_as_float(s[c4 + 3]), ksc_j, -ls.w)) : 0.f;
+          const float d0 = p0 * (__uint_as_float(dp[c4 + 0]) - dv.x), d1 = p1 * (__uint_as_float(dp[c4 + 1]) - dv.y);
+          const float d2 = p2 * (__uint_as_float(dp[c4 + 2]) - dv.z), d3 = p3 * (__uint_as_float(dp[c4 + 3]) - dv.w);
+          pk_p[c4 >> 1] = pack_bf16(p0, p1);  pk_p[(c4 >> 1) + 1] = pack_bf16(p2, p3);
+          pk_ds[c4 >> 1] = pack_bf16(d0, d1); pk_ds[(c4 >> 1) + 1] = pack_bf16(d2, d3);
+          // reuse s[] as the staging copy (dS * key scale) for dQ
+          s[c4 >> 1] = pack_bf16(d0 * kst_j, d1 * kst_j);
+          s[(c4 >> 1) + 1] = pack_bf16(d2 * kst_j, d3 * kst_j);
+        }
+        tmem_st16(r_st + (cc >> 1), pk_p);
+        tmem_st16(r_st + 64 + (cc >> 1), pk_ds);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 v;
+          v.x = s[4 * q]; v.y = s[4 * q + 1]; v.z = s[4 * q + 2]; v.w = s[4 * q + 3];
+          *reinterpret_cast<uint4 *>(dsrow + swz(row, (cc >> 3) + q)) = v;
+        }
+      }
+      tmem_st_wait();
+      fence_proxy_async();                                 // dS staging writes -> UMMA (async proxy)
+      tc_fence_before();
+      mbar_arrive(&sh.pds_full[h]);
+
+      if (it.iter_end) {
+        if (it.real) {
+          // ---- epilogue of key chunk t: warpgroup 0 -> dq (query side + key side), warpgroup 1 -> dv -----------
+          const int tk = sh.meta[slk].tk[row];
+          const int64_t orow = (static_cast<int64_t>(it.u) * p.N + tk) * 64;
+          if (h == 0) {
+            mbar_wait(&sh.dq_full[it.rit & 1], (it.rit >> 1) & 1);
+            mbar_wait(&sh.kv_full, it.rit & 1);
+            tc_fence_after();
+            uint32_t dk0[32], dk1[32];
+            tmem_ld32(t_lane + 256, dk0);
+            tmem_ld32(t_lane + 288, dk1);
+            tmem_ld_wait_dep(dk0);
+            tmem_ld_wait_dep(dk1);
+            // raw q row of this key (length-normalisation VJP, App. B5)
+            const uint8_t *kt = tiles + slk * BT_TILE_BYTES;
+            float dot = 0.f;
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+              const uint4 raw = *reinterpret_cast<const uint4 *>(kt + swz(row, ch));
+              const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 q2 = unpack_bf16(rw[e]);
+                const int c = ch * 8 + e * 2;
+                const float a = __uint_as_float(c < 32 ? dk0[c] : dk1[c - 32]);
+                const float bq = __uint_as_float(c + 1 < 32 ? dk0[c + 1] : dk1[c + 1 - 32]);
+                dot = fmaf(a, q2.x, dot);
+                dot = fmaf(bq, q2.y, dot);
+              }
+            }
+            const float r_j = 0.125f * kLog2e / ksc_j;       // sqrt(mean(q^2) + eps)
+            const float a_j = 0.125f / r_j;
+            const float c_j = dot * 0.125f / (64.f * r_j * r_j * r_j);
+            uint32_t dq0[32], dq1[32];
+            tmem_ld32(t_lane + 384 + 64 * (it.rit & 1), dq0);
+            tmem_ld32(t_lane + 416 + 64 * (it.rit & 1), dq1);
+            tmem_ld_wait_dep(dq0);
+            tmem_ld_wait_dep(dq1);
+            tc_fence_before();
+            mbar_arrive(&sh.kv_free);
+            __nv_bfloat16 *dst = p.dq_out + orow;
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+              const uint4 raw = *reinterpret_cast<const uint4 *>(kt + swz(row, ch));
+              const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
+              uint32_t o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 q2 = unpack_bf16(rw[e]);
+                const int c = ch * 8 + e * 2;
+                const float k0 = __uint_as_float(c < 32 ? dk0[c] : dk1[c - 32]);
+                const float k1 = __uint_as_float(c + 1 < 32 ? dk0[c + 1] : dk1[c + 1 - 32]);
+                const float g0q = __uint_as_float(c < 32 ? dq0[c] : dq1[c - 32]);
+                const float g1q = __uint_as_float(c + 1 < 32 ? dq0[c + 1] : dq1[c + 1 - 32]);
+                o[e] = pack_bf16(g0q + k0 * a_j - q2.x * c_j, g1q + k1 * a_j - q2.y * c_j);
+              }
+              uint4 v; v.x = o[0]; v.y = o[1]; v.z = o[2]; v.w = o[3];
+              *reinterpret_cast<uint4 *>(dst + ch * 8) = v;
+            }
+          } else {
+            mbar_wait(&sh.kv_full, it.rit & 1);
+            tc_fence_after();
+            uint32_t v0[32], v1[32];
+            tmem_ld32(t_lane + 320, v0);
+            tmem_ld32(t_lane + 352, v1);
+            tmem_ld_wait_dep(v0);
+            tmem_ld_wait_dep(v1);
+            tc_fence_before();
+            mbar_arrive(&sh.kv_free);
+            __nv_bfloat16 *dst = p.dv_out + orow;
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              uint4 v;
+              v.x = pack_bf16(__uint_as_float(v0[8 * q4 + 0]), __uint_as_float(v0[8 * q4 + 1]));
+              v.y = pack_bf16(__uint_as_float(v0[8 * q4 + 2]), __uint_as_float(v0[8 * q4 + 3]));
+              v.z = pack_bf16(__uint_as_float(v0[8 * q4 + 4]), __uint_as_float(v0[8 * q4 + 5]));
+              v.w = pack_bf16(__uint_as_float(v0[8 * q4 + 6]), __uint_as_float(v0[8 * q4 + 7]));
+              *reinterpret_cast<uint4 *>(dst + q4 * 8) = v;
+              v.x = pack_bf16(__uint_as_float(v1[8 * q4 + 0]), __uint_as_float(v1[8 * q4 + 1]));
+              v.y = pack_bf16(__uint_as_float(v1[8 * q4 + 2]), __uint_as_float(v1[8 * q4 + 3]));
+              v.z = pack_bf16(__uint_as_float(v1[8 * q4 + 4]), __uint_as_float(v1[8 * q4 + 5]));
+              v.w = pack_bf16(__uint_as_float(v1[8 * q4 + 6]), __uint_as_float(v1[8 * q4 + 7]));
+              *reinterpret_cast<uint4 *>(dst + 32 + q4 * 8) = v;
+            }
+          }
+        }
+        // this thread is done with the key tile (and, at a segment end, with the trailing query tile)
+        mbar_arrive(&sh.empty[slk]);
+        if (it.real && it.last_seg) mbar_arrive(&sh.empty[bt_slot(it.seq_k + 1)]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) tmem_dealloc(tmem, 512);
+}
+
+int attend_bwd_tc_run(const AttendBwdTcParams &p, int BH, cudaStream_t stream) {
+  const size_t smem = static_cast<size_t>(BT_NST) * BT_TILE_BYTES + 2 * BT_DS_BYTES + 1024;
+  LSH_OPT_IN_SMEM(attend_bwd_tc_kernel);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int total = BH * p.n_chunks;
+  const int grid = total < sms ? total : sms;
+  attend_bwd_tc_kernel<<<grid, BT_THREADS, smem, stream>>>(p, total);
+  LSH_CHECK_LAUNCH("attend_bwd_tc_kernel");
+  return 0;
+}
+
+}  // namespace lsh

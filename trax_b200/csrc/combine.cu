@@ -99,6 +99,51 @@ int bwd_prep_run(const LshAttnDims &d, const void *do_comb, const void *o_comb, 
   return 0;
 }
 
+// Token-level inputs of the tcgen05 backward kernel: D = do.o, lse2 = log2e*lse_tot and the causal compare value.
+// Rows whose log-sum-exp sits at the "-1e5" level saw only their own key class (EA:153-155): they keep exactly
+// that class (compare against pos + 1.5) and their shift absorbs the 1e5 again.
+__global__ void __launch_bounds__(ROW_THREADS) bwd_prep_tc_kernel(
+    const __nv_bfloat16 *__restrict__ do_comb, const __nv_bfloat16 *__restrict__ o_comb,
+    const float *__restrict__ lse_tot, float *__restrict__ dvec, float *__restrict__ lse2,
+    float *__restrict__ qcmp, int L, int H, int64_t total_rows) {
+  const int64_t row = (static_cast<int64_t>(blockIdx.x) * ROW_THREADS + threadIdx.x) >> 3;   // (b,t,h)
+  const int ch = threadIdx.x & 7;
+  const bool ok = row < total_rows;
+  float s = 0.f;
+  if (ok) {
+    float a[8], c[8];
+    bf16x8_to_f32(__ldg(reinterpret_cast<const uint4 *>(do_comb + row * 64) + ch), a);
+    bf16x8_to_f32(__ldg(reinterpret_cast<const uint4 *>(o_comb + row * 64) + ch), c);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s = fmaf(a[i], c[i], s);
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  if (ok && ch == 0) {
+    const int64_t h = row % H, bt = row / H;
+    const int64_t b = bt / L, t = bt % L;
+    const int64_t o = (b * H + h) * L + t;
+    const float lse = lse_tot[o];
+    const bool self_only = lse < -5e4f;
+    dvec[o] = s;
+    lse2[o] = lse * kLog2e + (self_only ? 1e5f * kLog2e : 0.f);
+    qcmp[o] = static_cast<float>(t + 1) + (self_only ? 0.5f : 0.f);
+  }
+}
+
+int bwd_prep_tc_run(const LshAttnDims &d, const void *do_comb, const void *o_comb, const float *lse_tot, float *dvec,
+                    float *lse2, float *qcmp, cudaStream_t stream) {
+  Derived dr = derive(d);
+  const int64_t rows = static_cast<int64_t>(dr.BH) * d.L;
+  const int64_t blocks = (rows * 8 + ROW_THREADS - 1) / ROW_THREADS;
+  bwd_prep_tc_kernel<<<static_cast<unsigned>(blocks), ROW_THREADS, 0, stream>>>(
+      static_cast<const __nv_bfloat16 *>(do_comb), static_cast<const __nv_bfloat16 *>(o_comb), lse_tot, dvec, lse2, qcmp,
+      d.L, d.H, rows);
+  LSH_CHECK_LAUNCH("bwd_prep_tc_kernel");
+  return 0;
+}
+
 // qscale[u][t] = log2(e) / (sqrt(mean(q^2) + 1e-6) * sqrt(dq))  — the per-key factor of EA:54-57, 229-231 folded with
 // the exp2 conversion; one value per (unit, token), consumed by the tcgen05 attention kernels.
 __global__ void __launch_bounds__(ROW_THREADS) qscale_kernel(const __nv_bfloat16 *__restrict__ qv,

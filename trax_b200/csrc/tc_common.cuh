@@ -53,7 +53,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
     if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
 #ifdef LSH_DEBUG_SPIN
-    if (++spins > (1u << 22)) __trap();   // a protocol bug becomes a trap instead of a hung GPU
+    if (++spins > (1u << 16)) __trap();   // a protocol bug becomes a trap instead of a hung GPU
 #endif
   }
 }
