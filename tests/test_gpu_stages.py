@@ -233,3 +233,31 @@ def test_make_rotations_statistics_and_determinism():
   assert abs(x.mean().item()) < 0.02 and abs(x.std().item() - 1.0) < 0.02
   assert abs((x ** 4).mean().item() - 3.0) < 0.2
   assert not torch.equal(r1[0], r1[1])
+
+
+@pytest.mark.parametrize('max_ctas', ['1', '3', '7'])
+@pytest.mark.parametrize('nh,L', [(4, 1024), (1, 2048), (3, 1280)])
+def test_persistent_walk_many_chunks_per_cta(max_ctas, nh, L, monkeypatch):
+  """The tcgen05 kernels walk contiguous chunk ranges per CTA (tile ring, carried dQ, unit-boundary replays).  The
+  default grid gives small problems one chunk per CTA, so force 1 / 3 / 7 CTAs: every CTA then crosses ring
+  wrap-arounds and (with B*H = 3 units) unit boundaries.  Forward and backward vs the oracle."""
+  from trax_b200 import ops
+  monkeypatch.setenv('LSH_ATTN_MAX_CTAS', max_ctas)
+  B, H, C, nbk = 1, 3, 128, 8
+  cfg, qv, buckets, mask = _core_case(31 + nh, B, H, L, C, 1, 0, nh, nbk, True, False)
+  rng = np.random.default_rng(6)
+  do = util.bf16_round(rng.standard_normal((B, L, H, 64)))
+  dims = _dims(B, H, L, 128, C, 1, 0, nh, [nbk], True, False)
+  qv_d = _cuda(qv, torch.bfloat16)
+  sticker, _ = ops.sort(dims, _cuda(buckets))
+  o_r, logits = ops.attend_fwd(dims, qv_d, sticker)
+  o_c, lse_tot = ops.combine_fwd(dims, o_r, logits)
+  dqv = ops.attend_bwd(dims, qv_d, sticker, o_c, lse_tot, _cuda(do, torch.bfloat16)).float().cpu().numpy()
+  res, grads = _oracle_core(cfg, qv, buckets, mask, B, H, dout=do)
+  o_r, logits = o_r.float().cpu().numpy(), logits.cpu().numpy()
+  for u in range(B * H):
+    b, h = divmod(u, H)
+    util.assert_close(o_r[u], res[u].o_rounds, 'o_rounds[%d]' % u)
+    util.assert_close(logits[u], res[u].logits, 'logits[%d]' % u)
+    util.assert_close(dqv[b, :, h, :64], grads[u][:, :64], 'dq[%d]' % u)
+    util.assert_close(dqv[b, :, h, 64:], grads[u][:, 64:], 'dv[%d]' % u)

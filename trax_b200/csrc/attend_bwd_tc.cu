@@ -20,6 +20,8 @@
 #include "attend_bwd_params.cuh"
 #include "tc_common.cuh"
 
+#include <stdlib.h>
+
 namespace lsh {
 
 constexpr int BT_C = 128;
@@ -226,6 +228,14 @@ __global__ void __launch_bounds__(BT_THREADS, 1) attend_bwd_tc_kernel(const Atte
         BtItem nxt = cur;
         if (have_next) nxt = w.item();
         const uint32_t qt = tile_addr(cur.seq_q), kt = tile_addr(cur.seq_k);
+        // Pre-issue the next item's S^T / dP^T inside this item only if its tiles have ALREADY landed: blocking here
+        // could deadlock (at a segment boundary the next tiles reuse the slot of the tile this item still holds).
+        bool pre_issue = false;
+        if (have_next) {
+          pre_issue = mbar_test(&sh.full[bt_slot(nxt.seq_k)], bt_phase(nxt.seq_k)) &&
+                      mbar_test(&sh.full[bt_slot(nxt.seq_q)], bt_phase(nxt.seq_q));
+          if (pre_issue) { fence_proxy_async(); tc_fence_after(); }
+        }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           mbar_wait(&sh.pds_full[h], cur.n & 1);
@@ -242,10 +252,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) attend_bwd_tc_kernel(const Atte
               umma_ts(tmem + 256, r + 64 + kk * 8, make_smem_desc(qt + h * 8192 + kk * 2048, 1024, 1024), BT_IDESC_KV,
                       !(cur.kv_first && h == 0 && kk == 0));
           }
-          if (have_next) {      // next item's S^T / dP^T for this half: the region is free once the MMAs above have read it
-            if (h == 0) wait_tiles(nxt);
-            issue_st(nxt, h);
-          }
+          if (pre_issue) issue_st(nxt, h);   // the region is free once the MMAs above have read it (in-order pipe)
         }
         if (cur.do_kv && cur.iter_end) umma_commit(&sh.kv_full);
         if (cur.do_dq) {
@@ -263,6 +270,11 @@ __global__ void __launch_bounds__(BT_THREADS, 1) attend_bwd_tc_kernel(const Atte
           if (cur.real && cur.last_seg) umma_commit(&sh.empty[bt_slot(cur.seq_k + 1)]);
         }
         if (!have_next) break;
+        if (!pre_issue) {
+          wait_tiles(nxt);
+          issue_st(nxt, 0);
+          issue_st(nxt, 1);
+        }
         cur = nxt;
       }
     }
@@ -434,7 +446,11 @@ int attend_bwd_tc_run(const AttendBwdTcParams &p, int BH, cudaStream_t stream) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int total = BH * p.n_chunks;
-  const int grid = total < sms ? total : sms;
+  int grid = total < sms ? total : sms;
+  if (const char *e = getenv("LSH_ATTN_MAX_CTAS")) {   // test hook: force many chunks per CTA on small problems
+    const int m = atoi(e);
+    if (m > 0 && m < grid) grid = m;
+  }
   attend_bwd_tc_kernel<<<grid, BT_THREADS, smem, stream>>>(p, total);
   LSH_CHECK_LAUNCH("attend_bwd_tc_kernel");
   return 0;

@@ -19,6 +19,8 @@
 #include "attend_params.cuh"
 #include "tc_common.cuh"
 
+#include <stdlib.h>
+
 namespace lsh {
 
 constexpr int TC_C = 128;
@@ -390,7 +392,11 @@ int attend_fwd_tc_run(const AttendFwdParams &p, int BH, cudaStream_t stream) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int total = BH * p.n_chunks;
-  const int grid = total < sms ? total : sms;
+  int grid = total < sms ? total : sms;
+  if (const char *e = getenv("LSH_ATTN_MAX_CTAS")) {   // test hook: force many chunks per CTA on small problems
+    const int m = atoi(e);
+    if (m > 0 && m < grid) grid = m;
+  }
   attend_fwd_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(p, total);
   LSH_CHECK_LAUNCH("attend_fwd_tc_kernel");
   return 0;
