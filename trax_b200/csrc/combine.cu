@@ -32,19 +32,50 @@ __global__ void __launch_bounds__(ROW_THREADS) combine_fwd_kernel(
   const int t = static_cast<int>(row - u * L);
   const int64_t b = u / H, h = u % H;
   const float *lg = logits + u * nh * L + t;
-  float mx = -INFINITY;
-  for (int r = 0; r < nh; ++r) mx = fmaxf(mx, __ldg(lg + static_cast<int64_t>(r) * L));
-  float den = 0.f;
-  for (int r = 0; r < nh; ++r) den += expf(__ldg(lg + static_cast<int64_t>(r) * L) - mx);
-  const float lse = mx + logf(den);                                   // logsumexp over rounds (EA:1991)
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int r = 0; r < nh; ++r) {
-    const float w = expf(__ldg(lg + static_cast<int64_t>(r) * L) - lse);
-    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(o_rounds + ((u * nh + r) * L + t) * 64) + ch);
-    float f[8];
-    bf16x8_to_f32(v, f);
+  float lse;
+  if (nh <= 8) {
+    // all rows of the token in flight at once (one 16-byte load per round per lane)
+    float lgv[8];
+    uint4 ov[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = fmaf(w, f[i], acc[i]);
+    for (int r = 0; r < 8; ++r) {
+      if (r < nh) {
+        lgv[r] = __ldg(lg + static_cast<int64_t>(r) * L);
+        ov[r] = __ldg(reinterpret_cast<const uint4 *>(o_rounds + ((u * nh + r) * L + t) * 64) + ch);
+      }
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) if (r < nh) mx = fmaxf(mx, lgv[r]);
+    float den = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) if (r < nh) den += expf(lgv[r] - mx);
+    lse = mx + logf(den);                                             // logsumexp over rounds (EA:1991)
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      if (r < nh) {
+        const float w = expf(lgv[r] - lse);
+        float f[8];
+        bf16x8_to_f32(ov[r], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(w, f[i], acc[i]);
+      }
+    }
+  } else {
+    float mx = -INFINITY;
+    for (int r = 0; r < nh; ++r) mx = fmaxf(mx, __ldg(lg + static_cast<int64_t>(r) * L));
+    float den = 0.f;
+    for (int r = 0; r < nh; ++r) den += expf(__ldg(lg + static_cast<int64_t>(r) * L) - mx);
+    lse = mx + logf(den);
+    for (int r = 0; r < nh; ++r) {
+      const float w = expf(__ldg(lg + static_cast<int64_t>(r) * L) - lse);
+      const uint4 v = __ldg(reinterpret_cast<const uint4 *>(o_rounds + ((u * nh + r) * L + t) * 64) + ch);
+      float f[8];
+      bf16x8_to_f32(v, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(w, f[i], acc[i]);
+    }
   }
   *(reinterpret_cast<uint4 *>(o_comb + ((b * L + t) * H + h) * 64) + ch) = f32_to_bf16x8(acc);
   if (lse_tot != nullptr && ch == 0) lse_tot[u * L + t] = lse;

@@ -60,15 +60,27 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_hist_kernel(const SortParam
     out[static_cast<int64_t>(i) * p.n_tiles + tile] = s_hist[i];
 }
 
-// Exclusive scan of one segment's (digit-major, tile-minor) histogram, in place.
+// Exclusive scan of one segment's (digit-major, tile-minor) histogram, in place.  The histogram is staged in shared
+// memory with coalesced 16-byte accesses (33-word padding per 32 entries keeps the per-thread runs conflict-free);
+// each thread then scans a contiguous run, a block scan links the runs.
 __global__ void __launch_bounds__(1024) sort_scan_kernel(int32_t *hist, int entries) {
+  extern __shared__ int s_h[];          // entries + entries/32 words
   __shared__ int s_warp[32];
   int32_t *h = hist + static_cast<int64_t>(blockIdx.x) * entries;
   const int per = (entries + 1023) / 1024;
+  for (int i = threadIdx.x * 4; i < entries; i += 4096) {
+    if ((entries & 3) == 0 && i + 3 < entries) {
+      const int4 v = *reinterpret_cast<const int4 *>(h + i);
+      s_h[i + (i >> 5)] = v.x; s_h[i + 1 + ((i + 1) >> 5)] = v.y;
+      s_h[i + 2 + ((i + 2) >> 5)] = v.z; s_h[i + 3 + ((i + 3) >> 5)] = v.w;
+    } else {
+      for (int k = i; k < min(i + 4, entries); ++k) s_h[k + (k >> 5)] = h[k];
+    }
+  }
+  __syncthreads();
   const int lo = threadIdx.x * per, hi = min(lo + per, entries);
   int sum = 0;
-  for (int i = lo; i < hi; ++i) sum += h[i];
-  // block exclusive scan of `sum`
+  for (int i = lo; i < hi; ++i) sum += s_h[i + (i >> 5)];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int incl = sum;
 #pragma unroll
@@ -91,9 +103,20 @@ __global__ void __launch_bounds__(1024) sort_scan_kernel(int32_t *hist, int entr
   __syncthreads();
   int run = s_warp[warp] + incl - sum;
   for (int i = lo; i < hi; ++i) {
-    int v = h[i];
-    h[i] = run;
+    const int v = s_h[i + (i >> 5)];
+    s_h[i + (i >> 5)] = run;
     run += v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x * 4; i < entries; i += 4096) {
+    if ((entries & 3) == 0 && i + 3 < entries) {
+      int4 v;
+      v.x = s_h[i + (i >> 5)]; v.y = s_h[i + 1 + ((i + 1) >> 5)];
+      v.z = s_h[i + 2 + ((i + 2) >> 5)]; v.w = s_h[i + 3 + ((i + 3) >> 5)];
+      *reinterpret_cast<int4 *>(h + i) = v;
+    } else {
+      for (int k = i; k < min(i + 4, entries); ++k) h[k] = s_h[k + (k >> 5)];
+    }
   }
 }
 
@@ -184,6 +207,10 @@ int sort_run(const LshAttnDims &d, const int32_t *buckets, int64_t bstride, int3
   int32_t *tmp = reinterpret_cast<int32_t *>(static_cast<char *>(ws) + s.hist_bytes);
   size_t smem_sc = static_cast<size_t>(SORT_WARPS) * s.n_digits * sizeof(int);
   LSH_OPT_IN_SMEM(sort_scatter_kernel);
+  LSH_OPT_IN_SMEM(sort_scan_kernel);
+  const int scan_entries = s.n_digits * s.n_tiles;
+  const size_t scan_smem = static_cast<size_t>(scan_entries + scan_entries / 32 + 32) * sizeof(int);
+  if (scan_smem > 200 * 1024) return set_error("lsh_sort: %d histogram entries per segment exceed shared memory", scan_entries);
   // ping-pong so that the last pass lands in `sticker`
   const int32_t *in = nullptr;
   for (int pass = 0; pass < s.passes; ++pass) {
@@ -196,7 +223,7 @@ int sort_run(const LshAttnDims &d, const int32_t *buckets, int64_t bstride, int3
     dim3 grid(s.n_tiles, dr.BH * d.nh);
     sort_hist_kernel<<<grid, SORT_THREADS, s.n_digits * sizeof(int), stream>>>(p);
     LSH_CHECK_LAUNCH("sort_hist_kernel");
-    sort_scan_kernel<<<dr.BH * d.nh, 1024, 0, stream>>>(hist, s.n_digits * s.n_tiles);
+    sort_scan_kernel<<<dr.BH * d.nh, 1024, scan_smem, stream>>>(hist, s.n_digits * s.n_tiles);
     LSH_CHECK_LAUNCH("sort_scan_kernel");
     sort_scatter_kernel<<<grid, SORT_THREADS, smem_sc, stream>>>(p);
     LSH_CHECK_LAUNCH("sort_scatter_kernel");

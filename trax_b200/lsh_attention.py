@@ -57,6 +57,13 @@ def _split_host(key, n):
   return gen.integers(0, 2 ** 32, size=(n, 2), dtype=np.uint64).astype(np.uint32)
 
 
+def _to_pinned_host(t):
+  """Async device->host copy into pinned memory (torch's caching host allocator recycles the blocks)."""
+  h = torch.empty(t.shape, dtype=t.dtype, device='cpu', pin_memory=True)
+  h.copy_(t, non_blocking=True)
+  return h
+
+
 class LSHSelfAttention:
   """LSH self-attention (see module docstring)."""
 
@@ -369,11 +376,13 @@ class LSHSelfAttention:
           ops._ptr(buckets_d), buckets_d.stride(0), ops._ptr(g_d), ops._ptr(out_d), ops._ptr(dx), ops._ptr(dw_q),
           ops._ptr(dw_v), ops._ptr(dw_o), ops._ptr(ws), ws.numel(), stream), 'lsh_layer_bwd')
       if host_io:
-        dx, dw_q, dw_v, dw_o = (t.cpu() for t in (dx, dw_q, dw_v, dw_o))
+        dx, dw_q, dw_v, dw_o = (_to_pinned_host(t) for t in (dx, dw_q, dw_v, dw_o))
       inputs_grad = dx if have_single_input else (dx,) + (None,) * (len(inputs) - 1)
       weights_grad = (dw_q, dw_v, dw_o)
     if update_state:
       new_state = (buckets_d, new_rng)    # state stays on the device, like a jitted Trax layer's
     if compute_output and host_io:
-      out_d = out_d.cpu()
+      out_d = _to_pinned_host(out_d)
+    if host_io:
+      torch.cuda.current_stream().synchronize()      # results are in pinned host memory when the call returns
     return out_d, new_state, inputs_grad, weights_grad
