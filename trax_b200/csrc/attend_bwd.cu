@@ -18,6 +18,8 @@
 
 namespace lsh {
 
+extern long long *g_fwd_trace;   // shared debug trace buffer (attend_fwd.cu)
+
 struct AttendBwdParams {
   const __nv_bfloat16 *qv;       // (B, L, H, 128)
   const int32_t *sticker;        // (BH, N)
@@ -326,7 +328,7 @@ int attend_bwd_run(const LshAttnDims &d, const void *qv, const int32_t *sticker,
     AttendBwdTcParams t;
     t.qv = static_cast<const __nv_bfloat16 *>(qv); t.sticker = sticker;
     t.do_comb = static_cast<const __nv_bfloat16 *>(do_comb); t.qscale = qscale; t.lse2 = lse2; t.dvec = dvec; t.qcmp = qcmp;
-    t.dq_out = dq_part; t.dv_out = dv_part; t.L = d.L; t.H = d.H; t.N = dr.N; t.n_chunks = dr.n_chunks;
+    t.trace = g_fwd_trace; t.dq_out = dq_part; t.dv_out = dv_part; t.L = d.L; t.H = d.H; t.N = dr.N; t.n_chunks = dr.n_chunks;
     if ((rc = attend_bwd_tc_run(t, dr.BH, stream))) return rc;
     return sum_rounds_run(d, dq_part, dv_part, dqv, 1, stream);
   }

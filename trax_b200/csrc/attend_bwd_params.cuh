@@ -15,6 +15,7 @@ struct AttendBwdTcParams {
   __nv_bfloat16 *dq_out;          // (BH, N, 64) ticker order: dq_query + dq_key of every token copy
   __nv_bfloat16 *dv_out;          // (BH, N, 64)
   int L, H, N, n_chunks;
+  long long *trace;               // debug: per-phase clock64 stamps of CTA 0 (null = off)
 };
 
 int attend_bwd_tc_run(const AttendBwdTcParams &p, int BH, cudaStream_t stream);

@@ -215,6 +215,7 @@ int attend_fwd_run(const LshAttnDims &d, const void *qv, const int32_t *sticker,
   p.qv = static_cast<const __nv_bfloat16 *>(qv); p.sticker = sticker;
   p.mask = d.masked ? mask : nullptr; p.o = static_cast<__nv_bfloat16 *>(o);
   p.o_sb = o_sb; p.o_sh = o_sh; p.o_sr = o_sr; p.o_sp = o_sp; p.lse = lse; p.qscale = qscale; p.trace = g_fwd_trace;
+  { const char *e = getenv("LSH_ATTN_STAGGER_NS"); p.stagger_ns = e ? static_cast<unsigned>(atoi(e)) : 0u; }
   p.L = d.L; p.H = d.H; p.N = dr.N; p.n_chunks = dr.n_chunks; p.nb = d.nb; p.nwin = dr.nwin;
   p.causal = d.causal; p.masked = d.masked;
   if (d.masked && !mask) return set_error("attend_fwd: dims.masked set but mask == NULL");

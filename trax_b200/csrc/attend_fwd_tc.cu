@@ -178,7 +178,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
     int n, u, cc, tka = 0, tkb = 0;
     bool have = next_mine(n, u, cc);
     if (have) fetch_sticker(u, cc, tka, tkb);
-    int prev_slot = -1;
     while (have) {
       int n2, u2, cc2, tka2 = 0, tkb2 = 0;
       const bool have2 = next_mine(n2, u2, cc2);
@@ -220,78 +219,71 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
         cp_async16((ch < 8 ? kt : vt) + swz(row, ch & 7), src);
       }
       cp_async_commit();
-      if (prev_slot >= 0) {
-        cp_async_wait<1>();               // this thread's previous tile has landed
-
-        fence_proxy_async();
-        mbar_arrive(&sh.full[prev_slot]);
-      }
-      prev_slot = static_cast<int>(slot);
-      have = have2; n = n2; u = u2; cc = cc2; tka = tka2; tkb = tkb2;
-    }
-    if (prev_slot >= 0) {
-      cp_async_wait<0>();
+      cp_async_wait<0>();                 // signal the tile as soon as it has landed (the other pair keeps loading)
       fence_proxy_async();
-      mbar_arrive(&sh.full[prev_slot]);
+      mbar_arrive(&sh.full[slot]);
+      have = have2; n = n2; u = u2; cc = cc2; tka = tka2; tkb = tkb2;
     }
   } else if (warp == 12) {
     // ================================ S issuer ========================================================
-    // S(k) goes out as soon as its two tiles have landed and its TMEM region has been drained.
-    if (lane == 0) {
-      for (Walker ws(g0, g1, p.n_chunks); ws.valid(); ws.next()) {
-        const int k = ws.k, n = ws.n;
-        const uint32_t w = k & 1, j = k >> 1;
-        mbar_wait(&sh.full[slot_of(n - 1)], phase_of(n - 1));
-        mbar_wait(&sh.full[slot_of(n)], phase_of(n));
-        mbar_wait(&sh.s_free[w], (j & 1) ^ 1);
-        TC_TRACE(k, 7);
-        fence_proxy_async();
-        tc_fence_after();
-        const uint32_t k0 = tiles_u32 + slot_of(n - 1) * TC_TILE_BYTES, k1 = tiles_u32 + slot_of(n) * TC_TILE_BYTES;
-        const uint32_t qa = p.nb ? k1 : k0;
-        const uint32_t s_t = tmem + w * 256;
+    // S(k) goes out as soon as its two tiles have landed and its TMEM region has been drained.  The warp runs
+    // converged (warp-uniform values); one elected lane issues.  Descriptors: constant hi, lo = base + (offset >> 4).
+    constexpr uint32_t HI = desc_hi(1024);
+    for (Walker ws(g0, g1, p.n_chunks); ws.valid(); ws.next()) {
+      const int k = ws.k, n = ws.n;
+      const uint32_t w = k & 1, j = k >> 1;
+      mbar_wait(&sh.full[slot_of(n - 1)], phase_of(n - 1));
+      mbar_wait(&sh.full[slot_of(n)], phase_of(n));
+      mbar_wait(&sh.s_free[w], (j & 1) ^ 1);
+      if (lane == 0) TC_TRACE(k, 7);
+      tc_fence_after();   // (the producers fenced generic->async proxy before arriving on `full`)
+      const uint32_t k0 = tiles_u32 + slot_of(n - 1) * TC_TILE_BYTES, k1 = tiles_u32 + slot_of(n) * TC_TILE_BYTES;
+      const uint32_t qa = desc_lo(p.nb ? k1 : k0, 16), b0 = desc_lo(k0, 16), b1 = desc_lo(k1, 16);
+      const uint32_t s_t = tmem + w * 256;
+      if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          umma_ss(s_t, make_smem_desc(qa + ks * 32, 16, 1024), make_smem_desc(k0 + ks * 32, 16, 1024), TC_IDESC_S, ks > 0);
+        for (int ks = 0; ks < 4; ++ks) umma_ss2(s_t, qa + ks * 2, HI, b0 + ks * 2, HI, TC_IDESC_S, ks > 0);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          umma_ss(s_t + 128, make_smem_desc(qa + ks * 32, 16, 1024), make_smem_desc(k1 + ks * 32, 16, 1024), TC_IDESC_S, ks > 0);
+        for (int ks = 0; ks < 4; ++ks) umma_ss2(s_t + 128, qa + ks * 2, HI, b1 + ks * 2, HI, TC_IDESC_S, ks > 0);
         umma_commit(&sh.s_full[w]);
-        TC_TRACE(k, 0);
       }
+      __syncwarp();
+      if (lane == 0) TC_TRACE(k, 0);
     }
-    __syncwarp();
   } else if (warp == 13) {
     // ================================ PV issuer =======================================================
-    // A second issuing thread so that PV(k) never queues behind an S that is still waiting for tiles.
-    if (lane == 0) {
-      for (Walker wo(g0, g1, p.n_chunks); wo.valid(); wo.next()) {
-        const int k = wo.k, n = wo.n;
-        const uint32_t w = k & 1, j = k >> 1;
-        mbar_wait(&sh.p_full[w], j & 1);
-        tc_fence_after();
-        const uint32_t v0 = tiles_u32 + slot_of(n - 1) * TC_TILE_BYTES + TC_C * 128;
-        const uint32_t v1 = tiles_u32 + slot_of(n) * TC_TILE_BYTES + TC_C * 128;
-        const uint32_t p_t = tmem + w * 256, o_t = p_t + 128;
+    // A second issuing warp so that PV(k) never queues behind an S that is still waiting for tiles.
+    constexpr uint32_t HI = desc_hi(1024);
+    for (Walker wo(g0, g1, p.n_chunks); wo.valid(); wo.next()) {
+      const int k = wo.k, n = wo.n;
+      const uint32_t w = k & 1, j = k >> 1;
+      const uint32_t v0 = desc_lo(tiles_u32 + slot_of(n - 1) * TC_TILE_BYTES + TC_C * 128, 1024);
+      const uint32_t v1 = desc_lo(tiles_u32 + slot_of(n) * TC_TILE_BYTES + TC_C * 128, 1024);
+      const uint32_t p_t = tmem + w * 256, o_t = p_t + 128;
+      const bool rel_own = !wo.next_reuses();
+      mbar_wait(&sh.p_full[w], j & 1);
+      tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          umma_ts(o_t, p_t + i * 8, make_smem_desc(v0 + i * 2048, 1024, 1024), TC_IDESC_O, i > 0);
+        for (int i = 0; i < 8; ++i) umma_ts2(o_t, p_t + i * 8, v0 + i * 128, HI, TC_IDESC_O, i > 0);
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          umma_ts(o_t, p_t + 64 + i * 8, make_smem_desc(v1 + i * 2048, 1024, 1024), TC_IDESC_O, 1);
+        for (int i = 0; i < 8; ++i) umma_ts2(o_t, p_t + 64 + i * 8, v1 + i * 128, HI, TC_IDESC_O, 1);
         umma_commit(&sh.o_full[w]);
-        TC_TRACE(k, 1);
         // S(k) (other issuer) finished before P(k) existed, so every reader of the look-back tile is covered
         umma_commit(&sh.empty[slot_of(n - 1)]);
-        if (!wo.next_reuses()) umma_commit(&sh.empty[slot_of(n)]);   // nobody will reuse the own tile
+        if (rel_own) umma_commit(&sh.empty[slot_of(n)]);   // nobody will reuse the own tile
       }
+      __syncwarp();
+      if (lane == 0) TC_TRACE(k, 1);
     }
-    __syncwarp();
   } else if (warp < 8) {
     // ================================ softmax warpgroups ==============================================
     const uint32_t w = warp >> 2;                          // warpgroup 0 / 1 <-> TMEM region
     const int row = (warp & 3) * 32 + lane;                // query row == TMEM lane (lane quarter = warp id % 4)
     const uint32_t t_lane = tmem + w * 256 + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    // Start the second warpgroup half a period late: the two groups then tend to alternate (one in its softmax pass while
+    // the other waits for MMAs / runs its epilogue) instead of contending for the same issue slots in lockstep.
+    if (w == 1 && p.stagger_ns > 0) __nanosleep(p.stagger_ns);
     for (Walker wk(g0, g1, p.n_chunks); wk.valid(); wk.next()) {
       if ((wk.k & 1) != static_cast<int>(w)) continue;
       const int n = wk.n;

@@ -13,6 +13,7 @@ struct AttendFwdParams {
   float *lse;                   // (BH, N) ticker order
   const float *qscale;          // (BH, L) per-token key scale (tcgen05 path only)
   long long *trace;             // debug: per-phase clock64 stamps of CTA 0 (null = off)
+  unsigned stagger_ns;          // start delay of the second softmax warpgroup (tcgen05 path)
   int L, H, N, n_chunks, nb, nwin, causal, masked;
 };
 
