@@ -98,12 +98,14 @@ def run_reference(args, wl, name):
   rank = int(os.environ.get('RANK', '0'))
   if rank != 0:
     return
+  cores = os.cpu_count() or 1
+  for var in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):   # torchrun pins these to 1
+    os.environ[var] = str(cores)
   import numpy as np
   from oracle import lsh_oracle as O
-  cores = os.cpu_count() or 1
   try:
-    import torch
-    torch.set_num_threads(cores)
+    import threadpoolctl
+    threadpoolctl.threadpool_limits(cores)
   except Exception:  # pylint: disable=broad-except
     pass
   L, D, H = wl['L'], wl['D'], wl['H']
@@ -146,7 +148,7 @@ def run_ours(args, wl, name):
   import torch
   import torch.distributed as dist
   import trax_b200
-  from trax_b200 import ops, _lib
+  from trax_b200 import ops, _lib, dp
 
   world = int(os.environ.get('WORLD_SIZE', '1'))
   rank = int(os.environ.get('RANK', '0'))
@@ -171,10 +173,7 @@ def run_ours(args, wl, name):
   def step(xi, gi):
     out = layer.forward(xi)                                                                   # forward call
     dx, dw = layer.backward(xi, out, gi, weights, None, layer.state, None)                    # backward call
-    if world > 1:
-      flat = torch.cat([t.reshape(-1) for t in dw])
-      dist.all_reduce(flat)                                                                   # psum (trainer.py:194-197)
-      flat /= world
+    dp.allreduce_mean_(dw)                                                                    # psum/n (trainer.py:194-199)
     return out, dx, dw
 
   def sync():
@@ -198,6 +197,19 @@ def run_ours(args, wl, name):
       dist.all_reduce(t, op=dist.ReduceOp.MAX)
       ms = float(t.item())
     return ms / steps
+
+  def timed_local(fn, steps, warmup):
+    """Rank-local CUDA-event timing (no collectives): used for the per-stage breakdown on rank 0."""
+    for _ in range(warmup):
+      fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+      fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
 
   # ---- headline: device-resident inputs ----
   sampler = ClockSampler(local)
@@ -230,7 +242,7 @@ def run_ours(args, wl, name):
 
   if rank == 0:
     peaks = _peaks()
-    stages = stage_breakdown(layer, x, dout, wl, args, timed)
+    stages = stage_breakdown(layer, x, dout, wl, args, timed_local)
     line['stages_ms'] = stages['ms']
     line['roofline'] = stages['roofline'](peaks)
     line['roofline_layer'] = layer_roofline(wl, ms, peaks)
