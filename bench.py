@@ -326,7 +326,11 @@ def stage_breakdown(layer, x, dout, wl, args, timed):
     else:
       ach = a['work'] / (ms[top] * 1e-3) / 1e9
       peak = peaks['hbm']
-    return dict(kernel=top, bound=a['bound'], achieved=ach, peak=peak, unit=a['unit'], frac=ach / peak, traffic=None,
+    traffic = None
+    tp = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+    if os.path.exists(tp):
+      traffic = json.load(open(tp)).get(top, {}).get('bytes')   # DRAM bytes per launch from the committed ncu capture
+    return dict(kernel=top, bound=a['bound'], achieved=ach, peak=peak, unit=a['unit'], frac=ach / peak, traffic=traffic,
                 peak_source=peaks['src'] + (' burst' if a['bound'] == 'tensor' else ''), ms_per_launch=ms[top])
   return dict(ms=ms, roofline=roofline)
 
