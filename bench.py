@@ -33,6 +33,8 @@ WORKLOADS = {
                desc='ReformerLM enwik8-style LSH layer: seq 65536, d_model 1024, 8 heads, d_qk=d_v=64, chunk 128, 4 hashes, n_buckets auto [32,32], causal'),
     'c3': dict(B=1, L=12288, D=1024, H=8, C=128, nh=2, n_buckets=192, dtype='bf16',
                desc='ReformerLM imagenet64-style LSH layer: seq 12288, d_model 1024, 8 heads, 2 hashes, 192 buckets, 1 example per GPU'),
+    'c5': dict(B=1, L=1 << 20, D=1024, H=2, C=128, nh=1, n_buckets=[32, 32], dtype='bf16',
+               desc='long-context 1M-token LSH attention, per-GPU share of 16 heads over 8 GPUs (2 heads), 1 hash, n_buckets [32,32] (int32-key safe)'),
     'c4': dict(B=1, L=16384, D=1024, H=8, C=128, nh=4, n_buckets=None, dtype='bf16',
                desc='n_hashes sweep member: seq 16384, 4 hashes'),
 }

@@ -42,6 +42,7 @@ LAYER_CASES = [
     (2, 512, 128, torch.bfloat16, util.make_cfg(H=4, C=128, nh=4, n_buckets=None)),               # config-2 style
     (1, 768, 256, torch.bfloat16, util.make_cfg(H=2, C=128, nh=2, n_buckets=12)),                 # int n_buckets, nh=2
     (2, 256, 64, torch.float32, util.make_cfg(H=2, C=64, nb=1, na=1, nh=2, n_buckets=8, causal=False, masked=True)),
+    (2, 512, 128, torch.bfloat16, util.make_cfg(H=2, C=128, nh=1, n_buckets=8)),    # single round on the tcgen05 path (rows go straight to o_comb)
 ]
 
 

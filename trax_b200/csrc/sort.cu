@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(1024) sort_scan_kernel(int32_t *hist, int entr
     }
   }
   __syncthreads();
-  const int lo = threadIdx.x * per, hi = min(lo + per, entries);
+  const int lo = min(threadIdx.x * per, entries), hi = min(lo + per, entries);
   int sum = 0;
   for (int i = lo; i < hi; ++i) sum += s_h[i + (i >> 5)];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -117,6 +117,43 @@ __global__ void __launch_bounds__(1024) sort_scan_kernel(int32_t *hist, int entr
     } else {
       for (int k = i; k < min(i + 4, entries); ++k) h[k] = s_h[k + (k >> 5)];
     }
+  }
+}
+
+// Fallback for segments whose histogram does not fit in shared memory (e.g. 1M-token sequences): same scan,
+// straight from global memory (each thread owns a contiguous run).
+__global__ void __launch_bounds__(1024) sort_scan_global_kernel(int32_t *hist, int entries) {
+  __shared__ int s_warp[32];
+  int32_t *h = hist + static_cast<int64_t>(blockIdx.x) * entries;
+  const int per = (entries + 1023) / 1024;
+  const int lo = min(threadIdx.x * per, entries), hi = min(lo + per, entries);
+  int sum = 0;
+  for (int i = lo; i < hi; ++i) sum += h[i];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = s_warp[lane];
+    int wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int v = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += v;
+    }
+    s_warp[lane] = wi - w;
+  }
+  __syncthreads();
+  int run = s_warp[warp] + incl - sum;
+  for (int i = lo; i < hi; ++i) {
+    const int v = h[i];
+    h[i] = run;
+    run += v;
   }
 }
 
@@ -210,7 +247,7 @@ int sort_run(const LshAttnDims &d, const int32_t *buckets, int64_t bstride, int3
   LSH_OPT_IN_SMEM(sort_scan_kernel);
   const int scan_entries = s.n_digits * s.n_tiles;
   const size_t scan_smem = static_cast<size_t>(scan_entries + scan_entries / 32 + 32) * sizeof(int);
-  if (scan_smem > 200 * 1024) return set_error("lsh_sort: %d histogram entries per segment exceed shared memory", scan_entries);
+  const bool scan_in_smem = scan_smem <= 200 * 1024;
   // ping-pong so that the last pass lands in `sticker`
   const int32_t *in = nullptr;
   for (int pass = 0; pass < s.passes; ++pass) {
@@ -223,7 +260,8 @@ int sort_run(const LshAttnDims &d, const int32_t *buckets, int64_t bstride, int3
     dim3 grid(s.n_tiles, dr.BH * d.nh);
     sort_hist_kernel<<<grid, SORT_THREADS, s.n_digits * sizeof(int), stream>>>(p);
     LSH_CHECK_LAUNCH("sort_hist_kernel");
-    sort_scan_kernel<<<dr.BH * d.nh, 1024, scan_smem, stream>>>(hist, s.n_digits * s.n_tiles);
+    if (scan_in_smem) sort_scan_kernel<<<dr.BH * d.nh, 1024, scan_smem, stream>>>(hist, s.n_digits * s.n_tiles);
+    else sort_scan_global_kernel<<<dr.BH * d.nh, 1024, 0, stream>>>(hist, s.n_digits * s.n_tiles);
     LSH_CHECK_LAUNCH("sort_scan_kernel");
     sort_scatter_kernel<<<grid, SORT_THREADS, smem_sc, stream>>>(p);
     LSH_CHECK_LAUNCH("sort_scatter_kernel");
