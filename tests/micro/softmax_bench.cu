@@ -1,0 +1,199 @@
+// Microbenchmark: the forward softmax pass in isolation (TMEM S -> exp2 -> bf16 P in place), two warpgroups on two
+// TMEM regions (2 softmax warps per SM sub-partition, as in attend_fwd_tc_kernel), no MMAs, no producers.
+// Variants of the 32-column block are compared by cycles per 128x256 pass.
+#include <cstdio>
+#include "tc_common.cuh"
+using namespace lsh;
+
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) { return (uint64_t)__float_as_uint(hi) << 32 | __float_as_uint(lo); }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+__device__ __forceinline__ float lo32(uint64_t v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float hi32(uint64_t v) { return __uint_as_float((uint32_t)(v >> 32)); }
+
+// V0: the kernel's current block (predicated FFMA + MUFU)
+__device__ __forceinline__ void block_v0(const uint32_t (&r)[32], const float *kin, const float *ksc, float qi, float m2, uint32_t t_dst, float &l) {
+  uint32_t pk[16];
+#pragma unroll
+  for (int c4 = 0; c4 < 32; c4 += 4) {
+    const float4 ki = *reinterpret_cast<const float4 *>(kin + c4), sc = *reinterpret_cast<const float4 *>(ksc + c4);
+    const float p0 = ki.x < qi ? fast_exp2(fmaf(__uint_as_float(r[c4 + 0]), sc.x, -m2)) : 0.f;
+    const float p1 = ki.y < qi ? fast_exp2(fmaf(__uint_as_float(r[c4 + 1]), sc.y, -m2)) : 0.f;
+    const float p2 = ki.z < qi ? fast_exp2(fmaf(__uint_as_float(r[c4 + 2]), sc.z, -m2)) : 0.f;
+    const float p3 = ki.w < qi ? fast_exp2(fmaf(__uint_as_float(r[c4 + 3]), sc.w, -m2)) : 0.f;
+    l += (p0 + p1) + (p2 + p3);
+    pk[c4 >> 1] = pack_bf16(p0, p1);
+    pk[(c4 >> 1) + 1] = pack_bf16(p2, p3);
+  }
+  tmem_st16(t_dst, pk);
+}
+// V1: packed FFMA2 for the scale, unconditional MUFU, select after, packed row-sum
+__device__ __forceinline__ void block_v1(const uint32_t (&r)[32], const float *kin, const float *ksc, float qi, float m2, uint32_t t_dst, uint64_t &l2) {
+  uint32_t pk[16];
+  const uint64_t mm = pk2(-m2, -m2);
+#pragma unroll
+  for (int c4 = 0; c4 < 32; c4 += 4) {
+    const float4 ki = *reinterpret_cast<const float4 *>(kin + c4);
+    const ulonglong2 sc = *reinterpret_cast<const ulonglong2 *>(ksc + c4);
+    const uint64_t t01 = ffma2((uint64_t)r[c4 + 1] << 32 | r[c4], sc.x, mm);
+    const uint64_t t23 = ffma2((uint64_t)r[c4 + 3] << 32 | r[c4 + 2], sc.y, mm);
+    float p0 = fast_exp2(lo32(t01)), p1 = fast_exp2(hi32(t01)), p2 = fast_exp2(lo32(t23)), p3 = fast_exp2(hi32(t23));
+    p0 = ki.x < qi ? p0 : 0.f; p1 = ki.y < qi ? p1 : 0.f; p2 = ki.z < qi ? p2 : 0.f; p3 = ki.w < qi ? p3 : 0.f;
+    l2 = fadd2(l2, pk2(p0, p1));
+    l2 = fadd2(l2, pk2(p2, p3));
+    pk[c4 >> 1] = pack_bf16(p0, p1);
+    pk[(c4 >> 1) + 1] = pack_bf16(p2, p3);
+  }
+  tmem_st16(t_dst, pk);
+}
+// V2: packed FFMA2, mask folded in BEFORE the exp (t = -inf), unconditional MUFU
+__device__ __forceinline__ void block_v2(const uint32_t (&r)[32], const float *kin, const float *ksc, float qi, float m2, uint32_t t_dst, uint64_t &l2) {
+  uint32_t pk[16];
+  const uint64_t mm = pk2(-m2, -m2);
+#pragma unroll
+  for (int c4 = 0; c4 < 32; c4 += 4) {
+    const float4 ki = *reinterpret_cast<const float4 *>(kin + c4);
+    const ulonglong2 sc = *reinterpret_cast<const ulonglong2 *>(ksc + c4);
+    const uint64_t t01 = ffma2((uint64_t)r[c4 + 1] << 32 | r[c4], sc.x, mm);
+    const uint64_t t23 = ffma2((uint64_t)r[c4 + 3] << 32 | r[c4 + 2], sc.y, mm);
+    const float p0 = fast_exp2(ki.x < qi ? lo32(t01) : -INFINITY), p1 = fast_exp2(ki.y < qi ? hi32(t01) : -INFINITY);
+    const float p2 = fast_exp2(ki.z < qi ? lo32(t23) : -INFINITY), p3 = fast_exp2(ki.w < qi ? hi32(t23) : -INFINITY);
+    l2 = fadd2(l2, pk2(p0, p1));
+    l2 = fadd2(l2, pk2(p2, p3));
+    pk[c4 >> 1] = pack_bf16(p0, p1);
+    pk[(c4 >> 1) + 1] = pack_bf16(p2, p3);
+  }
+  tmem_st16(t_dst, pk);
+}
+// V3: like V1 but staged in groups of 8 columns (all loads, all FFMA2, all MUFU, all selects) to widen the ILP window
+__device__ __forceinline__ void block_v3(const uint32_t (&r)[32], const float *kin, const float *ksc, float qi, float m2, uint32_t t_dst, uint64_t &l2) {
+  uint32_t pk[16];
+  const uint64_t mm = pk2(-m2, -m2);
+#pragma unroll
+  for (int c8 = 0; c8 < 32; c8 += 8) {
+    float ki[8]; uint64_t sc[4], t[4]; float pe[8];
+    *reinterpret_cast<float4 *>(ki) = *reinterpret_cast<const float4 *>(kin + c8);
+    *reinterpret_cast<float4 *>(ki + 4) = *reinterpret_cast<const float4 *>(kin + c8 + 4);
+    *reinterpret_cast<ulonglong2 *>(sc) = *reinterpret_cast<const ulonglong2 *>(ksc + c8);
+    *reinterpret_cast<ulonglong2 *>(sc + 2) = *reinterpret_cast<const ulonglong2 *>(ksc + c8 + 4);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) t[i] = ffma2((uint64_t)r[c8 + 2 * i + 1] << 32 | r[c8 + 2 * i], sc[i], mm);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { pe[2 * i] = fast_exp2(lo32(t[i])); pe[2 * i + 1] = fast_exp2(hi32(t[i])); }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) pe[i] = ki[i] < qi ? pe[i] : 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { l2 = fadd2(l2, pk2(pe[2 * i], pe[2 * i + 1])); pk[(c8 >> 1) + i] = pack_bf16(pe[2 * i], pe[2 * i + 1]); }
+  }
+  tmem_st16(t_dst, pk);
+}
+
+// V4: "interior" block of the position-sorted scheme: per-row scale/shift in registers, no metadata loads, no mask
+__device__ __forceinline__ void block_v4(const uint32_t (&r)[32], uint64_t a2, uint64_t mm, uint32_t t_dst, uint64_t &l2) {
+  uint32_t pk[16];
+#pragma unroll
+  for (int c2 = 0; c2 < 32; c2 += 2) {
+    const uint64_t t = ffma2((uint64_t)r[c2 + 1] << 32 | r[c2], a2, mm);
+    const float p0 = fast_exp2(lo32(t)), p1 = fast_exp2(hi32(t));
+    l2 = fadd2(l2, pk2(p0, p1));
+    pk[c2 >> 1] = pack_bf16(p0, p1);
+  }
+  tmem_st16(t_dst, pk);
+}
+// V5: boundary block: V4 + interval mask lo <= c < hi on the column index (no loads)
+__device__ __forceinline__ void block_v5(const uint32_t (&r)[32], uint64_t a2, uint64_t mm, int lo, int hi, uint32_t t_dst, uint64_t &l2) {
+  uint32_t pk[16];
+#pragma unroll
+  for (int c2 = 0; c2 < 32; c2 += 2) {
+    const uint64_t t = ffma2((uint64_t)r[c2 + 1] << 32 | r[c2], a2, mm);
+    const float p0 = fast_exp2((c2 >= lo && c2 < hi) ? lo32(t) : -INFINITY), p1 = fast_exp2((c2 + 1 >= lo && c2 + 1 < hi) ? hi32(t) : -INFINITY);
+    l2 = fadd2(l2, pk2(p0, p1));
+    pk[c2 >> 1] = pack_bf16(p0, p1);
+  }
+  tmem_st16(t_dst, pk);
+}
+
+template <int V>
+__global__ void __launch_bounds__(512, 1) bench(long long *out, float *sink, int passes, int nwg, float frac_visible) {
+  __shared__ uint32_t tmem_base;
+  __shared__ __align__(16) float kin[2][256], ksc[2][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) tmem_alloc(&tmem_base, 512);
+  if (threadIdx.x < 256) {
+    for (int w = 0; w < 2; ++w) { kin[w][threadIdx.x] = (float)((threadIdx.x * 37) % 256); ksc[w][threadIdx.x] = 0.01f + 0.0001f * threadIdx.x; }
+  }
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t w = warp >> 2;
+  const uint32_t t_lane = tmem_base + w * 256 + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+  // initialise the region with finite scores
+  if (warp < 8) {
+    uint32_t z[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) z[i] = __float_as_uint(0.5f * i + lane);
+    for (int c = 0; c < 256; c += 16) tmem_st16(t_lane + c, z);
+    tmem_st_wait();
+  }
+  __syncthreads();
+  const float qi = 256.f * frac_visible;      // fraction of keys that pass the causal compare
+  const float m2 = 3.f;
+  float l = 0.f; uint64_t l2 = 0;
+  long long t0 = clock64();
+  if (warp < 4 * nwg) {
+    for (int it = 0; it < passes; ++it) {
+      uint32_t ra[32], rb[32];
+      tmem_ld32(t_lane, ra);
+#pragma unroll 1
+      for (int kc = 0; kc < 8; kc += 2) {
+        tmem_ld_wait_dep(ra);
+        tmem_ld32(t_lane + (kc + 1) * 32, rb);
+        if (V == 0) block_v0(ra, kin[w] + kc * 32, ksc[w] + kc * 32, qi, m2, t_lane + kc * 16, l);
+        if (V == 1) block_v1(ra, kin[w] + kc * 32, ksc[w] + kc * 32, qi, m2, t_lane + kc * 16, l2);
+        if (V == 2) block_v2(ra, kin[w] + kc * 32, ksc[w] + kc * 32, qi, m2, t_lane + kc * 16, l2);
+        if (V == 3) block_v3(ra, kin[w] + kc * 32, ksc[w] + kc * 32, qi, m2, t_lane + kc * 16, l2);
+        if (V == 4) block_v4(ra, pk2(qi * 0.001f, qi * 0.001f), pk2(-m2, -m2), t_lane + kc * 16, l2);
+        if (V == 5) block_v5(ra, pk2(qi * 0.001f, qi * 0.001f), pk2(-m2, -m2), lane - kc, lane + 40, t_lane + kc * 16, l2);
+        tmem_ld_wait_dep(rb);
+        if (kc + 2 < 8) tmem_ld32(t_lane + (kc + 2) * 32, ra);
+        if (V == 0) block_v0(rb, kin[w] + (kc + 1) * 32, ksc[w] + (kc + 1) * 32, qi, m2, t_lane + (kc + 1) * 16, l);
+        if (V == 1) block_v1(rb, kin[w] + (kc + 1) * 32, ksc[w] + (kc + 1) * 32, qi, m2, t_lane + (kc + 1) * 16, l2);
+        if (V == 2) block_v2(rb, kin[w] + (kc + 1) * 32, ksc[w] + (kc + 1) * 32, qi, m2, t_lane + (kc + 1) * 16, l2);
+        if (V == 3) block_v3(rb, kin[w] + (kc + 1) * 32, ksc[w] + (kc + 1) * 32, qi, m2, t_lane + (kc + 1) * 16, l2);
+        if (V == 4) block_v4(rb, pk2(qi * 0.001f, qi * 0.001f), pk2(-m2, -m2), t_lane + (kc + 1) * 16, l2);
+        if (V == 5) block_v5(rb, pk2(qi * 0.001f, qi * 0.001f), pk2(-m2, -m2), lane - kc, lane + 40, t_lane + (kc + 1) * 16, l2);
+      }
+      tmem_st_wait();
+      // restore the upper half of the region's first 128 columns is not needed: values stay finite
+    }
+  }
+  long long t1 = clock64();
+  sink[threadIdx.x] = l + lo32(l2) + hi32(l2);
+  if (lane == 0 && warp < 8) out[warp] = t1 - t0;
+  tc_fence_before(); __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+int main() {
+  long long *d; cudaMalloc(&d, 64); float *sink; cudaMalloc(&sink, 4096);
+  long long h[8];
+  const int passes = 200;
+  for (float fv : {0.5f})
+    for (int nwg : {1, 2})
+      for (int v = 0; v < 6; ++v) {
+        for (int rep = 0; rep < 2; ++rep) {
+          if (v == 0) bench<0><<<1, 512>>>(d, sink, passes, nwg, fv);
+          if (v == 1) bench<1><<<1, 512>>>(d, sink, passes, nwg, fv);
+          if (v == 2) bench<2><<<1, 512>>>(d, sink, passes, nwg, fv);
+          if (v == 3) bench<3><<<1, 512>>>(d, sink, passes, nwg, fv);
+          if (v == 4) bench<4><<<1, 512>>>(d, sink, passes, nwg, fv);
+          if (v == 5) bench<5><<<1, 512>>>(d, sink, passes, nwg, fv);
+          cudaDeviceSynchronize();
+        }
+        cudaMemcpy(h, d, 64, cudaMemcpyDeviceToHost);
+        printf("visible %.1f  warpgroups %d  variant %d: %.0f cycles per 128x256 pass (%s)\n", fv, nwg, v, (double)h[0] / passes, cudaGetErrorString(cudaGetLastError()));
+      }
+  return 0;
+}

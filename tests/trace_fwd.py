@@ -10,13 +10,28 @@ keys = torch.arange(2 * B * H, dtype=torch.int32, device='cuda').reshape(B * H, 
 rot, _ = ops.make_rotations(dims, keys)
 sticker, _ = ops.sort(dims, ops.hash_qv(dims, qv, rot))
 ops.attend_fwd(dims, qv, sticker); torch.cuda.synchronize()
-tr = torch.zeros(120 * 8, dtype=torch.int64, device='cuda')
+tr = torch.zeros(120 * 8 + 148, dtype=torch.int64, device='cuda')
 lib = ctypes.CDLL(_lib.LIB_PATH); lib.lsh_debug_set_trace(ctypes.c_void_p(tr.data_ptr()))
 ops.attend_fwd(dims, qv, sticker); torch.cuda.synchronize()
 lib.lsh_debug_set_trace(None)
-t = tr.cpu().view(120, 8)
+percta = tr.cpu()[120 * 8:]; t = tr.cpu()[:120 * 8].view(120, 8)
 t0 = int(t[t > 0].min())
 names = ['S_iss', 'PV_iss', 's_full', 'passdone', 'o_full', 'epi_done', 'arr_swait', 'S_start']
 print('k ' + ' '.join('%9s' % n for n in names))
 for k in list(range(0, 24)) + list(range(100, 112)):
   print('%3d ' % k + ' '.join('%9d' % (int(v) - t0 if v > 0 else -1) for v in t[k]))
+
+import numpy as np
+a = t[8:108].numpy().astype(np.int64)
+print('SUMMARY lib=%s  chunk period %.0f  S->s_full %.0f  pass (s_full->passdone) %.0f  passdone->PV_iss %.0f  PV->o_full %.0f  o_full->epi %.0f  S_start->S_iss %.0f' % (
+    os.path.basename(_lib.LIB_PATH), (a[-1, 0] - a[0, 0]) / 99.0, (a[:, 2] - a[:, 0]).mean(), (a[:, 3] - a[:, 2]).mean(), (a[:, 1] - a[:, 3]).mean(),
+    (a[:, 4] - a[:, 1]).mean(), (a[:, 5] - a[:, 4]).mean(), (a[:, 0] - a[:, 7]).mean()))
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10): ops.attend_fwd(dims, qv, sticker)
+e1.record(); torch.cuda.synchronize()
+print('TIME lib=%s attend_fwd %.3f ms' % (os.path.basename(_lib.LIB_PATH), e0.elapsed_time(e1) / 10))
+
+pc = percta.numpy()
+print('PER-CTA cycles: min %d  median %d  max %d  (first 16: %s)' % (pc.min(), np.median(pc), pc.max(), pc[:16].tolist()))
+print('slowest CTAs:', np.argsort(-pc)[:12].tolist(), np.sort(pc)[-12:][::-1].tolist())

@@ -6,7 +6,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'liblsh_attn_b200.so')
+LIB_PATH = os.environ.get('LSH_ATTN_LIB') or os.path.join(_HERE, 'liblsh_attn_b200.so')   # override: kernel experiments
 
 LSH_DTYPE_F32, LSH_DTYPE_BF16 = 0, 1
 ABI_VERSION = 1

@@ -10,6 +10,10 @@ LIB = os.path.join(HERE, 'liblsh_attn_b200.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 FLAGS = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC', '--use_fast_math=false']
+for _d in os.environ.get('LSH_EXTRA_DEFS', '').split():
+  FLAGS.append('-D' + _d)             # experiment knobs (kernel bring-up only)
+if os.environ.get('LSH_LIB_OUT'):
+  LIB = os.environ['LSH_LIB_OUT']
 if os.environ.get('LSH_DEBUG_SPIN'):
   FLAGS.append('-DLSH_DEBUG_SPIN')   # barrier waits trap instead of hanging (kernel bring-up)
 
@@ -44,7 +48,7 @@ def build(force=False, verbose=False):
   if not force and not needs_build():
     return LIB
   objs = []
-  odir = os.path.join(HERE, 'build')
+  odir = os.path.join(HERE, 'build' if not os.environ.get('LSH_LIB_OUT') else os.path.join('build', os.path.basename(LIB)))
   os.makedirs(odir, exist_ok=True)
   procs = []
   for src in sources():

@@ -9,7 +9,7 @@
 
 #include <mutex>
 
-#include "common.cuh"
+#include "attend_params.cuh"
 
 namespace lsh {
 
@@ -34,8 +34,7 @@ int hash_f32_vecs(const LshAttnDims &, const float *, const float *, const uint8
 size_t sort_workspace_bytes(const LshAttnDims &);
 int sort_run(const LshAttnDims &, const int32_t *, int64_t, int32_t *, int32_t *, void *, size_t, cudaStream_t);
 int attend_fwd_run(const LshAttnDims &, const void *, const int32_t *, const uint8_t *, void *, int64_t, int64_t,
-                   int64_t, int64_t, float *, const float *, cudaStream_t);
-int qscale_run(const LshAttnDims &, const void *, float *, cudaStream_t);
+                   int64_t, int64_t, float *, const FwdAux *, cudaStream_t);
 int combine_fwd_run(const LshAttnDims &, const void *, const float *, void *, float *, cudaStream_t);
 size_t attend_bwd_workspace_bytes(const LshAttnDims &);
 int attend_bwd_run(const LshAttnDims &, const void *, const int32_t *, const uint8_t *, const void *, const float *,
@@ -118,7 +117,8 @@ struct Bump {
 struct LayerWs {
   void *cublas, *xb, *wqv, *wo, *qv, *o_rounds, *o_comb, *sort_ws, *doutb, *do_comb, *dqv, *bwd_ws;
   int32_t *sticker;
-  float *logits, *lse_tot, *dwqv, *qscale;
+  float *logits, *lse_tot, *dwqv;
+  FwdAux aux;
   size_t sort_bytes, bwd_bytes, total;
 };
 
@@ -132,7 +132,7 @@ static LayerWs carve(const LshAttnDims &d, void *ws, bool with_grad) {
   w.wqv = b.take(static_cast<size_t>(d.D) * d.H * dr.QV * 2);
   w.wo = b.take(static_cast<size_t>(d.H) * d.dv * d.D * 2);
   w.qv = b.take(BL * d.H * dr.QV * 2);
-  w.qscale = static_cast<float *>(b.take(static_cast<size_t>(dr.BH) * d.L * 4));
+  w.aux = fwd_aux_carve(d, b.take(fwd_aux_bytes(d)));
   w.sticker = static_cast<int32_t *>(b.take(rows * 4));
   w.sort_bytes = sort_workspace_bytes(d);
   w.sort_ws = b.take(w.sort_bytes);
@@ -168,20 +168,20 @@ static int forward_core(const LshAttnDims &d, const LayerWs &w, const void *x, c
   if ((rc = pack_weights_run(d, w_q, w_v, w_o, w.wqv, w.wo, s))) return rc;
   const int64_t NQV = static_cast<int64_t>(d.H) * dr.QV;
   if ((rc = gemm_rm(false, false, BL, NQV, d.D, xb, d.D, w.wqv, NQV, w.qv, NQV, false, w.cublas, s))) return rc;
-  if ((rc = qscale_run(d, w.qv, w.qscale, s))) return rc;
   if (rotations) {
     if ((rc = hash_bf16_qv(d, w.qv, rotations, mask, buckets, bstride, s))) return rc;
   }
   if ((rc = sort_run(d, buckets, bstride, w.sticker, nullptr, w.sort_ws, w.sort_bytes, s))) return rc;
+  if ((rc = fwd_aux_prepare(d, w.qv, w.sticker, w.aux, s))) return rc;
   if (d.nh > 1) {
     if ((rc = attend_fwd_run(d, w.qv, w.sticker, mask, w.o_rounds, static_cast<int64_t>(d.H) * dr.N * 64,
-                             static_cast<int64_t>(dr.N) * 64, static_cast<int64_t>(d.L) * 64, 64, w.logits, w.qscale, s)))
+                             static_cast<int64_t>(dr.N) * 64, static_cast<int64_t>(d.L) * 64, 64, w.logits, &w.aux, s)))
       return rc;
     if ((rc = combine_fwd_run(d, w.o_rounds, w.logits, w.o_comb, need_lse_tot ? w.lse_tot : nullptr, s))) return rc;
   } else {
     // single round: rows land directly in the (B, L, H, dv) layout, logits == lse_tot
     if ((rc = attend_fwd_run(d, w.qv, w.sticker, mask, w.o_comb, static_cast<int64_t>(d.L) * d.H * 64, 64, 0,
-                             static_cast<int64_t>(d.H) * 64, w.logits, w.qscale, s)))
+                             static_cast<int64_t>(d.H) * 64, w.logits, &w.aux, s)))
       return rc;
   }
   return 0;
@@ -239,7 +239,7 @@ int lsh_sort(const LshAttnDims *dims, const int32_t *buckets, int64_t buckets_st
 }
 
 size_t lsh_attend_fwd_workspace_bytes(const LshAttnDims *dims) {
-  return dims ? static_cast<size_t>(dims->B) * dims->H * dims->L * sizeof(float) + 256 : 0;
+  return dims ? fwd_aux_bytes(*dims) : 0;
 }
 
 int lsh_attend_fwd(const LshAttnDims *dims, const void *qv, const int32_t *sticker, const uint8_t *mask,
@@ -248,10 +248,10 @@ int lsh_attend_fwd(const LshAttnDims *dims, const void *qv, const int32_t *stick
   const LshAttnDims &d = *dims;
   Derived dr = derive(d);
   if (!ws || ws_bytes < lsh_attend_fwd_workspace_bytes(dims)) return set_error("lsh_attend_fwd: workspace too small");
-  float *qscale = static_cast<float *>(ws);
-  if (int rc = qscale_run(d, qv, qscale, static_cast<cudaStream_t>(stream))) return rc;
+  FwdAux aux = fwd_aux_carve(d, ws);
+  if (int rc = fwd_aux_prepare(d, qv, sticker, aux, static_cast<cudaStream_t>(stream))) return rc;
   return attend_fwd_run(d, qv, sticker, mask, o_rounds, static_cast<int64_t>(d.H) * dr.N * 64,
-                        static_cast<int64_t>(dr.N) * 64, static_cast<int64_t>(d.L) * 64, 64, logits, qscale,
+                        static_cast<int64_t>(dr.N) * 64, static_cast<int64_t>(d.L) * 64, 64, logits, &aux,
                         static_cast<cudaStream_t>(stream));
 }
 
@@ -331,7 +331,7 @@ int lsh_layer_bwd(const LshAttnDims *dims, const void *x, const float *w_q, cons
   if ((rc = gemm_rm(false, true, BL, KO, d.D, doutb, d.D, w.wo, d.D, w.do_comb, KO, false, w.cublas, s))) return rc;
   if ((rc = gemm_rm(true, false, KO, d.D, BL, w.o_comb, KO, doutb, d.D, dw_o, d.D, true, w.cublas, s))) return rc;
   // B2-B6
-  if ((rc = attend_bwd_run(d, w.qv, w.sticker, mask, w.o_comb, w.lse_tot, w.do_comb, w.qscale, w.dqv, w.bwd_ws, w.bwd_bytes, s)))
+  if ((rc = attend_bwd_run(d, w.qv, w.sticker, mask, w.o_comb, w.lse_tot, w.do_comb, w.aux.qscale, w.dqv, w.bwd_ws, w.bwd_bytes, s)))
     return rc;
   // B7: dW_q|dW_v = x^T·dqv ; dx = dqv·wqv^T
   if ((rc = gemm_rm(true, false, d.D, NQV, BL, xb, d.D, w.dqv, NQV, w.dwqv, NQV, true, w.cublas, s))) return rc;

@@ -295,7 +295,7 @@ int sum_rounds_run(const LshAttnDims &d, const void *dq_part, const void *dv_par
                    int n_kinds, cudaStream_t stream);
 int bwd_prep_tc_run(const LshAttnDims &d, const void *do_comb, const void *o_comb, const float *lse_tot, float *dvec,
                     float *lse2, float *qcmp, cudaStream_t stream);
-int qscale_run(const LshAttnDims &d, const void *qv, float *qscale, cudaStream_t stream);
+int qscale_run(const LshAttnDims &d, const void *qv, float *qscale, float2 *rowmeta, void *qhat, cudaStream_t stream);
 
 int attend_bwd_run(const LshAttnDims &d, const void *qv, const int32_t *sticker, const uint8_t *mask,
                    const void *o_comb, const float *lse_tot, const void *do_comb, const float *qscale_in, void *dqv,
@@ -321,7 +321,7 @@ int attend_bwd_run(const LshAttnDims &d, const void *qv, const int32_t *sticker,
   if (d.C == 128 && d.nb == 1 && d.na == 0 && d.causal && !d.masked && !force_mma) {
     const float *qscale = qscale_in;
     if (!qscale) {
-      if ((rc = qscale_run(d, qv, qscale_ws, stream))) return rc;
+      if ((rc = qscale_run(d, qv, qscale_ws, nullptr, nullptr, stream))) return rc;
       qscale = qscale_ws;
     }
     if ((rc = bwd_prep_tc_run(d, do_comb, o_comb, lse_tot, dvec, lse2, qcmp, stream))) return rc;

@@ -207,22 +207,60 @@ static int launch_attend_fwd(const AttendFwdParams &p, int BH, cudaStream_t stre
   return 0;
 }
 
+static bool force_mma_fwd() {
+  static const bool f = [] { const char *e = getenv("LSH_ATTN_FWD"); return e && strcmp(e, "mma") == 0; }();
+  return f;
+}
+// tcgen05 path for the long-sequence shape (chunk 128, 2-chunk window); LSH_ATTN_FWD=mma forces the mma.sync path
+bool attend_fwd_uses_tc(const LshAttnDims &d) { return d.C == 128 && 1 + d.nb + d.na == 2 && !force_mma_fwd(); }
+
+int qscale_run(const LshAttnDims &d, const void *qv, float *qscale, float2 *rowmeta, void *qhat, cudaStream_t stream);
+int chunk_possort_run(const LshAttnDims &d, const int32_t *sticker, int32_t *sticker2, cudaStream_t stream);
+
+static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+size_t fwd_aux_bytes(const LshAttnDims &d) {
+  Derived dr = derive(d);
+  const size_t rows = static_cast<size_t>(dr.BH) * d.L;
+  return align256(rows * 4) + align256(rows * 8) + align256(rows * 128) + align256(static_cast<size_t>(dr.BH) * dr.N * 4) + 256;
+}
+FwdAux fwd_aux_carve(const LshAttnDims &d, void *ws) {
+  Derived dr = derive(d);
+  const size_t rows = static_cast<size_t>(dr.BH) * d.L;
+  char *b = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255));
+  FwdAux a;
+  a.qscale = reinterpret_cast<float *>(b); b += align256(rows * 4);
+  a.rowmeta = reinterpret_cast<float2 *>(b); b += align256(rows * 8);
+  a.qhat = b; b += align256(rows * 128);
+  a.sticker2 = reinterpret_cast<int32_t *>(b);
+  return a;
+}
+// Everything the attention kernels need besides qv and sticker: per-token scales (always: the backward kernel reads
+// qscale), and for the tcgen05 forward path the normalised keys and the position-sorted chunks.
+int fwd_aux_prepare(const LshAttnDims &d, const void *qv, const int32_t *sticker, const FwdAux &aux, cudaStream_t stream) {
+  const bool tc = attend_fwd_uses_tc(d);
+  if (int rc = qscale_run(d, qv, aux.qscale, tc ? aux.rowmeta : nullptr, tc ? aux.qhat : nullptr, stream)) return rc;
+  if (tc && sticker) return chunk_possort_run(d, sticker, aux.sticker2, stream);
+  return 0;
+}
+
 int attend_fwd_run(const LshAttnDims &d, const void *qv, const int32_t *sticker, const uint8_t *mask,
                    void *o, int64_t o_sb, int64_t o_sh, int64_t o_sr, int64_t o_sp, float *lse,
-                   const float *qscale, cudaStream_t stream) {
+                   const FwdAux *aux, cudaStream_t stream) {
   Derived dr = derive(d);
   AttendFwdParams p;
   p.qv = static_cast<const __nv_bfloat16 *>(qv); p.sticker = sticker;
   p.mask = d.masked ? mask : nullptr; p.o = static_cast<__nv_bfloat16 *>(o);
-  p.o_sb = o_sb; p.o_sh = o_sh; p.o_sr = o_sr; p.o_sp = o_sp; p.lse = lse; p.qscale = qscale; p.trace = g_fwd_trace;
+  p.o_sb = o_sb; p.o_sh = o_sh; p.o_sr = o_sr; p.o_sp = o_sp; p.lse = lse; p.trace = g_fwd_trace;
+  p.qscale = aux ? aux->qscale : nullptr;
+  p.qhat = aux ? static_cast<const __nv_bfloat16 *>(aux->qhat) : nullptr;
+  p.rowmeta = aux ? aux->rowmeta : nullptr;
+  p.sticker2 = aux ? aux->sticker2 : nullptr;
   { const char *e = getenv("LSH_ATTN_STAGGER_NS"); p.stagger_ns = e ? static_cast<unsigned>(atoi(e)) : 0u; }
   p.L = d.L; p.H = d.H; p.N = dr.N; p.n_chunks = dr.n_chunks; p.nb = d.nb; p.nwin = dr.nwin;
   p.causal = d.causal; p.masked = d.masked;
   if (d.masked && !mask) return set_error("attend_fwd: dims.masked set but mask == NULL");
-  // tcgen05 path for the long-sequence shape (chunk 128, 2-chunk window); LSH_ATTN_FWD=mma forces the mma.sync path
-  static const bool force_mma = [] { const char *e = getenv("LSH_ATTN_FWD"); return e && strcmp(e, "mma") == 0; }();
-  if (d.C == 128 && dr.nwin == 2 && !force_mma) {
-    if (!qscale) return set_error("attend_fwd: the tcgen05 path needs the qscale workspace");
+  if (attend_fwd_uses_tc(d)) {
+    if (!aux) return set_error("attend_fwd: the tcgen05 path needs the auxiliary workspace");
     return attend_fwd_tc_run(p, dr.BH, stream);
   }
   switch (d.C) {

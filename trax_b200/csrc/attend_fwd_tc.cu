@@ -33,11 +33,11 @@ constexpr uint32_t TC_IDESC_S = make_idesc_bf16(128, 128, 0, 0);   // Q (K-major
 constexpr uint32_t TC_IDESC_O = make_idesc_bf16(128, 64, 0, 1);    // P (TMEM)    x V (MN-major)
 
 struct __align__(16) TcTileMeta {
-  float kinfo[TC_C];    // kv_info (+1 applied; negative = padding), fp32 like EA:148-149
-  int pos[TC_C];        // 0-based positions
+  float kinfo[TC_C];    // kv_info (+1 applied; negative = padding), fp32 like EA:148-149 (generic path)
+  int pos[TC_C];        // 0-based positions; ascending along the tile's rank order (see chunk_possort_kernel)
   int tk[TC_C];         // ticker values
-  float kscl[TC_C];     // per-key scale log2(e) / (sqrt(mean(q^2)+eps) * sqrt(dq)), gathered from qscale
-  float vmin[2], vmax[2];   // min / max of the valid kinfo per producer warp (visibility test)
+  float2 am[TC_C];      // {a = 8 r log2e, m2 = a |qhat|^2} of the row's token (query-side scale and softmax shift)
+  float vmin[2], vmax[2];   // min / max of the valid kinfo per producer warp (visibility test, generic path)
 };
 
 struct __align__(16) TcShared {
@@ -74,56 +74,72 @@ __device__ __forceinline__ uint32_t phase_of(int n) { return static_cast<uint32_
 
 constexpr float kBig = 1e9f * kLog2e, kSelf = 1e5f * kLog2e;   // EA:152-159 masks, log2 domain
 
-// 32 score columns of one query row: t = s * kscale_j - m (+ masks), p = 2^t, packed to bf16 and stored back
-// over the consumed S columns.  `kin` / `ksc`: shared-space addresses of the 32 keys' kv_info / kscale.
-__device__ __forceinline__ void softmax_block(const uint32_t (&r)[32], const float *kin, const float *ksc, float qi, float m2,
-                                              bool fast, int causal, int masked, uint32_t t_dst, float &l) {
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  return static_cast<uint64_t>(__float_as_uint(hi)) << 32 | __float_as_uint(lo);
+}
+__device__ __forceinline__ uint64_t pk2u(uint32_t lo, uint32_t hi) { return static_cast<uint64_t>(hi) << 32 | lo; }
+__device__ __forceinline__ float lo32(uint64_t v) { return __uint_as_float(static_cast<uint32_t>(v)); }
+__device__ __forceinline__ float hi32(uint64_t v) { return __uint_as_float(static_cast<uint32_t>(v >> 32)); }
+// Packed fp32 pairs (FFMA2 / FADD2): same FMA throughput per lane, half the issue slots.
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// 32 score columns of one query row, every key visible: t = s * a_i - m_i, p = 2^t, packed to bf16 and stored back
+// over the consumed S columns.  Scale and shift are per-ROW registers: no loads, no compares.
+__device__ __forceinline__ void softmax_block_full(const uint32_t (&r)[32], uint64_t a2, uint64_t mm2, uint32_t t_dst, uint64_t &l2) {
   uint32_t pk[16];
-  if (fast) {
-    if (causal) {
 #pragma unroll
-      for (int c4 = 0; c4 < 32; c4 += 4) {
-        const float4 ki = *reinterpret_cast<const float4 *>(kin + c4), sc = *reinterpret_cast<const float4 *>(ksc + c4);
-        const float p0 = ki.x < qi ? fast_exp2(fmaf(__uint_as_float(r[c4 + 0]), sc.x, -m2)) : 0.f;
-        const float p1 = ki.y < qi ? fast_exp2(fmaf(__uint_as_float(r[c4 + 1]), sc.y, -m2)) : 0.f;
-        const float p2 = ki.z < qi ? fast_exp2(fmaf(__uint_as_float(r[c4 + 2]), sc.z, -m2)) : 0.f;
-        const float p3 = ki.w < qi ? fast_exp2(fmaf(__uint_as_float(r[c4 + 3]), sc.w, -m2)) : 0.f;
-        l += (p0 + p1) + (p2 + p3);
-        pk[c4 >> 1] = pack_bf16(p0, p1);
-        pk[(c4 >> 1) + 1] = pack_bf16(p2, p3);
-      }
-    } else {
+  for (int c2 = 0; c2 < 32; c2 += 2) {
+    const uint64_t t = ffma2(pk2u(r[c2], r[c2 + 1]), a2, mm2);
+    const float p0 = fast_exp2(lo32(t)), p1 = fast_exp2(hi32(t));
+    l2 = fadd2(l2, pk2(p0, p1));
+    pk[c2 >> 1] = pack_bf16(p0, p1);
+  }
+  tmem_st16(t_dst, pk);
+}
+// Boundary block of the position-sorted scheme: column c of the block is visible iff lo <= c < hi (per row).
+__device__ __forceinline__ void softmax_block_interval(const uint32_t (&r)[32], uint64_t a2, uint64_t mm2, int lo, int hi, uint32_t t_dst,
+                                                       uint64_t &l2) {
+  uint32_t pk[16];
 #pragma unroll
-      for (int c4 = 0; c4 < 32; c4 += 4) {
-        const float4 ki = *reinterpret_cast<const float4 *>(kin + c4), sc = *reinterpret_cast<const float4 *>(ksc + c4);
-        const float p0 = ki.x != qi ? fast_exp2(fmaf(__uint_as_float(r[c4 + 0]), sc.x, -m2)) : 0.f;
-        const float p1 = ki.y != qi ? fast_exp2(fmaf(__uint_as_float(r[c4 + 1]), sc.y, -m2)) : 0.f;
-        const float p2 = ki.z != qi ? fast_exp2(fmaf(__uint_as_float(r[c4 + 2]), sc.z, -m2)) : 0.f;
-        const float p3 = ki.w != qi ? fast_exp2(fmaf(__uint_as_float(r[c4 + 3]), sc.w, -m2)) : 0.f;
-        l += (p0 + p1) + (p2 + p3);
-        pk[c4 >> 1] = pack_bf16(p0, p1);
-        pk[(c4 >> 1) + 1] = pack_bf16(p2, p3);
-      }
+  for (int c2 = 0; c2 < 32; c2 += 2) {
+    const uint64_t t = ffma2(pk2u(r[c2], r[c2 + 1]), a2, mm2);
+    const float p0 = fast_exp2((c2 >= lo && c2 < hi) ? lo32(t) : -INFINITY);
+    const float p1 = fast_exp2((c2 + 1 >= lo && c2 + 1 < hi) ? hi32(t) : -INFINITY);
+    l2 = fadd2(l2, pk2(p0, p1));
+    pk[c2 >> 1] = pack_bf16(p0, p1);
+  }
+  tmem_st16(t_dst, pk);
+}
+// Generic path (non-causal, padding mask, other windows): the reference's subtractive masks in order (EA:150-159) with the
+// key kv_info read from shared memory.
+__device__ __forceinline__ void softmax_block_generic(const uint32_t (&r)[32], const float *kin, float qi, float a, float m2, int causal,
+                                                      int masked, uint32_t t_dst, float &l) {
+  uint32_t pk[16];
+#pragma unroll
+  for (int c4 = 0; c4 < 32; c4 += 4) {
+    const float4 ki4 = *reinterpret_cast<const float4 *>(kin + c4);
+    const float kis[4] = {ki4.x, ki4.y, ki4.z, ki4.w};
+    float pv[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float t = fmaf(__uint_as_float(r[c4 + e]), a, -m2);
+      if (causal && qi < kis[e]) t -= kBig;
+      if (qi == kis[e]) t -= kSelf;
+      if (masked && kis[e] < 0.f) t -= kBig;
+      pv[e] = fast_exp2(t);
     }
-  } else {
-    // generic path: the reference's subtractive masks in order (EA:150-159)
-#pragma unroll
-    for (int c4 = 0; c4 < 32; c4 += 4) {
-      const float4 ki4 = *reinterpret_cast<const float4 *>(kin + c4), sc4 = *reinterpret_cast<const float4 *>(ksc + c4);
-      const float kis[4] = {ki4.x, ki4.y, ki4.z, ki4.w}, scs[4] = {sc4.x, sc4.y, sc4.z, sc4.w};
-      float pv[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float t = fmaf(__uint_as_float(r[c4 + e]), scs[e], -m2);
-        if (causal && qi < kis[e]) t -= kBig;
-        if (qi == kis[e]) t -= kSelf;
-        if (masked && kis[e] < 0.f) t -= kBig;
-        pv[e] = fast_exp2(t);
-      }
-      l += (pv[0] + pv[1]) + (pv[2] + pv[3]);
-      pk[c4 >> 1] = pack_bf16(pv[0], pv[1]);
-      pk[(c4 >> 1) + 1] = pack_bf16(pv[2], pv[3]);
-    }
+    l += (pv[0] + pv[1]) + (pv[2] + pv[3]);
+    pk[c4 >> 1] = pack_bf16(pv[0], pv[1]);
+    pk[(c4 >> 1) + 1] = pack_bf16(pv[2], pv[3]);
   }
   tmem_st16(t_dst, pk);
 }
@@ -135,6 +151,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
   __shared__ TcShared sh;                                   // static: keeps metadata accesses in the shared space (LDS)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long t_cta_start = clock64();
   // contiguous, balanced range of chunks for this CTA
   const int g0 = static_cast<int>(static_cast<int64_t>(total_chunks) * blockIdx.x / gridDim.x);
   const int g1 = static_cast<int>(static_cast<int64_t>(total_chunks) * (blockIdx.x + 1) / gridDim.x);
@@ -170,61 +187,81 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
       }
       return false;
     };
-    auto next_mine = [&](int &n, int &u, int &cc) -> bool {
-      return next_tile(n, u, cc);
-    };
+    // rank r of the position-sorted chunk goes to tile row r (even chunks) or 127 - r (odd chunks): the two softmax
+    // warpgroups own alternate chunks, so their heavy warps (the rows that see the most keys) sit on
+    // different SM sub-partitions.
     auto fetch_sticker = [&](int u, int cc, int &tka, int &tkb) {
-      const int32_t *stk = p.sticker + static_cast<int64_t>(u) * p.N + cc * TC_C + 64 * pw;
+      const int32_t *stk = p.sticker2 + static_cast<int64_t>(u) * p.N + cc * TC_C + 64 * pw;
       tka = __ldg(stk + lane); tkb = __ldg(stk + 32 + lane);
     };
-    int n, u, cc, tka = 0, tkb = 0;
-    bool have = next_mine(n, u, cc);
-    if (have) fetch_sticker(u, cc, tka, tkb);
-    while (have) {
-      int n2, u2, cc2, tka2 = 0, tkb2 = 0;
-      const bool have2 = next_mine(n2, u2, cc2);
-      if (have2) fetch_sticker(u2, cc2, tka2, tkb2);      // in flight while this tile is issued
+    // Requests run three tiles ahead of the copies so that the dependent chain sticker -> position -> row address never
+    // exposes a global-load latency (three statically named request slots: no register rotation, no early scoreboard wait).
+    struct TileReq { int n, u, cc, tka, tkb; bool have; };
+    auto request = [&](TileReq &r) {
+      r.tka = 0; r.tkb = 0;
+      r.have = next_tile(r.n, r.u, r.cc);
+      if (r.have) fetch_sticker(r.u, r.cc, r.tka, r.tkb);
+    };
+    const bool sorted_path = p.causal && !p.masked && p.nb == 1;
+    const int ch = lane & 15, hi = lane >> 4;              // 16-byte piece of the 256-byte row pair; row parity
+    auto issue = [&](const TileReq &r) {
+      const int n = r.n, u = r.u, tka = r.tka, tkb = r.tkb;
       const uint32_t slot = slot_of(n);
-      mbar_wait<256>(&sh.empty[slot], phase_of(n) ^ 1);
+      const int flip = (r.cc & 1) ? 127 : 0;                // row = rank ^ flip  (127 - rank for odd chunks)
+      mbar_wait<64>(&sh.empty[slot], phase_of(n) ^ 1);
       const int b = u / p.H, h = u - b * p.H;
       const int pa = tka % p.L, pb = tkb % p.L;
-      bool va = true, vb = true;
-      if (p.masked) {
-        va = p.mask[static_cast<int64_t>(b) * p.L + pa] != 0;
-        vb = p.mask[static_cast<int64_t>(b) * p.L + pb] != 0;
-      }
       TcTileMeta &mt = sh.meta[slot];
-      const float kia = static_cast<float>((va ? pa : -pa) + 1), kib = static_cast<float>((vb ? pb : -pb) + 1);
-      mt.kinfo[64 * pw + lane] = kia; mt.kinfo[64 * pw + 32 + lane] = kib;
-      mt.pos[64 * pw + lane] = pa;    mt.pos[64 * pw + 32 + lane] = pb;
-      mt.tk[64 * pw + lane] = tka;    mt.tk[64 * pw + 32 + lane] = tkb;
-      const float *qs = p.qscale + static_cast<int64_t>(u) * p.L;
-      cp_async4(smem_u32(&mt.kscl[64 * pw + lane]), qs + pa);
-      cp_async4(smem_u32(&mt.kscl[64 * pw + 32 + lane]), qs + pb);
-      float mn = fminf(kia > 0.f ? kia : INFINITY, kib > 0.f ? kib : INFINITY);
-      float mx = fmaxf(kia > 0.f ? kia : -INFINITY, kib > 0.f ? kib : -INFINITY);
+      const int rowa = (64 * pw + lane) ^ flip, rowb = (64 * pw + 32 + lane) ^ flip;
+      mt.pos[rowa] = pa;    mt.pos[rowb] = pb;
+      mt.tk[rowa] = tka;    mt.tk[rowb] = tkb;
+      const float2 *rm = p.rowmeta + static_cast<int64_t>(u) * p.L;
+      cp_async8(smem_u32(&mt.am[rowa]), rm + pa);
+      cp_async8(smem_u32(&mt.am[rowb]), rm + pb);
+      if (!sorted_path) {                                   // generic path: kv_info and the window visibility range
+        bool va = true, vb = true;
+        if (p.masked) {
+          va = p.mask[static_cast<int64_t>(b) * p.L + pa] != 0;
+          vb = p.mask[static_cast<int64_t>(b) * p.L + pb] != 0;
+        }
+        const float kia = static_cast<float>((va ? pa : -pa) + 1), kib = static_cast<float>((vb ? pb : -pb) + 1);
+        mt.kinfo[rowa] = kia; mt.kinfo[rowb] = kib;
+        float mn = fminf(kia > 0.f ? kia : INFINITY, kib > 0.f ? kib : INFINITY);
+        float mx = fmaxf(kia > 0.f ? kia : -INFINITY, kib > 0.f ? kib : -INFINITY);
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        for (int o = 16; o > 0; o >>= 1) {
+          mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        if (lane == 0) { mt.vmin[pw] = mn; mt.vmax[pw] = mx; }
       }
-      if (lane == 0) { mt.vmin[pw] = mn; mt.vmax[pw] = mx; }
-      const uint32_t kt = tiles_u32 + slot * TC_TILE_BYTES, vt = kt + TC_C * 128;
-      const int ch = lane & 15, hi = lane >> 4;
-      const __nv_bfloat16 *base = p.qv + (static_cast<int64_t>(b) * p.L * p.H + h) * 128 + ch * 8;
-#pragma unroll 8
+      // 16-byte pieces 0-7 of a row: normalised key qhat (BH, L, 64); pieces 8-15: value, second half of the qv row.
+      // Destination of rank R = 64 pw + 2 i + hi, piece c: tile + (X << 7) + (((c ^ X) & 7) << 4) with X = R ^ flip.  All
+      // bit fields are disjoint, so this is  tile + (lane_tile_const ^ imm(i)):  one LOP3 + one IADD per copy.
+      const char *base = ch < 8 ? reinterpret_cast<const char *>(p.qhat + static_cast<int64_t>(u) * p.L * 64 + ch * 8)
+                                : reinterpret_cast<const char *>(p.qv + (static_cast<int64_t>(b) * p.L * p.H + h) * 128 + ch * 8);
+      const uint32_t rbytes = ch < 8 ? 128u : static_cast<uint32_t>(p.H) * 256u;
+      const uint32_t tile = tiles_u32 + slot * TC_TILE_BYTES + (ch < 8 ? 0 : TC_C * 128);
+      const uint32_t lane_const = (static_cast<uint32_t>((64 * pw + hi) ^ flip) << 7) | (static_cast<uint32_t>((ch ^ flip ^ hi) & 7) << 4);
+#pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const int rel = 2 * i + hi;                                      // row within this warp's 64
-        const int pr = __shfl_sync(0xffffffffu, (i < 16) ? pa : pb, rel & 31);
-        const int row = 64 * pw + rel;
-        const __nv_bfloat16 *src = base + static_cast<int64_t>(pr) * p.H * 128;
-        cp_async16((ch < 8 ? kt : vt) + swz(row, ch & 7), src);
+        const int pr = __shfl_sync(0xffffffffu, (i < 16) ? pa : pb, (2 * i + hi) & 31);
+        const uint32_t imm = (static_cast<uint32_t>(i) << 8) ^ (static_cast<uint32_t>(i & 3) << 5);
+        cp_async16(tile + (lane_const ^ imm), base + static_cast<uint64_t>(static_cast<uint32_t>(pr)) * rbytes);
       }
-      cp_async_commit();
-      cp_async_wait<0>();                 // signal the tile as soon as it has landed (the other pair keeps loading)
-      fence_proxy_async();
-      mbar_arrive(&sh.full[slot]);
-      have = have2; n = n2; u = u2; cc = cc2; tka = tka2; tkb = tkb2;
+      // Completion is signalled by the copies themselves (no wait here): every free ring slot is a tile in flight.
+      // The metadata stores above precede the copies in program order and are long done when the last copy lands.
+      cp_async_mbar_arrive_noinc(&sh.full[slot]);
+    };
+    TileReq r0, r1, r2;
+    request(r0); request(r1); request(r2);
+    for (;;) {
+      if (!r0.have) break;
+      issue(r0); request(r0);
+      if (!r1.have) break;
+      issue(r1); request(r1);
+      if (!r2.have) break;
+      issue(r2); request(r2);
     }
   } else if (warp == 14) {
     // ================================ S issuer ========================================================
@@ -238,7 +275,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
       mbar_wait(&sh.full[slot_of(n)], phase_of(n));
       mbar_wait(&sh.s_free[w], (j & 1) ^ 1);
       if (lane == 0) TC_TRACE(k, 7);
-      tc_fence_after();   // (the producers fenced generic->async proxy before arriving on `full`)
+      fence_proxy_async();   // cp.async (generic proxy) tile writes -> tcgen05.mma operand reads (async proxy)
+      tc_fence_after();
       const uint32_t k0 = tiles_u32 + slot_of(n - 1) * TC_TILE_BYTES, k1 = tiles_u32 + slot_of(n) * TC_TILE_BYTES;
       const uint32_t qa = desc_lo(p.nb ? k1 : k0, 16), b0 = desc_lo(k0, 16), b1 = desc_lo(k1, 16);
       const uint32_t s_t = tmem + w * 256;
@@ -264,6 +302,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
       const uint32_t p_t = tmem + w * 256, o_t = p_t + 128;
       const bool rel_own = !wo.next_reuses();
       mbar_wait(&sh.p_full[w], j & 1);
+      fence_proxy_async();   // V tiles were written by cp.async (their `full` phases completed before S(k) was issued)
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
@@ -295,47 +334,115 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
       mbar_wait(&sh.full[sl1], phase_of(n));
       const TcTileMeta &m0 = sh.meta[sl0], &m1 = sh.meta[sl1];
       const TcTileMeta &mq = p.nb ? m1 : m0;
-      const float qi = static_cast<float>(mq.pos[row] + 1);          // q_info = pos + 1 (EA:201)
-      const float own_ki = mq.kinfo[row];
+      const int mypos = mq.pos[row];
+      const float qi = static_cast<float>(mypos + 1);               // q_info = pos + 1 (EA:201)
       const int tk = mq.tk[row];
-      const float wmin = fminf(fminf(m0.vmin[0], m0.vmin[1]), fminf(m1.vmin[0], m1.vmin[1]));
-      const float wmax = fmaxf(fmaxf(m0.vmax[0], m0.vmax[1]), fmaxf(m1.vmax[0], m1.vmax[1]));
-      // softmax shift (log2 domain): the un-masked self score |q_i|^2 * kscale_i bounds every score of the row
-      const float ksc_i = mq.kscl[row];
-      const float r_i = 0.125f * kLog2e / ksc_i;                      // sqrt(mean(q^2) + eps)
-      const float self2 = 64.f * fmaxf(r_i * r_i - 1e-6f, 0.f) * ksc_i;
-      const bool visible = p.causal ? (wmin < qi) : !(wmin == qi && wmax == qi);
-      // Fast path (warp-uniform): no padding mask, and masked-out entries contribute exp2(<= -144269) == 0 exactly, so
-      // ONE compare decides keep / drop.  A causal row with no visible key (only its own "-1e5" class, EA:153-155)
-      // keeps exactly that class instead: compare against qi + 0.5 (positions are integers) and put the -1e5 back
-      // into the reported log-sum-exp.
-      const bool fast = !p.masked && (p.causal || __all_sync(0xffffffffu, visible));
-      float m2 = self2, q_cmp = qi, lse_off = 0.f;
-      if (fast) {
-        if (!visible) { q_cmp = qi + 0.5f; lse_off = -1e5f; }
+      const float2 am = mq.am[row];                                  // query-side scale a_i, self score m_i (log2 domain)
+      const float a_i = am.x;
+      float m2 = am.y, lse_off = 0.f;
+      uint32_t need = 0xffu, full = 0u;                              // per 32-column block of the window (warp-uniform)
+      int lo_lb = 0, hi_lb = 128, lo_own = 0, hi_own = 128;          // visible column interval in each window tile
+      const bool sorted = p.causal && !p.masked && p.nb == 1;       // warp-uniform fast path
+      if (sorted) {
+        // Both tiles are ordered by position (rank r at row r ^ flip), so "key position < query position" (EA:150-152 and the
+        // self mask EA:153-155, whose -1e5 entries underflow to exactly 0 next to any visible key) is an interval of columns.
+        const int c_lb = wk.c > 0 ? wk.c - 1 : p.n_chunks - 1;      // cyclic look-back (EA:137-141)
+        const int flip_own = (wk.c & 1) ? 127 : 0, flip_lb = (c_lb & 1) ? 127 : 0;
+        const int myrank = row ^ flip_own;
+        int blo = 0, bhi = 128;                                      // look-back keys with position < mypos (lower bound)
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int mid = (blo + bhi) >> 1;
+          const int v = m0.pos[(mid & 127) ^ flip_lb];
+          const bool go = blo < bhi;
+          if (go && v < mypos) blo = mid + 1;
+          else if (go) bhi = mid;
+        }
+        int bound = blo, self_incl = 0;
+        if (bound == 0 && myrank == 0) {
+          // no visible key at all: the row keeps exactly its "-1e5" class (itself, and its copy from the previous hash
+          // round if the look-back tile holds it), and the -1e5 goes back into the reported log-sum-exp
+          self_incl = 1; lse_off = -1e5f;
+          bound = (m0.pos[flip_lb] == mypos) ? 1 : 0;
+        }
+        if (flip_lb) { lo_lb = 128 - bound; hi_lb = 128; } else { lo_lb = 0; hi_lb = bound; }
+        if (flip_own) { lo_own = row + 1 - self_incl; hi_own = 128; } else { lo_own = 0; hi_own = row + self_incl; }
+        const int lb_lo_min = __reduce_min_sync(0xffffffffu, lo_lb), lb_lo_max = __reduce_max_sync(0xffffffffu, lo_lb);
+        const int lb_hi_min = __reduce_min_sync(0xffffffffu, hi_lb), lb_hi_max = __reduce_max_sync(0xffffffffu, hi_lb);
+        const int ow_lo_min = __reduce_min_sync(0xffffffffu, lo_own), ow_lo_max = __reduce_max_sync(0xffffffffu, lo_own);
+        const int ow_hi_min = __reduce_min_sync(0xffffffffu, hi_own), ow_hi_max = __reduce_max_sync(0xffffffffu, hi_own);
+        need = 0u;
+#pragma unroll
+        for (int bq = 0; bq < 4; ++bq) {
+          const int c0 = 32 * bq, c1 = c0 + 32;
+          if (!(lb_hi_max <= c0 || lb_lo_min >= c1)) need |= 1u << bq;
+          if (lb_lo_max <= c0 && lb_hi_min >= c1) full |= 1u << bq;
+          if (!(ow_hi_max <= c0 || ow_lo_min >= c1)) need |= 16u << bq;
+          if (ow_lo_max <= c0 && ow_hi_min >= c1) full |= 16u << bq;
+        }
       } else {
-        m2 = visible ? self2 : self2 - kSelf;
+        const float own_ki = mq.kinfo[row];
+        const float wmin = fminf(fminf(m0.vmin[0], m0.vmin[1]), fminf(m1.vmin[0], m1.vmin[1]));
+        const float wmax = fmaxf(fmaxf(m0.vmax[0], m0.vmax[1]), fmaxf(m1.vmax[0], m1.vmax[1]));
+        const bool visible = p.causal ? (wmin < qi) : !(wmin == qi && wmax == qi);
+        if (!visible) m2 -= kSelf;                                    // only the "-1e5" class is left: shift by it
         if (p.masked && own_ki < 0.f) m2 = -kBig;                     // padding query: any finite result
       }
-      const float *kin0 = m0.kinfo, *kin1 = m1.kinfo, *ksc0 = m0.kscl, *ksc1 = m1.kscl;
+      const uint64_t a2 = pk2(a_i, a_i), mm2 = pk2(-m2, -m2);
       if (row == 0) TC_TRACE(wk.k, 6);
       mbar_wait(&sh.s_full[w], j & 1);
       tc_fence_after();
       if (row == 0) TC_TRACE(wk.k, 2);
       float l = 0.f;
+      uint64_t l2 = 0ull;
       uint32_t ra[32], rb[32];
-      tmem_ld32(t_lane, ra);
-#pragma unroll 1
-      for (int kc = 0; kc < 8; kc += 2) {
+      // Blocks in ascending order (P block b overwrites S columns [16b, 16b+16), already consumed); loads run one needed
+      // block ahead; skipped blocks get zeros, stored only after the loads they could overlap have completed.
+      auto process = [&](const uint32_t (&r)[32], int bq) {
+        if (sorted) {
+          if ((full >> bq) & 1u) {
+            softmax_block_full(r, a2, mm2, t_lane + bq * 16, l2);
+          } else {
+            const int base = (bq & 3) * 32;
+            softmax_block_interval(r, a2, mm2, (bq < 4 ? lo_lb : lo_own) - base, (bq < 4 ? hi_lb : hi_own) - base, t_lane + bq * 16, l2);
+          }
+        } else {
+          softmax_block_generic(r, (bq < 4 ? m0.kinfo : m1.kinfo) + (bq & 3) * 32, qi, a_i, m2, p.causal, p.masked, t_lane + bq * 16, l);
+        }
+      };
+      auto zero_until = [&](int from, int to) {                       // zero P for the skipped blocks in [from, to)
+        for (int bq = from; bq < to; ++bq) {
+          uint32_t z[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) z[i] = 0u;
+          tmem_st16(t_lane + bq * 16, z);
+        }
+      };
+      auto next_needed = [&](int after) -> int {                     // first needed block > after, or 8
+        const uint32_t rest = need & ~((2u << after) - 1u);
+        return rest ? __ffs(rest) - 1 : 8;
+      };
+      int b0 = need ? __ffs(need) - 1 : 8;
+      if (b0 < 8) tmem_ld32(t_lane + b0 * 32, ra);
+      int done_to = 0;                                                // blocks < done_to are final
+      while (b0 < 8) {
+        const int b1 = next_needed(b0);
         tmem_ld_wait_dep(ra);
-        tmem_ld32(t_lane + (kc + 1) * 32, rb);                        // prefetch the next 32 columns
-        softmax_block(ra, (kc < 4 ? kin0 : kin1) + (kc & 3) * 32, (kc < 4 ? ksc0 : ksc1) + (kc & 3) * 32, fast ? q_cmp : qi, m2, fast, p.causal,
-                      p.masked, t_lane + kc * 16, l);
+        zero_until(done_to, b0);
+        if (b1 < 8) tmem_ld32(t_lane + b1 * 32, rb);
+        process(ra, b0);
+        done_to = b0 + 1;
+        if (b1 >= 8) break;
+        const int b2 = next_needed(b1);
         tmem_ld_wait_dep(rb);
-        if (kc + 2 < 8) tmem_ld32(t_lane + (kc + 2) * 32, ra);
-        softmax_block(rb, (kc < 4 ? kin0 : kin1) + ((kc + 1) & 3) * 32, (kc < 4 ? ksc0 : ksc1) + ((kc + 1) & 3) * 32, fast ? q_cmp : qi, m2, fast,
-                      p.causal, p.masked, t_lane + (kc + 1) * 16, l);
+        zero_until(done_to, b1);
+        if (b2 < 8) tmem_ld32(t_lane + b2 * 32, ra);
+        process(rb, b1);
+        done_to = b1 + 1;
+        b0 = b2;
       }
+      zero_until(done_to, 8);
+      l += lo32(l2) + hi32(l2);
       // hand the row statistics to the epilogue warpgroup (visible through the p_full -> o_full chain)
       sh.row_il[w][row] = l > 0.f ? 1.f / l : 0.f;
       sh.row_lse[w][row] = l > 0.f ? (m2 + log2f(l)) * kLn2 + lse_off : -3e9f;
@@ -387,6 +494,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
   }
   tc_fence_before();
   __syncthreads();
+  if (p.trace && tid == 0) p.trace[120 * 8 + blockIdx.x] = clock64() - t_cta_start;   // per-CTA duration (load balance)
   if (warp == 14) tmem_dealloc(tmem, 512);
 }
 

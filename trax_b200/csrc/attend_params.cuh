@@ -11,12 +11,27 @@ struct AttendFwdParams {
   __nv_bfloat16 *o;             // rows addressed as b*o_sb + h*o_sh + round*o_sr + pos*o_sp
   int64_t o_sb, o_sh, o_sr, o_sp;
   float *lse;                   // (BH, N) ticker order
-  const float *qscale;          // (BH, L) per-token key scale (tcgen05 path only)
+  const float *qscale;          // (BH, L) per-token key scale (unused by the forward kernels; kept for the backward)
+  const __nv_bfloat16 *qhat;    // (BH, L, 64) normalised keys q / (8 r)                 } tcgen05 path only
+  const float2 *rowmeta;        // (BH, L) {a = 8 r log2e, m2 = a |qhat|^2}               }
+  const int32_t *sticker2;      // (BH, N) sticker with every chunk re-ordered by position }
   long long *trace;             // debug: per-phase clock64 stamps of CTA 0 (null = off)
   unsigned stagger_ns;          // start delay of the second softmax warpgroup (tcgen05 path)
   int L, H, N, n_chunks, nb, nwin, causal, masked;
 };
 
 int attend_fwd_tc_run(const AttendFwdParams &p, int BH, cudaStream_t stream);
+
+// Auxiliary per-call buffers of the tcgen05 forward path (produced by qscale_run / chunk_possort_run).
+struct FwdAux {
+  float *qscale;
+  float2 *rowmeta;
+  void *qhat;
+  int32_t *sticker2;
+};
+bool attend_fwd_uses_tc(const LshAttnDims &d);
+size_t fwd_aux_bytes(const LshAttnDims &d);
+FwdAux fwd_aux_carve(const LshAttnDims &d, void *ws);
+int fwd_aux_prepare(const LshAttnDims &d, const void *qv, const int32_t *sticker, const FwdAux &aux, cudaStream_t stream);
 
 }  // namespace lsh

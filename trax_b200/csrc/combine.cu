@@ -175,17 +175,22 @@ int bwd_prep_tc_run(const LshAttnDims &d, const void *do_comb, const void *o_com
   return 0;
 }
 
-// qscale[u][t] = log2(e) / (sqrt(mean(q^2) + 1e-6) * sqrt(dq))  — the per-key factor of EA:54-57, 229-231 folded with
-// the exp2 conversion; one value per (unit, token), consumed by the tcgen05 attention kernels.
+// Per-token key normalisation of EA:54-57, 229-231, done once per layer call for the tcgen05 kernels:
+//   qscale[u][t]  = log2(e) / (r * 8),  r = sqrt(mean(q^2) + 1e-6)        (per-key factor; backward kernel)
+//   qhat[u][t][:] = bf16(q / (8 r))                                        (the reference's normalised key)
+//   rowmeta[u][t] = {a, m2}:  a = 8 r log2(e) restores the un-normalised query, q_i·k_j = 8 r_i (qhat_i·qhat_j), so the
+//                   forward kernel uses ONE gathered row as query and as key and its softmax needs no per-key data;
+//                   m2 = a |qhat|^2 = the row's self score in the log2 domain (the analytic softmax shift).
 __global__ void __launch_bounds__(ROW_THREADS) qscale_kernel(const __nv_bfloat16 *__restrict__ qv,
-                                                            float *__restrict__ qscale, int L, int H,
+                                                            float *__restrict__ qscale, float2 *__restrict__ rowmeta,
+                                                            __nv_bfloat16 *__restrict__ qhat, int L, int H,
                                                             int64_t total_rows) {
   const int64_t row = (static_cast<int64_t>(blockIdx.x) * ROW_THREADS + threadIdx.x) >> 3;   // (b, t, h)
   const int ch = threadIdx.x & 7;
   const bool ok = row < total_rows;
   float s = 0.f;
+  float a[8];
   if (ok) {
-    float a[8];
     bf16x8_to_f32(__ldg(reinterpret_cast<const uint4 *>(qv + row * 128) + ch), a);
 #pragma unroll
     for (int i = 0; i < 8; ++i) s = fmaf(a[i], a[i], s);
@@ -193,19 +198,40 @@ __global__ void __launch_bounds__(ROW_THREADS) qscale_kernel(const __nv_bfloat16
   s += __shfl_xor_sync(0xffffffffu, s, 1);
   s += __shfl_xor_sync(0xffffffffu, s, 2);
   s += __shfl_xor_sync(0xffffffffu, s, 4);
+  const float r = sqrtf(s * (1.0f / 64) + 1e-6f);
+  const int64_t h = row % H, bt = row / H;
+  const int64_t b = bt / L, t = bt % L;
+  const int64_t ut = (b * H + h) * L + t;
+  float s2 = 0.f;
+  if (ok && qhat != nullptr) {
+    const float c = 0.125f / r;
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = a[i] * c;
+    const uint4 packed = f32_to_bf16x8(f);
+    bf16x8_to_f32(packed, f);                     // |qhat|^2 of the rounded values the tensor cores will see
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s2 = fmaf(f[i], f[i], s2);
+    *(reinterpret_cast<uint4 *>(qhat + ut * 64) + ch) = packed;
+  }
+  s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+  s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+  s2 += __shfl_xor_sync(0xffffffffu, s2, 4);
   if (ok && ch == 0) {
-    const int64_t h = row % H, bt = row / H;
-    const int64_t b = bt / L, t = bt % L;
-    qscale[(b * H + h) * L + t] = 0.125f * kLog2e / sqrtf(s * (1.0f / 64) + 1e-6f);
+    if (qscale != nullptr) qscale[ut] = 0.125f * kLog2e / r;
+    if (rowmeta != nullptr) {
+      const float am = 8.f * r * kLog2e;
+      rowmeta[ut] = make_float2(am, am * s2);
+    }
   }
 }
 
-int qscale_run(const LshAttnDims &d, const void *qv, float *qscale, cudaStream_t stream) {
+int qscale_run(const LshAttnDims &d, const void *qv, float *qscale, float2 *rowmeta, void *qhat, cudaStream_t stream) {
   Derived dr = derive(d);
   const int64_t rows = static_cast<int64_t>(dr.BH) * d.L;
   const int64_t blocks = (rows * 8 + ROW_THREADS - 1) / ROW_THREADS;
-  qscale_kernel<<<static_cast<unsigned>(blocks), ROW_THREADS, 0, stream>>>(static_cast<const __nv_bfloat16 *>(qv), qscale,
-                                                                          d.L, d.H, rows);
+  qscale_kernel<<<static_cast<unsigned>(blocks), ROW_THREADS, 0, stream>>>(static_cast<const __nv_bfloat16 *>(qv), qscale, rowmeta,
+                                                                          static_cast<__nv_bfloat16 *>(qhat), d.L, d.H, rows);
   LSH_CHECK_LAUNCH("qscale_kernel");
   return 0;
 }

@@ -71,6 +71,9 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(src));
 }
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(src));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -128,9 +131,13 @@ __device__ __forceinline__ float quad_sum(float v) {
 
 // 2^x on the SFU (MUFU.EX2), flush-to-zero: one instruction, ~2 ulp; exp2(-huge) == 0 exactly.
 __device__ __forceinline__ float fast_exp2(float x) {
+#if defined(LSH_EXP_NOMUFU)
+  return x * 1.0001f;
+#else
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
   return y;
+#endif
 }
 
 constexpr float kLog2e = 1.4426950408889634f;

@@ -129,10 +129,98 @@ __global__ void __launch_bounds__(HASH_THREADS) hash_kernel(const HashParams p) 
   }
 }
 
+// Fast variant: the rotation columns of ALL hash rounds stay resident in shared memory (one load per CTA, no per-round
+// barriers) and the row stride TC = n_hashes * Rpad is a compile-time constant so that every LDS has an immediate
+// offset.  Same arithmetic, same order => same bits.  Optionally emits the per-token key scale (qscale) from the q
+// registers it already holds.
+template <typename T, int TC>
+__global__ void __launch_bounds__(HASH_THREADS) hash_all_rounds_kernel(const HashParams p, float *__restrict__ qscale) {
+  constexpr int DQ = 64;
+  extern __shared__ __align__(16) float s_rot[];   // [DQ][TC], column = round * Rpad + c
+  const int u = blockIdx.y;
+  const int b = u / p.H, h = u % p.H;
+  const int t = blockIdx.x * HASH_THREADS + threadIdx.x;
+  const bool active = t < p.L;
+  const float *rot_u = p.rot + static_cast<int64_t>(u) * DQ * p.nh * p.R;
+  for (int i = threadIdx.x; i < DQ * TC; i += HASH_THREADS) {
+    const int f = i / TC, col = i % TC;
+    const int round = col / p.Rpad, c = col % p.Rpad;
+    s_rot[i] = (c < p.R) ? __ldg(rot_u + (static_cast<int64_t>(f) * p.nh + round) * p.R + c) : 0.f;
+  }
+  float q[DQ];
+  if (active) {
+    const T *src = reinterpret_cast<const T *>(p.vecs) + b * p.stride_b + h * p.stride_h + static_cast<int64_t>(t) * p.stride_t;
+    load_vec64<T>(src, q);
+  } else {
+#pragma unroll
+    for (int i = 0; i < DQ; ++i) q[i] = 0.f;
+  }
+  if (qscale != nullptr && active) {
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < DQ; ++i) ss = fmaf(q[i], q[i], ss);
+    qscale[static_cast<int64_t>(u) * p.L + t] = 0.125f * kLog2e / sqrtf(ss * (1.0f / 64) + 1e-6f);
+  }
+  bool valid_tok = true;
+  if (p.mask != nullptr && active) valid_tok = p.mask[static_cast<int64_t>(b) * p.L + t] != 0;
+  __syncthreads();
+  int32_t *out = p.buckets + static_cast<int64_t>(u) * p.buckets_stride + t;
+  for (int round = 0; round < p.nh; ++round) {
+    int fi = 0, pos = 0, half = p.factors[0] >> 1;
+    float best_pos = -INFINITY, best_neg = INFINITY;
+    int idx_pos = 0, idx_neg = 0, bucket = 0, prod = 1;
+    for (int c0 = 0; c0 < p.Rpad; c0 += HASH_COLS) {
+      float acc[HASH_COLS];
+#pragma unroll
+      for (int j = 0; j < HASH_COLS; ++j) acc[j] = 0.f;
+      const float *sr = s_rot + round * p.Rpad + c0;
+#pragma unroll
+      for (int f = 0; f < DQ; ++f) {
+        const float4 r0 = *reinterpret_cast<const float4 *>(sr + f * TC);
+        const float4 r1 = *reinterpret_cast<const float4 *>(sr + f * TC + 4);
+        acc[0] = __fmaf_rn(q[f], r0.x, acc[0]); acc[1] = __fmaf_rn(q[f], r0.y, acc[1]);
+        acc[2] = __fmaf_rn(q[f], r0.z, acc[2]); acc[3] = __fmaf_rn(q[f], r0.w, acc[3]);
+        acc[4] = __fmaf_rn(q[f], r1.x, acc[4]); acc[5] = __fmaf_rn(q[f], r1.y, acc[5]);
+        acc[6] = __fmaf_rn(q[f], r1.z, acc[6]); acc[7] = __fmaf_rn(q[f], r1.w, acc[7]);
+      }
+#pragma unroll
+      for (int j = 0; j < HASH_COLS; ++j) {
+        if (c0 + j < p.R) {
+          const float x = acc[j];
+          if (x > best_pos) { best_pos = x; idx_pos = pos; }
+          if (x < best_neg) { best_neg = x; idx_neg = pos; }
+          ++pos;
+          if (pos == half) {
+            const int am = (best_pos >= -best_neg) ? idx_pos : half + idx_neg;
+            bucket += prod * am;
+            prod *= p.factors[fi];
+            ++fi;
+            half = (fi < p.n_factors) ? (p.factors[fi] >> 1) : 0x7fffffff;
+            pos = 0; best_pos = -INFINITY; best_neg = INFINITY; idx_pos = 0; idx_neg = 0;
+          }
+        }
+      }
+    }
+    if (active) {
+      if (!valid_tok) bucket = p.n_buckets - 1;
+      out[static_cast<int64_t>(round) * p.L] = bucket + round * p.n_buckets;
+    }
+  }
+}
+
+template <typename T, int TC>
+static int launch_hash_fast(const HashParams &p, int BH, float *qscale, cudaStream_t stream) {
+  LSH_OPT_IN_SMEM((hash_all_rounds_kernel<T, TC>));
+  dim3 grid((p.L + HASH_THREADS - 1) / HASH_THREADS, BH);
+  hash_all_rounds_kernel<T, TC><<<grid, HASH_THREADS, 64 * TC * sizeof(float), stream>>>(p, qscale);
+  LSH_CHECK_LAUNCH("hash_all_rounds_kernel");
+  return 0;
+}
+
 template <typename T>
 static int launch_hash(const LshAttnDims &d, const void *vecs, int64_t sb, int64_t sh, int64_t st,
                        const float *rot, const uint8_t *mask, int32_t *buckets, int64_t bstride,
-                       cudaStream_t stream) {
+                       float *qscale, cudaStream_t stream) {
   Derived dr = derive(d);
   HashParams p;
   p.vecs = vecs; p.stride_b = sb; p.stride_h = sh; p.stride_t = st;
@@ -143,6 +231,16 @@ static int launch_hash(const LshAttnDims &d, const void *vecs, int64_t sb, int64
   size_t smem = static_cast<size_t>(64) * p.Rpad * sizeof(float);
   if (smem > 200 * 1024) return set_error("lsh_hash: sum(factors)/2 = %d too large for shared memory", dr.R);
   if (d.masked && mask == nullptr) return set_error("lsh_hash: dims.masked set but mask == NULL");
+  switch (d.nh * p.Rpad) {          // all rounds resident, compile-time stride
+    case 16: return launch_hash_fast<T, 16>(p, dr.BH, qscale, stream);
+    case 32: return launch_hash_fast<T, 32>(p, dr.BH, qscale, stream);
+    case 64: return launch_hash_fast<T, 64>(p, dr.BH, qscale, stream);
+    case 128: return launch_hash_fast<T, 128>(p, dr.BH, qscale, stream);
+    case 192: return launch_hash_fast<T, 192>(p, dr.BH, qscale, stream);
+    case 256: return launch_hash_fast<T, 256>(p, dr.BH, qscale, stream);
+    default: break;
+  }
+  if (qscale != nullptr) return set_error("lsh_hash: fused qscale needs a specialised column count (got %d)", d.nh * p.Rpad);
   LSH_OPT_IN_SMEM(hash_kernel<T>);
   dim3 grid((d.L + HASH_THREADS - 1) / HASH_THREADS, dr.BH);
   hash_kernel<T><<<grid, HASH_THREADS, smem, stream>>>(p);
@@ -155,14 +253,14 @@ int hash_bf16_qv(const LshAttnDims &d, const void *qv, const float *rot, const u
   Derived dr = derive(d);
   return launch_hash<__nv_bfloat16>(d, qv, static_cast<int64_t>(d.L) * d.H * dr.QV, dr.QV,
                                     static_cast<int64_t>(d.H) * dr.QV, rot, mask, buckets, bstride,
-                                    stream);
+                                    nullptr, stream);
 }
 
 int hash_f32_vecs(const LshAttnDims &d, const float *vecs, const float *rot, const uint8_t *mask,
                   int32_t *buckets, int64_t bstride, cudaStream_t stream) {
   return launch_hash<float>(d, vecs, static_cast<int64_t>(d.H) * d.L * d.dq,
                             static_cast<int64_t>(d.L) * d.dq, d.dq, rot, mask, buckets, bstride,
-                            stream);
+                            nullptr, stream);
 }
 
 }  // namespace lsh

@@ -270,4 +270,44 @@ int sort_run(const LshAttnDims &d, const int32_t *buckets, int64_t bstride, int3
   return 0;
 }
 
+// Re-orders every 128-slot chunk of `sticker` by token position (ascending; ties — only possible when a chunk straddles
+// two hash rounds — keep slot order).  Attention within a chunk window is a sum over keys and its rows are scattered
+// back by ticker, so the order inside a chunk is free: with position-sorted tiles the causal mask of EA:150-152 becomes
+// an interval of column indices per row, whole 32-column blocks are either fully visible or skipped, and no per-key
+// position has to be loaded in the softmax loop.  One warp per chunk, rank by counting (128 x 4 compares per lane).
+__global__ void __launch_bounds__(256) chunk_possort_kernel(const int32_t *__restrict__ sticker, int32_t *__restrict__ sticker2,
+                                                            int L, int64_t total_chunks) {
+  __shared__ int spos[8][128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t chunk = static_cast<int64_t>(blockIdx.x) * 8 + warp;
+  if (chunk >= total_chunks) return;
+  const int32_t *src = sticker + chunk * 128;
+  int tk[4], pos[4], rank[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    tk[j] = __ldg(src + lane + 32 * j);
+    pos[j] = tk[j] % L;
+    spos[warp][lane + 32 * j] = pos[j];
+    rank[j] = 0;
+  }
+  __syncwarp();
+#pragma unroll 8
+  for (int i = 0; i < 128; ++i) {
+    const int v = spos[warp][i];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) rank[j] += (v < pos[j] || (v == pos[j] && i < lane + 32 * j)) ? 1 : 0;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) sticker2[chunk * 128 + rank[j]] = tk[j];
+}
+
+int chunk_possort_run(const LshAttnDims &d, const int32_t *sticker, int32_t *sticker2, cudaStream_t stream) {
+  Derived dr = derive(d);
+  if (d.C != 128) return set_error("chunk_possort: chunk_len must be 128");
+  const int64_t chunks = static_cast<int64_t>(dr.BH) * dr.n_chunks;
+  chunk_possort_kernel<<<static_cast<unsigned>((chunks + 7) / 8), 256, 0, stream>>>(sticker, sticker2, d.L, chunks);
+  LSH_CHECK_LAUNCH("chunk_possort_kernel");
+  return 0;
+}
+
 }  // namespace lsh

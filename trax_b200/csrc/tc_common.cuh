@@ -57,6 +57,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 #endif
   }
 }
+// The mbarrier receives one (pre-counted) arrival once every cp.async issued so far by this thread has landed: tiles are
+// signalled by the copy engine itself, so a producer never blocks on its own loads and many tiles stay in flight.
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
 // generic-proxy writes (st.shared / cp.async) -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
