@@ -10,13 +10,13 @@ keys = torch.arange(2 * B * H, dtype=torch.int32, device='cuda').reshape(B * H, 
 rot, _ = ops.make_rotations(dims, keys)
 sticker, _ = ops.sort(dims, ops.hash_qv(dims, qv, rot))
 ops.attend_fwd(dims, qv, sticker); torch.cuda.synchronize()
-tr = torch.zeros(120 * 8 + 148, dtype=torch.int64, device='cuda')
+tr = torch.zeros(120 * 16 + 148 + 120 * 12, dtype=torch.int64, device='cuda')
 lib = ctypes.CDLL(_lib.LIB_PATH); lib.lsh_debug_set_trace(ctypes.c_void_p(tr.data_ptr()))
 ops.attend_fwd(dims, qv, sticker); torch.cuda.synchronize()
 lib.lsh_debug_set_trace(None)
-percta = tr.cpu()[120 * 8:]; t = tr.cpu()[:120 * 8].view(120, 8)
+percta = tr.cpu()[120 * 16:120 * 16 + 148]; t2 = tr.cpu()[120 * 16 + 148:].view(120, 4, 3); t = tr.cpu()[:120 * 16].view(120, 16)
 t0 = int(t[t > 0].min())
-names = ['S_iss', 'PV_iss', 's_full', 'passdone', 'o_full', 'epi_done', 'arr_swait', 'S_start']
+names = ['S_iss', 'PV_iss', 's_full', 'passdone', 'o_full', 'epi_done', 'arr_swait', 'S_start', 'PV0woke', 'PV0iss', 'PV1woke', 'PV1iss', 'S1start', 'w4sfull', 'w4end', '-']
 print('k ' + ' '.join('%9s' % n for n in names))
 for k in list(range(0, 24)) + list(range(100, 112)):
   print('%3d ' % k + ' '.join('%9d' % (int(v) - t0 if v > 0 else -1) for v in t[k]))
@@ -35,3 +35,10 @@ print('TIME lib=%s attend_fwd %.3f ms' % (os.path.basename(_lib.LIB_PATH), e0.el
 pc = percta.numpy()
 print('PER-CTA cycles: min %d  median %d  max %d  (first 16: %s)' % (pc.min(), np.median(pc), pc.max(), pc[:16].tolist()))
 print('slowest CTAs:', np.argsort(-pc)[:12].tolist(), np.sort(pc)[-12:][::-1].tolist())
+
+print('per-warp pass: k | (start-t0, dur, needed blocks, full blocks) x 4 warps')
+for k in range(16, 26):
+  print('%3d ' % k + '  '.join('%8d %5d (ldwait %5d) %d/%d' % (int(t2[k, w, 0]) - t0, int(t2[k, w, 1] - t2[k, w, 0]), int(t2[k, w, 2]) // 256, (int(t2[k, w, 2]) % 256) // 16, int(t2[k, w, 2]) % 16) for w in range(4)))
+d = (t2[8:108, :, 1] - t2[8:108, :, 0]).numpy(); nb = ((t2[8:108, :, 2] % 256) // 16).numpy()
+print('mean ld-wait cycles per warp pass:', (t2[8:108, :, 2] // 256).numpy().mean(0))
+print('mean pass cycles per warp:', d.mean(0), ' mean needed blocks per warp:', nb.mean(0), ' cycles per needed block: %.0f' % (d.sum() / nb.sum()))

@@ -43,11 +43,18 @@ struct __align__(16) TcTileMeta {
 struct __align__(16) TcShared {
   TcTileMeta meta[TC_NST];
   uint64_t full[TC_NST], empty[TC_NST];
-  uint64_t s_full[2], p_full[2], o_full[2], s_free[2];
-  float row_il[2][TC_C], row_lse[2][TC_C];   // softmax -> epilogue hand-off per TMEM region
+  uint64_t s_full[3], p_full[3], hb_free[3];     // per half-chunk score buffer (128 TMEM columns each)
+  uint64_t o_full[2], o_free[2], l_full[2];      // per output accumulator (64 TMEM columns each) / row statistics
+  float row_l[2][2][TC_C], row_m2[2][TC_C], row_off[2][TC_C];   // softmax -> epilogue hand-off per output buffer
   int row_tk[2][TC_C];
   uint32_t tmem_base;
 };
+
+// TMEM map (512 columns): three half-chunk score buffers S/P at 0, 128, 256 (a chunk's 256 keys are scored as two
+// independent halves: half h = 2 * chunk + part lives in buffer h % 3), two output accumulators O at 384 and 448.
+// Nothing but the PV MMA of the same half stands between a buffer's softmax pass and its next score MMA, and the
+// epilogue (O -> HBM) is off that path entirely.
+constexpr uint32_t TC_O_COL = 384;
 
 // Enumerates the work items of one CTA and the tile sequence numbers they use.
 struct Walker {
@@ -70,7 +77,7 @@ __device__ __forceinline__ uint32_t slot_of(int n) { return static_cast<uint32_t
 __device__ __forceinline__ uint32_t phase_of(int n) { return static_cast<uint32_t>((n / TC_NST) & 1); }
 
 // trace slots per chunk: 0 S issued, 1 PV issued, 2 s_full seen, 3 pass done, 4 o_full seen, 5 epilogue done, 6 tile issued, 7 tile landed
-#define TC_TRACE(k, slot) do { if (p.trace && blockIdx.x == 0 && (k) < 120) p.trace[(k) * 8 + (slot)] = clock64(); } while (0)
+#define TC_TRACE(k, slot) do { if (p.trace && blockIdx.x == 0 && (k) < 120) p.trace[(k) * 16 + (slot)] = clock64(); } while (0)
 
 constexpr float kBig = 1e9f * kLog2e, kSelf = 1e5f * kLog2e;   // EA:152-159 masks, log2 domain
 
@@ -150,7 +157,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
   uint8_t *tiles = smem;                                    // [TC_NST][K 16 KB | V 16 KB]
   __shared__ TcShared sh;                                   // static: keeps metadata accesses in the shared space (LDS)
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp_hw = tid >> 5;
+#if defined(LSH_EXP_REVROLES)
+  const int warp = 15 - warp_hw;     // experiment: softmax warps get the highest hardware warp ids
+#else
+  const int warp = warp_hw;
+#endif
   const long long t_cta_start = clock64();
   // contiguous, balanced range of chunks for this CTA
   const int g0 = static_cast<int>(static_cast<int64_t>(total_chunks) * blockIdx.x / gridDim.x);
@@ -159,9 +171,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
   if (warp == 14) tmem_alloc(&sh.tmem_base, 512);
   if (tid == 0) {
     for (int i = 0; i < TC_NST; ++i) { mbar_init(&sh.full[i], 64); mbar_init(&sh.empty[i], 1); }
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&sh.s_full[i], 1); mbar_init(&sh.p_full[i], 4);     // one arrival per softmax warp of the half's warpgroup
+      mbar_init(&sh.hb_free[i], 1);
+    }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&sh.s_full[i], 1); mbar_init(&sh.p_full[i], 128);
-      mbar_init(&sh.o_full[i], 1); mbar_init(&sh.s_free[i], 128);
+      mbar_init(&sh.o_full[i], 1); mbar_init(&sh.o_free[i], 4);     // one arrival per epilogue warp
+      mbar_init(&sh.l_full[i], 8);                                   // one arrival per softmax warp (both warpgroups)
     }
     fence_mbar_init();
   }
@@ -265,120 +281,131 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
     }
   } else if (warp == 14) {
     // ================================ S issuer ========================================================
-    // S(k) goes out as soon as its two tiles have landed and its TMEM region has been drained.  The warp runs
-    // converged (warp-uniform values); one elected lane issues.  Descriptors: constant hi, lo = base + (offset >> 4).
+    // Half h of chunk k (part 0: the first window tile's keys, part 1: the second's) goes out as soon as its tiles have
+    // landed and its score buffer has been consumed by the PV MMA three halves earlier.  The warp runs converged
+    // (warp-uniform values); one elected lane issues.  Descriptors: constant hi, lo = base + (offset >> 4).
     constexpr uint32_t HI = desc_hi(1024);
     for (Walker ws(g0, g1, p.n_chunks); ws.valid(); ws.next()) {
       const int k = ws.k, n = ws.n;
-      const uint32_t w = k & 1, j = k >> 1;
       mbar_wait(&sh.full[slot_of(n - 1)], phase_of(n - 1));
       mbar_wait(&sh.full[slot_of(n)], phase_of(n));
-      mbar_wait(&sh.s_free[w], (j & 1) ^ 1);
-      if (lane == 0) TC_TRACE(k, 7);
-      fence_proxy_async();   // cp.async (generic proxy) tile writes -> tcgen05.mma operand reads (async proxy)
-      tc_fence_after();
       const uint32_t k0 = tiles_u32 + slot_of(n - 1) * TC_TILE_BYTES, k1 = tiles_u32 + slot_of(n) * TC_TILE_BYTES;
-      const uint32_t qa = desc_lo(p.nb ? k1 : k0, 16), b0 = desc_lo(k0, 16), b1 = desc_lo(k1, 16);
-      const uint32_t s_t = tmem + w * 256;
-      if (elect_one()) {
+      const uint32_t qa = desc_lo(p.nb ? k1 : k0, 16);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) umma_ss2(s_t, qa + ks * 2, HI, b0 + ks * 2, HI, TC_IDESC_S, ks > 0);
+      for (int part = 0; part < 2; ++part) {
+        const uint32_t h = 2u * k + part, hb = h % 3u, j = h / 3u;
+        mbar_wait(&sh.hb_free[hb], (j & 1) ^ 1);
+        if (lane == 0) TC_TRACE(k, part == 0 ? 7 : 12);
+        // no proxy fence: the tile's mbarrier phase completes when its cp.async copies have landed, which is what the UMMA
+        // operand reads are ordered after (same protocol as CUTLASS's sm100 cp.async mainloop)
+        tc_fence_after();
+        const uint32_t kb = desc_lo(part ? k1 : k0, 16), s_t = tmem + hb * 128;
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) umma_ss2(s_t + 128, qa + ks * 2, HI, b1 + ks * 2, HI, TC_IDESC_S, ks > 0);
-        umma_commit(&sh.s_full[w]);
+          for (int ks = 0; ks < 4; ++ks) umma_ss2(s_t, qa + ks * 2, HI, kb + ks * 2, HI, TC_IDESC_S, ks > 0);
+          umma_commit(&sh.s_full[hb]);
+        }
+        __syncwarp();
       }
-      __syncwarp();
       if (lane == 0) TC_TRACE(k, 0);
     }
   } else if (warp == 15) {
     // ================================ PV issuer =======================================================
-    // A second issuing warp so that PV(k) never queues behind an S that is still waiting for tiles.
+    // A second issuing warp so that a PV never queues behind a score MMA that is still waiting for tiles.
     constexpr uint32_t HI = desc_hi(1024);
     for (Walker wo(g0, g1, p.n_chunks); wo.valid(); wo.next()) {
       const int k = wo.k, n = wo.n;
-      const uint32_t w = k & 1, j = k >> 1;
-      const uint32_t v0 = desc_lo(tiles_u32 + slot_of(n - 1) * TC_TILE_BYTES + TC_C * 128, 1024);
-      const uint32_t v1 = desc_lo(tiles_u32 + slot_of(n) * TC_TILE_BYTES + TC_C * 128, 1024);
-      const uint32_t p_t = tmem + w * 256, o_t = p_t + 128;
+      const uint32_t ob = k & 1, jo = k >> 1;
+      const uint32_t o_t = tmem + TC_O_COL + ob * 64;
       const bool rel_own = !wo.next_reuses();
-      mbar_wait(&sh.p_full[w], j & 1);
-      fence_proxy_async();   // V tiles were written by cp.async (their `full` phases completed before S(k) was issued)
-      tc_fence_after();
-      if (elect_one()) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) umma_ts2(o_t, p_t + i * 8, v0 + i * 128, HI, TC_IDESC_O, i > 0);
+      for (int part = 0; part < 2; ++part) {
+        const uint32_t h = 2u * k + part, hb = h % 3u, j = h / 3u;
+        const uint32_t vt = desc_lo(tiles_u32 + slot_of(part ? n : n - 1) * TC_TILE_BYTES + TC_C * 128, 1024);
+        const uint32_t p_t = tmem + hb * 128;
+        mbar_wait(&sh.p_full[hb], j & 1);
+        if (lane == 0) TC_TRACE(k, 8 + 2 * part);
+        if (part == 0) mbar_wait(&sh.o_free[ob], (jo & 1) ^ 1);     // the epilogue two chunks back has drained this O
+        tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) umma_ts2(o_t, p_t + 64 + i * 8, v1 + i * 128, HI, TC_IDESC_O, 1);
-        umma_commit(&sh.o_full[w]);
-        // S(k) (other issuer) finished before P(k) existed, so every reader of the look-back tile is covered
-        umma_commit(&sh.empty[slot_of(n - 1)]);
-        if (rel_own) umma_commit(&sh.empty[slot_of(n)]);   // nobody will reuse the own tile
+          for (int i = 0; i < 8; ++i) umma_ts2(o_t, p_t + i * 8, vt + i * 128, HI, TC_IDESC_O, (part > 0 || i > 0) ? 1u : 0u);
+          umma_commit(&sh.hb_free[hb]);
+          if (part == 0) {
+            // the score MMAs that read this tile (other issuer) finished before their P existed: every reader is covered
+            umma_commit(&sh.empty[slot_of(n - 1)]);
+          } else {
+            umma_commit(&sh.o_full[ob]);
+            if (rel_own) umma_commit(&sh.empty[slot_of(n)]);   // nobody will reuse the second tile
+          }
+        }
+        __syncwarp();
+        if (lane == 0) TC_TRACE(k, 9 + 2 * part);
       }
-      __syncwarp();
       if (lane == 0) TC_TRACE(k, 1);
     }
   } else if (warp < 8) {
     // ================================ softmax warpgroups ==============================================
-    const uint32_t w = warp >> 2;                          // warpgroup 0 / 1 <-> TMEM region
-    const int row = (warp & 3) * 32 + lane;                // query row == TMEM lane (lane quarter = warp id % 4)
-    const uint32_t t_lane = tmem + w * 256 + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-    // Start the second warpgroup half a period late: the two groups then tend to alternate (one in its softmax pass while
-    // the other waits for MMAs / runs its epilogue) instead of contending for the same issue slots in lockstep.
-    if (w == 1 && p.stagger_ns > 0) __nanosleep(p.stagger_ns);
+    // Column split: warpgroup 0 owns the look-back tile's 128 score columns of EVERY chunk, warpgroup 1 the own tile's.
+    // Chunks alternate between the two TMEM regions; a warp that finishes its (position-dependent) share early moves on
+    // to the next chunk, where the row order is reversed and it is the heavy one.
+    const uint32_t wg = warp >> 2;
+    const int row = (warp_hw & 3) * 32 + lane;                // query row == TMEM lane (lane quarter = warp id % 4)
+    const uint32_t t_wg = tmem + (static_cast<uint32_t>((warp_hw & 3) * 32) << 16);
+    const bool sorted = p.causal && !p.masked && p.nb == 1;       // warp-uniform fast path
     for (Walker wk(g0, g1, p.n_chunks); wk.valid(); wk.next()) {
-      if ((wk.k & 1) != static_cast<int>(w)) continue;
       const int n = wk.n;
-      const uint32_t j = wk.k >> 1;
+      const uint32_t h = 2u * wk.k + wg, hb = h % 3u, j = h / 3u;   // my half of this chunk and its score buffer
+      const uint32_t ob = wk.k & 1, jo = wk.k >> 1;
+      const uint32_t t_lane = t_wg + hb * 128;
       const uint32_t sl0 = slot_of(n - 1), sl1 = slot_of(n);
       mbar_wait(&sh.full[sl0], phase_of(n - 1));
       mbar_wait(&sh.full[sl1], phase_of(n));
       const TcTileMeta &m0 = sh.meta[sl0], &m1 = sh.meta[sl1];
       const TcTileMeta &mq = p.nb ? m1 : m0;
+      const TcTileMeta &mk = wg ? m1 : m0;                          // the tile whose keys this warpgroup scores
       const int mypos = mq.pos[row];
       const float qi = static_cast<float>(mypos + 1);               // q_info = pos + 1 (EA:201)
-      const int tk = mq.tk[row];
       const float2 am = mq.am[row];                                  // query-side scale a_i, self score m_i (log2 domain)
       const float a_i = am.x;
       float m2 = am.y, lse_off = 0.f;
-      uint32_t need = 0xffu, full = 0u;                              // per 32-column block of the window (warp-uniform)
-      int lo_lb = 0, hi_lb = 128, lo_own = 0, hi_own = 128;          // visible column interval in each window tile
-      const bool sorted = p.causal && !p.masked && p.nb == 1;       // warp-uniform fast path
+      uint32_t need = 0xfu, full = 0u;                               // per 32-column block of my tile (warp-uniform)
+      int lo = 0, hi = 128;                                          // visible column interval in my tile
       if (sorted) {
         // Both tiles are ordered by position (rank r at row r ^ flip), so "key position < query position" (EA:150-152 and the
         // self mask EA:153-155, whose -1e5 entries underflow to exactly 0 next to any visible key) is an interval of columns.
         const int c_lb = wk.c > 0 ? wk.c - 1 : p.n_chunks - 1;      // cyclic look-back (EA:137-141)
         const int flip_own = (wk.c & 1) ? 127 : 0, flip_lb = (c_lb & 1) ? 127 : 0;
         const int myrank = row ^ flip_own;
-        int blo = 0, bhi = 128;                                      // look-back keys with position < mypos (lower bound)
+        // a row without any visible key keeps exactly its "-1e5" class (itself, and its copy from the previous hash round
+        // if the look-back tile holds it), and the -1e5 goes back into the reported log-sum-exp
+        const int lb_min = m0.pos[flip_lb];                          // smallest look-back position
+        const bool lonely = myrank == 0 && lb_min >= mypos;
+        if (lonely) lse_off = -1e5f;
+        if (wg == 0) {
+          int blo = 0, bhi = 128;                                    // look-back keys with position < mypos (lower bound)
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int mid = (blo + bhi) >> 1;
-          const int v = m0.pos[(mid & 127) ^ flip_lb];
-          const bool go = blo < bhi;
-          if (go && v < mypos) blo = mid + 1;
-          else if (go) bhi = mid;
+          for (int it = 0; it < 8; ++it) {
+            const int mid = (blo + bhi) >> 1;
+            const int v = m0.pos[(mid & 127) ^ flip_lb];
+            const bool go = blo < bhi;
+            if (go && v < mypos) blo = mid + 1;
+            else if (go) bhi = mid;
+          }
+          const int bound = lonely ? (lb_min == mypos ? 1 : 0) : blo;
+          if (flip_lb) { lo = 128 - bound; hi = 128; } else { lo = 0; hi = bound; }
+        } else {
+          const int self_incl = lonely ? 1 : 0;
+          if (flip_own) { lo = row + 1 - self_incl; hi = 128; } else { lo = 0; hi = row + self_incl; }
         }
-        int bound = blo, self_incl = 0;
-        if (bound == 0 && myrank == 0) {
-          // no visible key at all: the row keeps exactly its "-1e5" class (itself, and its copy from the previous hash
-          // round if the look-back tile holds it), and the -1e5 goes back into the reported log-sum-exp
-          self_incl = 1; lse_off = -1e5f;
-          bound = (m0.pos[flip_lb] == mypos) ? 1 : 0;
-        }
-        if (flip_lb) { lo_lb = 128 - bound; hi_lb = 128; } else { lo_lb = 0; hi_lb = bound; }
-        if (flip_own) { lo_own = row + 1 - self_incl; hi_own = 128; } else { lo_own = 0; hi_own = row + self_incl; }
-        const int lb_lo_min = __reduce_min_sync(0xffffffffu, lo_lb), lb_lo_max = __reduce_max_sync(0xffffffffu, lo_lb);
-        const int lb_hi_min = __reduce_min_sync(0xffffffffu, hi_lb), lb_hi_max = __reduce_max_sync(0xffffffffu, hi_lb);
-        const int ow_lo_min = __reduce_min_sync(0xffffffffu, lo_own), ow_lo_max = __reduce_max_sync(0xffffffffu, lo_own);
-        const int ow_hi_min = __reduce_min_sync(0xffffffffu, hi_own), ow_hi_max = __reduce_max_sync(0xffffffffu, hi_own);
+        const int lo_min = __reduce_min_sync(0xffffffffu, lo), lo_max = __reduce_max_sync(0xffffffffu, lo);
+        const int hi_min = __reduce_min_sync(0xffffffffu, hi), hi_max = __reduce_max_sync(0xffffffffu, hi);
         need = 0u;
 #pragma unroll
         for (int bq = 0; bq < 4; ++bq) {
           const int c0 = 32 * bq, c1 = c0 + 32;
-          if (!(lb_hi_max <= c0 || lb_lo_min >= c1)) need |= 1u << bq;
-          if (lb_lo_max <= c0 && lb_hi_min >= c1) full |= 1u << bq;
-          if (!(ow_hi_max <= c0 || ow_lo_min >= c1)) need |= 16u << bq;
-          if (ow_lo_max <= c0 && ow_hi_min >= c1) full |= 16u << bq;
+          if (!(hi_max <= c0 || lo_min >= c1)) need |= 1u << bq;
+          if (lo_max <= c0 && hi_min >= c1) full |= 1u << bq;
         }
       } else {
         const float own_ki = mq.kinfo[row];
@@ -389,25 +416,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
         if (p.masked && own_ki < 0.f) m2 = -kBig;                     // padding query: any finite result
       }
       const uint64_t a2 = pk2(a_i, a_i), mm2 = pk2(-m2, -m2);
-      if (row == 0) TC_TRACE(wk.k, 6);
-      mbar_wait(&sh.s_full[w], j & 1);
+      if (warp == 0 && lane == 0) TC_TRACE(wk.k, 6);
+      mbar_wait(&sh.s_full[hb], j & 1);
       tc_fence_after();
-      if (row == 0) TC_TRACE(wk.k, 2);
+      if (warp == 0 && lane == 0) TC_TRACE(wk.k, 2);
+      if (warp == 4 && lane == 0) TC_TRACE(wk.k, 13);
+      long long *tr2 = (p.trace && blockIdx.x == 0 && wk.k < 120 && wg == 0) ? p.trace + 120 * 16 + 148 + wk.k * 12 + (warp_hw & 3) * 3 : nullptr;
+      if (tr2 && lane == 0) { tr2[0] = clock64(); tr2[2] = __popc(need) * 16 + __popc(full); }
       float l = 0.f;
       uint64_t l2 = 0ull;
       uint32_t ra[32], rb[32];
-      // Blocks in ascending order (P block b overwrites S columns [16b, 16b+16), already consumed); loads run one needed
-      // block ahead; skipped blocks get zeros, stored only after the loads they could overlap have completed.
+      // Blocks in ascending order (P block b overwrites S columns [16b, 16b+16) of my half, already consumed); loads run
+      // one needed block ahead; skipped blocks get zeros, stored only after the loads they could overlap have completed.
       auto process = [&](const uint32_t (&r)[32], int bq) {
+#if defined(LSH_EXP_NOPROC)
+        if (r[0] != 0x7fc12345u) { uint32_t z[16]; for (int i = 0; i < 16; ++i) z[i] = r[2 * i]; tmem_st16(t_lane + bq * 16, z); return; }
+#endif
         if (sorted) {
-          if ((full >> bq) & 1u) {
-            softmax_block_full(r, a2, mm2, t_lane + bq * 16, l2);
-          } else {
-            const int base = (bq & 3) * 32;
-            softmax_block_interval(r, a2, mm2, (bq < 4 ? lo_lb : lo_own) - base, (bq < 4 ? hi_lb : hi_own) - base, t_lane + bq * 16, l2);
-          }
+          if ((full >> bq) & 1u) softmax_block_full(r, a2, mm2, t_lane + bq * 16, l2);
+          else softmax_block_interval(r, a2, mm2, lo - bq * 32, hi - bq * 32, t_lane + bq * 16, l2);
         } else {
-          softmax_block_generic(r, (bq < 4 ? m0.kinfo : m1.kinfo) + (bq & 3) * 32, qi, a_i, m2, p.causal, p.masked, t_lane + bq * 16, l);
+          softmax_block_generic(r, mk.kinfo + bq * 32, qi, a_i, m2, p.causal, p.masked, t_lane + bq * 16, l);
         }
       };
       auto zero_until = [&](int from, int to) {                       // zero P for the skipped blocks in [from, to)
@@ -418,60 +447,74 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
           tmem_st16(t_lane + bq * 16, z);
         }
       };
-      auto next_needed = [&](int after) -> int {                     // first needed block > after, or 8
+      auto next_needed = [&](int after) -> int {                     // first needed block > after, or 4
         const uint32_t rest = need & ~((2u << after) - 1u);
-        return rest ? __ffs(rest) - 1 : 8;
+        return rest ? __ffs(rest) - 1 : 4;
       };
-      int b0 = need ? __ffs(need) - 1 : 8;
-      if (b0 < 8) tmem_ld32(t_lane + b0 * 32, ra);
+      int b0 = need ? __ffs(need) - 1 : 4;
+      if (b0 < 4) tmem_ld32(t_lane + b0 * 32, ra);
       int done_to = 0;                                                // blocks < done_to are final
-      while (b0 < 8) {
+      long long t_wait = 0;
+      while (b0 < 4) {
         const int b1 = next_needed(b0);
+        long long tw0 = tr2 ? clock64() : 0;
         tmem_ld_wait_dep(ra);
+        if (tr2) t_wait += clock64() - tw0;
         zero_until(done_to, b0);
-        if (b1 < 8) tmem_ld32(t_lane + b1 * 32, rb);
+        if (b1 < 4) tmem_ld32(t_lane + b1 * 32, rb);
         process(ra, b0);
         done_to = b0 + 1;
-        if (b1 >= 8) break;
+        if (b1 >= 4) break;
         const int b2 = next_needed(b1);
+        tw0 = tr2 ? clock64() : 0;
         tmem_ld_wait_dep(rb);
+        if (tr2) t_wait += clock64() - tw0;
         zero_until(done_to, b1);
-        if (b2 < 8) tmem_ld32(t_lane + b2 * 32, ra);
+        if (b2 < 4) tmem_ld32(t_lane + b2 * 32, ra);
         process(rb, b1);
         done_to = b1 + 1;
         b0 = b2;
       }
-      zero_until(done_to, 8);
+      zero_until(done_to, 4);
+      if (tr2 && lane == 0) { tr2[1] = clock64(); tr2[2] += t_wait * 256; }
+      if (warp == 4 && lane == 0) TC_TRACE(wk.k, 14);
       l += lo32(l2) + hi32(l2);
-      // hand the row statistics to the epilogue warpgroup (visible through the p_full -> o_full chain)
-      sh.row_il[w][row] = l > 0.f ? 1.f / l : 0.f;
-      sh.row_lse[w][row] = l > 0.f ? (m2 + log2f(l)) * kLn2 + lse_off : -3e9f;
-      sh.row_tk[w][row] = tk;
+      // hand the row statistics to the epilogue warpgroup (slot ob was read by the epilogue two chunks back)
+      mbar_wait(&sh.o_free[ob], (jo & 1) ^ 1);
+      sh.row_l[ob][wg][row] = l;
+      if (wg == 1) {
+        sh.row_m2[ob][row] = m2; sh.row_off[ob][row] = lse_off;
+        sh.row_tk[ob][row] = mq.tk[row];
+      }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&sh.p_full[w]);
-      if (lane == 0 && p.trace && blockIdx.x == 0 && wk.k < 120) atomicMax(reinterpret_cast<unsigned long long *>(p.trace) + wk.k * 8 + 3, static_cast<unsigned long long>(clock64()));
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&sh.p_full[hb]); mbar_arrive(&sh.l_full[ob]); }
+      if (lane == 0 && p.trace && blockIdx.x == 0 && wk.k < 120) atomicMax(reinterpret_cast<unsigned long long *>(p.trace) + wk.k * 16 + 3, static_cast<unsigned long long>(clock64()));
     }
   } else if (warp >= 8 && warp < 12) {
     // ================================ epilogue warpgroup ==============================================
-    const int row = (warp & 3) * 32 + lane;
-    const uint32_t t_row = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    const int row = (warp_hw & 3) * 32 + lane;
+    const uint32_t t_row = tmem + (static_cast<uint32_t>((warp_hw & 3) * 32) << 16);
     for (Walker wk(g0, g1, p.n_chunks); wk.valid(); wk.next()) {
       const uint32_t w = wk.k & 1, j = wk.k >> 1;
       const int u = wk.u, b = u / p.H, h = u - b * p.H;
-      mbar_wait(&sh.p_full[w], j & 1);                      // acquire the softmax threads' row statistics
+      mbar_wait(&sh.l_full[w], j & 1);                      // acquire the softmax threads' row statistics
       mbar_wait(&sh.o_full[w], j & 1);
       tc_fence_after();
       if (row == 0) TC_TRACE(wk.k, 4);
-      const float il = sh.row_il[w][row], lse = sh.row_lse[w][row];
+      const float l = sh.row_l[w][0][row] + sh.row_l[w][1][row], m2 = sh.row_m2[w][row];
+      const float il = l > 0.f ? 1.f / l : 0.f;
+      const float lse = l > 0.f ? (m2 + log2f(l)) * kLn2 + sh.row_off[w][row] : -3e9f;
       const int tk = sh.row_tk[w][row];
       uint32_t r0[32], r1[32];
-      tmem_ld32(t_row + w * 256 + 128, r0);
-      tmem_ld32(t_row + w * 256 + 160, r1);
+      tmem_ld32(t_row + TC_O_COL + w * 64, r0);
+      tmem_ld32(t_row + TC_O_COL + w * 64 + 32, r1);
       tmem_ld_wait_dep(r0);
       tmem_ld_wait_dep(r1);
       tc_fence_before();
-      mbar_arrive(&sh.s_free[w]);                           // region w may be overwritten by the next S
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh.o_free[w]);            // accumulator and statistics slot w may be reused
       const int round = tk / p.L, pos = tk - round * p.L;
       __nv_bfloat16 *dst = p.o + b * p.o_sb + h * p.o_sh + round * p.o_sr + pos * p.o_sp;
 #pragma unroll
@@ -494,7 +537,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
   }
   tc_fence_before();
   __syncthreads();
-  if (p.trace && tid == 0) p.trace[120 * 8 + blockIdx.x] = clock64() - t_cta_start;   // per-CTA duration (load balance)
+  if (p.trace && tid == 0) p.trace[120 * 16 + blockIdx.x] = clock64() - t_cta_start;   // per-CTA duration (load balance)
   if (warp == 14) tmem_dealloc(tmem, 512);
 }
 

@@ -277,28 +277,49 @@ int sort_run(const LshAttnDims &d, const int32_t *buckets, int64_t bstride, int3
 // position has to be loaded in the softmax loop.  One warp per chunk, rank by counting (128 x 4 compares per lane).
 __global__ void __launch_bounds__(256) chunk_possort_kernel(const int32_t *__restrict__ sticker, int32_t *__restrict__ sticker2,
                                                             int L, int64_t total_chunks) {
-  __shared__ int spos[8][128];
+  __shared__ int stk[8][128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t chunk = static_cast<int64_t>(blockIdx.x) * 8 + warp;
   if (chunk >= total_chunks) return;
   const int32_t *src = sticker + chunk * 128;
-  int tk[4], pos[4], rank[4];
+  // element e = 4 * lane + i; key = (position << 7) | slot: unique, so the bitonic network needs no tie rule
+  const int4 t4 = __ldg(reinterpret_cast<const int4 *>(src) + lane);
+  *reinterpret_cast<int4 *>(&stk[warp][4 * lane]) = t4;
+  uint32_t key[4] = {static_cast<uint32_t>(t4.x % L) << 7 | (4 * lane + 0), static_cast<uint32_t>(t4.y % L) << 7 | (4 * lane + 1),
+                     static_cast<uint32_t>(t4.z % L) << 7 | (4 * lane + 2), static_cast<uint32_t>(t4.w % L) << 7 | (4 * lane + 3)};
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    tk[j] = __ldg(src + lane + 32 * j);
-    pos[j] = tk[j] % L;
-    spos[warp][lane + 32 * j] = pos[j];
-    rank[j] = 0;
+  for (int k = 2; k <= 128; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 4) {                                   // partner element lives in lane ^ (j / 4), same i
+        const bool upper = (lane & (j >> 2)) != 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int e = 4 * lane + i;
+          const bool desc = (e & k) != 0;
+          const uint32_t other = __shfl_xor_sync(0xffffffffu, key[i], j >> 2);
+          const bool take_max = upper != desc;      // ascending block: lower index keeps the min
+          key[i] = take_max ? max(key[i], other) : min(key[i], other);
+        }
+      } else {                                        // both elements in this thread: i and i ^ j
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int i2 = i ^ j;
+          if (i2 > i) {
+            const int e = 4 * lane + i;
+            const bool desc = (e & k) != 0;
+            const uint32_t lo = min(key[i], key[i2]), hi = max(key[i], key[i2]);
+            key[i] = desc ? hi : lo;
+            key[i2] = desc ? lo : hi;
+          }
+        }
+      }
+    }
   }
   __syncwarp();
-#pragma unroll 8
-  for (int i = 0; i < 128; ++i) {
-    const int v = spos[warp][i];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) rank[j] += (v < pos[j] || (v == pos[j] && i < lane + 32 * j)) ? 1 : 0;
-  }
-#pragma unroll
-  for (int j = 0; j < 4; ++j) sticker2[chunk * 128 + rank[j]] = tk[j];
+  int4 o4;
+  o4.x = stk[warp][key[0] & 127]; o4.y = stk[warp][key[1] & 127]; o4.z = stk[warp][key[2] & 127]; o4.w = stk[warp][key[3] & 127];
+  *(reinterpret_cast<int4 *>(sticker2 + chunk * 128) + lane) = o4;
 }
 
 int chunk_possort_run(const LshAttnDims &d, const int32_t *sticker, int32_t *sticker2, cudaStream_t stream) {

@@ -51,6 +51,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   uint32_t spins = 0;
 #endif
   while (!mbar_try_wait(bar, parity)) {
+#if defined(LSH_EXP_SPINSLEEP)
+    __nanosleep(LSH_EXP_SPINSLEEP);
+#endif
     if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
 #ifdef LSH_DEBUG_SPIN
     if (++spins > (1u << 16)) __trap();   // a protocol bug becomes a trap instead of a hung GPU
