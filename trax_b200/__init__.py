@@ -5,6 +5,7 @@ Layout: csrc/ (CUDA kernels + C ABI, built to liblsh_attn_b200.so), _lib.py (cty
 ops.py (stage-level wrappers), lsh_attention.py (the layer with the reference's interface).
 Importing the package does not need a GPU; calling anything does, and raises otherwise.
 """
-from trax_b200.lsh_attention import LSHSelfAttention, ShapeDtype  # noqa: F401
+from trax_b200.lsh_attention import (LSHSelfAttention, ShapeDtype, host_io_bytes,  # noqa: F401
+                                     set_async_host_io, synchronize)
 
-__all__ = ['LSHSelfAttention', 'ShapeDtype']
+__all__ = ['LSHSelfAttention', 'ShapeDtype', 'set_async_host_io', 'synchronize', 'host_io_bytes']

@@ -23,6 +23,8 @@ def allreduce_mean_(grads, group=None):
   (6.3 MB at config 2/3: latency-bound, so a single bucket)."""
   if not dist.is_initialized() or dist.get_world_size(group) == 1:
     return grads
+  if not grads[0].is_cuda and torch.cuda.is_available():
+    torch.cuda.synchronize()        # host-side gradients may still be in flight (asynchronous host I/O)
   flat = torch.cat([g.reshape(-1) for g in grads])
   on_host = not flat.is_cuda and dist.get_backend(group) == 'nccl'
   if on_host:                       # host-buffer (e2e) path: NCCL reduces device memory only

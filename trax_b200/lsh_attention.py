@@ -57,11 +57,114 @@ def _split_host(key, n):
   return gen.integers(0, 2 ** 32, size=(n, 2), dtype=np.uint64).astype(np.uint32)
 
 
-def _to_pinned_host(t):
-  """Async device->host copy into pinned memory (torch's caching host allocator recycles the blocks)."""
-  h = torch.empty(t.shape, dtype=t.dtype, device='cpu', pin_memory=True)
-  h.copy_(t, non_blocking=True)
-  return h
+class _HostIO:
+  """Host <-> device plumbing of the layer's host-tensor path (what bench.py's `e2e` leg times).
+
+  Two side streams per device keep both PCIe directions busy: uploads of the NEXT call's inputs and downloads of the
+  PREVIOUS call's results run beside the kernels on the caller's stream.  An upload of the same host tensor object at
+  the same version (forward(x) followed by backward(x, ...), the reversible-layer pattern) is served from the device
+  copy made by the first call.  With `set_async_host_io(True)` a call returns as soon as its work is enqueued: results
+  are pinned host tensors that become valid after `trax_b200.synchronize()` (JAX-style asynchronous dispatch);
+  the default is to wait before returning.
+  """
+  _per_device = {}
+  async_mode = False
+
+  def __init__(self, dev):
+    self.dev = dev
+    self.h2d = torch.cuda.Stream(device=dev)
+    self.d2h = torch.cuda.Stream(device=dev)
+    self.cache_key, self.cache_val = None, None
+    self.rings = {}
+    self.h2d_bytes = 0
+    self.d2h_bytes = 0
+
+  @classmethod
+  def get(cls, dev):
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    io = cls._per_device.get(key)
+    if io is None:
+      io = cls._per_device[key] = cls(dev)
+    return io
+
+  def upload(self, t, cache=False):
+    """Host tensor -> device copy usable on the current stream (stream-ordered, no host wait).
+
+    cache=True: the copy is remembered for ONE more upload of the same host tensor (same storage, shape and version):
+    forward(x) followed by backward(x, ...) moves x across PCIe once.
+    """
+    if t is None or t.is_cuda:
+      return t
+    key = (t.data_ptr(), tuple(t.shape), t.dtype, t._version) if cache else None
+    if key is not None and key == self.cache_key:
+      d = self.cache_val
+      self.cache_key, self.cache_val = None, None
+      return d
+    main = torch.cuda.current_stream(self.dev)
+    with torch.cuda.stream(self.h2d):
+      d = t.to(self.dev, non_blocking=True)
+      ev = self.h2d.record_event()
+    main.wait_event(ev)
+    d.record_stream(main)
+    self.h2d_bytes += t.numel() * t.element_size()
+    if cache:
+      self.cache_key, self.cache_val = key, d
+    return d
+
+  def _staging(self, d, role):
+    """Pinned destination of a download.  Synchronous mode: a fresh tensor per call.  Asynchronous mode: a ring of
+    three staging buffers per (role, shape, dtype) — re-acquiring a slot waits for its previous copy (back-pressure,
+    bounded pinned memory); a returned tensor is overwritten by the third-next call of the same kind."""
+    if not _HostIO.async_mode:
+      return torch.empty(d.shape, dtype=d.dtype, device='cpu', pin_memory=True), None
+    key = (role, tuple(d.shape), d.dtype)
+    ring = self.rings.setdefault(key, {'bufs': [], 'events': [], 'next': 0})
+    i = ring['next']
+    ring['next'] = (i + 1) % 3
+    if len(ring['bufs']) <= i:
+      ring['bufs'].append(torch.empty(d.shape, dtype=d.dtype, device='cpu', pin_memory=True))
+      ring['events'].append(None)
+    elif ring['events'][i] is not None:
+      ring['events'][i].synchronize()
+    return ring['bufs'][i], (ring, i)
+
+  def download(self, d, role='out'):
+    """Device tensor -> pinned host tensor, copied on the download stream after the current stream's work so far."""
+    main = torch.cuda.current_stream(self.dev)
+    ev = main.record_event()
+    h, slot = self._staging(d, role)
+    with torch.cuda.stream(self.d2h):
+      self.d2h.wait_event(ev)
+      h.copy_(d, non_blocking=True)
+      if slot is not None:
+        slot[0]['events'][slot[1]] = self.d2h.record_event()
+    d.record_stream(self.d2h)
+    self.d2h_bytes += d.numel() * d.element_size()
+    return h
+
+  def finish(self):
+    if not _HostIO.async_mode:
+      self.d2h.synchronize()
+
+
+def set_async_host_io(flag):
+  """Host-tensor calls return without waiting for their device->host copies (see _HostIO)."""
+  _HostIO.async_mode = bool(flag)
+
+
+def synchronize():
+  """Waits for every enqueued layer call, including the host copies of results (pairs with set_async_host_io)."""
+  torch.cuda.synchronize()
+
+
+def host_io_bytes(reset=False):
+  """(h2d, d2h) bytes actually copied by host-tensor calls since the last reset."""
+  h = sum(io.h2d_bytes for io in _HostIO._per_device.values())
+  d = sum(io.d2h_bytes for io in _HostIO._per_device.values())
+  if reset:
+    for io in _HostIO._per_device.values():
+      io.h2d_bytes = io.d2h_bytes = 0
+  return h, d
 
 
 class LSHSelfAttention:
@@ -306,11 +409,13 @@ class LSHSelfAttention:
     host_io = not x.is_cuda
     dev = torch.device('cuda', torch.cuda.current_device()) if host_io else x.device
 
-    def to_dev(t):
+    io = _HostIO.get(dev) if host_io else None
+
+    def to_dev(t, cache=False):
       if t is None or t.is_cuda:
         return t
-      return t.to(dev, non_blocking=True)
-    x_d = to_dev(x).contiguous()
+      return _HostIO.get(dev).upload(t, cache)
+    x_d = to_dev(x, cache=True).contiguous()
     mask_d = None
     if self._masked:
       mask_d = to_dev(inputs[1]).to(torch.uint8).contiguous()
@@ -376,13 +481,13 @@ class LSHSelfAttention:
           ops._ptr(buckets_d), buckets_d.stride(0), ops._ptr(g_d), ops._ptr(out_d), ops._ptr(dx), ops._ptr(dw_q),
           ops._ptr(dw_v), ops._ptr(dw_o), ops._ptr(ws), ws.numel(), stream), 'lsh_layer_bwd')
       if host_io:
-        dx, dw_q, dw_v, dw_o = (_to_pinned_host(t) for t in (dx, dw_q, dw_v, dw_o))
+        dx, dw_q, dw_v, dw_o = (io.download(t, r) for t, r in ((dx, 'dx'), (dw_q, 'dw_q'), (dw_v, 'dw_v'), (dw_o, 'dw_o')))
       inputs_grad = dx if have_single_input else (dx,) + (None,) * (len(inputs) - 1)
       weights_grad = (dw_q, dw_v, dw_o)
     if update_state:
       new_state = (buckets_d, new_rng)    # state stays on the device, like a jitted Trax layer's
     if compute_output and host_io:
-      out_d = _to_pinned_host(out_d)
+      out_d = io.download(out_d)
     if host_io:
-      torch.cuda.current_stream().synchronize()      # results are in pinned host memory when the call returns
+      io.finish()      # default: results are in pinned host memory when the call returns (see set_async_host_io)
     return out_d, new_state, inputs_grad, weights_grad
