@@ -43,17 +43,19 @@ struct __align__(16) TcTileMeta {
 struct __align__(16) TcShared {
   TcTileMeta meta[TC_NST];
   uint64_t full[TC_NST], empty[TC_NST];
-  uint64_t s_full[3], p_full[3], hb_free[3];     // per half-chunk score buffer (128 TMEM columns each)
-  uint64_t o_full[2], o_free[2], l_full[2];      // per output accumulator (64 TMEM columns each) / row statistics
+  uint64_t s_full[2], s_free[2], p_full[2], p_free[2];   // per window part: score buffer / probability buffer hand-offs
+  uint64_t o_full[2], o_free[2], l_full[2];              // per output accumulator (64 TMEM columns each) / row statistics
   float row_l[2][2][TC_C], row_m2[2][TC_C], row_off[2][TC_C];   // softmax -> epilogue hand-off per output buffer
   int row_tk[2][TC_C];
   uint32_t tmem_base;
 };
 
-// TMEM map (512 columns): three half-chunk score buffers S/P at 0, 128, 256 (a chunk's 256 keys are scored as two
-// independent halves: half h = 2 * chunk + part lives in buffer h % 3), two output accumulators O at 384 and 448.
-// Nothing but the PV MMA of the same half stands between a buffer's softmax pass and its next score MMA, and the
-// epilogue (O -> HBM) is off that path entirely.
+// TMEM map (512 columns).  A chunk's 256 keys are scored as two independent halves (part 0: first window tile, part 1:
+// second), each owned by one softmax warpgroup with its own buffers: scores S[part] at 128 * part (fp32, 128 columns),
+// probabilities P[part] at 256 + 64 * part (bf16 pairs, 64 columns), two output accumulators O at 384 and 448.
+// P is NOT written over S: a score buffer is free for the next chunk's score MMA the moment its softmax pass has read
+// it — neither the PV MMA nor the epilogue sits between two passes of a warpgroup.
+constexpr uint32_t TC_P_COL = 256;
 constexpr uint32_t TC_O_COL = 384;
 
 // Enumerates the work items of one CTA and the tile sequence numbers they use.
@@ -112,15 +114,17 @@ __device__ __forceinline__ void softmax_block_full(const uint32_t (&r)[32], uint
   }
   tmem_st16(t_dst, pk);
 }
-// Boundary block of the position-sorted scheme: column c of the block is visible iff lo <= c < hi (per row).
-__device__ __forceinline__ void softmax_block_interval(const uint32_t (&r)[32], uint64_t a2, uint64_t mm2, int lo, int hi, uint32_t t_dst,
-                                                       uint64_t &l2) {
+// Boundary block of the position-sorted scheme: column c of the block is visible iff c < bound (PREFIX, ascending key
+// tile) or c >= bound (suffix, descending key tile) — one compare and one select per element.
+template <bool PREFIX>
+__device__ __forceinline__ void softmax_block_bound(const uint32_t (&r)[32], uint64_t a2, uint64_t mm2, int bound, uint32_t t_dst,
+                                                    uint64_t &l2) {
   uint32_t pk[16];
 #pragma unroll
   for (int c2 = 0; c2 < 32; c2 += 2) {
     const uint64_t t = ffma2(pk2u(r[c2], r[c2 + 1]), a2, mm2);
-    const float p0 = fast_exp2((c2 >= lo && c2 < hi) ? lo32(t) : -INFINITY);
-    const float p1 = fast_exp2((c2 + 1 >= lo && c2 + 1 < hi) ? hi32(t) : -INFINITY);
+    const bool v0 = PREFIX ? (c2 < bound) : (c2 >= bound), v1 = PREFIX ? (c2 + 1 < bound) : (c2 + 1 >= bound);
+    const float p0 = fast_exp2(v0 ? lo32(t) : -INFINITY), p1 = fast_exp2(v1 ? hi32(t) : -INFINITY);
     l2 = fadd2(l2, pk2(p0, p1));
     pk[c2 >> 1] = pack_bf16(p0, p1);
   }
@@ -171,11 +175,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
   if (warp == 14) tmem_alloc(&sh.tmem_base, 512);
   if (tid == 0) {
     for (int i = 0; i < TC_NST; ++i) { mbar_init(&sh.full[i], 64); mbar_init(&sh.empty[i], 1); }
-    for (int i = 0; i < 3; ++i) {
-      mbar_init(&sh.s_full[i], 1); mbar_init(&sh.p_full[i], 4);     // one arrival per softmax warp of the half's warpgroup
-      mbar_init(&sh.hb_free[i], 1);
-    }
     for (int i = 0; i < 2; ++i) {
+      mbar_init(&sh.s_full[i], 1); mbar_init(&sh.p_free[i], 1);     // tcgen05.commit arrivals
+      mbar_init(&sh.s_free[i], 4); mbar_init(&sh.p_full[i], 4);     // one arrival per softmax warp of the part's warpgroup
       mbar_init(&sh.o_full[i], 1); mbar_init(&sh.o_free[i], 4);     // one arrival per epilogue warp
       mbar_init(&sh.l_full[i], 8);                                   // one arrival per softmax warp (both warpgroups)
     }
@@ -281,8 +283,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
     }
   } else if (warp == 14) {
     // ================================ S issuer ========================================================
-    // Half h of chunk k (part 0: the first window tile's keys, part 1: the second's) goes out as soon as its tiles have
-    // landed and its score buffer has been consumed by the PV MMA three halves earlier.  The warp runs converged
+    // Part p of chunk k (part 0: the first window tile's keys, part 1: the second's) goes out as soon as its tiles have
+    // landed and warpgroup p has read the previous chunk's scores out of the buffer.  The warp runs converged
     // (warp-uniform values); one elected lane issues.  Descriptors: constant hi, lo = base + (offset >> 4).
     constexpr uint32_t HI = desc_hi(1024);
     for (Walker ws(g0, g1, p.n_chunks); ws.valid(); ws.next()) {
@@ -293,17 +295,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
       const uint32_t qa = desc_lo(p.nb ? k1 : k0, 16);
 #pragma unroll
       for (int part = 0; part < 2; ++part) {
-        const uint32_t h = 2u * k + part, hb = h % 3u, j = h / 3u;
-        mbar_wait(&sh.hb_free[hb], (j & 1) ^ 1);
+        mbar_wait(&sh.s_free[part], (k & 1) ^ 1);
         if (lane == 0) TC_TRACE(k, part == 0 ? 7 : 12);
         // no proxy fence: the tile's mbarrier phase completes when its cp.async copies have landed, which is what the UMMA
         // operand reads are ordered after (same protocol as CUTLASS's sm100 cp.async mainloop)
         tc_fence_after();
-        const uint32_t kb = desc_lo(part ? k1 : k0, 16), s_t = tmem + hb * 128;
+        const uint32_t kb = desc_lo(part ? k1 : k0, 16), s_t = tmem + part * 128;
         if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) umma_ss2(s_t, qa + ks * 2, HI, kb + ks * 2, HI, TC_IDESC_S, ks > 0);
-          umma_commit(&sh.s_full[hb]);
+          umma_commit(&sh.s_full[part]);
         }
         __syncwarp();
       }
@@ -320,17 +321,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
       const bool rel_own = !wo.next_reuses();
 #pragma unroll
       for (int part = 0; part < 2; ++part) {
-        const uint32_t h = 2u * k + part, hb = h % 3u, j = h / 3u;
         const uint32_t vt = desc_lo(tiles_u32 + slot_of(part ? n : n - 1) * TC_TILE_BYTES + TC_C * 128, 1024);
-        const uint32_t p_t = tmem + hb * 128;
-        mbar_wait(&sh.p_full[hb], j & 1);
+        const uint32_t p_t = tmem + TC_P_COL + part * 64;
+        mbar_wait(&sh.p_full[part], k & 1);
         if (lane == 0) TC_TRACE(k, 8 + 2 * part);
         if (part == 0) mbar_wait(&sh.o_free[ob], (jo & 1) ^ 1);     // the epilogue two chunks back has drained this O
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) umma_ts2(o_t, p_t + i * 8, vt + i * 128, HI, TC_IDESC_O, (part > 0 || i > 0) ? 1u : 0u);
-          umma_commit(&sh.hb_free[hb]);
+          umma_commit(&sh.p_free[part]);
           if (part == 0) {
             // the score MMAs that read this tile (other issuer) finished before their P existed: every reader is covered
             umma_commit(&sh.empty[slot_of(n - 1)]);
@@ -355,9 +355,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
     const bool sorted = p.causal && !p.masked && p.nb == 1;       // warp-uniform fast path
     for (Walker wk(g0, g1, p.n_chunks); wk.valid(); wk.next()) {
       const int n = wk.n;
-      const uint32_t h = 2u * wk.k + wg, hb = h % 3u, j = h / 3u;   // my half of this chunk and its score buffer
       const uint32_t ob = wk.k & 1, jo = wk.k >> 1;
-      const uint32_t t_lane = t_wg + hb * 128;
+      const uint32_t t_lane = t_wg + wg * 128;                       // my part's scores
+      const uint32_t t_p = t_wg + TC_P_COL + wg * 64;                // my part's probabilities
       const uint32_t sl0 = slot_of(n - 1), sl1 = slot_of(n);
       mbar_wait(&sh.full[sl0], phase_of(n - 1));
       mbar_wait(&sh.full[sl1], phase_of(n));
@@ -371,6 +371,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
       float m2 = am.y, lse_off = 0.f;
       uint32_t need = 0xfu, full = 0u;                               // per 32-column block of my tile (warp-uniform)
       int lo = 0, hi = 128;                                          // visible column interval in my tile
+      bool prefix = true;                                            // interval is [0, hi) (ascending key tile) or [lo, 128)
       if (sorted) {
         // Both tiles are ordered by position (rank r at row r ^ flip), so "key position < query position" (EA:150-152 and the
         // self mask EA:153-155, whose -1e5 entries underflow to exactly 0 next to any visible key) is an interval of columns.
@@ -393,9 +394,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
             else if (go) bhi = mid;
           }
           const int bound = lonely ? (lb_min == mypos ? 1 : 0) : blo;
+          prefix = flip_lb == 0;
           if (flip_lb) { lo = 128 - bound; hi = 128; } else { lo = 0; hi = bound; }
         } else {
           const int self_incl = lonely ? 1 : 0;
+          prefix = flip_own == 0;
           if (flip_own) { lo = row + 1 - self_incl; hi = 128; } else { lo = 0; hi = row + self_incl; }
         }
         const int lo_min = __reduce_min_sync(0xffffffffu, lo), lo_max = __reduce_max_sync(0xffffffffu, lo);
@@ -417,7 +420,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
       }
       const uint64_t a2 = pk2(a_i, a_i), mm2 = pk2(-m2, -m2);
       if (warp == 0 && lane == 0) TC_TRACE(wk.k, 6);
-      mbar_wait(&sh.s_full[hb], j & 1);
+      mbar_wait(&sh.s_full[wg], wk.k & 1);
+      mbar_wait(&sh.p_free[wg], (wk.k & 1) ^ 1);                     // the previous chunk's PV has read my P buffer
       tc_fence_after();
       if (warp == 0 && lane == 0) TC_TRACE(wk.k, 2);
       if (warp == 4 && lane == 0) TC_TRACE(wk.k, 13);
@@ -426,17 +430,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
       float l = 0.f;
       uint64_t l2 = 0ull;
       uint32_t ra[32], rb[32];
-      // Blocks in ascending order (P block b overwrites S columns [16b, 16b+16) of my half, already consumed); loads run
-      // one needed block ahead; skipped blocks get zeros, stored only after the loads they could overlap have completed.
+      // Loads run one needed block ahead; skipped blocks get zeros.
       auto process = [&](const uint32_t (&r)[32], int bq) {
 #if defined(LSH_EXP_NOPROC)
         if (r[0] != 0x7fc12345u) { uint32_t z[16]; for (int i = 0; i < 16; ++i) z[i] = r[2 * i]; tmem_st16(t_lane + bq * 16, z); return; }
 #endif
         if (sorted) {
-          if ((full >> bq) & 1u) softmax_block_full(r, a2, mm2, t_lane + bq * 16, l2);
-          else softmax_block_interval(r, a2, mm2, lo - bq * 32, hi - bq * 32, t_lane + bq * 16, l2);
+          if ((full >> bq) & 1u) softmax_block_full(r, a2, mm2, t_p + bq * 16, l2);
+          else if (prefix) softmax_block_bound<true>(r, a2, mm2, hi - bq * 32, t_p + bq * 16, l2);
+          else softmax_block_bound<false>(r, a2, mm2, lo - bq * 32, t_p + bq * 16, l2);
         } else {
-          softmax_block_generic(r, mk.kinfo + bq * 32, qi, a_i, m2, p.causal, p.masked, t_lane + bq * 16, l);
+          softmax_block_generic(r, mk.kinfo + bq * 32, qi, a_i, m2, p.causal, p.masked, t_p + bq * 16, l);
         }
       };
       auto zero_until = [&](int from, int to) {                       // zero P for the skipped blocks in [from, to)
@@ -444,7 +448,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
           uint32_t z[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) z[i] = 0u;
-          tmem_st16(t_lane + bq * 16, z);
+          tmem_st16(t_p + bq * 16, z);
         }
       };
       auto next_needed = [&](int after) -> int {                     // first needed block > after, or 4
@@ -454,29 +458,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
       int b0 = need ? __ffs(need) - 1 : 4;
       if (b0 < 4) tmem_ld32(t_lane + b0 * 32, ra);
       int done_to = 0;                                                // blocks < done_to are final
-      long long t_wait = 0;
       while (b0 < 4) {
         const int b1 = next_needed(b0);
-        long long tw0 = tr2 ? clock64() : 0;
         tmem_ld_wait_dep(ra);
-        if (tr2) t_wait += clock64() - tw0;
         zero_until(done_to, b0);
+#if !defined(LSH_EXP_NOLD)
         if (b1 < 4) tmem_ld32(t_lane + b1 * 32, rb);
+#endif
         process(ra, b0);
         done_to = b0 + 1;
         if (b1 >= 4) break;
         const int b2 = next_needed(b1);
-        tw0 = tr2 ? clock64() : 0;
         tmem_ld_wait_dep(rb);
-        if (tr2) t_wait += clock64() - tw0;
         zero_until(done_to, b1);
+#if !defined(LSH_EXP_NOLD)
         if (b2 < 4) tmem_ld32(t_lane + b2 * 32, ra);
+#endif
         process(rb, b1);
         done_to = b1 + 1;
         b0 = b2;
       }
       zero_until(done_to, 4);
-      if (tr2 && lane == 0) { tr2[1] = clock64(); tr2[2] += t_wait * 256; }
+      if (tr2 && lane == 0) tr2[1] = clock64();
       if (warp == 4 && lane == 0) TC_TRACE(wk.k, 14);
       l += lo32(l2) + hi32(l2);
       // hand the row statistics to the epilogue warpgroup (slot ob was read by the epilogue two chunks back)
@@ -489,7 +492,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) { mbar_arrive(&sh.p_full[hb]); mbar_arrive(&sh.l_full[ob]); }
+      if (lane == 0) { mbar_arrive(&sh.s_free[wg]); mbar_arrive(&sh.p_full[wg]); mbar_arrive(&sh.l_full[ob]); }
       if (lane == 0 && p.trace && blockIdx.x == 0 && wk.k < 120) atomicMax(reinterpret_cast<unsigned long long *>(p.trace) + wk.k * 16 + 3, static_cast<unsigned long long>(clock64()));
     }
   } else if (warp >= 8 && warp < 12) {
