@@ -79,7 +79,14 @@ __device__ __forceinline__ uint32_t slot_of(int n) { return static_cast<uint32_t
 __device__ __forceinline__ uint32_t phase_of(int n) { return static_cast<uint32_t>((n / TC_NST) & 1); }
 
 // trace slots per chunk: 0 S issued, 1 PV issued, 2 s_full seen, 3 pass done, 4 o_full seen, 5 epilogue done, 6 tile issued, 7 tile landed
+// (compiled in only with -DLSH_TRACE: the stamps cost instruction-cache space in every role)
+#ifdef LSH_TRACE
 #define TC_TRACE(k, slot) do { if (p.trace && blockIdx.x == 0 && (k) < 120) p.trace[(k) * 16 + (slot)] = clock64(); } while (0)
+#define TC_TRACE_ON 1
+#else
+#define TC_TRACE(k, slot) do { } while (0)
+#define TC_TRACE_ON 0
+#endif
 
 constexpr float kBig = 1e9f * kLog2e, kSelf = 1e5f * kLog2e;   // EA:152-159 masks, log2 domain
 
@@ -134,6 +141,9 @@ __device__ __forceinline__ void softmax_block_bound(const uint32_t (&r)[32], uin
 // key kv_info read from shared memory.
 __device__ __forceinline__ void softmax_block_generic(const uint32_t (&r)[32], const float *kin, float qi, float a, float m2, int causal,
                                                       int masked, uint32_t t_dst, float &l) {
+#if defined(LSH_EXP_NOGENERIC)
+  return;
+#endif
   uint32_t pk[16];
 #pragma unroll
   for (int c4 = 0; c4 < 32; c4 += 4) {
@@ -155,6 +165,10 @@ __device__ __forceinline__ void softmax_block_generic(const uint32_t (&r)[32], c
   tmem_st16(t_dst, pk);
 }
 
+// SORTED: causal, no padding mask, look-back window (every long-sequence config) — interval masks on position-sorted tiles.
+// !SORTED: the reference's masks evaluated per element from the keys' kv_info.  Two instantiations keep each one's code
+// (instruction-cache footprint) small.
+template <bool SORTED>
 __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const AttendFwdParams p, int total_chunks) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -220,7 +234,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
       r.have = next_tile(r.n, r.u, r.cc);
       if (r.have) fetch_sticker(r.u, r.cc, r.tka, r.tkb);
     };
-    const bool sorted_path = p.causal && !p.masked && p.nb == 1;
+    constexpr bool sorted_path = SORTED;
     const int ch = lane & 15, hi = lane >> 4;              // 16-byte piece of the 256-byte row pair; row parity
     auto issue = [&](const TileReq &r) {
       const int n = r.n, u = r.u, tka = r.tka, tkb = r.tkb;
@@ -236,7 +250,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
       const float2 *rm = p.rowmeta + static_cast<int64_t>(u) * p.L;
       cp_async8(smem_u32(&mt.am[rowa]), rm + pa);
       cp_async8(smem_u32(&mt.am[rowb]), rm + pb);
-      if (!sorted_path) {                                   // generic path: kv_info and the window visibility range
+      if constexpr (!sorted_path) {                         // generic path: kv_info and the window visibility range
         bool va = true, vb = true;
         if (p.masked) {
           va = p.mask[static_cast<int64_t>(b) * p.L + pa] != 0;
@@ -261,11 +275,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
       const uint32_t rbytes = ch < 8 ? 128u : static_cast<uint32_t>(p.H) * 256u;
       const uint32_t tile = tiles_u32 + slot * TC_TILE_BYTES + (ch < 8 ? 0 : TC_C * 128);
       const uint32_t lane_const = (static_cast<uint32_t>((64 * pw + hi) ^ flip) << 7) | (static_cast<uint32_t>((ch ^ flip ^ hi) & 7) << 4);
+#pragma unroll 1
+      for (int io = 0; io < 8; ++io) {                     // 4 copies per trip: compact code, constants stay immediates
+        const int psel = io < 4 ? pa : pb;
+        const uint32_t dst = tile + (lane_const ^ (static_cast<uint32_t>(io) << 10));
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int pr = __shfl_sync(0xffffffffu, (i < 16) ? pa : pb, (2 * i + hi) & 31);
-        const uint32_t imm = (static_cast<uint32_t>(i) << 8) ^ (static_cast<uint32_t>(i & 3) << 5);
-        cp_async16(tile + (lane_const ^ imm), base + static_cast<uint64_t>(static_cast<uint32_t>(pr)) * rbytes);
+        for (int ii = 0; ii < 4; ++ii) {
+          const int pr = __shfl_sync(0xffffffffu, psel, (8 * io + 2 * ii + hi) & 31);
+          cp_async16(dst ^ ((static_cast<uint32_t>(ii) << 8) ^ (static_cast<uint32_t>(ii) << 5)), base + static_cast<uint64_t>(static_cast<uint32_t>(pr)) * rbytes);
+        }
       }
       // Completion is signalled by the copies themselves (no wait here): every free ring slot is a tile in flight.
       // The metadata stores above precede the copies in program order and are long done when the last copy lands.
@@ -286,63 +304,82 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
     // Part p of chunk k (part 0: the first window tile's keys, part 1: the second's) goes out as soon as its tiles have
     // landed and warpgroup p has read the previous chunk's scores out of the buffer.  The warp runs converged
     // (warp-uniform values); one elected lane issues.  Descriptors: constant hi, lo = base + (offset >> 4).
+    // Issue order is skewed by one chunk between the parts — step i: (chunk i, part 0), then (chunk i-1, part 1) — so the
+    // two warpgroups work on different chunks at any time: consecutive chunks have opposite row orders, hence their heavy
+    // warps (the rows that see the most keys) sit on different SM sub-partitions.
     constexpr uint32_t HI = desc_hi(1024);
-    for (Walker ws(g0, g1, p.n_chunks); ws.valid(); ws.next()) {
-      const int k = ws.k, n = ws.n;
-      mbar_wait(&sh.full[slot_of(n - 1)], phase_of(n - 1));
-      mbar_wait(&sh.full[slot_of(n)], phase_of(n));
+    auto issue_s = [&](int k, int n, int part) {
       const uint32_t k0 = tiles_u32 + slot_of(n - 1) * TC_TILE_BYTES, k1 = tiles_u32 + slot_of(n) * TC_TILE_BYTES;
       const uint32_t qa = desc_lo(p.nb ? k1 : k0, 16);
+      mbar_wait(&sh.s_free[part], (k & 1) ^ 1);
+      if (lane == 0) TC_TRACE(k, part == 0 ? 7 : 12);
+      // no proxy fence: the tile's mbarrier phase completes when its cp.async copies have landed, which is what the UMMA
+      // operand reads are ordered after (same protocol as CUTLASS's sm100 cp.async mainloop)
+      tc_fence_after();
+      const uint32_t kb = desc_lo(part ? k1 : k0, 16), s_t = tmem + part * 128;
+      if (elect_one()) {
 #pragma unroll
-      for (int part = 0; part < 2; ++part) {
-        mbar_wait(&sh.s_free[part], (k & 1) ^ 1);
-        if (lane == 0) TC_TRACE(k, part == 0 ? 7 : 12);
-        // no proxy fence: the tile's mbarrier phase completes when its cp.async copies have landed, which is what the UMMA
-        // operand reads are ordered after (same protocol as CUTLASS's sm100 cp.async mainloop)
-        tc_fence_after();
-        const uint32_t kb = desc_lo(part ? k1 : k0, 16), s_t = tmem + part * 128;
-        if (elect_one()) {
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) umma_ss2(s_t, qa + ks * 2, HI, kb + ks * 2, HI, TC_IDESC_S, ks > 0);
-          umma_commit(&sh.s_full[part]);
-        }
-        __syncwarp();
+        for (int ks = 0; ks < 4; ++ks) umma_ss2(s_t, qa + ks * 2, HI, kb + ks * 2, HI, TC_IDESC_S, ks > 0);
+        umma_commit(&sh.s_full[part]);
       }
-      if (lane == 0) TC_TRACE(k, 0);
+      __syncwarp();
+      if (lane == 0 && part == 1) TC_TRACE(k, 0);
+    };
+    Walker ws(g0, g1, p.n_chunks);
+    bool have_prev = false;
+    int pk = 0, pn = 0;
+    while (ws.valid() || have_prev) {
+      const bool cur = ws.valid();
+      if (cur) {
+        mbar_wait(&sh.full[slot_of(ws.n - 1)], phase_of(ws.n - 1));
+        mbar_wait(&sh.full[slot_of(ws.n)], phase_of(ws.n));
+        issue_s(ws.k, ws.n, 0);
+      }
+      if (have_prev) issue_s(pk, pn, 1);
+      have_prev = cur;
+      if (cur) { pk = ws.k; pn = ws.n; ws.next(); }
     }
   } else if (warp == 15) {
     // ================================ PV issuer =======================================================
-    // A second issuing warp so that a PV never queues behind a score MMA that is still waiting for tiles.
+    // A second issuing warp so that a PV never queues behind a score MMA that is still waiting for tiles.  Same skewed
+    // order as the score issuer.
     constexpr uint32_t HI = desc_hi(1024);
-    for (Walker wo(g0, g1, p.n_chunks); wo.valid(); wo.next()) {
-      const int k = wo.k, n = wo.n;
+    auto issue_pv = [&](int k, int n, int part, bool release_first) {
       const uint32_t ob = k & 1, jo = k >> 1;
       const uint32_t o_t = tmem + TC_O_COL + ob * 64;
-      const bool rel_own = !wo.next_reuses();
+      const uint32_t vt = desc_lo(tiles_u32 + slot_of(part ? n : n - 1) * TC_TILE_BYTES + TC_C * 128, 1024);
+      const uint32_t p_t = tmem + TC_P_COL + part * 64;
+      mbar_wait(&sh.p_full[part], k & 1);
+      if (lane == 0) TC_TRACE(k, 8 + 2 * part);
+      if (part == 0) mbar_wait(&sh.o_free[ob], (jo & 1) ^ 1);       // the epilogue two chunks back has drained this O
+      tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
-      for (int part = 0; part < 2; ++part) {
-        const uint32_t vt = desc_lo(tiles_u32 + slot_of(part ? n : n - 1) * TC_TILE_BYTES + TC_C * 128, 1024);
-        const uint32_t p_t = tmem + TC_P_COL + part * 64;
-        mbar_wait(&sh.p_full[part], k & 1);
-        if (lane == 0) TC_TRACE(k, 8 + 2 * part);
-        if (part == 0) mbar_wait(&sh.o_free[ob], (jo & 1) ^ 1);     // the epilogue two chunks back has drained this O
-        tc_fence_after();
-        if (elect_one()) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) umma_ts2(o_t, p_t + i * 8, vt + i * 128, HI, TC_IDESC_O, (part > 0 || i > 0) ? 1u : 0u);
-          umma_commit(&sh.p_free[part]);
-          if (part == 0) {
-            // the score MMAs that read this tile (other issuer) finished before their P existed: every reader is covered
-            umma_commit(&sh.empty[slot_of(n - 1)]);
-          } else {
-            umma_commit(&sh.o_full[ob]);
-            if (rel_own) umma_commit(&sh.empty[slot_of(n)]);   // nobody will reuse the second tile
-          }
+        for (int i = 0; i < 8; ++i) umma_ts2(o_t, p_t + i * 8, vt + i * 128, HI, TC_IDESC_O, (part > 0 || i > 0) ? 1u : 0u);
+        umma_commit(&sh.p_free[part]);
+        // Tile release.  The score MMAs that read a tile (other issuer) finished before the P of their part existed.
+        // Part 1 of chunk k is the last reader of tile n: part 0 of chunk k+1 (its look-back use) was issued just before.
+        // A first window tile that is not shared with the previous chunk (range / unit start) has part 0 as only reader.
+        if (part == 0) {
+          if (release_first) umma_commit(&sh.empty[slot_of(n - 1)]);
+        } else {
+          umma_commit(&sh.o_full[ob]);
+          umma_commit(&sh.empty[slot_of(n)]);
         }
-        __syncwarp();
-        if (lane == 0) TC_TRACE(k, 9 + 2 * part);
       }
-      if (lane == 0) TC_TRACE(k, 1);
+      __syncwarp();
+      if (lane == 0) TC_TRACE(k, 9 + 2 * part);
+      if (lane == 0 && part == 1) TC_TRACE(k, 1);
+    };
+    Walker wo(g0, g1, p.n_chunks);
+    bool have_prev = false;
+    int pk = 0, pn = 0;
+    while (wo.valid() || have_prev) {
+      const bool cur = wo.valid();
+      if (cur) issue_pv(wo.k, wo.n, 0, !wo.reuse);
+      if (have_prev) issue_pv(pk, pn, 1, false);
+      have_prev = cur;
+      if (cur) { pk = wo.k; pn = wo.n; wo.next(); }
     }
   } else if (warp < 8) {
     // ================================ softmax warpgroups ==============================================
@@ -352,7 +389,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
     const uint32_t wg = warp >> 2;
     const int row = (warp_hw & 3) * 32 + lane;                // query row == TMEM lane (lane quarter = warp id % 4)
     const uint32_t t_wg = tmem + (static_cast<uint32_t>((warp_hw & 3) * 32) << 16);
-    const bool sorted = p.causal && !p.masked && p.nb == 1;       // warp-uniform fast path
+    constexpr bool sorted = SORTED;
     for (Walker wk(g0, g1, p.n_chunks); wk.valid(); wk.next()) {
       const int n = wk.n;
       const uint32_t ob = wk.k & 1, jo = wk.k >> 1;
@@ -372,7 +409,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
       uint32_t need = 0xfu, full = 0u;                               // per 32-column block of my tile (warp-uniform)
       int lo = 0, hi = 128;                                          // visible column interval in my tile
       bool prefix = true;                                            // interval is [0, hi) (ascending key tile) or [lo, 128)
-      if (sorted) {
+      if constexpr (sorted) {
         // Both tiles are ordered by position (rank r at row r ^ flip), so "key position < query position" (EA:150-152 and the
         // self mask EA:153-155, whose -1e5 entries underflow to exactly 0 next to any visible key) is an interval of columns.
         const int c_lb = wk.c > 0 ? wk.c - 1 : p.n_chunks - 1;      // cyclic look-back (EA:137-141)
@@ -425,7 +462,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
       tc_fence_after();
       if (warp == 0 && lane == 0) TC_TRACE(wk.k, 2);
       if (warp == 4 && lane == 0) TC_TRACE(wk.k, 13);
-      long long *tr2 = (p.trace && blockIdx.x == 0 && wk.k < 120 && wg == 0) ? p.trace + 120 * 16 + 148 + wk.k * 12 + (warp_hw & 3) * 3 : nullptr;
+      long long *tr2 = (TC_TRACE_ON && p.trace && blockIdx.x == 0 && wk.k < 120 && wg == 0) ? p.trace + 120 * 16 + 148 + wk.k * 12 + (warp_hw & 3) * 3 : nullptr;
       if (tr2 && lane == 0) { tr2[0] = clock64(); tr2[2] = __popc(need) * 16 + __popc(full); }
       float l = 0.f;
       uint64_t l2 = 0ull;
@@ -435,7 +472,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
 #if defined(LSH_EXP_NOPROC)
         if (r[0] != 0x7fc12345u) { uint32_t z[16]; for (int i = 0; i < 16; ++i) z[i] = r[2 * i]; tmem_st16(t_lane + bq * 16, z); return; }
 #endif
-        if (sorted) {
+        if constexpr (sorted) {
           if ((full >> bq) & 1u) softmax_block_full(r, a2, mm2, t_p + bq * 16, l2);
           else if (prefix) softmax_block_bound<true>(r, a2, mm2, hi - bq * 32, t_p + bq * 16, l2);
           else softmax_block_bound<false>(r, a2, mm2, lo - bq * 32, t_p + bq * 16, l2);
@@ -493,7 +530,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
       tc_fence_before();
       __syncwarp();
       if (lane == 0) { mbar_arrive(&sh.s_free[wg]); mbar_arrive(&sh.p_full[wg]); mbar_arrive(&sh.l_full[ob]); }
-      if (lane == 0 && p.trace && blockIdx.x == 0 && wk.k < 120) atomicMax(reinterpret_cast<unsigned long long *>(p.trace) + wk.k * 16 + 3, static_cast<unsigned long long>(clock64()));
+      if (TC_TRACE_ON && lane == 0 && p.trace && blockIdx.x == 0 && wk.k < 120) atomicMax(reinterpret_cast<unsigned long long *>(p.trace) + wk.k * 16 + 3, static_cast<unsigned long long>(clock64()));
     }
   } else if (warp >= 8 && warp < 12) {
     // ================================ epilogue warpgroup ==============================================
@@ -540,13 +577,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
   }
   tc_fence_before();
   __syncthreads();
-  if (p.trace && tid == 0) p.trace[120 * 16 + blockIdx.x] = clock64() - t_cta_start;   // per-CTA duration (load balance)
+  if (TC_TRACE_ON && p.trace && tid == 0) p.trace[120 * 16 + blockIdx.x] = clock64() - t_cta_start;   // per-CTA duration (load balance)
   if (warp == 14) tmem_dealloc(tmem, 512);
 }
 
 int attend_fwd_tc_run(const AttendFwdParams &p, int BH, cudaStream_t stream) {
   const size_t smem = static_cast<size_t>(TC_NST) * TC_TILE_BYTES + 1024;   // + static TcShared
-  LSH_OPT_IN_SMEM(attend_fwd_tc_kernel);
+  const bool sorted = p.causal && !p.masked && p.nb == 1;
+  LSH_OPT_IN_SMEM(attend_fwd_tc_kernel<true>);
+  LSH_OPT_IN_SMEM(attend_fwd_tc_kernel<false>);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -556,7 +595,8 @@ int attend_fwd_tc_run(const AttendFwdParams &p, int BH, cudaStream_t stream) {
     const int m = atoi(e);
     if (m > 0 && m < grid) grid = m;
   }
-  attend_fwd_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(p, total);
+  if (sorted) attend_fwd_tc_kernel<true><<<grid, TC_THREADS, smem, stream>>>(p, total);
+  else attend_fwd_tc_kernel<false><<<grid, TC_THREADS, smem, stream>>>(p, total);
   LSH_CHECK_LAUNCH("attend_fwd_tc_kernel");
   return 0;
 }

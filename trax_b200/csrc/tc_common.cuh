@@ -126,6 +126,9 @@ __device__ __forceinline__ bool elect_one() {
 }
 __device__ __forceinline__ void umma_ss2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
                                          uint32_t idesc, uint32_t accum) {
+#if defined(LSH_EXP_NOMMA)
+  return;
+#endif
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
@@ -139,6 +142,9 @@ __device__ __forceinline__ void umma_ss2(uint32_t d_tmem, uint32_t a_lo, uint32_
 }
 __device__ __forceinline__ void umma_ts2(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
                                          uint32_t accum) {
+#if defined(LSH_EXP_NOMMA)
+  return;
+#endif
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
