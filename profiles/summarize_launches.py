@@ -13,7 +13,7 @@ ci = {h: i for i, h in enumerate(hdr)}
 data = [r for r in rows if r is not hdr and r[ci['Metric Name']] == 'gpu__time_duration.sum']
 names = [re.sub(r'\(.*', '', r[ci['Kernel Name']])[:64] for r in data]
 vals = [float(r[ci['Metric Value']].replace(',', '')) / 1e3 for r in data]   # ns -> us
-h = [i for i, n in enumerate(names) if 'hash_kernel' in n]
+h = [i for i, n in enumerate(names) if 'hash_' in n and 'kernel' in n]
 a, b = h[3] - 5, h[4] - 5            # one full step (forward call starts 5 launches before its hash kernel)
 agg, cnt = collections.OrderedDict(), collections.Counter()
 for n, v in zip(names[a:b], vals[a:b]):

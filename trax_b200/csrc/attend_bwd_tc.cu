@@ -37,7 +37,12 @@ constexpr uint32_t BT_IDESC_DQ = make_idesc_bf16(128, 64, 1, 1);   // dQ (A and 
 
 // trace slots per item: 0 MMA: pds_full[0] seen, 1 MMA: pds_full[1] seen, 2 MMA: item done (commits issued),
 // 3 WG0: st_full seen, 4 WG0: pass done, 5 WG1: st_full seen, 6 WG1: pass done, 7 WG0: epilogue done
+// (compiled in only with -DLSH_TRACE: the stamps cost instruction-cache space in every role)
+#ifdef LSH_TRACE
 #define BT_TRACE(n, slot) do { if (p.trace && blockIdx.x == 0 && (n) < 120) p.trace[(n) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define BT_TRACE(n, slot) do { } while (0)
+#endif
 
 struct __align__(16) BtTileMeta {
   float kinfo[BT_C];    // pos + 1 as fp32 (key side of the causal compare)
@@ -159,33 +164,43 @@ __global__ void __launch_bounds__(BT_THREADS, 1) attend_bwd_tc_kernel(const Atte
       cp_async4(smem_u32(&mt.dvec[ra]), p.dvec + oa);   cp_async4(smem_u32(&mt.dvec[rb]), p.dvec + ob);
       cp_async4(smem_u32(&mt.qcmp[ra]), p.qcmp + oa);   cp_async4(smem_u32(&mt.qcmp[rb]), p.qcmp + ob);
       const uint32_t kt = tiles_u32 + slot * BT_TILE_BYTES, vt = kt + BT_C * 128, dt = vt + BT_C * 128;
-      {   // q|v rows: 16 lanes per 256-byte row, 2 rows per instruction
+      {   // q|v rows: 16 lanes per 256-byte row, 2 rows per instruction.  Destination of row R = 64 pw + 2 i + hi, piece c:
+          // tile + (R << 7) + (((c ^ R) & 7) << 4) = tile + (lane_const ^ imm(i)) — all bit fields are disjoint.
         const int ch = lane & 15, hi = lane >> 4;
-        const __nv_bfloat16 *base = p.qv + (static_cast<int64_t>(b) * p.L * p.H + h) * 128 + ch * 8;
-#pragma unroll 8
-        for (int i = 0; i < 32; ++i) {
-          const int rel = 2 * i + hi;
-          const int pr = __shfl_sync(0xffffffffu, (i < 16) ? pa : pb, rel & 31);
-          cp_async16((ch < 8 ? kt : vt) + swz(64 * pw + rel, ch & 7), base + static_cast<int64_t>(pr) * p.H * 128);
+        const char *base = reinterpret_cast<const char *>(p.qv + (static_cast<int64_t>(b) * p.L * p.H + h) * 128 + ch * 8);
+        const uint32_t rbytes = static_cast<uint32_t>(p.H) * 256u;
+        const uint32_t tile = ch < 8 ? kt : vt;
+        const uint32_t lane_const = (static_cast<uint32_t>(64 * pw + hi) << 7) | (static_cast<uint32_t>((ch ^ hi) & 7) << 4);
+#pragma unroll 1
+        for (int io = 0; io < 8; ++io) {
+          const int psel = io < 4 ? pa : pb;
+          const uint32_t dst = tile + (lane_const ^ (static_cast<uint32_t>(io) << 10));
+#pragma unroll
+          for (int ii = 0; ii < 4; ++ii) {
+            const int pr = __shfl_sync(0xffffffffu, psel, (8 * io + 2 * ii + hi) & 31);
+            cp_async16(dst ^ ((static_cast<uint32_t>(ii) << 8) ^ (static_cast<uint32_t>(ii) << 5)), base + static_cast<uint64_t>(static_cast<uint32_t>(pr)) * rbytes);
+          }
         }
       }
-      {   // do rows: 8 lanes per 128-byte row, 4 rows per instruction
+      {   // do rows: 8 lanes per 128-byte row, 4 rows per instruction: R = 64 pw + 4 i + hi (hi = 0..3)
         const int ch = lane & 7, hi = lane >> 3;
-        const __nv_bfloat16 *base = p.do_comb + (static_cast<int64_t>(b) * p.L * p.H + h) * 64 + ch * 8;
-#pragma unroll 8
-        for (int i = 0; i < 16; ++i) {
-          const int rel = 4 * i + hi;
-          const int pr = __shfl_sync(0xffffffffu, (i < 8) ? pa : pb, rel & 31);
-          cp_async16(dt + swz(64 * pw + rel, ch), base + static_cast<int64_t>(pr) * p.H * 64);
+        const char *base = reinterpret_cast<const char *>(p.do_comb + (static_cast<int64_t>(b) * p.L * p.H + h) * 64 + ch * 8);
+        const uint32_t rbytes = static_cast<uint32_t>(p.H) * 128u;
+        const uint32_t lane_const = (static_cast<uint32_t>(64 * pw + hi) << 7) | (static_cast<uint32_t>((ch ^ hi) & 7) << 4);
+#pragma unroll 1
+        for (int io = 0; io < 8; ++io) {                  // i = 2 io + ii: rows 8 io + 4 ii + hi
+          const int psel = io < 4 ? pa : pb;
+          const uint32_t dst = dt + (lane_const ^ (static_cast<uint32_t>(io) << 10));
+#pragma unroll
+          for (int ii = 0; ii < 2; ++ii) {
+            const int pr = __shfl_sync(0xffffffffu, psel, (8 * io + 4 * ii + hi) & 31);
+            cp_async16(dst ^ ((static_cast<uint32_t>(ii) << 9) ^ (static_cast<uint32_t>(ii) << 6)), base + static_cast<uint64_t>(static_cast<uint32_t>(pr)) * rbytes);
+          }
         }
       }
-      cp_async_commit();
-      // Signal the tile as soon as it has landed.  (Deferring the arrival to the next tile's issue couples tile t+1's
-      // visibility to the release of tile t-1's ring slot, i.e. to the epilogue warpgroup — measured as a ~6K-cycle
-      // stall per iteration.)
-      cp_async_wait<0>();
-      fence_proxy_async();
-      mbar_arrive(&sh.full[slot]);
+      // Completion is signalled by the copies themselves (cp.async.mbarrier.arrive.noinc): the producer never waits for
+      // its own loads, and the tile becomes visible the moment it has landed.
+      cp_async_mbar_arrive_noinc(&sh.full[slot]);
     };
     for (BtWalk w(g0, g1, p.n_chunks); w.valid();) {
       const BtItem it = w.item();
@@ -221,7 +236,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) attend_bwd_tc_kernel(const Atte
     auto wait_tiles = [&](const BtItem &it) {
       mbar_wait(&sh.full[bt_slot(it.seq_k)], bt_phase(it.seq_k));
       mbar_wait(&sh.full[bt_slot(it.seq_q)], bt_phase(it.seq_q));
-      tc_fence_after();   // (writers fence generic->async proxy before arriving; no consumer-side proxy fence)
+      tc_fence_after();   // (tiles are signalled by their cp.async copies; same protocol as CUTLASS's sm100 cp.async mainloop)
     };
     BtWalk w(g0, g1, p.n_chunks);
     BtItem cur = w.item();
