@@ -38,7 +38,7 @@ int attend_fwd_run(const LshAttnDims &, const void *, const int32_t *, const uin
 int combine_fwd_run(const LshAttnDims &, const void *, const float *, void *, float *, cudaStream_t);
 size_t attend_bwd_workspace_bytes(const LshAttnDims &);
 int attend_bwd_run(const LshAttnDims &, const void *, const int32_t *, const uint8_t *, const void *, const float *,
-                   const void *, const float *, void *, void *, size_t, cudaStream_t);
+                   const void *, const float *, const int32_t *, void *, void *, size_t, cudaStream_t);
 int pack_weights_run(const LshAttnDims &, const float *, const float *, const float *, void *, void *, cudaStream_t);
 int f32_to_bf16_run(const float *, void *, int64_t, cudaStream_t);
 int unpack_dwqv_run(const LshAttnDims &, const float *, float *, float *, cudaStream_t);
@@ -276,7 +276,7 @@ int lsh_attend_bwd(const LshAttnDims *dims, const void *qv, const int32_t *stick
                    const void *o_comb, const float *lse_tot, const void *do_comb, void *dqv, void *ws, size_t ws_bytes,
                    void *stream) {
   if (int rc = check_dims(dims, true)) return rc;
-  return attend_bwd_run(*dims, qv, sticker, mask, o_comb, lse_tot, do_comb, nullptr, dqv, ws, ws_bytes,
+  return attend_bwd_run(*dims, qv, sticker, mask, o_comb, lse_tot, do_comb, nullptr, nullptr, dqv, ws, ws_bytes,
                         static_cast<cudaStream_t>(stream));
 }
 
@@ -331,7 +331,7 @@ int lsh_layer_bwd(const LshAttnDims *dims, const void *x, const float *w_q, cons
   if ((rc = gemm_rm(false, true, BL, KO, d.D, doutb, d.D, w.wo, d.D, w.do_comb, KO, false, w.cublas, s))) return rc;
   if ((rc = gemm_rm(true, false, KO, d.D, BL, w.o_comb, KO, doutb, d.D, dw_o, d.D, true, w.cublas, s))) return rc;
   // B2-B6
-  if ((rc = attend_bwd_run(d, w.qv, w.sticker, mask, w.o_comb, w.lse_tot, w.do_comb, w.aux.qscale, w.dqv, w.bwd_ws, w.bwd_bytes, s)))
+  if ((rc = attend_bwd_run(d, w.qv, w.sticker, mask, w.o_comb, w.lse_tot, w.do_comb, w.aux.qscale, attend_fwd_uses_tc(d) ? w.aux.sticker2 : nullptr, w.dqv, w.bwd_ws, w.bwd_bytes, s)))
     return rc;
   // B7: dW_q|dW_v = x^T·dqv ; dx = dqv·wqv^T
   if ((rc = gemm_rm(true, false, d.D, NQV, BL, xb, d.D, w.dqv, NQV, w.dwqv, NQV, true, w.cublas, s))) return rc;

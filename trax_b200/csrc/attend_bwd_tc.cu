@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) attend_bwd_tc_kernel(const Atte
     auto load_tile = [&](int seq, int u, int cc) {
       const uint32_t slot = bt_slot(seq);
       const int b = u / p.H, h = u - b * p.H;
-      const int32_t *stk = p.sticker + static_cast<int64_t>(u) * p.N + cc * BT_C + 64 * pw;
+      const int32_t *stk = p.sticker2 + static_cast<int64_t>(u) * p.N + cc * BT_C + 64 * pw;   // chunk rows ascending in position
       const int tka = __ldg(stk + lane), tkb = __ldg(stk + 32 + lane);
       const int pa = tka % p.L, pb = tkb % p.L;
       mbar_wait<128>(&sh.empty[slot], bt_phase(seq) ^ 1);
@@ -324,38 +324,87 @@ __global__ void __launch_bounds__(BT_THREADS, 1) attend_bwd_tc_kernel(const Atte
       const BtTileMeta &mq = sh.meta[slq];
       const float kst_j = ksc_j * kLn2;                    // true key scale 1/(r*sqrt(dq)) for the dQ operand
       uint8_t *dsrow = dsbuf + (it.n & 1) * BT_DS_BYTES + h * (BT_C * 128);
+      // Tiles are ordered by position (chunk_possort_kernel), so for key j the queries of the tile split into three index
+      // ranges: [0, lo) position below the key's — never visible (EA:150-152); [lo, hi) the same position — the key's own
+      // token or its copy from the neighbouring hash round, visible only to self-only rows (qcmp rule); [hi, 128) visible.
+      // Per warp, a 32-query block is skipped (zeros), evaluated without any mask (no per-query position loads), or
+      // — only around the boundary — evaluated with the per-element compare.
+      int lo_j, hi_j;
+      if (it.seq_q == it.seq_k) {
+        lo_j = row; hi_j = row + 1;
+      } else {
+        int blo = 0, bhi = 128;
+#pragma unroll
+        for (int sidx = 0; sidx < 8; ++sidx) {
+          const int mid = (blo + bhi) >> 1;
+          const float v = mq.kinfo[mid & 127];
+          const bool go = blo < bhi;
+          if (go && v < ki_j) blo = mid + 1;
+          else if (go) bhi = mid;
+        }
+        lo_j = blo;
+        hi_j = blo + ((blo < 128 && mq.kinfo[blo & 127] == ki_j) ? 1 : 0);
+      }
+      const int min_lo = __reduce_min_sync(0xffffffffu, lo_j), max_hi = __reduce_max_sync(0xffffffffu, hi_j);
       mbar_wait(&sh.st_full[h], it.n & 1);
       mbar_wait(&sh.dsm_free[it.n & 1], ((it.n >> 1) & 1) ^ 1);
       tc_fence_after();
       if (row == 0) BT_TRACE(it.n, 3 + 2 * h);
 #pragma unroll 1
       for (int cc = 0; cc < 64; cc += 32) {
-        uint32_t s[32], dp[32];
-        tmem_ld32(r_st + cc, s);
-        tmem_ld32(r_st + 64 + cc, dp);
-        tmem_ld_wait_dep(s);
-        tmem_ld_wait_dep(dp);
-        uint32_t pk_p[16], pk_ds[16];
+        const int c0 = 64 * h + cc;
+        uint32_t s[32], pk_p[16], pk_ds[16];
+        if (c0 + 32 <= min_lo) {
+          // no key of this warp sees any query of the block
 #pragma unroll
-        for (int c4 = 0; c4 < 32; c4 += 4) {
-          const int i0 = 64 * h + cc + c4;
-          const float4 qc = *reinterpret_cast<const float4 *>(&mq.qcmp[i0]);
-          const float4 ls = *reinterpret_cast<const float4 *>(&mq.lse2[i0]);
-          const float4 dv = *reinterpret_cast<const float4 *>(&mq.dvec[i0]);
-          const float p0 = ki_j < qc.x ? fast_exp2(fmaf(__uint_as_float(s[c4 + 0]), ksc_j, -ls.x)) : 0.f;
-          const float p1 = ki_j < qc.y ? fast_exp2(fmaf(__uint_as_float(s[c4 + 1]), ksc_j, -ls.y)) : 0.f;
-          const float p2 = ki_j < qc.z ? fast_exp2(fmaf(__uint_as_float(s[c4 + 2]), ksc_j, -ls.z)) : 0.f;
-          const float p3 = ki_j < qc.w ? fast_exp2(fmaf(__uint_as_float(s[c4 + 3]), ksc_j, -ls.w)) : 0.f;
-          const float d0 = p0 * (__uint_as_float(dp[c4 + 0]) - dv.x), d1 = p1 * (__uint_as_float(dp[c4 + 1]) - dv.y);
-          const float d2 = p2 * (__uint_as_float(dp[c4 + 2]) - dv.z), d3 = p3 * (__uint_as_float(dp[c4 + 3]) - dv.w);
-          pk_p[c4 >> 1] = pack_bf16(p0, p1);  pk_p[(c4 >> 1) + 1] = pack_bf16(p2, p3);
-          pk_ds[c4 >> 1] = pack_bf16(d0, d1); pk_ds[(c4 >> 1) + 1] = pack_bf16(d2, d3);
-          // reuse s[] as the staging copy (dS * key scale) for dQ
-          s[c4 >> 1] = pack_bf16(d0 * kst_j, d1 * kst_j);
-          s[(c4 >> 1) + 1] = pack_bf16(d2 * kst_j, d3 * kst_j);
+          for (int i = 0; i < 16; ++i) { pk_p[i] = 0u; s[i] = 0u; }
+          tmem_st16(r_st + (cc >> 1), pk_p);
+          tmem_st16(r_st + 64 + (cc >> 1), pk_p);
+        } else {
+          uint32_t dp[32];
+          tmem_ld32(r_st + cc, s);
+          tmem_ld32(r_st + 64 + cc, dp);
+          tmem_ld_wait_dep(s);
+          tmem_ld_wait_dep(dp);
+          if (c0 >= max_hi) {
+            // every key of this warp sees every query of the block
+#pragma unroll
+            for (int c4 = 0; c4 < 32; c4 += 4) {
+              const float4 ls = *reinterpret_cast<const float4 *>(&mq.lse2[c0 + c4]);
+              const float4 dv = *reinterpret_cast<const float4 *>(&mq.dvec[c0 + c4]);
+              const float p0 = fast_exp2(fmaf(__uint_as_float(s[c4 + 0]), ksc_j, -ls.x));
+              const float p1 = fast_exp2(fmaf(__uint_as_float(s[c4 + 1]), ksc_j, -ls.y));
+              const float p2 = fast_exp2(fmaf(__uint_as_float(s[c4 + 2]), ksc_j, -ls.z));
+              const float p3 = fast_exp2(fmaf(__uint_as_float(s[c4 + 3]), ksc_j, -ls.w));
+              const float d0 = p0 * (__uint_as_float(dp[c4 + 0]) - dv.x), d1 = p1 * (__uint_as_float(dp[c4 + 1]) - dv.y);
+              const float d2 = p2 * (__uint_as_float(dp[c4 + 2]) - dv.z), d3 = p3 * (__uint_as_float(dp[c4 + 3]) - dv.w);
+              pk_p[c4 >> 1] = pack_bf16(p0, p1);  pk_p[(c4 >> 1) + 1] = pack_bf16(p2, p3);
+              pk_ds[c4 >> 1] = pack_bf16(d0, d1); pk_ds[(c4 >> 1) + 1] = pack_bf16(d2, d3);
+              s[c4 >> 1] = pack_bf16(d0 * kst_j, d1 * kst_j);
+              s[(c4 >> 1) + 1] = pack_bf16(d2 * kst_j, d3 * kst_j);
+            }
+          } else {
+#pragma unroll
+            for (int c4 = 0; c4 < 32; c4 += 4) {
+              const float4 qc = *reinterpret_cast<const float4 *>(&mq.qcmp[c0 + c4]);
+              const float4 ls = *reinterpret_cast<const float4 *>(&mq.lse2[c0 + c4]);
+              const float4 dv = *reinterpret_cast<const float4 *>(&mq.dvec[c0 + c4]);
+              const float p0 = ki_j < qc.x ? fast_exp2(fmaf(__uint_as_float(s[c4 + 0]), ksc_j, -ls.x)) : 0.f;
+              const float p1 = ki_j < qc.y ? fast_exp2(fmaf(__uint_as_float(s[c4 + 1]), ksc_j, -ls.y)) : 0.f;
+              const float p2 = ki_j < qc.z ? fast_exp2(fmaf(__uint_as_float(s[c4 + 2]), ksc_j, -ls.z)) : 0.f;
+              const float p3 = ki_j < qc.w ? fast_exp2(fmaf(__uint_as_float(s[c4 + 3]), ksc_j, -ls.w)) : 0.f;
+              const float d0 = p0 * (__uint_as_float(dp[c4 + 0]) - dv.x), d1 = p1 * (__uint_as_float(dp[c4 + 1]) - dv.y);
+              const float d2 = p2 * (__uint_as_float(dp[c4 + 2]) - dv.z), d3 = p3 * (__uint_as_float(dp[c4 + 3]) - dv.w);
+              pk_p[c4 >> 1] = pack_bf16(p0, p1);  pk_p[(c4 >> 1) + 1] = pack_bf16(p2, p3);
+              pk_ds[c4 >> 1] = pack_bf16(d0, d1); pk_ds[(c4 >> 1) + 1] = pack_bf16(d2, d3);
+              // reuse s[] as the staging copy (dS * key scale) for dQ
+              s[c4 >> 1] = pack_bf16(d0 * kst_j, d1 * kst_j);
+              s[(c4 >> 1) + 1] = pack_bf16(d2 * kst_j, d3 * kst_j);
+            }
+          }
+          tmem_st16(r_st + (cc >> 1), pk_p);
+          tmem_st16(r_st + 64 + (cc >> 1), pk_ds);
         }
-        tmem_st16(r_st + (cc >> 1), pk_p);
-        tmem_st16(r_st + 64 + (cc >> 1), pk_ds);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint4 v;
