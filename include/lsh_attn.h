@@ -93,10 +93,18 @@ int lsh_sort(const LshAttnDims *dims, const int32_t *buckets, int64_t buckets_st
 /* EA:1958-1986: gather by sticker, `attend` (EA:163-268) with look-back window, masks
  * (EA:145-160), per-row log-sum-exp, and the un-sort of EA:1985-1986 (rows are written straight to
  * their ticker slot).  o_rounds may alias o_comb's layout when nh==1 via lsh_attend_fwd_strided. */
+/* The workspace holds the per-call auxiliaries of the tcgen05 path: per-token key scale, normalised keys
+ * q / (8 r) (EA:229-231), {query scale, softmax shift} pairs and the position-sorted chunks (see lsh_chunk_possort). */
 size_t lsh_attend_fwd_workspace_bytes(const LshAttnDims *dims);
 int lsh_attend_fwd(const LshAttnDims *dims, const void *qv_bf16, const int32_t *sticker,
                    const uint8_t *mask, void *o_rounds_bf16, float *logits, void *ws, size_t ws_bytes,
                    void *stream);
+
+/* Internal order used by the tcgen05 attention kernels (chunk_len 128): sticker2 = sticker with every 128-slot
+ * chunk re-ordered by token position (ticker % L, ascending; ties keep slot order).  Attention inside a chunk
+ * window (EA:209-268) is a sum over keys and its rows are un-sorted by ticker (EA:1985-1986), so results do not
+ * depend on the order inside a chunk; the reference's sticker / undo_sort (EA:1951-1956) are untouched. */
+int lsh_chunk_possort(const LshAttnDims *dims, const int32_t *sticker, int32_t *sticker2, void *stream);
 
 /* EA:1988-1992 multi-round combine; also emits lse_tot = logsumexp_h(logits) (BH, L) when non-null. */
 int lsh_combine_fwd(const LshAttnDims *dims, const void *o_rounds_bf16, const float *logits,

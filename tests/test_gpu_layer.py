@@ -237,3 +237,42 @@ def test_host_buffers_roundtrip():
   assert not out.is_cuda and out.shape == x.shape
   out_d = layer.forward_and_or_backward(x.cuda(), layer.weights, layer.state, None, update_state=False)[0]
   torch.testing.assert_close(out, out_d.cpu(), rtol=0, atol=0)
+
+
+def test_async_host_io_matches_sync():
+  """Asynchronous dispatch (side-stream copies, staging rings, one-shot reuse of forward's upload in backward)
+  returns the same bits as the default synchronous host path and as device-resident inputs."""
+  import trax_b200
+  cfg = util.make_cfg(H=2, C=128, nh=2, n_buckets=8)
+  layer = _layer(cfg)
+  layer.init(trax_b200.ShapeDtype((1, 512, 64)))
+  g = torch.Generator().manual_seed(3)
+  xs = [torch.randn(1, 512, 64, generator=g).pin_memory() for _ in range(4)]
+  gs = [torch.randn(1, 512, 64, generator=g).pin_memory() for _ in range(4)]
+  layer.forward(xs[0])                               # fixes the buckets in the state; every call below re-uses them
+  state = layer.state
+
+  def run(x, gr):
+    # forward call then backward call on the same host tensor (the second upload of x is served from the first)
+    out = layer.forward_and_or_backward(x, layer.weights, state, None, update_state=False)[0]
+    _, _, dx, dw = layer.forward_and_or_backward(x, layer.weights, state, None, output_grad=gr, compute_output=False,
+                                                 update_state=False)
+    return out, dx, dw
+  ref = []
+  for x, gr in zip(xs, gs):
+    out, dx, dw = run(x, gr)
+    ref.append([t.clone() for t in (out, dx) + tuple(dw)])
+  trax_b200.set_async_host_io(True)
+  try:
+    got = []
+    for x, gr in zip(xs, gs):
+      out, dx, dw = run(x, gr)
+      trax_b200.synchronize()                      # staging buffers are recycled after three calls: copy out now
+      got.append([t.clone() for t in (out, dx) + tuple(dw)])
+  finally:
+    trax_b200.set_async_host_io(False)
+  for r, o in zip(ref, got):
+    for a, b in zip(r, o):
+      torch.testing.assert_close(a, b, rtol=0, atol=0)
+  h2d, d2h = trax_b200.host_io_bytes(reset=True)
+  assert h2d > 0 and d2h > 0

@@ -109,6 +109,24 @@ def test_sort_bit_exact(L, nh, nbk):
     np.testing.assert_array_equal(undo[u][sticker[u]], np.arange(nh * L))
 
 
+@pytest.mark.parametrize('L,nh,nbk', [(1024, 3, 8), (192, 2, 4), (65536, 1, 1024)])
+def test_chunk_possort_bit_exact(L, nh, nbk):
+  """Internal order of the tcgen05 kernels: every 128-slot chunk of sticker re-ordered by position, ties (a chunk that
+  straddles two hash rounds, L % 128 != 0) keeping slot order — against a stable NumPy argsort."""
+  from trax_b200 import ops
+  rng = np.random.default_rng(L + nh)
+  BH = 2
+  buckets = util.random_valid_buckets(rng, BH, nh, L, nbk)
+  dims = _dims(1, BH, L, 64, 128, 1, 0, nh, [nbk])
+  sticker, _ = ops.sort(dims, _cuda(buckets))
+  s2 = ops.chunk_possort(dims, sticker).cpu().numpy()
+  st = sticker.cpu().numpy()
+  for u in range(BH):
+    ch = st[u].reshape(-1, 128)
+    order = np.argsort(ch % L, axis=1, kind='stable')
+    np.testing.assert_array_equal(s2[u].reshape(-1, 128), np.take_along_axis(ch, order, axis=1))
+
+
 def test_sort_rejects_int32_key_overflow():
   from trax_b200 import _lib
   lib = _lib.load()

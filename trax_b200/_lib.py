@@ -39,6 +39,7 @@ SIGNATURES = {
     'lsh_sort': (_I, [_D, _P, _I64, _P, _P, _P, _SZ, _P]),
     'lsh_attend_fwd_workspace_bytes': (_SZ, [_D]),
     'lsh_attend_fwd': (_I, [_D, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    'lsh_chunk_possort': (_I, [_D, _P, _P, _P]),
     'lsh_combine_fwd': (_I, [_D, _P, _P, _P, _P, _P]),
     'lsh_project_out': (_I, [_D, _P, _P, _P, _P, _SZ, _P]),
     'lsh_attend_bwd_workspace_bytes': (_SZ, [_D]),

@@ -36,6 +36,7 @@ int sort_run(const LshAttnDims &, const int32_t *, int64_t, int32_t *, int32_t *
 int attend_fwd_run(const LshAttnDims &, const void *, const int32_t *, const uint8_t *, void *, int64_t, int64_t,
                    int64_t, int64_t, float *, const FwdAux *, cudaStream_t);
 int combine_fwd_run(const LshAttnDims &, const void *, const float *, void *, float *, cudaStream_t);
+int chunk_possort_run(const LshAttnDims &, const int32_t *, int32_t *, cudaStream_t);
 size_t attend_bwd_workspace_bytes(const LshAttnDims &);
 int attend_bwd_run(const LshAttnDims &, const void *, const int32_t *, const uint8_t *, const void *, const float *,
                    const void *, const float *, const int32_t *, void *, void *, size_t, cudaStream_t);
@@ -253,6 +254,12 @@ int lsh_attend_fwd(const LshAttnDims *dims, const void *qv, const int32_t *stick
   return attend_fwd_run(d, qv, sticker, mask, o_rounds, static_cast<int64_t>(d.H) * dr.N * 64,
                         static_cast<int64_t>(dr.N) * 64, static_cast<int64_t>(d.L) * 64, 64, logits, &aux,
                         static_cast<cudaStream_t>(stream));
+}
+
+int lsh_chunk_possort(const LshAttnDims *dims, const int32_t *sticker, int32_t *sticker2, void *stream) {
+  if (int rc = check_dims(dims, false)) return rc;
+  if (!sticker || !sticker2 || sticker == sticker2) return set_error("lsh_chunk_possort: sticker / sticker2 must be distinct non-NULL buffers");
+  return chunk_possort_run(*dims, sticker, sticker2, static_cast<cudaStream_t>(stream));
 }
 
 int lsh_combine_fwd(const LshAttnDims *dims, const void *o_rounds, const float *logits, void *o_comb, float *lse_tot,

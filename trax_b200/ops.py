@@ -107,6 +107,14 @@ def sort(dims, buckets, want_undo=True):
   return sticker, undo
 
 
+def chunk_possort(dims, sticker):
+  """sticker with every 128-slot chunk re-ordered by position (internal order of the tcgen05 kernels)."""
+  lib = _lib.load()
+  out = torch.empty_like(sticker)
+  _lib.check(lib.lsh_chunk_possort(ctypes.byref(dims), _ptr(sticker), _ptr(out), _stream()), 'lsh_chunk_possort')
+  return out
+
+
 def attend_fwd(dims, qv, sticker, mask=None):
   lib = _lib.load()
   bh, n = dims.B * dims.H, dims.nh * dims.L
