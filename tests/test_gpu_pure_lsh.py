@@ -1,0 +1,95 @@
+"""GPU parity tests of `trax_b200.PureLSHSelfAttention` (EA:2564-3265) against the CPU oracle and
+against the full layer, modelled on `efficient_attention_test.py:376-440` (LSH == projections + weight-less core + w_o).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import lsh_oracle as O
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _pure(cfg, **kw):
+  import trax_b200
+  return trax_b200.PureLSHSelfAttention(
+      n_heads=cfg.n_heads, d_qk=64, d_v=64, causal=cfg.causal, masked=cfg.masked, chunk_len=cfg.chunk_len,
+      n_chunks_before=cfg.n_chunks_before, n_chunks_after=cfg.n_chunks_after, n_hashes=cfg.n_hashes,
+      n_buckets=cfg.n_buckets, **kw)
+
+
+PURE_CASES = [
+    # (B, L, cfg)
+    (2, 512, util.make_cfg(H=2, C=128, nh=4, n_buckets=8)),                                     # tcgen05 path
+    (1, 1024, util.make_cfg(H=2, C=64, nh=1, n_buckets=32)),                                    # BASELINE config 1 core
+    (1, 512, util.make_cfg(H=2, C=64, nb=1, na=1, nh=2, n_buckets=16, causal=False, masked=True)),
+]
+
+
+@pytest.mark.parametrize('B,L,cfg', PURE_CASES)
+def test_pure_lsh_matches_oracle(B, L, cfg):
+  """Output and (dqk, dv) vs the oracle's unit with identity projections; buckets bit-exact with the oracle's hash."""
+  H = cfg.n_heads
+  rng = np.random.default_rng(5)
+  qk = util.bf16_round(rng.standard_normal((B * H, L, 64)))
+  v = util.bf16_round(rng.standard_normal((B * H, L, 64)))
+  dout = util.bf16_round(rng.standard_normal((B * H, L, 64)))
+  mask = (rng.random((B, L)) > 0.2) if cfg.masked else None
+  if mask is not None:
+    dout = dout * np.repeat(mask, H, axis=0)[:, :, None]
+  factors = O.bucket_factors(cfg.n_buckets, L, cfg.chunk_len)
+  rot = rng.standard_normal((B * H, 64, cfg.n_hashes, sum(factors) // 2)).astype(np.float32)
+  layer = _pure(cfg)
+  sig = [trax_sig((B * H, L, 64)), trax_sig((B * H, L, 64))] + ([trax_sig((B, L))] if cfg.masked else [])
+  weights, state = layer.init(tuple(sig))
+  assert weights == () and state[0].shape == (B * H, cfg.n_hashes * L) and state[1].shape == (B * H, 2)
+  layer._rotations_override = torch.from_numpy(rot)
+  inputs = (torch.from_numpy(qk).cuda(), torch.from_numpy(v).cuda())
+  if cfg.masked:
+    inputs = inputs + (torch.from_numpy(mask).cuda(),)
+  out = layer.forward(inputs)
+  dq_dv, dw = layer.backward(inputs, out, torch.from_numpy(dout).cuda(), (), None, layer.state, None)
+  assert dw == () and out.shape == (B * H, L, 64)
+  got_buckets = layer.state[0].cpu().numpy()
+  w_q, w_v, w_o = util.core_identity_weights()
+  for u in range(B * H):
+    b = u // H
+    x = np.concatenate([qk[u], v[u]], axis=1).astype(np.float64)
+    r = O.forward_unit(cfg, x, w_q, w_v, w_o, rotations=rot[u], mask=None if mask is None else mask[b])
+    np.testing.assert_array_equal(got_buckets[u], r.buckets)
+    util.assert_close(out[u].float().cpu().numpy(), r.out, 'out[%d]' % u)
+    g = O.backward_unit(cfg, r, dout[u].astype(np.float64))[0]
+    util.assert_close(dq_dv[0][u].float().cpu().numpy(), g[:, :64], 'dqk[%d]' % u)
+    util.assert_close(dq_dv[1][u].float().cpu().numpy(), g[:, 64:], 'dv[%d]' % u)
+
+
+def trax_sig(shape):
+  import trax_b200
+  return trax_b200.ShapeDtype(shape)
+
+
+def test_lsh_equals_projections_plus_pure_core():
+  """efficient_attention_test.py:376-440: LSHSelfAttention(x) == (PureLSH(x w_q, x w_v) per head) w_o summed over heads,
+  with the same hash rotations."""
+  import trax_b200
+  B, L, D, H = 1, 512, 128, 2
+  cfg = util.make_cfg(H=H, C=128, nh=2, n_buckets=8)
+  rng = np.random.default_rng(11)
+  x = torch.from_numpy(util.bf16_round(rng.standard_normal((B, L, D)))).cuda()
+  rot = torch.from_numpy(rng.standard_normal((B * H, 64, cfg.n_hashes, 4)).astype(np.float32))
+  full = trax_b200.LSHSelfAttention(n_heads=H, d_qk=64, d_v=64, causal=True, chunk_len=128, n_hashes=2, n_buckets=8)
+  full.init(trax_b200.ShapeDtype((B, L, D)))
+  full._rotations_override = rot
+  want = full.forward(x.to(torch.bfloat16)).float()
+  w_q, w_v, w_o = (w.float() for w in full.weights)                 # (H, D, 64), (H, D, 64), (H, 64, D)
+  xb = x.to(torch.bfloat16).float()
+  q = torch.einsum('bld,hdk->bhlk', xb, w_q.to(torch.bfloat16).float()).reshape(B * H, L, 64)
+  v = torch.einsum('bld,hdk->bhlk', xb, w_v.to(torch.bfloat16).float()).reshape(B * H, L, 64)
+  pure = _pure(cfg)
+  pure.init((trax_b200.ShapeDtype((B * H, L, 64)), trax_b200.ShapeDtype((B * H, L, 64))))
+  pure._rotations_override = rot
+  o = pure.forward((q, v)).float()                                   # (B*H, L, 64)
+  np.testing.assert_array_equal(pure.state[0].cpu().numpy(), full.state[0].cpu().numpy())   # same buckets
+  got = torch.einsum('bhlk,hkd->bld', o.reshape(B, H, L, 64).to(torch.bfloat16).float(), w_o.to(torch.bfloat16).float())
+  util.assert_close(got.cpu().numpy(), want.cpu().numpy(), 'LSH vs projections + PureLSH + w_o')

@@ -2,10 +2,12 @@
 `trax.layers.research.efficient_attention.LSHSelfAttention` forward + backward.
 
 Layout: csrc/ (CUDA kernels + C ABI, built to liblsh_attn_b200.so), _lib.py (ctypes binding),
-ops.py (stage-level wrappers), lsh_attention.py (the layer with the reference's interface).
+ops.py (stage-level wrappers), lsh_attention.py (the layer with the reference's interface),
+pure_lsh_attention.py (its weight-less core, `PureLSHSelfAttention`).
 Importing the package does not need a GPU; calling anything does, and raises otherwise.
 """
 from trax_b200.lsh_attention import (LSHSelfAttention, ShapeDtype, host_io_bytes,  # noqa: F401
                                      set_async_host_io, synchronize)
+from trax_b200.pure_lsh_attention import PureLSHSelfAttention  # noqa: F401
 
-__all__ = ['LSHSelfAttention', 'ShapeDtype', 'set_async_host_io', 'synchronize', 'host_io_bytes']
+__all__ = ['LSHSelfAttention', 'PureLSHSelfAttention', 'ShapeDtype', 'set_async_host_io', 'synchronize', 'host_io_bytes']
