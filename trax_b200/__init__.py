@@ -7,7 +7,7 @@ pure_lsh_attention.py (its weight-less core, `PureLSHSelfAttention`).
 Importing the package does not need a GPU; calling anything does, and raises otherwise.
 """
 from trax_b200.lsh_attention import (LSHSelfAttention, ShapeDtype, host_io_bytes,  # noqa: F401
-                                     set_async_host_io, synchronize)
+                                     set_async_host_io, set_weight_grad_allreduce, synchronize)
 from trax_b200.pure_lsh_attention import PureLSHSelfAttention  # noqa: F401
 
-__all__ = ['LSHSelfAttention', 'PureLSHSelfAttention', 'ShapeDtype', 'set_async_host_io', 'synchronize', 'host_io_bytes']
+__all__ = ['LSHSelfAttention', 'PureLSHSelfAttention', 'ShapeDtype', 'set_async_host_io', 'set_weight_grad_allreduce', 'synchronize', 'host_io_bytes']

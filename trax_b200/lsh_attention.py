@@ -152,6 +152,16 @@ def set_async_host_io(flag):
   _HostIO.async_mode = bool(flag)
 
 
+_GRAD_ALLREDUCE = {'on': False}
+
+
+def set_weight_grad_allreduce(flag):
+  """Data-parallel training: average (dw_q, dw_v, dw_o) over the default process group INSIDE the backward call, on
+  the device, before they are returned / downloaded — the analogue of `psum(grads) / n` inside Trax's pmapped step
+  (`trax/optimizers/trainer.py:172-199`).  Off by default (the caller then reduces the returned gradients itself)."""
+  _GRAD_ALLREDUCE['on'] = bool(flag)
+
+
 def synchronize():
   """Waits for every enqueued layer call, including the host copies of results (pairs with set_async_host_io)."""
   torch.cuda.synchronize()
@@ -480,6 +490,9 @@ class LSHSelfAttention:
           ctypes.byref(dims), ops._ptr(x_d), ops._ptr(w_q), ops._ptr(w_v), ops._ptr(w_o), ops._ptr(mask_d),
           ops._ptr(buckets_d), buckets_d.stride(0), ops._ptr(g_d), ops._ptr(out_d), ops._ptr(dx), ops._ptr(dw_q),
           ops._ptr(dw_v), ops._ptr(dw_o), ops._ptr(ws), ws.numel(), stream), 'lsh_layer_bwd')
+      if _GRAD_ALLREDUCE['on']:
+        from trax_b200 import dp
+        dp.allreduce_mean_((dw_q, dw_v, dw_o))
       if host_io:
         dx, dw_q, dw_v, dw_o = (io.download(t, r) for t, r in ((dx, 'dx'), (dw_q, 'dw_q'), (dw_v, 'dw_v'), (dw_o, 'dw_o')))
       inputs_grad = dx if have_single_input else (dx,) + (None,) * (len(inputs) - 1)
