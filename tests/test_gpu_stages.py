@@ -172,6 +172,8 @@ CORE_CASES = [
     (1, 1, 128, 128, 1, 0, 1, 2, True, False),       # one chunk: window = [itself, itself]
     (1, 2, 512, 256, 1, 0, 2, 4, True, False),
     (1, 1, 256, 32, 1, 0, 2, 8, True, False),        # forward only for C=32
+    (1, 2, 192, 128, 1, 0, 2, 4, True, False),       # L % chunk_len != 0: a chunk straddles two hash rounds (same position twice)
+    (1, 1, 320, 128, 1, 0, 2, 4, True, False),
 ]
 
 

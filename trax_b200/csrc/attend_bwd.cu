@@ -319,7 +319,7 @@ int attend_bwd_run(const LshAttnDims &d, const void *qv, const int32_t *sticker,
   int rc;
   // tcgen05 path for the long-sequence shape; LSH_ATTN_BWD=mma forces the mma.sync path
   static const bool force_mma = [] { const char *e = getenv("LSH_ATTN_BWD"); return e && strcmp(e, "mma") == 0; }();
-  if (d.C == 128 && d.nb == 1 && d.na == 0 && d.causal && !d.masked && !force_mma) {
+  if (d.C == 128 && d.nb == 1 && d.na == 0 && d.causal && !d.masked && d.L % 128 == 0 && !force_mma) {
     const float *qscale = qscale_in;
     if (!qscale) {
       if ((rc = qscale_run(d, qv, qscale_ws, nullptr, nullptr, stream))) return rc;

@@ -212,7 +212,9 @@ static bool force_mma_fwd() {
   return f;
 }
 // tcgen05 path for the long-sequence shape (chunk 128, 2-chunk window); LSH_ATTN_FWD=mma forces the mma.sync path
-bool attend_fwd_uses_tc(const LshAttnDims &d) { return d.C == 128 && 1 + d.nb + d.na == 2 && !force_mma_fwd(); }
+// (L % 128 == 0: every chunk lies inside one hash round, so positions inside a tile are unique — the position-sorted
+// interval masks rely on that; other lengths take the mma.sync path)
+bool attend_fwd_uses_tc(const LshAttnDims &d) { return d.C == 128 && 1 + d.nb + d.na == 2 && d.L % 128 == 0 && !force_mma_fwd(); }
 
 int qscale_run(const LshAttnDims &d, const void *qv, float *qscale, float2 *rowmeta, void *qhat, cudaStream_t stream);
 int chunk_possort_run(const LshAttnDims &d, const int32_t *sticker, int32_t *sticker2, cudaStream_t stream);
