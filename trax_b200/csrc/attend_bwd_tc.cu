@@ -57,7 +57,7 @@ struct __align__(16) BtShared {
   BtTileMeta meta[BT_NST];
   uint64_t full[BT_NST], empty[BT_NST];
   uint64_t st_full[2], pds_full[2], dsm_free[2], dq_full[2];
-  uint64_t kv_full, kv_free;
+  uint64_t kv_full, kv_free, dq_free[2];
   uint32_t tmem_base;
 };
 
@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) attend_bwd_tc_kernel(const Atte
       mbar_init(&sh.dsm_free[i], 1); mbar_init(&sh.dq_full[i], 1);
     }
     mbar_init(&sh.kv_full, 1); mbar_init(&sh.kv_free, 128);
+    mbar_init(&sh.dq_free[0], 128); mbar_init(&sh.dq_free[1], 128);
     fence_mbar_init();
   }
   tc_fence_before();
@@ -238,6 +239,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) attend_bwd_tc_kernel(const Atte
       mbar_wait(&sh.full[bt_slot(it.seq_q)], bt_phase(it.seq_q));
       tc_fence_after();   // (tiles are signalled by their cp.async copies; same protocol as CUTLASS's sm100 cp.async mainloop)
     };
+    int n_epi[2] = {0, 0};                                   // epilogues started per dQ slot (kv_full commits)
     BtWalk w(g0, g1, p.n_chunks);
     BtItem cur = w.item();
     wait_tiles(cur);
@@ -249,15 +251,19 @@ __global__ void __launch_bounds__(BT_THREADS, 1) attend_bwd_tc_kernel(const Atte
       BtItem nxt = cur;
       if (have_next) nxt = w.item();
       const uint32_t qt = tile_addr(cur.seq_q), kt = tile_addr(cur.seq_k);
-      // Pre-issue the next item's S^T / dP^T inside this item only if its tiles have ALREADY landed: blocking here
-      // could deadlock (at a segment boundary the next tiles reuse the slot of the tile this item still holds).
-      bool pre_issue = false;
-      if (have_next) {
-        pre_issue = mbar_test(&sh.full[bt_slot(nxt.seq_k)], bt_phase(nxt.seq_k)) &&
+      // Pre-issue the next item's S^T / dP^T inside this item as soon as its tiles have landed — probed (never waited
+      // for: at a segment boundary the next tiles reuse the slot of a tile this item still holds) before each half and
+      // once more after the dQ MMAs, because at an iteration boundary the new key tile typically lands late in the item.
+      bool pre_ok = false;
+      int st_issued = 0;                                     // halves of the next item already issued
+      auto probe = [&]() {
+        if (have_next && !pre_ok) {
+          bool ok = mbar_test(&sh.full[bt_slot(nxt.seq_k)], bt_phase(nxt.seq_k)) &&
                     mbar_test(&sh.full[bt_slot(nxt.seq_q)], bt_phase(nxt.seq_q));
-        pre_issue = __all_sync(0xffffffffu, pre_issue);
-        if (pre_issue) tc_fence_after();
-      }
+          ok = __all_sync(0xffffffffu, ok);
+          if (ok) { tc_fence_after(); pre_ok = true; }
+        }
+      };
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const uint32_t r = tmem + 128 * h;
@@ -276,11 +282,19 @@ __global__ void __launch_bounds__(BT_THREADS, 1) attend_bwd_tc_kernel(const Atte
           }
           __syncwarp();
         }
-        if (pre_issue) issue_st(nxt, h);   // the region is free once the MMAs above have read it (in-order pipe)
+        // region h is free once the MMAs above have read it (in-order pipe)
+        probe();
+        if (pre_ok) {
+          for (; st_issued <= h; ++st_issued) issue_st(nxt, st_issued);
+        }
       }
       {
         const uint32_t a0 = desc_lo(ds_u32 + (cur.n & 1) * BT_DS_BYTES, 16384), kb = desc_lo(kt, 1024);
         const uint32_t dq_t = tmem + 384 + 64 * cur.dq_slot;
+        // a fresh dQ accumulation re-uses the slot the epilogue of two iterations back drained (it signals dq_free as
+        // soon as its dQ loads are done; dK^/dV are handed back separately and earlier through kv_free)
+        if (cur.do_dq && cur.dq_fresh && n_epi[cur.dq_slot] > 0) mbar_wait(&sh.dq_free[cur.dq_slot], (n_epi[cur.dq_slot] - 1) & 1);
+        if (cur.do_kv && cur.iter_end) ++n_epi[cur.rit & 1];
         if (elect_one()) {
           if (cur.do_kv && cur.iter_end) umma_commit(&sh.kv_full);
           if (cur.do_dq) {
@@ -296,12 +310,15 @@ __global__ void __launch_bounds__(BT_THREADS, 1) attend_bwd_tc_kernel(const Atte
         }
         __syncwarp();
       }
+      probe();
+      if (pre_ok) {
+        for (; st_issued < 2; ++st_issued) issue_st(nxt, st_issued);
+      }
       if (lane == 0) BT_TRACE(cur.n, 2);
       if (!have_next) break;
-      if (!pre_issue) {
+      if (st_issued < 2) {
         wait_tiles(nxt);
-        issue_st(nxt, 0);
-        issue_st(nxt, 1);
+        for (; st_issued < 2; ++st_issued) issue_st(nxt, st_issued);
       }
       cur = nxt;
     }
@@ -444,10 +461,32 @@ __global__ void __launch_bounds__(BT_THREADS, 1) attend_bwd_tc_kernel(const Atte
         mbar_wait(&sh.kv_full, it.rit & 1);
         tc_fence_after();
         uint32_t dk0[32], dk1[32];
+        __nv_bfloat16 *dq_dst = p.dq_out + orow, *dv_dst = p.dv_out + orow;
         tmem_ld32(t_lane + 256, dk0);
         tmem_ld32(t_lane + 288, dk1);
-        tmem_ld_wait_dep(dk0);
-        tmem_ld_wait_dep(dk1);
+        // dV first: together with the dK^ loads above it empties both accumulators, so the next key chunk's dV / dK^
+        // MMAs (kv_free) wait for four TMEM loads instead of the whole epilogue
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t g[32];
+          tmem_ld32(t_lane + 320 + 32 * half, g);
+          tmem_ld_wait_dep(g);
+          if (half == 1) {
+            tmem_ld_wait_dep(dk0);
+            tmem_ld_wait_dep(dk1);
+            tc_fence_before();
+            mbar_arrive(&sh.kv_free);
+          }
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            uint4 v;
+            v.x = pack_bf16(__uint_as_float(g[8 * q4 + 0]), __uint_as_float(g[8 * q4 + 1]));
+            v.y = pack_bf16(__uint_as_float(g[8 * q4 + 2]), __uint_as_float(g[8 * q4 + 3]));
+            v.z = pack_bf16(__uint_as_float(g[8 * q4 + 4]), __uint_as_float(g[8 * q4 + 5]));
+            v.w = pack_bf16(__uint_as_float(g[8 * q4 + 6]), __uint_as_float(g[8 * q4 + 7]));
+            *reinterpret_cast<uint4 *>(dv_dst + half * 32 + q4 * 8) = v;
+          }
+        }
         float dot = 0.f;
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) {
@@ -464,12 +503,15 @@ __global__ void __launch_bounds__(BT_THREADS, 1) attend_bwd_tc_kernel(const Atte
         const float r_j = 0.125f * kLog2e / ksc_j;       // sqrt(mean(q^2) + eps)
         const float a_j = 0.125f / r_j;
         const float c_j = dot * 0.125f / (64.f * r_j * r_j * r_j);
-        __nv_bfloat16 *dq_dst = p.dq_out + orow, *dv_dst = p.dv_out + orow;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           uint32_t g[32];
           tmem_ld32(t_lane + 384 + 64 * (it.rit & 1) + 32 * half, g);
           tmem_ld_wait_dep(g);
+          if (half == 1) {                               // the dQ slot may be re-used by the next fresh accumulation
+            tc_fence_before();
+            mbar_arrive(&sh.dq_free[it.rit & 1]);
+          }
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4) {
             const int ch = half * 4 + c4;
@@ -487,29 +529,13 @@ __global__ void __launch_bounds__(BT_THREADS, 1) attend_bwd_tc_kernel(const Atte
             *reinterpret_cast<uint4 *>(dq_dst + ch * 8) = v;
           }
         }
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t g[32];
-          tmem_ld32(t_lane + 320 + 32 * half, g);
-          tmem_ld_wait_dep(g);
-          if (half == 1) {                               // every TMEM read of this iteration is complete
-            tc_fence_before();
-            mbar_arrive(&sh.kv_free);
-          }
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            uint4 v;
-            v.x = pack_bf16(__uint_as_float(g[8 * q4 + 0]), __uint_as_float(g[8 * q4 + 1]));
-            v.y = pack_bf16(__uint_as_float(g[8 * q4 + 2]), __uint_as_float(g[8 * q4 + 3]));
-            v.z = pack_bf16(__uint_as_float(g[8 * q4 + 4]), __uint_as_float(g[8 * q4 + 5]));
-            v.w = pack_bf16(__uint_as_float(g[8 * q4 + 6]), __uint_as_float(g[8 * q4 + 7]));
-            *reinterpret_cast<uint4 *>(dv_dst + half * 32 + q4 * 8) = v;
-          }
-        }
+        // last read of the key tile's rows is behind us: give the ring slot back
+        mbar_arrive(&sh.empty[slk]);
+        if (it.last_seg) mbar_arrive(&sh.empty[bt_slot(it.seq_k + 1)]);
         if (row == 0) BT_TRACE(it.n, 7);
+      } else {
+        mbar_arrive(&sh.empty[slk]);                           // pre item: this warpgroup never touches the tile
       }
-      mbar_arrive(&sh.empty[slk]);
-      if (it.real && it.last_seg) mbar_arrive(&sh.empty[bt_slot(it.seq_k + 1)]);
     }
   }
   tc_fence_before();
