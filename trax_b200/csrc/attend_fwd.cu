@@ -257,7 +257,6 @@ int attend_fwd_run(const LshAttnDims &d, const void *qv, const int32_t *sticker,
   p.qhat = aux ? static_cast<const __nv_bfloat16 *>(aux->qhat) : nullptr;
   p.rowmeta = aux ? aux->rowmeta : nullptr;
   p.sticker2 = aux ? aux->sticker2 : nullptr;
-  { const char *e = getenv("LSH_ATTN_STAGGER_NS"); p.stagger_ns = e ? static_cast<unsigned>(atoi(e)) : 0u; }
   p.L = d.L; p.H = d.H; p.N = dr.N; p.n_chunks = dr.n_chunks; p.nb = d.nb; p.nwin = dr.nwin;
   p.causal = d.causal; p.masked = d.masked;
   if (d.masked && !mask) return set_error("attend_fwd: dims.masked set but mask == NULL");

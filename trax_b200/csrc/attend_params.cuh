@@ -16,7 +16,6 @@ struct AttendFwdParams {
   const float2 *rowmeta;        // (BH, L) {a = 8 r log2e, m2 = a |qhat|^2}               }
   const int32_t *sticker2;      // (BH, N) sticker with every chunk re-ordered by position }
   long long *trace;             // debug: per-phase clock64 stamps of CTA 0 (null = off)
-  unsigned stagger_ns;          // start delay of the second softmax warpgroup (tcgen05 path)
   int L, H, N, n_chunks, nb, nwin, causal, masked;
 };
 

@@ -131,13 +131,9 @@ __device__ __forceinline__ float quad_sum(float v) {
 
 // 2^x on the SFU (MUFU.EX2), flush-to-zero: one instruction, ~2 ulp; exp2(-huge) == 0 exactly.
 __device__ __forceinline__ float fast_exp2(float x) {
-#if defined(LSH_EXP_NOMUFU)
-  return x * 1.0001f;
-#else
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
   return y;
-#endif
 }
 
 constexpr float kLog2e = 1.4426950408889634f;

@@ -51,9 +51,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   uint32_t spins = 0;
 #endif
   while (!mbar_try_wait(bar, parity)) {
-#if defined(LSH_EXP_SPINSLEEP)
-    __nanosleep(LSH_EXP_SPINSLEEP);
-#endif
     if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
 #ifdef LSH_DEBUG_SPIN
     if (++spins > (1u << 16)) __trap();   // a protocol bug becomes a trap instead of a hung GPU
@@ -126,9 +123,6 @@ __device__ __forceinline__ bool elect_one() {
 }
 __device__ __forceinline__ void umma_ss2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
                                          uint32_t idesc, uint32_t accum) {
-#if defined(LSH_EXP_NOMMA)
-  return;
-#endif
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
@@ -142,9 +136,6 @@ __device__ __forceinline__ void umma_ss2(uint32_t d_tmem, uint32_t a_lo, uint32_
 }
 __device__ __forceinline__ void umma_ts2(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
                                          uint32_t accum) {
-#if defined(LSH_EXP_NOMMA)
-  return;
-#endif
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
