@@ -123,6 +123,27 @@ int lsh_attend_bwd(const LshAttnDims *dims, const void *qv_bf16, const int32_t *
                    const void *do_comb_bf16, void *dqv_bf16, void *ws, size_t ws_bytes,
                    void *stream);
 
+/* ---- neighbours of the layer inside the reversible block -------------------
+ * trax/layers/reversible.py:244-412 `ReversibleHalfResidual(LayerNorm(), attention_layer=LSHSelfAttention)`:
+ * forward  y1 = x1 + Attn(LN(x2));  reverse_and_grad  x1 = y1 - Attn(LN(x2)), ct_x2 += LN_vjp(dz).
+ * Activations (rows, d_model) in dims-style act_dtype (LSH_DTYPE_F32 / LSH_DTYPE_BF16); d_model in {256,512,1024,2048}. */
+
+/* trax/layers/normalization.py:129-136 (center=True): z = (x - mean) / sqrt(var + epsilon) * scale + bias.
+ * stats (rows, 2) f32 receives {mean, 1/sqrt(var + epsilon)} for the backward (may be NULL). */
+int lsh_layernorm_fwd(int64_t rows, int d_model, int act_dtype, const void *x, const float *scale,
+                      const float *bias, void *z, float *stats, float epsilon, void *stream);
+
+/* VJP of the above: ct_out = (ct_in ? ct_in : 0) + dx (reversible.py:397-398 adds it to the context cotangent);
+ * d_scale, d_bias (d_model) f32 are overwritten. */
+int lsh_layernorm_bwd(int64_t rows, int d_model, int act_dtype, const void *x, const void *dz,
+                      const void *ct_in, const float *stats, const float *scale, void *ct_out,
+                      float *d_scale, float *d_bias, void *stream);
+
+/* reversible.py:400 reconstructed_x = accumulator_output - residual (n elements, n % 8 == 0; out may alias a). */
+int lsh_residual_sub(int64_t n, int act_dtype, const void *a, const void *b, void *out, void *stream);
+/* reversible.py:318 output = accumulator + residual. */
+int lsh_residual_add(int64_t n, int act_dtype, const void *a, const void *b, void *out, void *stream);
+
 /* ---- layer-level entry points (EA:2261-2561 forward_and_or_backward) -------------------------- */
 
 size_t lsh_layer_workspace_bytes(const LshAttnDims *dims, int with_grad);

@@ -451,3 +451,43 @@ def init_weights(n_heads, d_model, d_qk, d_v, seed=1):
   w_v = np.stack([ki((d_model, d_v)) for _ in range(n_heads)])
   w_o = np.stack([ki((d_model, d_v)).T for _ in range(n_heads)])
   return w_q, w_v, np.ascontiguousarray(w_o)
+
+
+# ---- the reversible block around the layer (trax/layers/reversible.py:244-412, layers/normalization.py:121-142) -------
+def layernorm(x, scale, bias, epsilon=1e-6):
+  """normalization.py:129-136 (center=True), fp64."""
+  x = np.asarray(x, np.float64)
+  mean = x.mean(axis=-1, keepdims=True)
+  centered = x - mean
+  variance = (centered * centered).mean(axis=-1, keepdims=True)
+  return centered / np.sqrt(variance + epsilon) * scale + bias
+
+
+def layernorm_vjp(x, scale, dz, epsilon=1e-6):
+  """VJP of `layernorm` at x for cotangent dz: (dx, d_scale, d_bias) — what fastmath.vjp(call_compute_residual) returns
+  at reversible.py:352-353 / 384-385."""
+  x, dz = np.asarray(x, np.float64), np.asarray(dz, np.float64)
+  mean = x.mean(axis=-1, keepdims=True)
+  centered = x - mean
+  rstd = 1.0 / np.sqrt((centered * centered).mean(axis=-1, keepdims=True) + epsilon)
+  norm = centered * rstd
+  g = dz * scale
+  dx = rstd * (g - g.mean(axis=-1, keepdims=True) - norm * (g * norm).mean(axis=-1, keepdims=True))
+  red = tuple(range(x.ndim - 1))
+  return dx, (dz * norm).sum(axis=red), dz.sum(axis=red)
+
+
+def reversible_half_forward(cfg: LSHConfig, x1, x2, ln_weights, attn_weights, rotations, epsilon=1e-6):
+  """ReversibleHalfResidual(LayerNorm(), attention_layer=LSHSelfAttention).forward (reversible.py:296-321):
+  returns ((y1, x2), buckets)."""
+  z = layernorm(x2, ln_weights[0], ln_weights[1], epsilon)
+  res, buckets, _, _ = forward_and_or_backward(cfg, z, attn_weights, rotations=rotations, update_state=True)
+  return (np.asarray(x1, np.float64) + res, x2), buckets
+
+
+def reversible_half_reverse_and_grad(cfg: LSHConfig, y1, x2, ct_y1, ct_x2, ln_weights, attn_weights, buckets, epsilon=1e-6):
+  """reverse_and_grad (reversible.py:326-412): returns ((x1, x2), ((ct_y1, ct_x2'), ((d_scale, d_bias), attn dW)))."""
+  z = layernorm(x2, ln_weights[0], ln_weights[1], epsilon)
+  res, _, dz, dw = forward_and_or_backward(cfg, z, attn_weights, buckets=buckets, output_grad=ct_y1, update_state=False)
+  dx2, d_scale, d_bias = layernorm_vjp(x2, ln_weights[0], dz, epsilon)
+  return (np.asarray(y1, np.float64) - res, x2), ((ct_y1, np.asarray(ct_x2, np.float64) + dx2), ((d_scale, d_bias), dw))

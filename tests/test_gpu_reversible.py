@@ -1,0 +1,84 @@
+"""GPU parity tests of the reversible block around the layer (`trax_b200.ReversibleHalfResidual`)
+against the oracle's restatement of `trax/layers/reversible.py:296-412` + `layers/normalization.py:129-136`."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import lsh_oracle as O
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('rows,D', [(37, 256), (1000, 1024), (8, 2048)])
+def test_layernorm_fwd_bwd(rows, D, dtype):
+  from trax_b200 import reversible as R
+  rng = np.random.default_rng(rows + D)
+  rnd = util.bf16_round if dtype == torch.bfloat16 else (lambda a: np.asarray(a, np.float32))
+  x = rnd(rng.standard_normal((rows, D)) * 2 + 0.5)
+  dz = rnd(rng.standard_normal((rows, D)))
+  ct = rnd(rng.standard_normal((rows, D)))
+  scale = (1 + 0.1 * rng.standard_normal(D)).astype(np.float32)
+  bias = (0.1 * rng.standard_normal(D)).astype(np.float32)
+  cu = lambda a, dt=torch.float32: torch.from_numpy(np.asarray(a, np.float32)).cuda().to(dt)
+  z, stats = R.layernorm_fwd(cu(x, dtype), cu(scale), cu(bias))
+  util.assert_close(z.float().cpu().numpy(), O.layernorm(x, scale, bias), 'z')
+  ct_out, d_scale, d_bias = R.layernorm_bwd(cu(x, dtype), cu(dz, dtype), cu(ct, dtype), stats, cu(scale))
+  dx, ws, wb = O.layernorm_vjp(x, scale, dz)
+  util.assert_close(ct_out.float().cpu().numpy(), ct + dx, 'ct + dx')
+  util.assert_close(d_scale.cpu().numpy(), ws, 'd_scale')
+  util.assert_close(d_bias.cpu().numpy(), wb, 'd_bias')
+  only_dx, _, _ = R.layernorm_bwd(cu(x, dtype), cu(dz, dtype), None, stats, cu(scale))
+  util.assert_close(only_dx.float().cpu().numpy(), dx, 'dx')
+
+
+@pytest.mark.parametrize('B,L,D,dtype,cfg', [
+    (1, 512, 256, torch.float32, util.make_cfg(H=2, C=128, nh=2, n_buckets=8)),
+    (2, 512, 256, torch.bfloat16, util.make_cfg(H=4, C=128, nh=4, n_buckets=None)),
+    (1, 1024, 256, torch.float32, util.make_cfg(H=2, C=64, nh=1, n_buckets=32)),
+])
+def test_reversible_half_forward_and_reverse_and_grad(B, L, D, dtype, cfg):
+  import trax_b200
+  rng = np.random.default_rng(17)
+  rnd = util.bf16_round if dtype == torch.bfloat16 else (lambda a: np.asarray(a, np.float32))
+  x1, x2 = rnd(rng.standard_normal((B, L, D))), rnd(rng.standard_normal((B, L, D)))
+  ct_y1, ct_x2 = rnd(rng.standard_normal((B, L, D))), rnd(rng.standard_normal((B, L, D)))
+  scale = (1 + 0.1 * rng.standard_normal(D)).astype(np.float32)
+  bias = (0.1 * rng.standard_normal(D)).astype(np.float32)
+  attn_w = O.init_weights(cfg.n_heads, D, 64, 64, seed=3)
+  factors = O.bucket_factors(cfg.n_buckets, L, cfg.chunk_len)
+  rot = rng.standard_normal((B * cfg.n_heads, 64, cfg.n_hashes, sum(factors) // 2)).astype(np.float32)
+
+  attn = trax_b200.LSHSelfAttention(n_heads=cfg.n_heads, d_qk=64, d_v=64, causal=True, chunk_len=cfg.chunk_len,
+                                    n_hashes=cfg.n_hashes, n_buckets=cfg.n_buckets)
+  block = trax_b200.ReversibleHalfResidual(attn)
+  sig = trax_b200.ShapeDtype((B, L, D))
+  block.init((sig, sig))
+  cu = lambda a, dt=torch.float32: torch.from_numpy(np.asarray(a, np.float32)).cuda().to(dt)
+  block.weights = ((cu(scale), cu(bias)), tuple(cu(w) for w in attn_w))
+  attn._rotations_override = torch.from_numpy(rot)
+
+  # forward: (x1, x2) -> (x1 + Attn(LN(x2)), x2); bucket ids bit-exact would need identical z bits, so they are taken from
+  # the GPU state for the reverse pass (the reference stores them in new_state for the same reason, reversible.py:263-265)
+  y1, ctx = block.forward((cu(x1, dtype), cu(x2, dtype)))
+  buckets = block.state[1][0].cpu().numpy()
+  z = O.layernorm(x2, scale, bias)
+  want_res, _, _, _ = O.forward_and_or_backward(cfg, z, attn_w, buckets=buckets, update_state=False)
+  util.assert_close(y1.float().cpu().numpy(), x1 + want_res, 'y1')
+  assert ctx.data_ptr() == ctx.data_ptr() and torch.equal(ctx.float().cpu(), torch.from_numpy(x2))
+
+  # reverse_and_grad from (y1, x2) and cotangents
+  y1_np = rnd(y1.float().cpu().numpy())
+  (rx1, rx2), ((g_y1, g_x2), ((d_scale, d_bias), dw)) = block.reverse_and_grad(
+      (y1, ctx), (cu(ct_y1, dtype), cu(ct_x2, dtype)), block.weights, None, block.state, None)
+  (wx1, _), ((_, w_ct_x2), ((w_ds, w_db), w_dw)) = O.reversible_half_reverse_and_grad(
+      cfg, y1_np, x2, ct_y1, ct_x2, (scale, bias), attn_w, buckets)
+  util.assert_close(rx1.float().cpu().numpy(), wx1, 'reconstructed x1')
+  util.assert_close(rx1.float().cpu().numpy(), x1, 'reconstructed x1 vs the original input', rtol=3e-2)
+  assert torch.equal(rx2, ctx) and torch.equal(g_y1.float().cpu(), torch.from_numpy(ct_y1))
+  util.assert_close(g_x2.float().cpu().numpy(), w_ct_x2, 'ct_x2')
+  util.assert_close(d_scale.cpu().numpy(), w_ds, 'd_scale')
+  util.assert_close(d_bias.cpu().numpy(), w_db, 'd_bias')
+  for n, g, w in zip(('dw_q', 'dw_v', 'dw_o'), dw, w_dw):
+    util.assert_close(g.float().cpu().numpy(), w, n)

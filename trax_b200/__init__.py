@@ -9,5 +9,6 @@ Importing the package does not need a GPU; calling anything does, and raises oth
 from trax_b200.lsh_attention import (LSHSelfAttention, ShapeDtype, host_io_bytes,  # noqa: F401
                                      set_async_host_io, set_weight_grad_allreduce, synchronize)
 from trax_b200.pure_lsh_attention import PureLSHSelfAttention  # noqa: F401
+from trax_b200.reversible import ReversibleHalfResidual  # noqa: F401
 
-__all__ = ['LSHSelfAttention', 'PureLSHSelfAttention', 'ShapeDtype', 'set_async_host_io', 'set_weight_grad_allreduce', 'synchronize', 'host_io_bytes']
+__all__ = ['LSHSelfAttention', 'PureLSHSelfAttention', 'ReversibleHalfResidual', 'ShapeDtype', 'set_async_host_io', 'set_weight_grad_allreduce', 'synchronize', 'host_io_bytes']

@@ -48,6 +48,10 @@ SIGNATURES = {
     'lsh_layer_fwd': (_I, [_D, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _SZ, _P]),
     'lsh_layer_bwd': (_I, [_D, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     'lsh_make_rotations': (_I, [_D, _P, _P, _P, _P]),
+    'lsh_layernorm_fwd': (_I, [_I64, _I, _I, _P, _P, _P, _P, _P, ctypes.c_float, _P]),
+    'lsh_layernorm_bwd': (_I, [_I64, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'lsh_residual_sub': (_I, [_I64, _I, _P, _P, _P, _P]),
+    'lsh_residual_add': (_I, [_I64, _I, _P, _P, _P, _P]),
     'lsh_attn_launch_count': (_I64, [_I]),
 }
 

@@ -44,6 +44,10 @@ int pack_weights_run(const LshAttnDims &, const float *, const float *, const fl
 int f32_to_bf16_run(const float *, void *, int64_t, cudaStream_t);
 int unpack_dwqv_run(const LshAttnDims &, const float *, float *, float *, cudaStream_t);
 int make_rotations_run(const LshAttnDims &, const uint32_t *, uint32_t *, float *, cudaStream_t);
+int layernorm_fwd_run(int64_t, int, int, const void *, const float *, const float *, void *, float2 *, float, cudaStream_t);
+int layernorm_bwd_run(int64_t, int, int, const void *, const void *, const void *, const float2 *, const float *, void *, float *,
+                      float *, cudaStream_t);
+int residual_sub_run(int64_t, int, const void *, const void *, void *, float, cudaStream_t);
 
 // ---- dims ------------------------------------------------------------------------------------------
 static int check_dims(const LshAttnDims *dp, bool need_bwd) {
@@ -344,6 +348,34 @@ int lsh_layer_bwd(const LshAttnDims *dims, const void *x, const float *w_q, cons
   if ((rc = gemm_rm(true, false, d.D, NQV, BL, xb, d.D, w.dqv, NQV, w.dwqv, NQV, true, w.cublas, s))) return rc;
   if ((rc = unpack_dwqv_run(d, w.dwqv, dw_q, dw_v, s))) return rc;
   return gemm_rm(false, true, BL, d.D, NQV, w.dqv, NQV, w.wqv, NQV, dx, d.D, f32, w.cublas, s);
+}
+
+int lsh_layernorm_fwd(int64_t rows, int d_model, int act_dtype, const void *x, const float *scale, const float *bias, void *z,
+                      float *stats, float epsilon, void *stream) {
+  if (!x || !scale || !bias || !z) return set_error("lsh_layernorm_fwd: NULL argument");
+  if (act_dtype != LSH_DTYPE_F32 && act_dtype != LSH_DTYPE_BF16) return set_error("lsh_layernorm_fwd: bad act_dtype");
+  return layernorm_fwd_run(rows, d_model, act_dtype, x, scale, bias, z, reinterpret_cast<float2 *>(stats), epsilon,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int lsh_layernorm_bwd(int64_t rows, int d_model, int act_dtype, const void *x, const void *dz, const void *ct_in,
+                      const float *stats, const float *scale, void *ct_out, float *d_scale, float *d_bias, void *stream) {
+  if (!x || !dz || !stats || !scale || !ct_out || !d_scale || !d_bias) return set_error("lsh_layernorm_bwd: NULL argument");
+  if (act_dtype != LSH_DTYPE_F32 && act_dtype != LSH_DTYPE_BF16) return set_error("lsh_layernorm_bwd: bad act_dtype");
+  return layernorm_bwd_run(rows, d_model, act_dtype, x, dz, ct_in, reinterpret_cast<const float2 *>(stats), scale, ct_out, d_scale,
+                           d_bias, static_cast<cudaStream_t>(stream));
+}
+
+int lsh_residual_sub(int64_t n, int act_dtype, const void *a, const void *b, void *out, void *stream) {
+  if (!a || !b || !out) return set_error("lsh_residual_sub: NULL argument");
+  if (act_dtype != LSH_DTYPE_F32 && act_dtype != LSH_DTYPE_BF16) return set_error("lsh_residual_sub: bad act_dtype");
+  return residual_sub_run(n, act_dtype, a, b, out, -1.f, static_cast<cudaStream_t>(stream));
+}
+
+int lsh_residual_add(int64_t n, int act_dtype, const void *a, const void *b, void *out, void *stream) {
+  if (!a || !b || !out) return set_error("lsh_residual_add: NULL argument");
+  if (act_dtype != LSH_DTYPE_F32 && act_dtype != LSH_DTYPE_BF16) return set_error("lsh_residual_add: bad act_dtype");
+  return residual_sub_run(n, act_dtype, a, b, out, 1.f, static_cast<cudaStream_t>(stream));
 }
 
 /* Debug aid (not in the public header): device buffer receiving per-phase clock stamps of CTA 0. */
