@@ -155,6 +155,10 @@ def run_ours(args, wl, name):
   world = int(os.environ.get('WORLD_SIZE', '1'))
   rank = int(os.environ.get('RANK', '0'))
   local = int(os.environ.get('LOCAL_RANK', '0'))
+  # Libraries (NCCL's version banner) write to fd 1: park stdout on stderr until the ONE JSON line is printed
+  sys.stdout.flush()
+  saved_stdout = os.dup(1)
+  os.dup2(2, 1)
   torch.cuda.set_device(local)
   dev = torch.device('cuda', local)
   if world > 1:
@@ -273,6 +277,9 @@ def run_ours(args, wl, name):
   if world > 1:
     dist.barrier()
     dist.destroy_process_group()
+  sys.stdout.flush()
+  os.dup2(saved_stdout, 1)
+  os.close(saved_stdout)
   if rank == 0:
     print(json.dumps(line))
 
