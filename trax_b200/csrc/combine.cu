@@ -185,9 +185,14 @@ __global__ void __launch_bounds__(ROW_THREADS) qscale_kernel(const __nv_bfloat16
                                                             float *__restrict__ qscale, float2 *__restrict__ rowmeta,
                                                             __nv_bfloat16 *__restrict__ qhat, int L, int H,
                                                             int64_t total_rows) {
-  const int64_t row = (static_cast<int64_t>(blockIdx.x) * ROW_THREADS + threadIdx.x) >> 3;   // (b, t, h)
+  // rows in (unit, position) order: the three outputs are written contiguously; the q reads are 128-byte pieces at a
+  // stride of H * 256 bytes (whole sectors either way)
+  const int64_t ut = (static_cast<int64_t>(blockIdx.x) * ROW_THREADS + threadIdx.x) >> 3;    // (u, t)
   const int ch = threadIdx.x & 7;
-  const bool ok = row < total_rows;
+  const bool ok = ut < total_rows;
+  const int64_t u = ut / L, t = ut - u * L;
+  const int64_t b = u / H, h = u - b * H;
+  const int64_t row = (b * L + t) * H + h;                                                      // row of qv
   float s = 0.f;
   float a[8];
   if (ok) {
@@ -199,9 +204,6 @@ __global__ void __launch_bounds__(ROW_THREADS) qscale_kernel(const __nv_bfloat16
   s += __shfl_xor_sync(0xffffffffu, s, 2);
   s += __shfl_xor_sync(0xffffffffu, s, 4);
   const float r = sqrtf(s * (1.0f / 64) + 1e-6f);
-  const int64_t h = row % H, bt = row / H;
-  const int64_t b = bt / L, t = bt % L;
-  const int64_t ut = (b * H + h) * L + t;
   float s2 = 0.f;
   if (ok && qhat != nullptr) {
     const float c = 0.125f / r;
