@@ -486,12 +486,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
         const uint32_t rest = need & ~((2u << after) - 1u);
         return rest ? __ffs(rest) - 1 : 4;
       };
+      // The score buffer goes back to the issuer as soon as the LAST load of the pass has completed — before that
+      // block's math, the row statistics and the wait for the P stores — so the next chunk's score MMA overlaps them.
+      auto release_scores = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh.s_free[wg]);
+      };
       int b0 = need ? __ffs(need) - 1 : 4;
       if (b0 < 4) tmem_ld32(t_lane + b0 * 32, ra);
+      else release_scores();
       int done_to = 0;                                                // blocks < done_to are final
       while (b0 < 4) {
         const int b1 = next_needed(b0);
         tmem_ld_wait_dep(ra);
+        if (b1 >= 4) release_scores();
         zero_until(done_to, b0);
         if (b1 < 4) tmem_ld32(t_lane + b1 * 32, rb);
         process(ra, b0);
@@ -499,6 +508,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
         if (b1 >= 4) break;
         const int b2 = next_needed(b1);
         tmem_ld_wait_dep(rb);
+        if (b2 >= 4) release_scores();
         zero_until(done_to, b1);
         if (b2 < 4) tmem_ld32(t_lane + b2 * 32, ra);
         process(rb, b1);
@@ -519,7 +529,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) { mbar_arrive(&sh.s_free[wg]); mbar_arrive(&sh.p_full[wg]); mbar_arrive(&sh.l_full[ob]); }
+      if (lane == 0) { mbar_arrive(&sh.p_full[wg]); mbar_arrive(&sh.l_full[ob]); }
       if (TC_TRACE_ON && lane == 0 && p.trace && blockIdx.x == 0 && wk.k < 120) atomicMax(reinterpret_cast<unsigned long long *>(p.trace) + wk.k * 16 + 3, static_cast<unsigned long long>(clock64()));
     }
   } else if (warp >= 8 && warp < 12) {
