@@ -10,8 +10,8 @@ struct AttendBwdTcParams {
   const int32_t *sticker2;        // (BH, N) sticker with every 128-slot chunk re-ordered by position (chunk_possort_kernel)
   const __nv_bfloat16 *do_comb;   // (B, L, H, 64)
   const float *qscale;            // (BH, L)  log2e / (sqrt(mean(q^2)+eps) sqrt(dq))
-  const float *lse2;              // (BH, L)  log2e * lse_tot (+ log2e*1e5 for self-only rows)
-  const float *dvec;              // (BH, L)  do . o
+  const float *lse2;              // (BH, L)  -(log2e * lse_tot (+ log2e*1e5 for self-only rows))   } stored negated
+  const float *dvec;              // (BH, L)  -(do . o)                                              }
   const float *qcmp;              // (BH, L)  pos + 1 (+ 0.5 for self-only rows)
   __nv_bfloat16 *dq_out;          // (BH, N, 64) ticker order: dq_query + dq_key of every token copy
   __nv_bfloat16 *dv_out;          // (BH, N, 64)

@@ -47,8 +47,8 @@ constexpr uint32_t BT_IDESC_DQ = make_idesc_bf16(128, 64, 1, 1);   // dQ (A and 
 struct __align__(16) BtTileMeta {
   float kinfo[BT_C];    // pos + 1 as fp32 (key side of the causal compare)
   float qcmp[BT_C];     // pos + 1, or pos + 1.5 for rows whose only visible key is their own "-1e5" class
-  float lse2[BT_C];     // log2(e) * lse_tot (+ the -1e5 class shift for those rows)
-  float dvec[BT_C];     // D_i = do_i . o_i
+  float lse2[BT_C];     // -(log2(e) * lse_tot (+ the -1e5 class shift for those rows))
+  float dvec[BT_C];     // -D_i = -(do_i . o_i)
   float kscl[BT_C];     // log2(e) / (sqrt(mean(q^2)+eps) * sqrt(dq))
   int tk[BT_C];         // ticker
 };
@@ -340,6 +340,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) attend_bwd_tc_kernel(const Atte
       mbar_wait(&sh.full[slq], bt_phase(it.seq_q));
       const BtTileMeta &mq = sh.meta[slq];
       const float kst_j = ksc_j * kLn2;                    // true key scale 1/(r*sqrt(dq)) for the dQ operand
+      const uint64_t ksc2 = pk2(ksc_j, ksc_j), kst2 = pk2(kst_j, kst_j);
       uint8_t *dsrow = dsbuf + (it.n & 1) * BT_DS_BYTES + h * (BT_C * 128);
       // Tiles are ordered by position (chunk_possort_kernel), so for key j the queries of the tile split into three index
       // ranges: [0, lo) position below the key's — never visible (EA:150-152); [lo, hi) the same position — the key's own
@@ -387,36 +388,35 @@ __global__ void __launch_bounds__(BT_THREADS, 1) attend_bwd_tc_kernel(const Atte
             // every key of this warp sees every query of the block
 #pragma unroll
             for (int c4 = 0; c4 < 32; c4 += 4) {
-              const float4 ls = *reinterpret_cast<const float4 *>(&mq.lse2[c0 + c4]);
-              const float4 dv = *reinterpret_cast<const float4 *>(&mq.dvec[c0 + c4]);
-              const float p0 = fast_exp2(fmaf(__uint_as_float(s[c4 + 0]), ksc_j, -ls.x));
-              const float p1 = fast_exp2(fmaf(__uint_as_float(s[c4 + 1]), ksc_j, -ls.y));
-              const float p2 = fast_exp2(fmaf(__uint_as_float(s[c4 + 2]), ksc_j, -ls.z));
-              const float p3 = fast_exp2(fmaf(__uint_as_float(s[c4 + 3]), ksc_j, -ls.w));
-              const float d0 = p0 * (__uint_as_float(dp[c4 + 0]) - dv.x), d1 = p1 * (__uint_as_float(dp[c4 + 1]) - dv.y);
-              const float d2 = p2 * (__uint_as_float(dp[c4 + 2]) - dv.z), d3 = p3 * (__uint_as_float(dp[c4 + 3]) - dv.w);
-              pk_p[c4 >> 1] = pack_bf16(p0, p1);  pk_p[(c4 >> 1) + 1] = pack_bf16(p2, p3);
-              pk_ds[c4 >> 1] = pack_bf16(d0, d1); pk_ds[(c4 >> 1) + 1] = pack_bf16(d2, d3);
-              s[c4 >> 1] = pack_bf16(d0 * kst_j, d1 * kst_j);
-              s[(c4 >> 1) + 1] = pack_bf16(d2 * kst_j, d3 * kst_j);
+              const ulonglong2 ls = *reinterpret_cast<const ulonglong2 *>(&mq.lse2[c0 + c4]);   // -lse2 pairs
+              const ulonglong2 dv = *reinterpret_cast<const ulonglong2 *>(&mq.dvec[c0 + c4]);   // -D pairs
+              const uint64_t t01 = ffma2(pk2u(s[c4 + 0], s[c4 + 1]), ksc2, ls.x), t23 = ffma2(pk2u(s[c4 + 2], s[c4 + 3]), ksc2, ls.y);
+              const uint64_t p01 = pk2(fast_exp2(lo32(t01)), fast_exp2(hi32(t01))), p23 = pk2(fast_exp2(lo32(t23)), fast_exp2(hi32(t23)));
+              const uint64_t d01 = fmul2(p01, fadd2(pk2u(dp[c4 + 0], dp[c4 + 1]), dv.x));
+              const uint64_t d23 = fmul2(p23, fadd2(pk2u(dp[c4 + 2], dp[c4 + 3]), dv.y));
+              const uint64_t g01 = fmul2(d01, kst2), g23 = fmul2(d23, kst2);
+              pk_p[c4 >> 1] = pack_bf16(lo32(p01), hi32(p01));  pk_p[(c4 >> 1) + 1] = pack_bf16(lo32(p23), hi32(p23));
+              pk_ds[c4 >> 1] = pack_bf16(lo32(d01), hi32(d01)); pk_ds[(c4 >> 1) + 1] = pack_bf16(lo32(d23), hi32(d23));
+              s[c4 >> 1] = pack_bf16(lo32(g01), hi32(g01));
+              s[(c4 >> 1) + 1] = pack_bf16(lo32(g23), hi32(g23));
             }
           } else {
 #pragma unroll
             for (int c4 = 0; c4 < 32; c4 += 4) {
               const float4 qc = *reinterpret_cast<const float4 *>(&mq.qcmp[c0 + c4]);
-              const float4 ls = *reinterpret_cast<const float4 *>(&mq.lse2[c0 + c4]);
-              const float4 dv = *reinterpret_cast<const float4 *>(&mq.dvec[c0 + c4]);
-              const float p0 = ki_j < qc.x ? fast_exp2(fmaf(__uint_as_float(s[c4 + 0]), ksc_j, -ls.x)) : 0.f;
-              const float p1 = ki_j < qc.y ? fast_exp2(fmaf(__uint_as_float(s[c4 + 1]), ksc_j, -ls.y)) : 0.f;
-              const float p2 = ki_j < qc.z ? fast_exp2(fmaf(__uint_as_float(s[c4 + 2]), ksc_j, -ls.z)) : 0.f;
-              const float p3 = ki_j < qc.w ? fast_exp2(fmaf(__uint_as_float(s[c4 + 3]), ksc_j, -ls.w)) : 0.f;
-              const float d0 = p0 * (__uint_as_float(dp[c4 + 0]) - dv.x), d1 = p1 * (__uint_as_float(dp[c4 + 1]) - dv.y);
-              const float d2 = p2 * (__uint_as_float(dp[c4 + 2]) - dv.z), d3 = p3 * (__uint_as_float(dp[c4 + 3]) - dv.w);
-              pk_p[c4 >> 1] = pack_bf16(p0, p1);  pk_p[(c4 >> 1) + 1] = pack_bf16(p2, p3);
-              pk_ds[c4 >> 1] = pack_bf16(d0, d1); pk_ds[(c4 >> 1) + 1] = pack_bf16(d2, d3);
+              const ulonglong2 ls = *reinterpret_cast<const ulonglong2 *>(&mq.lse2[c0 + c4]);   // -lse2 pairs
+              const ulonglong2 dv = *reinterpret_cast<const ulonglong2 *>(&mq.dvec[c0 + c4]);   // -D pairs
+              const uint64_t t01 = ffma2(pk2u(s[c4 + 0], s[c4 + 1]), ksc2, ls.x), t23 = ffma2(pk2u(s[c4 + 2], s[c4 + 3]), ksc2, ls.y);
+              const uint64_t p01 = pk2(fast_exp2(ki_j < qc.x ? lo32(t01) : -INFINITY), fast_exp2(ki_j < qc.y ? hi32(t01) : -INFINITY));
+              const uint64_t p23 = pk2(fast_exp2(ki_j < qc.z ? lo32(t23) : -INFINITY), fast_exp2(ki_j < qc.w ? hi32(t23) : -INFINITY));
+              const uint64_t d01 = fmul2(p01, fadd2(pk2u(dp[c4 + 0], dp[c4 + 1]), dv.x));
+              const uint64_t d23 = fmul2(p23, fadd2(pk2u(dp[c4 + 2], dp[c4 + 3]), dv.y));
+              const uint64_t g01 = fmul2(d01, kst2), g23 = fmul2(d23, kst2);
+              pk_p[c4 >> 1] = pack_bf16(lo32(p01), hi32(p01));  pk_p[(c4 >> 1) + 1] = pack_bf16(lo32(p23), hi32(p23));
+              pk_ds[c4 >> 1] = pack_bf16(lo32(d01), hi32(d01)); pk_ds[(c4 >> 1) + 1] = pack_bf16(lo32(d23), hi32(d23));
               // reuse s[] as the staging copy (dS * key scale) for dQ
-              s[c4 >> 1] = pack_bf16(d0 * kst_j, d1 * kst_j);
-              s[(c4 >> 1) + 1] = pack_bf16(d2 * kst_j, d3 * kst_j);
+              s[c4 >> 1] = pack_bf16(lo32(g01), hi32(g01));
+              s[(c4 >> 1) + 1] = pack_bf16(lo32(g23), hi32(g23));
             }
           }
           tmem_st16(r_st + (cc >> 1), pk_p);

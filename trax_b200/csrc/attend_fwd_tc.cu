@@ -95,24 +95,6 @@ __device__ __forceinline__ uint32_t phase_of(int n) { return static_cast<uint32_
 
 constexpr float kBig = 1e9f * kLog2e, kSelf = 1e5f * kLog2e;   // EA:152-159 masks, log2 domain
 
-__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
-  return static_cast<uint64_t>(__float_as_uint(hi)) << 32 | __float_as_uint(lo);
-}
-__device__ __forceinline__ uint64_t pk2u(uint32_t lo, uint32_t hi) { return static_cast<uint64_t>(hi) << 32 | lo; }
-__device__ __forceinline__ float lo32(uint64_t v) { return __uint_as_float(static_cast<uint32_t>(v)); }
-__device__ __forceinline__ float hi32(uint64_t v) { return __uint_as_float(static_cast<uint32_t>(v >> 32)); }
-// Packed fp32 pairs (FFMA2 / FADD2): same FMA throughput per lane, half the issue slots.
-__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-
 // 32 score columns of one query row, every key visible: t = s * a_i - m_i, p = 2^t, packed to bf16 and stored back
 // over the consumed S columns.  Scale and shift are per-ROW registers: no loads, no compares.
 __device__ __forceinline__ void softmax_block_full(const uint32_t (&r)[32], uint64_t a2, uint64_t mm2, uint32_t t_dst, uint64_t &l2) {

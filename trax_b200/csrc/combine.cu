@@ -130,7 +130,7 @@ int bwd_prep_run(const LshAttnDims &d, const void *do_comb, const void *o_comb, 
   return 0;
 }
 
-// Token-level inputs of the tcgen05 backward kernel: D = do.o, lse2 = log2e*lse_tot and the causal compare value.
+// Token-level inputs of the tcgen05 backward kernel: -D = -(do.o), -lse2 = -log2e*lse_tot and the causal compare value.
 // Rows whose log-sum-exp sits at the "-1e5" level saw only their own key class (EA:153-155): they keep exactly
 // that class (compare against pos + 1.5) and their shift absorbs the 1e5 again.
 __global__ void __launch_bounds__(ROW_THREADS) bwd_prep_tc_kernel(
@@ -157,8 +157,9 @@ __global__ void __launch_bounds__(ROW_THREADS) bwd_prep_tc_kernel(
     const int64_t o = (b * H + h) * L + t;
     const float lse = lse_tot[o];
     const bool self_only = lse < -5e4f;
-    dvec[o] = s;
-    lse2[o] = lse * kLog2e + (self_only ? 1e5f * kLog2e : 0.f);
+    // both are stored NEGATED: the kernel folds them into packed FFMA2 / FADD2 without a sign flip
+    dvec[o] = -s;
+    lse2[o] = -(lse * kLog2e + (self_only ? 1e5f * kLog2e : 0.f));
     qcmp[o] = static_cast<float>(t + 1) + (self_only ? 0.5f : 0.f);
   }
 }

@@ -171,6 +171,30 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ---- packed fp32 pairs ----------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  return static_cast<uint64_t>(__float_as_uint(hi)) << 32 | __float_as_uint(lo);
+}
+__device__ __forceinline__ uint64_t pk2u(uint32_t lo, uint32_t hi) { return static_cast<uint64_t>(hi) << 32 | lo; }
+__device__ __forceinline__ float lo32(uint64_t v) { return __uint_as_float(static_cast<uint32_t>(v)); }
+__device__ __forceinline__ float hi32(uint64_t v) { return __uint_as_float(static_cast<uint32_t>(v >> 32)); }
+// Packed fp32 pairs (FFMA2 / FADD2): same FMA throughput per lane, half the issue slots.
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 // ---- TMEM <-> registers (32 lanes x 32-bit, N consecutive columns; lane = thread) ----------------------
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
