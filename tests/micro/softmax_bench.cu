@@ -5,17 +5,9 @@
 #include "tc_common.cuh"
 using namespace lsh;
 
-__device__ __forceinline__ uint64_t pk2(float lo, float hi) { return (uint64_t)__float_as_uint(hi) << 32 | __float_as_uint(lo); }
-__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
-}
-__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
-  uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
-}
-__device__ __forceinline__ float lo32(uint64_t v) { return __uint_as_float((uint32_t)v); }
-__device__ __forceinline__ float hi32(uint64_t v) { return __uint_as_float((uint32_t)(v >> 32)); }
+// (pk2 / ffma2 / fadd2 / lo32 / hi32 come from tc_common.cuh)
 
-// V0: the kernel's current block (predicated FFMA + MUFU)
+// V0: the round-1 kernel's first block (per-key scale and position loaded from shared memory, predicated FFMA + MUFU)
 __device__ __forceinline__ void block_v0(const uint32_t (&r)[32], const float *kin, const float *ksc, float qi, float m2, uint32_t t_dst, float &l) {
   uint32_t pk[16];
 #pragma unroll
