@@ -256,7 +256,7 @@ def test_make_rotations_statistics_and_determinism():
 
 
 @pytest.mark.parametrize('max_ctas', ['1', '3', '7'])
-@pytest.mark.parametrize('nh,L', [(4, 1024), (1, 2048), (3, 1280)])
+@pytest.mark.parametrize('nh,L', [(4, 1024), (1, 2048), (3, 1280), (1, 384), (3, 384)])   # incl. odd chunk counts (look-back of chunk 0 has the same row order)
 def test_persistent_walk_many_chunks_per_cta(max_ctas, nh, L, monkeypatch):
   """The tcgen05 kernels walk contiguous chunk ranges per CTA (tile ring, carried dQ, unit-boundary replays).  The
   default grid gives small problems one chunk per CTA, so force 1 / 3 / 7 CTAs: every CTA then crosses ring
