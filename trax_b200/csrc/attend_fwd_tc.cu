@@ -16,8 +16,8 @@
 //   warps 0-3, 4-7 two softmax warpgroups, warpgroup p owns part p of EVERY chunk: thread = query row = TMEM lane.
 //                          One pass: t = s * a_i - m_i (per-row scale and shift: q_i·k_j = 8 r_i (qhat_i·qhat_j)), p = exp2(t),
 //                          P (bf16) into its own TMEM buffer; the causal / self masks are an INTERVAL of columns per row
-//                          (position-sorted tiles), so 32-column blocks are skipped, evaluated mask-free, or — around the
-//                          boundary — evaluated with one compare per element.  The score buffer is handed back to the
+//                          (position-sorted tiles): 32-column blocks no row of the warp sees are skipped, the others go
+//                          through one block routine with a per-row visibility bit mask.  The score buffer is handed back to the
 //                          issuer by the pass itself.
 //   warps 8-11 epilogue warpgroup: O (TMEM) * 1/l -> bf16 row -> ticker slot; l = l_part0 + l_part1 through shared memory.
 // The softmax shift m_i is the un-masked self score (it bounds every score of the row, Cauchy-Schwarz with |khat| ~ 1),
@@ -95,30 +95,18 @@ __device__ __forceinline__ uint32_t phase_of(int n) { return static_cast<uint32_
 
 constexpr float kBig = 1e9f * kLog2e, kSelf = 1e5f * kLog2e;   // EA:152-159 masks, log2 domain
 
-// 32 score columns of one query row, every key visible: t = s * a_i - m_i, p = 2^t, packed to bf16 and stored back
-// over the consumed S columns.  Scale and shift are per-ROW registers: no loads, no compares.
-__device__ __forceinline__ void softmax_block_full(const uint32_t (&r)[32], uint64_t a2, uint64_t mm2, uint32_t t_dst, uint64_t &l2) {
+// 32 score columns of one query row: t = s * a_i - m_i, p = 2^t, packed to bf16 into the P buffer.  Scale and shift are
+// per-ROW registers (no loads); bit c of `vis` says whether column c is visible.  ONE code copy serves interior blocks
+// (all ones) and boundary blocks: fewer instructions for the former were measured to be worth less than the
+// instruction-cache footprint of separate variants (A/B on one box: 0.329 vs 0.337 ms per launch + auxiliaries).
+__device__ __forceinline__ void softmax_block_mask(const uint32_t (&r)[32], uint64_t a2, uint64_t mm2, uint32_t vis, uint32_t t_dst,
+                                                   uint64_t &l2) {
   uint32_t pk[16];
 #pragma unroll
   for (int c2 = 0; c2 < 32; c2 += 2) {
     const uint64_t t = ffma2(pk2u(r[c2], r[c2 + 1]), a2, mm2);
-    const float p0 = fast_exp2(lo32(t)), p1 = fast_exp2(hi32(t));
-    l2 = fadd2(l2, pk2(p0, p1));
-    pk[c2 >> 1] = pack_bf16(p0, p1);
-  }
-  tmem_st16(t_dst, pk);
-}
-// Boundary block of the position-sorted scheme: column c of the block is visible iff c < bound (PREFIX, ascending key
-// tile) or c >= bound (suffix, descending key tile) — one compare and one select per element.
-template <bool PREFIX>
-__device__ __forceinline__ void softmax_block_bound(const uint32_t (&r)[32], uint64_t a2, uint64_t mm2, int bound, uint32_t t_dst,
-                                                    uint64_t &l2) {
-  uint32_t pk[16];
-#pragma unroll
-  for (int c2 = 0; c2 < 32; c2 += 2) {
-    const uint64_t t = ffma2(pk2u(r[c2], r[c2 + 1]), a2, mm2);
-    const bool v0 = PREFIX ? (c2 < bound) : (c2 >= bound), v1 = PREFIX ? (c2 + 1 < bound) : (c2 + 1 >= bound);
-    const float p0 = fast_exp2(v0 ? lo32(t) : -INFINITY), p1 = fast_exp2(v1 ? hi32(t) : -INFINITY);
+    const float p0 = fast_exp2((vis & (1u << c2)) ? lo32(t) : -INFINITY);
+    const float p1 = fast_exp2((vis & (2u << c2)) ? hi32(t) : -INFINITY);
     l2 = fadd2(l2, pk2(p0, p1));
     pk[c2 >> 1] = pack_bf16(p0, p1);
   }
@@ -385,9 +373,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
       const float2 am = mq.am[row];                                  // query-side scale a_i, self score m_i (log2 domain)
       const float a_i = am.x;
       float m2 = am.y, lse_off = 0.f;
-      uint32_t need = 0xfu, full = 0u;                               // per 32-column block of my tile (warp-uniform)
+      uint32_t need = 0xfu;                                          // 32-column blocks of my tile any row of this warp sees
       int lo = 0, hi = 128;                                          // visible column interval in my tile
-      bool prefix = true;                                            // interval is [0, hi) (ascending key tile) or [lo, 128)
       if constexpr (sorted) {
         // Both tiles are ordered by position (rank r at row r ^ flip), so "key position < query position" (EA:150-152 and the
         // self mask EA:153-155, whose -1e5 entries underflow to exactly 0 next to any visible key) is an interval of columns.
@@ -410,21 +397,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
             else if (go) bhi = mid;
           }
           const int bound = lonely ? (lb_min == mypos ? 1 : 0) : blo;
-          prefix = flip_lb == 0;
           if (flip_lb) { lo = 128 - bound; hi = 128; } else { lo = 0; hi = bound; }
         } else {
           const int self_incl = lonely ? 1 : 0;
-          prefix = flip_own == 0;
           if (flip_own) { lo = row + 1 - self_incl; hi = 128; } else { lo = 0; hi = row + self_incl; }
         }
-        const int lo_min = __reduce_min_sync(0xffffffffu, lo), lo_max = __reduce_max_sync(0xffffffffu, lo);
-        const int hi_min = __reduce_min_sync(0xffffffffu, hi), hi_max = __reduce_max_sync(0xffffffffu, hi);
+        const int lo_min = __reduce_min_sync(0xffffffffu, lo), hi_max = __reduce_max_sync(0xffffffffu, hi);
         need = 0u;
 #pragma unroll
         for (int bq = 0; bq < 4; ++bq) {
           const int c0 = 32 * bq, c1 = c0 + 32;
           if (!(hi_max <= c0 || lo_min >= c1)) need |= 1u << bq;
-          if (lo_max <= c0 && hi_min >= c1) full |= 1u << bq;
         }
       } else {
         const float own_ki = mq.kinfo[row];
@@ -442,16 +425,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
       if (warp == 0 && lane == 0) TC_TRACE(wk.k, 2);
       if (warp == 4 && lane == 0) TC_TRACE(wk.k, 13);
       long long *tr2 = (TC_TRACE_ON && p.trace && blockIdx.x == 0 && wk.k < 120 && wg == 0) ? p.trace + 120 * 16 + 148 + wk.k * 12 + (warp & 3) * 3 : nullptr;
-      if (tr2 && lane == 0) { tr2[0] = clock64(); tr2[2] = __popc(need) * 16 + __popc(full); }
+      if (tr2 && lane == 0) { tr2[0] = clock64(); tr2[2] = __popc(need) * 16; }
       float l = 0.f;
       uint64_t l2 = 0ull;
       uint32_t ra[32], rb[32];
       // Loads run one needed block ahead; skipped blocks get zeros.
       auto process = [&](const uint32_t (&r)[32], int bq) {
         if constexpr (sorted) {
-          if ((full >> bq) & 1u) softmax_block_full(r, a2, mm2, t_p + bq * 16, l2);
-          else if (prefix) softmax_block_bound<true>(r, a2, mm2, hi - bq * 32, t_p + bq * 16, l2);
-          else softmax_block_bound<false>(r, a2, mm2, lo - bq * 32, t_p + bq * 16, l2);
+          const int lr = lo - bq * 32, hr = hi - bq * 32;     // my visible interval [lo, hi) relative to the block
+          const uint32_t below_hi = hr >= 32 ? 0xffffffffu : (hr <= 0 ? 0u : ((1u << hr) - 1u));
+          const uint32_t below_lo = lr >= 32 ? 0xffffffffu : (lr <= 0 ? 0u : ((1u << lr) - 1u));
+          softmax_block_mask(r, a2, mm2, below_hi & ~below_lo, t_p + bq * 16, l2);
         } else {
           softmax_block_generic(r, mk.kinfo + bq * 32, qi, a_i, m2, p.causal, p.masked, t_p + bq * 16, l);
         }
