@@ -14,9 +14,9 @@
 
 namespace lsh {
 
-constexpr int SORT_THREADS = 256;
+constexpr int SORT_THREADS = 512;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
-constexpr int SORT_TILE = 2048;                       // positions per CTA
+constexpr int SORT_TILE = 4096;                       // positions per CTA
 constexpr int SORT_PER_WARP = SORT_TILE / SORT_WARPS; // contiguous positions per warp
 constexpr int SORT_MAX_BITS = 11;
 
@@ -166,14 +166,19 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_scatter_kernel(const SortPa
   __syncthreads();
   int *my_cnt = s_cnt + warp * p.n_digits;
   const int wbase = tile * SORT_TILE + warp * SORT_PER_WARP;
-  // phase A: per-warp digit counts
-  for (int i = lane; i < SORT_PER_WARP; i += 32) {
-    int idx = wbase + i;
-    if (idx < p.L) {
-      int pos;
-      atomicAdd(&my_cnt[sort_digit(p, u, round, idx, pos)], 1);
-    }
+  // phase A: per-warp digit counts.  The digits (one dependent global load each) are fetched ONCE, all in flight
+  // together, and kept in registers for phase C — its counter chain would otherwise serialise eight load latencies.
+  constexpr int PER_LANE = SORT_PER_WARP / 32;
+  int dg[PER_LANE], ps[PER_LANE];
+#pragma unroll
+  for (int k = 0; k < PER_LANE; ++k) {
+    const int idx = wbase + k * 32 + lane;
+    ps[k] = 0;
+    dg[k] = (idx < p.L) ? sort_digit(p, u, round, idx, ps[k]) : -1;
   }
+#pragma unroll
+  for (int k = 0; k < PER_LANE; ++k)
+    if (dg[k] >= 0) atomicAdd(&my_cnt[dg[k]], 1);
   __syncthreads();
   // phase B: counts -> starting offsets (tile base from the scanned histogram, then warps in order)
   const int32_t *hs = p.hist + static_cast<int64_t>(seg) * p.n_digits * p.n_tiles;
@@ -189,11 +194,11 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_scatter_kernel(const SortPa
   __syncthreads();
   // phase C: stable scatter, 32 elements of the warp's range at a time, in order
   const int64_t row = static_cast<int64_t>(u) * p.N + static_cast<int64_t>(round) * p.L;
-  for (int i0 = 0; i0 < SORT_PER_WARP; i0 += 32) {
-    const int idx = wbase + i0 + lane;
-    const bool valid = idx < p.L;
-    int pos = 0;
-    unsigned dgt = valid ? static_cast<unsigned>(sort_digit(p, u, round, idx, pos)) : 0xffffffffu;
+#pragma unroll
+  for (int k = 0; k < PER_LANE; ++k) {
+    const bool valid = dg[k] >= 0;
+    const int pos = ps[k];
+    const unsigned dgt = static_cast<unsigned>(dg[k]);   // 0xffffffff for lanes past the end
     const unsigned peers = __match_any_sync(0xffffffffu, dgt);
     const int rank = __popc(peers & ((1u << lane) - 1u));
     int off = 0;
