@@ -54,6 +54,9 @@ static int check_dims(const LshAttnDims *dp, bool need_bwd) {
   if (!dp) return set_error("dims == NULL");
   const LshAttnDims &d = *dp;
   if (d.B < 1 || d.H < 1 || d.L < 1 || d.D < 1) return set_error("B, H, L, D must be >= 1");
+  if (static_cast<int64_t>(d.B) * d.H * d.L * (d.nh > 0 ? d.nh : 1) >= (1ll << 31))
+    return set_error("B*H*n_hashes*seqlen = %lld does not fit 31 bits (row indices of the per-token kernels)",
+                     static_cast<long long>(d.B) * d.H * d.L * d.nh);
   if (d.dq != 64 || d.dv != 64)
     return set_error("unsupported head size d_qk=%d d_v=%d: the sm_100a kernels are specialised for 64/64", d.dq, d.dv);
   if (d.C != 32 && d.C != 64 && d.C != 128 && d.C != 256)

@@ -28,9 +28,9 @@ __global__ void __launch_bounds__(ROW_THREADS) combine_fwd_kernel(
   const int64_t row = (static_cast<int64_t>(blockIdx.x) * ROW_THREADS + threadIdx.x) >> 3;   // (u, t)
   const int ch = threadIdx.x & 7;
   if (row >= total_rows) return;
-  const int64_t u = row / L;
+  const int64_t u = static_cast<uint32_t>(row) / static_cast<uint32_t>(L);   // rows < 2^31 (checked on the host): 32-bit divide
   const int t = static_cast<int>(row - u * L);
-  const int64_t b = u / H, h = u % H;
+  const int64_t b = static_cast<uint32_t>(u) / static_cast<uint32_t>(H), h = u - b * H;
   const float *lg = logits + u * nh * L + t;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   float lse;
@@ -50,12 +50,13 @@ __global__ void __launch_bounds__(ROW_THREADS) combine_fwd_kernel(
     for (int r = 0; r < 8; ++r) if (r < nh) mx = fmaxf(mx, lgv[r]);
     float den = 0.f;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) if (r < nh) den += expf(lgv[r] - mx);
-    lse = mx + logf(den);                                             // logsumexp over rounds (EA:1991)
+    for (int r = 0; r < 8; ++r) if (r < nh) den += __expf(lgv[r] - mx);
+    lse = mx + __logf(den);                                           // logsumexp over rounds (EA:1991); MUFU-based
+                                                                      // exp / log (2 ulp): the kernel is issue-bound
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       if (r < nh) {
-        const float w = expf(lgv[r] - lse);
+        const float w = __expf(lgv[r] - lse);
         float f[8];
         bf16x8_to_f32(ov[r], f);
 #pragma unroll
@@ -112,8 +113,9 @@ __global__ void __launch_bounds__(ROW_THREADS) bwd_prep_kernel(
   s += __shfl_xor_sync(0xffffffffu, s, 2);
   s += __shfl_xor_sync(0xffffffffu, s, 4);
   if (ok && ch == 0) {
-    const int64_t h = row % H, bt = row / H;
-    const int64_t b = bt / L, t = bt % L;
+    const uint32_t bt32 = static_cast<uint32_t>(row) / static_cast<uint32_t>(H);
+    const int64_t h = static_cast<uint32_t>(row) - bt32 * static_cast<uint32_t>(H), bt = bt32;
+    const int64_t b = static_cast<uint32_t>(bt) / static_cast<uint32_t>(L), t = bt - b * L;
     dvec[(b * H + h) * L + t] = s;
   }
 }
@@ -152,8 +154,9 @@ __global__ void __launch_bounds__(ROW_THREADS) bwd_prep_tc_kernel(
   s += __shfl_xor_sync(0xffffffffu, s, 2);
   s += __shfl_xor_sync(0xffffffffu, s, 4);
   if (ok && ch == 0) {
-    const int64_t h = row % H, bt = row / H;
-    const int64_t b = bt / L, t = bt % L;
+    const uint32_t bt32 = static_cast<uint32_t>(row) / static_cast<uint32_t>(H);
+    const int64_t h = static_cast<uint32_t>(row) - bt32 * static_cast<uint32_t>(H), bt = bt32;
+    const int64_t b = static_cast<uint32_t>(bt) / static_cast<uint32_t>(L), t = bt - b * L;
     const int64_t o = (b * H + h) * L + t;
     const float lse = lse_tot[o];
     const bool self_only = lse < -5e4f;
@@ -191,8 +194,8 @@ __global__ void __launch_bounds__(ROW_THREADS) qscale_kernel(const __nv_bfloat16
   const int64_t ut = (static_cast<int64_t>(blockIdx.x) * ROW_THREADS + threadIdx.x) >> 3;    // (u, t)
   const int ch = threadIdx.x & 7;
   const bool ok = ut < total_rows;
-  const int64_t u = ut / L, t = ut - u * L;
-  const int64_t b = u / H, h = u - b * H;
+  const int64_t u = static_cast<uint32_t>(ut) / static_cast<uint32_t>(L), t = ut - u * L;
+  const int64_t b = static_cast<uint32_t>(u) / static_cast<uint32_t>(H), h = u - b * H;
   const int64_t row = (b * L + t) * H + h;                                                      // row of qv
   float s = 0.f;
   float a[8];
@@ -248,9 +251,9 @@ __global__ void __launch_bounds__(ROW_THREADS) sum_rounds_kernel(
   const int64_t row = (static_cast<int64_t>(blockIdx.x) * ROW_THREADS + threadIdx.x) >> 3;   // (u, t)
   const int ch = threadIdx.x & 7;
   if (row >= total_rows) return;
-  const int64_t u = row / L;
+  const int64_t u = static_cast<uint32_t>(row) / static_cast<uint32_t>(L);   // rows < 2^31 (checked on the host): 32-bit divide
   const int t = static_cast<int>(row - u * L);
-  const int64_t b = u / H, h = u % H;
+  const int64_t b = static_cast<uint32_t>(u) / static_cast<uint32_t>(H), h = u - b * H;
   float aq[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, av[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int r = 0; r < nh; ++r) {
     const int64_t off = ((u * nh + r) * L + t) * 64;
