@@ -255,17 +255,42 @@ __global__ void __launch_bounds__(ROW_THREADS) sum_rounds_kernel(
   const int t = static_cast<int>(row - u * L);
   const int64_t b = static_cast<uint32_t>(u) / static_cast<uint32_t>(H), h = u - b * H;
   float aq[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, av[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int r = 0; r < nh; ++r) {
-    const int64_t off = ((u * nh + r) * L + t) * 64;
-    float f[8];
-    for (int k = 0; k < n_kinds; ++k) {
-      bf16x8_to_f32(__ldg(reinterpret_cast<const uint4 *>(dq_part + k * kind_stride + off) + ch), f);
+  if (n_kinds == 1 && nh <= 8) {
+    // tcgen05 path: one dq and one dv row per round — all 2 * nh loads of the token in flight at once
+    uint4 vq[8], vv[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) aq[i] += f[i];
+    for (int r = 0; r < 8; ++r) {
+      if (r < nh) {
+        const int64_t off = ((u * nh + r) * L + t) * 64;
+        vq[r] = __ldg(reinterpret_cast<const uint4 *>(dq_part + off) + ch);
+        vv[r] = __ldg(reinterpret_cast<const uint4 *>(dv_part + off) + ch);
+      }
     }
-    bf16x8_to_f32(__ldg(reinterpret_cast<const uint4 *>(dv_part + off) + ch), f);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) av[i] += f[i];
+    for (int r = 0; r < 8; ++r) {
+      if (r < nh) {
+        float f[8];
+        bf16x8_to_f32(vq[r], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) aq[i] += f[i];
+        bf16x8_to_f32(vv[r], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) av[i] += f[i];
+      }
+    }
+  } else {
+    for (int r = 0; r < nh; ++r) {
+      const int64_t off = ((u * nh + r) * L + t) * 64;
+      float f[8];
+      for (int k = 0; k < n_kinds; ++k) {
+        bf16x8_to_f32(__ldg(reinterpret_cast<const uint4 *>(dq_part + k * kind_stride + off) + ch), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) aq[i] += f[i];
+      }
+      bf16x8_to_f32(__ldg(reinterpret_cast<const uint4 *>(dv_part + off) + ch), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) av[i] += f[i];
+    }
   }
   __nv_bfloat16 *dst = dqv + ((b * L + t) * H + h) * 128;
   *(reinterpret_cast<uint4 *>(dst) + ch) = f32_to_bf16x8(aq);
