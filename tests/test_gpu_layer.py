@@ -276,3 +276,16 @@ def test_async_host_io_matches_sync():
       torch.testing.assert_close(a, b, rtol=0, atol=0)
   h2d, d2h = trax_b200.host_io_bytes(reset=True)
   assert h2d > 0 and d2h > 0
+
+
+def test_hashing_call_and_recompute_agree_bitwise():
+  """A forward call that hashes takes the per-token scales / normalised keys from the hash kernel; a call that re-uses
+  the buckets (the backward's recompute) takes them from qscale_kernel.  Same operation order => the same output bits."""
+  import trax_b200
+  cfg = util.make_cfg(H=4, C=128, nh=4, n_buckets=None)
+  layer = _layer(cfg)
+  layer.init(trax_b200.ShapeDtype((2, 1024, 256)))
+  x = torch.randn(2, 1024, 256, device='cuda', generator=torch.Generator('cuda').manual_seed(5)).bfloat16()
+  out1 = layer.forward(x)                                                               # update_state=True
+  out2 = layer.forward_and_or_backward(x, layer.weights, layer.state, None, update_state=False)[0]
+  assert torch.equal(out1, out2)

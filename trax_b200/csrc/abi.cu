@@ -31,6 +31,9 @@ extern long long *g_fwd_trace;   // attend_fwd.cu (debug trace buffer)
 // ---- kernels implemented in the other translation units --------------------------------------------
 int hash_bf16_qv(const LshAttnDims &, const void *, const float *, const uint8_t *, int32_t *, int64_t, cudaStream_t);
 int hash_f32_vecs(const LshAttnDims &, const float *, const float *, const uint8_t *, int32_t *, int64_t, cudaStream_t);
+bool hash_can_fuse_aux(const LshAttnDims &);
+int hash_bf16_qv_aux(const LshAttnDims &, const void *, const float *, const uint8_t *, int32_t *, int64_t, float *, float2 *, void *,
+                     cudaStream_t);
 size_t sort_workspace_bytes(const LshAttnDims &);
 int sort_run(const LshAttnDims &, const int32_t *, int64_t, int32_t *, int32_t *, void *, size_t, cudaStream_t);
 int attend_fwd_run(const LshAttnDims &, const void *, const int32_t *, const uint8_t *, void *, int64_t, int64_t,
@@ -176,11 +179,17 @@ static int forward_core(const LshAttnDims &d, const LayerWs &w, const void *x, c
   if ((rc = pack_weights_run(d, w_q, w_v, w_o, w.wqv, w.wo, s))) return rc;
   const int64_t NQV = static_cast<int64_t>(d.H) * dr.QV;
   if ((rc = gemm_rm(false, false, BL, NQV, d.D, xb, d.D, w.wqv, NQV, w.qv, NQV, false, w.cublas, s))) return rc;
+  bool scales_done = false;
   if (rotations) {
-    if ((rc = hash_bf16_qv(d, w.qv, rotations, mask, buckets, bstride, s))) return rc;
+    if (attend_fwd_uses_tc(d) && hash_can_fuse_aux(d)) {
+      if ((rc = hash_bf16_qv_aux(d, w.qv, rotations, mask, buckets, bstride, w.aux.qscale, w.aux.rowmeta, w.aux.qhat, s))) return rc;
+      scales_done = true;
+    } else if ((rc = hash_bf16_qv(d, w.qv, rotations, mask, buckets, bstride, s))) {
+      return rc;
+    }
   }
   if ((rc = sort_run(d, buckets, bstride, w.sticker, nullptr, w.sort_ws, w.sort_bytes, s))) return rc;
-  if ((rc = fwd_aux_prepare(d, w.qv, w.sticker, w.aux, s))) return rc;
+  if ((rc = fwd_aux_prepare(d, w.qv, w.sticker, w.aux, s, scales_done))) return rc;
   if (d.nh > 1) {
     if ((rc = attend_fwd_run(d, w.qv, w.sticker, mask, w.o_rounds, static_cast<int64_t>(d.H) * dr.N * 64,
                              static_cast<int64_t>(dr.N) * 64, static_cast<int64_t>(d.L) * 64, 64, w.logits, &w.aux, s)))

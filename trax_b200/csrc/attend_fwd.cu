@@ -238,9 +238,12 @@ FwdAux fwd_aux_carve(const LshAttnDims &d, void *ws) {
 }
 // Everything the attention kernels need besides qv and sticker: per-token scales (always: the backward kernel reads
 // qscale), and for the tcgen05 forward path the normalised keys and the position-sorted chunks.
-int fwd_aux_prepare(const LshAttnDims &d, const void *qv, const int32_t *sticker, const FwdAux &aux, cudaStream_t stream) {
+int fwd_aux_prepare(const LshAttnDims &d, const void *qv, const int32_t *sticker, const FwdAux &aux, cudaStream_t stream,
+                    bool scales_done) {
   const bool tc = attend_fwd_uses_tc(d);
-  if (int rc = qscale_run(d, qv, aux.qscale, tc ? aux.rowmeta : nullptr, tc ? aux.qhat : nullptr, stream)) return rc;
+  if (!scales_done) {     // (a forward call that hashes gets them from the hash kernel, which already holds q)
+    if (int rc = qscale_run(d, qv, aux.qscale, tc ? aux.rowmeta : nullptr, tc ? aux.qhat : nullptr, stream)) return rc;
+  }
   if (tc && sticker) return chunk_possort_run(d, sticker, aux.sticker2, stream);
   return 0;
 }

@@ -31,6 +31,7 @@ struct FwdAux {
 bool attend_fwd_uses_tc(const LshAttnDims &d);
 size_t fwd_aux_bytes(const LshAttnDims &d);
 FwdAux fwd_aux_carve(const LshAttnDims &d, void *ws);
-int fwd_aux_prepare(const LshAttnDims &d, const void *qv, const int32_t *sticker, const FwdAux &aux, cudaStream_t stream);
+int fwd_aux_prepare(const LshAttnDims &d, const void *qv, const int32_t *sticker, const FwdAux &aux, cudaStream_t stream,
+                    bool scales_done = false);
 
 }  // namespace lsh

@@ -14,6 +14,14 @@ namespace lsh {
 constexpr int HASH_THREADS = 128;
 constexpr int HASH_COLS = 8;   // rotation columns processed together per thread
 
+// Optional per-token by-products of the hash kernel (it already holds q in registers): exactly what qscale_kernel
+// (combine.cu) writes, in the same operation order, so a forward call with hashing skips that kernel.
+struct HashAux {
+  float *qscale;            // (BH, L)      or null
+  float2 *rowmeta;          // (BH, L)      or null
+  __nv_bfloat16 *qhat;      // (BH, L, 64)  or null
+};
+
 struct HashParams {
   const void *vecs;        // bf16 or f32
   int64_t stride_b, stride_h, stride_t;   // element strides of vecs for (example, head, token)
@@ -139,7 +147,7 @@ template <typename T, int TC, int NT>
 #ifndef LSH_HASH_MINB
 #define LSH_HASH_MINB 2
 #endif
-__global__ void __launch_bounds__(HASH_THREADS, NT == 1 ? 4 : LSH_HASH_MINB) hash_all_rounds_kernel(const HashParams p, float *__restrict__ qscale) {
+__global__ void __launch_bounds__(HASH_THREADS, NT == 1 ? 4 : LSH_HASH_MINB) hash_all_rounds_kernel(const HashParams p, const HashAux aux) {
   constexpr int DQ = 64;
   extern __shared__ __align__(16) float s_rot[];   // [DQ][TC], column = round * Rpad + c
   const int u = blockIdx.y;
@@ -169,11 +177,39 @@ __global__ void __launch_bounds__(HASH_THREADS, NT == 1 ? 4 : LSH_HASH_MINB) has
 #pragma unroll
       for (int i = 0; i < DQ; ++i) q[k][i] = 0.f;
     }
-    if (qscale != nullptr && active[k]) {
-      float ss = 0.f;
+    if (aux.qscale != nullptr && active[k]) {
+      // sum of squares in qscale_kernel's order: eight 8-element fmaf chains, then the xor-shuffle tree of lane 0
+      auto tree_sumsq = [](const float (&v)[DQ]) {
+        float part[8];
 #pragma unroll
-      for (int i = 0; i < DQ; ++i) ss = fmaf(q[k][i], q[k][i], ss);
-      qscale[static_cast<int64_t>(u) * p.L + t[k]] = 0.125f * kLog2e / sqrtf(ss * (1.0f / 64) + 1e-6f);
+        for (int c8 = 0; c8 < 8; ++c8) {
+          float acc = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc = fmaf(v[8 * c8 + i], v[8 * c8 + i], acc);
+          part[c8] = acc;
+        }
+        return ((part[0] + part[1]) + (part[2] + part[3])) + ((part[4] + part[5]) + (part[6] + part[7]));
+      };
+      const float r = sqrtf(tree_sumsq(q[k]) * (1.0f / 64) + 1e-6f);
+      const int64_t ut = static_cast<int64_t>(u) * p.L + t[k];
+      aux.qscale[ut] = 0.125f * kLog2e / r;
+      if (aux.qhat != nullptr) {
+        const float c = 0.125f / r;
+        float qh[DQ];
+        uint4 *dst = reinterpret_cast<uint4 *>(aux.qhat + ut * 64);
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {
+          uint4 pk;
+          pk.x = pack_bf16(q[k][8 * c8 + 0] * c, q[k][8 * c8 + 1] * c); pk.y = pack_bf16(q[k][8 * c8 + 2] * c, q[k][8 * c8 + 3] * c);
+          pk.z = pack_bf16(q[k][8 * c8 + 4] * c, q[k][8 * c8 + 5] * c); pk.w = pack_bf16(q[k][8 * c8 + 6] * c, q[k][8 * c8 + 7] * c);
+          dst[c8] = pk;
+          const float2 a2 = unpack_bf16(pk.x), b2 = unpack_bf16(pk.y), c2 = unpack_bf16(pk.z), d2 = unpack_bf16(pk.w);
+          qh[8 * c8 + 0] = a2.x; qh[8 * c8 + 1] = a2.y; qh[8 * c8 + 2] = b2.x; qh[8 * c8 + 3] = b2.y;
+          qh[8 * c8 + 4] = c2.x; qh[8 * c8 + 5] = c2.y; qh[8 * c8 + 6] = d2.x; qh[8 * c8 + 7] = d2.y;
+        }
+        const float am = 8.f * r * kLog2e;
+        aux.rowmeta[ut] = make_float2(am, am * tree_sumsq(qh));
+      }
     }
   }
   for (int round = 0; round < p.nh; ++round) {
@@ -238,18 +274,18 @@ __global__ void __launch_bounds__(HASH_THREADS, NT == 1 ? 4 : LSH_HASH_MINB) has
 }
 
 template <typename T, int TC>
-static int launch_hash_fast(const HashParams &p, int BH, float *qscale, cudaStream_t stream) {
+static int launch_hash_fast(const HashParams &p, int BH, const HashAux &aux, cudaStream_t stream) {
   // two tokens per thread when there are enough CTAs to fill the machine twice over
   const int64_t ctas2 = static_cast<int64_t>((p.L + 2 * HASH_THREADS - 1) / (2 * HASH_THREADS)) * BH;
   if (ctas2 >= 2 * 148) {
     LSH_OPT_IN_SMEM((hash_all_rounds_kernel<T, TC, 2>));
     const int groups = (p.L + 2 * HASH_THREADS - 1) / (2 * HASH_THREADS), per_unit = (LSH_HASH_MINB * 148 + BH - 1) / BH;
     dim3 grid(groups < per_unit ? groups : per_unit, BH);      // LSH_HASH_MINB resident CTAs per SM, one wave
-    hash_all_rounds_kernel<T, TC, 2><<<grid, HASH_THREADS, 64 * TC * sizeof(float), stream>>>(p, qscale);
+    hash_all_rounds_kernel<T, TC, 2><<<grid, HASH_THREADS, 64 * TC * sizeof(float), stream>>>(p, aux);
   } else {
     LSH_OPT_IN_SMEM((hash_all_rounds_kernel<T, TC, 1>));
     dim3 grid((p.L + HASH_THREADS - 1) / HASH_THREADS, BH);
-    hash_all_rounds_kernel<T, TC, 1><<<grid, HASH_THREADS, 64 * TC * sizeof(float), stream>>>(p, qscale);
+    hash_all_rounds_kernel<T, TC, 1><<<grid, HASH_THREADS, 64 * TC * sizeof(float), stream>>>(p, aux);
   }
   LSH_CHECK_LAUNCH("hash_all_rounds_kernel");
   return 0;
@@ -258,7 +294,7 @@ static int launch_hash_fast(const HashParams &p, int BH, float *qscale, cudaStre
 template <typename T>
 static int launch_hash(const LshAttnDims &d, const void *vecs, int64_t sb, int64_t sh, int64_t st,
                        const float *rot, const uint8_t *mask, int32_t *buckets, int64_t bstride,
-                       float *qscale, cudaStream_t stream) {
+                       const HashAux &aux, cudaStream_t stream) {
   Derived dr = derive(d);
   HashParams p;
   p.vecs = vecs; p.stride_b = sb; p.stride_h = sh; p.stride_t = st;
@@ -270,15 +306,15 @@ static int launch_hash(const LshAttnDims &d, const void *vecs, int64_t sb, int64
   if (smem > 200 * 1024) return set_error("lsh_hash: sum(factors)/2 = %d too large for shared memory", dr.R);
   if (d.masked && mask == nullptr) return set_error("lsh_hash: dims.masked set but mask == NULL");
   switch (d.nh * p.Rpad) {          // all rounds resident, compile-time stride
-    case 16: return launch_hash_fast<T, 16>(p, dr.BH, qscale, stream);
-    case 32: return launch_hash_fast<T, 32>(p, dr.BH, qscale, stream);
-    case 64: return launch_hash_fast<T, 64>(p, dr.BH, qscale, stream);
-    case 128: return launch_hash_fast<T, 128>(p, dr.BH, qscale, stream);
-    case 192: return launch_hash_fast<T, 192>(p, dr.BH, qscale, stream);
-    case 256: return launch_hash_fast<T, 256>(p, dr.BH, qscale, stream);
+    case 16: return launch_hash_fast<T, 16>(p, dr.BH, aux, stream);
+    case 32: return launch_hash_fast<T, 32>(p, dr.BH, aux, stream);
+    case 64: return launch_hash_fast<T, 64>(p, dr.BH, aux, stream);
+    case 128: return launch_hash_fast<T, 128>(p, dr.BH, aux, stream);
+    case 192: return launch_hash_fast<T, 192>(p, dr.BH, aux, stream);
+    case 256: return launch_hash_fast<T, 256>(p, dr.BH, aux, stream);
     default: break;
   }
-  if (qscale != nullptr) return set_error("lsh_hash: fused qscale needs a specialised column count (got %d)", d.nh * p.Rpad);
+  if (aux.qscale != nullptr) return set_error("lsh_hash: fused qscale needs a specialised column count (got %d)", d.nh * p.Rpad);
   LSH_OPT_IN_SMEM(hash_kernel<T>);
   dim3 grid((d.L + HASH_THREADS - 1) / HASH_THREADS, dr.BH);
   hash_kernel<T><<<grid, HASH_THREADS, smem, stream>>>(p);
@@ -291,14 +327,28 @@ int hash_bf16_qv(const LshAttnDims &d, const void *qv, const float *rot, const u
   Derived dr = derive(d);
   return launch_hash<__nv_bfloat16>(d, qv, static_cast<int64_t>(d.L) * d.H * dr.QV, dr.QV,
                                     static_cast<int64_t>(d.H) * dr.QV, rot, mask, buckets, bstride,
-                                    nullptr, stream);
+                                    HashAux{nullptr, nullptr, nullptr}, stream);
+}
+
+// Hash + the per-token by-products of qscale_kernel in one pass over q (specialised column counts only).
+bool hash_can_fuse_aux(const LshAttnDims &d) {
+  Derived dr = derive(d);
+  const int tc = d.nh * ((dr.R + HASH_COLS - 1) / HASH_COLS * HASH_COLS);
+  return tc == 16 || tc == 32 || tc == 64 || tc == 128 || tc == 192 || tc == 256;
+}
+int hash_bf16_qv_aux(const LshAttnDims &d, const void *qv, const float *rot, const uint8_t *mask, int32_t *buckets,
+                     int64_t bstride, float *qscale, float2 *rowmeta, void *qhat, cudaStream_t stream) {
+  Derived dr = derive(d);
+  return launch_hash<__nv_bfloat16>(d, qv, static_cast<int64_t>(d.L) * d.H * dr.QV, dr.QV,
+                                    static_cast<int64_t>(d.H) * dr.QV, rot, mask, buckets, bstride,
+                                    HashAux{qscale, rowmeta, static_cast<__nv_bfloat16 *>(qhat)}, stream);
 }
 
 int hash_f32_vecs(const LshAttnDims &d, const float *vecs, const float *rot, const uint8_t *mask,
                   int32_t *buckets, int64_t bstride, cudaStream_t stream) {
   return launch_hash<float>(d, vecs, static_cast<int64_t>(d.H) * d.L * d.dq,
                             static_cast<int64_t>(d.L) * d.dq, d.dq, rot, mask, buckets, bstride,
-                            nullptr, stream);
+                            HashAux{nullptr, nullptr, nullptr}, stream);
 }
 
 }  // namespace lsh
