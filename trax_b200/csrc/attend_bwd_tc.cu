@@ -133,7 +133,8 @@ __global__ void __launch_bounds__(BT_THREADS, 1) attend_bwd_tc_kernel(const Atte
 
   if (warp == 14) tmem_alloc(&sh.tmem_base, 512);
   if (tid == 0) {
-    for (int i = 0; i < BT_NST; ++i) { mbar_init(&sh.full[i], 64); mbar_init(&sh.empty[i], 385); }
+    // full: per producer thread one arrival by its copies (noinc) and one ordinary arrival releasing its metadata stores
+    for (int i = 0; i < BT_NST; ++i) { mbar_init(&sh.full[i], 128); mbar_init(&sh.empty[i], 385); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sh.st_full[i], 1); mbar_init(&sh.pds_full[i], 128);
       mbar_init(&sh.dsm_free[i], 1); mbar_init(&sh.dq_full[i], 1);
@@ -205,6 +206,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) attend_bwd_tc_kernel(const Atte
       // Completion is signalled by the copies themselves (cp.async.mbarrier.arrive.noinc): the producer never waits for
       // its own loads, and the tile becomes visible the moment it has landed.
       cp_async_mbar_arrive_noinc(&sh.full[slot]);
+      mbar_arrive(&sh.full[slot]);                         // (release of the plain kinfo / tk stores above)
     };
     for (BtWalk w(g0, g1, p.n_chunks); w.valid();) {
       const BtItem it = w.item();

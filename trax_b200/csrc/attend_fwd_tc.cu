@@ -155,12 +155,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
 
   if (warp == 14) tmem_alloc(&sh.tmem_base, 512);
   if (tid == 0) {
-    for (int i = 0; i < TC_NST; ++i) { mbar_init(&sh.full[i], 64); mbar_init(&sh.empty[i], 1); }
+    // full: per producer thread one arrival by its copies (cp.async ... noinc) and one ordinary arrival that releases its
+    // plain metadata stores
+    for (int i = 0; i < TC_NST; ++i) { mbar_init(&sh.full[i], 128); mbar_init(&sh.empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sh.s_full[i], 1); mbar_init(&sh.p_free[i], 1);     // tcgen05.commit arrivals
       mbar_init(&sh.s_free[i], 4); mbar_init(&sh.p_full[i], 4);     // one arrival per softmax warp of the part's warpgroup
       mbar_init(&sh.o_full[i], 1); mbar_init(&sh.o_free[i], 4);     // one arrival per epilogue warp
-      mbar_init(&sh.l_full[i], 8);                                   // one arrival per softmax warp (both warpgroups)
+      mbar_init(&sh.l_full[i], 256);                                 // every softmax thread releases its own row statistics
     }
     fence_mbar_init();
   }
@@ -253,8 +255,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
         }
       }
       // Completion is signalled by the copies themselves (no wait here): every free ring slot is a tile in flight.
-      // The metadata stores above precede the copies in program order and are long done when the last copy lands.
+      // The ordinary arrival (release) publishes this thread's plain metadata stores.
       cp_async_mbar_arrive_noinc(&sh.full[slot]);
+      mbar_arrive(&sh.full[slot]);
     };
     TileReq r0, r1, r2;
     request(r0); request(r1); request(r2);
@@ -495,7 +498,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) { mbar_arrive(&sh.p_full[wg]); mbar_arrive(&sh.l_full[ob]); }
+      mbar_arrive(&sh.l_full[ob]);
+      if (lane == 0) mbar_arrive(&sh.p_full[wg]);
       if (TC_TRACE_ON && lane == 0 && p.trace && blockIdx.x == 0 && wk.k < 120) atomicMax(reinterpret_cast<unsigned long long *>(p.trace) + wk.k * 16 + 3, static_cast<unsigned long long>(clock64()));
     }
   } else if (warp >= 8 && warp < 12) {
