@@ -158,7 +158,8 @@ int lsh_layer_fwd(const LshAttnDims *dims, const void *x, const float *w_q, cons
  * backward.  `out` may be NULL (compute_output=False, EA:2256-2258) or a buffer
  * (compute_output=True, the call ReversibleHalfResidual makes, reversible.py:374-378).
  * dw_q/dw_v/dw_o are fully overwritten with the sum over examples (EA:2431); dx (B,L,D) with the
- * sum over heads (EA:2430). */
+ * sum over heads (EA:2430).  Work is ordered on `stream`; one GEMM (do = dout·w_o^T) runs on an internal
+ * helper stream that is forked from and joined back into `stream` by events (no host wait, capture-safe). */
 int lsh_layer_bwd(const LshAttnDims *dims, const void *x, const float *w_q, const float *w_v,
                   const float *w_o, const uint8_t *mask, const int32_t *buckets,
                   int64_t buckets_stride, const void *dout, void *out, void *dx, float *dw_q,

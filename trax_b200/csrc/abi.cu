@@ -113,6 +113,28 @@ static int gemm_rm(bool ta, bool tb, int64_t M, int64_t N, int64_t K, const void
   return 0;
 }
 
+// ---- side stream of lsh_layer_bwd -----------------------------------------------------------------------
+// do = dout·w_o^T depends only on the packed weights and on dout, not on the forward recompute: it runs on an internal
+// stream (fork / join by events, no host wait; legal inside a stream capture) beside the recompute's latency-bound
+// kernels (qscale, sort, position sort), which leave most SMs idle.
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  int dev = -1;
+};
+static SideStream *side_stream() {
+  static thread_local SideStream ss;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  if (ss.stream == nullptr || ss.dev != cur) {
+    if (cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    ss.dev = cur;
+  }
+  return &ss;
+}
+
 // ---- workspace carving -----------------------------------------------------------------------------
 struct Bump {
   char *base; size_t off;
@@ -126,7 +148,7 @@ struct Bump {
 };
 
 struct LayerWs {
-  void *cublas, *xb, *wqv, *wo, *qv, *o_rounds, *o_comb, *sort_ws, *doutb, *do_comb, *dqv, *bwd_ws;
+  void *cublas, *cublas2, *xb, *wqv, *wo, *qv, *o_rounds, *o_comb, *sort_ws, *doutb, *do_comb, *dqv, *bwd_ws;
   int32_t *sticker;
   float *logits, *lse_tot, *dwqv;
   FwdAux aux;
@@ -152,6 +174,7 @@ static LayerWs carve(const LshAttnDims &d, void *ws, bool with_grad) {
   w.o_comb = b.take(BL * d.H * d.dv * 2);
   w.lse_tot = d.nh > 1 ? static_cast<float *>(b.take(static_cast<size_t>(dr.BH) * d.L * 4)) : w.logits;
   if (with_grad) {
+    w.cublas2 = b.take(kCublasWs);                       // the side-stream GEMM of lsh_layer_bwd needs its own scratch
     w.doutb = d.act_dtype == LSH_DTYPE_F32 ? b.take(BL * d.D * 2) : nullptr;
     w.do_comb = b.take(BL * d.H * d.dv * 2);
     w.dqv = b.take(BL * d.H * dr.QV * 2);
@@ -166,7 +189,7 @@ static LayerWs carve(const LshAttnDims &d, void *ws, bool with_grad) {
 // Forward up to o_comb (EA:1923-1992 for all units).  Returns xb (bf16 view of x).
 static int forward_core(const LshAttnDims &d, const LayerWs &w, const void *x, const float *w_q, const float *w_v,
                         const float *w_o, const float *rotations, const uint8_t *mask, int32_t *buckets,
-                        int64_t bstride, bool need_lse_tot, const void **xb_out, cudaStream_t s) {
+                        int64_t bstride, bool need_lse_tot, const void **xb_out, cudaStream_t s, bool weights_packed = false) {
   Derived dr = derive(d);
   const int64_t BL = static_cast<int64_t>(d.B) * d.L;
   int rc;
@@ -176,7 +199,7 @@ static int forward_core(const LshAttnDims &d, const LayerWs &w, const void *x, c
     xb = w.xb;
   }
   *xb_out = xb;
-  if ((rc = pack_weights_run(d, w_q, w_v, w_o, w.wqv, w.wo, s))) return rc;
+  if (!weights_packed && (rc = pack_weights_run(d, w_q, w_v, w_o, w.wqv, w.wo, s))) return rc;
   const int64_t NQV = static_cast<int64_t>(d.H) * dr.QV;
   if ((rc = gemm_rm(false, false, BL, NQV, d.D, xb, d.D, w.wqv, NQV, w.qv, NQV, false, w.cublas, s))) return rc;
   bool scales_done = false;
@@ -336,22 +359,31 @@ int lsh_layer_bwd(const LshAttnDims *dims, const void *x, const float *w_q, cons
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const void *xb;
   int rc;
-  if ((rc = forward_core(d, w, x, w_q, w_v, w_o, nullptr, mask, const_cast<int32_t *>(buckets), buckets_stride, true,
-                         &xb, s)))
-    return rc;
   const int64_t BL = static_cast<int64_t>(d.B) * d.L, KO = static_cast<int64_t>(d.H) * d.dv;
   const int64_t NQV = static_cast<int64_t>(d.H) * dr.QV;
   const bool f32 = d.act_dtype == LSH_DTYPE_F32;
+  // B1 (first half) on the side stream: do = dout·w_o^T
+  if ((rc = pack_weights_run(d, w_q, w_v, w_o, w.wqv, w.wo, s))) return rc;
+  SideStream *side = side_stream();
+  if (!side) return set_error("lsh_layer_bwd: could not create the internal stream");
+  cudaEventRecord(side->fork, s);
+  cudaStreamWaitEvent(side->stream, side->fork, 0);
+  const void *doutb = dout;
+  if (f32) {
+    if ((rc = f32_to_bf16_run(static_cast<const float *>(dout), w.doutb, BL * d.D, side->stream))) return rc;
+    doutb = w.doutb;
+  }
+  if ((rc = gemm_rm(false, true, BL, KO, d.D, doutb, d.D, w.wo, d.D, w.do_comb, KO, false, w.cublas2, side->stream))) return rc;
+  cudaEventRecord(side->join, side->stream);
+  // forward recompute on the caller's stream
+  if ((rc = forward_core(d, w, x, w_q, w_v, w_o, nullptr, mask, const_cast<int32_t *>(buckets), buckets_stride, true,
+                         &xb, s, /*weights_packed=*/true)))
+    return rc;
   if (out) {
     if ((rc = gemm_rm(false, false, BL, d.D, KO, w.o_comb, KO, w.wo, d.D, out, d.D, f32, w.cublas, s))) return rc;
   }
-  const void *doutb = dout;
-  if (f32) {
-    if ((rc = f32_to_bf16_run(static_cast<const float *>(dout), w.doutb, BL * d.D, s))) return rc;
-    doutb = w.doutb;
-  }
-  // B1: do = dout·w_o^T ; dW_o = o^T·dout
-  if ((rc = gemm_rm(false, true, BL, KO, d.D, doutb, d.D, w.wo, d.D, w.do_comb, KO, false, w.cublas, s))) return rc;
+  cudaStreamWaitEvent(s, side->join, 0);
+  // B1 (second half): dW_o = o^T·dout
   if ((rc = gemm_rm(true, false, KO, d.D, BL, w.o_comb, KO, doutb, d.D, dw_o, d.D, true, w.cublas, s))) return rc;
   // B2-B6
   if ((rc = attend_bwd_run(d, w.qv, w.sticker, mask, w.o_comb, w.lse_tot, w.do_comb, w.aux.qscale, attend_fwd_uses_tc(d) ? w.aux.sticker2 : nullptr, w.dqv, w.bwd_ws, w.bwd_bytes, s)))
