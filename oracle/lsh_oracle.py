@@ -491,3 +491,100 @@ def reversible_half_reverse_and_grad(cfg: LSHConfig, y1, x2, ct_y1, ct_x2, ln_we
   res, _, dz, dw = forward_and_or_backward(cfg, z, attn_weights, buckets=buckets, output_grad=ct_y1, update_state=False)
   dx2, d_scale, d_bias = layernorm_vjp(x2, ln_weights[0], dz, epsilon)
   return (np.asarray(y1, np.float64) - res, x2), ((ct_y1, np.asarray(ct_x2, np.float64) + dx2), ((d_scale, d_bias), dw))
+
+
+# ---- PureLSHSelfAttentionWrapper (EA:3493-3620) with _ProjectAndSplitHeads weights_format='model' (EA:3294-3312, 3360-3372) ---
+def rotary(x):
+  """research/rotary_positional_embedding.py:27-44 on (B, L, d), fp64."""
+  x = np.asarray(x, np.float64)
+  _, l, d = x.shape
+  inv_freq = np.exp(np.arange(0, d, 2) * -(np.log(10000.0) / d))
+  freqs = np.arange(l)[:, None] * inv_freq[None, :]
+  emb = np.concatenate((freqs, freqs), axis=-1)
+  half = d // 2
+  rot_half = np.concatenate((-x[..., half:], x[..., :half]), axis=-1)
+  return x * np.cos(emb) + rot_half * np.sin(emb)
+
+
+def rotary_vjp(g):
+  """VJP of `rotary` (linear in x): g cos + rotate_half^T(g sin), rotate_half^T(u) = (u2, -u1)."""
+  g = np.asarray(g, np.float64)
+  _, l, d = g.shape
+  inv_freq = np.exp(np.arange(0, d, 2) * -(np.log(10000.0) / d))
+  freqs = np.arange(l)[:, None] * inv_freq[None, :]
+  emb = np.concatenate((freqs, freqs), axis=-1)
+  u = g * np.sin(emb)
+  half = d // 2
+  return g * np.cos(emb) + np.concatenate((u[..., half:], -u[..., :half]), axis=-1)
+
+
+def _dense(x, w):
+  """core.py:79-98: w is `(kernel, bias)` or a bare kernel."""
+  if isinstance(w, (tuple, list)):
+    return np.matmul(x, np.asarray(w[0], np.float64)) + np.asarray(w[1], np.float64)
+  return np.matmul(x, np.asarray(w, np.float64))
+
+
+def _dense_vjp(x, w, dy):
+  """(dx, dw) with dw shaped like w."""
+  kernel = np.asarray(w[0] if isinstance(w, (tuple, list)) else w, np.float64)
+  x2, dy2 = x.reshape(-1, x.shape[-1]), dy.reshape(-1, dy.shape[-1])
+  dk = np.matmul(x2.T, dy2)
+  dx = np.matmul(dy, kernel.T)
+  return dx, ((dk, dy2.sum(axis=0)) if isinstance(w, (tuple, list)) else dk)
+
+
+def split_heads(x, n_heads):
+  """attention.py:347-364: (B, L, H d) -> (B H, L, d)."""
+  b, l, f = x.shape
+  return x.reshape(b, l, n_heads, f // n_heads).transpose(0, 2, 1, 3).reshape(b * n_heads, l, f // n_heads)
+
+
+def merge_heads(x, n_heads):
+  """attention.py:369-388: (B H, L, d) -> (B, L, H d)."""
+  bh, l, d = x.shape
+  return x.reshape(bh // n_heads, n_heads, l, d).transpose(0, 2, 1, 3).reshape(bh // n_heads, l, n_heads * d)
+
+
+def pure_lsh_wrapper(cfg: LSHConfig, x, qkv_weights, dense_weights, *, buckets=None, rotations=None, mask=None,
+                     output_grad=None, rotary_position_emb=False):
+  """`PureLSHSelfAttentionWrapper` = Serial(_ProjectAndSplitHeads('model'), PureLSHSelfAttention, MergeHeads, Dense)
+  (EA:3512-3540) and its `forward_and_or_backward` (EA:3542-3620): x (B, L, d_model); `qkv_weights` holds two
+  (qk, v: EA:3360-3372) or three (q, k, v with qk = (q + k)/2: EA:3294-3312) Dense weights; either `rotations`
+  (B H, dq, nh, R) or stored `buckets` (B H, nh L).  Returns (out, buckets, dx, (d_qkv_weights, d_dense_weights))."""
+  x = np.asarray(x, np.float64)
+  H = cfg.n_heads
+  proj = [_dense(x, w) for w in qkv_weights]
+  n_rot = len(proj) - 1                                            # q (and k) are rotated, v never (EA:3303-3304, 3363-3365)
+  rot = [rotary(p) if (rotary_position_emb and i < n_rot) else p for i, p in enumerate(proj)]
+  qk = (rot[0] + rot[1]) / 2.0 if len(proj) == 3 else rot[0]       # EA:3306
+  v = rot[-1]
+  qk_h, v_h = split_heads(qk, H), split_heads(v, H)                # EA:3309-3311
+  eye_q = np.concatenate([np.eye(cfg.d_qk), np.zeros((cfg.d_v, cfg.d_qk))], axis=0)
+  eye_v = np.concatenate([np.zeros((cfg.d_qk, cfg.d_v)), np.eye(cfg.d_v)], axis=0)
+  units, new_buckets = [], []
+  for u in range(qk_h.shape[0]):                                   # PureLSH forward_unbatched (EA:2739-2826) per unit
+    xu = np.concatenate([qk_h[u], v_h[u]], axis=1)
+    r = forward_unit(cfg, xu, eye_q, eye_v, np.eye(cfg.d_v),
+                     buckets=None if buckets is None else buckets[u],
+                     rotations=None if rotations is None else rotations[u],
+                     mask=None if mask is None else mask[u // H])
+    units.append(r)
+    new_buckets.append(r.buckets)
+  merged = merge_heads(np.stack([r.out for r in units]), H)        # EA:3531
+  out = _dense(merged, dense_weights)                              # EA:3533
+  if output_grad is None:
+    return out, np.stack(new_buckets), None, None
+  d_merged, d_dense = _dense_vjp(merged, dense_weights, np.asarray(output_grad, np.float64))   # EA:3590-3592
+  d_heads = split_heads(d_merged, H)                               # EA:3596-3597 (vjp of MergeHeads)
+  g = np.stack([backward_unit(cfg, units[u], d_heads[u])[0] for u in range(len(units))])      # EA:3600-3602
+  d_qk, d_v = merge_heads(g[..., :cfg.d_qk], H), merge_heads(g[..., cfg.d_qk:], H)
+  d_rot = [d_qk / 2.0, d_qk / 2.0, d_v] if len(proj) == 3 else [d_qk, d_v]
+  d_proj = [rotary_vjp(d) if (rotary_position_emb and i < n_rot) else d for i, d in enumerate(d_rot)]
+  dx = np.zeros_like(x)
+  d_qkv = []
+  for w, d in zip(qkv_weights, d_proj):                            # EA:3605
+    dxi, dw = _dense_vjp(x, w, d)
+    dx += dxi
+    d_qkv.append(dw)
+  return out, np.stack(new_buckets), dx, (tuple(d_qkv), d_dense)

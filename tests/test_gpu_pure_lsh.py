@@ -93,3 +93,44 @@ def test_lsh_equals_projections_plus_pure_core():
   np.testing.assert_array_equal(pure.state[0].cpu().numpy(), full.state[0].cpu().numpy())   # same buckets
   got = torch.einsum('bhlk,hkd->bld', o.reshape(B, H, L, 64).to(torch.bfloat16).float(), w_o.to(torch.bfloat16).float())
   util.assert_close(got.cpu().numpy(), want.cpu().numpy(), 'LSH vs projections + PureLSH + w_o')
+
+
+@pytest.mark.parametrize('num_weights,bias,rotary,dtype', [(3, True, False, torch.float32), (2, False, True, torch.bfloat16)])
+def test_pure_lsh_wrapper_matches_oracle(num_weights, bias, rotary, dtype):
+  """`PureLSHSelfAttentionWrapper` (EA:3493-3620) on the CUDA core vs the oracle's restatement.  The buckets the device
+  hashed (from its bf16 qk) are handed to the oracle, so near-tie hash flips do not enter the comparison; they must be
+  valid bucket ids and survive the backward call unchanged."""
+  import trax_b200
+  B, L, H = 2, 512, 2
+  D = 64 * H
+  cfg = util.make_cfg(H=H, C=128, nh=2, n_buckets=8)
+  wrap = trax_b200.PureLSHSelfAttentionWrapper(
+      n_heads=H, d_qk=64, d_v=64, causal=True, bias=bias, num_weights=num_weights, weights_format='model',
+      rotary_position_emb=rotary, chunk_len=128, n_hashes=2, n_buckets=8)
+  weights, _ = wrap.init(trax_b200.ShapeDtype((B, L, D)), rng=np.array([3, 4], np.uint32))
+  rng = np.random.default_rng(23)
+  x = util.bf16_round(rng.standard_normal((B, L, D)))
+  dout = util.bf16_round(rng.standard_normal((B, L, D)))
+  xd = torch.from_numpy(x).cuda().to(dtype)
+  out = wrap.forward(xd)
+  buckets = wrap.state[1][0].cpu().numpy()
+  assert buckets.shape == (B * H, 2 * L) and buckets.min() >= 0 and buckets.max() < 2 * 8
+  assert (buckets[:, :L] < 8).all() and (buckets[:, L:] >= 8).all()                # per-round offsets (EA:1913-1915)
+  np_w = lambda w: tuple(l.cpu().numpy().astype(np.float64) for l in w) if isinstance(w, tuple) \
+      else w.cpu().numpy().astype(np.float64)
+  qkv_w, dense_w = tuple(np_w(w) for w in weights[0]), np_w(weights[3])
+  want_out, _, want_dx, (want_dqkv, want_ddense) = O.pure_lsh_wrapper(
+      cfg, x, qkv_w, dense_w, buckets=buckets, output_grad=dout, rotary_position_emb=rotary)
+  util.assert_close(out.float().cpu().numpy(), want_out, 'wrapper out')
+  out2, new_state, dx, dw = wrap.forward_and_or_backward(xd, weights, wrap.state, None,
+                                                         output_grad=torch.from_numpy(dout).cuda(), update_state=False)
+  assert new_state is None
+  np.testing.assert_array_equal(wrap.state[1][0].cpu().numpy(), buckets)
+  util.assert_close(out2.float().cpu().numpy(), want_out, 'wrapper out (backward call)')
+  util.assert_close(dx.float().cpu().numpy(), want_dx, 'wrapper dx')
+  leaves = lambda w: list(w) if isinstance(w, tuple) else [w]
+  for i in range(num_weights):
+    for got, want in zip(leaves(dw[0][i]), leaves(want_dqkv[i])):
+      util.assert_close(got.float().cpu().numpy(), want, 'wrapper d_qkv[%d]' % i)
+  for got, want in zip(leaves(dw[3]), leaves(want_ddense)):
+    util.assert_close(got.float().cpu().numpy(), want, 'wrapper d_dense')
