@@ -82,3 +82,46 @@ def test_reversible_half_forward_and_reverse_and_grad(B, L, D, dtype, cfg):
   util.assert_close(d_bias.cpu().numpy(), w_db, 'd_bias')
   for n, g, w in zip(('dw_q', 'dw_v', 'dw_o'), dw, w_dw):
     util.assert_close(g.float().cpu().numpy(), w, n)
+
+
+def test_reversible_half_around_the_pure_lsh_wrapper():
+  """The Terraformer-style block: ReversibleHalfResidual(LayerNorm, attention_layer=PureLSHSelfAttentionWrapper)
+  (reversible.py:281-286 accepts any layer with `forward_and_or_backward`; EA:3542-3620 serves exactly this call)."""
+  import trax_b200
+  B, L, H = 1, 512, 4
+  D = 64 * H
+  cfg = util.make_cfg(H=H, C=128, nh=2, n_buckets=8)
+  rng = np.random.default_rng(29)
+  x1, x2 = (rng.standard_normal((B, L, D)).astype(np.float32) for _ in range(2))
+  ct_y1, ct_x2 = (rng.standard_normal((B, L, D)).astype(np.float32) for _ in range(2))
+  scale = (1 + 0.1 * rng.standard_normal(D)).astype(np.float32)
+  bias = (0.1 * rng.standard_normal(D)).astype(np.float32)
+  wrap = trax_b200.PureLSHSelfAttentionWrapper(n_heads=H, d_qk=64, d_v=64, causal=True, chunk_len=128, n_hashes=2,
+                                               n_buckets=8, bias=True, num_weights=3)
+  block = trax_b200.ReversibleHalfResidual(wrap)
+  sig = trax_b200.ShapeDtype((B, L, D))
+  (_, attn_w), _ = block.init((sig, sig), rng=np.array([5, 6], np.uint32))
+  cu = lambda a: torch.from_numpy(np.asarray(a, np.float32)).cuda()
+  block.weights = ((cu(scale), cu(bias)), attn_w)
+  y1, ctx = block.forward((cu(x1), cu(x2)))
+  buckets = block.state[1][1][0].cpu().numpy()                      # wrapper state -> core state -> buckets
+  np_w = lambda w: tuple(l.cpu().numpy().astype(np.float64) for l in w)
+  qkv_w, dense_w = tuple(np_w(w) for w in attn_w[0]), np_w(attn_w[3])
+  z = O.layernorm(x2, scale, bias)
+  want_res, _, want_dz, (want_dqkv, want_ddense) = O.pure_lsh_wrapper(cfg, z, qkv_w, dense_w, buckets=buckets,
+                                                                     output_grad=ct_y1)
+  util.assert_close(y1.cpu().numpy(), x1 + want_res, 'y1')
+  (rx1, rx2), ((g_y1, g_x2), ((d_scale, d_bias), dw)) = block.reverse_and_grad(
+      (y1, ctx), (cu(ct_y1), cu(ct_x2)), block.weights, None, block.state, None)
+  util.assert_close(rx1.cpu().numpy(), x1, 'reconstructed x1', rtol=3e-2)
+  assert torch.equal(rx2, ctx) and torch.equal(g_y1.cpu(), torch.from_numpy(ct_y1))
+  w_dx2, w_ds, w_db = O.layernorm_vjp(x2, scale, want_dz)
+  util.assert_close(g_x2.cpu().numpy(), ct_x2 + w_dx2, 'ct_x2')
+  util.assert_close(d_scale.cpu().numpy(), w_ds, 'd_scale')
+  util.assert_close(d_bias.cpu().numpy(), w_db, 'd_bias')
+  assert dw[1] == () and dw[2] == ()
+  for i in range(3):
+    for got, want, nm in zip(dw[0][i], want_dqkv[i], ('kernel', 'bias')):
+      util.assert_close(got.cpu().numpy(), want, 'd_qkv[%d] %s' % (i, nm))
+  for got, want, nm in zip(dw[3], want_ddense, ('kernel', 'bias')):
+    util.assert_close(got.cpu().numpy(), want, 'd_dense %s' % nm)
