@@ -11,8 +11,8 @@ unit SURVEY.md §8(d) defines.  N>1: every rank runs the same per-GPU workload o
 scaling over batch) and the timed step ends with the NCCL all-reduce of the weight gradients
 (the analogue of trax/optimizers/trainer.py:172-199).
 
-Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle (the reference itself needs JAX,
-which this image lacks) on the host cores instead.
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle (pinned to the reference's own code by
+tests/test_reference_pin.py; the reference's jitted path needs JAX, which this image lacks) on the host cores instead.
 """
 import argparse
 import json

@@ -5,14 +5,27 @@ CPU restatement (NumPy + a small C helper) of the reference's Reformer LSH-atten
 the reference lines it follows.  Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s
 `cpu_baseline` / `--impl reference` legs may import this module.
 
-PARITY UNPINNED: the reference is pure Python on JAX/XLA; JAX is not installable in this image and
-the checkout holds no golden vectors for this path.  This restatement is
-therefore pinned only by (a) line-by-line correspondence with EA, (b) an independent torch-autograd
-restatement (`lsh_oracle_torch.py`) and (c) the reference tests' own invariants re-run on it
-(tests/test_oracle.py).  It is NOT pinned against outputs of the live reference.
+PARITY PINNED AGAINST THE LIVE REFERENCE (forward directly, backward through derivatives of the
+reference's forward).  JAX is not installable in this image and the checkout holds no golden vectors
+for this path, but the reference is pure Python with a NumPy backend of its
+own: `oracle/ref_live.py` executes the reference's files from /root/reference under that backend
+(stubs only for the absent third-party packages; `use_reference_code=True` is the reference's own
+Python loop over units around `forward_unbatched`).  `tests/golden/make_reference_golden.py` stores
+what it returns in `tests/golden/reference_live.npz`; `tests/test_reference_pin.py` checks that this
+restatement reproduces the reference's bucket ids bit for bit and its float64 outputs to 1e-12
+(causal / bidirectional, masked, look-ahead chunks, single and factored bucket counts, the auto
+factor-list rule, the weight-less PureLSH core), and that the analytic VJP below equals central
+differences of the reference's forward to 1e-6 relative (observed 1e-9..1e-11) — the reference's
+backward is `jax.vjp` of exactly that function (EA:2399-2421).  What is NOT pinned: XLA's own fp32
+summation order inside the hash einsum on an accelerator (no XLA here; bucket ids can differ from a
+TPU/GPU run of the reference at exact near-ties of the argmax, as they do between XLA backends), and
+`jax.random` bit streams (rotations and dropout masks are inputs).  Further cross-checks: an
+independent torch-autograd restatement (`lsh_oracle_torch.py`) and the reference tests' own
+invariants re-run on it (tests/test_oracle.py).
 
 Random rotations are an explicit input (EA:91-93 draws them with jax.random.normal, which is not
-reproducible offline); so are dropout keep-masks.
+reproducible offline; under the reference's NumPy backend they come from numpy.random, which the pin
+script seeds and records); so are dropout keep-masks.
 """
 from __future__ import annotations
 

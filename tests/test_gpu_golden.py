@@ -1,5 +1,5 @@
-"""The CUDA path against the COMMITTED golden fixtures (tests/golden/*.npz, written by tests/golden/make_golden.py from
-the oracle; the reference itself cannot run here — SURVEY F2/F4)."""
+"""The CUDA path against the COMMITTED golden fixtures: tests/golden/reference_live.npz holds outputs of the reference's own
+code (tests/golden/make_reference_golden.py); lsh_small.npz / reversible_c128.npz hold oracle outputs (make_golden.py)."""
 import os
 
 import numpy as np
@@ -66,3 +66,66 @@ def test_reversible_block_against_reversible_c128_fixture(dtype):
   util.assert_close(db.cpu().numpy(), g['d_bias'], 'd_bias')
   for k, w in zip(('dw_q', 'dw_v', 'dw_o'), dw):
     util.assert_close(w.float().cpu().numpy(), g[k], k)
+
+
+# ---- reference_live.npz: what google/trax's own code returned for these inputs (tests/golden/make_reference_golden.py) ----
+def _directional_ok(grad, direction, want, name):
+  """<grad, dir> against the reference's directional derivative.  An elementwise relative error e on grad moves the inner
+  product by about e * |grad| |dir| / sqrt(n); allow four times that at e = RTOL."""
+  grad, direction = np.asarray(grad, np.float64), np.asarray(direction, np.float64)
+  got = float((grad * direction).sum())
+  tol = 4 * util.RTOL * np.linalg.norm(grad) * np.linalg.norm(direction) / np.sqrt(grad.size) + util.ATOL
+  assert abs(got - want) <= tol, '%s: <grad, dir> = %.6g, the reference forward differentiates to %.6g (tol %.3g)' % (
+      name, got, want, tol)
+
+
+@pytest.mark.parametrize('name', ['lsh_c128', 'lsh_c64_auto', 'lsh_masked_factored'])
+def test_layer_against_the_live_reference(name):
+  """Output vs the reference layer's own output (buckets: the reference's, fed through the state as the reversible block
+  does), gradients vs derivatives of the reference's forward and vs the oracle's VJP (pinned to the same numbers on CPU)."""
+  import trax_b200
+  from oracle import lsh_oracle as O
+  from tests.golden import reference_cases as RC
+  c, d, g = RC.CASES[name], RC.inputs(name), np.load(os.path.join(HERE, 'reference_live.npz'))
+  B, H, L, D = c['B'], c['H'], c['L'], c['D']
+  layer = trax_b200.LSHSelfAttention(n_heads=H, d_qk=64, d_v=64, causal=c['causal'], masked=c['masked'], chunk_len=c['C'],
+                                     n_chunks_before=c['nb'], n_chunks_after=c['na'], n_hashes=c['nh'],
+                                     n_buckets=c['n_buckets'])
+  sig = trax_b200.ShapeDtype((B, L, D))
+  layer.init((sig, trax_b200.ShapeDtype((B, L))) if c['masked'] else sig)
+  weights = tuple(_cu(d[k]) for k in ('w_q', 'w_v', 'w_o'))
+  inputs = (_cu(d['x']), torch.from_numpy(d['mask']).cuda()) if c['masked'] else _cu(d['x'])
+  state = (torch.from_numpy(g[name + '/buckets']).cuda(), layer.state[1])
+  out, _, dx, dw = layer.forward_and_or_backward(inputs, weights, state, None, output_grad=_cu(d['dout']),
+                                                 compute_output=True, update_state=False)
+  util.assert_close(out.cpu().numpy(), g[name + '/out'], 'out vs the reference')
+  dx = dx[0] if c['masked'] else dx
+  cfg = O.LSHConfig(n_heads=H, d_qk=64, d_v=64, causal=c['causal'], masked=c['masked'], chunk_len=c['C'],
+                    n_chunks_before=c['nb'], n_chunks_after=c['na'], n_hashes=c['nh'], n_buckets=c['n_buckets'])
+  _, _, want_dx, want_dw = O.forward_and_or_backward(cfg, d['x'], (d['w_q'], d['w_v'], d['w_o']), buckets=g[name + '/buckets'],
+                                                     mask=d['mask'], output_grad=d['dout'], update_state=False)
+  for key, got, want in zip(('x', 'w_q', 'w_v', 'w_o'), (dx,) + tuple(dw), (want_dx,) + tuple(want_dw)):
+    util.assert_close(got.float().cpu().numpy(), want, 'd' + key)
+    _directional_ok(got.float().cpu().numpy(), d['dir_' + key], float(g[name + '/ddir_' + key]), 'd' + key)
+
+
+def test_pure_core_against_the_live_reference():
+  """PureLSHSelfAttention with update_state=True on bf16-exact inputs and the reference's rotations: the device's buckets
+  equal the reference's bit for bit; output and (dqk, dv) follow."""
+  import trax_b200
+  from tests.golden import reference_cases as RC
+  name = 'pure_c128'
+  c, d, g = RC.CASES[name], RC.inputs(name), np.load(os.path.join(HERE, 'reference_live.npz'))
+  BH, L = c['B'] * c['H'], c['L']
+  layer = trax_b200.PureLSHSelfAttention(n_heads=c['H'], d_qk=64, d_v=64, causal=True, chunk_len=c['C'], n_hashes=c['nh'],
+                                         n_buckets=c['n_buckets'])
+  sig = trax_b200.ShapeDtype((BH, L, 64))
+  layer.init((sig, sig))
+  layer._rotations_override = torch.from_numpy(g[name + '/rot'])
+  inputs = (_cu(d['qk']), _cu(d['v']))
+  out = layer.forward(inputs)
+  np.testing.assert_array_equal(layer.state[0].cpu().numpy(), g[name + '/buckets'])
+  util.assert_close(out.cpu().numpy(), g[name + '/out'], 'out vs the reference')
+  (dqk, dv), _ = layer.backward(inputs, out, _cu(d['dout']), (), None, layer.state, None)
+  _directional_ok(dqk.cpu().numpy(), d['dir_qk'], float(g[name + '/ddir_qk']), 'dqk')
+  _directional_ok(dv.cpu().numpy(), d['dir_v'], float(g[name + '/ddir_v']), 'dv')

@@ -1,0 +1,88 @@
+"""The oracle against the LIVE REFERENCE.  tests/golden/reference_live.npz holds what google/trax's own code returned
+(written by tests/golden/make_reference_golden.py through oracle/ref_live.py: the reference's files executed from
+/root/reference under the reference's own NumPy backend).  Here:
+
+  * the oracle must reproduce the reference's buckets bit for bit and its float64 outputs to 1e-12;
+  * the oracle's analytic VJP must agree with derivatives of the reference's forward function (the reference's backward
+    is `jax.vjp` of that function, EA:2399-2421);
+  * where /root/reference is present (the build container), the fixture is regenerated from it and must come out equal —
+    the committed numbers are the reference's, not ours.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import lsh_oracle as O
+from oracle import ref_live
+from tests import util
+from tests.golden import reference_cases as RC
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+FIXTURE = os.path.join(GOLDEN, 'reference_live.npz')
+
+
+def _cfg(c):
+  return O.LSHConfig(n_heads=c['H'], d_qk=RC.D_HEAD, d_v=RC.D_HEAD, causal=c['causal'], masked=c['masked'],
+                     chunk_len=c['C'], n_chunks_before=c['nb'], n_chunks_after=c['na'], n_hashes=c['nh'],
+                     n_buckets=c['n_buckets'])
+
+
+@pytest.mark.parametrize('name', [n for n, c in RC.CASES.items() if c['kind'] == 'lsh'])
+def test_oracle_layer_matches_live_reference(name):
+  c, d, g = RC.CASES[name], RC.inputs(name), np.load(FIXTURE)
+  cfg, weights = _cfg(c), (d['w_q'], d['w_v'], d['w_o'])
+  out, buckets, _, _ = O.forward_and_or_backward(cfg, d['x'], weights, rotations=g[name + '/rot'], mask=d['mask'])
+  np.testing.assert_array_equal(buckets, g[name + '/buckets'])      # fp32 sequential-FMA hash == the reference's hash
+  np.testing.assert_allclose(out, g[name + '/out'], rtol=1e-12, atol=1e-12)
+  _, _, dx, dw = O.forward_and_or_backward(cfg, d['x'], weights, buckets=g[name + '/buckets'], mask=d['mask'],
+                                           output_grad=d['dout'], update_state=False)
+  for key, grad in zip(('x', 'w_q', 'w_v', 'w_o'), (dx,) + tuple(dw)):
+    want = float(g[name + '/ddir_' + key])
+    np.testing.assert_allclose((grad * d['dir_' + key]).sum(), want, rtol=1e-6, atol=1e-7, err_msg=key)
+
+
+def test_oracle_pure_core_matches_live_reference():
+  name = 'pure_c128'
+  c, d, g = RC.CASES[name], RC.inputs(name), np.load(FIXTURE)
+  cfg = _cfg(c)
+  w_q, w_v, w_o = util.core_identity_weights()
+  an = dict(qk=0.0, v=0.0)
+  for u in range(c['B'] * c['H']):
+    x = np.concatenate([d['qk'][u], d['v'][u]], axis=1)
+    r = O.forward_unit(cfg, x, w_q, w_v, w_o, rotations=g[name + '/rot'][u])
+    np.testing.assert_array_equal(r.buckets, g[name + '/buckets'][u])
+    np.testing.assert_allclose(r.out, g[name + '/out'][u], rtol=1e-12, atol=1e-12)
+    grad = O.backward_unit(cfg, r, d['dout'][u])[0]
+    an['qk'] += (grad[:, :RC.D_HEAD] * d['dir_qk'][u]).sum()
+    an['v'] += (grad[:, RC.D_HEAD:] * d['dir_v'][u]).sum()
+  for key in ('qk', 'v'):
+    np.testing.assert_allclose(an[key], float(g[name + '/ddir_' + key]), rtol=1e-6, atol=1e-7, err_msg=key)
+
+
+def test_oracle_hash_auto_factor_list_matches_live_reference():
+  """n_buckets=None with 2 L / C > 128: the reference picks the factor list itself (EA:1896-1902)."""
+  name = 'hash_auto_factors'
+  c, d, g = RC.CASES[name], RC.inputs(name), np.load(FIXTURE)
+  assert O.bucket_factors(None, c['L'], c['C']) == [32, 8]
+  q = d['x'][0] @ d['w_q'][0]
+  for fn in (O.hash_vectors, O.hash_vectors_c):
+    np.testing.assert_array_equal(fn(_cfg(c), q.astype(np.float32), g[name + '/rot'][0]), g[name + '/buckets'])
+
+
+@pytest.mark.skipif(not ref_live.available(), reason='the reference checkout exists only in the build container')
+def test_fixture_is_what_the_reference_returns(tmp_path):
+  """Re-runs the reference (own process: the import stubs are process-global) and compares with the committed file."""
+  out = str(tmp_path / 'regenerated.npz')
+  repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  subprocess.run([sys.executable, os.path.join(GOLDEN, 'make_reference_golden.py'), '--out', out], check=True, cwd=repo,
+                 timeout=900, stdout=subprocess.DEVNULL)
+  new, old = np.load(out), np.load(FIXTURE)
+  assert sorted(new.files) == sorted(old.files)
+  for k in old.files:
+    if old[k].dtype.kind in 'iuU':
+      np.testing.assert_array_equal(new[k], old[k], err_msg=k)
+    else:
+      np.testing.assert_allclose(new[k], old[k], rtol=1e-7 if '/ddir_' in k else 1e-12, atol=1e-12, err_msg=k)
