@@ -14,7 +14,8 @@ Python loop over units around `forward_unbatched`).  `tests/golden/make_referenc
 what it returns in `tests/golden/reference_live.npz`; `tests/test_reference_pin.py` checks that this
 restatement reproduces the reference's bucket ids bit for bit and its float64 outputs to 1e-12
 (causal / bidirectional, masked, look-ahead chunks, single and factored bucket counts, the auto
-factor-list rule, the weight-less PureLSH core), and that the analytic VJP below equals central
+factor-list rule, the weight-less PureLSH core, PureLSHSelfAttentionWrapper with and without rotary
+embedding, the ReversibleHalfResidual block with LayerNorm), and that the analytic VJP below equals central
 differences of the reference's forward to 1e-6 relative (observed 1e-9..1e-11) — the reference's
 backward is `jax.vjp` of exactly that function (EA:2399-2421).  What is NOT pinned: XLA's own fp32
 summation order inside the hash einsum on an accelerator (no XLA here; bucket ids can differ from a

@@ -11,17 +11,24 @@ loop over (example, head) units around `forward_unbatched` (EA:2127-2170) — no
   2. registers an empty `trax` package whose `__path__` points INTO `/root/reference/trax`, so that submodules
      (`trax.fastmath`, `trax.layers.research.efficient_attention`, ...) are the reference's files, executed where they
      lie — nothing is copied — while the heavyweight `trax/__init__.py` is skipped;
-  3. switches `trax.fastmath` to the reference's NumPy backend and adds the four primitives that backend lacks and the
-     path calls, each a one-line NumPy statement of the `jax.lax` primitive the JAX backend binds
-     (`trax/fastmath/jax.py:199, 213, 214`, `ops.py:300-315`):
+  3. switches `trax.fastmath` to the reference's NumPy backend and adds the primitives that backend lacks and the
+     path calls, each a one-line NumPy statement of the `jax` primitive the JAX backend binds
+     (`trax/fastmath/jax.py:192-199, 213, 214`, `ops.py:300-315`):
        sort_key_val(keys, values, dimension)  -> stable argsort of keys applied to both
        stop_gradient(x)                       -> x
        lt(a, b)                               -> a < b
        custom_grad(f_vjp, f)                  -> f          (forward semantics of a custom-VJP function)
+       index_update(x, idx, y) / index_add    -> copy of x with x[idx] = y / x[idx] += y   (`x.at[idx].set/add`)
+       jax.numpy.index_exp                    -> numpy.index_exp
+     and replaces that backend's `random_split` (it returns `None` keys, `fastmath/numpy.py:72`, which the layers'
+     shape inference cannot take) by one returning zero-valued uint32 keys — the NumPy backend never reads a key.
+     With these the batched drivers run too when asked for their Python loop (`use_python_loop=True,
+     n_parallel_heads=1`; EA:2261-2561, 3052-3265), and so do `PureLSHSelfAttentionWrapper` and `ReversibleHalfResidual`.
 
 Everything else that runs — hashing (EA:60-119), `look_adjacent`, `mask_self_attention`, `attend` (EA:164-281),
 `LSHSelfAttention.forward_unbatched` (EA:1918-1997), `PureLSHSelfAttention.forward_unbatched` (EA:2739-2826), the
-`use_reference_code` driver loop, `core.Dense`, `LayerNorm`, the Serial / reversible combinators — is the reference's code.
+`use_reference_code` driver loop and the batched drivers' Python loop, `core.Dense`, `LayerNorm`, rotary embedding, head
+split / merge, the Serial / Branch / reversible combinators — is the reference's code.
 Random numbers under that backend come from NumPy's global generator (`fastmath/numpy.py:37-40` ignores the key), so the
 caller seeds `numpy.random` to make the hash rotations reproducible.
 
@@ -42,8 +49,9 @@ _THIRD_PARTY = ('jax', 'jaxlib', 'tensorflow', 'tensorflow_datasets', 'tensorflo
 
 
 class _Anything:
-  """Attribute of a stub package: any attribute chain exists, a call with one callable acts as a bare decorator, any
-  other call returns another stub (so it also works as a decorator factory or a base class)."""
+  """Attribute of a stub package: any attribute chain exists, a call whose first argument is a function or class hands it
+  back (bare decorator, `gin.external_configurable(cls, module=...)`), any other call returns another stub (so it also
+  works as a decorator factory or a base class)."""
 
   def __init__(self, name):
     self._name = name
@@ -54,7 +62,7 @@ class _Anything:
     return _Anything(self._name + '.' + k)
 
   def __call__(self, *a, **kw):
-    if len(a) == 1 and callable(a[0]) and not kw and not isinstance(a[0], _Anything):
+    if a and callable(a[0]) and not isinstance(a[0], _Anything):     # decorator / gin.external_configurable(cls, ...)
       return a[0]
     return _Anything(self._name + '()')
 
@@ -101,7 +109,7 @@ def available(root=REFERENCE_ROOT):
 
 def load(root=REFERENCE_ROOT):
   """Returns a namespace with the reference's modules: `.EA` (efficient_attention), `.fastmath`, `.shapes`, `.layers`,
-  `.reversible`, and `.stubbed` (the absent third-party packages that were stubbed)."""
+  `.reversible`, `.normalization`, and `.stubbed` (the absent third-party packages that were stubbed)."""
   import numpy as np
   if not available(root):
     raise FileNotFoundError('the reference checkout is not present at %s' % root)
@@ -124,15 +132,28 @@ def load(root=REFERENCE_ROOT):
   from trax import fastmath, shapes
   from trax.fastmath.numpy import NUMPY_BACKEND
   from trax import layers                            # imported under the default backend name: module-level pmap etc.
-  from trax.layers import reversible
+  from trax.layers import normalization, reversible
   from trax.layers.research import efficient_attention as EA
 
   def sort_key_val(keys, values, dimension=-1):
     order = np.argsort(keys, axis=dimension, kind='stable')
     return np.take_along_axis(keys, order, axis=dimension), np.take_along_axis(values, order, axis=dimension)
+
+  def index_update(x, idx, y):
+    x = np.array(x, copy=True)
+    x[idx] = y
+    return x
+
+  def index_add(x, idx, y):
+    x = np.array(x, copy=True)
+    x[idx] += y
+    return x
   NUMPY_BACKEND.update(sort_key_val=sort_key_val, stop_gradient=lambda x: x, lt=np.less,
-                       custom_grad=lambda f_vjp, f: f)
+                       custom_grad=lambda f_vjp, f: f, index_update=index_update, index_add=index_add,
+                       random_split=lambda prng, num=2: np.zeros((num, 2), np.uint32))
+  if 'jax' in absent:
+    jax.numpy.index_exp = np.index_exp
   fastmath.ops.set_backend('numpy')
   assert fastmath.backend_name() == 'numpy'
-  return types.SimpleNamespace(EA=EA, fastmath=fastmath, shapes=shapes, layers=layers, reversible=reversible,
+  return types.SimpleNamespace(EA=EA, fastmath=fastmath, shapes=shapes, layers=layers, reversible=reversible, normalization=normalization,
                                stubbed=absent, root=root)

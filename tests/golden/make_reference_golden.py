@@ -11,6 +11,9 @@ what the reference returned:
   <case>/out       that call's output, float64
                    (`forward_unbatched(..., update_state=False)` with those buckets, EA:1939-1941, is checked here to
                    return the same numbers and is the function differentiated below)
+  wrapper_* / reversible_*: the same for `PureLSHSelfAttentionWrapper` (Serial of Dense projections, core, Dense) and for
+                   `ReversibleHalfResidual(LayerNorm, attention_layer=LSHSelfAttention)`, run through the batched drivers'
+                   Python loop; every evaluation re-seeds NumPy so the same rotations (and, checked, buckets) recur.
   <case>/ddir_*    d/de <out(theta + e dir), dout> at e = 0 with the buckets held, by central differences of the reference's forward in
                    float64 — the reference's backward IS `jax.vjp` of this function (EA:2399-2421), so these numbers pin a
                    VJP without running JAX.
@@ -106,11 +109,102 @@ def run_hash(R, name, c, d, out):
   out[name + '/buckets'] = np.asarray(layer.hash_vectors(q, None), np.int32)      # EA:1889-1916
 
 
+def leaves(w):
+  return list(w) if isinstance(w, tuple) else [w]
+
+
+def set_leaves(R, layer, new_leaves):
+  """Replaces the layer's weights, leaf by leaf in tree order, keeping the reference's own nesting."""
+  old, _ = R.fastmath.tree_flatten(layer.weights), None
+  assert [np.shape(a) for a in old] == [np.shape(a) for a in new_leaves], ([np.shape(a) for a in old],)
+  tree, rest = R.fastmath.tree_unflatten(list(new_leaves), layer.weights)
+  assert not rest
+  layer.weights = tree
+
+
+def run_wrapper(R, name, c, d, out):
+  """PureLSHSelfAttentionWrapper as a Serial (EA:3512-3540), its core driven by the batched driver's Python loop."""
+  B, H, L, D = c['B'], c['H'], c['L'], c['D']
+  layer = R.EA.PureLSHSelfAttentionWrapper(
+      n_heads=H, d_qk=RC.D_HEAD, d_v=RC.D_HEAD, causal=c['causal'], pure_lsh_implementation=R.EA.PureLSHSelfAttention,
+      bias=c['bias'], num_weights=c['num_weights'], weights_format='model', rotary_position_emb=c['rotary'],
+      chunk_len=c['C'], n_hashes=c['nh'], n_buckets=c['n_buckets'], use_python_loop=True, n_parallel_heads=1)
+  layer.init(R.shapes.ShapeDtype((B, L, D), np.float64))
+  np.random.seed(d['rot_seed'])
+  out[name + '/rot'] = np.stack([np.random.normal(size=(RC.D_HEAD, c['nh'], c['n_buckets'] // 2)).astype(np.float64)
+                                 .astype(np.float32) for _ in range(B * H)])
+
+  def call(x, qkv, dense):                                          # re-seeded: every call draws the same rotations
+    set_leaves(R, layer, [l for w in qkv for l in leaves(w)] + leaves(dense))
+    np.random.seed(d['rot_seed'])
+    y = layer(x)
+    return np.asarray(y, np.float64), np.asarray(layer.state[1][0], np.int32)
+  y, buckets = call(d['x'], d['qkv'], d['dense'])
+  out[name + '/out'], out[name + '/buckets'] = y, buckets
+
+  def ddir(hi, lo):
+    (yh, bh), (yl, bl) = call(*hi), call(*lo)
+    assert np.array_equal(bh, buckets) and np.array_equal(bl, buckets)   # the differentiated function holds the buckets
+    return np.float64(((yh - yl) * d['dout']).sum() / (2 * EPS))
+  shift = lambda w, dw, e: tuple(a + e * b for a, b in zip(w, dw)) if isinstance(w, tuple) else w + e * dw
+  out[name + '/ddir_x'] = ddir((d['x'] + EPS * d['dir_x'], d['qkv'], d['dense']), (d['x'] - EPS * d['dir_x'], d['qkv'], d['dense']))
+  for i in range(c['num_weights']):
+    mv = lambda e: d['qkv'][:i] + (shift(d['qkv'][i], d['dir_qkv'][i], e),) + d['qkv'][i + 1:]
+    out[name + '/ddir_qkv%d' % i] = ddir((d['x'], mv(EPS), d['dense']), (d['x'], mv(-EPS), d['dense']))
+  out[name + '/ddir_dense'] = ddir((d['x'], d['qkv'], shift(d['dense'], d['dir_dense'], EPS)),
+                                   (d['x'], d['qkv'], shift(d['dense'], d['dir_dense'], -EPS)))
+
+
+def run_reversible(R, name, c, d, out):
+  """ReversibleHalfResidual(LayerNorm(), attention_layer=LSHSelfAttention(...)).forward (reversible.py:296-321)."""
+  B, H, L, D = c['B'], c['H'], c['L'], c['D']
+  attn = R.EA.LSHSelfAttention(n_heads=H, d_qk=RC.D_HEAD, d_v=RC.D_HEAD, causal=c['causal'], chunk_len=c['C'],
+                               n_hashes=c['nh'], n_buckets=c['n_buckets'], use_python_loop=True, n_parallel_heads=1)
+  block = R.reversible.ReversibleHalfResidual(R.normalization.LayerNorm(), attention_layer=attn)
+  sig = R.shapes.ShapeDtype((B, L, D), np.float64)
+  block.init((sig, sig))
+  np.random.seed(d['rot_seed'])
+  out[name + '/rot'] = np.stack([np.random.normal(size=(RC.D_HEAD, c['nh'], c['n_buckets'] // 2)).astype(np.float64)
+                                 .astype(np.float32) for _ in range(B * H)])
+
+  def call(x2, scale, bias, w_q, w_v, w_o):
+    set_leaves(R, block, [scale, bias, w_q, w_v, w_o])
+    np.random.seed(d['rot_seed'])
+    y1, ctx = block((d['x1'], x2))
+    assert np.array_equal(ctx, x2)
+    return np.asarray(y1, np.float64), np.asarray(block.state[1][0], np.int32)
+  base = [d[k] for k in ('x2', 'scale', 'bias', 'w_q', 'w_v', 'w_o')]
+  y1, buckets = call(*base)
+  out[name + '/y1'], out[name + '/buckets'] = y1, buckets
+  for i, key in enumerate(('x2', 'scale', 'bias', 'w_q', 'w_v', 'w_o')):
+    hi = [a + (EPS * d['dir_' + key] if j == i else 0) for j, a in enumerate(base)]
+    lo = [a - (EPS * d['dir_' + key] if j == i else 0) for j, a in enumerate(base)]
+    (yh, bh), (yl, bl) = call(*hi), call(*lo)
+    assert np.array_equal(bh, buckets) and np.array_equal(bl, buckets)
+    out[name + '/ddir_' + key] = np.float64(((yh - yl) * d['ct_y1']).sum() / (2 * EPS))
+
+
+def check_batched_driver(R, out):
+  """The batched driver in Python-loop mode (EA:2261-2561) returns what the `use_reference_code` loop returns."""
+  c, d = RC.CASES['lsh_c128'], RC.inputs('lsh_c128')
+  res = []
+  for kw in (dict(use_reference_code=True), dict(use_python_loop=True, n_parallel_heads=1)):
+    layer = R.EA.LSHSelfAttention(n_heads=c['H'], d_qk=RC.D_HEAD, d_v=RC.D_HEAD, causal=True, chunk_len=c['C'],
+                                  n_hashes=c['nh'], n_buckets=c['n_buckets'], **kw)
+    layer.init(R.shapes.ShapeDtype((c['B'], c['L'], c['D']), np.float64))
+    layer.weights = (d['w_q'], d['w_v'], d['w_o'])
+    np.random.seed(d['rot_seed'])
+    res.append((np.asarray(layer(d['x'])), np.asarray(layer.state[0])))
+  assert np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][1], out['lsh_c128/buckets'])
+  out['lsh_c128/batched_driver_max_abs_diff'] = np.float64(np.abs(res[0][0] - res[1][0]).max())
+
+
 def generate():
   R = ref_live.load()
   out = {}
   for name, c in RC.CASES.items():
-    {'lsh': run_lsh, 'pure': run_pure, 'hash': run_hash}[c['kind']](R, name, c, RC.inputs(name), out)
+    {'lsh': run_lsh, 'pure': run_pure, 'hash': run_hash, 'wrapper': run_wrapper, 'reversible': run_reversible}[c['kind']](R, name, c, RC.inputs(name), out)
+  check_batched_driver(R, out)
   out['stubbed_third_party'] = np.array(','.join(R.stubbed))
   return out
 

@@ -2,7 +2,8 @@
 the tests that compare the oracle / the CUDA path with what the reference returned.  Only NumPy; no oracle, no reference."""
 import numpy as np
 
-# kind 'lsh': LSHSelfAttention (EA:1729);  'pure': PureLSHSelfAttention (EA:2564);  'hash': LSHSelfAttention.hash_vectors alone
+# kind 'lsh': LSHSelfAttention (EA:1729);  'pure': PureLSHSelfAttention (EA:2564);  'hash': LSHSelfAttention.hash_vectors alone;
+# 'wrapper': PureLSHSelfAttentionWrapper (EA:3493);  'reversible': ReversibleHalfResidual around the LSH layer
 CASES = {
     # the tcgen05 kernels' shape (chunk 128, look-back 1, causal, 2 rounds); also run on the GPU
     'lsh_c128': dict(kind='lsh', B=1, H=2, L=512, D=64, C=128, nb=1, na=0, nh=2, n_buckets=8, causal=True, masked=False, seed=101),
@@ -14,6 +15,15 @@ CASES = {
     'pure_c128': dict(kind='pure', B=1, H=2, L=256, D=64, C=128, nb=1, na=0, nh=2, n_buckets=4, causal=True, masked=False, seed=104),
     # n_buckets=None with 2*L/C = 260 > 128 -> factor list [32, 8] (EA:1896-1902)
     'hash_auto_factors': dict(kind='hash', B=1, H=1, L=4160, D=64, C=32, nb=1, na=0, nh=2, n_buckets=None, causal=True, masked=False, seed=105),
+    # PureLSHSelfAttentionWrapper (EA:3493): Dense q, k, v with bias -> (q + k)/2 -> core -> Dense; also run on the GPU
+    'wrapper_c128': dict(kind='wrapper', B=1, H=2, L=256, D=128, C=128, nb=1, na=0, nh=2, n_buckets=4, causal=True, masked=False,
+                         num_weights=3, bias=True, rotary=False, seed=106),
+    # two weights, no bias, rotary position embedding of qk (the hourglass config's settings)
+    'wrapper_rotary': dict(kind='wrapper', B=2, H=2, L=128, D=128, C=64, nb=1, na=0, nh=2, n_buckets=4, causal=True, masked=False,
+                           num_weights=2, bias=False, rotary=True, seed=107),
+    # ReversibleHalfResidual(LayerNorm, attention_layer=LSHSelfAttention) (reversible.py:244-321); also run on the GPU
+    'reversible_c128': dict(kind='reversible', B=1, H=2, L=256, D=256, C=128, nb=1, na=0, nh=2, n_buckets=4, causal=True,
+                            masked=False, seed=108),
 }
 D_HEAD = 64
 
@@ -35,6 +45,18 @@ def inputs(name):
   if c['kind'] == 'pure':
     d.update(qk=n(B * H, L, D_HEAD), v=n(B * H, L, D_HEAD), dout=n(B * H, L, D_HEAD),
              dir_qk=n(B * H, L, D_HEAD), dir_v=n(B * H, L, D_HEAD))
+  elif c['kind'] == 'wrapper':
+    s = 1.0 / np.sqrt(D)
+    nw = c['num_weights']
+    dense = lambda: (n(D, D) * s, n(D) * 0.25) if c['bias'] else n(D, D) * s
+    d.update(x=n(B, L, D), qkv=tuple(dense() for _ in range(nw)), dense=dense(), dout=n(B, L, D), dir_x=n(B, L, D),
+             dir_qkv=tuple(dense() for _ in range(nw)), dir_dense=dense())
+  elif c['kind'] == 'reversible':
+    s = 1.0 / np.sqrt(D)
+    d.update(x1=n(B, L, D), x2=n(B, L, D), ct_y1=n(B, L, D), scale=1.0 + 0.25 * n(D), bias=0.25 * n(D),
+             w_q=n(H, D, D_HEAD) * s, w_v=n(H, D, D_HEAD) * s, w_o=n(H, D_HEAD, D) * 0.125,
+             dir_x2=n(B, L, D), dir_scale=n(D), dir_bias=n(D), dir_w_q=n(H, D, D_HEAD) * s, dir_w_v=n(H, D, D_HEAD) * s,
+             dir_w_o=n(H, D_HEAD, D) * 0.125)
   else:
     s = 1.0 / np.sqrt(D)
     d.update(x=n(B, L, D), w_q=n(H, D, D_HEAD) * s, w_v=n(H, D, D_HEAD) * s, w_o=n(H, D_HEAD, D) * 0.125,

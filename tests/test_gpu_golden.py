@@ -129,3 +129,66 @@ def test_pure_core_against_the_live_reference():
   (dqk, dv), _ = layer.backward(inputs, out, _cu(d['dout']), (), None, layer.state, None)
   _directional_ok(dqk.cpu().numpy(), d['dir_qk'], float(g[name + '/ddir_qk']), 'dqk')
   _directional_ok(dv.cpu().numpy(), d['dir_v'], float(g[name + '/ddir_v']), 'dv')
+
+
+@pytest.mark.parametrize('name', ['wrapper_c128', 'wrapper_rotary'])
+def test_wrapper_against_the_live_reference(name):
+  """PureLSHSelfAttentionWrapper vs the reference's Serial run (reference buckets through the state, as in the reversible
+  backward pass that `forward_and_or_backward` serves, EA:3566-3568)."""
+  import trax_b200
+  from oracle import lsh_oracle as O
+  from tests.golden import reference_cases as RC
+  c, d, g = RC.CASES[name], RC.inputs(name), np.load(os.path.join(HERE, 'reference_live.npz'))
+  wrap = trax_b200.PureLSHSelfAttentionWrapper(
+      n_heads=c['H'], d_qk=64, d_v=64, causal=True, bias=c['bias'], num_weights=c['num_weights'], weights_format='model',
+      rotary_position_emb=c['rotary'], chunk_len=c['C'], n_hashes=c['nh'], n_buckets=c['n_buckets'])
+  wrap.init(trax_b200.ShapeDtype((c['B'], c['L'], c['D'])))
+  dev = lambda w: tuple(_cu(l) for l in w) if isinstance(w, tuple) else _cu(w)
+  weights = (tuple(dev(w) for w in d['qkv']), (), (), dev(d['dense']))
+  state = ((), (torch.from_numpy(g[name + '/buckets']).cuda(), wrap.state[1][1]), (), ())
+  out, _, dx, dw = wrap.forward_and_or_backward(_cu(d['x']), weights, state, None, output_grad=_cu(d['dout']),
+                                                update_state=False)
+  util.assert_close(out.cpu().numpy(), g[name + '/out'], 'out vs the reference')
+  cfg = O.LSHConfig(n_heads=c['H'], d_qk=64, d_v=64, causal=True, masked=False, chunk_len=c['C'], n_chunks_before=1,
+                    n_chunks_after=0, n_hashes=c['nh'], n_buckets=c['n_buckets'])
+  _, _, want_dx, (want_qkv, want_dense) = O.pure_lsh_wrapper(cfg, d['x'], d['qkv'], d['dense'], buckets=g[name + '/buckets'],
+                                                             output_grad=d['dout'], rotary_position_emb=c['rotary'])
+  leaves = lambda w: list(w) if isinstance(w, tuple) else [w]
+  util.assert_close(dx.cpu().numpy(), want_dx, 'dx')
+  _directional_ok(dx.cpu().numpy(), d['dir_x'], float(g[name + '/ddir_x']), 'dx')
+  for i in range(c['num_weights']):
+    for got, want in zip(leaves(dw[0][i]), leaves(want_qkv[i])):
+      util.assert_close(got.cpu().numpy(), want, 'd_qkv[%d]' % i)
+    got = np.concatenate([l.cpu().numpy().ravel() for l in leaves(dw[0][i])])
+    direction = np.concatenate([l.ravel() for l in leaves(d['dir_qkv'][i])])
+    _directional_ok(got, direction, float(g[name + '/ddir_qkv%d' % i]), 'd_qkv[%d]' % i)
+  for got, want in zip(leaves(dw[3]), leaves(want_dense)):
+    util.assert_close(got.cpu().numpy(), want, 'd_dense')
+
+
+def test_reversible_block_against_the_live_reference():
+  """ReversibleHalfResidual(LayerNorm, LSHSelfAttention) vs the reference block's forward output and the derivatives of
+  that forward (tcgen05 shape)."""
+  import trax_b200
+  from tests.golden import reference_cases as RC
+  name = 'reversible_c128'
+  c, d, g = RC.CASES[name], RC.inputs(name), np.load(os.path.join(HERE, 'reference_live.npz'))
+  attn = trax_b200.LSHSelfAttention(n_heads=c['H'], d_qk=64, d_v=64, causal=True, chunk_len=c['C'], n_hashes=c['nh'],
+                                    n_buckets=c['n_buckets'])
+  block = trax_b200.ReversibleHalfResidual(attn)
+  sig = trax_b200.ShapeDtype((c['B'], c['L'], c['D']))
+  block.init((sig, sig))
+  block.weights = ((_cu(d['scale']), _cu(d['bias'])), tuple(_cu(d[k]) for k in ('w_q', 'w_v', 'w_o')))
+  attn._rotations_override = torch.from_numpy(g[name + '/rot'])
+  y1, ctx = block.forward((_cu(d['x1']), _cu(d['x2'])))              # own hash (bf16 projections): output still close
+  mismatch = float((block.state[1][0].cpu().numpy() != g[name + '/buckets']).mean())
+  assert mismatch <= 0.05, 'device buckets differ from the reference at %.2f%% of the tokens' % (100 * mismatch)
+  state = ((), (torch.from_numpy(g[name + '/buckets']).cuda(), block.state[1][1]))
+  y1_ref = _cu(g[name + '/y1'])
+  (rx1, _), ((_, g2), ((ds, db), dw)) = block.reverse_and_grad(
+      (y1_ref, ctx), (_cu(d['ct_y1']), torch.zeros_like(ctx)), block.weights, None, state, None)
+  util.assert_close(rx1.cpu().numpy(), d['x1'], 'x1 reconstructed from the reference y1', rtol=3e-2)
+  for key, got in zip(('x2', 'scale', 'bias', 'w_q', 'w_v', 'w_o'), (g2, ds, db) + tuple(dw)):
+    _directional_ok(got.float().cpu().numpy(), d['dir_' + key], float(g[name + '/ddir_' + key]), 'd' + key)
+  if mismatch == 0.0:
+    util.assert_close(y1.cpu().numpy(), g[name + '/y1'], 'y1 vs the reference')

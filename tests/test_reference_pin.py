@@ -86,3 +86,51 @@ def test_fixture_is_what_the_reference_returns(tmp_path):
       np.testing.assert_array_equal(new[k], old[k], err_msg=k)
     else:
       np.testing.assert_allclose(new[k], old[k], rtol=1e-7 if '/ddir_' in k else 1e-12, atol=1e-12, err_msg=k)
+
+
+def _leaves(w):
+  return list(w) if isinstance(w, tuple) else [w]
+
+
+@pytest.mark.parametrize('name', [n for n, c in RC.CASES.items() if c['kind'] == 'wrapper'])
+def test_oracle_wrapper_matches_live_reference(name):
+  """`PureLSHSelfAttentionWrapper` run as the reference's Serial (Dense / Branch / rotary / SplitIntoHeads / core driver /
+  MergeHeads / Dense are all the reference's code) vs `oracle.pure_lsh_wrapper`."""
+  c, d, g = RC.CASES[name], RC.inputs(name), np.load(FIXTURE)
+  cfg = _cfg(c)
+  out, buckets, _, _ = O.pure_lsh_wrapper(cfg, d['x'], d['qkv'], d['dense'], rotations=g[name + '/rot'],
+                                          rotary_position_emb=c['rotary'])
+  np.testing.assert_array_equal(buckets, g[name + '/buckets'])
+  np.testing.assert_allclose(out, g[name + '/out'], rtol=1e-12, atol=1e-12)
+  _, _, dx, (d_qkv, d_dense) = O.pure_lsh_wrapper(cfg, d['x'], d['qkv'], d['dense'], buckets=g[name + '/buckets'],
+                                                  output_grad=d['dout'], rotary_position_emb=c['rotary'])
+  inner = lambda grads, dirs: sum((a * b).sum() for a, b in zip(_leaves(grads), _leaves(dirs)))
+  np.testing.assert_allclose((dx * d['dir_x']).sum(), float(g[name + '/ddir_x']), rtol=1e-6, atol=1e-7)
+  for i in range(c['num_weights']):
+    np.testing.assert_allclose(inner(d_qkv[i], d['dir_qkv'][i]), float(g[name + '/ddir_qkv%d' % i]), rtol=1e-6, atol=1e-7)
+  np.testing.assert_allclose(inner(d_dense, d['dir_dense']), float(g[name + '/ddir_dense']), rtol=1e-6, atol=1e-7)
+
+
+def test_oracle_reversible_block_matches_live_reference():
+  """`ReversibleHalfResidual(LayerNorm(), attention_layer=LSHSelfAttention)`: forward vs the reference's forward, and the
+  cotangents `reverse_and_grad` must return vs derivatives of that forward (reversible.py:326-412 computes them with
+  jax.vjp of the same two sublayers)."""
+  name = 'reversible_c128'
+  c, d, g = RC.CASES[name], RC.inputs(name), np.load(FIXTURE)
+  cfg, ln, aw = _cfg(c), (d['scale'], d['bias']), (d['w_q'], d['w_v'], d['w_o'])
+  (y1, x2), buckets = O.reversible_half_forward(cfg, d['x1'], d['x2'], ln, aw, g[name + '/rot'])
+  np.testing.assert_array_equal(buckets, g[name + '/buckets'])
+  np.testing.assert_allclose(y1, g[name + '/y1'], rtol=1e-12, atol=1e-12)
+  (x1, _), ((ct1, ct2), ((d_scale, d_bias), dw)) = O.reversible_half_reverse_and_grad(
+      cfg, y1, d['x2'], d['ct_y1'], np.zeros_like(d['x2']), ln, aw, buckets)
+  np.testing.assert_allclose(x1, d['x1'], rtol=1e-12, atol=1e-12)   # the block inverts
+  np.testing.assert_array_equal(ct1, d['ct_y1'])
+  for key, grad in zip(('x2', 'scale', 'bias', 'w_q', 'w_v', 'w_o'), (ct2, d_scale, d_bias) + tuple(dw)):
+    np.testing.assert_allclose((grad * d['dir_' + key]).sum(), float(g[name + '/ddir_' + key]), rtol=1e-6, atol=1e-7,
+                               err_msg=key)
+
+
+def test_reference_batched_driver_equals_its_reference_loop():
+  """Recorded by the generator: the reference's batched driver (Python-loop mode, EA:2261-2561) and its
+  `use_reference_code` loop (EA:2127-2170) return the same output — the oracle restates the latter."""
+  assert float(np.load(FIXTURE)['lsh_c128/batched_driver_max_abs_diff']) <= 1e-12
