@@ -289,3 +289,51 @@ def test_hashing_call_and_recompute_agree_bitwise():
   out1 = layer.forward(x)                                                               # update_state=True
   out2 = layer.forward_and_or_backward(x, layer.weights, layer.state, None, update_state=False)[0]
   assert torch.equal(out1, out2)
+
+
+def test_output_dropout_is_a_shared_column_mask():
+  """EA:1995-1996, 271-280: out = (o w_o) * keep / keep_prob with ONE (d_model,) keep-mask for all positions, heads and
+  examples.  Explicit mask vs the oracle (out, dx, dW); rng-derived mask: same rng -> same mask in the backward call,
+  dropped columns exactly zero, other rng -> other mask."""
+  import trax_b200
+  B, L, D = 2, 512, 128
+  cfg = util.make_cfg(H=2, C=128, nh=2, n_buckets=8)
+  x, weights, rot, dout, _ = _case(31, B, L, D, cfg, torch.float32)
+  rate = 0.25
+  keep = np.random.default_rng(5).random(D) < 1 - rate
+  mult = keep / (1 - rate)
+  want_out, buckets, _, _ = O.forward_and_or_backward(cfg, x, weights, rotations=rot, out_keep=mult)
+  _, _, want_dx, want_dw = O.forward_and_or_backward(cfg, x, weights, buckets=buckets, output_grad=dout, out_keep=mult,
+                                                     update_state=False)
+  layer = trax_b200.LSHSelfAttention(n_heads=2, d_qk=64, d_v=64, causal=True, chunk_len=128, n_hashes=2, n_buckets=8,
+                                     output_dropout=rate)
+  layer.init(trax_b200.ShapeDtype((B, L, D)))
+  w_d = tuple(torch.from_numpy(w).cuda() for w in weights)
+  x_d, g_d = torch.from_numpy(x).cuda(), torch.from_numpy(dout).cuda()
+  state = (torch.from_numpy(buckets).cuda(), layer.state[1])
+  layer._out_keep_override = keep
+  out, _, dx, dw = layer.forward_and_or_backward(x_d, w_d, state, None, output_grad=g_d, update_state=False)
+  util.assert_close(out.cpu().numpy(), want_out, 'out')
+  assert (out[..., torch.from_numpy(~keep).cuda()] == 0).all()
+  util.assert_close(dx.cpu().numpy(), want_dx, 'dx')
+  for name, g, w in zip(('dw_q', 'dw_v', 'dw_o'), dw, want_dw):
+    util.assert_close(g.cpu().numpy(), w, name)
+  assert (dw[2][..., torch.from_numpy(~keep).cuda()] == 0).all()
+  # rng-derived masks
+  layer._out_keep_override = None
+  with pytest.raises(ValueError):
+    layer.forward_and_or_backward(x_d, w_d, state, None, update_state=False)
+  rng_a, rng_b = np.array([1, 2], np.uint32), np.array([1, 3], np.uint32)
+  out_a, _, _, _ = layer.forward_and_or_backward(x_d, w_d, state, rng_a, update_state=False)
+  out_a2, _, _, dw_a = layer.forward_and_or_backward(x_d, w_d, state, rng_a, output_grad=g_d, update_state=False)
+  out_b, _, _, _ = layer.forward_and_or_backward(x_d, w_d, state, rng_b, update_state=False)
+  assert torch.equal(out_a, out_a2)
+  dropped_a, dropped_b = (out_a == 0).all(dim=0).all(dim=0), (out_b == 0).all(dim=0).all(dim=0)
+  assert 0 < int(dropped_a.sum()) < D // 2 and not torch.equal(dropped_a, dropped_b)
+  assert (dw_a[2][..., dropped_a] == 0).all() and (dw_a[2][..., ~dropped_a] != 0).any()
+  # eval mode switches dropout off (EA:1790-1795)
+  ev = trax_b200.LSHSelfAttention(n_heads=2, d_qk=64, d_v=64, causal=True, chunk_len=128, n_hashes=2, n_buckets=8,
+                                  output_dropout=rate, mode='eval')
+  ev.init(trax_b200.ShapeDtype((B, L, D)))
+  out_e, _, _, _ = ev.forward_and_or_backward(x_d, w_d, state, None, update_state=False)
+  assert not (out_e == 0).all(dim=0).all(dim=0).any()

@@ -14,7 +14,8 @@ Kept from the reference (names, argument meaning, error behaviour):
     attributes (base.py:675-706).
 Not provided (raise, never silently differ): mode='predict' (EA:1999-2109, out of scope for this
 tier), `use_reference_code=True` (would be a CPU path), `bias=True` (broken in the reference too:
-EA:1921 unpacks exactly three weights), dropout rates > 0 (keep-masks need jax.random's bits).
+EA:1921 unpacks exactly three weights), attention_dropout > 0 (needs the keep-mask inside the kernels).  output_dropout
+is supported (a column scaling of w_o; the mask is a function of `rng`, not jax.random's bits).
 
 torch plays the role JAX plays for the reference: device memory, streams, autograd glue
 (`torch.autograd.Function` ≙ `fastmath.custom_vjp` in base.py:644-673).
@@ -227,9 +228,12 @@ class LSHSelfAttention:
       self._attention_dropout, self._output_dropout = attention_dropout, output_dropout
     else:
       self._attention_dropout = self._output_dropout = 0.0
-    if self._attention_dropout or self._output_dropout:
+    if self._attention_dropout:
       raise NotImplementedError(
-          'attention_dropout/output_dropout > 0 need jax.random keep-masks (EA:254-262, 271-280); not supported')
+          'attention_dropout > 0 needs the (chunk_len, window) keep-mask of EA:254-262 inside the attention kernels; '
+          'not supported yet')
+    if not 0.0 <= self._output_dropout < 1.0:
+      raise ValueError('output_dropout must be in [0, 1)')
     self._n_hashes = n_hashes
     self._n_buckets = n_buckets
     self._max_length_for_buckets = max_length_for_buckets
@@ -237,6 +241,7 @@ class LSHSelfAttention:
     self._state = ()
     self._rng = None
     self._rotations_override = None     # tests / a JAX host inject explicit rotations here
+    self._out_keep_override = None      # likewise an explicit (d_model,) bool keep-mask for output dropout
 
   # ---- attribute discipline (base.py:675-706) -----------------------------------------------------
   def __setattr__(self, attr, value):
@@ -387,6 +392,23 @@ class LSHSelfAttention:
     return out, holder['new_state']
 
   # ---- the batched driver (EA:2261-2561) -----------------------------------------------------------
+  def _output_multiplier(self, rng, d_model, dev):
+    """keep / keep_prob of `apply_broadcasted_dropout` (EA:271-280) as a (d_model,) fp32 device tensor, or None.  The
+    keep-mask is a deterministic function of `rng` (so the backward call, which gets the same rng, EA:2251-2259, re-draws
+    the same mask) but not jax.random's bit stream — like the hash rotations, it can be supplied explicitly."""
+    if not self._output_dropout:
+      return None
+    keep_prob = 1.0 - self._output_dropout
+    if self._out_keep_override is not None:
+      keep = torch.as_tensor(np.asarray(self._out_keep_override)).to(torch.bool).reshape(d_model)
+    else:
+      if rng is None:
+        raise ValueError('output_dropout > 0 needs an rng (EA:274)')
+      key = np.asarray(rng.cpu() if isinstance(rng, torch.Tensor) else rng).astype(np.uint32).reshape(-1)
+      gen = torch.Generator().manual_seed(((int(key[0]) << 32) | int(key[-1])) ^ 0x6f75745f64726f70)   # 'out_drop'
+      keep = torch.rand(d_model, generator=gen) < keep_prob
+    return (keep.to(torch.float32) / keep_prob).to(dev)
+
   def _dims(self, batch_size, seqlen, d_model, act_dtype):
     factors = ops.bucket_factors(self._n_buckets, seqlen, self._chunk_len)     # EA:1890-1902
     return _lib.make_dims(batch_size, self._n_heads, seqlen, d_model, self._d_qk, self._d_v,
@@ -402,7 +424,6 @@ class LSHSelfAttention:
     Tensors may live on the GPU (no copies) or on the host (pinned or pageable): host inputs are
     copied to cuda:current, results copied back — the e2e path bench.py times.
     """
-    del rng   # only dropout consumes it (EA:1920) and dropout is rejected at construction
     have_single_input = not isinstance(inputs, (tuple, list))
     if have_single_input:
       inputs = (inputs,)
@@ -430,6 +451,12 @@ class LSHSelfAttention:
     if self._masked:
       mask_d = to_dev(inputs[1]).to(torch.uint8).contiguous()
     w_q, w_v, w_o = (to_dev(w).to(torch.float32).contiguous() for w in weights)
+    out_mult = self._output_multiplier(rng, int(x_d.shape[2]), dev)
+    if out_mult is not None:
+      # EA:1995-1996: (o w_o) * m with m of shape (d_model,) shared by every position, head and example (EA:271-280, same
+      # rng for all units EA:2334-2335) == o (w_o * m): the mask is folded into the packed weight in both passes and
+      # into dw_o afterwards; the kernels are unchanged.
+      w_o = w_o * out_mult
     buckets, hash_rng = state
     batch_size, seqlen, d_model = (int(s) for s in x_d.shape)
     if tuple(w_q.shape) != (self._n_heads, d_model, self._d_qk) or tuple(w_o.shape) != (self._n_heads, self._d_v, d_model):
@@ -490,6 +517,8 @@ class LSHSelfAttention:
           ctypes.byref(dims), ops._ptr(x_d), ops._ptr(w_q), ops._ptr(w_v), ops._ptr(w_o), ops._ptr(mask_d),
           ops._ptr(buckets_d), buckets_d.stride(0), ops._ptr(g_d), ops._ptr(out_d), ops._ptr(dx), ops._ptr(dw_q),
           ops._ptr(dw_v), ops._ptr(dw_o), ops._ptr(ws), ws.numel(), stream), 'lsh_layer_bwd')
+      if out_mult is not None:
+        dw_o.mul_(out_mult)
       if _GRAD_ALLREDUCE['on']:
         from trax_b200 import dp
         dp.allreduce_mean_((dw_q, dw_v, dw_o))
