@@ -134,3 +134,15 @@ def test_reference_batched_driver_equals_its_reference_loop():
   """Recorded by the generator: the reference's batched driver (Python-loop mode, EA:2261-2561) and its
   `use_reference_code` loop (EA:2127-2170) return the same output — the oracle restates the latter."""
   assert float(np.load(FIXTURE)['lsh_c128/batched_driver_max_abs_diff']) <= 1e-12
+
+
+@pytest.mark.skipif(not ref_live.available(), reason='the reference checkout exists only in the build container')
+def test_randomised_sweep_against_the_live_reference():
+  """oracle/ref_live_sweep.py: 32 random option combinations (incl. the reference tests' own d_qk 7 / d_v 17 / chunk 5
+  shape, look-back 0..2, look-ahead, masks, factor lists, max_length_for_buckets): buckets equal, outputs to 1e-11,
+  VJP vs a central difference of the reference's forward."""
+  repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  r = subprocess.run([sys.executable, os.path.join(repo, 'oracle', 'ref_live_sweep.py'), '32', '7'], cwd=repo, timeout=900,
+                     capture_output=True, text=True)
+  assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+  assert r.stdout.count('\nok') + r.stdout.startswith('ok') == 32
