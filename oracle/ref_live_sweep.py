@@ -2,7 +2,7 @@
 against the reference's own code (see ref_live.py) over the layer's options: causal / bidirectional, padding mask,
 look-back 0..2 and look-ahead 0..1 chunks, 1..3 hash rounds, bucket counts given as int, factor list or None, head sizes
 and chunk lengths that are NOT the kernels' (the reference's tests use d_qk 7, d_v 17, chunk 5, seqlen 10, d_model 13 —
-efficient_attention_test.py:138-151), `max_length_for_buckets`.  For each case: bucket ids equal, float64 outputs equal
+efficient_attention_test.py:138-151), `max_length_for_buckets`, and — every fourth case — attention + output dropout.  For each case: bucket ids equal, float64 outputs equal
 to 1e-11, and the analytic VJP equal to a central difference of the reference's forward along one random direction.
 
     python oracle/ref_live_sweep.py [n_cases] [seed]        # prints one line per case, exits non-zero on a mismatch
@@ -80,6 +80,40 @@ def run_case(R, c, rng):
   return n_diff, err, vjp_err
 
 
+def run_dropout_case(R, c, rng):
+  """Attention dropout (EA:254-262: one (chunk_len, window) keep-mask broadcast over chunks, applied after the softmax,
+  the log-sum-exp untouched) and output dropout (EA:271-280), one unit at a time with the buckets held.  The reference's
+  NumPy backend draws the masks with numpy.random.binomial, so seeding reproduces them for the oracle."""
+  H, L, D = c['H'], c['L'], c['D']
+  a_rate, o_rate = 0.3, 0.25
+  kw = dict(n_heads=H, d_qk=c['dq'], d_v=c['dv'], causal=c['causal'], masked=False, chunk_len=c['C'],
+            n_chunks_before=c['nb'], n_chunks_after=c['na'], n_hashes=c['nh'], n_buckets=c['n_buckets'])
+  layer = R.EA.LSHSelfAttention(use_reference_code=True, attention_dropout=a_rate, output_dropout=o_rate, mode='train', **kw)
+  cfg = O.LSHConfig(**kw)
+  x, direction, dout = (rng.standard_normal((L, D)) for _ in range(3))
+  w = (rng.standard_normal((D, c['dq'])) / np.sqrt(D), rng.standard_normal((D, c['dv'])) / np.sqrt(D),
+       rng.standard_normal((c['dv'], D)) / np.sqrt(c['dv']))
+  factors = O.bucket_factors(c['n_buckets'], L, c['C'])
+  nb_total = int(np.prod(factors))
+  buckets = (rng.integers(0, nb_total, size=(c['nh'], L)) + np.arange(c['nh'])[:, None] * nb_total).astype(np.int32).reshape(-1)
+  seed = int(rng.integers(1 << 30))
+  key = np.zeros(2, np.uint32)                                       # the NumPy backend ignores it; it must not be None
+
+  def live(xx):
+    np.random.seed(seed)
+    return np.asarray(layer.forward_unbatched(xx, weights=w, state=(buckets, None), rng=key, update_state=False)[0])
+  y = live(x)
+  window = c['C'] * (1 + c['nb'] + c['na'])
+  np.random.seed(seed)
+  attn_keep = np.random.binomial(1, 1 - a_rate, size=(c['C'], window)) / (1 - a_rate)
+  out_keep = np.random.binomial(1, 1 - o_rate, size=(D,)) / (1 - o_rate)
+  r = O.forward_unit(cfg, x, *w, buckets=buckets, attn_keep=attn_keep, out_keep=out_keep)
+  err = float(np.abs(r.out - y).max())
+  fd = float(((live(x + EPS * direction) - live(x - EPS * direction)) * dout).sum() / (2 * EPS))
+  an = float((O.backward_unit(cfg, r, dout)[0] * direction).sum())
+  return 0, err, abs(an - fd) / max(abs(fd), 1e-3)
+
+
 if __name__ == '__main__':
   n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 24
   rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
@@ -87,7 +121,9 @@ if __name__ == '__main__':
   bad = 0
   for i in range(n_cases):
     c = draw_case(rng, i)
-    n_diff, err, vjp_err = run_case(R, c, rng)
+    dropout = i % 4 == 3 and not c['masked']
+    n_diff, err, vjp_err = (run_dropout_case if dropout else run_case)(R, c, rng)
+    c = dict(c, dropout=dropout)
     ok = n_diff == 0 and err <= 1e-11 and vjp_err <= 1e-5
     bad += not ok
     print('%s case %2d buckets_differ=%d out_err=%.1e vjp_rel_err=%.1e %s' % ('ok  ' if ok else 'FAIL', i, n_diff, err, vjp_err, c))
