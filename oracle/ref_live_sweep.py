@@ -2,7 +2,8 @@
 against the reference's own code (see ref_live.py) over the layer's options: causal / bidirectional, padding mask,
 look-back 0..2 and look-ahead 0..1 chunks, 1..3 hash rounds, bucket counts given as int, factor list or None, head sizes
 and chunk lengths that are NOT the kernels' (the reference's tests use d_qk 7, d_v 17, chunk 5, seqlen 10, d_model 13 —
-efficient_attention_test.py:138-151), `max_length_for_buckets`, and — every fourth case — attention + output dropout.  For each case: bucket ids equal, float64 outputs equal
+efficient_attention_test.py:138-151), `max_length_for_buckets`, and — every fourth case — attention + output dropout;
+every fourth case instead checks `oracle/self_attention_oracle.py` against the reference's `SelfAttention` (EA:936).  For each case: bucket ids equal, float64 outputs equal
 to 1e-11, and the analytic VJP equal to a central difference of the reference's forward along one random direction.
 
     python oracle/ref_live_sweep.py [n_cases] [seed]        # prints one line per case, exits non-zero on a mismatch
@@ -114,6 +115,52 @@ def run_dropout_case(R, c, rng):
   return 0, err, abs(an - fd) / max(abs(fd), 1e-3)
 
 
+def run_self_attention_case(R, rng, i):
+  """`SelfAttention` (EA:936, the chunked local attention ReformerLM interleaves with the LSH layer) vs
+  `oracle/self_attention_oracle.py`: both share_qk variants, chunked / unchunked, causal, masked."""
+  from oracle import self_attention_oracle as S
+  share_qk, causal, masked = bool(i % 2), bool(rng.random() < 0.6), bool(rng.random() < 0.4)
+  chunked = rng.random() < 0.8
+  C = int(rng.choice([4, 8, 16]))
+  L = C * int(rng.choice([2, 3, 4]))
+  B, H, D, dq, dv = int(rng.choice([1, 2])), int(rng.choice([1, 2, 3])), int(rng.choice([8, 13])), int(rng.choice([4, 7])), int(rng.choice([4, 9]))
+  kw = dict(n_heads=H, d_qk=dq, d_v=dv, share_qk=share_qk, causal=causal, masked=masked, chunk_len=C if chunked else None,
+            n_chunks_before=int(rng.choice([0, 1, 2])) if chunked else 0,
+            n_chunks_after=int(rng.choice([0, 1])) if chunked and not causal else 0)
+  layer = R.EA.SelfAttention(use_reference_code=True, **kw)
+  x, dout, direction = (rng.standard_normal((B, L, D)) for _ in range(3))
+  mask = (rng.random((B, L)) > 0.3) if masked else None
+  if mask is not None:
+    dout = dout * mask[:, :, None]
+  n_w = 3 if share_qk else 4
+  w = tuple(rng.standard_normal((H, D, dq)) / np.sqrt(D) for _ in range(n_w - 2)) + (
+      rng.standard_normal((H, D, dv)) / np.sqrt(D), rng.standard_normal((H, dv, D)) / np.sqrt(dv))
+  sig = R.shapes.ShapeDtype((B, L, D), np.float64)
+  layer.init((sig, R.shapes.ShapeDtype((B, L), np.bool_)) if masked else sig)
+  layer.weights = w
+
+  def live(xx):
+    return np.asarray(layer((xx, mask)) if masked else layer(xx))
+  cfg = S.SelfAttentionConfig(**kw)
+  out, dx, _ = S.forward_and_or_backward(cfg, x, w, mask=mask, output_grad=dout)
+  err = float(np.abs(out - live(x)).max())
+  fd = float(((live(x + EPS * direction) - live(x - EPS * direction)) * dout).sum() / (2 * EPS))
+  an = float((dx * direction).sum())
+  # weight gradients along one direction per weight
+  werr = 0.0
+  for j in range(n_w):
+    dw = rng.standard_normal(w[j].shape)
+    def shifted(e):
+      layer.weights = tuple(a + (e * dw if jj == j else 0) for jj, a in enumerate(w))
+      y = live(x)
+      layer.weights = w
+      return y
+    fdw = float(((shifted(EPS) - shifted(-EPS)) * dout).sum() / (2 * EPS))
+    gw = S.forward_and_or_backward(cfg, x, w, mask=mask, output_grad=dout)[2][j]
+    werr = max(werr, abs(float((gw * dw).sum()) - fdw) / max(abs(fdw), 1e-3))
+  return 0, err, max(abs(an - fd) / max(abs(fd), 1e-3), werr), dict(kw, B=B, L=L, D=D, kind='SelfAttention')
+
+
 if __name__ == '__main__':
   n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 24
   rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
@@ -121,9 +168,12 @@ if __name__ == '__main__':
   bad = 0
   for i in range(n_cases):
     c = draw_case(rng, i)
-    dropout = i % 4 == 3 and not c['masked']
-    n_diff, err, vjp_err = (run_dropout_case if dropout else run_case)(R, c, rng)
-    c = dict(c, dropout=dropout)
+    if i % 4 == 2:
+      n_diff, err, vjp_err, c = run_self_attention_case(R, rng, i // 4)
+    else:
+      dropout = i % 4 == 3 and not c['masked']
+      n_diff, err, vjp_err = (run_dropout_case if dropout else run_case)(R, c, rng)
+      c = dict(c, dropout=dropout)
     ok = n_diff == 0 and err <= 1e-11 and vjp_err <= 1e-5
     bad += not ok
     print('%s case %2d buckets_differ=%d out_err=%.1e vjp_rel_err=%.1e %s' % ('ok  ' if ok else 'FAIL', i, n_diff, err, vjp_err, c))
