@@ -27,6 +27,14 @@
 
 #include <stdlib.h>
 
+// k-step loops of the MMA issuer: fully unrolled by default (immediate descriptor offsets); -DLSH_BWD_ROLL_ISSUE rolls
+// them (A/B hook for the issuer's instruction footprint).
+#ifdef LSH_BWD_ROLL_ISSUE
+#define BT_ISSUE_UNROLL _Pragma("unroll 1")
+#else
+#define BT_ISSUE_UNROLL _Pragma("unroll")
+#endif
+
 namespace lsh {
 
 constexpr int BT_C = 128;
@@ -231,9 +239,9 @@ __global__ void __launch_bounds__(BT_THREADS, 1) attend_bwd_tc_kernel(const Atte
       const uint32_t ka = desc_lo(kt, 16), qb = desc_lo(qt + h * 8192, 16);
       const uint32_t va = desc_lo(kt + BT_C * 128, 16), db = desc_lo(qt + 2 * BT_C * 128 + h * 8192, 16);
       if (elect_one()) {
-#pragma unroll
+BT_ISSUE_UNROLL
         for (int ks = 0; ks < 4; ++ks) umma_ss2(r, ka + ks * 2, HI, qb + ks * 2, HI, BT_IDESC_ST, ks > 0);
-#pragma unroll
+BT_ISSUE_UNROLL
         for (int ks = 0; ks < 4; ++ks) umma_ss2(r + 64, va + ks * 2, HI, db + ks * 2, HI, BT_IDESC_ST, ks > 0);
         umma_commit(&sh.st_full[h]);
       }
@@ -280,9 +288,9 @@ __global__ void __launch_bounds__(BT_THREADS, 1) attend_bwd_tc_kernel(const Atte
           if (cur.kv_first && h == 0) mbar_wait(&sh.kv_free, (cur.rit & 1) ^ 1);   // epilogue warpgroup has drained dK^/dV/dQ
           const uint32_t fresh = (cur.kv_first && h == 0) ? 1u : 0u;
           if (elect_one()) {
-#pragma unroll
+BT_ISSUE_UNROLL
             for (int kk = 0; kk < 4; ++kk) umma_ts2(tmem + 320, r + kk * 8, dob + kk * 128, HI, BT_IDESC_KV, !(fresh && kk == 0));
-#pragma unroll
+BT_ISSUE_UNROLL
             for (int kk = 0; kk < 4; ++kk) umma_ts2(tmem + 256, r + 64 + kk * 8, qb + kk * 128, HI, BT_IDESC_KV, !(fresh && kk == 0));
           }
           __syncwarp();
@@ -303,7 +311,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) attend_bwd_tc_kernel(const Atte
         if (elect_one()) {
           if (cur.do_kv && cur.iter_end) umma_commit(&sh.kv_full);
           if (cur.do_dq) {
-#pragma unroll
+BT_ISSUE_UNROLL
             for (int kk = 0; kk < 8; ++kk) umma_ss2(dq_t, a0 + kk * 128, HI, kb + kk * 128, HI, BT_IDESC_DQ, !(cur.dq_fresh && kk == 0));
           }
           umma_commit(&sh.dsm_free[cur.n & 1]);
