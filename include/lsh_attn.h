@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define LSH_ATTN_ABI_VERSION 1
+#define LSH_ATTN_ABI_VERSION 2
 
 enum { LSH_DTYPE_F32 = 0, LSH_DTYPE_BF16 = 1 };
 
@@ -59,6 +59,8 @@ typedef struct LshAttnDims {
 } LshAttnDims;
 
 int lsh_attn_abi_version(void);
+/* Content hash of the sources this library was compiled from (trax_b200/build.py); the loader refuses a stale build. */
+const char *lsh_attn_source_hash(void);
 const char *lsh_attn_last_error(void);
 
 /* 0 when the shape is supported by the sm_100a kernels; otherwise non-zero + message.  There is no
@@ -103,8 +105,13 @@ int lsh_attend_fwd(const LshAttnDims *dims, const void *qv_bf16, const int32_t *
 /* Internal order used by the tcgen05 attention kernels (chunk_len 128): sticker2 = sticker with every 128-slot
  * chunk re-ordered by token position (ticker % L, ascending; ties keep slot order).  Attention inside a chunk
  * window (EA:209-268) is a sum over keys and its rows are un-sorted by ticker (EA:1985-1986), so results do not
- * depend on the order inside a chunk; the reference's sticker / undo_sort (EA:1951-1956) are untouched. */
-int lsh_chunk_possort(const LshAttnDims *dims, const int32_t *sticker, int32_t *sticker2, void *stream);
+ * depend on the order inside a chunk; the reference's sticker / undo_sort (EA:1951-1956) are untouched.
+ * bounds (B*H, nh*L) int32, may be NULL: per row of sticker2, where the row's position falls inside the two neighbour
+ * chunks of its unit (cyclic, EA:137-141): cnt_prev | eq_prev << 8 | cnt_next << 16 | eq_next << 24 with cnt = number of
+ * the neighbour's tokens at a lower position (0..128), eq = the neighbour holds the same position (the token's copy from
+ * the adjacent hash round).  These are the column intervals the causal / self masks of EA:150-155 reduce to. */
+int lsh_chunk_possort(const LshAttnDims *dims, const int32_t *sticker, int32_t *sticker2, int32_t *bounds,
+                      void *stream);
 
 /* EA:1988-1992 multi-round combine; also emits lse_tot = logsumexp_h(logits) (BH, L) when non-null. */
 int lsh_combine_fwd(const LshAttnDims *dims, const void *o_rounds_bf16, const float *logits,

@@ -119,12 +119,25 @@ def test_chunk_possort_bit_exact(L, nh, nbk):
   buckets = util.random_valid_buckets(rng, BH, nh, L, nbk)
   dims = _dims(1, BH, L, 64, 128, 1, 0, nh, [nbk])
   sticker, _ = ops.sort(dims, _cuda(buckets))
-  s2 = ops.chunk_possort(dims, sticker).cpu().numpy()
+  s2, bounds = ops.chunk_possort(dims, sticker, with_bounds=True)
+  s2, bounds = s2.cpu().numpy(), bounds.cpu().numpy()
   st = sticker.cpu().numpy()
   for u in range(BH):
     ch = st[u].reshape(-1, 128)
     order = np.argsort(ch % L, axis=1, kind='stable')
     np.testing.assert_array_equal(s2[u].reshape(-1, 128), np.take_along_axis(ch, order, axis=1))
+    if L % 128:
+      continue      # the interval bounds are only defined (and used) when positions inside a chunk are unique
+    # neighbour-chunk bounds: cnt_prev | eq_prev << 8 | cnt_next << 16 | eq_next << 24 (cyclic inside the unit)
+    pos = s2[u].reshape(-1, 128) % L
+    bd = bounds[u].reshape(-1, 128)
+    nc = pos.shape[0]
+    for c in range(nc):
+      for name, other, shift in (('prev', pos[(c - 1) % nc], 0), ('next', pos[(c + 1) % nc], 16)):
+        cnt = (other[None, :] < pos[c][:, None]).sum(1)
+        eq = (other[None, :] == pos[c][:, None]).any(1)
+        np.testing.assert_array_equal((bd[c] >> shift) & 0xff, cnt, err_msg='%s cnt chunk %d' % (name, c))
+        np.testing.assert_array_equal((bd[c] >> (shift + 8)) & 1, eq.astype(np.int64), err_msg='%s eq chunk %d' % (name, c))
 
 
 def test_sort_rejects_int32_key_overflow():

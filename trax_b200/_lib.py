@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('LSH_ATTN_LIB') or os.path.join(_HERE, 'liblsh_attn_b200.so')   # override: kernel experiments
 
 LSH_DTYPE_F32, LSH_DTYPE_BF16 = 0, 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class LshAttnDims(ctypes.Structure):
@@ -29,6 +29,7 @@ _P, _I64, _SZ, _I = ctypes.c_void_p, ctypes.c_int64, ctypes.c_size_t, ctypes.c_i
 _D = ctypes.POINTER(LshAttnDims)
 SIGNATURES = {
     'lsh_attn_abi_version': (_I, []),
+    'lsh_attn_source_hash': (ctypes.c_char_p, []),
     'lsh_attn_last_error': (ctypes.c_char_p, []),
     'lsh_attn_check_dims': (_I, [_D]),
     'lsh_pack_weights': (_I, [_D, _P, _P, _P, _P, _P, _P]),
@@ -39,7 +40,7 @@ SIGNATURES = {
     'lsh_sort': (_I, [_D, _P, _I64, _P, _P, _P, _SZ, _P]),
     'lsh_attend_fwd_workspace_bytes': (_SZ, [_D]),
     'lsh_attend_fwd': (_I, [_D, _P, _P, _P, _P, _P, _P, _SZ, _P]),
-    'lsh_chunk_possort': (_I, [_D, _P, _P, _P]),
+    'lsh_chunk_possort': (_I, [_D, _P, _P, _P, _P]),
     'lsh_combine_fwd': (_I, [_D, _P, _P, _P, _P, _P]),
     'lsh_project_out': (_I, [_D, _P, _P, _P, _P, _SZ, _P]),
     'lsh_attend_bwd_workspace_bytes': (_SZ, [_D]),
@@ -67,14 +68,16 @@ def load():
   global _lib
   if _lib is not None:
     return _lib
-  if not os.path.exists(LIB_PATH):
-    from trax_b200 import build as _build  # lazy: needs nvcc
+  from trax_b200 import build as _build
+  override = bool(os.environ.get('LSH_ATTN_LIB'))      # an explicitly named library (kernel A/B experiments) is taken as is
+  if not override and _build.needs_build():
+    # missing, or compiled from other sources than the ones beside it (content hash): rebuild, never load a stale library
     try:
       _build.build()
     except Exception as e:  # pylint: disable=broad-except
       raise ImportError(
-          'trax_b200: %s is missing and could not be built (%s). There is no CPU fallback.'
-          % (LIB_PATH, e)) from e
+          'trax_b200: %s is %s and could not be built (%s). There is no CPU fallback.'
+          % (LIB_PATH, 'stale' if os.path.exists(LIB_PATH) else 'missing', e)) from e
   try:
     import torch  # noqa: F401  pylint: disable=unused-import  (loads the cuBLAS/cudart the .so links to)
   except ImportError:
@@ -85,6 +88,9 @@ def load():
     fn.restype, fn.argtypes = res, args
   if lib.lsh_attn_abi_version() != ABI_VERSION:
     raise ImportError('trax_b200: ABI version mismatch (%d != %d)' % (lib.lsh_attn_abi_version(), ABI_VERSION))
+  if not override and lib.lsh_attn_source_hash().decode() != _build.source_hash():
+    raise ImportError('trax_b200: %s was compiled from different sources (%s != %s)'
+                      % (LIB_PATH, lib.lsh_attn_source_hash().decode(), _build.source_hash()))
   _lib = lib
   return lib
 

@@ -35,26 +35,44 @@ def sources():
   return sorted(glob.glob(os.path.join(CSRC, '*.cu')))
 
 
+def source_hash():
+  """Content hash of everything the library is compiled from (+ the flags): embedded in the library
+  (`lsh_attn_source_hash()`) and stored beside it, so that a stale build is detected by content, not by mtime."""
+  import hashlib
+  h = hashlib.sha256()
+  deps = sources() + sorted(glob.glob(os.path.join(CSRC, '*.cuh'))) + [os.path.join(HERE, '..', 'include', 'lsh_attn.h')]
+  for path in deps:
+    h.update(os.path.basename(path).encode())
+    with open(path, 'rb') as f:
+      h.update(f.read())
+  h.update(' '.join(ARCH + FLAGS).encode())
+  return h.hexdigest()[:16]
+
+
+def built_hash():
+  try:
+    with open(LIB + '.hash') as f:
+      return f.read().strip()
+  except OSError:
+    return None
+
+
 def needs_build():
-  if not os.path.exists(LIB):
-    return True
-  t = os.path.getmtime(LIB)
-  deps = sources() + glob.glob(os.path.join(CSRC, '*.cuh')) + [
-      os.path.join(HERE, '..', 'include', 'lsh_attn.h')]
-  return any(os.path.getmtime(s) > t for s in deps)
+  return not os.path.exists(LIB) or built_hash() != source_hash()
 
 
 def build(force=False, verbose=False):
   if not force and not needs_build():
     return LIB
   objs = []
+  src_hash = source_hash()
   odir = os.path.join(HERE, 'build' if not os.environ.get('LSH_LIB_OUT') else os.path.join('build', os.path.basename(LIB)))
   os.makedirs(odir, exist_ok=True)
   procs = []
   for src in sources():
     obj = os.path.join(odir, os.path.basename(src)[:-3] + '.o')
     cmd = [NVCC] + ARCH + [f for f in FLAGS if not f.startswith('--use_fast_math')] + [
-        '-Xptxas', '-v' if verbose else '-warn-spills', '-c', src, '-o', obj]
+        '-Xptxas', '-v' if verbose else '-warn-spills', '-DLSH_SRC_HASH="%s"' % src_hash, '-c', src, '-o', obj]
     procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     objs.append(obj)
   failed = False
@@ -80,6 +98,8 @@ def build(force=False, verbose=False):
       break
   link += [cublas or '-lcublas', '-lcudart']
   subprocess.check_call(link)
+  with open(LIB + '.hash', 'w') as f:
+    f.write(src_hash + '\n')
   return LIB
 
 

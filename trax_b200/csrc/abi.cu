@@ -39,10 +39,10 @@ int sort_run(const LshAttnDims &, const int32_t *, int64_t, int32_t *, int32_t *
 int attend_fwd_run(const LshAttnDims &, const void *, const int32_t *, const uint8_t *, void *, int64_t, int64_t,
                    int64_t, int64_t, float *, const FwdAux *, cudaStream_t);
 int combine_fwd_run(const LshAttnDims &, const void *, const float *, void *, float *, cudaStream_t);
-int chunk_possort_run(const LshAttnDims &, const int32_t *, int32_t *, cudaStream_t);
+int chunk_possort_run(const LshAttnDims &, const int32_t *, int32_t *, int32_t *, cudaStream_t);
 size_t attend_bwd_workspace_bytes(const LshAttnDims &);
 int attend_bwd_run(const LshAttnDims &, const void *, const int32_t *, const uint8_t *, const void *, const float *,
-                   const void *, const float *, const int32_t *, void *, void *, size_t, cudaStream_t);
+                   const void *, const float *, const int32_t *, const int32_t *, void *, void *, size_t, cudaStream_t);
 int pack_weights_run(const LshAttnDims &, const float *, const float *, const float *, void *, void *, cudaStream_t);
 int f32_to_bf16_run(const float *, void *, int64_t, cudaStream_t);
 int unpack_dwqv_run(const LshAttnDims &, const float *, float *, float *, cudaStream_t);
@@ -234,6 +234,10 @@ using namespace lsh;
 extern "C" {
 
 int lsh_attn_abi_version(void) { return LSH_ATTN_ABI_VERSION; }
+#ifndef LSH_SRC_HASH
+#define LSH_SRC_HASH "unknown"
+#endif
+const char *lsh_attn_source_hash(void) { return LSH_SRC_HASH; }
 const char *lsh_attn_last_error(void) { return g_err; }
 int64_t lsh_attn_launch_count(int reset) {
   int64_t v = g_launches;
@@ -295,10 +299,10 @@ int lsh_attend_fwd(const LshAttnDims *dims, const void *qv, const int32_t *stick
                         static_cast<cudaStream_t>(stream));
 }
 
-int lsh_chunk_possort(const LshAttnDims *dims, const int32_t *sticker, int32_t *sticker2, void *stream) {
+int lsh_chunk_possort(const LshAttnDims *dims, const int32_t *sticker, int32_t *sticker2, int32_t *bounds, void *stream) {
   if (int rc = check_dims(dims, false)) return rc;
   if (!sticker || !sticker2 || sticker == sticker2) return set_error("lsh_chunk_possort: sticker / sticker2 must be distinct non-NULL buffers");
-  return chunk_possort_run(*dims, sticker, sticker2, static_cast<cudaStream_t>(stream));
+  return chunk_possort_run(*dims, sticker, sticker2, bounds, static_cast<cudaStream_t>(stream));
 }
 
 int lsh_combine_fwd(const LshAttnDims *dims, const void *o_rounds, const float *logits, void *o_comb, float *lse_tot,
@@ -322,7 +326,7 @@ int lsh_attend_bwd(const LshAttnDims *dims, const void *qv, const int32_t *stick
                    const void *o_comb, const float *lse_tot, const void *do_comb, void *dqv, void *ws, size_t ws_bytes,
                    void *stream) {
   if (int rc = check_dims(dims, true)) return rc;
-  return attend_bwd_run(*dims, qv, sticker, mask, o_comb, lse_tot, do_comb, nullptr, nullptr, dqv, ws, ws_bytes,
+  return attend_bwd_run(*dims, qv, sticker, mask, o_comb, lse_tot, do_comb, nullptr, nullptr, nullptr, dqv, ws, ws_bytes,
                         static_cast<cudaStream_t>(stream));
 }
 
@@ -386,7 +390,7 @@ int lsh_layer_bwd(const LshAttnDims *dims, const void *x, const float *w_q, cons
   // B1 (second half): dW_o = o^T·dout
   if ((rc = gemm_rm(true, false, KO, d.D, BL, w.o_comb, KO, doutb, d.D, dw_o, d.D, true, w.cublas, s))) return rc;
   // B2-B6
-  if ((rc = attend_bwd_run(d, w.qv, w.sticker, mask, w.o_comb, w.lse_tot, w.do_comb, w.aux.qscale, attend_fwd_uses_tc(d) ? w.aux.sticker2 : nullptr, w.dqv, w.bwd_ws, w.bwd_bytes, s)))
+  if ((rc = attend_bwd_run(d, w.qv, w.sticker, mask, w.o_comb, w.lse_tot, w.do_comb, w.aux.qscale, attend_fwd_uses_tc(d) ? w.aux.sticker2 : nullptr, attend_fwd_uses_tc(d) ? w.aux.bounds : nullptr, w.dqv, w.bwd_ws, w.bwd_bytes, s)))
     return rc;
   // B7: dW_q|dW_v = x^T·dqv ; dx = dqv·wqv^T
   if ((rc = gemm_rm(true, false, d.D, NQV, BL, xb, d.D, w.dqv, NQV, w.dwqv, NQV, true, w.cublas, s))) return rc;

@@ -296,11 +296,11 @@ int sum_rounds_run(const LshAttnDims &d, const void *dq_part, const void *dv_par
 int bwd_prep_tc_run(const LshAttnDims &d, const void *do_comb, const void *o_comb, const float *lse_tot, float *dvec,
                     float *lse2, float *qcmp, cudaStream_t stream);
 int qscale_run(const LshAttnDims &d, const void *qv, float *qscale, float2 *rowmeta, void *qhat, cudaStream_t stream);
-int chunk_possort_run(const LshAttnDims &d, const int32_t *sticker, int32_t *sticker2, cudaStream_t stream);
+int chunk_possort_run(const LshAttnDims &d, const int32_t *sticker, int32_t *sticker2, int32_t *bounds, cudaStream_t stream);
 
 int attend_bwd_run(const LshAttnDims &d, const void *qv, const int32_t *sticker, const uint8_t *mask,
                    const void *o_comb, const float *lse_tot, const void *do_comb, const float *qscale_in,
-                   const int32_t *sticker2_in, void *dqv, void *ws, size_t ws_bytes, cudaStream_t stream) {
+                   const int32_t *sticker2_in, const int32_t *bounds_in, void *dqv, void *ws, size_t ws_bytes, cudaStream_t stream) {
   Derived dr = derive(d);
   if (ws_bytes < attend_bwd_workspace_bytes(d))
     return set_error("lsh_attend_bwd: workspace too small (%zu < %zu)", ws_bytes, attend_bwd_workspace_bytes(d));
@@ -328,14 +328,14 @@ int attend_bwd_run(const LshAttnDims &d, const void *qv, const int32_t *sticker,
     if ((rc = bwd_prep_tc_run(d, do_comb, o_comb, lse_tot, dvec, lse2, qcmp, stream))) return rc;
     // position-sorted chunks: from the forward pass of the same layer call if it made them, else into the (unused on this
     // path) second partial-dq area of the workspace
-    const int32_t *sticker2 = sticker2_in;
-    if (!sticker2) {
-      int32_t *s2 = reinterpret_cast<int32_t *>(dq_part + rows * 64);
-      if ((rc = chunk_possort_run(d, sticker, s2, stream))) return rc;
-      sticker2 = s2;
+    const int32_t *sticker2 = sticker2_in, *bounds = bounds_in;
+    if (!sticker2 || !bounds) {
+      int32_t *s2 = reinterpret_cast<int32_t *>(dq_part + rows * 64), *bd = s2 + rows;
+      if ((rc = chunk_possort_run(d, sticker, s2, bd, stream))) return rc;
+      sticker2 = s2; bounds = bd;
     }
     AttendBwdTcParams t;
-    t.qv = static_cast<const __nv_bfloat16 *>(qv); t.sticker = sticker; t.sticker2 = sticker2;
+    t.qv = static_cast<const __nv_bfloat16 *>(qv); t.sticker = sticker; t.sticker2 = sticker2; t.bounds = bounds;
     t.do_comb = static_cast<const __nv_bfloat16 *>(do_comb); t.qscale = qscale; t.lse2 = lse2; t.dvec = dvec; t.qcmp = qcmp;
     t.trace = g_fwd_trace; t.dq_out = dq_part; t.dv_out = dv_part; t.L = d.L; t.H = d.H; t.N = dr.N; t.n_chunks = dr.n_chunks;
     if ((rc = attend_bwd_tc_run(t, dr.BH, stream))) return rc;

@@ -8,6 +8,7 @@ struct AttendBwdTcParams {
   const __nv_bfloat16 *qv;        // (B, L, H, 128)
   const int32_t *sticker;         // (BH, N)
   const int32_t *sticker2;        // (BH, N) sticker with every 128-slot chunk re-ordered by position (chunk_possort_kernel)
+  const int32_t *bounds;          // (BH, N) neighbour-chunk interval bounds per row of sticker2 (chunk_possort_kernel)
   const __nv_bfloat16 *do_comb;   // (B, L, H, 64)
   const float *qscale;            // (BH, L)  log2e / (sqrt(mean(q^2)+eps) sqrt(dq))
   const float *lse2;              // (BH, L)  -(log2e * lse_tot (+ log2e*1e5 for self-only rows))   } stored negated

@@ -217,13 +217,14 @@ static bool force_mma_fwd() {
 bool attend_fwd_uses_tc(const LshAttnDims &d) { return d.C == 128 && 1 + d.nb + d.na == 2 && d.L % 128 == 0 && !force_mma_fwd(); }
 
 int qscale_run(const LshAttnDims &d, const void *qv, float *qscale, float2 *rowmeta, void *qhat, cudaStream_t stream);
-int chunk_possort_run(const LshAttnDims &d, const int32_t *sticker, int32_t *sticker2, cudaStream_t stream);
+int chunk_possort_run(const LshAttnDims &d, const int32_t *sticker, int32_t *sticker2, int32_t *bounds, cudaStream_t stream);
 
 static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 size_t fwd_aux_bytes(const LshAttnDims &d) {
   Derived dr = derive(d);
   const size_t rows = static_cast<size_t>(dr.BH) * d.L;
-  return align256(rows * 4) + align256(rows * 8) + align256(rows * 128) + align256(static_cast<size_t>(dr.BH) * dr.N * 4) + 256;
+  return align256(rows * 4) + align256(rows * 8) + align256(rows * 128) + 2 * align256(static_cast<size_t>(dr.BH) * dr.N * 4) +
+         align256(static_cast<size_t>(dr.BH) * dr.N * 8 + 16) + 256;
 }
 FwdAux fwd_aux_carve(const LshAttnDims &d, void *ws) {
   Derived dr = derive(d);
@@ -233,7 +234,9 @@ FwdAux fwd_aux_carve(const LshAttnDims &d, void *ws) {
   a.qscale = reinterpret_cast<float *>(b); b += align256(rows * 4);
   a.rowmeta = reinterpret_cast<float2 *>(b); b += align256(rows * 8);
   a.qhat = b; b += align256(rows * 128);
-  a.sticker2 = reinterpret_cast<int32_t *>(b);
+  a.sticker2 = reinterpret_cast<int32_t *>(b); b += align256(static_cast<size_t>(dr.BH) * dr.N * 4);
+  a.bounds = reinterpret_cast<int32_t *>(b); b += align256(static_cast<size_t>(dr.BH) * dr.N * 4);
+  a.redo = reinterpret_cast<int *>(b);
   return a;
 }
 // Everything the attention kernels need besides qv and sticker: per-token scales (always: the backward kernel reads
@@ -244,7 +247,7 @@ int fwd_aux_prepare(const LshAttnDims &d, const void *qv, const int32_t *sticker
   if (!scales_done) {     // (a forward call that hashes gets them from the hash kernel, which already holds q)
     if (int rc = qscale_run(d, qv, aux.qscale, tc ? aux.rowmeta : nullptr, tc ? aux.qhat : nullptr, stream)) return rc;
   }
-  if (tc && sticker) return chunk_possort_run(d, sticker, aux.sticker2, stream);
+  if (tc && sticker) return chunk_possort_run(d, sticker, aux.sticker2, aux.bounds, stream);
   return 0;
 }
 
@@ -260,6 +263,9 @@ int attend_fwd_run(const LshAttnDims &d, const void *qv, const int32_t *sticker,
   p.qhat = aux ? static_cast<const __nv_bfloat16 *>(aux->qhat) : nullptr;
   p.rowmeta = aux ? aux->rowmeta : nullptr;
   p.sticker2 = aux ? aux->sticker2 : nullptr;
+  p.bounds = aux ? aux->bounds : nullptr;
+  p.redo = aux ? aux->redo : nullptr;
+  p.keep_bits = nullptr; p.keep_scale = 1.f;
   p.L = d.L; p.H = d.H; p.N = dr.N; p.n_chunks = dr.n_chunks; p.nb = d.nb; p.nwin = dr.nwin;
   p.causal = d.causal; p.masked = d.masked;
   if (d.masked && !mask) return set_error("attend_fwd: dims.masked set but mask == NULL");

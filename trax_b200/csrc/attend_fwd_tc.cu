@@ -41,6 +41,7 @@ struct __align__(16) TcTileMeta {
   float kinfo[TC_C];    // kv_info (+1 applied; negative = padding), fp32 like EA:148-149 (generic path)
   int pos[TC_C];        // 0-based positions; ascending along the tile's rank order (see chunk_possort_kernel)
   int tk[TC_C];         // ticker values
+  int bnd[TC_C];        // neighbour-chunk interval bounds of the row (chunk_possort_kernel)
   float2 am[TC_C];      // {a = 8 r log2e, m2 = a |qhat|^2} of the row's token (query-side scale and softmax shift)
   float vmin[2], vmax[2];   // min / max of the valid kinfo per producer warp (visibility test, generic path)
 };
@@ -94,6 +95,7 @@ __device__ __forceinline__ uint32_t phase_of(int n) { return static_cast<uint32_
 #endif
 
 constexpr float kBig = 1e9f * kLog2e, kSelf = 1e5f * kLog2e;   // EA:152-159 masks, log2 domain
+constexpr float kRedoBelow = 1e-30f, kRedoAbove = 1e30f;       // row sums outside this range are redone with the true max
 
 // 32 score columns of one query row: t = s * a_i - m_i, p = 2^t, packed to bf16 into the P buffer.  Scale and shift are
 // per-ROW registers (no loads); bit c of `vis` says whether column c is visible.  ONE code copy serves interior blocks
@@ -191,17 +193,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
     // rank r of the position-sorted chunk goes to tile row r (even chunks) or 127 - r (odd chunks): the two softmax
     // warpgroups own alternate chunks, so their heavy warps (the rows that see the most keys) sit on
     // different SM sub-partitions.
-    auto fetch_sticker = [&](int u, int cc, int &tka, int &tkb) {
-      const int32_t *stk = p.sticker2 + static_cast<int64_t>(u) * p.N + cc * TC_C + 64 * pw;
+    auto fetch_sticker = [&](int u, int cc, int &tka, int &tkb, int &bda, int &bdb) {
+      const int64_t off = static_cast<int64_t>(u) * p.N + cc * TC_C + 64 * pw;
+      const int32_t *stk = p.sticker2 + off;
       tka = __ldg(stk + lane); tkb = __ldg(stk + 32 + lane);
+      if constexpr (SORTED) { bda = __ldg(p.bounds + off + lane); bdb = __ldg(p.bounds + off + 32 + lane); }
     };
     // Requests run three tiles ahead of the copies so that the dependent chain sticker -> position -> row address never
     // exposes a global-load latency (three statically named request slots: no register rotation, no early scoreboard wait).
-    struct TileReq { int n, u, cc, tka, tkb; bool have; };
+    struct TileReq { int n, u, cc, tka, tkb, bda, bdb; bool have; };
     auto request = [&](TileReq &r) {
-      r.tka = 0; r.tkb = 0;
+      r.tka = 0; r.tkb = 0; r.bda = 0; r.bdb = 0;
       r.have = next_tile(r.n, r.u, r.cc);
-      if (r.have) fetch_sticker(r.u, r.cc, r.tka, r.tkb);
+      if (r.have) fetch_sticker(r.u, r.cc, r.tka, r.tkb, r.bda, r.bdb);
     };
     constexpr bool sorted_path = SORTED;
     const int ch = lane & 15, hi = lane >> 4;              // 16-byte piece of the 256-byte row pair; row parity
@@ -216,6 +220,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
       const int rowa = (64 * pw + lane) ^ flip, rowb = (64 * pw + 32 + lane) ^ flip;
       mt.pos[rowa] = pa;    mt.pos[rowb] = pb;
       mt.tk[rowa] = tka;    mt.tk[rowb] = tkb;
+      if constexpr (sorted_path) { mt.bnd[rowa] = r.bda; mt.bnd[rowb] = r.bdb; }
       const float2 *rm = p.rowmeta + static_cast<int64_t>(u) * p.L;
       cp_async8(smem_u32(&mt.am[rowa]), rm + pa);
       cp_async8(smem_u32(&mt.am[rowb]), rm + pb);
@@ -384,22 +389,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
         const int c_lb = wk.c > 0 ? wk.c - 1 : p.n_chunks - 1;      // cyclic look-back (EA:137-141)
         const int flip_own = (wk.c & 1) ? 127 : 0, flip_lb = (c_lb & 1) ? 127 : 0;
         const int myrank = row ^ flip_own;
-        // a row without any visible key keeps exactly its "-1e5" class (itself, and its copy from the previous hash round
-        // if the look-back tile holds it), and the -1e5 goes back into the reported log-sum-exp
-        const int lb_min = m0.pos[flip_lb];                          // smallest look-back position
-        const bool lonely = myrank == 0 && lb_min >= mypos;
+        // Where my position falls inside the look-back chunk comes precomputed (chunk_possort_kernel): cnt = look-back keys
+        // with position < mine, eq = the look-back chunk holds my own position (my copy from the previous hash round).
+        // A row without any visible key keeps exactly its "-1e5" class (itself, and that copy), and the -1e5 goes back
+        // into the reported log-sum-exp.
+        const int bnd = mq.bnd[row], cnt_lb = bnd & 0xff, eq_lb = (bnd >> 8) & 1;
+        const bool lonely = myrank == 0 && cnt_lb == 0;
         if (lonely) lse_off = -1e5f;
         if (wg == 0) {
-          int blo = 0, bhi = 128;                                    // look-back keys with position < mypos (lower bound)
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int mid = (blo + bhi) >> 1;
-            const int v = m0.pos[(mid & 127) ^ flip_lb];
-            const bool go = blo < bhi;
-            if (go && v < mypos) blo = mid + 1;
-            else if (go) bhi = mid;
-          }
-          const int bound = lonely ? (lb_min == mypos ? 1 : 0) : blo;
+          const int bound = lonely ? eq_lb : cnt_lb;
           if (flip_lb) { lo = 128 - bound; hi = 128; } else { lo = 0; hi = bound; }
         } else {
           const int self_incl = lonely ? 1 : 0;
@@ -517,6 +515,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
       const float il = l > 0.f ? 1.f / l : 0.f;
       const float lse = l > 0.f ? (m2 + log2f(l)) * kLn2 + sh.row_off[w][row] : -3e9f;
       const int tk = sh.row_tk[w][row];
+      // The shift m2 is the row's analytic self score, not the maximum over its visible keys: when every visible key scores
+      // ~83 (natural log units) or more below it, the exponentials flush to zero (large-norm queries whose nearest visible
+      // key is far away).  Such rows are queued and redone with the true maximum by attend_fwd_redo_kernel.
+      if (!(l >= kRedoBelow) || !(l < kRedoAbove)) {
+        const int slot = atomicAdd(p.redo, 1);
+        p.redo[2 + 2 * slot] = wk.u * p.n_chunks + wk.c;
+        p.redo[3 + 2 * slot] = tk;
+      }
       uint32_t r0[32], r1[32];
       tmem_ld32(t_row + TC_O_COL + w * 64, r0);
       tmem_ld32(t_row + TC_O_COL + w * 64 + 32, r1);
@@ -551,6 +557,92 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
   if (warp == 14) tmem_dealloc(tmem, 512);
 }
 
+// Exact redo of the rows the tensor-core kernel could not normalise (see the epilogue): one warp per queued row walks the
+// row's window in the reference's slot order with fp32 arithmetic and the reference's subtractive masks (EA:229-231,
+// 244, 148-159, 251-252, 254-265), true maximum first.  Rare by construction (the queue is usually empty).
+__global__ void __launch_bounds__(256) attend_fwd_redo_kernel(const AttendFwdParams p) {
+  const int lane = threadIdx.x & 31;
+  const int n = p.redo[0];
+  for (int e = blockIdx.x * 8 + (threadIdx.x >> 5); e < n; e += gridDim.x * 8) {
+    const int item = p.redo[2 + 2 * e], tk = p.redo[3 + 2 * e];
+    const int u = item / p.n_chunks, c = item - u * p.n_chunks, b = u / p.H, h = u - b * p.H;
+    const int round = tk / p.L, pos = tk - round * p.L;
+    const int32_t *stk = p.sticker + static_cast<int64_t>(u) * p.N;
+    const __nv_bfloat16 *qv_u = p.qv + (static_cast<int64_t>(b) * p.L * p.H + h) * 128;
+    const int64_t rstride = static_cast<int64_t>(p.H) * 128;
+    const float2 q2 = unpack_bf16(*reinterpret_cast<const uint32_t *>(qv_u + pos * rstride + 2 * lane));
+    bool qvalid = true;
+    if (p.masked) qvalid = p.mask[static_cast<int64_t>(b) * p.L + pos] != 0;
+    const float qi = static_cast<float>(pos + 1);                      // q_info (EA:201)
+    int qslot = 0;                                                     // my slot in the chunk (dropout row)
+    for (int l4 = 0; l4 < 4; ++l4) {
+      const unsigned hit = __ballot_sync(0xffffffffu, stk[c * TC_C + l4 * 32 + lane] == tk);
+      if (hit) qslot = l4 * 32 + __ffs(hit) - 1;
+    }
+    float sc[8];                                                       // scores of keys j with j % 32 == lane
+    float mx = -INFINITY;
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      sc[jj] = -INFINITY;
+      if (jj * 32 < p.nwin * TC_C) {
+        const int cc = ((c + (jj >> 2) - p.nb) % p.n_chunks + p.n_chunks) % p.n_chunks;   // cyclic window (EA:137-141)
+        const int ktk_l = stk[cc * TC_C + (jj & 3) * 32 + lane];
+        for (int l = 0; l < 32; ++l) {
+          const int kpos = __shfl_sync(0xffffffffu, ktk_l, l) % p.L;
+          const float2 k2 = unpack_bf16(*reinterpret_cast<const uint32_t *>(qv_u + kpos * rstride + 2 * lane));
+          float dot = q2.x * k2.x + q2.y * k2.y, ss = k2.x * k2.x + k2.y * k2.y;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            dot += __shfl_xor_sync(0xffffffffu, dot, o);
+            ss += __shfl_xor_sync(0xffffffffu, ss, o);
+          }
+          bool kvalid = true;
+          if (p.masked) kvalid = p.mask[static_cast<int64_t>(b) * p.L + kpos] != 0;
+          const float ki = static_cast<float>((kvalid ? kpos : -kpos) + 1);
+          float s = dot / sqrtf(ss * (1.f / 64) + 1e-6f) * 0.125f;     // EA:229-231, 244
+          if (p.causal && qi < ki) s -= 1e9f;                          // EA:150-152
+          if (qi == ki) s -= 1e5f;                                     // EA:153-155
+          if (p.masked && ki < 0.f) s -= 1e9f;                         // EA:156-159
+          if (lane == l) sc[jj] = s;
+        }
+        mx = fmaxf(mx, sc[jj]);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float lsum = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      sc[jj] = jj * 32 < p.nwin * TC_C ? __expf(sc[jj] - mx) : 0.f;
+      lsum += sc[jj];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+    const float inv = 1.f / lsum;
+    float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      if (jj * 32 < p.nwin * TC_C) {
+        const int cc = ((c + (jj >> 2) - p.nb) % p.n_chunks + p.n_chunks) % p.n_chunks;
+        const int ktk_l = stk[cc * TC_C + (jj & 3) * 32 + lane];
+        uint32_t keep = 0xffffffffu;
+        if (p.keep_bits) keep = p.keep_bits[qslot * (p.nwin * TC_C / 32) + jj];
+        for (int l = 0; l < 32; ++l) {
+          const int kpos = __shfl_sync(0xffffffffu, ktk_l, l) % p.L;
+          float pj = __shfl_sync(0xffffffffu, sc[jj], l) * inv;
+          if (p.keep_bits) pj = (keep >> l) & 1u ? pj * p.keep_scale : 0.f;   // EA:254-262: after the softmax, lse untouched
+          const float2 v2 = unpack_bf16(*reinterpret_cast<const uint32_t *>(qv_u + kpos * rstride + 64 + 2 * lane));
+          o0 = fmaf(pj, v2.x, o0); o1 = fmaf(pj, v2.y, o1);
+        }
+      }
+    }
+    __nv_bfloat16 *dst = p.o + b * p.o_sb + h * p.o_sh + round * p.o_sr + pos * p.o_sp;
+    *reinterpret_cast<uint32_t *>(dst + 2 * lane) = pack_bf16(o0, o1);
+    if (lane == 0) p.lse[static_cast<int64_t>(u) * p.N + tk] = mx + __logf(lsum);
+    (void)qvalid;
+  }
+}
+
 int attend_fwd_tc_run(const AttendFwdParams &p, int BH, cudaStream_t stream) {
   const size_t smem = static_cast<size_t>(TC_NST) * TC_TILE_BYTES + 1024;   // + static TcShared
   const bool sorted = p.causal && !p.masked && p.nb == 1;
@@ -565,9 +657,13 @@ int attend_fwd_tc_run(const AttendFwdParams &p, int BH, cudaStream_t stream) {
     const int m = atoi(e);
     if (m > 0 && m < grid) grid = m;
   }
+  if (!p.redo) return set_error("attend_fwd_tc: redo queue missing from the workspace");
+  if (cudaMemsetAsync(p.redo, 0, 8, stream) != cudaSuccess) return set_error("attend_fwd_tc: cudaMemsetAsync failed");
   if (sorted) attend_fwd_tc_kernel<true><<<grid, TC_THREADS, smem, stream>>>(p, total);
   else attend_fwd_tc_kernel<false><<<grid, TC_THREADS, smem, stream>>>(p, total);
   LSH_CHECK_LAUNCH("attend_fwd_tc_kernel");
+  attend_fwd_redo_kernel<<<sms, 256, 0, stream>>>(p);
+  LSH_CHECK_LAUNCH("attend_fwd_redo_kernel");
   return 0;
 }
 

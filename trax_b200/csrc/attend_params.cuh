@@ -15,6 +15,10 @@ struct AttendFwdParams {
   const __nv_bfloat16 *qhat;    // (BH, L, 64) normalised keys q / (8 r)                 } tcgen05 path only
   const float2 *rowmeta;        // (BH, L) {a = 8 r log2e, m2 = a |qhat|^2}               }
   const int32_t *sticker2;      // (BH, N) sticker with every chunk re-ordered by position }
+  const int32_t *bounds;        // (BH, N) per row of sticker2: neighbour-chunk interval bounds (chunk_possort_kernel)
+  const uint32_t *keep_bits;    // attention dropout (EA:254-262): (C, W / 32) bit rows, bit = keep; null = no dropout
+  float keep_scale;             // 1 / (1 - rate)
+  int *redo;                    // tcgen05 path: [0] = number of queued rows, [2 + 2 i], [3 + 2 i] = {unit * n_chunks + chunk, ticker}
   long long *trace;             // debug: per-phase clock64 stamps of CTA 0 (null = off)
   int L, H, N, n_chunks, nb, nwin, causal, masked;
 };
@@ -27,6 +31,8 @@ struct FwdAux {
   float2 *rowmeta;
   void *qhat;
   int32_t *sticker2;
+  int32_t *bounds;
+  int *redo;
 };
 bool attend_fwd_uses_tc(const LshAttnDims &d);
 size_t fwd_aux_bytes(const LshAttnDims &d);

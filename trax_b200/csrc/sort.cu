@@ -279,16 +279,31 @@ int sort_run(const LshAttnDims &d, const int32_t *buckets, int64_t bstride, int3
 // two hash rounds — keep slot order).  Attention within a chunk window is a sum over keys and its rows are scattered
 // back by ticker, so the order inside a chunk is free: with position-sorted tiles the causal mask of EA:150-152 becomes
 // an interval of column indices per row, whole 32-column blocks are either fully visible or skipped, and no per-key
-// position has to be loaded in the softmax loop.  One warp per chunk, rank by counting (128 x 4 compares per lane).
-__global__ void __launch_bounds__(256) chunk_possort_kernel(const int32_t *__restrict__ sticker, int32_t *__restrict__ sticker2,
-                                                            int L, int64_t total_chunks) {
-  __shared__ int stk[8][128];
+// position has to be loaded in the softmax loop.
+//
+// The same launch emits, per row (in the new order), where the row's position falls inside the two NEIGHBOUR chunks of
+// its unit (cyclic, EA:137-141) — the interval bounds the attention kernels would otherwise find by an 8-step binary
+// search per row and pass:
+//   bounds = cnt_prev | eq_prev << 8 | cnt_next << 16 | eq_next << 24
+//   cnt_prev / cnt_next = number of tokens of chunk c-1 / c+1 whose position is BELOW the row's; eq_* = that chunk holds
+//   the row's own position (its copy from the neighbouring hash round).
+// One warp per chunk (warp-level bitonic network on (position << 7 | slot) keys); a CTA covers 8 consecutive chunks of
+// one unit and sorts the two halo chunks redundantly (10 warps).
+constexpr int POSSORT_WARPS = 10;
+__global__ void __launch_bounds__(32 * POSSORT_WARPS) chunk_possort_kernel(const int32_t *__restrict__ sticker,
+                                                                          int32_t *__restrict__ sticker2,
+                                                                          int32_t *__restrict__ bounds, int L, int n_chunks,
+                                                                          int blocks_per_unit) {
+  __shared__ int stk[POSSORT_WARPS][128];
+  __shared__ int spos[POSSORT_WARPS][128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t chunk = static_cast<int64_t>(blockIdx.x) * 8 + warp;
-  if (chunk >= total_chunks) return;
-  const int32_t *src = sticker + chunk * 128;
+  const int u = blockIdx.x / blocks_per_unit, c0 = (blockIdx.x - u * blocks_per_unit) * 8;
+  const int c_raw = c0 - 1 + warp;
+  const int c = ((c_raw % n_chunks) + n_chunks) % n_chunks;                        // cyclic inside the unit
+  const bool owner = warp >= 1 && warp <= 8 && c_raw < n_chunks;                  // this warp's chunk is written by this CTA
+  const int64_t base = (static_cast<int64_t>(u) * n_chunks + c) * 128;
   // element e = 4 * lane + i; key = (position << 7) | slot: unique, so the bitonic network needs no tie rule
-  const int4 t4 = __ldg(reinterpret_cast<const int4 *>(src) + lane);
+  const int4 t4 = __ldg(reinterpret_cast<const int4 *>(sticker + base) + lane);
   *reinterpret_cast<int4 *>(&stk[warp][4 * lane]) = t4;
   uint32_t key[4] = {static_cast<uint32_t>(t4.x % L) << 7 | (4 * lane + 0), static_cast<uint32_t>(t4.y % L) << 7 | (4 * lane + 1),
                      static_cast<uint32_t>(t4.z % L) << 7 | (4 * lane + 2), static_cast<uint32_t>(t4.w % L) << 7 | (4 * lane + 3)};
@@ -322,16 +337,43 @@ __global__ void __launch_bounds__(256) chunk_possort_kernel(const int32_t *__res
     }
   }
   __syncwarp();
-  int4 o4;
-  o4.x = stk[warp][key[0] & 127]; o4.y = stk[warp][key[1] & 127]; o4.z = stk[warp][key[2] & 127]; o4.w = stk[warp][key[3] & 127];
-  *(reinterpret_cast<int4 *>(sticker2 + chunk * 128) + lane) = o4;
+  if (owner) {
+    int4 o4;
+    o4.x = stk[warp][key[0] & 127]; o4.y = stk[warp][key[1] & 127]; o4.z = stk[warp][key[2] & 127]; o4.w = stk[warp][key[3] & 127];
+    *(reinterpret_cast<int4 *>(sticker2 + base) + lane) = o4;
+  }
+  if (bounds == nullptr) return;
+  *reinterpret_cast<int4 *>(&spos[warp][4 * lane]) = make_int4(static_cast<int>(key[0] >> 7), static_cast<int>(key[1] >> 7),
+                                                               static_cast<int>(key[2] >> 7), static_cast<int>(key[3] >> 7));
+  __syncthreads();
+  if (!owner) return;
+  // neighbours: warp - 1 holds chunk c - 1, warp + 1 chunk c + 1 (both cyclic; for a one-chunk unit all three coincide)
+  const int *prev = spos[warp - 1], *next = spos[warp + 1];
+  int4 b4;
+  int *bo = reinterpret_cast<int *>(&b4);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int pos = static_cast<int>(key[i] >> 7);
+    int lp = 0, ln = 0;                                 // lower bounds (number of entries below pos)
+#pragma unroll
+    for (int s = 64; s >= 1; s >>= 1) {
+      if (prev[lp + s - 1] < pos) lp += s;
+      if (next[ln + s - 1] < pos) ln += s;
+    }
+    if (lp == 127 && prev[127] < pos) lp = 128;
+    if (ln == 127 && next[127] < pos) ln = 128;
+    const int ep = (lp < 128 && prev[lp] == pos) ? 1 : 0, en = (ln < 128 && next[ln] == pos) ? 1 : 0;
+    bo[i] = lp | (ep << 8) | (ln << 16) | (en << 24);
+  }
+  *(reinterpret_cast<int4 *>(bounds + base) + lane) = b4;
 }
 
-int chunk_possort_run(const LshAttnDims &d, const int32_t *sticker, int32_t *sticker2, cudaStream_t stream) {
+int chunk_possort_run(const LshAttnDims &d, const int32_t *sticker, int32_t *sticker2, int32_t *bounds, cudaStream_t stream) {
   Derived dr = derive(d);
   if (d.C != 128) return set_error("chunk_possort: chunk_len must be 128");
-  const int64_t chunks = static_cast<int64_t>(dr.BH) * dr.n_chunks;
-  chunk_possort_kernel<<<static_cast<unsigned>((chunks + 7) / 8), 256, 0, stream>>>(sticker, sticker2, d.L, chunks);
+  const int bpu = (dr.n_chunks + 7) / 8;
+  chunk_possort_kernel<<<static_cast<unsigned>(dr.BH * bpu), 32 * POSSORT_WARPS, 0, stream>>>(sticker, sticker2, bounds, d.L,
+                                                                                             dr.n_chunks, bpu);
   LSH_CHECK_LAUNCH("chunk_possort_kernel");
   return 0;
 }

@@ -107,12 +107,14 @@ def sort(dims, buckets, want_undo=True):
   return sticker, undo
 
 
-def chunk_possort(dims, sticker):
-  """sticker with every 128-slot chunk re-ordered by position (internal order of the tcgen05 kernels)."""
+def chunk_possort(dims, sticker, with_bounds=False):
+  """sticker with every 128-slot chunk re-ordered by position (internal order of the tcgen05 kernels); with_bounds also
+  returns the packed neighbour-chunk interval bounds of every row (see include/lsh_attn.h)."""
   lib = _lib.load()
   out = torch.empty_like(sticker)
-  _lib.check(lib.lsh_chunk_possort(ctypes.byref(dims), _ptr(sticker), _ptr(out), _stream()), 'lsh_chunk_possort')
-  return out
+  bounds = torch.empty_like(sticker) if with_bounds else None
+  _lib.check(lib.lsh_chunk_possort(ctypes.byref(dims), _ptr(sticker), _ptr(out), _ptr(bounds), _stream()), 'lsh_chunk_possort')
+  return (out, bounds) if with_bounds else out
 
 
 def attend_fwd(dims, qv, sticker, mask=None):
