@@ -337,3 +337,44 @@ def test_output_dropout_is_a_shared_column_mask():
   ev.init(trax_b200.ShapeDtype((B, L, D)))
   out_e, _, _, _ = ev.forward_and_or_backward(x_d, w_d, state, None, update_state=False)
   assert not (out_e == 0).all(dim=0).all(dim=0).any()
+
+
+def test_fresh_host_tensors_are_never_served_from_a_stale_device_copy():
+  """forward-only loops and fused calls on FRESH host tensors of one shape (the allocator hands the freed
+  address out again) must see their own data; only forward(x) -> backward(x) of the same tensor object shares the upload."""
+  import trax_b200
+  B, L, D = 1, 512, 128
+  cfg = util.make_cfg(H=2, C=128, nh=2, n_buckets=8)
+  layer = _layer(cfg)
+  layer.init(trax_b200.ShapeDtype((B, L, D)), rng=np.array([3, 4], np.uint32))
+  rng = np.random.default_rng(0)
+  factors = O.bucket_factors(cfg.n_buckets, L, cfg.chunk_len)
+  layer._rotations_override = torch.from_numpy(
+      rng.standard_normal((B * cfg.n_heads, 64, cfg.n_hashes, sum(factors) // 2)).astype(np.float32))
+  def fresh(i):
+    return torch.from_numpy(np.random.default_rng(100 + i).standard_normal((B, L, D)).astype(np.float32))
+  for i in range(6):
+    want = layer.forward(fresh(i).cuda()).cpu()
+    got = layer.forward(fresh(i))                       # fresh host tensor, same shape, likely the same address
+    assert torch.equal(got, want), 'host call %d computed on another tensor\'s data' % i
+  # fused call on host tensors after a forward of a DIFFERENT tensor: must not take the stash
+  x0, x1, g = fresh(20), fresh(21), fresh(22)
+  layer.forward(x0)
+  state = layer.state
+  _, _, dx_h, _ = layer.forward_and_or_backward(x1, layer.weights, state, None, output_grad=g, compute_output=False,
+                                                update_state=False)
+  _, _, dx_d, _ = layer.forward_and_or_backward(x1.cuda(), layer.weights, state, None, output_grad=g.cuda(),
+                                                compute_output=False, update_state=False)
+  assert torch.equal(dx_h, dx_d.cpu())
+  # the legitimate pairing moves x once
+  trax_b200.host_io_bytes(reset=True)
+  out = layer.forward(x0)
+  layer.backward(x0, out, g, layer.weights, None, layer.state, None)
+  h2d, _ = trax_b200.host_io_bytes(reset=True)
+  assert h2d == (x0.numel() + g.numel()) * 4, h2d
+  # ... and an in-place change torch can see invalidates it
+  out = layer.forward(x0)
+  x0.add_(1.0)
+  dx_h, _ = layer.backward(x0, out, g, layer.weights, None, layer.state, None)
+  dx_d, _ = layer.backward(x0.cuda(), out, g.cuda(), layer.weights, None, layer.state, None)
+  assert torch.equal(dx_h, dx_d.cpu())

@@ -125,3 +125,34 @@ def test_reversible_half_around_the_pure_lsh_wrapper():
       util.assert_close(got.cpu().numpy(), want, 'd_qkv[%d] %s' % (i, nm))
   for got, want, nm in zip(dw[3], want_ddense, ('kernel', 'bias')):
     util.assert_close(got.cpu().numpy(), want, 'd_dense %s' % nm)
+
+
+def test_reversible_half_with_output_dropout_uses_one_mask_in_both_passes():
+  """The attention sub-key is `_split_rngs(rng, 2)[1]` in `forward` AND in `reverse_and_grad` (reversible.py:297, 328): with
+  output dropout the mask of the backward pass must be the forward's, otherwise x1 = y1 - residual is reconstructed
+  from a different residual."""
+  import trax_b200
+  B, L, D = 1, 512, 256
+  rng = np.random.default_rng(5)
+  x1, x2 = (rng.standard_normal((B, L, D)).astype(np.float32) for _ in range(2))
+  ct_y1, ct_x2 = (rng.standard_normal((B, L, D)).astype(np.float32) for _ in range(2))
+  attn = trax_b200.LSHSelfAttention(n_heads=2, d_qk=64, d_v=64, causal=True, chunk_len=128, n_hashes=2, n_buckets=8,
+                                    output_dropout=0.5)
+  block = trax_b200.ReversibleHalfResidual(attn)
+  sig = trax_b200.ShapeDtype((B, L, D))
+  key = np.array([11, 22], np.uint32)
+  block.init((sig, sig), rng=key)
+  cu = lambda a: torch.from_numpy(a).cuda()
+  y1, ctx = block.forward((cu(x1), cu(x2)))
+  res = (y1 - cu(x1)).cpu().numpy()
+  dropped = np.all(res == 0, axis=(0, 1))
+  assert 0.2 < dropped.mean() < 0.8, 'output dropout 0.5 should zero about half of the d_model columns'
+  (rx1, _), ((_, g_x2), _) = block.reverse_and_grad((y1, ctx), (cu(ct_y1), cu(ct_x2)), block.weights, None, block.state,
+                                                    key)
+  util.assert_close(rx1.cpu().numpy(), x1, 'x1 reconstructed through the same dropout mask', rtol=3e-2)
+  # a different key draws a different mask: the reconstruction must then differ (the test has teeth)
+  (bad, _), _ = block.reverse_and_grad((y1, ctx), (cu(ct_y1), cu(ct_x2)), block.weights, None, block.state,
+                                       np.array([33, 44], np.uint32))
+  assert np.abs(bad.cpu().numpy() - x1).max() > 1e-2
+  with pytest.raises(ValueError):
+    block.reverse_and_grad((y1, ctx), (cu(ct_y1), cu(ct_x2)), block.weights, None, block.state, None)

@@ -10,9 +10,12 @@ from oracle import lsh_oracle as O
 # score perturbations (DESIGN.md "Numerics").  The tolerance is therefore asserted in norm form:
 #   (a) ||got - want||_2 / ||want||_2        <= RTOL                          (2e-2 relative)
 #   (b) max|got - want|                      <= RTOL * max|want| + ATOL       (2e-2 relative / 1e-3 absolute, max norm)
-# A wrong row / wrong mask produces an error of the order of max|want| and trips (b).  The literal elementwise form
-# |got-want| <= ATOL + RTOL*|want| is REPORTED (frac_bad, tests/gpu_debug_report.py) but not asserted.
+#   (c) the literal elementwise form |got - want| <= ATOL + RTOL*|want| holds for >= 99 % of the elements (frac_bad <=
+#       FRAC_BAD_MAX): the elements it fails on are values near zero whose error is a few bf16 roundings of O(1) operands
+#       (measured 0.01-0.7 %); asserting the fraction keeps that number from regressing silently.
+# A wrong row / wrong mask produces an error of the order of max|want| and trips (b).
 RTOL, ATOL = 2e-2, 1e-3
+FRAC_BAD_MAX = 0.01
 
 
 def bf16_round(a):
@@ -32,11 +35,13 @@ def close_report(got, want, rtol=RTOL, atol=ATOL):
               worst_ratio=float((err / (atol + rtol * np.abs(want))).max()))
 
 
-def assert_close(got, want, name, rtol=RTOL, atol=ATOL):
+def assert_close(got, want, name, rtol=RTOL, atol=ATOL, frac_bad_max=FRAC_BAD_MAX):
   assert np.isfinite(np.asarray(got, np.float64)).all(), '%s has non-finite values' % name
   r = close_report(got, want, rtol, atol)
   assert r['rel_l2'] <= rtol, '%s: relative L2 error above %g: %s' % (name, rtol, r)
   assert r['max_abs'] <= rtol * r['max_ref'] + atol, '%s: max error above %g*max|ref| + %g: %s' % (name, rtol, atol, r)
+  assert r['frac_bad'] <= frac_bad_max, '%s: %.3f %% of the elements violate |err| <= %g + %g*|ref| (limit %.1f %%): %s' % (
+      name, 100 * r['frac_bad'], atol, rtol, 100 * frac_bad_max, r)
   return r
 
 

@@ -7,9 +7,9 @@ pure_lsh_attention.py (its weight-less core, `PureLSHSelfAttention`, and `PureLS
 Importing the package does not need a GPU; calling anything does, and raises otherwise.
 """
 from trax_b200.lsh_attention import (LSHSelfAttention, ShapeDtype, host_io_bytes,  # noqa: F401
-                                     set_async_host_io, set_weight_grad_allreduce, synchronize)
+                                     set_async_host_io, set_reuse_forward_upload, set_weight_grad_allreduce, synchronize)
 from trax_b200.pure_lsh_attention import PureLSHSelfAttention, PureLSHSelfAttentionWrapper  # noqa: F401
 from trax_b200.reversible import ReversibleHalfResidual  # noqa: F401
 from trax_b200.self_attention import SelfAttention  # noqa: F401
 
-__all__ = ['LSHSelfAttention', 'PureLSHSelfAttention', 'PureLSHSelfAttentionWrapper', 'ReversibleHalfResidual', 'SelfAttention', 'ShapeDtype', 'set_async_host_io', 'set_weight_grad_allreduce', 'synchronize', 'host_io_bytes']
+__all__ = ['LSHSelfAttention', 'PureLSHSelfAttention', 'PureLSHSelfAttentionWrapper', 'ReversibleHalfResidual', 'SelfAttention', 'ShapeDtype', 'set_async_host_io', 'set_reuse_forward_upload', 'set_weight_grad_allreduce', 'synchronize', 'host_io_bytes']

@@ -21,6 +21,7 @@ torch plays the role JAX plays for the reference: device memory, streams, autogr
 (`torch.autograd.Function` ≙ `fastmath.custom_vjp` in base.py:644-673).
 """
 import ctypes
+import weakref
 from typing import NamedTuple
 
 import numpy as np
@@ -62,11 +63,10 @@ class _HostIO:
   """Host <-> device plumbing of the layer's host-tensor path (what bench.py's `e2e` leg times).
 
   Two side streams per device keep both PCIe directions busy: uploads of the NEXT call's inputs and downloads of the
-  PREVIOUS call's results run beside the kernels on the caller's stream.  An upload of the same host tensor object at
-  the same version (forward(x) followed by backward(x, ...), the reversible-layer pattern) is served from the device
-  copy made by the first call.  With `set_async_host_io(True)` a call returns as soon as its work is enqueued: results
-  are pinned host tensors that become valid after `trax_b200.synchronize()` (JAX-style asynchronous dispatch);
-  the default is to wait before returning.
+  PREVIOUS call's results run beside the kernels on the caller's stream.  With `set_async_host_io(True)` a call returns
+  as soon as its work is enqueued: results are pinned host tensors that become valid after `trax_b200.synchronize()`
+  (JAX-style asynchronous dispatch); the default is to wait before returning.  (Re-use of forward's device copy of x by
+  the matching backward call is the LAYER's business — `LSHSelfAttention._x_stash` — not a cache in here.)
   """
   _per_device = {}
   async_mode = False
@@ -75,7 +75,6 @@ class _HostIO:
     self.dev = dev
     self.h2d = torch.cuda.Stream(device=dev)
     self.d2h = torch.cuda.Stream(device=dev)
-    self.cache_key, self.cache_val = None, None
     self.rings = {}
     self.h2d_bytes = 0
     self.d2h_bytes = 0
@@ -88,19 +87,10 @@ class _HostIO:
       io = cls._per_device[key] = cls(dev)
     return io
 
-  def upload(self, t, cache=False):
-    """Host tensor -> device copy usable on the current stream (stream-ordered, no host wait).
-
-    cache=True: the copy is remembered for ONE more upload of the same host tensor (same storage, shape and version):
-    forward(x) followed by backward(x, ...) moves x across PCIe once.
-    """
+  def upload(self, t):
+    """Host tensor -> device copy usable on the current stream (stream-ordered, no host wait)."""
     if t is None or t.is_cuda:
       return t
-    key = (t.data_ptr(), tuple(t.shape), t.dtype, t._version) if cache else None
-    if key is not None and key == self.cache_key:
-      d = self.cache_val
-      self.cache_key, self.cache_val = None, None
-      return d
     main = torch.cuda.current_stream(self.dev)
     with torch.cuda.stream(self.h2d):
       d = t.to(self.dev, non_blocking=True)
@@ -108,8 +98,6 @@ class _HostIO:
     main.wait_event(ev)
     d.record_stream(main)
     self.h2d_bytes += t.numel() * t.element_size()
-    if cache:
-      self.cache_key, self.cache_val = key, d
     return d
 
   def _staging(self, d, role):
@@ -151,6 +139,18 @@ class _HostIO:
 def set_async_host_io(flag):
   """Host-tensor calls return without waiting for their device->host copies (see _HostIO)."""
   _HostIO.async_mode = bool(flag)
+
+
+_REUSE_UPLOAD = {'on': True}
+
+
+def set_reuse_forward_upload(flag):
+  """`backward(x_host, ...)` right after `forward(x_host)` of the SAME host tensor object (weak reference identity and
+  `_version`) re-uses the device copy forward made instead of crossing PCIe again (default on).  The stash lives on the
+  layer, is consumed by the next `backward` and dropped by any other call.  Turn it off if host inputs are mutated in
+  place between the two calls through a path torch cannot see (a NumPy view of a `torch.from_numpy` tensor does not bump
+  `_version`)."""
+  _REUSE_UPLOAD['on'] = bool(flag)
 
 
 _GRAD_ALLREDUCE = {'on': False}
@@ -240,6 +240,7 @@ class LSHSelfAttention:
     self._weights = ()
     self._state = ()
     self._rng = None
+    self._x_stash = None                # (weakref to a host x, its _version, device copy): forward -> matching backward
     self._rotations_override = None     # tests / a JAX host inject explicit rotations here
     self._out_keep_override = None      # likewise an explicit (d_model,) bool keep-mask for output dropout
 
@@ -326,15 +327,15 @@ class LSHSelfAttention:
   # ---- forward / backward (EA:2111-2126, 2251-2259) ------------------------------------------------
   def forward(self, inputs):
     weights, state, rng = self.weights, self.state, self.rng
-    output, new_state, _, _ = self.forward_and_or_backward(
-        inputs, weights, state, rng, compute_output=True, update_state=True)
+    output, new_state, _, _ = self._forward_and_or_backward(
+        inputs, weights, state, rng, compute_output=True, update_state=True, _stash='store')
     self.state = new_state
     return output
 
   def backward(self, inputs, output, grad, weights, state, new_state, rng=None, **kwargs):
     del output, state, kwargs
-    _, _, inputs_grad, weights_grad = self.forward_and_or_backward(
-        inputs, weights, new_state, rng, output_grad=grad, compute_output=False, update_state=False)
+    _, _, inputs_grad, weights_grad = self._forward_and_or_backward(
+        inputs, weights, new_state, rng, output_grad=grad, compute_output=False, update_state=False, _stash='consume')
     return inputs_grad, weights_grad
 
   def pure_fn(self, x, weights, state, rng, use_cache=False):       # base.py:541-600
@@ -373,8 +374,8 @@ class LSHSelfAttention:
       @staticmethod
       def forward(ctx, x0, w_q, w_v, w_o):
         inputs = x0 if have_single_input else (x0,) + xs[1:]
-        out, new_state, _, _ = layer.forward_and_or_backward(
-            inputs, (w_q, w_v, w_o), state, rng, compute_output=True, update_state=True)
+        out, new_state, _, _ = layer._forward_and_or_backward(
+            inputs, (w_q, w_v, w_o), state, rng, compute_output=True, update_state=True, _stash='store')
         ctx.save_for_backward(x0, w_q, w_v, w_o)
         holder['new_state'] = new_state                             # residual (base.py:659)
         return out
@@ -417,6 +418,11 @@ class LSHSelfAttention:
 
   def forward_and_or_backward(self, inputs, weights, state, rng, output_grad=None,
                               compute_output=True, update_state=True):
+    """Performs batched forward and/or backward passes (EA:2261-2289); see _forward_and_or_backward."""
+    return self._forward_and_or_backward(inputs, weights, state, rng, output_grad, compute_output, update_state)
+
+  def _forward_and_or_backward(self, inputs, weights, state, rng, output_grad=None,
+                               compute_output=True, update_state=True, _stash=None):
     """Performs batched forward and/or backward passes (EA:2261-2289).
 
     Returns (output, new_state, inputs_grad, weights_grad):
@@ -442,11 +448,20 @@ class LSHSelfAttention:
 
     io = _HostIO.get(dev) if host_io else None
 
-    def to_dev(t, cache=False):
+    def to_dev(t):
       if t is None or t.is_cuda:
         return t
-      return _HostIO.get(dev).upload(t, cache)
-    x_d = to_dev(x, cache=True).contiguous()
+      return _HostIO.get(dev).upload(t)
+    # forward(x_host) -> backward(x_host, ...): the backward call may take over the device copy forward made of the very
+    # same tensor object; every call drops whatever stash it finds (see set_reuse_forward_upload).
+    stash, self._x_stash = self._x_stash, None
+    if (host_io and _stash == 'consume' and stash is not None and _REUSE_UPLOAD['on'] and stash[0]() is x
+        and stash[1] == x._version and stash[2].device == dev):
+      x_d = stash[2]
+    else:
+      x_d = to_dev(x).contiguous()
+    if host_io and _stash == 'store' and _REUSE_UPLOAD['on']:
+      self._x_stash = (weakref.ref(x), x._version, x_d)
     mask_d = None
     if self._masked:
       mask_d = to_dev(inputs[1]).to(torch.uint8).contiguous()

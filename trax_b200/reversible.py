@@ -15,9 +15,21 @@ Weights `((scale, bias), attention_weights)` and state `((), attention_state)` f
 """
 import ctypes
 
+import numpy as np
 import torch
 
 from trax_b200 import _lib, ops
+from trax_b200.lsh_attention import _split_host
+
+
+def _split_rngs(rng, n):
+  """`combinators._split_rngs` (trax/layers/combinators.py): one sub-key per sublayer, `(None,) * n` without a key.  The
+  SAME function of `rng` in `forward` and in `reverse_and_grad` (reversible.py:297, 328), so a sublayer that draws from its
+  key (output / attention dropout) draws the same mask in both passes.  Not jax.random's bits (see _split_host)."""
+  if rng is None:
+    return (None,) * n
+  key = np.asarray(rng.cpu() if isinstance(rng, torch.Tensor) else rng).astype(np.uint32).reshape(-1)
+  return tuple(_split_host(key, n))
 
 
 def _rows(x):
@@ -71,6 +83,17 @@ class ReversibleHalfResidual:
     self._attention_layer = attention_layer
     self._epsilon = float(epsilon)
     self._ln_weights = ()
+    self._rng = None
+
+  @property
+  def rng(self):
+    if self._rng is None:
+      self._rng = np.array([0, 0], dtype=np.uint32)                       # base.py: default key from seed 0
+    return self._rng
+
+  @rng.setter
+  def rng(self, rng):
+    self._rng = rng
 
   n_in = n_out = 2                                                          # reversible.py:288-294 (1 + 1 context)
 
@@ -101,14 +124,20 @@ class ReversibleHalfResidual:
     dev = 'cuda' if torch.cuda.is_available() else 'cpu'
     self._ln_weights = (torch.ones(d_model, dtype=torch.float32, device=dev),      # normalization.py:138-142
                         torch.zeros(d_model, dtype=torch.float32, device=dev))
+    if rng is not None:
+      self.rng = rng
     self._attention_layer.init(ctx, rng=rng)
     return self.weights, self.state
 
   def forward(self, xs):
     accumulator, context = xs
     scale, bias = self._ln_weights
+    rngs = _split_rngs(self.rng, 2)                                        # reversible.py:297: (LayerNorm, attention)
     z, _ = layernorm_fwd(context, scale, bias, self._epsilon)
-    residual = self._attention_layer.forward(z)                            # updates the attention state (buckets)
+    attn = self._attention_layer
+    with torch.no_grad():
+      residual, new_state = attn.pure_fn(z, attn.weights, attn.state, rngs[1])     # reversible.py:308
+    attn.state = new_state                                                 # buckets of this step, read back by reverse_and_grad
     return _residual(accumulator, residual, +1.0), context
 
   def reverse(self, output, weights=(), state=(), new_state=(), rng=None):
@@ -121,9 +150,10 @@ class ReversibleHalfResidual:
     accumulator_output_ct, context_ct = ct
     (scale, bias), attn_weights = weights if weights else self.weights
     attn_state = (new_state if new_state else self.state)[1]
+    rngs = _split_rngs(rng, 2)                                             # reversible.py:328: same split as forward
     z, stats = layernorm_fwd(context, scale, bias, self._epsilon)
     residual, _, dz, attn_weights_ct = self._attention_layer.forward_and_or_backward(
-        z, attn_weights, attn_state, rng, output_grad=accumulator_output_ct, compute_output=True, update_state=False)
+        z, attn_weights, attn_state, rngs[1], output_grad=accumulator_output_ct, compute_output=True, update_state=False)
     context_ct_new, d_scale, d_bias = layernorm_bwd(context, dz, context_ct, stats, scale)
     reconstructed_x = _residual(accumulator_output, residual, -1.0)
     return (reconstructed_x, context), ((accumulator_output_ct, context_ct_new), ((d_scale, d_bias), attn_weights_ct))
