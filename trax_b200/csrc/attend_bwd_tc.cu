@@ -35,6 +35,18 @@
 #define BT_ISSUE_UNROLL _Pragma("unroll")
 #endif
 
+// A/B switches of the round-2 restructuring (defaults = what was measured fastest):
+//   BT_EPI_ORDER  0: epilogue releases the key tile's ring slot at its very end (round 1)
+//                 1: dK^/dV loads first (kv_free as early as in round 1), then the key-row math, slot release, dQ
+//                 2: key-row math and slot release before the dV loads
+//   BT_BLOCK16    1: 16-query blocks with the TMEM loads running one block ahead; 0: 32-query blocks, load-then-compute
+#ifndef BT_EPI_ORDER
+#define BT_EPI_ORDER 1
+#endif
+#ifndef BT_BLOCK16
+#define BT_BLOCK16 1
+#endif
+
 namespace lsh {
 
 constexpr int BT_C = 128;
@@ -379,6 +391,7 @@ BT_ISSUE_UNROLL
       mbar_wait(&sh.dsm_free[it.n & 1], ((it.n >> 1) & 1) ^ 1);
       tc_fence_after();
       if (row == 0) BT_TRACE(it.n, 3 + 2 * h);
+#if BT_BLOCK16
       uint32_t sa[16], da[16], sb[16], db[16];
       // one 16-query block: P^T and dS^T (bf16) back into TMEM in place, dS * key scale into the staging tile
       auto block = [&](const uint32_t (&sv)[16], const uint32_t (&dp)[16], int k) {
@@ -448,6 +461,65 @@ BT_ISSUE_UNROLL
           block(sa, da, k);
         }
       }
+#else
+      (void)k_first;
+#pragma unroll 1
+      for (int cc = 0; cc < 64; cc += 32) {
+        const int c0 = 64 * h + cc;
+        uint32_t sv[32], pk_p[16], pk_ds[16];
+        if (c0 + 32 <= min_lo) {
+          // no key of this warp sees any query of the block
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { pk_p[i] = 0u; sv[i] = 0u; }
+          tmem_st16(r_st + (cc >> 1), pk_p);
+          tmem_st16(r_st + 64 + (cc >> 1), pk_p);
+        } else {
+          uint32_t dp[32];
+          tmem_ld32(r_st + cc, sv);
+          tmem_ld32(r_st + 64 + cc, dp);
+          tmem_ld_wait_dep(sv);
+          tmem_ld_wait_dep(dp);
+          if (c0 >= max_hi) {
+#pragma unroll
+            for (int c4 = 0; c4 < 32; c4 += 4) {
+              const ulonglong2 ls = *reinterpret_cast<const ulonglong2 *>(&mq.lse2[c0 + c4]);   // -lse2 pairs
+              const ulonglong2 dv = *reinterpret_cast<const ulonglong2 *>(&mq.dvec[c0 + c4]);   // -D pairs
+              const uint64_t t01 = ffma2(pk2u(sv[c4 + 0], sv[c4 + 1]), ksc2, ls.x), t23 = ffma2(pk2u(sv[c4 + 2], sv[c4 + 3]), ksc2, ls.y);
+              const uint64_t p01 = pk2(fast_exp2(lo32(t01)), fast_exp2(hi32(t01))), p23 = pk2(fast_exp2(lo32(t23)), fast_exp2(hi32(t23)));
+              const uint64_t d01 = fmul2(p01, fadd2(pk2u(dp[c4 + 0], dp[c4 + 1]), dv.x));
+              const uint64_t d23 = fmul2(p23, fadd2(pk2u(dp[c4 + 2], dp[c4 + 3]), dv.y));
+              const uint64_t g01 = fmul2(d01, kst2), g23 = fmul2(d23, kst2);
+              pk_p[c4 >> 1] = pack_bf16(lo32(p01), hi32(p01));  pk_p[(c4 >> 1) + 1] = pack_bf16(lo32(p23), hi32(p23));
+              pk_ds[c4 >> 1] = pack_bf16(lo32(d01), hi32(d01)); pk_ds[(c4 >> 1) + 1] = pack_bf16(lo32(d23), hi32(d23));
+              sv[c4 >> 1] = pack_bf16(lo32(g01), hi32(g01));
+              sv[(c4 >> 1) + 1] = pack_bf16(lo32(g23), hi32(g23));
+            }
+          } else {
+#pragma unroll
+            for (int c4 = 0; c4 < 32; c4 += 4) {
+              const float4 qc = *reinterpret_cast<const float4 *>(&mq.qcmp[c0 + c4]);
+              const ulonglong2 ls = *reinterpret_cast<const ulonglong2 *>(&mq.lse2[c0 + c4]);   // -lse2 pairs
+              const ulonglong2 dv = *reinterpret_cast<const ulonglong2 *>(&mq.dvec[c0 + c4]);   // -D pairs
+              const uint64_t t01 = ffma2(pk2u(sv[c4 + 0], sv[c4 + 1]), ksc2, ls.x), t23 = ffma2(pk2u(sv[c4 + 2], sv[c4 + 3]), ksc2, ls.y);
+              const uint64_t p01 = pk2(fast_exp2(ki_j < qc.x ? lo32(t01) : -INFINITY), fast_exp2(ki_j < qc.y ? hi32(t01) : -INFINITY));
+              const uint64_t p23 = pk2(fast_exp2(ki_j < qc.z ? lo32(t23) : -INFINITY), fast_exp2(ki_j < qc.w ? hi32(t23) : -INFINITY));
+              const uint64_t d01 = fmul2(p01, fadd2(pk2u(dp[c4 + 0], dp[c4 + 1]), dv.x));
+              const uint64_t d23 = fmul2(p23, fadd2(pk2u(dp[c4 + 2], dp[c4 + 3]), dv.y));
+              const uint64_t g01 = fmul2(d01, kst2), g23 = fmul2(d23, kst2);
+              pk_p[c4 >> 1] = pack_bf16(lo32(p01), hi32(p01));  pk_p[(c4 >> 1) + 1] = pack_bf16(lo32(p23), hi32(p23));
+              pk_ds[c4 >> 1] = pack_bf16(lo32(d01), hi32(d01)); pk_ds[(c4 >> 1) + 1] = pack_bf16(lo32(d23), hi32(d23));
+              sv[c4 >> 1] = pack_bf16(lo32(g01), hi32(g01));
+              sv[(c4 >> 1) + 1] = pack_bf16(lo32(g23), hi32(g23));
+            }
+          }
+          tmem_st16(r_st + (cc >> 1), pk_p);
+          tmem_st16(r_st + 64 + (cc >> 1), pk_ds);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          sts128(ds_dst + ((((cc >> 3) + q) ^ r7) << 4), sv[4 * q], sv[4 * q + 1], sv[4 * q + 2], sv[4 * q + 3]);
+      }
+#endif
       tmem_st_wait();
       fence_proxy_async();                                 // dS staging writes -> UMMA (async proxy)
       tc_fence_before();
@@ -483,68 +555,87 @@ BT_ISSUE_UNROLL
         __nv_bfloat16 *dq_dst = p.dq_out + orow, *dv_dst = p.dv_out + orow;
         tmem_ld32(t_lane + 256, dk0);
         tmem_ld32(t_lane + 288, dk1);
-        // Key-side length-normalisation VJP (App. B5) first: it is the only reader of the key tile's rows in this role, so
-        // the ring slot goes back to the producers after ~1K cycles instead of at the end of the epilogue (the next
-        // tile's gather then starts a whole epilogue earlier).  dk0 / dk1 end up holding
-        //   e = dK^ / (r sqrt(dq)) - q (dK^ . q) / (dq r^3 sqrt(dq)),  which is added to dQ below.
         const float r_j = 0.125f * kLog2e / ksc_j;       // sqrt(mean(q^2) + eps)
         const float a_j = 0.125f / r_j;
-        tmem_ld_wait_dep(dk0);
-        tmem_ld_wait_dep(dk1);
-        float dot = 0.f;
+        // Key-side length-normalisation VJP (App. B5): afterwards dk0 / dk1 hold
+        //   e = dK^ / (r sqrt(dq)) - q (dK^ . q) / (dq r^3 sqrt(dq)),  which is added to dQ below.
+        // It is the only reader of the key tile's rows in this role: the ring slot goes back to the producers right after
+        // it instead of at the end of the epilogue (the next tile's gather starts that much earlier).
+        auto key_side = [&]() {
+          float dot = 0.f;
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-          const uint4 raw = lds128u(kt_row + ((ch ^ r7) << 4));
-          const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
+          for (int ch = 0; ch < 8; ++ch) {
+            const uint4 raw = lds128u(kt_row + ((ch ^ r7) << 4));
+            const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 q2 = unpack_bf16(rw[e]);
-            const int c = ch * 8 + e * 2;
-            dot = fmaf(__uint_as_float(c < 32 ? dk0[c] : dk1[c - 32]), q2.x, dot);
-            dot = fmaf(__uint_as_float(c + 1 < 32 ? dk0[c + 1] : dk1[c + 1 - 32]), q2.y, dot);
-          }
-        }
-        const float c_j = dot * 0.125f / (64.f * r_j * r_j * r_j);
-#pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-          const uint4 raw = lds128u(kt_row + ((ch ^ r7) << 4));
-          const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 q2 = unpack_bf16(rw[e]);
-            const int c = ch * 8 + e * 2;
-            if (c < 32) {
-              dk0[c] = __float_as_uint(__uint_as_float(dk0[c]) * a_j - q2.x * c_j);
-              dk0[c + 1] = __float_as_uint(__uint_as_float(dk0[c + 1]) * a_j - q2.y * c_j);
-            } else {
-              dk1[c - 32] = __float_as_uint(__uint_as_float(dk1[c - 32]) * a_j - q2.x * c_j);
-              dk1[c - 31] = __float_as_uint(__uint_as_float(dk1[c - 31]) * a_j - q2.y * c_j);
+            for (int e = 0; e < 4; ++e) {
+              const float2 q2 = unpack_bf16(rw[e]);
+              const int c = ch * 8 + e * 2;
+              dot = fmaf(__uint_as_float(c < 32 ? dk0[c] : dk1[c - 32]), q2.x, dot);
+              dot = fmaf(__uint_as_float(c + 1 < 32 ? dk0[c + 1] : dk1[c + 1 - 32]), q2.y, dot);
             }
           }
-        }
-        // last read of the key tile's rows is behind us: give the ring slot back
-        mbar_arrive(&sh.empty[slk]);
-        if (it.last_seg) mbar_arrive(&sh.empty[bt_slot(it.seq_k + 1)]);
-        // dV: once its loads are done both accumulators are empty and the next key chunk may accumulate (kv_free)
+          const float c_j = dot * 0.125f / (64.f * r_j * r_j * r_j);
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t g[32];
-          tmem_ld32(t_lane + 320 + 32 * half, g);
-          tmem_ld_wait_dep(g);
-          if (half == 1) {
-            tc_fence_before();
-            mbar_arrive(&sh.kv_free);
-          }
+          for (int ch = 0; ch < 8; ++ch) {
+            const uint4 raw = lds128u(kt_row + ((ch ^ r7) << 4));
+            const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            uint4 v;
-            v.x = pack_bf16(__uint_as_float(g[8 * q4 + 0]), __uint_as_float(g[8 * q4 + 1]));
-            v.y = pack_bf16(__uint_as_float(g[8 * q4 + 2]), __uint_as_float(g[8 * q4 + 3]));
-            v.z = pack_bf16(__uint_as_float(g[8 * q4 + 4]), __uint_as_float(g[8 * q4 + 5]));
-            v.w = pack_bf16(__uint_as_float(g[8 * q4 + 6]), __uint_as_float(g[8 * q4 + 7]));
-            *reinterpret_cast<uint4 *>(dv_dst + half * 32 + q4 * 8) = v;
+            for (int e = 0; e < 4; ++e) {
+              const float2 q2 = unpack_bf16(rw[e]);
+              const int c = ch * 8 + e * 2;
+              if (c < 32) {
+                dk0[c] = __float_as_uint(__uint_as_float(dk0[c]) * a_j - q2.x * c_j);
+                dk0[c + 1] = __float_as_uint(__uint_as_float(dk0[c + 1]) * a_j - q2.y * c_j);
+              } else {
+                dk1[c - 32] = __float_as_uint(__uint_as_float(dk1[c - 32]) * a_j - q2.x * c_j);
+                dk1[c - 31] = __float_as_uint(__uint_as_float(dk1[c - 31]) * a_j - q2.y * c_j);
+              }
+            }
           }
-        }
+        };
+        auto release_slot = [&]() {
+          mbar_arrive(&sh.empty[slk]);
+          if (it.last_seg) mbar_arrive(&sh.empty[bt_slot(it.seq_k + 1)]);
+        };
+        // dV: once its loads (and the dK^ loads above) are done both accumulators are empty and the next key chunk may
+        // accumulate (kv_free)
+        auto drain_dv = [&]() {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t g[32];
+            tmem_ld32(t_lane + 320 + 32 * half, g);
+            tmem_ld_wait_dep(g);
+            if (half == 1) {
+              tmem_ld_wait_dep(dk0);
+              tmem_ld_wait_dep(dk1);
+              tc_fence_before();
+              mbar_arrive(&sh.kv_free);
+            }
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              uint4 v;
+              v.x = pack_bf16(__uint_as_float(g[8 * q4 + 0]), __uint_as_float(g[8 * q4 + 1]));
+              v.y = pack_bf16(__uint_as_float(g[8 * q4 + 2]), __uint_as_float(g[8 * q4 + 3]));
+              v.z = pack_bf16(__uint_as_float(g[8 * q4 + 4]), __uint_as_float(g[8 * q4 + 5]));
+              v.w = pack_bf16(__uint_as_float(g[8 * q4 + 6]), __uint_as_float(g[8 * q4 + 7]));
+              *reinterpret_cast<uint4 *>(dv_dst + half * 32 + q4 * 8) = v;
+            }
+          }
+        };
+#if BT_EPI_ORDER == 2
+        tmem_ld_wait_dep(dk0);
+        tmem_ld_wait_dep(dk1);
+        key_side();
+        release_slot();
+        drain_dv();
+#else
+        drain_dv();
+        key_side();
+#if BT_EPI_ORDER == 1
+        release_slot();
+#endif
+#endif
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           uint32_t g[32];
@@ -567,6 +658,9 @@ BT_ISSUE_UNROLL
             *reinterpret_cast<uint4 *>(dq_dst + (half * 4 + q4) * 8) = v;
           }
         }
+#if BT_EPI_ORDER == 0
+        release_slot();
+#endif
         if (row == 0) BT_TRACE(it.n, 7);
       } else {
         mbar_arrive(&sh.empty[slk]);                           // pre item: this warpgroup never touches the tile
