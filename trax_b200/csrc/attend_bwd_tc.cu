@@ -59,10 +59,12 @@ constexpr uint32_t BT_IDESC_KV = make_idesc_bf16(128, 64, 0, 1);   // dV, dK^ (B
 constexpr uint32_t BT_IDESC_DQ = make_idesc_bf16(128, 64, 1, 1);   // dQ (A and B MN-major)
 
 // trace slots per item: 0 MMA: pds_full[0] seen, 1 MMA: pds_full[1] seen, 2 MMA: item done (commits issued),
-// 3 WG0: st_full seen, 4 WG0: pass done, 5 WG1: st_full seen, 6 WG1: pass done, 7 WG0: epilogue done
+// 3 WG0: st_full seen, 4 WG0: pass done, 5 WG1: st_full seen, 6 WG1: pass done, 7 WG0: epilogue done,
+// 8/9 MMA: dV/dK of half 0/1 issued, 10/11 MMA: next item's S^T half 0/1 issued, 12 MMA: dQ issued, 13 WG0: tiles seen,
+// 14 epilogue: kv_full seen, 15 producer: tile of this item's iteration requested (slot free)
 // (compiled in only with -DLSH_TRACE: the stamps cost instruction-cache space in every role)
 #ifdef LSH_TRACE
-#define BT_TRACE(n, slot) do { if (p.trace && blockIdx.x == 0 && (n) < 120) p.trace[(n) * 8 + (slot)] = clock64(); } while (0)
+#define BT_TRACE(n, slot) do { if (p.trace && blockIdx.x == 0 && (n) < 120) p.trace[(n) * 16 + (slot)] = clock64(); } while (0)
 #else
 #define BT_TRACE(n, slot) do { } while (0)
 #endif
@@ -173,6 +175,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) attend_bwd_tc_kernel(const Atte
   if (warp == 12 || warp == 13) {
     // ================================ producers ========================================================
     const int pw = warp - 12;                              // rows [64*pw, 64*pw + 64) of every tile
+    int trace_n = 0;
     auto load_tile = [&](int seq, int u, int cc) {
       const uint32_t slot = bt_slot(seq);
       const int b = u / p.H, h = u - b * p.H;
@@ -182,6 +185,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) attend_bwd_tc_kernel(const Atte
       const int bda = __ldg(p.bounds + soff + lane), bdb = __ldg(p.bounds + soff + 32 + lane);
       const int pa = tka % p.L, pb = tkb % p.L;
       mbar_wait<128>(&sh.empty[slot], bt_phase(seq) ^ 1);
+      if (tid == 12 * 32) BT_TRACE(trace_n, 15);
       BtTileMeta &mt = sh.meta[slot];
       const int ra = 64 * pw + lane, rb = ra + 32;
       mt.kinfo[ra] = static_cast<float>(pa + 1); mt.kinfo[rb] = static_cast<float>(pb + 1);
@@ -236,6 +240,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) attend_bwd_tc_kernel(const Atte
       const BtItem it = w.item();
       if (it.first) {               // one visit per iteration: a pre iteration brings two tiles, a real one brings one
         int c_key, c_next;
+        trace_n = it.n;
         w.chunks(c_key, c_next);
         if (!it.real) load_tile(it.seq_k, it.u, c_key);
         load_tile(it.seq_k + 1, it.u, c_next);
@@ -311,10 +316,11 @@ BT_ISSUE_UNROLL
           }
           __syncwarp();
         }
+        if (lane == 0) BT_TRACE(cur.n, 8 + h);
         // region h is free once the MMAs above have read it (in-order pipe)
         probe();
         if (pre_ok) {
-          for (; st_issued <= h; ++st_issued) issue_st(nxt, st_issued);
+          for (; st_issued <= h; ++st_issued) { issue_st(nxt, st_issued); if (lane == 0) BT_TRACE(cur.n, 10 + st_issued); }
         }
       }
       {
@@ -339,15 +345,16 @@ BT_ISSUE_UNROLL
         }
         __syncwarp();
       }
+      if (lane == 0) BT_TRACE(cur.n, 12);
       probe();
       if (pre_ok) {
-        for (; st_issued < 2; ++st_issued) issue_st(nxt, st_issued);
+        for (; st_issued < 2; ++st_issued) { issue_st(nxt, st_issued); if (lane == 0) BT_TRACE(cur.n, 10 + st_issued); }
       }
       if (lane == 0) BT_TRACE(cur.n, 2);
       if (!have_next) break;
       if (st_issued < 2) {
         wait_tiles(nxt);
-        for (; st_issued < 2; ++st_issued) issue_st(nxt, st_issued);
+        for (; st_issued < 2; ++st_issued) { issue_st(nxt, st_issued); if (lane == 0) BT_TRACE(cur.n, 10 + st_issued); }
       }
       cur = nxt;
     }
@@ -372,6 +379,7 @@ BT_ISSUE_UNROLL
         lo_next = (bnd >> 16) & 0xff; hi_next = lo_next + ((bnd >> 24) & 1);
       }
       mbar_wait(&sh.full[slq], bt_phase(it.seq_q));
+      if (row == 0) BT_TRACE(it.n, 13);
       const BtTileMeta &mq = sh.meta[slq];
       const float kst_j = ksc_j * kLn2;                    // true key scale 1/(r*sqrt(dq)) for the dQ operand
       const uint64_t ksc2 = pk2(ksc_j, ksc_j), kst2 = pk2(kst_j, kst_j);
@@ -551,6 +559,7 @@ BT_ISSUE_UNROLL
         mbar_wait(&sh.dq_full[it.rit & 1], (it.rit >> 1) & 1);
         mbar_wait(&sh.kv_full, it.rit & 1);
         tc_fence_after();
+        if (row == 0) BT_TRACE(it.n, 14);
         uint32_t dk0[32], dk1[32];
         __nv_bfloat16 *dq_dst = p.dq_out + orow, *dv_dst = p.dv_out + orow;
         tmem_ld32(t_lane + 256, dk0);
