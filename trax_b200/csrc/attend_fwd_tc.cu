@@ -28,6 +28,15 @@
 
 #include <stdlib.h>
 
+// A/B switches (round 2): TC_FWD_BOUNDS 1 = look-back interval from the bounds chunk_possort_kernel precomputes, 0 = 8-step
+// binary search per row and pass (round 1); TC_FWD_REDO 1 = rows whose sum under/overflows are queued for the exact redo.
+#ifndef TC_FWD_BOUNDS
+#define TC_FWD_BOUNDS 1
+#endif
+#ifndef TC_FWD_REDO
+#define TC_FWD_REDO 1
+#endif
+
 namespace lsh {
 
 constexpr int TC_C = 128;
@@ -197,7 +206,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
       const int64_t off = static_cast<int64_t>(u) * p.N + cc * TC_C + 64 * pw;
       const int32_t *stk = p.sticker2 + off;
       tka = __ldg(stk + lane); tkb = __ldg(stk + 32 + lane);
+#if TC_FWD_BOUNDS
       if constexpr (SORTED) { bda = __ldg(p.bounds + off + lane); bdb = __ldg(p.bounds + off + 32 + lane); }
+#endif
     };
     // Requests run three tiles ahead of the copies so that the dependent chain sticker -> position -> row address never
     // exposes a global-load latency (three statically named request slots: no register rotation, no early scoreboard wait).
@@ -220,7 +231,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
       const int rowa = (64 * pw + lane) ^ flip, rowb = (64 * pw + 32 + lane) ^ flip;
       mt.pos[rowa] = pa;    mt.pos[rowb] = pb;
       mt.tk[rowa] = tka;    mt.tk[rowb] = tkb;
+#if TC_FWD_BOUNDS
       if constexpr (sorted_path) { mt.bnd[rowa] = r.bda; mt.bnd[rowb] = r.bdb; }
+#endif
       const float2 *rm = p.rowmeta + static_cast<int64_t>(u) * p.L;
       cp_async8(smem_u32(&mt.am[rowa]), rm + pa);
       cp_async8(smem_u32(&mt.am[rowb]), rm + pb);
@@ -393,11 +406,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
         // with position < mine, eq = the look-back chunk holds my own position (my copy from the previous hash round).
         // A row without any visible key keeps exactly its "-1e5" class (itself, and that copy), and the -1e5 goes back
         // into the reported log-sum-exp.
+#if TC_FWD_BOUNDS
         const int bnd = mq.bnd[row], cnt_lb = bnd & 0xff, eq_lb = (bnd >> 8) & 1;
         const bool lonely = myrank == 0 && cnt_lb == 0;
+#else
+        const int lb_min = m0.pos[flip_lb];                          // smallest look-back position
+        const bool lonely = myrank == 0 && lb_min >= mypos;
+#endif
         if (lonely) lse_off = -1e5f;
         if (wg == 0) {
+#if TC_FWD_BOUNDS
           const int bound = lonely ? eq_lb : cnt_lb;
+#else
+          int blo = 0, bhi = 128;                                    // look-back keys with position < mypos (lower bound)
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int mid = (blo + bhi) >> 1;
+            const int v = m0.pos[(mid & 127) ^ flip_lb];
+            const bool go = blo < bhi;
+            if (go && v < mypos) blo = mid + 1;
+            else if (go) bhi = mid;
+          }
+          const int bound = lonely ? (lb_min == mypos ? 1 : 0) : blo;
+#endif
           if (flip_lb) { lo = 128 - bound; hi = 128; } else { lo = 0; hi = bound; }
         } else {
           const int self_incl = lonely ? 1 : 0;
@@ -518,11 +549,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
       // The shift m2 is the row's analytic self score, not the maximum over its visible keys: when every visible key scores
       // ~83 (natural log units) or more below it, the exponentials flush to zero (large-norm queries whose nearest visible
       // key is far away).  Such rows are queued and redone with the true maximum by attend_fwd_redo_kernel.
+#if TC_FWD_REDO
       if (!(l >= kRedoBelow) || !(l < kRedoAbove)) {
         const int slot = atomicAdd(p.redo, 1);
         p.redo[2 + 2 * slot] = wk.u * p.n_chunks + wk.c;
         p.redo[3 + 2 * slot] = tk;
       }
+#endif
       uint32_t r0[32], r1[32];
       tmem_ld32(t_row + TC_O_COL + w * 64, r0);
       tmem_ld32(t_row + TC_O_COL + w * 64 + 32, r1);
