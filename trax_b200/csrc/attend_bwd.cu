@@ -297,6 +297,7 @@ int bwd_prep_tc_run(const LshAttnDims &d, const void *do_comb, const void *o_com
                     float *lse2, float *qcmp, cudaStream_t stream);
 int qscale_run(const LshAttnDims &d, const void *qv, float *qscale, float2 *rowmeta, void *qhat, cudaStream_t stream);
 int chunk_possort_run(const LshAttnDims &d, const int32_t *sticker, int32_t *sticker2, int32_t *bounds, cudaStream_t stream);
+bool attend_tc_uses_bounds();
 
 int attend_bwd_run(const LshAttnDims &d, const void *qv, const int32_t *sticker, const uint8_t *mask,
                    const void *o_comb, const float *lse_tot, const void *do_comb, const float *qscale_in,
@@ -329,8 +330,8 @@ int attend_bwd_run(const LshAttnDims &d, const void *qv, const int32_t *sticker,
     // position-sorted chunks: from the forward pass of the same layer call if it made them, else into the (unused on this
     // path) second partial-dq area of the workspace
     const int32_t *sticker2 = sticker2_in, *bounds = bounds_in;
-    if (!sticker2 || !bounds) {
-      int32_t *s2 = reinterpret_cast<int32_t *>(dq_part + rows * 64), *bd = s2 + rows;
+    if (!sticker2 || (!bounds && attend_tc_uses_bounds())) {
+      int32_t *s2 = reinterpret_cast<int32_t *>(dq_part + rows * 64), *bd = attend_tc_uses_bounds() ? s2 + rows : nullptr;
       if ((rc = chunk_possort_run(d, sticker, s2, bd, stream))) return rc;
       sticker2 = s2; bounds = bd;
     }

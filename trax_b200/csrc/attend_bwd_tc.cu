@@ -35,16 +35,23 @@
 #define BT_ISSUE_UNROLL _Pragma("unroll")
 #endif
 
-// A/B switches of the round-2 restructuring (defaults = what was measured fastest):
-//   BT_EPI_ORDER  0: epilogue releases the key tile's ring slot at its very end (round 1)
-//                 1: dK^/dV loads first (kv_free as early as in round 1), then the key-row math, slot release, dQ
-//                 2: key-row math and slot release before the dV loads
-//   BT_BLOCK16    1: 16-query blocks with the TMEM loads running one block ahead; 0: 32-query blocks, load-then-compute
+// A/B switches of the round-2 restructuring attempts.  Defaults = what measured fastest at config 2 (ncu, one box,
+// interleaved): every alternative below was slower or equal.
+//   BT_EPI_ORDER  0: epilogue releases the key tile's ring slot at its very end (round 1; 709 us)
+//                 1: dK^/dV loads first, then the key-row math, slot release, dQ (711 us)
+//                 2: key-row math and slot release before the dV loads (with BT_BLOCK16: 756 us)
+//   BT_BLOCK16    0: 32-query blocks, load-then-compute (709 us)
+//                 1: 16-query blocks with the TMEM loads running one block ahead (770-790 us: twice the TMEM instructions)
+//   BT_BOUNDS     0: 8-step binary search per key row and item (714 us)
+//                 1: interval bounds precomputed by chunk_possort_kernel (709 us, but +12 us in that kernel per call)
 #ifndef BT_EPI_ORDER
-#define BT_EPI_ORDER 1
+#define BT_EPI_ORDER 0
 #endif
 #ifndef BT_BLOCK16
-#define BT_BLOCK16 1
+#define BT_BLOCK16 0
+#endif
+#ifndef BT_BOUNDS
+#define BT_BOUNDS 0
 #endif
 
 namespace lsh {
@@ -182,7 +189,9 @@ __global__ void __launch_bounds__(BT_THREADS, 1) attend_bwd_tc_kernel(const Atte
       const int64_t soff = static_cast<int64_t>(u) * p.N + cc * BT_C + 64 * pw;
       const int32_t *stk = p.sticker2 + soff;                     // chunk rows ascending in position
       const int tka = __ldg(stk + lane), tkb = __ldg(stk + 32 + lane);
+#if BT_BOUNDS
       const int bda = __ldg(p.bounds + soff + lane), bdb = __ldg(p.bounds + soff + 32 + lane);
+#endif
       const int pa = tka % p.L, pb = tkb % p.L;
       mbar_wait<128>(&sh.empty[slot], bt_phase(seq) ^ 1);
       if (tid == 12 * 32) BT_TRACE(trace_n, 15);
@@ -190,7 +199,9 @@ __global__ void __launch_bounds__(BT_THREADS, 1) attend_bwd_tc_kernel(const Atte
       const int ra = 64 * pw + lane, rb = ra + 32;
       mt.kinfo[ra] = static_cast<float>(pa + 1); mt.kinfo[rb] = static_cast<float>(pb + 1);
       mt.tk[ra] = tka; mt.tk[rb] = tkb;
+#if BT_BOUNDS
       mt.bnd[ra] = bda; mt.bnd[rb] = bdb;
+#endif
       const int64_t oa = static_cast<int64_t>(u) * p.L + pa, ob = static_cast<int64_t>(u) * p.L + pb;
       cp_async4(smem_u32(&mt.kscl[ra]), p.qscale + oa); cp_async4(smem_u32(&mt.kscl[rb]), p.qscale + ob);
       cp_async4(smem_u32(&mt.lse2[ra]), p.lse2 + oa);   cp_async4(smem_u32(&mt.lse2[rb]), p.lse2 + ob);
@@ -374,9 +385,11 @@ BT_ISSUE_UNROLL
         mbar_wait(&sh.full[slk], bt_phase(it.seq_k));
         ksc_j = sh.meta[slk].kscl[row];
         ki_j = sh.meta[slk].kinfo[row];
+#if BT_BOUNDS
         // where this key's position falls among the queries of the NEXT chunk: precomputed by chunk_possort_kernel
         const int bnd = sh.meta[slk].bnd[row];
         lo_next = (bnd >> 16) & 0xff; hi_next = lo_next + ((bnd >> 24) & 1);
+#endif
       }
       mbar_wait(&sh.full[slq], bt_phase(it.seq_q));
       if (row == 0) BT_TRACE(it.n, 13);
@@ -390,6 +403,21 @@ BT_ISSUE_UNROLL
       // Per warp, a 16-query block is skipped (zeros), evaluated without any mask (no per-query position loads), or
       // — only around the boundary — evaluated with the per-element compare.
       const bool same = it.seq_q == it.seq_k;
+#if !BT_BOUNDS
+      if (!same) {                                           // lower bound of my position among the query tile's (sorted) positions
+        int blo = 0, bhi = 128;
+#pragma unroll
+        for (int sidx = 0; sidx < 8; ++sidx) {
+          const int mid = (blo + bhi) >> 1;
+          const float v = mq.kinfo[mid & 127];
+          const bool go = blo < bhi;
+          if (go && v < ki_j) blo = mid + 1;
+          else if (go) bhi = mid;
+        }
+        lo_next = blo;
+        hi_next = blo + ((blo < 128 && mq.kinfo[blo & 127] == ki_j) ? 1 : 0);
+      }
+#endif
       const int lo_j = same ? row : lo_next, hi_j = same ? row + 1 : hi_next;
       const int min_lo = __reduce_min_sync(0xffffffffu, lo_j), max_hi = __reduce_max_sync(0xffffffffu, hi_j);
       // skipped blocks are a prefix of my 64 queries: those that lie entirely below every key of this warp
@@ -680,6 +708,8 @@ BT_ISSUE_UNROLL
   __syncthreads();
   if (warp == 14) tmem_dealloc(tmem, 512);
 }
+
+bool attend_bwd_tc_uses_bounds() { return BT_BOUNDS != 0; }
 
 int attend_bwd_tc_run(const AttendBwdTcParams &p, int BH, cudaStream_t stream) {
   const size_t smem = static_cast<size_t>(BT_NST) * BT_TILE_BYTES + 2 * BT_DS_BYTES + 1024;

@@ -216,6 +216,9 @@ static bool force_mma_fwd() {
 // interval masks rely on that; other lengths take the mma.sync path)
 bool attend_fwd_uses_tc(const LshAttnDims &d) { return d.C == 128 && 1 + d.nb + d.na == 2 && d.L % 128 == 0 && !force_mma_fwd(); }
 
+bool attend_fwd_tc_uses_bounds();
+bool attend_bwd_tc_uses_bounds();
+bool attend_tc_uses_bounds() { return attend_fwd_tc_uses_bounds() || attend_bwd_tc_uses_bounds(); }
 int qscale_run(const LshAttnDims &d, const void *qv, float *qscale, float2 *rowmeta, void *qhat, cudaStream_t stream);
 int chunk_possort_run(const LshAttnDims &d, const int32_t *sticker, int32_t *sticker2, int32_t *bounds, cudaStream_t stream);
 
@@ -247,7 +250,7 @@ int fwd_aux_prepare(const LshAttnDims &d, const void *qv, const int32_t *sticker
   if (!scales_done) {     // (a forward call that hashes gets them from the hash kernel, which already holds q)
     if (int rc = qscale_run(d, qv, aux.qscale, tc ? aux.rowmeta : nullptr, tc ? aux.qhat : nullptr, stream)) return rc;
   }
-  if (tc && sticker) return chunk_possort_run(d, sticker, aux.sticker2, aux.bounds, stream);
+  if (tc && sticker) return chunk_possort_run(d, sticker, aux.sticker2, attend_tc_uses_bounds() ? aux.bounds : nullptr, stream);
   return 0;
 }
 

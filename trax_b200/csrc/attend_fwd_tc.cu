@@ -30,8 +30,9 @@
 
 // A/B switches (round 2): TC_FWD_BOUNDS 1 = look-back interval from the bounds chunk_possort_kernel precomputes, 0 = 8-step
 // binary search per row and pass (round 1); TC_FWD_REDO 1 = rows whose sum under/overflows are queued for the exact redo.
+// Measured at config 2 (ncu, one box, interleaved): search + redo 288.5 us, bounds + redo 298.5 us, search without redo 287 us.
 #ifndef TC_FWD_BOUNDS
-#define TC_FWD_BOUNDS 1
+#define TC_FWD_BOUNDS 0
 #endif
 #ifndef TC_FWD_REDO
 #define TC_FWD_REDO 1
@@ -675,6 +676,8 @@ __global__ void __launch_bounds__(256) attend_fwd_redo_kernel(const AttendFwdPar
     (void)qvalid;
   }
 }
+
+bool attend_fwd_tc_uses_bounds() { return TC_FWD_BOUNDS != 0; }
 
 int attend_fwd_tc_run(const AttendFwdParams &p, int BH, cudaStream_t stream) {
   const size_t smem = static_cast<size_t>(TC_NST) * TC_TILE_BYTES + 1024;   // + static TcShared

@@ -301,6 +301,7 @@ __global__ void __launch_bounds__(32 * POSSORT_WARPS) chunk_possort_kernel(const
   const int c_raw = c0 - 1 + warp;
   const int c = ((c_raw % n_chunks) + n_chunks) % n_chunks;                        // cyclic inside the unit
   const bool owner = warp >= 1 && warp <= 8 && c_raw < n_chunks;                  // this warp's chunk is written by this CTA
+  if (bounds == nullptr && !owner) return;                                        // halo warps only serve the bounds
   const int64_t base = (static_cast<int64_t>(u) * n_chunks + c) * 128;
   // element e = 4 * lane + i; key = (position << 7) | slot: unique, so the bitonic network needs no tie rule
   const int4 t4 = __ldg(reinterpret_cast<const int4 *>(sticker + base) + lane);
