@@ -13,13 +13,13 @@ o_r, logits = ops.attend_fwd(dims, qv, sticker)
 o_c, lse = ops.combine_fwd(dims, o_r, logits)
 do = torch.randn_like(o_c)
 ops.attend_bwd(dims, qv, sticker, o_c, lse, do); torch.cuda.synchronize()
-tr = torch.zeros(120 * 16, dtype=torch.int64, device='cuda')
+tr = torch.zeros(120 * 8, dtype=torch.int64, device='cuda')
 lib = ctypes.CDLL(_lib.LIB_PATH); lib.lsh_debug_set_trace(ctypes.c_void_p(tr.data_ptr()))
 ops.attend_bwd(dims, qv, sticker, o_c, lse, do); torch.cuda.synchronize()
 lib.lsh_debug_set_trace(None)
-t = tr.cpu().view(120, 16)
+t = tr.cpu().view(120, 8)
 t0 = int(t[t > 0].min())
-names = ['mma_pds0', 'mma_pds1', 'mma_done', 'w0_st', 'w0_pass', 'w1_st', 'w1_pass', 'w0_epi', 'kv0_iss', 'kv1_iss', 'st0_iss', 'st1_iss', 'dq_iss', 'w0_tiles', 'epi_kvf', 'prod_req']
+names = ['mma_pds0', 'mma_pds1', 'mma_done', 'w0_st', 'w0_pass', 'w1_st', 'w1_pass', 'w0_epi']
 print('n  ' + ' '.join('%9s' % n for n in names))
-for k in list(range(0, 6)) + list(range(100, 112)):
+for k in list(range(0, 8)) + list(range(100, 116)):
   print('%3d ' % k + ' '.join('%9d' % (int(v) - t0 if v > 0 else -1) for v in t[k]))

@@ -35,25 +35,6 @@
 #define BT_ISSUE_UNROLL _Pragma("unroll")
 #endif
 
-// A/B switches of the round-2 restructuring attempts.  Defaults = what measured fastest at config 2 (ncu, one box,
-// interleaved): every alternative below was slower or equal.
-//   BT_EPI_ORDER  0: epilogue releases the key tile's ring slot at its very end (round 1; 709 us)
-//                 1: dK^/dV loads first, then the key-row math, slot release, dQ (711 us)
-//                 2: key-row math and slot release before the dV loads (with BT_BLOCK16: 756 us)
-//   BT_BLOCK16    0: 32-query blocks, load-then-compute (709 us)
-//                 1: 16-query blocks with the TMEM loads running one block ahead (770-790 us: twice the TMEM instructions)
-//   BT_BOUNDS     0: 8-step binary search per key row and item (714 us)
-//                 1: interval bounds precomputed by chunk_possort_kernel (709 us, but +12 us in that kernel per call)
-#ifndef BT_EPI_ORDER
-#define BT_EPI_ORDER 0
-#endif
-#ifndef BT_BLOCK16
-#define BT_BLOCK16 0
-#endif
-#ifndef BT_BOUNDS
-#define BT_BOUNDS 0
-#endif
-
 namespace lsh {
 
 constexpr int BT_C = 128;
@@ -66,12 +47,10 @@ constexpr uint32_t BT_IDESC_KV = make_idesc_bf16(128, 64, 0, 1);   // dV, dK^ (B
 constexpr uint32_t BT_IDESC_DQ = make_idesc_bf16(128, 64, 1, 1);   // dQ (A and B MN-major)
 
 // trace slots per item: 0 MMA: pds_full[0] seen, 1 MMA: pds_full[1] seen, 2 MMA: item done (commits issued),
-// 3 WG0: st_full seen, 4 WG0: pass done, 5 WG1: st_full seen, 6 WG1: pass done, 7 WG0: epilogue done,
-// 8/9 MMA: dV/dK of half 0/1 issued, 10/11 MMA: next item's S^T half 0/1 issued, 12 MMA: dQ issued, 13 WG0: tiles seen,
-// 14 epilogue: kv_full seen, 15 producer: tile of this item's iteration requested (slot free)
+// 3 WG0: st_full seen, 4 WG0: pass done, 5 WG1: st_full seen, 6 WG1: pass done, 7 WG0: epilogue done
 // (compiled in only with -DLSH_TRACE: the stamps cost instruction-cache space in every role)
 #ifdef LSH_TRACE
-#define BT_TRACE(n, slot) do { if (p.trace && blockIdx.x == 0 && (n) < 120) p.trace[(n) * 16 + (slot)] = clock64(); } while (0)
+#define BT_TRACE(n, slot) do { if (p.trace && blockIdx.x == 0 && (n) < 120) p.trace[(n) * 8 + (slot)] = clock64(); } while (0)
 #else
 #define BT_TRACE(n, slot) do { } while (0)
 #endif
@@ -83,7 +62,6 @@ struct __align__(16) BtTileMeta {
   float dvec[BT_C];     // -D_i = -(do_i . o_i)
   float kscl[BT_C];     // log2(e) / (sqrt(mean(q^2)+eps) * sqrt(dq))
   int tk[BT_C];         // ticker
-  int bnd[BT_C];        // neighbour-chunk interval bounds of the row (chunk_possort_kernel)
 };
 
 struct __align__(16) BtShared {
@@ -182,26 +160,17 @@ __global__ void __launch_bounds__(BT_THREADS, 1) attend_bwd_tc_kernel(const Atte
   if (warp == 12 || warp == 13) {
     // ================================ producers ========================================================
     const int pw = warp - 12;                              // rows [64*pw, 64*pw + 64) of every tile
-    int trace_n = 0;
     auto load_tile = [&](int seq, int u, int cc) {
       const uint32_t slot = bt_slot(seq);
       const int b = u / p.H, h = u - b * p.H;
-      const int64_t soff = static_cast<int64_t>(u) * p.N + cc * BT_C + 64 * pw;
-      const int32_t *stk = p.sticker2 + soff;                     // chunk rows ascending in position
+      const int32_t *stk = p.sticker2 + static_cast<int64_t>(u) * p.N + cc * BT_C + 64 * pw;   // chunk rows ascending in position
       const int tka = __ldg(stk + lane), tkb = __ldg(stk + 32 + lane);
-#if BT_BOUNDS
-      const int bda = __ldg(p.bounds + soff + lane), bdb = __ldg(p.bounds + soff + 32 + lane);
-#endif
       const int pa = tka % p.L, pb = tkb % p.L;
       mbar_wait<128>(&sh.empty[slot], bt_phase(seq) ^ 1);
-      if (tid == 12 * 32) BT_TRACE(trace_n, 15);
       BtTileMeta &mt = sh.meta[slot];
       const int ra = 64 * pw + lane, rb = ra + 32;
       mt.kinfo[ra] = static_cast<float>(pa + 1); mt.kinfo[rb] = static_cast<float>(pb + 1);
       mt.tk[ra] = tka; mt.tk[rb] = tkb;
-#if BT_BOUNDS
-      mt.bnd[ra] = bda; mt.bnd[rb] = bdb;
-#endif
       const int64_t oa = static_cast<int64_t>(u) * p.L + pa, ob = static_cast<int64_t>(u) * p.L + pb;
       cp_async4(smem_u32(&mt.kscl[ra]), p.qscale + oa); cp_async4(smem_u32(&mt.kscl[rb]), p.qscale + ob);
       cp_async4(smem_u32(&mt.lse2[ra]), p.lse2 + oa);   cp_async4(smem_u32(&mt.lse2[rb]), p.lse2 + ob);
@@ -251,7 +220,6 @@ __global__ void __launch_bounds__(BT_THREADS, 1) attend_bwd_tc_kernel(const Atte
       const BtItem it = w.item();
       if (it.first) {               // one visit per iteration: a pre iteration brings two tiles, a real one brings one
         int c_key, c_next;
-        trace_n = it.n;
         w.chunks(c_key, c_next);
         if (!it.real) load_tile(it.seq_k, it.u, c_key);
         load_tile(it.seq_k + 1, it.u, c_next);
@@ -327,11 +295,10 @@ BT_ISSUE_UNROLL
           }
           __syncwarp();
         }
-        if (lane == 0) BT_TRACE(cur.n, 8 + h);
         // region h is free once the MMAs above have read it (in-order pipe)
         probe();
         if (pre_ok) {
-          for (; st_issued <= h; ++st_issued) { issue_st(nxt, st_issued); if (lane == 0) BT_TRACE(cur.n, 10 + st_issued); }
+          for (; st_issued <= h; ++st_issued) issue_st(nxt, st_issued);
         }
       }
       {
@@ -356,16 +323,15 @@ BT_ISSUE_UNROLL
         }
         __syncwarp();
       }
-      if (lane == 0) BT_TRACE(cur.n, 12);
       probe();
       if (pre_ok) {
-        for (; st_issued < 2; ++st_issued) { issue_st(nxt, st_issued); if (lane == 0) BT_TRACE(cur.n, 10 + st_issued); }
+        for (; st_issued < 2; ++st_issued) issue_st(nxt, st_issued);
       }
       if (lane == 0) BT_TRACE(cur.n, 2);
       if (!have_next) break;
       if (st_issued < 2) {
         wait_tiles(nxt);
-        for (; st_issued < 2; ++st_issued) { issue_st(nxt, st_issued); if (lane == 0) BT_TRACE(cur.n, 10 + st_issued); }
+        for (; st_issued < 2; ++st_issued) issue_st(nxt, st_issued);
       }
       cur = nxt;
     }
@@ -376,8 +342,6 @@ BT_ISSUE_UNROLL
     const uint32_t t_lane = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     const uint32_t r_st = t_lane + 128 * h;
     float ksc_j = 0.f, ki_j = 0.f;
-    int lo_next = 0, hi_next = 0;
-    const uint32_t ds_row = ds_u32 + h * (BT_C * 128) + row * 128, r7 = static_cast<uint32_t>(row & 7);
     for (BtWalk w(g0, g1, p.n_chunks); w.valid(); w.next()) {
       const BtItem it = w.item();
       const uint32_t slk = bt_slot(it.seq_k), slq = bt_slot(it.seq_q);
@@ -385,26 +349,21 @@ BT_ISSUE_UNROLL
         mbar_wait(&sh.full[slk], bt_phase(it.seq_k));
         ksc_j = sh.meta[slk].kscl[row];
         ki_j = sh.meta[slk].kinfo[row];
-#if BT_BOUNDS
-        // where this key's position falls among the queries of the NEXT chunk: precomputed by chunk_possort_kernel
-        const int bnd = sh.meta[slk].bnd[row];
-        lo_next = (bnd >> 16) & 0xff; hi_next = lo_next + ((bnd >> 24) & 1);
-#endif
       }
       mbar_wait(&sh.full[slq], bt_phase(it.seq_q));
-      if (row == 0) BT_TRACE(it.n, 13);
       const BtTileMeta &mq = sh.meta[slq];
       const float kst_j = ksc_j * kLn2;                    // true key scale 1/(r*sqrt(dq)) for the dQ operand
       const uint64_t ksc2 = pk2(ksc_j, ksc_j), kst2 = pk2(kst_j, kst_j);
-      const uint32_t ds_dst = ds_row + (it.n & 1) * BT_DS_BYTES;
+      uint8_t *dsrow = dsbuf + (it.n & 1) * BT_DS_BYTES + h * (BT_C * 128);
       // Tiles are ordered by position (chunk_possort_kernel), so for key j the queries of the tile split into three index
       // ranges: [0, lo) position below the key's — never visible (EA:150-152); [lo, hi) the same position — the key's own
       // token or its copy from the neighbouring hash round, visible only to self-only rows (qcmp rule); [hi, 128) visible.
-      // Per warp, a 16-query block is skipped (zeros), evaluated without any mask (no per-query position loads), or
+      // Per warp, a 32-query block is skipped (zeros), evaluated without any mask (no per-query position loads), or
       // — only around the boundary — evaluated with the per-element compare.
-      const bool same = it.seq_q == it.seq_k;
-#if !BT_BOUNDS
-      if (!same) {                                           // lower bound of my position among the query tile's (sorted) positions
+      int lo_j, hi_j;
+      if (it.seq_q == it.seq_k) {
+        lo_j = row; hi_j = row + 1;
+      } else {
         int blo = 0, bhi = 128;
 #pragma unroll
         for (int sidx = 0; sidx < 8; ++sidx) {
@@ -414,121 +373,45 @@ BT_ISSUE_UNROLL
           if (go && v < ki_j) blo = mid + 1;
           else if (go) bhi = mid;
         }
-        lo_next = blo;
-        hi_next = blo + ((blo < 128 && mq.kinfo[blo & 127] == ki_j) ? 1 : 0);
+        lo_j = blo;
+        hi_j = blo + ((blo < 128 && mq.kinfo[blo & 127] == ki_j) ? 1 : 0);
       }
-#endif
-      const int lo_j = same ? row : lo_next, hi_j = same ? row + 1 : hi_next;
       const int min_lo = __reduce_min_sync(0xffffffffu, lo_j), max_hi = __reduce_max_sync(0xffffffffu, hi_j);
-      // skipped blocks are a prefix of my 64 queries: those that lie entirely below every key of this warp
-      int k_first = (min_lo - 64 * h) >> 4;
-      k_first = k_first < 0 ? 0 : (k_first > 4 ? 4 : k_first);
       mbar_wait(&sh.st_full[h], it.n & 1);
       mbar_wait(&sh.dsm_free[it.n & 1], ((it.n >> 1) & 1) ^ 1);
       tc_fence_after();
       if (row == 0) BT_TRACE(it.n, 3 + 2 * h);
-#if BT_BLOCK16
-      uint32_t sa[16], da[16], sb[16], db[16];
-      // one 16-query block: P^T and dS^T (bf16) back into TMEM in place, dS * key scale into the staging tile
-      auto block = [&](const uint32_t (&sv)[16], const uint32_t (&dp)[16], int k) {
-        const int c0 = 64 * h + 16 * k;
-        uint32_t pk_p[8], pk_ds[8], g[8];
-        if (c0 >= max_hi) {
-          // every key of this warp sees every query of the block
-#pragma unroll
-          for (int c4 = 0; c4 < 16; c4 += 4) {
-            const ulonglong2 ls = *reinterpret_cast<const ulonglong2 *>(&mq.lse2[c0 + c4]);   // -lse2 pairs
-            const ulonglong2 dv = *reinterpret_cast<const ulonglong2 *>(&mq.dvec[c0 + c4]);   // -D pairs
-            const uint64_t t01 = ffma2(pk2u(sv[c4 + 0], sv[c4 + 1]), ksc2, ls.x), t23 = ffma2(pk2u(sv[c4 + 2], sv[c4 + 3]), ksc2, ls.y);
-            const uint64_t p01 = pk2(fast_exp2(lo32(t01)), fast_exp2(hi32(t01))), p23 = pk2(fast_exp2(lo32(t23)), fast_exp2(hi32(t23)));
-            const uint64_t d01 = fmul2(p01, fadd2(pk2u(dp[c4 + 0], dp[c4 + 1]), dv.x));
-            const uint64_t d23 = fmul2(p23, fadd2(pk2u(dp[c4 + 2], dp[c4 + 3]), dv.y));
-            const uint64_t g01 = fmul2(d01, kst2), g23 = fmul2(d23, kst2);
-            pk_p[c4 >> 1] = pack_bf16(lo32(p01), hi32(p01));  pk_p[(c4 >> 1) + 1] = pack_bf16(lo32(p23), hi32(p23));
-            pk_ds[c4 >> 1] = pack_bf16(lo32(d01), hi32(d01)); pk_ds[(c4 >> 1) + 1] = pack_bf16(lo32(d23), hi32(d23));
-            g[c4 >> 1] = pack_bf16(lo32(g01), hi32(g01));     g[(c4 >> 1) + 1] = pack_bf16(lo32(g23), hi32(g23));
-          }
-        } else {
-#pragma unroll
-          for (int c4 = 0; c4 < 16; c4 += 4) {
-            const float4 qc = *reinterpret_cast<const float4 *>(&mq.qcmp[c0 + c4]);
-            const ulonglong2 ls = *reinterpret_cast<const ulonglong2 *>(&mq.lse2[c0 + c4]);   // -lse2 pairs
-            const ulonglong2 dv = *reinterpret_cast<const ulonglong2 *>(&mq.dvec[c0 + c4]);   // -D pairs
-            const uint64_t t01 = ffma2(pk2u(sv[c4 + 0], sv[c4 + 1]), ksc2, ls.x), t23 = ffma2(pk2u(sv[c4 + 2], sv[c4 + 3]), ksc2, ls.y);
-            const uint64_t p01 = pk2(fast_exp2(ki_j < qc.x ? lo32(t01) : -INFINITY), fast_exp2(ki_j < qc.y ? hi32(t01) : -INFINITY));
-            const uint64_t p23 = pk2(fast_exp2(ki_j < qc.z ? lo32(t23) : -INFINITY), fast_exp2(ki_j < qc.w ? hi32(t23) : -INFINITY));
-            const uint64_t d01 = fmul2(p01, fadd2(pk2u(dp[c4 + 0], dp[c4 + 1]), dv.x));
-            const uint64_t d23 = fmul2(p23, fadd2(pk2u(dp[c4 + 2], dp[c4 + 3]), dv.y));
-            const uint64_t g01 = fmul2(d01, kst2), g23 = fmul2(d23, kst2);
-            pk_p[c4 >> 1] = pack_bf16(lo32(p01), hi32(p01));  pk_p[(c4 >> 1) + 1] = pack_bf16(lo32(p23), hi32(p23));
-            pk_ds[c4 >> 1] = pack_bf16(lo32(d01), hi32(d01)); pk_ds[(c4 >> 1) + 1] = pack_bf16(lo32(d23), hi32(d23));
-            g[c4 >> 1] = pack_bf16(lo32(g01), hi32(g01));     g[(c4 >> 1) + 1] = pack_bf16(lo32(g23), hi32(g23));
-          }
-        }
-        tmem_st8(r_st + 8 * k, pk_p);
-        tmem_st8(r_st + 64 + 8 * k, pk_ds);
-        sts128(ds_dst + (((2 * k) ^ r7) << 4), g[0], g[1], g[2], g[3]);
-        sts128(ds_dst + (((2 * k + 1) ^ r7) << 4), g[4], g[5], g[6], g[7]);
-      };
-      // TMEM loads run one block ahead of the math (two statically named register sets)
-      if (k_first == 0) { tmem_ld16(r_st, sa); tmem_ld16(r_st + 64, da); }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (k < k_first) {
-          // no key of this warp sees any query of the block
-          uint32_t z[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) z[i] = 0u;
-          tmem_st8(r_st + 8 * k, z);
-          tmem_st8(r_st + 64 + 8 * k, z);
-          sts128(ds_dst + (((2 * k) ^ r7) << 4), 0u, 0u, 0u, 0u);
-          sts128(ds_dst + (((2 * k + 1) ^ r7) << 4), 0u, 0u, 0u, 0u);
-          if (k + 1 == k_first && k + 1 < 4) {
-            if ((k + 1) & 1) { tmem_ld16(r_st + 16 * (k + 1), sb); tmem_ld16(r_st + 64 + 16 * (k + 1), db); }
-            else { tmem_ld16(r_st + 16 * (k + 1), sa); tmem_ld16(r_st + 64 + 16 * (k + 1), da); }
-          }
-        } else if (k & 1) {
-          tmem_ld_wait_dep16(sb, db);
-          if (k + 1 < 4) { tmem_ld16(r_st + 16 * (k + 1), sa); tmem_ld16(r_st + 64 + 16 * (k + 1), da); }
-          block(sb, db, k);
-        } else {
-          tmem_ld_wait_dep16(sa, da);
-          if (k + 1 < 4) { tmem_ld16(r_st + 16 * (k + 1), sb); tmem_ld16(r_st + 64 + 16 * (k + 1), db); }
-          block(sa, da, k);
-        }
-      }
-#else
-      (void)k_first;
 #pragma unroll 1
       for (int cc = 0; cc < 64; cc += 32) {
         const int c0 = 64 * h + cc;
-        uint32_t sv[32], pk_p[16], pk_ds[16];
+        uint32_t s[32], pk_p[16], pk_ds[16];
         if (c0 + 32 <= min_lo) {
           // no key of this warp sees any query of the block
 #pragma unroll
-          for (int i = 0; i < 16; ++i) { pk_p[i] = 0u; sv[i] = 0u; }
+          for (int i = 0; i < 16; ++i) { pk_p[i] = 0u; s[i] = 0u; }
           tmem_st16(r_st + (cc >> 1), pk_p);
           tmem_st16(r_st + 64 + (cc >> 1), pk_p);
         } else {
           uint32_t dp[32];
-          tmem_ld32(r_st + cc, sv);
+          tmem_ld32(r_st + cc, s);
           tmem_ld32(r_st + 64 + cc, dp);
-          tmem_ld_wait_dep(sv);
+          tmem_ld_wait_dep(s);
           tmem_ld_wait_dep(dp);
           if (c0 >= max_hi) {
+            // every key of this warp sees every query of the block
 #pragma unroll
             for (int c4 = 0; c4 < 32; c4 += 4) {
               const ulonglong2 ls = *reinterpret_cast<const ulonglong2 *>(&mq.lse2[c0 + c4]);   // -lse2 pairs
               const ulonglong2 dv = *reinterpret_cast<const ulonglong2 *>(&mq.dvec[c0 + c4]);   // -D pairs
-              const uint64_t t01 = ffma2(pk2u(sv[c4 + 0], sv[c4 + 1]), ksc2, ls.x), t23 = ffma2(pk2u(sv[c4 + 2], sv[c4 + 3]), ksc2, ls.y);
+              const uint64_t t01 = ffma2(pk2u(s[c4 + 0], s[c4 + 1]), ksc2, ls.x), t23 = ffma2(pk2u(s[c4 + 2], s[c4 + 3]), ksc2, ls.y);
               const uint64_t p01 = pk2(fast_exp2(lo32(t01)), fast_exp2(hi32(t01))), p23 = pk2(fast_exp2(lo32(t23)), fast_exp2(hi32(t23)));
               const uint64_t d01 = fmul2(p01, fadd2(pk2u(dp[c4 + 0], dp[c4 + 1]), dv.x));
               const uint64_t d23 = fmul2(p23, fadd2(pk2u(dp[c4 + 2], dp[c4 + 3]), dv.y));
               const uint64_t g01 = fmul2(d01, kst2), g23 = fmul2(d23, kst2);
               pk_p[c4 >> 1] = pack_bf16(lo32(p01), hi32(p01));  pk_p[(c4 >> 1) + 1] = pack_bf16(lo32(p23), hi32(p23));
               pk_ds[c4 >> 1] = pack_bf16(lo32(d01), hi32(d01)); pk_ds[(c4 >> 1) + 1] = pack_bf16(lo32(d23), hi32(d23));
-              sv[c4 >> 1] = pack_bf16(lo32(g01), hi32(g01));
-              sv[(c4 >> 1) + 1] = pack_bf16(lo32(g23), hi32(g23));
+              s[c4 >> 1] = pack_bf16(lo32(g01), hi32(g01));
+              s[(c4 >> 1) + 1] = pack_bf16(lo32(g23), hi32(g23));
             }
           } else {
 #pragma unroll
@@ -536,7 +419,7 @@ BT_ISSUE_UNROLL
               const float4 qc = *reinterpret_cast<const float4 *>(&mq.qcmp[c0 + c4]);
               const ulonglong2 ls = *reinterpret_cast<const ulonglong2 *>(&mq.lse2[c0 + c4]);   // -lse2 pairs
               const ulonglong2 dv = *reinterpret_cast<const ulonglong2 *>(&mq.dvec[c0 + c4]);   // -D pairs
-              const uint64_t t01 = ffma2(pk2u(sv[c4 + 0], sv[c4 + 1]), ksc2, ls.x), t23 = ffma2(pk2u(sv[c4 + 2], sv[c4 + 3]), ksc2, ls.y);
+              const uint64_t t01 = ffma2(pk2u(s[c4 + 0], s[c4 + 1]), ksc2, ls.x), t23 = ffma2(pk2u(s[c4 + 2], s[c4 + 3]), ksc2, ls.y);
               const uint64_t p01 = pk2(fast_exp2(ki_j < qc.x ? lo32(t01) : -INFINITY), fast_exp2(ki_j < qc.y ? hi32(t01) : -INFINITY));
               const uint64_t p23 = pk2(fast_exp2(ki_j < qc.z ? lo32(t23) : -INFINITY), fast_exp2(ki_j < qc.w ? hi32(t23) : -INFINITY));
               const uint64_t d01 = fmul2(p01, fadd2(pk2u(dp[c4 + 0], dp[c4 + 1]), dv.x));
@@ -544,18 +427,21 @@ BT_ISSUE_UNROLL
               const uint64_t g01 = fmul2(d01, kst2), g23 = fmul2(d23, kst2);
               pk_p[c4 >> 1] = pack_bf16(lo32(p01), hi32(p01));  pk_p[(c4 >> 1) + 1] = pack_bf16(lo32(p23), hi32(p23));
               pk_ds[c4 >> 1] = pack_bf16(lo32(d01), hi32(d01)); pk_ds[(c4 >> 1) + 1] = pack_bf16(lo32(d23), hi32(d23));
-              sv[c4 >> 1] = pack_bf16(lo32(g01), hi32(g01));
-              sv[(c4 >> 1) + 1] = pack_bf16(lo32(g23), hi32(g23));
+              // reuse s[] as the staging copy (dS * key scale) for dQ
+              s[c4 >> 1] = pack_bf16(lo32(g01), hi32(g01));
+              s[(c4 >> 1) + 1] = pack_bf16(lo32(g23), hi32(g23));
             }
           }
           tmem_st16(r_st + (cc >> 1), pk_p);
           tmem_st16(r_st + 64 + (cc >> 1), pk_ds);
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          sts128(ds_dst + ((((cc >> 3) + q) ^ r7) << 4), sv[4 * q], sv[4 * q + 1], sv[4 * q + 2], sv[4 * q + 3]);
+        for (int q = 0; q < 4; ++q) {
+          uint4 v;
+          v.x = s[4 * q]; v.y = s[4 * q + 1]; v.z = s[4 * q + 2]; v.w = s[4 * q + 3];
+          *reinterpret_cast<uint4 *>(dsrow + swz(row, (cc >> 3) + q)) = v;
+        }
       }
-#endif
       tmem_st_wait();
       fence_proxy_async();                                 // dS staging writes -> UMMA (async proxy)
       tc_fence_before();
@@ -583,96 +469,53 @@ BT_ISSUE_UNROLL
         const float ksc_j = sh.meta[slk].kscl[row];
         const int tk = sh.meta[slk].tk[row];
         const int64_t orow = (static_cast<int64_t>(it.u) * p.N + tk) * 64;
-        const uint32_t kt_row = tiles_u32 + slk * BT_TILE_BYTES + row * 128, r7 = static_cast<uint32_t>(row & 7);
+        const uint8_t *kt = tiles + slk * BT_TILE_BYTES;
         mbar_wait(&sh.dq_full[it.rit & 1], (it.rit >> 1) & 1);
         mbar_wait(&sh.kv_full, it.rit & 1);
         tc_fence_after();
-        if (row == 0) BT_TRACE(it.n, 14);
         uint32_t dk0[32], dk1[32];
         __nv_bfloat16 *dq_dst = p.dq_out + orow, *dv_dst = p.dv_out + orow;
         tmem_ld32(t_lane + 256, dk0);
         tmem_ld32(t_lane + 288, dk1);
+        // dV first: together with the dK^ loads above it empties both accumulators, so the next key chunk's dV / dK^
+        // MMAs (kv_free) wait for four TMEM loads instead of the whole epilogue
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t g[32];
+          tmem_ld32(t_lane + 320 + 32 * half, g);
+          tmem_ld_wait_dep(g);
+          if (half == 1) {
+            tmem_ld_wait_dep(dk0);
+            tmem_ld_wait_dep(dk1);
+            tc_fence_before();
+            mbar_arrive(&sh.kv_free);
+          }
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            uint4 v;
+            v.x = pack_bf16(__uint_as_float(g[8 * q4 + 0]), __uint_as_float(g[8 * q4 + 1]));
+            v.y = pack_bf16(__uint_as_float(g[8 * q4 + 2]), __uint_as_float(g[8 * q4 + 3]));
+            v.z = pack_bf16(__uint_as_float(g[8 * q4 + 4]), __uint_as_float(g[8 * q4 + 5]));
+            v.w = pack_bf16(__uint_as_float(g[8 * q4 + 6]), __uint_as_float(g[8 * q4 + 7]));
+            *reinterpret_cast<uint4 *>(dv_dst + half * 32 + q4 * 8) = v;
+          }
+        }
+        float dot = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          const uint4 raw = *reinterpret_cast<const uint4 *>(kt + swz(row, ch));
+          const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 q2 = unpack_bf16(rw[e]);
+            const int c = ch * 8 + e * 2;
+            dot = fmaf(__uint_as_float(c < 32 ? dk0[c] : dk1[c - 32]), q2.x, dot);
+            dot = fmaf(__uint_as_float(c + 1 < 32 ? dk0[c + 1] : dk1[c + 1 - 32]), q2.y, dot);
+          }
+        }
         const float r_j = 0.125f * kLog2e / ksc_j;       // sqrt(mean(q^2) + eps)
         const float a_j = 0.125f / r_j;
-        // Key-side length-normalisation VJP (App. B5): afterwards dk0 / dk1 hold
-        //   e = dK^ / (r sqrt(dq)) - q (dK^ . q) / (dq r^3 sqrt(dq)),  which is added to dQ below.
-        // It is the only reader of the key tile's rows in this role: the ring slot goes back to the producers right after
-        // it instead of at the end of the epilogue (the next tile's gather starts that much earlier).
-        auto key_side = [&]() {
-          float dot = 0.f;
-#pragma unroll
-          for (int ch = 0; ch < 8; ++ch) {
-            const uint4 raw = lds128u(kt_row + ((ch ^ r7) << 4));
-            const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 q2 = unpack_bf16(rw[e]);
-              const int c = ch * 8 + e * 2;
-              dot = fmaf(__uint_as_float(c < 32 ? dk0[c] : dk1[c - 32]), q2.x, dot);
-              dot = fmaf(__uint_as_float(c + 1 < 32 ? dk0[c + 1] : dk1[c + 1 - 32]), q2.y, dot);
-            }
-          }
-          const float c_j = dot * 0.125f / (64.f * r_j * r_j * r_j);
-#pragma unroll
-          for (int ch = 0; ch < 8; ++ch) {
-            const uint4 raw = lds128u(kt_row + ((ch ^ r7) << 4));
-            const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 q2 = unpack_bf16(rw[e]);
-              const int c = ch * 8 + e * 2;
-              if (c < 32) {
-                dk0[c] = __float_as_uint(__uint_as_float(dk0[c]) * a_j - q2.x * c_j);
-                dk0[c + 1] = __float_as_uint(__uint_as_float(dk0[c + 1]) * a_j - q2.y * c_j);
-              } else {
-                dk1[c - 32] = __float_as_uint(__uint_as_float(dk1[c - 32]) * a_j - q2.x * c_j);
-                dk1[c - 31] = __float_as_uint(__uint_as_float(dk1[c - 31]) * a_j - q2.y * c_j);
-              }
-            }
-          }
-        };
-        auto release_slot = [&]() {
-          mbar_arrive(&sh.empty[slk]);
-          if (it.last_seg) mbar_arrive(&sh.empty[bt_slot(it.seq_k + 1)]);
-        };
-        // dV: once its loads (and the dK^ loads above) are done both accumulators are empty and the next key chunk may
-        // accumulate (kv_free)
-        auto drain_dv = [&]() {
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            uint32_t g[32];
-            tmem_ld32(t_lane + 320 + 32 * half, g);
-            tmem_ld_wait_dep(g);
-            if (half == 1) {
-              tmem_ld_wait_dep(dk0);
-              tmem_ld_wait_dep(dk1);
-              tc_fence_before();
-              mbar_arrive(&sh.kv_free);
-            }
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              uint4 v;
-              v.x = pack_bf16(__uint_as_float(g[8 * q4 + 0]), __uint_as_float(g[8 * q4 + 1]));
-              v.y = pack_bf16(__uint_as_float(g[8 * q4 + 2]), __uint_as_float(g[8 * q4 + 3]));
-              v.z = pack_bf16(__uint_as_float(g[8 * q4 + 4]), __uint_as_float(g[8 * q4 + 5]));
-              v.w = pack_bf16(__uint_as_float(g[8 * q4 + 6]), __uint_as_float(g[8 * q4 + 7]));
-              *reinterpret_cast<uint4 *>(dv_dst + half * 32 + q4 * 8) = v;
-            }
-          }
-        };
-#if BT_EPI_ORDER == 2
-        tmem_ld_wait_dep(dk0);
-        tmem_ld_wait_dep(dk1);
-        key_side();
-        release_slot();
-        drain_dv();
-#else
-        drain_dv();
-        key_side();
-#if BT_EPI_ORDER == 1
-        release_slot();
-#endif
-#endif
+        const float c_j = dot * 0.125f / (64.f * r_j * r_j * r_j);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           uint32_t g[32];
@@ -683,21 +526,25 @@ BT_ISSUE_UNROLL
             mbar_arrive(&sh.dq_free[it.rit & 1]);
           }
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const int ch = half * 4 + c4;
+            const uint4 raw = *reinterpret_cast<const uint4 *>(kt + swz(row, ch));
+            const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
             uint32_t o[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const int c = q4 * 8 + e * 2;              // column within this half
-              const float e0 = __uint_as_float(half == 0 ? dk0[c] : dk1[c]), e1 = __uint_as_float(half == 0 ? dk0[c + 1] : dk1[c + 1]);
-              o[e] = pack_bf16(__uint_as_float(g[c]) + e0, __uint_as_float(g[c + 1]) + e1);
+              const float2 q2 = unpack_bf16(rw[e]);
+              const int c = c4 * 8 + e * 2;              // column within this half
+              const float k0 = __uint_as_float(half == 0 ? dk0[c] : dk1[c]), k1 = __uint_as_float(half == 0 ? dk0[c + 1] : dk1[c + 1]);
+              o[e] = pack_bf16(__uint_as_float(g[c]) + k0 * a_j - q2.x * c_j, __uint_as_float(g[c + 1]) + k1 * a_j - q2.y * c_j);
             }
             uint4 v; v.x = o[0]; v.y = o[1]; v.z = o[2]; v.w = o[3];
-            *reinterpret_cast<uint4 *>(dq_dst + (half * 4 + q4) * 8) = v;
+            *reinterpret_cast<uint4 *>(dq_dst + ch * 8) = v;
           }
         }
-#if BT_EPI_ORDER == 0
-        release_slot();
-#endif
+        // last read of the key tile's rows is behind us: give the ring slot back
+        mbar_arrive(&sh.empty[slk]);
+        if (it.last_seg) mbar_arrive(&sh.empty[bt_slot(it.seq_k + 1)]);
         if (row == 0) BT_TRACE(it.n, 7);
       } else {
         mbar_arrive(&sh.empty[slk]);                           // pre item: this warpgroup never touches the tile
@@ -709,7 +556,11 @@ BT_ISSUE_UNROLL
   if (warp == 14) tmem_dealloc(tmem, 512);
 }
 
-bool attend_bwd_tc_uses_bounds() { return BT_BOUNDS != 0; }
+// Round-2 restructuring attempts of this kernel (all measured slower or equal at config 2; the
+// code is in the history at commit "Backward kernel: A/B switches ..."): precomputed interval bounds instead of the binary
+// search (-0.7 %, but +12 us in chunk_possort_kernel), 16-query blocks with TMEM loads one block ahead (+9 %), early
+// release of the key tile's ring slot by the epilogue (+-0).
+bool attend_bwd_tc_uses_bounds() { return false; }
 
 int attend_bwd_tc_run(const AttendBwdTcParams &p, int BH, cudaStream_t stream) {
   const size_t smem = static_cast<size_t>(BT_NST) * BT_TILE_BYTES + 2 * BT_DS_BYTES + 1024;
