@@ -32,10 +32,10 @@ def test_layer_against_lsh_small_fixture():
   state = (_cu(g['buckets']).to(torch.int32), layer.state[1])
   out, _, dx, dw = layer.forward_and_or_backward(x, layer.weights, state, None, output_grad=_cu(g['dout']),
                                                  compute_output=True, update_state=False)
-  util.assert_close(out.cpu().numpy(), g['out'], 'out')
-  util.assert_close(dx.cpu().numpy(), g['dx'], 'dx')
+  util.assert_close_layer(out.cpu().numpy(), g['out'], 'out')
+  util.assert_close_layer(dx.cpu().numpy(), g['dx'], 'dx')
   for k, w in zip(('dw_q', 'dw_v', 'dw_o'), dw):
-    util.assert_close(w.cpu().numpy(), g[k], k)
+    util.assert_close_layer(w.cpu().numpy(), g[k], k)
   dims = _lib.make_dims(1, 2, 128, 32, 64, 64, 64, 1, 0, 2, [4, 2], True, False, _lib.LSH_DTYPE_F32)
   sticker, undo = ops.sort(dims, state[0])
   np.testing.assert_array_equal(sticker[0].cpu().numpy(), g['sticker0'])
@@ -60,12 +60,12 @@ def test_reversible_block_against_reversible_c128_fixture(dtype):
   ctx = _cu(x2, dtype)
   (rx1, _), ((_, g2), ((ds, db), dw)) = block.reverse_and_grad((_cu(g['y1'], dtype), ctx), (_cu(ct1, dtype), _cu(ct2, dtype)),
                                                                block.weights, None, state, None)
-  util.assert_close(rx1.float().cpu().numpy(), x1, 'reconstructed x1', rtol=3e-2)
-  util.assert_close(g2.float().cpu().numpy(), g['ct2_out'], 'ct_x2')
-  util.assert_close(ds.cpu().numpy(), g['d_scale'], 'd_scale')
-  util.assert_close(db.cpu().numpy(), g['d_bias'], 'd_bias')
+  util.assert_close_layer(rx1.float().cpu().numpy(), x1, 'reconstructed x1', rtol=3e-2)
+  util.assert_close_layer(g2.float().cpu().numpy(), g['ct2_out'], 'ct_x2')
+  util.assert_close_layer(ds.cpu().numpy(), g['d_scale'], 'd_scale')
+  util.assert_close_layer(db.cpu().numpy(), g['d_bias'], 'd_bias')
   for k, w in zip(('dw_q', 'dw_v', 'dw_o'), dw):
-    util.assert_close(w.float().cpu().numpy(), g[k], k)
+    util.assert_close_layer(w.float().cpu().numpy(), g[k], k)
 
 
 # ---- reference_live.npz: what google/trax's own code returned for these inputs (tests/golden/make_reference_golden.py) ----
@@ -98,14 +98,14 @@ def test_layer_against_the_live_reference(name):
   state = (torch.from_numpy(g[name + '/buckets']).cuda(), layer.state[1])
   out, _, dx, dw = layer.forward_and_or_backward(inputs, weights, state, None, output_grad=_cu(d['dout']),
                                                  compute_output=True, update_state=False)
-  util.assert_close(out.cpu().numpy(), g[name + '/out'], 'out vs the reference')
+  util.assert_close_layer(out.cpu().numpy(), g[name + '/out'], 'out vs the reference')
   dx = dx[0] if c['masked'] else dx
   cfg = O.LSHConfig(n_heads=H, d_qk=64, d_v=64, causal=c['causal'], masked=c['masked'], chunk_len=c['C'],
                     n_chunks_before=c['nb'], n_chunks_after=c['na'], n_hashes=c['nh'], n_buckets=c['n_buckets'])
   _, _, want_dx, want_dw = O.forward_and_or_backward(cfg, d['x'], (d['w_q'], d['w_v'], d['w_o']), buckets=g[name + '/buckets'],
                                                      mask=d['mask'], output_grad=d['dout'], update_state=False)
   for key, got, want in zip(('x', 'w_q', 'w_v', 'w_o'), (dx,) + tuple(dw), (want_dx,) + tuple(want_dw)):
-    util.assert_close(got.float().cpu().numpy(), want, 'd' + key)
+    util.assert_close_layer(got.float().cpu().numpy(), want, 'd' + key)
     _directional_ok(got.float().cpu().numpy(), d['dir_' + key], float(g[name + '/ddir_' + key]), 'd' + key)
 
 
@@ -148,22 +148,22 @@ def test_wrapper_against_the_live_reference(name):
   state = ((), (torch.from_numpy(g[name + '/buckets']).cuda(), wrap.state[1][1]), (), ())
   out, _, dx, dw = wrap.forward_and_or_backward(_cu(d['x']), weights, state, None, output_grad=_cu(d['dout']),
                                                 update_state=False)
-  util.assert_close(out.cpu().numpy(), g[name + '/out'], 'out vs the reference')
+  util.assert_close_layer(out.cpu().numpy(), g[name + '/out'], 'out vs the reference')
   cfg = O.LSHConfig(n_heads=c['H'], d_qk=64, d_v=64, causal=True, masked=False, chunk_len=c['C'], n_chunks_before=1,
                     n_chunks_after=0, n_hashes=c['nh'], n_buckets=c['n_buckets'])
   _, _, want_dx, (want_qkv, want_dense) = O.pure_lsh_wrapper(cfg, d['x'], d['qkv'], d['dense'], buckets=g[name + '/buckets'],
                                                              output_grad=d['dout'], rotary_position_emb=c['rotary'])
   leaves = lambda w: list(w) if isinstance(w, tuple) else [w]
-  util.assert_close(dx.cpu().numpy(), want_dx, 'dx')
+  util.assert_close_layer(dx.cpu().numpy(), want_dx, 'dx')
   _directional_ok(dx.cpu().numpy(), d['dir_x'], float(g[name + '/ddir_x']), 'dx')
   for i in range(c['num_weights']):
     for got, want in zip(leaves(dw[0][i]), leaves(want_qkv[i])):
-      util.assert_close(got.cpu().numpy(), want, 'd_qkv[%d]' % i)
+      util.assert_close_layer(got.cpu().numpy(), want, 'd_qkv[%d]' % i)
     got = np.concatenate([l.cpu().numpy().ravel() for l in leaves(dw[0][i])])
     direction = np.concatenate([l.ravel() for l in leaves(d['dir_qkv'][i])])
     _directional_ok(got, direction, float(g[name + '/ddir_qkv%d' % i]), 'd_qkv[%d]' % i)
   for got, want in zip(leaves(dw[3]), leaves(want_dense)):
-    util.assert_close(got.cpu().numpy(), want, 'd_dense')
+    util.assert_close_layer(got.cpu().numpy(), want, 'd_dense')
 
 
 def test_reversible_block_against_the_live_reference():
@@ -187,8 +187,8 @@ def test_reversible_block_against_the_live_reference():
   y1_ref = _cu(g[name + '/y1'])
   (rx1, _), ((_, g2), ((ds, db), dw)) = block.reverse_and_grad(
       (y1_ref, ctx), (_cu(d['ct_y1']), torch.zeros_like(ctx)), block.weights, None, state, None)
-  util.assert_close(rx1.cpu().numpy(), d['x1'], 'x1 reconstructed from the reference y1', rtol=3e-2)
+  util.assert_close_layer(rx1.cpu().numpy(), d['x1'], 'x1 reconstructed from the reference y1', rtol=3e-2)
   for key, got in zip(('x2', 'scale', 'bias', 'w_q', 'w_v', 'w_o'), (g2, ds, db) + tuple(dw)):
     _directional_ok(got.float().cpu().numpy(), d['dir_' + key], float(g[name + '/ddir_' + key]), 'd' + key)
   if mismatch == 0.0:
-    util.assert_close(y1.cpu().numpy(), g[name + '/y1'], 'y1 vs the reference')
+    util.assert_close_layer(y1.cpu().numpy(), g[name + '/y1'], 'y1 vs the reference')

@@ -121,16 +121,16 @@ def test_pure_lsh_wrapper_matches_oracle(num_weights, bias, rotary, dtype):
   qkv_w, dense_w = tuple(np_w(w) for w in weights[0]), np_w(weights[3])
   want_out, _, want_dx, (want_dqkv, want_ddense) = O.pure_lsh_wrapper(
       cfg, x, qkv_w, dense_w, buckets=buckets, output_grad=dout, rotary_position_emb=rotary)
-  util.assert_close(out.float().cpu().numpy(), want_out, 'wrapper out')
+  util.assert_close_layer(out.float().cpu().numpy(), want_out, 'wrapper out')
   out2, new_state, dx, dw = wrap.forward_and_or_backward(xd, weights, wrap.state, None,
                                                          output_grad=torch.from_numpy(dout).cuda(), update_state=False)
   assert new_state is None
   np.testing.assert_array_equal(wrap.state[1][0].cpu().numpy(), buckets)
-  util.assert_close(out2.float().cpu().numpy(), want_out, 'wrapper out (backward call)')
-  util.assert_close(dx.float().cpu().numpy(), want_dx, 'wrapper dx')
+  util.assert_close_layer(out2.float().cpu().numpy(), want_out, 'wrapper out (backward call)')
+  util.assert_close_layer(dx.float().cpu().numpy(), want_dx, 'wrapper dx')
   leaves = lambda w: list(w) if isinstance(w, tuple) else [w]
   for i in range(num_weights):
     for got, want in zip(leaves(dw[0][i]), leaves(want_dqkv[i])):
-      util.assert_close(got.float().cpu().numpy(), want, 'wrapper d_qkv[%d]' % i)
+      util.assert_close_layer(got.float().cpu().numpy(), want, 'wrapper d_qkv[%d]' % i)
   for got, want in zip(leaves(dw[3]), leaves(want_ddense)):
-    util.assert_close(got.float().cpu().numpy(), want, 'wrapper d_dense')
+    util.assert_close_layer(got.float().cpu().numpy(), want, 'wrapper d_dense')

@@ -23,14 +23,14 @@ def test_layernorm_fwd_bwd(rows, D, dtype):
   bias = (0.1 * rng.standard_normal(D)).astype(np.float32)
   cu = lambda a, dt=torch.float32: torch.from_numpy(np.asarray(a, np.float32)).cuda().to(dt)
   z, stats = R.layernorm_fwd(cu(x, dtype), cu(scale), cu(bias))
-  util.assert_close(z.float().cpu().numpy(), O.layernorm(x, scale, bias), 'z')
+  util.assert_close_layer(z.float().cpu().numpy(), O.layernorm(x, scale, bias), 'z')
   ct_out, d_scale, d_bias = R.layernorm_bwd(cu(x, dtype), cu(dz, dtype), cu(ct, dtype), stats, cu(scale))
   dx, ws, wb = O.layernorm_vjp(x, scale, dz)
-  util.assert_close(ct_out.float().cpu().numpy(), ct + dx, 'ct + dx')
-  util.assert_close(d_scale.cpu().numpy(), ws, 'd_scale')
-  util.assert_close(d_bias.cpu().numpy(), wb, 'd_bias')
+  util.assert_close_layer(ct_out.float().cpu().numpy(), ct + dx, 'ct + dx')
+  util.assert_close_layer(d_scale.cpu().numpy(), ws, 'd_scale')
+  util.assert_close_layer(d_bias.cpu().numpy(), wb, 'd_bias')
   only_dx, _, _ = R.layernorm_bwd(cu(x, dtype), cu(dz, dtype), None, stats, cu(scale))
-  util.assert_close(only_dx.float().cpu().numpy(), dx, 'dx')
+  util.assert_close_layer(only_dx.float().cpu().numpy(), dx, 'dx')
 
 
 @pytest.mark.parametrize('B,L,D,dtype,cfg', [
@@ -65,7 +65,7 @@ def test_reversible_half_forward_and_reverse_and_grad(B, L, D, dtype, cfg):
   buckets = block.state[1][0].cpu().numpy()
   z = O.layernorm(x2, scale, bias)
   want_res, _, _, _ = O.forward_and_or_backward(cfg, z, attn_w, buckets=buckets, update_state=False)
-  util.assert_close(y1.float().cpu().numpy(), x1 + want_res, 'y1')
+  util.assert_close_layer(y1.float().cpu().numpy(), x1 + want_res, 'y1')
   assert ctx.data_ptr() == ctx.data_ptr() and torch.equal(ctx.float().cpu(), torch.from_numpy(x2))
 
   # reverse_and_grad from (y1, x2) and cotangents
@@ -74,14 +74,14 @@ def test_reversible_half_forward_and_reverse_and_grad(B, L, D, dtype, cfg):
       (y1, ctx), (cu(ct_y1, dtype), cu(ct_x2, dtype)), block.weights, None, block.state, None)
   (wx1, _), ((_, w_ct_x2), ((w_ds, w_db), w_dw)) = O.reversible_half_reverse_and_grad(
       cfg, y1_np, x2, ct_y1, ct_x2, (scale, bias), attn_w, buckets)
-  util.assert_close(rx1.float().cpu().numpy(), wx1, 'reconstructed x1')
-  util.assert_close(rx1.float().cpu().numpy(), x1, 'reconstructed x1 vs the original input', rtol=3e-2)
+  util.assert_close_layer(rx1.float().cpu().numpy(), wx1, 'reconstructed x1')
+  util.assert_close_layer(rx1.float().cpu().numpy(), x1, 'reconstructed x1 vs the original input', rtol=3e-2)
   assert torch.equal(rx2, ctx) and torch.equal(g_y1.float().cpu(), torch.from_numpy(ct_y1))
-  util.assert_close(g_x2.float().cpu().numpy(), w_ct_x2, 'ct_x2')
-  util.assert_close(d_scale.cpu().numpy(), w_ds, 'd_scale')
-  util.assert_close(d_bias.cpu().numpy(), w_db, 'd_bias')
+  util.assert_close_layer(g_x2.float().cpu().numpy(), w_ct_x2, 'ct_x2')
+  util.assert_close_layer(d_scale.cpu().numpy(), w_ds, 'd_scale')
+  util.assert_close_layer(d_bias.cpu().numpy(), w_db, 'd_bias')
   for n, g, w in zip(('dw_q', 'dw_v', 'dw_o'), dw, w_dw):
-    util.assert_close(g.float().cpu().numpy(), w, n)
+    util.assert_close_layer(g.float().cpu().numpy(), w, n)
 
 
 def test_reversible_half_around_the_pure_lsh_wrapper():
@@ -110,21 +110,21 @@ def test_reversible_half_around_the_pure_lsh_wrapper():
   z = O.layernorm(x2, scale, bias)
   want_res, _, want_dz, (want_dqkv, want_ddense) = O.pure_lsh_wrapper(cfg, z, qkv_w, dense_w, buckets=buckets,
                                                                      output_grad=ct_y1)
-  util.assert_close(y1.cpu().numpy(), x1 + want_res, 'y1')
+  util.assert_close_layer(y1.cpu().numpy(), x1 + want_res, 'y1')
   (rx1, rx2), ((g_y1, g_x2), ((d_scale, d_bias), dw)) = block.reverse_and_grad(
       (y1, ctx), (cu(ct_y1), cu(ct_x2)), block.weights, None, block.state, None)
-  util.assert_close(rx1.cpu().numpy(), x1, 'reconstructed x1', rtol=3e-2)
+  util.assert_close_layer(rx1.cpu().numpy(), x1, 'reconstructed x1', rtol=3e-2)
   assert torch.equal(rx2, ctx) and torch.equal(g_y1.cpu(), torch.from_numpy(ct_y1))
   w_dx2, w_ds, w_db = O.layernorm_vjp(x2, scale, want_dz)
-  util.assert_close(g_x2.cpu().numpy(), ct_x2 + w_dx2, 'ct_x2')
-  util.assert_close(d_scale.cpu().numpy(), w_ds, 'd_scale')
-  util.assert_close(d_bias.cpu().numpy(), w_db, 'd_bias')
+  util.assert_close_layer(g_x2.cpu().numpy(), ct_x2 + w_dx2, 'ct_x2')
+  util.assert_close_layer(d_scale.cpu().numpy(), w_ds, 'd_scale')
+  util.assert_close_layer(d_bias.cpu().numpy(), w_db, 'd_bias')
   assert dw[1] == () and dw[2] == ()
   for i in range(3):
     for got, want, nm in zip(dw[0][i], want_dqkv[i], ('kernel', 'bias')):
-      util.assert_close(got.cpu().numpy(), want, 'd_qkv[%d] %s' % (i, nm))
+      util.assert_close_layer(got.cpu().numpy(), want, 'd_qkv[%d] %s' % (i, nm))
   for got, want, nm in zip(dw[3], want_ddense, ('kernel', 'bias')):
-    util.assert_close(got.cpu().numpy(), want, 'd_dense %s' % nm)
+    util.assert_close_layer(got.cpu().numpy(), want, 'd_dense %s' % nm)
 
 
 def test_reversible_half_with_output_dropout_uses_one_mask_in_both_passes():
@@ -149,7 +149,7 @@ def test_reversible_half_with_output_dropout_uses_one_mask_in_both_passes():
   assert 0.2 < dropped.mean() < 0.8, 'output dropout 0.5 should zero about half of the d_model columns'
   (rx1, _), ((_, g_x2), _) = block.reverse_and_grad((y1, ctx), (cu(ct_y1), cu(ct_x2)), block.weights, None, block.state,
                                                     key)
-  util.assert_close(rx1.cpu().numpy(), x1, 'x1 reconstructed through the same dropout mask', rtol=3e-2)
+  util.assert_close_layer(rx1.cpu().numpy(), x1, 'x1 reconstructed through the same dropout mask', rtol=3e-2)
   # a different key draws a different mask: the reconstruction must then differ (the test has teeth)
   (bad, _), _ = block.reverse_and_grad((y1, ctx), (cu(ct_y1), cu(ct_x2)), block.weights, None, block.state,
                                        np.array([33, 44], np.uint32))

@@ -36,11 +36,11 @@ def test_self_attention_share_qk_matches_oracle(B, L, D, H, C, nb, na, causal, m
   x_d = torch.from_numpy(x).cuda().to(dtype)
   inputs = (x_d, torch.from_numpy(mask).cuda()) if masked else x_d
   out = layer.forward(inputs)
-  util.assert_close(out.float().cpu().numpy(), want_out, 'out')
+  util.assert_close_layer(out.float().cpu().numpy(), want_out, 'out')
   dx, dw = layer.backward(inputs, out, torch.from_numpy(dout).cuda().to(dtype), weights, (), (), None)
-  util.assert_close((dx[0] if masked else dx).float().cpu().numpy(), want_dx, 'dx')
+  util.assert_close_layer((dx[0] if masked else dx).float().cpu().numpy(), want_dx, 'dx')
   for name, g, w in zip(('dw_q', 'dw_v', 'dw_o'), dw, want_dw):
-    util.assert_close(g.cpu().numpy(), w, name)
+    util.assert_close_layer(g.cpu().numpy(), w, name)
 
 
 def test_self_attention_rejects_what_is_not_built():
