@@ -46,7 +46,8 @@ class SelfAttention(LSHSelfAttention):
                                                    update_state=True)
     return output
 
-  def forward_and_or_backward(self, inputs, weights, state, rng, output_grad=None, compute_output=True, update_state=True):
+  def _forward_and_or_backward(self, inputs, weights, state, rng, output_grad=None, compute_output=True, update_state=True,
+                               _stash=None):
     x = inputs[0] if isinstance(inputs, (tuple, list)) else inputs
     if not torch.cuda.is_available():
       from trax_b200 import _lib
@@ -54,6 +55,7 @@ class SelfAttention(LSHSelfAttention):
     dev = x.device if x.is_cuda else torch.device('cuda', torch.cuda.current_device())
     # identity permutation == stable sort of constant bucket ids (EA:1946-1947)
     buckets = torch.zeros((int(x.shape[0]) * self._n_heads, int(x.shape[1])), dtype=torch.int32, device=dev)
-    out, _, inputs_grad, weights_grad = super().forward_and_or_backward(
-        inputs, weights, (buckets, None), rng, output_grad=output_grad, compute_output=compute_output, update_state=False)
+    out, _, inputs_grad, weights_grad = super()._forward_and_or_backward(
+        inputs, weights, (buckets, None), rng, output_grad=output_grad, compute_output=compute_output, update_state=False,
+        _stash=_stash)
     return out, (state if update_state else None), inputs_grad, weights_grad
