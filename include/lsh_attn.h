@@ -97,10 +97,14 @@ int lsh_sort(const LshAttnDims *dims, const int32_t *buckets, int64_t buckets_st
  * their ticker slot).  o_rounds may alias o_comb's layout when nh==1 via lsh_attend_fwd_strided. */
 /* The workspace holds the per-call auxiliaries of the tcgen05 path: per-token key scale, normalised keys
  * q / (8 r) (EA:229-231), {query scale, softmax shift} pairs and the position-sorted chunks (see lsh_chunk_possort). */
+/* attn_keep (may be NULL): the attention-dropout multiplier of EA:254-262, a (chunk_len, window) f32 matrix with values in
+ * {0, 1 / (1 - rate)} drawn by the caller (`bernoulli(rng, keep_prob, (C, W)) / keep_prob`, EA:258-262; a JAX host draws it
+ * with jax.random from `attend_rng`, EA:1920) — ONE matrix per call, shared by every chunk, unit and hash round.  It
+ * multiplies exp(dots - lse) before the product with v; the returned log-sum-exp does not see it. */
 size_t lsh_attend_fwd_workspace_bytes(const LshAttnDims *dims);
 int lsh_attend_fwd(const LshAttnDims *dims, const void *qv_bf16, const int32_t *sticker,
-                   const uint8_t *mask, void *o_rounds_bf16, float *logits, void *ws, size_t ws_bytes,
-                   void *stream);
+                   const uint8_t *mask, const float *attn_keep, void *o_rounds_bf16, float *logits, void *ws,
+                   size_t ws_bytes, void *stream);
 
 /* Internal order used by the tcgen05 attention kernels (chunk_len 128): sticker2 = sticker with every 128-slot
  * chunk re-ordered by token position (ticker % L, ascending; ties keep slot order).  Attention inside a chunk
@@ -126,7 +130,7 @@ int lsh_project_out(const LshAttnDims *dims, const void *o_comb_bf16, const void
  * (B,L,H,dv) bf16.  Writes dqv (B,L,H,dq+dv) bf16, the cotangent of qv. */
 size_t lsh_attend_bwd_workspace_bytes(const LshAttnDims *dims);
 int lsh_attend_bwd(const LshAttnDims *dims, const void *qv_bf16, const int32_t *sticker,
-                   const uint8_t *mask, const void *o_comb_bf16, const float *lse_tot,
+                   const uint8_t *mask, const float *attn_keep, const void *o_comb_bf16, const float *lse_tot,
                    const void *do_comb_bf16, void *dqv_bf16, void *ws, size_t ws_bytes,
                    void *stream);
 
@@ -158,8 +162,8 @@ size_t lsh_layer_workspace_bytes(const LshAttnDims *dims, int with_grad);
 /* compute_output=True.  update_state=True when `rotations` != NULL: buckets are computed and
  * written (EA:1926-1937); otherwise buckets are read (EA:1939-1941). */
 int lsh_layer_fwd(const LshAttnDims *dims, const void *x, const float *w_q, const float *w_v,
-                  const float *w_o, const float *rotations, const uint8_t *mask, int32_t *buckets,
-                  int64_t buckets_stride, void *out, void *ws, size_t ws_bytes, void *stream);
+                  const float *w_o, const float *rotations, const uint8_t *mask, const float *attn_keep,
+                  int32_t *buckets, int64_t buckets_stride, void *out, void *ws, size_t ws_bytes, void *stream);
 
 /* output_grad given, update_state=False: recomputes the forward from the stored buckets, then the
  * backward.  `out` may be NULL (compute_output=False, EA:2256-2258) or a buffer
@@ -168,7 +172,7 @@ int lsh_layer_fwd(const LshAttnDims *dims, const void *x, const float *w_q, cons
  * sum over heads (EA:2430).  Work is ordered on `stream`; one GEMM (do = dout·w_o^T) runs on an internal
  * helper stream that is forked from and joined back into `stream` by events (no host wait, capture-safe). */
 int lsh_layer_bwd(const LshAttnDims *dims, const void *x, const float *w_q, const float *w_v,
-                  const float *w_o, const uint8_t *mask, const int32_t *buckets,
+                  const float *w_o, const uint8_t *mask, const float *attn_keep, const int32_t *buckets,
                   int64_t buckets_stride, const void *dout, void *out, void *dx, float *dw_q,
                   float *dw_v, float *dw_o, void *ws, size_t ws_bytes, void *stream);
 

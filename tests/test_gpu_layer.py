@@ -220,8 +220,8 @@ def test_unsupported_shapes_are_rejected():
     layer.forward(torch.zeros(2, 10, 13, device='cuda'))
   with pytest.raises(NotImplementedError):
     trax_b200.LSHSelfAttention(mode='predict', causal=True)
-  with pytest.raises(NotImplementedError):
-    trax_b200.LSHSelfAttention(attention_dropout=0.1)
+  with pytest.raises(ValueError):
+    trax_b200.LSHSelfAttention(attention_dropout=1.0)
   with pytest.raises(ValueError):
     trax_b200.LSHSelfAttention(n_heads=6, n_parallel_heads=4)
 
@@ -378,3 +378,42 @@ def test_fresh_host_tensors_are_never_served_from_a_stale_device_copy():
   dx_h, _ = layer.backward(x0, out, g, layer.weights, None, layer.state, None)
   dx_d, _ = layer.backward(x0.cuda(), out, g.cuda(), layer.weights, None, layer.state, None)
   assert torch.equal(dx_h, dx_d.cpu())
+
+
+@pytest.mark.parametrize('B,L,D,dtype,cfg', [
+    (2, 512, 128, torch.bfloat16, util.make_cfg(H=4, C=128, nh=4, n_buckets=None)),               # config-2 style (tcgen05 forward)
+    (1, 1024, 256, torch.float32, util.make_cfg(H=2, C=64, nh=1, n_buckets=32)),                  # BASELINE config 1
+])
+def test_layer_with_attention_and_output_dropout(B, L, D, dtype, cfg):
+  """Both reference training configs use attention_dropout = 0.2 (reformer_enwik8.gin:94, reformer_imagenet64.gin:69):
+  forward, fused forward+backward and backward against the oracle with the SAME keep matrices (EA:254-262, 271-280)."""
+  x, weights, rot, dout, _ = _case(61, B, L, D, cfg, dtype)
+  layer = _layer(cfg, attention_dropout=0.2, output_dropout=0.1)
+  key = np.array([7, 9], np.uint32)
+  W = cfg.chunk_len * (1 + cfg.n_chunks_before + cfg.n_chunks_after)
+  attn_keep = layer._attention_multiplier(key, 'cpu').numpy().astype(np.float64)
+  out_keep = layer._output_multiplier(key, D, 'cpu').numpy().astype(np.float64)
+  assert attn_keep.shape == (cfg.chunk_len, W) and 0.1 < (attn_keep == 0).mean() < 0.3
+  want_out, buckets, _, _ = O.forward_and_or_backward(cfg, x, weights, rotations=rot, update_state=True, attn_keep=attn_keep,
+                                                      out_keep=out_keep)
+  _, _, want_dx, want_dw = O.forward_and_or_backward(cfg, x, weights, buckets=buckets, output_grad=dout, update_state=False,
+                                                     attn_keep=attn_keep, out_keep=out_keep)
+  w_d = tuple(torch.from_numpy(w).cuda() for w in weights)
+  x_d = torch.from_numpy(x).cuda().to(dtype)
+  state = (torch.from_numpy(buckets).cuda(), torch.zeros((B * cfg.n_heads, 2), dtype=torch.int32, device='cuda'))
+  out, _, dx, dw = layer.forward_and_or_backward(x_d, w_d, state, key, output_grad=torch.from_numpy(dout).cuda().to(dtype),
+                                                 compute_output=True, update_state=False)
+  util.assert_close_layer(out.float().cpu().numpy(), want_out, 'out')
+  util.assert_close_layer(dx.float().cpu().numpy(), want_dx, 'dx')
+  for name, g, w in zip(('dw_q', 'dw_v', 'dw_o'), dw, want_dw):
+    util.assert_close_layer(g.cpu().numpy(), w, name)
+  # the masks are functions of rng: another key changes the result, the same key reproduces it bit for bit
+  out2, _, _, _ = layer.forward_and_or_backward(x_d, w_d, state, key, compute_output=True, update_state=False)
+  out3, _, _, _ = layer.forward_and_or_backward(x_d, w_d, state, np.array([8, 9], np.uint32), compute_output=True,
+                                                update_state=False)
+  assert torch.equal(out, out2) and not torch.equal(out, out3)
+  # eval mode switches both off (EA:1790-1795)
+  ev = _layer(cfg, attention_dropout=0.2, output_dropout=0.1, mode='eval')
+  want_plain, _, _, _ = O.forward_and_or_backward(cfg, x, weights, buckets=buckets, update_state=False)
+  got_plain, _, _, _ = ev.forward_and_or_backward(x_d, w_d, state, None, compute_output=True, update_state=False)
+  util.assert_close_layer(got_plain.float().cpu().numpy(), want_plain, 'eval-mode out')

@@ -161,14 +161,14 @@ def _core_case(seed, B, H, L, C, nb, na, nh, nbk, causal, masked):
   return cfg, qv, buckets, mask
 
 
-def _oracle_core(cfg, qv, buckets, mask, B, H, dout=None):
+def _oracle_core(cfg, qv, buckets, mask, B, H, dout=None, attn_keep=None):
   """Runs the oracle per unit with identity projections; returns dict of stacked results."""
   w_q, w_v, w_o = util.core_identity_weights()
   res, grads = [], []
   for u in range(B * H):
     b, h = divmod(u, H)
     r = O.forward_unit(cfg, qv[b, :, h, :].astype(np.float64), w_q, w_v, w_o, buckets=buckets[u],
-                       mask=None if mask is None else mask[b])
+                       mask=None if mask is None else mask[b], attn_keep=attn_keep)
     res.append(r)
     if dout is not None:
       grads.append(O.backward_unit(cfg, r, dout[b, :, h, :].astype(np.float64))[0])
@@ -237,6 +237,69 @@ def test_attend_bwd(case):
     b, h = divmod(u, H)
     util.assert_close(dqv[b, :, h, :64], grads[u][:, :64], 'dq[%d]' % u)
     util.assert_close(dqv[b, :, h, 64:], grads[u][:, 64:], 'dv[%d]' % u)
+
+
+DROPOUT_CASES = [
+    # (B, H, L, C, nb, na, nh, nbk, causal, masked)
+    (2, 2, 512, 128, 1, 0, 4, 8, True, False),       # the tcgen05 shape: dropout takes its slot-ordered (generic) instantiation
+    (1, 3, 640, 128, 1, 0, 2, 4, True, False),       # odd chunk count per round: look-back of chunk 0 has the same row flip
+    (1, 2, 1024, 64, 1, 0, 1, 32, True, False),      # mma.sync shape (BASELINE config 1)
+    (1, 2, 512, 64, 1, 1, 2, 16, False, True),       # look-ahead window, padding mask
+    (1, 2, 512, 128, 0, 1, 2, 8, False, False),      # tcgen05 generic path, window = [own, next]
+    (1, 1, 512, 256, 1, 0, 2, 4, True, False),       # chunk_len 256 (reformer_enwik8.gin:40)
+]
+
+
+@pytest.mark.parametrize('case', DROPOUT_CASES)
+@pytest.mark.parametrize('rate', [0.2, 0.5])
+def test_attention_dropout_fwd_bwd(case, rate):
+  """EA:254-262: ONE (chunk_len, window) keep multiplier, indexed by the ORIGINAL slot of query and key inside their
+  chunks, applied to exp(dots - lse) before the product with v (the log-sum-exp does not see it) — and its VJP
+  (dV += (P∘m)^T do, dS = P∘(m∘dP - D)).  reformer_enwik8.gin:94 / reformer_imagenet64.gin:69 train with 0.2."""
+  from trax_b200 import ops
+  B, H, L, C, nb, na, nh, nbk, causal, masked = case
+  cfg, qv, buckets, mask = _core_case(41, B, H, L, C, nb, na, nh, nbk, causal, masked)
+  rng = np.random.default_rng(int(rate * 100) + C)
+  W = C * (1 + nb + na)
+  keep = ((rng.random((C, W)) >= rate) / (1.0 - rate)).astype(np.float32)
+  do = util.bf16_round(rng.standard_normal((B, L, H, 64)))
+  if mask is not None:
+    do = do * mask[:, :, None, None]
+  dims = _dims(B, H, L, 128, C, nb, na, nh, [nbk], causal, masked)
+  mask_d = None if mask is None else _cuda(mask.astype(np.uint8))
+  qv_d, keep_d = _cuda(qv, torch.bfloat16), _cuda(keep)
+  sticker, _ = ops.sort(dims, _cuda(buckets))
+  o_r, logits = ops.attend_fwd(dims, qv_d, sticker, mask_d, attn_keep=keep_d)
+  o_c, lse_tot = ops.combine_fwd(dims, o_r, logits)
+  dqv = ops.attend_bwd(dims, qv_d, sticker, o_c, lse_tot, _cuda(do, torch.bfloat16), mask_d, attn_keep=keep_d)
+  res, grads = _oracle_core(cfg, qv, buckets, mask, B, H, dout=do, attn_keep=keep.astype(np.float64))
+  o_r, logits, dqv = o_r.float().cpu().numpy(), logits.cpu().numpy(), dqv.float().cpu().numpy()
+  no_drop, _ = ops.attend_fwd(dims, qv_d, sticker, mask_d)
+  assert not torch.equal(no_drop, torch.from_numpy(o_r).cuda().to(torch.bfloat16)), 'the keep matrix had no effect'
+  for u in range(B * H):
+    b, h = divmod(u, H)
+    util.assert_close(o_r[u], res[u].o_rounds, 'o_rounds[%d]' % u)
+    util.assert_close(logits[u], res[u].logits, 'logits[%d]' % u)
+    util.assert_close(dqv[b, :, h, :64], grads[u][:, :64], 'dq[%d]' % u, frac_bad_max=0.02)
+    util.assert_close(dqv[b, :, h, 64:], grads[u][:, 64:], 'dv[%d]' % u, frac_bad_max=0.02)
+
+
+def test_forward_rows_whose_softmax_underflows_are_redone_exactly():
+  """the tcgen05 forward shifts every row by its analytic self score; with large-norm queries whose visible keys
+  all score far below it the exponentials flush to zero.  Such rows are queued and redone with the true maximum."""
+  from trax_b200 import ops
+  B, H, L, C, nh, nbk = 1, 2, 512, 128, 2, 4
+  cfg, qv, buckets, _ = _core_case(43, B, H, L, C, 1, 0, nh, nbk, True, False)
+  qv[..., :64] = util.bf16_round(qv[..., :64] * 24.0)          # |q| ~ 190: self score 8 r = 190, typical neighbour far below
+  dims = _dims(B, H, L, 128, C, 1, 0, nh, [nbk], True, False)
+  sticker, _ = ops.sort(dims, _cuda(buckets))
+  o_r, logits = ops.attend_fwd(dims, _cuda(qv, torch.bfloat16), sticker)
+  res, _ = _oracle_core(cfg, qv, buckets, None, B, H)
+  o_r, logits = o_r.float().cpu().numpy(), logits.cpu().numpy()
+  assert np.isfinite(logits).all() and (logits > -2e5).all()
+  for u in range(B * H):
+    util.assert_close(logits[u], res[u].logits, 'logits[%d]' % u)
+    util.assert_close(o_r[u], res[u].o_rounds, 'o_rounds[%d]' % u, frac_bad_max=0.03)
 
 
 def test_degenerate_rows():

@@ -39,15 +39,15 @@ SIGNATURES = {
     'lsh_sort_workspace_bytes': (_SZ, [_D]),
     'lsh_sort': (_I, [_D, _P, _I64, _P, _P, _P, _SZ, _P]),
     'lsh_attend_fwd_workspace_bytes': (_SZ, [_D]),
-    'lsh_attend_fwd': (_I, [_D, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    'lsh_attend_fwd': (_I, [_D, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     'lsh_chunk_possort': (_I, [_D, _P, _P, _P, _P]),
     'lsh_combine_fwd': (_I, [_D, _P, _P, _P, _P, _P]),
     'lsh_project_out': (_I, [_D, _P, _P, _P, _P, _SZ, _P]),
     'lsh_attend_bwd_workspace_bytes': (_SZ, [_D]),
-    'lsh_attend_bwd': (_I, [_D, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    'lsh_attend_bwd': (_I, [_D, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     'lsh_layer_workspace_bytes': (_SZ, [_D, _I]),
-    'lsh_layer_fwd': (_I, [_D, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _SZ, _P]),
-    'lsh_layer_bwd': (_I, [_D, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    'lsh_layer_fwd': (_I, [_D, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _SZ, _P]),
+    'lsh_layer_bwd': (_I, [_D, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     'lsh_make_rotations': (_I, [_D, _P, _P, _P, _P]),
     'lsh_layernorm_fwd': (_I, [_I64, _I, _I, _P, _P, _P, _P, _P, ctypes.c_float, _P]),
     'lsh_layernorm_bwd': (_I, [_I64, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

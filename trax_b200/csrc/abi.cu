@@ -37,12 +37,13 @@ int hash_bf16_qv_aux(const LshAttnDims &, const void *, const float *, const uin
 size_t sort_workspace_bytes(const LshAttnDims &);
 int sort_run(const LshAttnDims &, const int32_t *, int64_t, int32_t *, int32_t *, void *, size_t, cudaStream_t);
 int attend_fwd_run(const LshAttnDims &, const void *, const int32_t *, const uint8_t *, void *, int64_t, int64_t,
-                   int64_t, int64_t, float *, const FwdAux *, cudaStream_t);
+                   int64_t, int64_t, float *, const FwdAux *, const AttnKeep *, cudaStream_t);
 int combine_fwd_run(const LshAttnDims &, const void *, const float *, void *, float *, cudaStream_t);
 int chunk_possort_run(const LshAttnDims &, const int32_t *, int32_t *, int32_t *, cudaStream_t);
 size_t attend_bwd_workspace_bytes(const LshAttnDims &);
 int attend_bwd_run(const LshAttnDims &, const void *, const int32_t *, const uint8_t *, const void *, const float *,
-                   const void *, const float *, const int32_t *, const int32_t *, void *, void *, size_t, cudaStream_t);
+                   const void *, const float *, const int32_t *, const int32_t *, const AttnKeep *, void *, void *, size_t,
+                   cudaStream_t);
 int pack_weights_run(const LshAttnDims &, const float *, const float *, const float *, void *, void *, cudaStream_t);
 int f32_to_bf16_run(const float *, void *, int64_t, cudaStream_t);
 int unpack_dwqv_run(const LshAttnDims &, const float *, float *, float *, cudaStream_t);
@@ -86,16 +87,15 @@ static int check_dims(const LshAttnDims *dp, bool need_bwd) {
 // ---- cuBLAS ----------------------------------------------------------------------------------------
 static constexpr size_t kCublasWs = 32ull << 20;
 
+// One handle per (thread, device): a thread that moves between devices gets that device's handle back instead of leaking
+// the previous one (handles live for the life of the thread, like torch's own).
+static constexpr int kMaxDevices = 64;
 static cublasHandle_t get_handle() {
-  static thread_local cublasHandle_t h = nullptr;
-  static thread_local int dev = -1;
+  static thread_local cublasHandle_t handles[kMaxDevices] = {};
   int cur = 0;
-  cudaGetDevice(&cur);
-  if (h == nullptr || dev != cur) {
-    if (cublasCreate(&h) != CUBLAS_STATUS_SUCCESS) return nullptr;
-    dev = cur;
-  }
-  return h;
+  if (cudaGetDevice(&cur) != cudaSuccess || cur < 0 || cur >= kMaxDevices) return nullptr;
+  if (handles[cur] == nullptr && cublasCreate(&handles[cur]) != CUBLAS_STATUS_SUCCESS) handles[cur] = nullptr;
+  return handles[cur];
 }
 
 // Row-major C[M,N] = op(A)·op(B); A/B bf16, C bf16 or f32; fp32 accumulation.
@@ -120,20 +120,31 @@ static int gemm_rm(bool ta, bool tb, int64_t M, int64_t N, int64_t K, const void
 struct SideStream {
   cudaStream_t stream = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
-  int dev = -1;
 };
-static SideStream *side_stream() {
-  static thread_local SideStream ss;
+static SideStream *side_stream() {      // per (thread, device), created once
+  static thread_local SideStream per_dev[kMaxDevices];
   int cur = 0;
-  cudaGetDevice(&cur);
-  if (ss.stream == nullptr || ss.dev != cur) {
-    if (cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    ss.dev = cur;
+  if (cudaGetDevice(&cur) != cudaSuccess || cur < 0 || cur >= kMaxDevices) return nullptr;
+  SideStream &ss = per_dev[cur];
+  if (ss.stream == nullptr) {
+    cudaStream_t st = nullptr;
+    cudaEvent_t f = nullptr, j = nullptr;
+    if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&f, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&j, cudaEventDisableTiming) != cudaSuccess) {
+      cudaStreamDestroy(st);
+      if (f) cudaEventDestroy(f);
+      return nullptr;
+    }
+    ss.stream = st; ss.fork = f; ss.join = j;
   }
   return &ss;
 }
+#define LSH_CUDA_OK(call)                                                                          \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) return set_error("%s: %s", #call, cudaGetErrorString(e_));              \
+  } while (0)
 
 // ---- workspace carving -----------------------------------------------------------------------------
 struct Bump {
@@ -148,7 +159,7 @@ struct Bump {
 };
 
 struct LayerWs {
-  void *cublas, *cublas2, *xb, *wqv, *wo, *qv, *o_rounds, *o_comb, *sort_ws, *doutb, *do_comb, *dqv, *bwd_ws;
+  void *cublas, *cublas2, *xb, *wqv, *wo, *qv, *o_rounds, *o_comb, *sort_ws, *doutb, *do_comb, *dqv, *bwd_ws, *keep_ws;
   int32_t *sticker;
   float *logits, *lse_tot, *dwqv;
   FwdAux aux;
@@ -166,6 +177,7 @@ static LayerWs carve(const LshAttnDims &d, void *ws, bool with_grad) {
   w.wo = b.take(static_cast<size_t>(d.H) * d.dv * d.D * 2);
   w.qv = b.take(BL * d.H * dr.QV * 2);
   w.aux = fwd_aux_carve(d, b.take(fwd_aux_bytes(d)));
+  w.keep_ws = b.take(attn_keep_bytes(d));
   w.sticker = static_cast<int32_t *>(b.take(rows * 4));
   w.sort_bytes = sort_workspace_bytes(d);
   w.sort_ws = b.take(w.sort_bytes);
@@ -188,7 +200,7 @@ static LayerWs carve(const LshAttnDims &d, void *ws, bool with_grad) {
 
 // Forward up to o_comb (EA:1923-1992 for all units).  Returns xb (bf16 view of x).
 static int forward_core(const LshAttnDims &d, const LayerWs &w, const void *x, const float *w_q, const float *w_v,
-                        const float *w_o, const float *rotations, const uint8_t *mask, int32_t *buckets,
+                        const float *w_o, const float *rotations, const uint8_t *mask, const AttnKeep *keep, int32_t *buckets,
                         int64_t bstride, bool need_lse_tot, const void **xb_out, cudaStream_t s, bool weights_packed = false) {
   Derived dr = derive(d);
   const int64_t BL = static_cast<int64_t>(d.B) * d.L;
@@ -215,13 +227,13 @@ static int forward_core(const LshAttnDims &d, const LayerWs &w, const void *x, c
   if ((rc = fwd_aux_prepare(d, w.qv, w.sticker, w.aux, s, scales_done))) return rc;
   if (d.nh > 1) {
     if ((rc = attend_fwd_run(d, w.qv, w.sticker, mask, w.o_rounds, static_cast<int64_t>(d.H) * dr.N * 64,
-                             static_cast<int64_t>(dr.N) * 64, static_cast<int64_t>(d.L) * 64, 64, w.logits, &w.aux, s)))
+                             static_cast<int64_t>(dr.N) * 64, static_cast<int64_t>(d.L) * 64, 64, w.logits, &w.aux, keep, s)))
       return rc;
     if ((rc = combine_fwd_run(d, w.o_rounds, w.logits, w.o_comb, need_lse_tot ? w.lse_tot : nullptr, s))) return rc;
   } else {
     // single round: rows land directly in the (B, L, H, dv) layout, logits == lse_tot
     if ((rc = attend_fwd_run(d, w.qv, w.sticker, mask, w.o_comb, static_cast<int64_t>(d.L) * d.H * 64, 64, 0,
-                             static_cast<int64_t>(d.H) * 64, w.logits, &w.aux, s)))
+                             static_cast<int64_t>(d.H) * 64, w.logits, &w.aux, keep, s)))
       return rc;
   }
   return 0;
@@ -283,20 +295,22 @@ int lsh_sort(const LshAttnDims *dims, const int32_t *buckets, int64_t buckets_st
 }
 
 size_t lsh_attend_fwd_workspace_bytes(const LshAttnDims *dims) {
-  return dims ? fwd_aux_bytes(*dims) : 0;
+  return dims ? fwd_aux_bytes(*dims) + attn_keep_bytes(*dims) : 0;
 }
 
 int lsh_attend_fwd(const LshAttnDims *dims, const void *qv, const int32_t *sticker, const uint8_t *mask,
-                   void *o_rounds, float *logits, void *ws, size_t ws_bytes, void *stream) {
+                   const float *attn_keep, void *o_rounds, float *logits, void *ws, size_t ws_bytes, void *stream) {
   if (int rc = check_dims(dims, false)) return rc;
   const LshAttnDims &d = *dims;
   Derived dr = derive(d);
   if (!ws || ws_bytes < lsh_attend_fwd_workspace_bytes(dims)) return set_error("lsh_attend_fwd: workspace too small");
   FwdAux aux = fwd_aux_carve(d, ws);
+  AttnKeep keep;
+  if (int rc = attn_keep_prepare(d, attn_keep, static_cast<char *>(ws) + fwd_aux_bytes(d), &keep, static_cast<cudaStream_t>(stream))) return rc;
   if (int rc = fwd_aux_prepare(d, qv, sticker, aux, static_cast<cudaStream_t>(stream))) return rc;
   return attend_fwd_run(d, qv, sticker, mask, o_rounds, static_cast<int64_t>(d.H) * dr.N * 64,
                         static_cast<int64_t>(dr.N) * 64, static_cast<int64_t>(d.L) * 64, 64, logits, &aux,
-                        static_cast<cudaStream_t>(stream));
+                        attn_keep ? &keep : nullptr, static_cast<cudaStream_t>(stream));
 }
 
 int lsh_chunk_possort(const LshAttnDims *dims, const int32_t *sticker, int32_t *sticker2, int32_t *bounds, void *stream) {
@@ -320,14 +334,20 @@ int lsh_project_out(const LshAttnDims *dims, const void *o_comb, const void *wo,
                  ws_bytes >= kCublasWs ? ws : nullptr, static_cast<cudaStream_t>(stream));
 }
 
-size_t lsh_attend_bwd_workspace_bytes(const LshAttnDims *dims) { return dims ? attend_bwd_workspace_bytes(*dims) : 0; }
+size_t lsh_attend_bwd_workspace_bytes(const LshAttnDims *dims) {
+  return dims ? attend_bwd_workspace_bytes(*dims) + attn_keep_bytes(*dims) : 0;
+}
 
 int lsh_attend_bwd(const LshAttnDims *dims, const void *qv, const int32_t *sticker, const uint8_t *mask,
-                   const void *o_comb, const float *lse_tot, const void *do_comb, void *dqv, void *ws, size_t ws_bytes,
-                   void *stream) {
+                   const float *attn_keep, const void *o_comb, const float *lse_tot, const void *do_comb, void *dqv, void *ws,
+                   size_t ws_bytes, void *stream) {
   if (int rc = check_dims(dims, true)) return rc;
-  return attend_bwd_run(*dims, qv, sticker, mask, o_comb, lse_tot, do_comb, nullptr, nullptr, nullptr, dqv, ws, ws_bytes,
-                        static_cast<cudaStream_t>(stream));
+  if (!ws || ws_bytes < lsh_attend_bwd_workspace_bytes(dims)) return set_error("lsh_attend_bwd: workspace too small");
+  AttnKeep keep;
+  const size_t core = attend_bwd_workspace_bytes(*dims);
+  if (int rc = attn_keep_prepare(*dims, attn_keep, static_cast<char *>(ws) + core, &keep, static_cast<cudaStream_t>(stream))) return rc;
+  return attend_bwd_run(*dims, qv, sticker, mask, o_comb, lse_tot, do_comb, nullptr, nullptr, nullptr,
+                        attn_keep ? &keep : nullptr, dqv, ws, core, static_cast<cudaStream_t>(stream));
 }
 
 size_t lsh_layer_workspace_bytes(const LshAttnDims *dims, int with_grad) {
@@ -336,8 +356,8 @@ size_t lsh_layer_workspace_bytes(const LshAttnDims *dims, int with_grad) {
 }
 
 int lsh_layer_fwd(const LshAttnDims *dims, const void *x, const float *w_q, const float *w_v, const float *w_o,
-                  const float *rotations, const uint8_t *mask, int32_t *buckets, int64_t buckets_stride, void *out,
-                  void *ws, size_t ws_bytes, void *stream) {
+                  const float *rotations, const uint8_t *mask, const float *attn_keep, int32_t *buckets,
+                  int64_t buckets_stride, void *out, void *ws, size_t ws_bytes, void *stream) {
   if (int rc = check_dims(dims, false)) return rc;
   const LshAttnDims &d = *dims;
   if (!x || !w_q || !w_v || !w_o || !buckets || !out || !ws) return set_error("lsh_layer_fwd: NULL argument");
@@ -345,14 +365,19 @@ int lsh_layer_fwd(const LshAttnDims *dims, const void *x, const float *w_q, cons
   if (ws_bytes < w.total) return set_error("lsh_layer_fwd: workspace too small (%zu < %zu)", ws_bytes, w.total);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const void *xb;
-  if (int rc = forward_core(d, w, x, w_q, w_v, w_o, rotations, mask, buckets, buckets_stride, false, &xb, s)) return rc;
+  AttnKeep keep;
+  if (int rc = attn_keep_prepare(d, attn_keep, w.keep_ws, &keep, s)) return rc;
+  if (int rc = forward_core(d, w, x, w_q, w_v, w_o, rotations, mask, attn_keep ? &keep : nullptr, buckets, buckets_stride, false,
+                            &xb, s))
+    return rc;
   const int64_t BL = static_cast<int64_t>(d.B) * d.L, KO = static_cast<int64_t>(d.H) * d.dv;
   return gemm_rm(false, false, BL, d.D, KO, w.o_comb, KO, w.wo, d.D, out, d.D, d.act_dtype == LSH_DTYPE_F32, w.cublas, s);
 }
 
 int lsh_layer_bwd(const LshAttnDims *dims, const void *x, const float *w_q, const float *w_v, const float *w_o,
-                  const uint8_t *mask, const int32_t *buckets, int64_t buckets_stride, const void *dout, void *out,
-                  void *dx, float *dw_q, float *dw_v, float *dw_o, void *ws, size_t ws_bytes, void *stream) {
+                  const uint8_t *mask, const float *attn_keep, const int32_t *buckets, int64_t buckets_stride,
+                  const void *dout, void *out, void *dx, float *dw_q, float *dw_v, float *dw_o, void *ws, size_t ws_bytes,
+                  void *stream) {
   if (int rc = check_dims(dims, true)) return rc;
   const LshAttnDims &d = *dims;
   if (!x || !w_q || !w_v || !w_o || !buckets || !dout || !dx || !dw_q || !dw_v || !dw_o || !ws)
@@ -370,27 +395,30 @@ int lsh_layer_bwd(const LshAttnDims *dims, const void *x, const float *w_q, cons
   if ((rc = pack_weights_run(d, w_q, w_v, w_o, w.wqv, w.wo, s))) return rc;
   SideStream *side = side_stream();
   if (!side) return set_error("lsh_layer_bwd: could not create the internal stream");
-  cudaEventRecord(side->fork, s);
-  cudaStreamWaitEvent(side->stream, side->fork, 0);
+  LSH_CUDA_OK(cudaEventRecord(side->fork, s));
+  LSH_CUDA_OK(cudaStreamWaitEvent(side->stream, side->fork, 0));
   const void *doutb = dout;
   if (f32) {
     if ((rc = f32_to_bf16_run(static_cast<const float *>(dout), w.doutb, BL * d.D, side->stream))) return rc;
     doutb = w.doutb;
   }
   if ((rc = gemm_rm(false, true, BL, KO, d.D, doutb, d.D, w.wo, d.D, w.do_comb, KO, false, w.cublas2, side->stream))) return rc;
-  cudaEventRecord(side->join, side->stream);
+  LSH_CUDA_OK(cudaEventRecord(side->join, side->stream));
   // forward recompute on the caller's stream
-  if ((rc = forward_core(d, w, x, w_q, w_v, w_o, nullptr, mask, const_cast<int32_t *>(buckets), buckets_stride, true,
+  AttnKeep keep;
+  if ((rc = attn_keep_prepare(d, attn_keep, w.keep_ws, &keep, s))) return rc;
+  const AttnKeep *kp = attn_keep ? &keep : nullptr;
+  if ((rc = forward_core(d, w, x, w_q, w_v, w_o, nullptr, mask, kp, const_cast<int32_t *>(buckets), buckets_stride, true,
                          &xb, s, /*weights_packed=*/true)))
     return rc;
   if (out) {
     if ((rc = gemm_rm(false, false, BL, d.D, KO, w.o_comb, KO, w.wo, d.D, out, d.D, f32, w.cublas, s))) return rc;
   }
-  cudaStreamWaitEvent(s, side->join, 0);
+  LSH_CUDA_OK(cudaStreamWaitEvent(s, side->join, 0));
   // B1 (second half): dW_o = o^T·dout
   if ((rc = gemm_rm(true, false, KO, d.D, BL, w.o_comb, KO, doutb, d.D, dw_o, d.D, true, w.cublas, s))) return rc;
   // B2-B6
-  if ((rc = attend_bwd_run(d, w.qv, w.sticker, mask, w.o_comb, w.lse_tot, w.do_comb, w.aux.qscale, attend_fwd_uses_tc(d) ? w.aux.sticker2 : nullptr, attend_fwd_uses_tc(d) ? w.aux.bounds : nullptr, w.dqv, w.bwd_ws, w.bwd_bytes, s)))
+  if ((rc = attend_bwd_run(d, w.qv, w.sticker, mask, w.o_comb, w.lse_tot, w.do_comb, w.aux.qscale, attend_fwd_uses_tc(d) ? w.aux.sticker2 : nullptr, attend_fwd_uses_tc(d) ? w.aux.bounds : nullptr, kp, w.dqv, w.bwd_ws, w.bwd_bytes, s)))
     return rc;
   // B7: dW_q|dW_v = x^T·dqv ; dx = dqv·wqv^T
   if ((rc = gemm_rm(true, false, d.D, NQV, BL, xb, d.D, w.dqv, NQV, w.dwqv, NQV, true, w.cublas, s))) return rc;

@@ -15,6 +15,7 @@
 #include <string.h>
 
 #include "attend_bwd_params.cuh"
+#include "attend_params.cuh"
 
 namespace lsh {
 
@@ -30,6 +31,8 @@ struct AttendBwdParams {
   __nv_bfloat16 *dq_part;        // (nwin+1, BH, N, 64): kinds 0..nwin-1 = query side, kind nwin = key side
   __nv_bfloat16 *dv_part;        // (BH, N, 64)
   int64_t kind_stride;
+  const uint32_t *keep_bits_t;   // attention dropout: (W, C / 32) bit rows by window column (null = none), see AttnKeep
+  const float *keep_scale;
   int L, H, N, n_chunks, nb, nwin, causal, masked;
 };
 
@@ -163,10 +166,16 @@ __global__ void __launch_bounds__(2 * C, 1) attend_bwd_kernel(const AttendBwdPar
         }
       }
       // masks (EA:145-160), P_tot^T, dS^T -> fragments + shared memory
+      // attention dropout m (EA:254-262): so = (P∘m) V  =>  dV += (P∘m)^T do,  dS = P ∘ (m∘dP - D)   
+      const uint32_t *kt0 = p.keep_bits_t ? p.keep_bits_t + static_cast<size_t>(wslot * C + krow0 + g) * (C / 32) + sub * 2 : nullptr;
+      const uint32_t *kt1 = p.keep_bits_t ? kt0 + 8 * (C / 32) : nullptr;
+      const float kscale_m = p.keep_bits_t ? __ldg(p.keep_scale) : 1.f;
       uint32_t pa[4][4], dsa[4][4];
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
         float pv[4], dsv[4];
+        uint32_t kw0 = 0xffffffffu, kw1 = 0xffffffffu;
+        if (kt0) { kw0 = __ldg(kt0 + (nt >> 2)) >> ((nt & 3) * 8 + 2 * t); kw1 = __ldg(kt1 + (nt >> 2)) >> ((nt & 3) * 8 + 2 * t); }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int col = nt * 8 + 2 * t + (e & 1);
@@ -177,8 +186,9 @@ __global__ void __launch_bounds__(2 * C, 1) attend_bwd_kernel(const AttendBwdPar
           if (qi == ki) v = v - 1e5f;
           if (p.masked && ki < 0.f) v = v - 1e9f;
           const float pt = exp2f((v - qlse[col]) * kLog2e);
-          pv[e] = pt;
-          dsv[e] = pt * (dp[nt][e] - qD[col]);
+          const float mk = (((e < 2 ? kw0 : kw1) >> (e & 1)) & 1u) ? kscale_m : 0.f;
+          pv[e] = pt * mk;
+          dsv[e] = pt * (mk * dp[nt][e] - qD[col]);
         }
         const int kk = nt >> 1, hi = (nt & 1) * 2;
         pa[kk][hi] = pack_bf16(pv[0], pv[1]);   pa[kk][hi + 1] = pack_bf16(pv[2], pv[3]);
@@ -301,7 +311,8 @@ bool attend_tc_uses_bounds();
 
 int attend_bwd_run(const LshAttnDims &d, const void *qv, const int32_t *sticker, const uint8_t *mask,
                    const void *o_comb, const float *lse_tot, const void *do_comb, const float *qscale_in,
-                   const int32_t *sticker2_in, const int32_t *bounds_in, void *dqv, void *ws, size_t ws_bytes, cudaStream_t stream) {
+                   const int32_t *sticker2_in, const int32_t *bounds_in, const AttnKeep *keep, void *dqv, void *ws, size_t ws_bytes,
+                   cudaStream_t stream) {
   Derived dr = derive(d);
   if (ws_bytes < attend_bwd_workspace_bytes(d))
     return set_error("lsh_attend_bwd: workspace too small (%zu < %zu)", ws_bytes, attend_bwd_workspace_bytes(d));
@@ -320,7 +331,8 @@ int attend_bwd_run(const LshAttnDims &d, const void *qv, const int32_t *sticker,
   int rc;
   // tcgen05 path for the long-sequence shape; LSH_ATTN_BWD=mma forces the mma.sync path
   static const bool force_mma = [] { const char *e = getenv("LSH_ATTN_BWD"); return e && strcmp(e, "mma") == 0; }();
-  if (d.C == 128 && d.nb == 1 && d.na == 0 && d.causal && !d.masked && d.L % 128 == 0 && !force_mma) {
+  const bool dropout = keep && keep->bits_t;   // the tcgen05 backward works on position-sorted tiles; the keep matrix is in slot order
+  if (d.C == 128 && d.nb == 1 && d.na == 0 && d.causal && !d.masked && d.L % 128 == 0 && !force_mma && !dropout) {
     const float *qscale = qscale_in;
     if (!qscale) {
       if ((rc = qscale_run(d, qv, qscale_ws, nullptr, nullptr, stream))) return rc;
@@ -350,6 +362,7 @@ int attend_bwd_run(const LshAttnDims &d, const void *qv, const int32_t *sticker,
   p.dq_part = dq_part; p.dv_part = dv_part; p.kind_stride = static_cast<int64_t>(rows) * 64;
   p.L = d.L; p.H = d.H; p.N = dr.N; p.n_chunks = dr.n_chunks; p.nb = d.nb; p.nwin = dr.nwin;
   p.causal = d.causal; p.masked = d.masked;
+  p.keep_bits_t = dropout ? keep->bits_t : nullptr; p.keep_scale = dropout ? keep->scale : nullptr;
   switch (d.C) {
     case 64: rc = launch_attend_bwd<64>(p, dr.BH, stream); break;
     case 128: rc = launch_attend_bwd<128>(p, dr.BH, stream); break;

@@ -102,6 +102,9 @@ __global__ void __launch_bounds__(2 * C) attend_fwd_kernel(const AttendFwdParams
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
   const uint32_t ks_base = smem_u32(Ks), vs_base = smem_u32(Vs);
   const int n_kb = W / 64;
+  // attention dropout (EA:254-262): rows of the (C, W) keep matrix of my two query slots; tiles are in slot order here
+  const uint32_t *kb0 = p.keep_bits ? p.keep_bits + static_cast<size_t>(warp * 16 + g) * (W / 32) : nullptr;
+  const uint32_t *kb1 = p.keep_bits ? kb0 + 8 * (W / 32) : nullptr;
   for (int kb = 0; kb < n_kb; ++kb) {
     float s[8][4];
 #pragma unroll
@@ -145,10 +148,17 @@ __global__ void __launch_bounds__(2 * C) attend_fwd_kernel(const AttendFwdParams
     for (int nt = 0; nt < 8; ++nt) {
       const float p0 = exp2f((s[nt][0] - mn0) * kLog2e), p1 = exp2f((s[nt][1] - mn0) * kLog2e);
       const float p2 = exp2f((s[nt][2] - mn1) * kLog2e), p3 = exp2f((s[nt][3] - mn1) * kLog2e);
-      rs0 += p0 + p1; rs1 += p2 + p3;
+      rs0 += p0 + p1; rs1 += p2 + p3;                       // the log-sum-exp does not see the dropout (EA:251-262)
+      float d0 = p0, d1 = p1, d2 = p2, d3 = p3;
+      if (kb0) {
+        const int sh = (nt & 3) * 8 + 2 * t;
+        const uint32_t w0 = __ldg(kb0 + kb * 2 + (nt >> 2)) >> sh, w1 = __ldg(kb1 + kb * 2 + (nt >> 2)) >> sh;
+        d0 = (w0 & 1u) ? p0 : 0.f; d1 = (w0 & 2u) ? p1 : 0.f;
+        d2 = (w1 & 1u) ? p2 : 0.f; d3 = (w1 & 2u) ? p3 : 0.f;
+      }
       const int kk = nt >> 1;
-      if ((nt & 1) == 0) { pa[kk][0] = pack_bf16(p0, p1); pa[kk][1] = pack_bf16(p2, p3); }
-      else               { pa[kk][2] = pack_bf16(p0, p1); pa[kk][3] = pack_bf16(p2, p3); }
+      if ((nt & 1) == 0) { pa[kk][0] = pack_bf16(d0, d1); pa[kk][1] = pack_bf16(d2, d3); }
+      else               { pa[kk][2] = pack_bf16(d0, d1); pa[kk][3] = pack_bf16(d2, d3); }
     }
     l0 = l0 * al0 + rs0; l1 = l1 * al1 + rs1;
 #pragma unroll
@@ -167,7 +177,8 @@ __global__ void __launch_bounds__(2 * C) attend_fwd_kernel(const AttendFwdParams
     }
   }
   l0 = quad_sum(l0); l1 = quad_sum(l1);
-  const float il0 = 1.f / l0, il1 = 1.f / l1;
+  const float ksc = p.keep_bits ? __ldg(p.keep_scale) : 1.f;        // keep / (1 - rate): folded into the normalisation
+  const float il0 = ksc / l0, il1 = ksc / l1;
 
   // ---- epilogue: stage the 16x64 stripe in shared memory, then 128-byte row stores -----------------
   __syncthreads();   // every warp is done reading Ks/Vs
@@ -256,7 +267,7 @@ int fwd_aux_prepare(const LshAttnDims &d, const void *qv, const int32_t *sticker
 
 int attend_fwd_run(const LshAttnDims &d, const void *qv, const int32_t *sticker, const uint8_t *mask,
                    void *o, int64_t o_sb, int64_t o_sh, int64_t o_sr, int64_t o_sp, float *lse,
-                   const FwdAux *aux, cudaStream_t stream) {
+                   const FwdAux *aux, const AttnKeep *keep, cudaStream_t stream) {
   Derived dr = derive(d);
   AttendFwdParams p;
   p.qv = static_cast<const __nv_bfloat16 *>(qv); p.sticker = sticker;
@@ -268,7 +279,7 @@ int attend_fwd_run(const LshAttnDims &d, const void *qv, const int32_t *sticker,
   p.sticker2 = aux ? aux->sticker2 : nullptr;
   p.bounds = aux ? aux->bounds : nullptr;
   p.redo = aux ? aux->redo : nullptr;
-  p.keep_bits = nullptr; p.keep_scale = 1.f;
+  p.keep_bits = keep ? keep->bits : nullptr; p.keep_scale = keep ? keep->scale : nullptr;
   p.L = d.L; p.H = d.H; p.N = dr.N; p.n_chunks = dr.n_chunks; p.nb = d.nb; p.nwin = dr.nwin;
   p.causal = d.causal; p.masked = d.masked;
   if (d.masked && !mask) return set_error("attend_fwd: dims.masked set but mask == NULL");

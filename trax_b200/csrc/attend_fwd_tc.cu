@@ -126,8 +126,10 @@ __device__ __forceinline__ void softmax_block_mask(const uint32_t (&r)[32], uint
 }
 // Generic path (non-causal, padding mask, other windows): the reference's subtractive masks in order (EA:150-159) with the
 // key kv_info read from shared memory.
+// `keep`: attention-dropout bits of the block's 32 columns (EA:254-262; all ones without dropout) — applied to P after the
+// row sum, which, like the reference's log-sum-exp, does not see the dropout.
 __device__ __forceinline__ void softmax_block_generic(const uint32_t (&r)[32], const float *kin, float qi, float a, float m2, int causal,
-                                                      int masked, uint32_t t_dst, float &l) {
+                                                      int masked, uint32_t keep, uint32_t t_dst, float &l) {
   uint32_t pk[16];
 #pragma unroll
   for (int c4 = 0; c4 < 32; c4 += 4) {
@@ -143,8 +145,9 @@ __device__ __forceinline__ void softmax_block_generic(const uint32_t (&r)[32], c
       pv[e] = fast_exp2(t);
     }
     l += (pv[0] + pv[1]) + (pv[2] + pv[3]);
-    pk[c4 >> 1] = pack_bf16(pv[0], pv[1]);
-    pk[(c4 >> 1) + 1] = pack_bf16(pv[2], pv[3]);
+    const uint32_t kq = keep >> c4;
+    pk[c4 >> 1] = pack_bf16((kq & 1u) ? pv[0] : 0.f, (kq & 2u) ? pv[1] : 0.f);
+    pk[(c4 >> 1) + 1] = pack_bf16((kq & 4u) ? pv[2] : 0.f, (kq & 8u) ? pv[3] : 0.f);
   }
   tmem_st16(t_dst, pk);
 }
@@ -205,7 +208,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
     // different SM sub-partitions.
     auto fetch_sticker = [&](int u, int cc, int &tka, int &tkb, int &bda, int &bdb) {
       const int64_t off = static_cast<int64_t>(u) * p.N + cc * TC_C + 64 * pw;
-      const int32_t *stk = p.sticker2 + off;
+      // attention dropout indexes its keep matrix by SLOT: those calls keep the reference's order inside a chunk
+      const int32_t *stk = ((!SORTED && p.keep_bits) ? p.sticker : p.sticker2) + off;
       tka = __ldg(stk + lane); tkb = __ldg(stk + 32 + lane);
 #if TC_FWD_BOUNDS
       if constexpr (SORTED) { bda = __ldg(p.bounds + off + lane); bdb = __ldg(p.bounds + off + 32 + lane); }
@@ -397,6 +401,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
       float m2 = am.y, lse_off = 0.f;
       uint32_t need = 0xfu;                                          // 32-column blocks of my tile any row of this warp sees
       int lo = 0, hi = 128;                                          // visible column interval in my tile
+      uint32_t keep4[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};   // dropout keep bits per 32-column block
       if constexpr (sorted) {
         // Both tiles are ordered by position (rank r at row r ^ flip), so "key position < query position" (EA:150-152 and the
         // self mask EA:153-155, whose -1e5 entries underflow to exactly 0 next to any visible key) is an interval of columns.
@@ -443,6 +448,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
           if (!(hi_max <= c0 || lo_min >= c1)) need |= 1u << bq;
         }
       } else {
+        if (p.keep_bits) {
+          // my row of the (C, W) keep matrix, the 128 columns of my window part: tile rows are slot ^ flip of their chunk
+          const int c_k = ((wk.c + static_cast<int>(wg) - p.nb) % p.n_chunks + p.n_chunks) % p.n_chunks;
+          const int qslot = row ^ ((wk.c & 1) ? 127 : 0);
+          const uint4 kw = __ldg(reinterpret_cast<const uint4 *>(p.keep_bits + qslot * 8 + wg * 4));
+          if (c_k & 1) { keep4[0] = __brev(kw.w); keep4[1] = __brev(kw.z); keep4[2] = __brev(kw.y); keep4[3] = __brev(kw.x); }
+          else { keep4[0] = kw.x; keep4[1] = kw.y; keep4[2] = kw.z; keep4[3] = kw.w; }
+        }
         const float own_ki = mq.kinfo[row];
         const float wmin = fminf(fminf(m0.vmin[0], m0.vmin[1]), fminf(m1.vmin[0], m1.vmin[1]));
         const float wmax = fmaxf(fmaxf(m0.vmax[0], m0.vmax[1]), fmaxf(m1.vmax[0], m1.vmax[1]));
@@ -470,7 +483,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
           const uint32_t below_lo = lr >= 32 ? 0xffffffffu : (lr <= 0 ? 0u : ((1u << lr) - 1u));
           softmax_block_mask(r, a2, mm2, below_hi & ~below_lo, t_p + bq * 16, l2);
         } else {
-          softmax_block_generic(r, mk.kinfo + bq * 32, qi, a_i, m2, p.causal, p.masked, t_p + bq * 16, l);
+          const uint32_t kpw = bq == 0 ? keep4[0] : (bq == 1 ? keep4[1] : (bq == 2 ? keep4[2] : keep4[3]));
+          softmax_block_generic(r, mk.kinfo + bq * 32, qi, a_i, m2, p.causal, p.masked, kpw, t_p + bq * 16, l);
         }
       };
       auto zero_until = [&](int from, int to) {                       // zero P for the skipped blocks in [from, to)
@@ -536,6 +550,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
     // ================================ epilogue warpgroup ==============================================
     const int row = (warp & 3) * 32 + lane;
     const uint32_t t_row = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    const float keep_mul = p.keep_bits ? __ldg(p.keep_scale) : 1.f;   // dropout multiplier 1 / (1 - rate), folded into 1 / l
     for (Walker wk(g0, g1, p.n_chunks); wk.valid(); wk.next()) {
       const uint32_t w = wk.k & 1, j = wk.k >> 1;
       const int u = wk.u, b = u / p.H, h = u - b * p.H;
@@ -544,7 +559,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
       tc_fence_after();
       if (row == 0) TC_TRACE(wk.k, 4);
       const float l = sh.row_l[w][0][row] + sh.row_l[w][1][row], m2 = sh.row_m2[w][row];
-      const float il = l > 0.f ? 1.f / l : 0.f;
+      const float il = l > 0.f ? keep_mul / l : 0.f;
       const float lse = l > 0.f ? (m2 + log2f(l)) * kLn2 + sh.row_off[w][row] : -3e9f;
       const int tk = sh.row_tk[w][row];
       // The shift m2 is the row's analytic self score, not the maximum over its visible keys: when every visible key scores
@@ -605,8 +620,6 @@ __global__ void __launch_bounds__(256) attend_fwd_redo_kernel(const AttendFwdPar
     const __nv_bfloat16 *qv_u = p.qv + (static_cast<int64_t>(b) * p.L * p.H + h) * 128;
     const int64_t rstride = static_cast<int64_t>(p.H) * 128;
     const float2 q2 = unpack_bf16(*reinterpret_cast<const uint32_t *>(qv_u + pos * rstride + 2 * lane));
-    bool qvalid = true;
-    if (p.masked) qvalid = p.mask[static_cast<int64_t>(b) * p.L + pos] != 0;
     const float qi = static_cast<float>(pos + 1);                      // q_info (EA:201)
     int qslot = 0;                                                     // my slot in the chunk (dropout row)
     for (int l4 = 0; l4 < 4; ++l4) {
@@ -664,7 +677,7 @@ __global__ void __launch_bounds__(256) attend_fwd_redo_kernel(const AttendFwdPar
         for (int l = 0; l < 32; ++l) {
           const int kpos = __shfl_sync(0xffffffffu, ktk_l, l) % p.L;
           float pj = __shfl_sync(0xffffffffu, sc[jj], l) * inv;
-          if (p.keep_bits) pj = (keep >> l) & 1u ? pj * p.keep_scale : 0.f;   // EA:254-262: after the softmax, lse untouched
+          if (p.keep_bits) pj = (keep >> l) & 1u ? pj * __ldg(p.keep_scale) : 0.f;   // EA:254-262: after the softmax, lse untouched
           const float2 v2 = unpack_bf16(*reinterpret_cast<const uint32_t *>(qv_u + kpos * rstride + 64 + 2 * lane));
           o0 = fmaf(pj, v2.x, o0); o1 = fmaf(pj, v2.y, o1);
         }
@@ -673,7 +686,6 @@ __global__ void __launch_bounds__(256) attend_fwd_redo_kernel(const AttendFwdPar
     __nv_bfloat16 *dst = p.o + b * p.o_sb + h * p.o_sh + round * p.o_sr + pos * p.o_sp;
     *reinterpret_cast<uint32_t *>(dst + 2 * lane) = pack_bf16(o0, o1);
     if (lane == 0) p.lse[static_cast<int64_t>(u) * p.N + tk] = mx + __logf(lsum);
-    (void)qvalid;
   }
 }
 
@@ -681,7 +693,7 @@ bool attend_fwd_tc_uses_bounds() { return TC_FWD_BOUNDS != 0; }
 
 int attend_fwd_tc_run(const AttendFwdParams &p, int BH, cudaStream_t stream) {
   const size_t smem = static_cast<size_t>(TC_NST) * TC_TILE_BYTES + 1024;   // + static TcShared
-  const bool sorted = p.causal && !p.masked && p.nb == 1;
+  const bool sorted = p.causal && !p.masked && p.nb == 1 && !p.keep_bits;
   LSH_OPT_IN_SMEM(attend_fwd_tc_kernel<true>);
   LSH_OPT_IN_SMEM(attend_fwd_tc_kernel<false>);
   int dev = 0, sms = 148;

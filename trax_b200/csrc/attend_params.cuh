@@ -16,14 +16,25 @@ struct AttendFwdParams {
   const float2 *rowmeta;        // (BH, L) {a = 8 r log2e, m2 = a |qhat|^2}               }
   const int32_t *sticker2;      // (BH, N) sticker with every chunk re-ordered by position }
   const int32_t *bounds;        // (BH, N) per row of sticker2: neighbour-chunk interval bounds (chunk_possort_kernel)
-  const uint32_t *keep_bits;    // attention dropout (EA:254-262): (C, W / 32) bit rows, bit = keep; null = no dropout
-  float keep_scale;             // 1 / (1 - rate)
+  const uint32_t *keep_bits;    // attention dropout (EA:254-262): (C, W / 32) bit rows, bit j of word w = keep[i][32 w + j]; null = none
+  const float *keep_scale;      // device scalar: the keep multiplier 1 / (1 - rate)
   int *redo;                    // tcgen05 path: [0] = number of queued rows, [2 + 2 i], [3 + 2 i] = {unit * n_chunks + chunk, ticker}
   long long *trace;             // debug: per-phase clock64 stamps of CTA 0 (null = off)
   int L, H, N, n_chunks, nb, nwin, causal, masked;
 };
 
 int attend_fwd_tc_run(const AttendFwdParams &p, int BH, cudaStream_t stream);
+
+// Attention dropout (EA:254-262): ONE (chunk_len, window) keep multiplier per layer call — shared by every chunk, unit and
+// hash round — with values in {0, 1 / (1 - rate)}.  The kernels consume it as bit rows (by query slot; `bits_t`: by window
+// column, for the key-centric backward) plus the scalar; attn_keep_prepare converts the caller's float matrix.
+struct AttnKeep {
+  const uint32_t *bits;     // (C, W / 32)
+  const uint32_t *bits_t;   // (W, C / 32)
+  const float *scale;       // device scalar
+};
+size_t attn_keep_bytes(const LshAttnDims &d);
+int attn_keep_prepare(const LshAttnDims &d, const float *keep_f32, void *ws, AttnKeep *out, cudaStream_t stream);
 
 // Auxiliary per-call buffers of the tcgen05 forward path (produced by qscale_run / chunk_possort_run).
 struct FwdAux {

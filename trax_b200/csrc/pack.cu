@@ -1,5 +1,5 @@
 // Layout / dtype plumbing around the projection GEMMs (EA:1923-1924, 1995 and their VJPs).
-#include "common.cuh"
+#include "attend_params.cuh"
 
 namespace lsh {
 
@@ -45,6 +45,57 @@ __global__ void unpack_dwqv_kernel(const float *__restrict__ dwqv, float *__rest
     if (c < dq) dw_q[(static_cast<int64_t>(h) * D + dm) * dq + c] = dwqv[i];
     else dw_v[(static_cast<int64_t>(h) * D + dm) * dv + (c - dq)] = dwqv[i];
   }
+}
+
+// (C, W) float keep multiplier -> bit rows in both orientations + the multiplier value (see AttnKeep)
+__global__ void __launch_bounds__(256) attn_keep_kernel(const float *__restrict__ keep, uint32_t *__restrict__ bits,
+                                                        uint32_t *__restrict__ bits_t, float *__restrict__ scale, int C, int W) {
+  __shared__ float smax[8];
+  float mx = 0.f;
+  const int wpr = W / 32, cpr = C / 32;
+  for (int i = threadIdx.x; i < C * wpr; i += blockDim.x) {              // bits[r][w]
+    const int r = i / wpr, w = i - r * wpr;
+    uint32_t v = 0u;
+    for (int j = 0; j < 32; ++j) {
+      const float k = keep[static_cast<int64_t>(r) * W + 32 * w + j];
+      mx = fmaxf(mx, k);
+      v |= (k != 0.f ? 1u : 0u) << j;
+    }
+    bits[i] = v;
+  }
+  for (int i = threadIdx.x; i < W * cpr; i += blockDim.x) {              // bits_t[col][w]: bit j = keep[32 w + j][col]
+    const int col = i / cpr, w = i - col * cpr;
+    uint32_t v = 0u;
+    for (int j = 0; j < 32; ++j) v |= (keep[static_cast<int64_t>(32 * w + j) * W + col] != 0.f ? 1u : 0u) << j;
+    bits_t[i] = v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) mx = fmaxf(mx, smax[i]);
+    *scale = mx;
+  }
+}
+
+size_t attn_keep_bytes(const LshAttnDims &d) {
+  Derived dr = derive(d);
+  return static_cast<size_t>(d.C) * dr.W / 8 * 2 + 512;
+}
+
+int attn_keep_prepare(const LshAttnDims &d, const float *keep_f32, void *ws, AttnKeep *out, cudaStream_t stream) {
+  Derived dr = derive(d);
+  out->bits = out->bits_t = nullptr; out->scale = nullptr;
+  if (!keep_f32) return 0;
+  if (!ws) return set_error("attention dropout: workspace missing");
+  char *b = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255));
+  uint32_t *bits = reinterpret_cast<uint32_t *>(b), *bits_t = bits + static_cast<size_t>(d.C) * dr.W / 32;
+  float *scale = reinterpret_cast<float *>(bits_t + static_cast<size_t>(d.C) * dr.W / 32);
+  attn_keep_kernel<<<1, 256, 0, stream>>>(keep_f32, bits, bits_t, scale, d.C, dr.W);
+  LSH_CHECK_LAUNCH("attn_keep_kernel");
+  out->bits = bits; out->bits_t = bits_t; out->scale = scale;
+  return 0;
 }
 
 static unsigned grid_for(int64_t n, int threads) {

@@ -14,8 +14,9 @@ Kept from the reference (names, argument meaning, error behaviour):
     attributes (base.py:675-706).
 Not provided (raise, never silently differ): mode='predict' (EA:1999-2109, out of scope for this
 tier), `use_reference_code=True` (would be a CPU path), `bias=True` (broken in the reference too:
-EA:1921 unpacks exactly three weights), attention_dropout > 0 (needs the keep-mask inside the kernels).  output_dropout
-is supported (a column scaling of w_o; the mask is a function of `rng`, not jax.random's bits).
+EA:1921 unpacks exactly three weights).  attention_dropout (the (chunk_len, window) keep matrix of EA:254-262, applied inside
+the attention kernels) and output_dropout (a column scaling of w_o) are supported; their masks are functions of `rng`, not
+jax.random's bits, and can be supplied explicitly.
 
 torch plays the role JAX plays for the reference: device memory, streams, autograd glue
 (`torch.autograd.Function` ≙ `fastmath.custom_vjp` in base.py:644-673).
@@ -57,6 +58,17 @@ def _split_host(key, n):
   key = np.asarray(key, dtype=np.uint32).reshape(-1)[:2]
   gen = np.random.Generator(np.random.Philox(key=int(key[0]) << 32 | int(key[1])))
   return gen.integers(0, 2 ** 32, size=(n, 2), dtype=np.uint64).astype(np.uint32)
+
+
+def _split_rngs(rng, n):
+  """`combinators._split_rngs` (trax/layers/combinators.py): one sub-key per sublayer, `(None,) * n` without a key.  The
+  same function of `rng` wherever a combinator hands keys to its sublayers (reversible.py:297, 328; EA:3570), so a sublayer
+  that draws from its key (output / attention dropout) draws the same mask in the forward and in the backward pass.
+  Not jax.random's bits (see _split_host)."""
+  if rng is None:
+    return (None,) * n
+  key = np.asarray(rng.cpu() if isinstance(rng, torch.Tensor) else rng).astype(np.uint32).reshape(-1)
+  return tuple(_split_host(key, n))
 
 
 class _HostIO:
@@ -228,10 +240,8 @@ class LSHSelfAttention:
       self._attention_dropout, self._output_dropout = attention_dropout, output_dropout
     else:
       self._attention_dropout = self._output_dropout = 0.0
-    if self._attention_dropout:
-      raise NotImplementedError(
-          'attention_dropout > 0 needs the (chunk_len, window) keep-mask of EA:254-262 inside the attention kernels; '
-          'not supported yet')
+    if not 0.0 <= self._attention_dropout < 1.0:
+      raise ValueError('attention_dropout must be in [0, 1)')
     if not 0.0 <= self._output_dropout < 1.0:
       raise ValueError('output_dropout must be in [0, 1)')
     self._n_hashes = n_hashes
@@ -243,6 +253,7 @@ class LSHSelfAttention:
     self._x_stash = None                # (weakref to a host x, its _version, device copy): forward -> matching backward
     self._rotations_override = None     # tests / a JAX host inject explicit rotations here
     self._out_keep_override = None      # likewise an explicit (d_model,) bool keep-mask for output dropout
+    self._attn_keep_override = None     # and an explicit (chunk_len, window) bool keep-mask for attention dropout
 
   # ---- attribute discipline (base.py:675-706) -----------------------------------------------------
   def __setattr__(self, attr, value):
@@ -410,6 +421,25 @@ class LSHSelfAttention:
       keep = torch.rand(d_model, generator=gen) < keep_prob
     return (keep.to(torch.float32) / keep_prob).to(dev)
 
+  def _attention_multiplier(self, rng, dev):
+    """keep / keep_prob of EA:254-262 as a (chunk_len, window) fp32 device tensor, or None: ONE matrix per call, shared by
+    every chunk, head, example and hash round (`attend_rng` is the same for all units, EA:1920, 2334-2335).  Like the
+    output-dropout mask it is a deterministic function of `rng` (the backward call re-draws the forward's mask) but not
+    jax.random's bits; a JAX host supplies the matrix it drew itself (`_attn_keep_override`)."""
+    if not self._attention_dropout:
+      return None
+    keep_prob = 1.0 - self._attention_dropout
+    shape = (self._chunk_len, self._chunk_len * (1 + self._n_chunks_before + self._n_chunks_after))
+    if self._attn_keep_override is not None:
+      keep = torch.as_tensor(np.asarray(self._attn_keep_override)).to(torch.bool).reshape(shape)
+    else:
+      if rng is None:
+        raise ValueError('attention_dropout > 0 needs an rng (EA:255-260)')
+      key = np.asarray(rng.cpu() if isinstance(rng, torch.Tensor) else rng).astype(np.uint32).reshape(-1)
+      gen = torch.Generator().manual_seed(((int(key[0]) << 32) | int(key[-1])) ^ 0x6174746e5f647270)   # 'attn_drp'
+      keep = torch.rand(shape, generator=gen) < keep_prob
+    return (keep.to(torch.float32) / keep_prob).contiguous().to(dev)
+
   def _dims(self, batch_size, seqlen, d_model, act_dtype):
     factors = ops.bucket_factors(self._n_buckets, seqlen, self._chunk_len)     # EA:1890-1902
     return _lib.make_dims(batch_size, self._n_heads, seqlen, d_model, self._d_qk, self._d_v,
@@ -467,6 +497,7 @@ class LSHSelfAttention:
       mask_d = to_dev(inputs[1]).to(torch.uint8).contiguous()
     w_q, w_v, w_o = (to_dev(w).to(torch.float32).contiguous() for w in weights)
     out_mult = self._output_multiplier(rng, int(x_d.shape[2]), dev)
+    attn_keep = self._attention_multiplier(rng, dev)
     if out_mult is not None:
       # EA:1995-1996: (o w_o) * m with m of shape (d_model,) shared by every position, head and example (EA:271-280, same
       # rng for all units EA:2334-2335) == o (w_o * m): the mask is folded into the packed weight in both passes and
@@ -513,14 +544,14 @@ class LSHSelfAttention:
     if not compute_grad:
       _lib.check(lib.lsh_layer_fwd(
           ctypes.byref(dims), ops._ptr(x_d), ops._ptr(w_q), ops._ptr(w_v), ops._ptr(w_o), ops._ptr(rotations),
-          ops._ptr(mask_d), ops._ptr(buckets_d), buckets_d.stride(0), ops._ptr(out_d), ops._ptr(ws), ws.numel(),
-          stream), 'lsh_layer_fwd')
+          ops._ptr(mask_d), ops._ptr(attn_keep), ops._ptr(buckets_d), buckets_d.stride(0), ops._ptr(out_d), ops._ptr(ws),
+          ws.numel(), stream), 'lsh_layer_fwd')
     else:
       if update_state:
         # EA allows update_state together with output_grad; the hash must then run first.
         _lib.check(lib.lsh_layer_fwd(
             ctypes.byref(dims), ops._ptr(x_d), ops._ptr(w_q), ops._ptr(w_v), ops._ptr(w_o), ops._ptr(rotations),
-            ops._ptr(mask_d), ops._ptr(buckets_d), buckets_d.stride(0),
+            ops._ptr(mask_d), ops._ptr(attn_keep), ops._ptr(buckets_d), buckets_d.stride(0),
             ops._ptr(out_d if out_d is not None else torch.empty_like(x_d)), ops._ptr(ws), ws.numel(), stream),
             'lsh_layer_fwd')
       g_d = to_dev(output_grad).to(x_d.dtype).contiguous()
@@ -530,7 +561,7 @@ class LSHSelfAttention:
       dw_q, dw_v, dw_o = torch.empty_like(w_q), torch.empty_like(w_v), torch.empty_like(w_o)
       _lib.check(lib.lsh_layer_bwd(
           ctypes.byref(dims), ops._ptr(x_d), ops._ptr(w_q), ops._ptr(w_v), ops._ptr(w_o), ops._ptr(mask_d),
-          ops._ptr(buckets_d), buckets_d.stride(0), ops._ptr(g_d), ops._ptr(out_d), ops._ptr(dx), ops._ptr(dw_q),
+          ops._ptr(attn_keep), ops._ptr(buckets_d), buckets_d.stride(0), ops._ptr(g_d), ops._ptr(out_d), ops._ptr(dx), ops._ptr(dw_q),
           ops._ptr(dw_v), ops._ptr(dw_o), ops._ptr(ws), ws.numel(), stream), 'lsh_layer_bwd')
       if out_mult is not None:
         dw_o.mul_(out_mult)

@@ -117,14 +117,15 @@ def chunk_possort(dims, sticker, with_bounds=False):
   return (out, bounds) if with_bounds else out
 
 
-def attend_fwd(dims, qv, sticker, mask=None):
+def attend_fwd(dims, qv, sticker, mask=None, attn_keep=None):
+  """attn_keep: optional (chunk_len, window) f32 dropout multiplier of EA:254-262 (values 0 or 1 / (1 - rate))."""
   lib = _lib.load()
   bh, n = dims.B * dims.H, dims.nh * dims.L
   o = torch.empty((bh, n, dims.dv), dtype=torch.bfloat16, device=qv.device)
   logits = torch.empty((bh, n), dtype=torch.float32, device=qv.device)
   ws = workspace(qv.device, lib.lsh_attend_fwd_workspace_bytes(ctypes.byref(dims)))
-  _lib.check(lib.lsh_attend_fwd(ctypes.byref(dims), _ptr(qv), _ptr(sticker), _ptr(mask), _ptr(o), _ptr(logits),
-                                _ptr(ws), ws.numel(), _stream()), 'lsh_attend_fwd')
+  _lib.check(lib.lsh_attend_fwd(ctypes.byref(dims), _ptr(qv), _ptr(sticker), _ptr(mask), _ptr(attn_keep), _ptr(o),
+                                _ptr(logits), _ptr(ws), ws.numel(), _stream()), 'lsh_attend_fwd')
   return o, logits
 
 
@@ -137,12 +138,12 @@ def combine_fwd(dims, o_rounds, logits):
   return o, lse
 
 
-def attend_bwd(dims, qv, sticker, o_comb, lse_tot, do_comb, mask=None):
+def attend_bwd(dims, qv, sticker, o_comb, lse_tot, do_comb, mask=None, attn_keep=None):
   lib = _lib.load()
   dqv = torch.empty_like(qv)
   nbytes = lib.lsh_attend_bwd_workspace_bytes(ctypes.byref(dims))
   ws = workspace(qv.device, nbytes)
-  _lib.check(lib.lsh_attend_bwd(ctypes.byref(dims), _ptr(qv), _ptr(sticker), _ptr(mask), _ptr(o_comb),
+  _lib.check(lib.lsh_attend_bwd(ctypes.byref(dims), _ptr(qv), _ptr(sticker), _ptr(mask), _ptr(attn_keep), _ptr(o_comb),
                                 _ptr(lse_tot), _ptr(do_comb), _ptr(dqv), _ptr(ws), ws.numel(), _stream()),
              'lsh_attend_bwd')
   return dqv

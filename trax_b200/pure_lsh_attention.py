@@ -21,7 +21,7 @@ import numpy as np
 import torch
 
 from trax_b200 import _lib, ops
-from trax_b200.lsh_attention import LSHSelfAttention, ShapeDtype, _split_host, _to_int32_bits
+from trax_b200.lsh_attention import LSHSelfAttention, ShapeDtype, _split_host, _split_rngs, _to_int32_bits
 
 
 class PureLSHSelfAttention(LSHSelfAttention):
@@ -73,7 +73,6 @@ class PureLSHSelfAttention(LSHSelfAttention):
   def forward_and_or_backward(self, inputs, state, rng, output_grad=None, compute_output=True, update_state=True):
     """Returns (output, new_state, inputs_grad): output iff compute_output, new_state iff update_state,
     inputs_grad = (dqk, dv[, None for the mask]) iff output_grad is given."""
-    del rng
     if not isinstance(inputs, (tuple, list)) or len(inputs) != self._n_in:
       raise ValueError('PureLSHSelfAttention(masked=%s) takes %d inputs' % (self._masked, self._n_in))
     compute_grad = output_grad is not None
@@ -92,6 +91,7 @@ class PureLSHSelfAttention(LSHSelfAttention):
     dev = qk.device
     dims = self._dims(batch, seqlen, 64, _lib.LSH_DTYPE_BF16)
     _lib.check(_lib.load().lsh_attn_check_dims(ctypes.byref(dims)), 'PureLSHSelfAttention')
+    attn_keep = self._attention_multiplier(rng, dev)                # EA:254-262 keep matrix (None without dropout)
     # (B*H, L, d) x 2  ->  (B, L, H, [q | v]) bf16: the row layout every kernel gathers from
     qv = torch.cat([qk.view(batch, self._n_heads, seqlen, self._d_qk), v.view(batch, self._n_heads, seqlen, self._d_v)],
                    dim=3).permute(0, 2, 1, 3).to(torch.bfloat16).contiguous()
@@ -119,7 +119,7 @@ class PureLSHSelfAttention(LSHSelfAttention):
                          % (tuple(buckets_d.shape), buckets_d.dtype))
 
     sticker, _ = ops.sort(dims, buckets_d, want_undo=False)         # EA:2766-2778
-    o_rounds, logits = ops.attend_fwd(dims, qv, sticker, mask=mask_d)   # EA:2780-2808 (un-sorted rows)
+    o_rounds, logits = ops.attend_fwd(dims, qv, sticker, mask=mask_d, attn_keep=attn_keep)   # EA:2780-2808 (un-sorted rows)
     o_comb, lse_tot = ops.combine_fwd(dims, o_rounds, logits)       # EA:2810-2814
 
     def unpack(t, d):                                               # (B, L, H, d) -> (B*H, L, d) in the input dtype
@@ -128,7 +128,7 @@ class PureLSHSelfAttention(LSHSelfAttention):
     inputs_grad = None
     if compute_grad:
       do = output_grad.to(dev).view(batch, self._n_heads, seqlen, self._d_v).permute(0, 2, 1, 3).to(torch.bfloat16).contiguous()
-      dqv = ops.attend_bwd(dims, qv, sticker, o_comb, lse_tot, do, mask=mask_d)
+      dqv = ops.attend_bwd(dims, qv, sticker, o_comb, lse_tot, do, mask=mask_d, attn_keep=attn_keep)
       inputs_grad = (unpack(dqv[..., :self._d_qk], self._d_qk), unpack(dqv[..., self._d_qk:], self._d_v))
       if self._masked:
         inputs_grad = inputs_grad + (None,)
@@ -258,7 +258,7 @@ class PureLSHSelfAttentionWrapper:
   def _kernel_bias(w):
     return (w[0], w[1]) if isinstance(w, (tuple, list)) else (w, None)
 
-  def _run(self, inputs, weights, state, output_grad, update_state):
+  def _run(self, inputs, weights, state, output_grad, update_state, rng=None):
     x, mask = (inputs[0], inputs[1]) if isinstance(inputs, (tuple, list)) else (inputs, None)
     if (mask is not None) != self._masked:
       raise ValueError('PureLSHSelfAttentionWrapper(masked=%s) takes %d inputs' % (self._masked, self._n_in))
@@ -284,7 +284,7 @@ class PureLSHSelfAttentionWrapper:
       dy = output_grad.to(device=x.device, dtype=x.dtype).reshape(B * L, D)
       d_merged = torch.matmul(dy, w_o.to(x.dtype).t()).view(B, L, D)
     core_out, new_core_state, core_grads = self._attn.forward_and_or_backward(
-        core_in, state[1], None, output_grad=self._split(d_merged).contiguous() if compute_grad else None,
+        core_in, state[1], _split_rngs(rng, 4)[1], output_grad=self._split(d_merged).contiguous() if compute_grad else None,
         compute_output=True, update_state=update_state)               # EA:3575-3577 + 3600-3602 in one call
     merged = self._merge(core_out)                                    # EA:3579-3581
     out = torch.matmul(merged.reshape(B * L, D), w_o.to(x.dtype)).view(B, L, D)      # EA:3584-3586
@@ -311,25 +311,24 @@ class PureLSHSelfAttentionWrapper:
   # ---- Layer interface ------------------------------------------------------------------------------------------
   def forward(self, inputs):
     """Serial.forward: hashes (update_state) and stores the core's new state."""
-    out, new_state, _, _ = self._run(inputs, self.weights, self.state, None, True)
+    out, new_state, _, _ = self._run(inputs, self.weights, self.state, None, True, self.rng)
     self.state = new_state
     self._attn.state = new_state[1]
     return out
 
   def pure_fn(self, inputs, weights, state, rng, use_cache=False):
-    del rng, use_cache
-    out, new_state, _, _ = self._run(inputs, weights, state, None, True)
+    del use_cache
+    out, new_state, _, _ = self._run(inputs, weights, state, None, True, rng)
     return out, new_state
 
   def forward_and_or_backward(self, inputs, weights, state, rng, output_grad=None, compute_output=True,
                               update_state=True):
     """EA:3542-3620 → (output, None, inputs_grad, weights_grad); like the reference it only serves the reversible
     backward pass: `compute_output`, not `update_state`, and an `output_grad` (EA:3566-3568)."""
-    del rng
     assert compute_output
     assert not update_state
     assert output_grad is not None
-    return self._run(inputs, weights, state, output_grad, False)
+    return self._run(inputs, weights, state, output_grad, False, rng)
 
   def backward(self, inputs, output, grad, weights, state, new_state, rng=None, **kwargs):
     del output, state, kwargs

@@ -19,17 +19,7 @@ import numpy as np
 import torch
 
 from trax_b200 import _lib, ops
-from trax_b200.lsh_attention import _split_host
-
-
-def _split_rngs(rng, n):
-  """`combinators._split_rngs` (trax/layers/combinators.py): one sub-key per sublayer, `(None,) * n` without a key.  The
-  SAME function of `rng` in `forward` and in `reverse_and_grad` (reversible.py:297, 328), so a sublayer that draws from its
-  key (output / attention dropout) draws the same mask in both passes.  Not jax.random's bits (see _split_host)."""
-  if rng is None:
-    return (None,) * n
-  key = np.asarray(rng.cpu() if isinstance(rng, torch.Tensor) else rng).astype(np.uint32).reshape(-1)
-  return tuple(_split_host(key, n))
+from trax_b200.lsh_attention import _split_rngs
 
 
 def _rows(x):
