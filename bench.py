@@ -35,9 +35,11 @@ WORKLOADS = {
                desc='ReformerLM imagenet64-style LSH layer: seq 12288, d_model 1024, 8 heads, 2 hashes, 192 buckets, 1 example per GPU'),
     'c5': dict(B=1, L=1 << 20, D=1024, H=2, C=128, nh=1, n_buckets=[32, 32], dtype='bf16',
                desc='long-context 1M-token LSH attention, per-GPU share of 16 heads over 8 GPUs (2 heads), 1 hash, n_buckets [32,32] (int32-key safe)'),
-    'c4': dict(B=1, L=16384, D=1024, H=8, C=128, nh=4, n_buckets=None, dtype='bf16',
-               desc='n_hashes sweep member: seq 16384, 4 hashes'),
 }
+for _nh in (1, 2, 4, 8):   # BASELINE config 4: n_hashes sweep at seq 16384 (n_buckets None -> [16, 16])
+  WORKLOADS['c4-nh%d' % _nh] = dict(B=1, L=16384, D=1024, H=8, C=128, nh=_nh, n_buckets=None, dtype='bf16',
+                                    desc='n_hashes sweep member: seq 16384, d_model 1024, 8 heads, chunk 128, %d hashes, n_buckets auto [16,16], causal' % _nh)
+WORKLOADS['c4'] = WORKLOADS['c4-nh4']
 
 
 def _peaks():

@@ -91,3 +91,81 @@ def test_layer_step_runs_at_full_size_and_backward_matches_reduced_dout():
   assert tuple(layer.state[0].shape) == (B * H, NH * L)
   dx, dw = layer.backward(x, out, torch.zeros_like(x), layer.weights, None, layer.state, None)
   assert float(dx.float().abs().max()) == 0.0 and all(float(g.abs().max()) == 0.0 for g in dw)
+
+
+# ---- numeric parity AT SIZE: one (example, head) unit of every BASELINE config against the fp32 oracle ---------------------
+AT_SIZE = {
+    # name: (L, C, nh, n_buckets)
+    'c2': (65536, 128, 4, None),            # BASELINE config 2 (headline): [32, 32] buckets
+    'c3': (12288, 128, 2, 192),             # config 3: imagenet64, int n_buckets = 192 (R = 96)
+    'c4-nh1': (16384, 128, 1, None),        # config 4: n_hashes sweep at seq 16384, [16, 16] buckets
+    'c4-nh2': (16384, 128, 2, None),
+    'c4-nh4': (16384, 128, 4, None),
+    'c4-nh8': (16384, 128, 8, None),
+}
+
+
+@pytest.mark.parametrize('name', sorted(AT_SIZE))
+def test_one_unit_at_size_against_the_oracle(name):
+  """VERDICT r1 #4a: bucket ids, sticker and undo_sort bit-exact, per-round logits, combined output and the attention
+  gradients within tolerance — at the sequence length, chunking, hash rounds and bucket factorisation each BASELINE config
+  names, one unit (units are independent, EA:2402-2432).  The oracle runs in fp32 (its BLAS path; ~4 s at config 2)."""
+  from oracle import lsh_oracle as O
+  from tests import util
+  from trax_b200 import ops, _lib
+  L_, C_, nh, nbk = AT_SIZE[name]
+  rng = np.random.default_rng(len(name) + L_ + nh)
+  factors = O.bucket_factors(nbk, L_, C_)
+  cfg = util.make_cfg(H=1, C=C_, nh=nh, n_buckets=nbk)
+  qv = util.bf16_round(rng.standard_normal((1, L_, 1, 128)))
+  rot = rng.standard_normal((1, 64, nh, sum(factors) // 2)).astype(np.float32)
+  do = util.bf16_round(rng.standard_normal((1, L_, 1, 64)))
+  dims = _lib.make_dims(1, 1, L_, 128, 64, 64, C_, 1, 0, nh, factors, True, False, _lib.LSH_DTYPE_BF16)
+  cu = lambda a, dt=None: torch.from_numpy(np.ascontiguousarray(a)).cuda().to(dt) if dt else torch.from_numpy(np.ascontiguousarray(a)).cuda()
+  qv_d = cu(qv, torch.bfloat16)
+  buckets = ops.hash_qv(dims, qv_d, cu(rot))
+  sticker, undo = ops.sort(dims, buckets)
+  o_r, logits = ops.attend_fwd(dims, qv_d, sticker)
+  o_c, lse = ops.combine_fwd(dims, o_r, logits)
+  dqv = ops.attend_bwd(dims, qv_d, sticker, o_c, lse, cu(do, torch.bfloat16))
+  torch.cuda.synchronize()
+
+  w_q, w_v, w_o = (w.astype(np.float32) for w in util.core_identity_weights())
+  res = O.forward_unit(cfg, qv[0, :, 0, :], w_q, w_v, w_o, rotations=rot[0], dtype=np.float32)
+  np.testing.assert_array_equal(buckets[0].cpu().numpy(), res.buckets)                 # bit-exact (north_star 1)
+  np.testing.assert_array_equal(sticker[0].cpu().numpy(), res.sticker)                 # bit-exact (north_star 2)
+  np.testing.assert_array_equal(undo[0].cpu().numpy(), res.undo_sort)
+  util.assert_close(logits[0].cpu().numpy(), res.logits, 'logits')
+  util.assert_close(o_c[0, :, 0, :].float().cpu().numpy(), res.o, 'o_comb')
+  grads = O.backward_unit(cfg, res, do[0, :, 0, :].astype(np.float32))[0]
+  got = dqv[0, :, 0, :].float().cpu().numpy()
+  util.assert_close(got[:, :64], grads[:, :64], 'dq', frac_bad_max=0.02)
+  util.assert_close(got[:, 64:], grads[:, 64:], 'dv', frac_bad_max=0.02)
+
+
+def test_config5_share_permutation_and_invariants():
+  """BASELINE config 5, one GPU's share (2 of 16 heads, 2^20 tokens, n_buckets [32, 32] so the int32 key of EA:1947 does
+  not wrap): bucket range, permutation validity / sortedness, finite outputs, partition invariance of the forward."""
+  from trax_b200 import ops, _lib
+  L5, H5 = 1 << 20, 2
+  dims = _lib.make_dims(1, H5, L5, 1024, 64, 64, 128, 1, 0, 1, [32, 32], True, False, 1)
+  g = torch.Generator('cuda').manual_seed(5)
+  qv = torch.randn((1, L5, H5, 128), device='cuda', generator=g).bfloat16()
+  keys = torch.arange(2 * H5, dtype=torch.int32, device='cuda').reshape(H5, 2) + 11
+  rot, _ = ops.make_rotations(dims, keys)
+  buckets = ops.hash_qv(dims, qv, rot)
+  assert int(buckets.min()) >= 0 and int(buckets.max()) < 1024
+  sticker, undo = ops.sort(dims, buckets)
+  ar = torch.arange(L5, device='cuda')
+  for u in range(H5):
+    s, b = sticker[u].long(), buckets[u].long()
+    assert torch.equal(undo[u].long()[s], ar)
+    key = L5 * b[s] + s
+    assert bool((key[1:] > key[:-1]).all())
+  o1, l1 = ops.attend_fwd(dims, qv, sticker)
+  assert bool(torch.isfinite(o1.float()).all()) and bool(torch.isfinite(l1).all())
+  torch.testing.assert_close(o1[:, 0].float(), qv[0, 0, :, 64:].float(), rtol=1e-2, atol=1e-2)   # position 0 sees itself only
+  do = torch.randn((1, L5, H5, 64), device='cuda', generator=g).bfloat16()
+  oc = o1.view(1, H5, L5, 64).permute(0, 2, 1, 3).contiguous()                                 # nh = 1: o_rounds == o_comb rows
+  g1 = ops.attend_bwd(dims, qv, sticker, oc, l1, do)
+  assert bool(torch.isfinite(g1.float()).all())

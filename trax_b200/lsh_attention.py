@@ -417,8 +417,9 @@ class LSHSelfAttention:
       if rng is None:
         raise ValueError('output_dropout > 0 needs an rng (EA:274)')
       key = np.asarray(rng.cpu() if isinstance(rng, torch.Tensor) else rng).astype(np.uint32).reshape(-1)
-      gen = torch.Generator().manual_seed(((int(key[0]) << 32) | int(key[-1])) ^ 0x6f75745f64726f70)   # 'out_drop'
-      keep = torch.rand(d_model, generator=gen) < keep_prob
+      # (a Philox stream keyed by all 64 key bits: torch's CPU generator only looks at the low 32 bits of its seed)
+      gen = np.random.Generator(np.random.Philox(key=((int(key[0]) << 32) | int(key[-1])) ^ 0x6f75745f64726f70))   # 'out_drop'
+      keep = torch.from_numpy(gen.random(d_model) < keep_prob)
     return (keep.to(torch.float32) / keep_prob).to(dev)
 
   def _attention_multiplier(self, rng, dev):
@@ -436,8 +437,8 @@ class LSHSelfAttention:
       if rng is None:
         raise ValueError('attention_dropout > 0 needs an rng (EA:255-260)')
       key = np.asarray(rng.cpu() if isinstance(rng, torch.Tensor) else rng).astype(np.uint32).reshape(-1)
-      gen = torch.Generator().manual_seed(((int(key[0]) << 32) | int(key[-1])) ^ 0x6174746e5f647270)   # 'attn_drp'
-      keep = torch.rand(shape, generator=gen) < keep_prob
+      gen = np.random.Generator(np.random.Philox(key=((int(key[0]) << 32) | int(key[-1])) ^ 0x6174746e5f647270))   # 'attn_drp'
+      keep = torch.from_numpy(gen.random(shape) < keep_prob)
     return (keep.to(torch.float32) / keep_prob).contiguous().to(dev)
 
   def _dims(self, batch_size, seqlen, d_model, act_dtype):
