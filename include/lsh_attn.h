@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define LSH_ATTN_ABI_VERSION 2
+#define LSH_ATTN_ABI_VERSION 3
 
 enum { LSH_DTYPE_F32 = 0, LSH_DTYPE_BF16 = 1 };
 
@@ -170,11 +170,16 @@ int lsh_layer_fwd(const LshAttnDims *dims, const void *x, const float *w_q, cons
  * (compute_output=True, the call ReversibleHalfResidual makes, reversible.py:374-378).
  * dw_q/dw_v/dw_o are fully overwritten with the sum over examples (EA:2431); dx (B,L,D) with the
  * sum over heads (EA:2430).  Work is ordered on `stream`; one GEMM (do = dout·w_o^T) runs on an internal
- * helper stream that is forked from and joined back into `stream` by events (no host wait, capture-safe). */
+ * helper stream that is forked from and joined back into `stream` by events (no host wait, capture-safe).
+ * ev_dwo_ready / ev_dwqv_ready (cudaEvent_t passed as void*, either may be NULL) are recorded on `stream` the moment
+ * dw_o, resp. dw_q and dw_v, are final — dw_o before the attention-gradient kernels start, dw_q|dw_v before the last
+ * GEMM (dx) — so a data-parallel caller can start the gradient all-reduce (`psum`, trax/optimizers/trainer.py:197-199)
+ * on its own communication stream underneath the rest of the call. */
 int lsh_layer_bwd(const LshAttnDims *dims, const void *x, const float *w_q, const float *w_v,
                   const float *w_o, const uint8_t *mask, const float *attn_keep, const int32_t *buckets,
                   int64_t buckets_stride, const void *dout, void *out, void *dx, float *dw_q,
-                  float *dw_v, float *dw_o, void *ws, size_t ws_bytes, void *stream);
+                  float *dw_v, float *dw_o, void *ws, size_t ws_bytes, void *ev_dwo_ready,
+                  void *ev_dwqv_ready, void *stream);
 
 /* ---- helpers ---------------------------------------------------------------------------------- */
 

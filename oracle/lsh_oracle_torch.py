@@ -37,12 +37,12 @@ def forward_unit_torch(x, w_q, w_v, w_o, sticker, *, seqlen, chunk_len, n_hashes
                       for i in range(-n_chunks_before, n_chunks_after + 1)], dim=1)
   k, cv, ki = look(k), look(cv), look(ki)
   dots = cq @ k.transpose(-1, -2)                                  # EA:244
-  qf, kf = qi[:, :, None].double(), ki[:, None, :].double()
+  qf, kf = qi[:, :, None].to(dots.dtype), ki[:, None, :].to(dots.dtype)   # (float32 inputs: the timing path of bench.py)
   if causal:
-    dots = dots - 1e9 * (qf < kf).double()                         # EA:150-152
-  dots = dots - 1e5 * (qf == kf).double()                          # EA:153-155
+    dots = dots - 1e9 * (qf < kf).to(dots.dtype)                   # EA:150-152
+  dots = dots - 1e5 * (qf == kf).to(dots.dtype)                    # EA:153-155
   if masked:
-    dots = dots - 1e9 * (kf < 0).double()                          # EA:156-159
+    dots = dots - 1e9 * (kf < 0).to(dots.dtype)                    # EA:156-159
   lse = torch.logsumexp(dots, -1, keepdim=True)                    # EA:251
   p = torch.exp(dots - lse)                                        # EA:252
   if attn_keep is not None:

@@ -13,13 +13,15 @@ o_r, logits = ops.attend_fwd(dims, qv, sticker)
 o_c, lse = ops.combine_fwd(dims, o_r, logits)
 do = torch.randn_like(o_c)
 ops.attend_bwd(dims, qv, sticker, o_c, lse, do); torch.cuda.synchronize()
-tr = torch.zeros(120 * 8, dtype=torch.int64, device='cuda')
+tr = torch.zeros(120 * 32, dtype=torch.int64, device='cuda')
 lib = ctypes.CDLL(_lib.LIB_PATH); lib.lsh_debug_set_trace(ctypes.c_void_p(tr.data_ptr()))
 ops.attend_bwd(dims, qv, sticker, o_c, lse, do); torch.cuda.synchronize()
 lib.lsh_debug_set_trace(None)
-t = tr.cpu().view(120, 8)
+t = tr.cpu().view(120, 32)
+if not bool((t > 0).any()):
+  print('(library built without -DLSH_TRACE)'); sys.exit(0)
 t0 = int(t[t > 0].min())
-names = ['mma_pds0', 'mma_pds1', 'mma_done', 'w0_st', 'w0_pass', 'w1_st', 'w1_pass', 'w0_epi']
-print('n  ' + ' '.join('%9s' % n for n in names))
-for k in list(range(0, 8)) + list(range(100, 116)):
-  print('%3d ' % k + ' '.join('%9d' % (int(v) - t0 if v > 0 else -1) for v in t[k]))
+names = ['pds0', 'pds1', 'done'] + ['p%d' % w for w in range(8)] + ['s%d' % w for w in range(8)] + ['kv0', 'st0', 'kv1', 'st1', 'dq', 'epi', 'kvful', 'prod', 'tiles', 'Wblk', 'Wstw', 'Wfnc', 'Wmid']
+print('n   ' + ' '.join('%7s' % n for n in names))
+for k in list(range(0, 6)) + list(range(96, 112)):
+  print('%3d ' % k + ' '.join('%7d' % (int(v) - t0 if v > 0 else -1) for v in t[k][:len(names)]))

@@ -11,5 +11,6 @@ from trax_b200.lsh_attention import (LSHSelfAttention, ShapeDtype, host_io_bytes
 from trax_b200.pure_lsh_attention import PureLSHSelfAttention, PureLSHSelfAttentionWrapper  # noqa: F401
 from trax_b200.reversible import ReversibleHalfResidual  # noqa: F401
 from trax_b200.self_attention import SelfAttention  # noqa: F401
+from trax_b200.dp import HeadShardedLSHSelfAttention  # noqa: F401
 
-__all__ = ['LSHSelfAttention', 'PureLSHSelfAttention', 'PureLSHSelfAttentionWrapper', 'ReversibleHalfResidual', 'SelfAttention', 'ShapeDtype', 'set_async_host_io', 'set_reuse_forward_upload', 'set_weight_grad_allreduce', 'synchronize', 'host_io_bytes']
+__all__ = ['HeadShardedLSHSelfAttention', 'LSHSelfAttention', 'PureLSHSelfAttention', 'PureLSHSelfAttentionWrapper', 'ReversibleHalfResidual', 'SelfAttention', 'ShapeDtype', 'set_async_host_io', 'set_reuse_forward_upload', 'set_weight_grad_allreduce', 'synchronize', 'host_io_bytes']

@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('LSH_ATTN_LIB') or os.path.join(_HERE, 'liblsh_attn_b200.so')   # override: kernel experiments
 
 LSH_DTYPE_F32, LSH_DTYPE_BF16 = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class LshAttnDims(ctypes.Structure):
@@ -47,7 +47,7 @@ SIGNATURES = {
     'lsh_attend_bwd': (_I, [_D, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     'lsh_layer_workspace_bytes': (_SZ, [_D, _I]),
     'lsh_layer_fwd': (_I, [_D, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _SZ, _P]),
-    'lsh_layer_bwd': (_I, [_D, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    'lsh_layer_bwd': (_I, [_D, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _SZ, _P, _P, _P]),
     'lsh_make_rotations': (_I, [_D, _P, _P, _P, _P]),
     'lsh_layernorm_fwd': (_I, [_I64, _I, _I, _P, _P, _P, _P, _P, ctypes.c_float, _P]),
     'lsh_layernorm_bwd': (_I, [_I64, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -27,6 +27,7 @@ int set_error(const char *fmt, ...) {
 void count_launch(int n) { g_launches += n; }
 
 extern long long *g_fwd_trace;   // attend_fwd.cu (debug trace buffer)
+extern int g_bwd_parts;          // attend_bwd.cu (measurement hook)
 
 // ---- kernels implemented in the other translation units --------------------------------------------
 int hash_bf16_qv(const LshAttnDims &, const void *, const float *, const uint8_t *, int32_t *, int64_t, cudaStream_t);
@@ -377,7 +378,7 @@ int lsh_layer_fwd(const LshAttnDims *dims, const void *x, const float *w_q, cons
 int lsh_layer_bwd(const LshAttnDims *dims, const void *x, const float *w_q, const float *w_v, const float *w_o,
                   const uint8_t *mask, const float *attn_keep, const int32_t *buckets, int64_t buckets_stride,
                   const void *dout, void *out, void *dx, float *dw_q, float *dw_v, float *dw_o, void *ws, size_t ws_bytes,
-                  void *stream) {
+                  void *ev_dwo_ready, void *ev_dwqv_ready, void *stream) {
   if (int rc = check_dims(dims, true)) return rc;
   const LshAttnDims &d = *dims;
   if (!x || !w_q || !w_v || !w_o || !buckets || !dout || !dx || !dw_q || !dw_v || !dw_o || !ws)
@@ -417,12 +418,14 @@ int lsh_layer_bwd(const LshAttnDims *dims, const void *x, const float *w_q, cons
   LSH_CUDA_OK(cudaStreamWaitEvent(s, side->join, 0));
   // B1 (second half): dW_o = o^T·dout
   if ((rc = gemm_rm(true, false, KO, d.D, BL, w.o_comb, KO, doutb, d.D, dw_o, d.D, true, w.cublas, s))) return rc;
+  if (ev_dwo_ready) LSH_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(ev_dwo_ready), s));
   // B2-B6
   if ((rc = attend_bwd_run(d, w.qv, w.sticker, mask, w.o_comb, w.lse_tot, w.do_comb, w.aux.qscale, attend_fwd_uses_tc(d) ? w.aux.sticker2 : nullptr, attend_fwd_uses_tc(d) ? w.aux.bounds : nullptr, kp, w.dqv, w.bwd_ws, w.bwd_bytes, s)))
     return rc;
   // B7: dW_q|dW_v = x^T·dqv ; dx = dqv·wqv^T
   if ((rc = gemm_rm(true, false, d.D, NQV, BL, xb, d.D, w.dqv, NQV, w.dwqv, NQV, true, w.cublas, s))) return rc;
   if ((rc = unpack_dwqv_run(d, w.dwqv, dw_q, dw_v, s))) return rc;
+  if (ev_dwqv_ready) LSH_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(ev_dwqv_ready), s));
   return gemm_rm(false, true, BL, d.D, NQV, w.dqv, NQV, w.wqv, NQV, dx, d.D, f32, w.cublas, s);
 }
 
@@ -456,6 +459,9 @@ int lsh_residual_add(int64_t n, int act_dtype, const void *a, const void *b, voi
 
 /* Debug aid (not in the public header): device buffer receiving per-phase clock stamps of CTA 0. */
 int lsh_debug_set_trace(void *dev_ptr) { lsh::g_fwd_trace = static_cast<long long *>(dev_ptr); return 0; }
+
+/* Measurement hook (not in the public header): see g_bwd_parts in attend_bwd.cu.  Returns the previous mask. */
+int lsh_debug_set_bwd_parts(int mask) { const int old = lsh::g_bwd_parts; lsh::g_bwd_parts = mask & 7; return old; }
 
 int lsh_make_rotations(const LshAttnDims *dims, const uint32_t *keys, uint32_t *new_keys, float *rotations,
                        void *stream) {

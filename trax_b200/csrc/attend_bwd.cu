@@ -309,6 +309,11 @@ int qscale_run(const LshAttnDims &d, const void *qv, float *qscale, float2 *rowm
 int chunk_possort_run(const LshAttnDims &d, const int32_t *sticker, int32_t *sticker2, int32_t *bounds, cudaStream_t stream);
 bool attend_tc_uses_bounds();
 
+// Measurement hook (lsh_debug_set_bwd_parts, bench.py): which parts of the stage run — bit 0 the per-token preparation
+// kernels, bit 1 the attention-gradient kernel, bit 2 the sum over hash rounds.  7 = everything (the only product setting);
+// a part that is skipped leaves the workspace of an earlier full call in place, so one part can be timed alone.
+int g_bwd_parts = 7;
+
 int attend_bwd_run(const LshAttnDims &d, const void *qv, const int32_t *sticker, const uint8_t *mask,
                    const void *o_comb, const float *lse_tot, const void *do_comb, const float *qscale_in,
                    const int32_t *sticker2_in, const int32_t *bounds_in, const AttnKeep *keep, void *dqv, void *ws, size_t ws_bytes,
@@ -334,27 +339,28 @@ int attend_bwd_run(const LshAttnDims &d, const void *qv, const int32_t *sticker,
   const bool dropout = keep && keep->bits_t;   // the tcgen05 backward works on position-sorted tiles; the keep matrix is in slot order
   if (d.C == 128 && d.nb == 1 && d.na == 0 && d.causal && !d.masked && d.L % 128 == 0 && !force_mma && !dropout) {
     const float *qscale = qscale_in;
+    const bool prep = g_bwd_parts & 1;
     if (!qscale) {
-      if ((rc = qscale_run(d, qv, qscale_ws, nullptr, nullptr, stream))) return rc;
+      if (prep && (rc = qscale_run(d, qv, qscale_ws, nullptr, nullptr, stream))) return rc;
       qscale = qscale_ws;
     }
-    if ((rc = bwd_prep_tc_run(d, do_comb, o_comb, lse_tot, dvec, lse2, qcmp, stream))) return rc;
+    if (prep && (rc = bwd_prep_tc_run(d, do_comb, o_comb, lse_tot, dvec, lse2, qcmp, stream))) return rc;
     // position-sorted chunks: from the forward pass of the same layer call if it made them, else into the (unused on this
     // path) second partial-dq area of the workspace
     const int32_t *sticker2 = sticker2_in, *bounds = bounds_in;
     if (!sticker2 || (!bounds && attend_tc_uses_bounds())) {
       int32_t *s2 = reinterpret_cast<int32_t *>(dq_part + rows * 64), *bd = attend_tc_uses_bounds() ? s2 + rows : nullptr;
-      if ((rc = chunk_possort_run(d, sticker, s2, bd, stream))) return rc;
+      if (prep && (rc = chunk_possort_run(d, sticker, s2, bd, stream))) return rc;
       sticker2 = s2; bounds = bd;
     }
     AttendBwdTcParams t;
     t.qv = static_cast<const __nv_bfloat16 *>(qv); t.sticker = sticker; t.sticker2 = sticker2; t.bounds = bounds;
     t.do_comb = static_cast<const __nv_bfloat16 *>(do_comb); t.qscale = qscale; t.lse2 = lse2; t.dvec = dvec; t.qcmp = qcmp;
     t.trace = g_fwd_trace; t.dq_out = dq_part; t.dv_out = dv_part; t.L = d.L; t.H = d.H; t.N = dr.N; t.n_chunks = dr.n_chunks;
-    if ((rc = attend_bwd_tc_run(t, dr.BH, stream))) return rc;
-    return sum_rounds_run(d, dq_part, dv_part, dqv, 1, stream);
+    if ((g_bwd_parts & 2) && (rc = attend_bwd_tc_run(t, dr.BH, stream))) return rc;
+    return (g_bwd_parts & 4) ? sum_rounds_run(d, dq_part, dv_part, dqv, 1, stream) : 0;
   }
-  rc = bwd_prep_run(d, do_comb, o_comb, dvec, stream);
+  rc = (g_bwd_parts & 1) ? bwd_prep_run(d, do_comb, o_comb, dvec, stream) : 0;
   if (rc) return rc;
   AttendBwdParams p;
   p.qv = static_cast<const __nv_bfloat16 *>(qv); p.sticker = sticker; p.mask = d.masked ? mask : nullptr;
@@ -363,14 +369,14 @@ int attend_bwd_run(const LshAttnDims &d, const void *qv, const int32_t *sticker,
   p.L = d.L; p.H = d.H; p.N = dr.N; p.n_chunks = dr.n_chunks; p.nb = d.nb; p.nwin = dr.nwin;
   p.causal = d.causal; p.masked = d.masked;
   p.keep_bits_t = dropout ? keep->bits_t : nullptr; p.keep_scale = dropout ? keep->scale : nullptr;
-  switch (d.C) {
+  if (g_bwd_parts & 2) switch (d.C) {
     case 64: rc = launch_attend_bwd<64>(p, dr.BH, stream); break;
     case 128: rc = launch_attend_bwd<128>(p, dr.BH, stream); break;
     case 256: rc = launch_attend_bwd<256>(p, dr.BH, stream); break;
     default: return set_error("attend_bwd: chunk_len %d unsupported (64, 128, 256)", d.C);
   }
   if (rc) return rc;
-  return sum_rounds_run(d, dq_part, dv_part, dqv, dr.nwin + 1, stream);
+  return (g_bwd_parts & 4) ? sum_rounds_run(d, dq_part, dv_part, dqv, dr.nwin + 1, stream) : 0;
 }
 
 }  // namespace lsh

@@ -46,11 +46,13 @@ constexpr uint32_t BT_IDESC_ST = make_idesc_bf16(128, 64, 0, 0);   // S^T, dP^T
 constexpr uint32_t BT_IDESC_KV = make_idesc_bf16(128, 64, 0, 1);   // dV, dK^ (B MN-major)
 constexpr uint32_t BT_IDESC_DQ = make_idesc_bf16(128, 64, 1, 1);   // dQ (A and B MN-major)
 
-// trace slots per item: 0 MMA: pds_full[0] seen, 1 MMA: pds_full[1] seen, 2 MMA: item done (commits issued),
-// 3 WG0: st_full seen, 4 WG0: pass done, 5 WG1: st_full seen, 6 WG1: pass done, 7 WG0: epilogue done
+// trace slots per item (32): 0 MMA: pds_full[0] seen, 1 MMA: pds_full[1] seen, 2 MMA: item done (commits issued),
+// 3..10 softmax warp w: pass done, 11..18 softmax warp w: st_full seen, 19/21 MMA: dV/dK of half 0/1 issued, 20/22 MMA: next
+// item's S^T half 0/1 issued, 23 MMA: dQ issued, 24 epilogue done, 25 epilogue: kv_full seen, 26 producer: tile issued,
+// 27 softmax warp 0: tiles seen
 // (compiled in only with -DLSH_TRACE: the stamps cost instruction-cache space in every role)
 #ifdef LSH_TRACE
-#define BT_TRACE(n, slot) do { if (p.trace && blockIdx.x == 0 && (n) < 120) p.trace[(n) * 8 + (slot)] = clock64(); } while (0)
+#define BT_TRACE(n, slot) do { if (p.trace && blockIdx.x == 0 && (n) < 120) p.trace[(n) * 32 + (slot)] = clock64(); } while (0)
 #else
 #define BT_TRACE(n, slot) do { } while (0)
 #endif
@@ -223,6 +225,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) attend_bwd_tc_kernel(const Atte
         w.chunks(c_key, c_next);
         if (!it.real) load_tile(it.seq_k, it.u, c_key);
         load_tile(it.seq_k + 1, it.u, c_next);
+        if (tid == 12 * 32) BT_TRACE(it.n, 26);
       }
       w.next();
     }
@@ -295,10 +298,12 @@ BT_ISSUE_UNROLL
           }
           __syncwarp();
         }
+        if (lane == 0) BT_TRACE(cur.n, 19 + 2 * h);
         // region h is free once the MMAs above have read it (in-order pipe)
         probe();
         if (pre_ok) {
           for (; st_issued <= h; ++st_issued) issue_st(nxt, st_issued);
+          if (lane == 0) BT_TRACE(cur.n, 20 + 2 * h);
         }
       }
       {
@@ -323,6 +328,7 @@ BT_ISSUE_UNROLL
         }
         __syncwarp();
       }
+      if (lane == 0) BT_TRACE(cur.n, 23);
       probe();
       if (pre_ok) {
         for (; st_issued < 2; ++st_issued) issue_st(nxt, st_issued);
@@ -342,6 +348,8 @@ BT_ISSUE_UNROLL
     const uint32_t t_lane = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     const uint32_t r_st = t_lane + 128 * h;
     float ksc_j = 0.f, ki_j = 0.f;
+    // my 128-byte row of the dS staging tile (shared-space address: plain STS, no generic-address stores)
+    const uint32_t ds_row = ds_u32 + h * (BT_C * 128) + row * 128, r7 = static_cast<uint32_t>(row & 7);
     for (BtWalk w(g0, g1, p.n_chunks); w.valid(); w.next()) {
       const BtItem it = w.item();
       const uint32_t slk = bt_slot(it.seq_k), slq = bt_slot(it.seq_q);
@@ -351,10 +359,11 @@ BT_ISSUE_UNROLL
         ki_j = sh.meta[slk].kinfo[row];
       }
       mbar_wait(&sh.full[slq], bt_phase(it.seq_q));
+      if (tid == 0) BT_TRACE(it.n, 27);
       const BtTileMeta &mq = sh.meta[slq];
       const float kst_j = ksc_j * kLn2;                    // true key scale 1/(r*sqrt(dq)) for the dQ operand
       const uint64_t ksc2 = pk2(ksc_j, ksc_j), kst2 = pk2(kst_j, kst_j);
-      uint8_t *dsrow = dsbuf + (it.n & 1) * BT_DS_BYTES + h * (BT_C * 128);
+      const uint32_t ds_dst = ds_row + (it.n & 1) * BT_DS_BYTES;
       // Tiles are ordered by position (chunk_possort_kernel), so for key j the queries of the tile split into three index
       // ranges: [0, lo) position below the key's — never visible (EA:150-152); [lo, hi) the same position — the key's own
       // token or its copy from the neighbouring hash round, visible only to self-only rows (qcmp rule); [hi, 128) visible.
@@ -380,10 +389,13 @@ BT_ISSUE_UNROLL
       mbar_wait(&sh.st_full[h], it.n & 1);
       mbar_wait(&sh.dsm_free[it.n & 1], ((it.n >> 1) & 1) ^ 1);
       tc_fence_after();
-      if (row == 0) BT_TRACE(it.n, 3 + 2 * h);
+      if (lane == 0) BT_TRACE(it.n, 11 + warp);
 #pragma unroll 1
       for (int cc = 0; cc < 64; cc += 32) {
         const int c0 = 64 * h + cc;
+#ifdef LSH_TRACE_WARP
+        if (cc == 32 && warp == LSH_TRACE_WARP && lane == 0) BT_TRACE(it.n, 31);
+#endif
         uint32_t s[32], pk_p[16], pk_ds[16];
         if (c0 + 32 <= min_lo) {
           // no key of this warp sees any query of the block
@@ -436,17 +448,23 @@ BT_ISSUE_UNROLL
           tmem_st16(r_st + 64 + (cc >> 1), pk_ds);
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 v;
-          v.x = s[4 * q]; v.y = s[4 * q + 1]; v.z = s[4 * q + 2]; v.w = s[4 * q + 3];
-          *reinterpret_cast<uint4 *>(dsrow + swz(row, (cc >> 3) + q)) = v;
-        }
+        for (int q = 0; q < 4; ++q)
+          sts128(ds_dst + ((static_cast<uint32_t>((cc >> 3) + q) ^ r7) << 4), s[4 * q], s[4 * q + 1], s[4 * q + 2], s[4 * q + 3]);
       }
+#ifdef LSH_TRACE_WARP
+      if (warp == LSH_TRACE_WARP && lane == 0) BT_TRACE(it.n, 28);
+#endif
       tmem_st_wait();
+#ifdef LSH_TRACE_WARP
+      if (warp == LSH_TRACE_WARP && lane == 0) BT_TRACE(it.n, 29);
+#endif
       fence_proxy_async();                                 // dS staging writes -> UMMA (async proxy)
+#ifdef LSH_TRACE_WARP
+      if (warp == LSH_TRACE_WARP && lane == 0) BT_TRACE(it.n, 30);
+#endif
       tc_fence_before();
       mbar_arrive(&sh.pds_full[h]);
-      if (row == 0) BT_TRACE(it.n, 4 + 2 * h);
+      if (lane == 0) BT_TRACE(it.n, 3 + warp);
 
       if (it.iter_end) {
         // this thread is done with the key tile (and, at a segment end, with the trailing query tile)
@@ -469,10 +487,11 @@ BT_ISSUE_UNROLL
         const float ksc_j = sh.meta[slk].kscl[row];
         const int tk = sh.meta[slk].tk[row];
         const int64_t orow = (static_cast<int64_t>(it.u) * p.N + tk) * 64;
-        const uint8_t *kt = tiles + slk * BT_TILE_BYTES;
+        const uint32_t kt_row = tiles_u32 + slk * BT_TILE_BYTES + row * 128, r7 = static_cast<uint32_t>(row & 7);
         mbar_wait(&sh.dq_full[it.rit & 1], (it.rit >> 1) & 1);
         mbar_wait(&sh.kv_full, it.rit & 1);
         tc_fence_after();
+        if (row == 0) BT_TRACE(it.n, 25);
         uint32_t dk0[32], dk1[32];
         __nv_bfloat16 *dq_dst = p.dq_out + orow, *dv_dst = p.dv_out + orow;
         tmem_ld32(t_lane + 256, dk0);
@@ -503,7 +522,7 @@ BT_ISSUE_UNROLL
         float dot = 0.f;
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) {
-          const uint4 raw = *reinterpret_cast<const uint4 *>(kt + swz(row, ch));
+          const uint4 raw = lds128u(kt_row + ((static_cast<uint32_t>(ch) ^ r7) << 4));
           const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -528,7 +547,7 @@ BT_ISSUE_UNROLL
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4) {
             const int ch = half * 4 + c4;
-            const uint4 raw = *reinterpret_cast<const uint4 *>(kt + swz(row, ch));
+            const uint4 raw = lds128u(kt_row + ((static_cast<uint32_t>(ch) ^ r7) << 4));
             const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
             uint32_t o[4];
 #pragma unroll
@@ -545,7 +564,7 @@ BT_ISSUE_UNROLL
         // last read of the key tile's rows is behind us: give the ring slot back
         mbar_arrive(&sh.empty[slk]);
         if (it.last_seg) mbar_arrive(&sh.empty[bt_slot(it.seq_k + 1)]);
-        if (row == 0) BT_TRACE(it.n, 7);
+        if (row == 0) BT_TRACE(it.n, 24);
       } else {
         mbar_arrive(&sh.empty[slk]);                           // pre item: this warpgroup never touches the tile
       }

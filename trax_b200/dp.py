@@ -18,6 +18,60 @@ def shard_batch(x, rank, world_size):
   return x[rank * per:(rank + 1) * per]
 
 
+class GradOverlap:
+  """Mean of the layer's weight gradients over the data-parallel group, overlapped with the rest of the backward call.
+
+  `lsh_layer_bwd` records one CUDA event when dw_o is final (before the attention-gradient kernels) and one when
+  dw_q | dw_v are final (before the dx GEMM).  `reduce` makes a per-device communication stream wait for those events,
+  all-reduces the two slices of the caller's flat gradient buffer IN PLACE there (NCCL `AVG`: no concatenation, no
+  copy back, no separate division) and lets the caller's stream wait for the result — which by then has travelled
+  underneath the remaining kernels of the call."""
+  _per_device = {}
+
+  def __init__(self, dev):
+    self.dev = dev
+    self.comm = torch.cuda.Stream(device=dev)
+    self._events = None
+
+  @classmethod
+  def get(cls, dev):
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1 or dist.get_backend() != 'nccl':
+      return None
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    inst = cls._per_device.get(key)
+    if inst is None:
+      inst = cls._per_device[key] = cls(dev)
+    return inst
+
+  def events(self):
+    """Two events per call from a small ring (torch creates the CUDA event at its first record)."""
+    if self._events is None:
+      self._events, self._next = [], 0
+      main = torch.cuda.current_stream(self.dev)
+      for _ in range(8):
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self._events.append(ev)
+    pair = self._events[self._next], self._events[self._next + 1]
+    self._next = (self._next + 2) % len(self._events)
+    return pair
+
+  def reduce(self, flat, n_qv, ev_o, ev_qv):
+    main = torch.cuda.current_stream(self.dev)
+    flat.record_stream(self.comm)
+    with torch.cuda.stream(self.comm):
+      if ev_o is not None:
+        self.comm.wait_event(ev_o)
+        dist.all_reduce(flat[n_qv:], op=dist.ReduceOp.AVG)
+      self.comm.wait_event(ev_qv)
+      dist.all_reduce(flat[:n_qv], op=dist.ReduceOp.AVG)
+      if ev_o is None:                       # dw_o was finalised on the caller's stream after the C call
+        self.comm.wait_event(main.record_event())
+        dist.all_reduce(flat[n_qv:], op=dist.ReduceOp.AVG)
+      done = self.comm.record_event()
+    main.wait_event(done)
+
+
 def allreduce_mean_(grads, group=None):
   """In-place mean of a tuple of gradient tensors over the process group, as ONE flat all-reduce
   (6.3 MB at config 2/3: latency-bound, so a single bucket)."""
@@ -39,3 +93,112 @@ def allreduce_mean_(grads, group=None):
     g.copy_(flat[off:off + n].view_as(g))
     off += n
   return grads
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Head sharding (BASELINE config 5): few examples, many heads, one long sequence
+# ---------------------------------------------------------------------------------------------------------------------
+def head_range(n_heads, rank, world_size):
+  """Heads [h0, h1) owned by `rank`: contiguous blocks, the unit order b*H + h of EA:2406-2407 restricted to them."""
+  if n_heads % world_size != 0:
+    raise ValueError('n_heads %d not divisible by %d ranks' % (n_heads, world_size))
+  per = n_heads // world_size
+  return rank * per, (rank + 1) * per
+
+
+def shard_heads(weights, state, n_heads, rank, world_size):
+  """A rank's slice of the full layer's `(w_q, w_v, w_o)` (head-major, EA:1829-1830) and `(buckets, rng)` state
+  (rows b*H + h, EA:1831): the result is the weights / state of a layer with n_heads / world_size heads."""
+  h0, h1 = head_range(n_heads, rank, world_size)
+  w = tuple(t[h0:h1].contiguous() for t in weights)
+  s = state
+  if state is not None and len(state) == 2:
+    buckets, rng = state
+    bsz = buckets.shape[0] // n_heads
+    rows = torch.arange(bsz).repeat_interleave(h1 - h0) * n_heads + torch.arange(h0, h1).repeat(bsz)
+    rows = rows.to(buckets.device)
+    s = (buckets[rows].contiguous(), rng[rows.to(rng.device)].contiguous())
+  return w, s
+
+
+class HeadShardedLSHSelfAttention:
+  """`LSHSelfAttention` with its heads split over the ranks of a process group (one process per GPU).
+
+  The reference sums heads into the output and into the input gradient (`index_add` at EA:2426 and EA:2430); units are
+  otherwise independent (EA:2402-2432).  Here every rank owns n_heads / world_size heads — their weights, their bucket
+  state — and sees the whole input; the two head sums become `all_reduce(SUM)` of the (B, L, D) partial output and
+  partial input gradient over NVLink (NCCL on the GPU box, gloo in the CPU tests).  There is no weight-gradient collective:
+  a head's weights live on one rank.  `reduce='scatter'` leaves each rank with its L / world_size rows of the sum instead
+  (a sequence-parallel consumer — the position-wise residual / feed-forward half of the block — then all-gathers only
+  what the next attention layer needs; half the traffic of the all-reduce per call).
+
+  `local_layer` is the per-rank layer (built by the caller with n_heads / world_size heads), so the CPU tests can run
+  the same plumbing around the oracle.  Collectives are issued on the caller's stream, after the call's last kernel;
+  they are INSIDE whatever the caller times.
+  """
+
+  def __init__(self, local_layer, n_heads, group=None, reduce='all'):
+    if reduce not in ('all', 'scatter'):
+      raise ValueError("reduce must be 'all' or 'scatter'")
+    self._local = local_layer
+    self._n_heads = n_heads
+    self._group = group
+    self._reduce = reduce
+    self._world = dist.get_world_size(group) if dist.is_initialized() else 1
+    self._rank = dist.get_rank(group) if dist.is_initialized() else 0
+    head_range(n_heads, self._rank, self._world)
+    self.comm_bytes = 0
+
+  @property
+  def local(self):
+    return self._local
+
+  @property
+  def weights(self):
+    return self._local.weights
+
+  @property
+  def state(self):
+    return self._local.state
+
+  def load_full(self, weights, state):
+    """Takes this rank's heads out of the full layer's weights / state (same values on every rank)."""
+    self._local.weights, self._local.state = shard_heads(weights, state, self._n_heads, self._rank, self._world)
+
+  def _head_sum(self, t):
+    """Sum of the per-rank partial results over the group (EA:2426 / EA:2430 across ranks)."""
+    if self._world == 1 or t is None:
+      return t
+    on_host = not t.is_cuda and dist.get_backend(self._group) == 'nccl'
+    d = t.cuda(non_blocking=True) if on_host else t
+    self.comm_bytes += d.numel() * d.element_size()
+    if self._reduce == 'all':
+      dist.all_reduce(d, op=dist.ReduceOp.SUM, group=self._group)
+    else:
+      bsz, seqlen = d.shape[0], d.shape[1]
+      if seqlen % self._world != 0:
+        raise ValueError('seqlen %d not divisible by %d ranks' % (seqlen, self._world))
+      per = seqlen // self._world
+      mine = torch.empty((bsz, per) + tuple(d.shape[2:]), dtype=d.dtype, device=d.device)
+      chunks = [d[:, r * per:(r + 1) * per].contiguous() for r in range(self._world)]
+      dist.reduce_scatter(mine, chunks, op=dist.ReduceOp.SUM, group=self._group)
+      d = mine
+    return d.cpu() if on_host else d
+
+  def forward(self, inputs):
+    return self._head_sum(self._local.forward(inputs))
+
+  def backward(self, inputs, output, grad, weights, state, new_state, rng=None, **kwargs):
+    dx, dw = self._local.backward(inputs, output, grad, weights, state, new_state, rng, **kwargs)
+    if isinstance(dx, tuple):
+      return (self._head_sum(dx[0]),) + dx[1:], dw
+    return self._head_sum(dx), dw
+
+  def forward_and_or_backward(self, inputs, weights, state, rng, output_grad=None, compute_output=True, update_state=True):
+    out, new_state, dx, dw = self._local.forward_and_or_backward(inputs, weights, state, rng, output_grad=output_grad,
+                                                                 compute_output=compute_output, update_state=update_state)
+    if isinstance(dx, tuple):
+      dx = (self._head_sum(dx[0]),) + dx[1:]
+    else:
+      dx = self._head_sum(dx)
+    return self._head_sum(out), new_state, dx, dw

@@ -559,15 +559,30 @@ class LSHSelfAttention:
       if g_d.shape != x_d.shape:
         raise ValueError('output_grad shape %s != input shape %s' % (tuple(g_d.shape), tuple(x_d.shape)))
       dx = torch.empty_like(x_d)
-      dw_q, dw_v, dw_o = torch.empty_like(w_q), torch.empty_like(w_v), torch.empty_like(w_o)
+      # one contiguous gradient buffer (dw_q | dw_v | dw_o): the data-parallel mean below reduces slices of it in place
+      n_q, n_v, n_o = w_q.numel(), w_v.numel(), w_o.numel()
+      dw_flat = torch.empty(n_q + n_v + n_o, dtype=torch.float32, device=dev)
+      dw_q, dw_v = dw_flat[:n_q].view_as(w_q), dw_flat[n_q:n_q + n_v].view_as(w_v)
+      dw_o = dw_flat[n_q + n_v:].view_as(w_o)
+      overlap = None
+      if _GRAD_ALLREDUCE['on']:
+        from trax_b200 import dp
+        overlap = dp.GradOverlap.get(dev)         # None without an initialised NCCL group of more than one rank
+      ev_o, ev_qv = (overlap.events() if overlap is not None else (None, None))
       _lib.check(lib.lsh_layer_bwd(
           ctypes.byref(dims), ops._ptr(x_d), ops._ptr(w_q), ops._ptr(w_v), ops._ptr(w_o), ops._ptr(mask_d),
           ops._ptr(attn_keep), ops._ptr(buckets_d), buckets_d.stride(0), ops._ptr(g_d), ops._ptr(out_d), ops._ptr(dx), ops._ptr(dw_q),
-          ops._ptr(dw_v), ops._ptr(dw_o), ops._ptr(ws), ws.numel(), stream), 'lsh_layer_bwd')
+          ops._ptr(dw_v), ops._ptr(dw_o), ops._ptr(ws), ws.numel(),
+          ev_o.cuda_event if ev_o is not None and out_mult is None else None,
+          ev_qv.cuda_event if ev_qv is not None else None, stream), 'lsh_layer_bwd')
       if out_mult is not None:
         dw_o.mul_(out_mult)
-      if _GRAD_ALLREDUCE['on']:
-        from trax_b200 import dp
+      if overlap is not None:
+        # psum(grads) / n (trainer.py:197-199) on the communication stream, started by the events lsh_layer_bwd recorded
+        # when each gradient became final: dw_o travels under the attention-gradient kernels and the dw_q|dw_v / dx GEMMs,
+        # dw_q|dw_v under the dx GEMM.  (With output dropout dw_o is rescaled after the call, so it goes last.)
+        overlap.reduce(dw_flat, n_q + n_v, ev_o if out_mult is None else None, ev_qv)
+      elif _GRAD_ALLREDUCE['on']:
         dp.allreduce_mean_((dw_q, dw_v, dw_o))
       if host_io:
         dx, dw_q, dw_v, dw_o = (io.download(t, r) for t, r in ((dx, 'dx'), (dw_q, 'dw_q'), (dw_v, 'dw_v'), (dw_o, 'dw_o')))
