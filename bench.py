@@ -226,7 +226,7 @@ def run_ours(args, wl, name):
   os.dup2(2, 1)
   torch.cuda.set_device(local)
   dev = torch.device('cuda', local)
-  numa = _bind_to_gpu_numa_node(local) if world > 1 else None
+  numa = _bind_to_gpu_numa_node(local) if world > 1 and not os.environ.get('LSH_BENCH_NO_NUMA') else None
   if world > 1:
     os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
     if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
@@ -340,7 +340,8 @@ def run_ours(args, wl, name):
               vs_baseline=None, dtype='bf16' if dtype == torch.bfloat16 else 'f32 I/O, bf16 tensor-core operands',
               data='synthetic', config=_config(name, wl, world), clocks=clocks, e2e=e2e, gpu_launches=launches)
   if head_sharded and world > 1:
-    line['collective_bytes_per_step'] = 2 * B * L * D * x.element_size()   # out and dx, all-reduced once each
+    # out and dx, all-reduced once each per step (counted by the layer from the tensors it reduced)
+    line['collective_bytes_per_step'] = layer.comm_bytes // max(1, layer.n_calls // 2)
 
   if rank == 0:
     peaks = _peaks()

@@ -148,6 +148,7 @@ class HeadShardedLSHSelfAttention:
     self._rank = dist.get_rank(group) if dist.is_initialized() else 0
     head_range(n_heads, self._rank, self._world)
     self.comm_bytes = 0
+    self.n_calls = 0
 
   @property
   def local(self):
@@ -172,6 +173,7 @@ class HeadShardedLSHSelfAttention:
     on_host = not t.is_cuda and dist.get_backend(self._group) == 'nccl'
     d = t.cuda(non_blocking=True) if on_host else t
     self.comm_bytes += d.numel() * d.element_size()
+    self.n_calls += 1
     if self._reduce == 'all':
       dist.all_reduce(d, op=dist.ReduceOp.SUM, group=self._group)
     else:
