@@ -167,36 +167,67 @@ class HeadShardedLSHSelfAttention:
     self._local.weights, self._local.state = shard_heads(weights, state, self._n_heads, self._rank, self._world)
 
   def _head_sum(self, t):
-    """Sum of the per-rank partial results over the group (EA:2426 / EA:2430 across ranks)."""
+    """Sum of the per-rank partial results over the group (EA:2426 / EA:2430 across ranks), in place on the tensor's
+    device (NCCL reduces device memory, gloo host memory)."""
     if self._world == 1 or t is None:
       return t
-    on_host = not t.is_cuda and dist.get_backend(self._group) == 'nccl'
-    d = t.cuda(non_blocking=True) if on_host else t
-    self.comm_bytes += d.numel() * d.element_size()
+    self.comm_bytes += t.numel() * t.element_size()
     self.n_calls += 1
     if self._reduce == 'all':
-      dist.all_reduce(d, op=dist.ReduceOp.SUM, group=self._group)
-    else:
-      bsz, seqlen = d.shape[0], d.shape[1]
-      if seqlen % self._world != 0:
-        raise ValueError('seqlen %d not divisible by %d ranks' % (seqlen, self._world))
-      per = seqlen // self._world
-      mine = torch.empty((bsz, per) + tuple(d.shape[2:]), dtype=d.dtype, device=d.device)
-      chunks = [d[:, r * per:(r + 1) * per].contiguous() for r in range(self._world)]
-      dist.reduce_scatter(mine, chunks, op=dist.ReduceOp.SUM, group=self._group)
-      d = mine
-    return d.cpu() if on_host else d
+      dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self._group)
+      return t
+    bsz, seqlen = t.shape[0], t.shape[1]
+    if seqlen % self._world != 0:
+      raise ValueError('seqlen %d not divisible by %d ranks' % (seqlen, self._world))
+    per = seqlen // self._world
+    mine = torch.empty((bsz, per) + tuple(t.shape[2:]), dtype=t.dtype, device=t.device)
+    chunks = [t[:, r * per:(r + 1) * per].contiguous() for r in range(self._world)]
+    dist.reduce_scatter(mine, chunks, op=dist.ReduceOp.SUM, group=self._group)
+    return mine
+
+  # Host tensors with an NCCL group: upload once, run the local layer and the head sum on the device, download the SUM —
+  # never a partial result (the local layer's own host path would download its partial output first).
+  def _io(self, t):
+    if t is None or t.is_cuda or not (dist.is_initialized() and dist.get_backend(self._group) == 'nccl'):
+      return None
+    from trax_b200.lsh_attention import _HostIO
+    return _HostIO.get(torch.device('cuda', torch.cuda.current_device()))
 
   def forward(self, inputs):
-    return self._head_sum(self._local.forward(inputs))
+    x = inputs[0] if isinstance(inputs, (tuple, list)) else inputs
+    io = self._io(x)
+    if io is None:
+      return self._head_sum(self._local.forward(inputs))
+    x_d = io.upload(x).contiguous()
+    self._x_stash = (x, x._version, x_d)
+    dev_inputs = x_d if not isinstance(inputs, (tuple, list)) else (x_d,) + tuple(io.upload(t) for t in inputs[1:])
+    out = io.download(self._head_sum(self._local.forward(dev_inputs)))
+    io.finish()
+    return out
 
   def backward(self, inputs, output, grad, weights, state, new_state, rng=None, **kwargs):
+    x = inputs[0] if isinstance(inputs, (tuple, list)) else inputs
+    io = self._io(x)
+    if io is not None:
+      stash, self._x_stash = getattr(self, '_x_stash', None), None
+      x_d = stash[2] if stash is not None and stash[0] is x and stash[1] == x._version else io.upload(x).contiguous()
+      inputs = x_d if not isinstance(inputs, (tuple, list)) else (x_d,) + tuple(io.upload(t) for t in inputs[1:])
+      grad = io.upload(grad)
     dx, dw = self._local.backward(inputs, output, grad, weights, state, new_state, rng, **kwargs)
+    rest = ()
     if isinstance(dx, tuple):
-      return (self._head_sum(dx[0]),) + dx[1:], dw
-    return self._head_sum(dx), dw
+      dx, rest = dx[0], dx[1:]
+    dx = self._head_sum(dx)
+    if io is not None:
+      dx = io.download(dx, 'dx')
+      dw = tuple(io.download(g, 'dw%d' % i) for i, g in enumerate(dw))
+      io.finish()
+    return ((dx,) + rest if rest else dx), dw
 
   def forward_and_or_backward(self, inputs, weights, state, rng, output_grad=None, compute_output=True, update_state=True):
+    if self._io(inputs[0] if isinstance(inputs, (tuple, list)) else inputs) is not None:
+      raise NotImplementedError('HeadShardedLSHSelfAttention.forward_and_or_backward takes device tensors under NCCL '
+                                '(forward / backward accept host tensors)')
     out, new_state, dx, dw = self._local.forward_and_or_backward(inputs, weights, state, rng, output_grad=output_grad,
                                                                  compute_output=compute_output, update_state=update_state)
     if isinstance(dx, tuple):
