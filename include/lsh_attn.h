@@ -20,6 +20,7 @@
  *   x, out, dout, dx : (B, L, D)            act_dtype (f32 or bf16)
  *   w_q              : (H, D, dq) f32       w_v : (H, D, dv) f32       w_o : (H, dv, D) f32   (EA:1845-1868)
  *   wqv (packed)     : (D, H, dq+dv) bf16   — columns [h][0:dq]=w_q[h], [h][dq:dq+dv]=w_v[h]
+ *                      (dims.separate_k: (D, H, dq+dv+dq), columns [h][dq+dv:] = w_k[h]; likewise qv, dqv below)
  *   wo  (packed)     : (H*dv, D) bf16
  *   qv               : (B, L, H, dq+dv) bf16 — q then v of head h for token (b,t)
  *   rotations        : (B*H, dq, nh, R) f32 (EA:91, one draw per unit because the hash rng lives in
@@ -55,7 +56,12 @@ typedef struct LshAttnDims {
   int32_t factors[4];      /* even ints; n_buckets = prod(factors) (+1 when masked, EA:1908) */
   int32_t causal, masked;  /* bools */
   int32_t act_dtype;       /* LSH_DTYPE_* of x/out/dout/dx */
-  int32_t reserved[3];
+  int32_t separate_k;      /* 0: shared-QK (LSHSelfAttention; SelfAttention(share_qk=True)): keys are the length-normalised
+                            * queries, a token does not attend to itself (EA:229-231, 153-155).
+                            * 1: SelfAttention(share_qk=False) (EA:1133-1197): keys have their own projection w_k, are NOT
+                            * normalised (only divided by sqrt(d_qk), EA:232) and self-attention is allowed (EA:1175-1178);
+                            * every "qv" buffer then has dq+dv+dq columns per head: q | v | k.  n_hashes must be 1. */
+  int32_t reserved[2];
 } LshAttnDims;
 
 int lsh_attn_abi_version(void);
@@ -70,7 +76,8 @@ int lsh_attn_check_dims(const LshAttnDims *dims);
 /* ---- stage-level entry points ---------------------------------------------------------------- */
 
 /* Weight layout change + f32→bf16 (replaces nothing in EA; prepares operands for EA:1923-1924, 1995). */
-int lsh_pack_weights(const LshAttnDims *dims, const float *w_q, const float *w_v, const float *w_o,
+/* w_k (H, D, dq) f32: the key projection of SelfAttention(share_qk=False) (EA:1112-1128); NULL unless dims.separate_k. */
+int lsh_pack_weights(const LshAttnDims *dims, const float *w_q, const float *w_v, const float *w_o, const float *w_k,
                      void *wqv_bf16, void *wo_bf16, void *stream);
 
 /* EA:1923-1924  q = x·w_q ; v = x·w_v for every unit at once.  x_bf16 (B,L,D) bf16. */
@@ -162,7 +169,7 @@ size_t lsh_layer_workspace_bytes(const LshAttnDims *dims, int with_grad);
 /* compute_output=True.  update_state=True when `rotations` != NULL: buckets are computed and
  * written (EA:1926-1937); otherwise buckets are read (EA:1939-1941). */
 int lsh_layer_fwd(const LshAttnDims *dims, const void *x, const float *w_q, const float *w_v,
-                  const float *w_o, const float *rotations, const uint8_t *mask, const float *attn_keep,
+                  const float *w_o, const float *w_k, const float *rotations, const uint8_t *mask, const float *attn_keep,
                   int32_t *buckets, int64_t buckets_stride, void *out, void *ws, size_t ws_bytes, void *stream);
 
 /* output_grad given, update_state=False: recomputes the forward from the stored buckets, then the
@@ -176,9 +183,9 @@ int lsh_layer_fwd(const LshAttnDims *dims, const void *x, const float *w_q, cons
  * GEMM (dx) — so a data-parallel caller can start the gradient all-reduce (`psum`, trax/optimizers/trainer.py:197-199)
  * on its own communication stream underneath the rest of the call. */
 int lsh_layer_bwd(const LshAttnDims *dims, const void *x, const float *w_q, const float *w_v,
-                  const float *w_o, const uint8_t *mask, const float *attn_keep, const int32_t *buckets,
+                  const float *w_o, const float *w_k, const uint8_t *mask, const float *attn_keep, const int32_t *buckets,
                   int64_t buckets_stride, const void *dout, void *out, void *dx, float *dw_q,
-                  float *dw_v, float *dw_o, void *ws, size_t ws_bytes, void *ev_dwo_ready,
+                  float *dw_v, float *dw_o, float *dw_k, void *ws, size_t ws_bytes, void *ev_dwo_ready,
                   void *ev_dwqv_ready, void *stream);
 
 /* ---- helpers ---------------------------------------------------------------------------------- */

@@ -20,7 +20,7 @@ class LshAttnDims(ctypes.Structure):
       ('C', ctypes.c_int32), ('nb', ctypes.c_int32), ('na', ctypes.c_int32), ('nh', ctypes.c_int32),
       ('n_factors', ctypes.c_int32), ('factors', ctypes.c_int32 * 4),
       ('causal', ctypes.c_int32), ('masked', ctypes.c_int32),
-      ('act_dtype', ctypes.c_int32), ('reserved', ctypes.c_int32 * 3),
+      ('act_dtype', ctypes.c_int32), ('separate_k', ctypes.c_int32), ('reserved', ctypes.c_int32 * 2),
   ]
 
 
@@ -32,7 +32,7 @@ SIGNATURES = {
     'lsh_attn_source_hash': (ctypes.c_char_p, []),
     'lsh_attn_last_error': (ctypes.c_char_p, []),
     'lsh_attn_check_dims': (_I, [_D]),
-    'lsh_pack_weights': (_I, [_D, _P, _P, _P, _P, _P, _P]),
+    'lsh_pack_weights': (_I, [_D, _P, _P, _P, _P, _P, _P, _P]),
     'lsh_project_qv': (_I, [_D, _P, _P, _P, _P, _SZ, _P]),
     'lsh_hash': (_I, [_D, _P, _P, _P, _P, _I64, _P]),
     'lsh_hash_f32': (_I, [_D, _P, _P, _P, _P, _I64, _P]),
@@ -46,8 +46,8 @@ SIGNATURES = {
     'lsh_attend_bwd_workspace_bytes': (_SZ, [_D]),
     'lsh_attend_bwd': (_I, [_D, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     'lsh_layer_workspace_bytes': (_SZ, [_D, _I]),
-    'lsh_layer_fwd': (_I, [_D, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _SZ, _P]),
-    'lsh_layer_bwd': (_I, [_D, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _SZ, _P, _P, _P]),
+    'lsh_layer_fwd': (_I, [_D, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _SZ, _P]),
+    'lsh_layer_bwd': (_I, [_D, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P, _P, _P]),
     'lsh_make_rotations': (_I, [_D, _P, _P, _P, _P]),
     'lsh_layernorm_fwd': (_I, [_I64, _I, _I, _P, _P, _P, _P, _P, ctypes.c_float, _P]),
     'lsh_layernorm_bwd': (_I, [_I64, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
@@ -101,7 +101,7 @@ def check(rc, what=''):
     raise LshAttnError('%s: %s' % (what or 'lsh_attn', msg))
 
 
-def make_dims(B, H, L, D, dq, dv, C, nb, na, nh, factors, causal, masked, act_dtype):
+def make_dims(B, H, L, D, dq, dv, C, nb, na, nh, factors, causal, masked, act_dtype, separate_k=False):
   d = LshAttnDims()
   d.B, d.H, d.L, d.D, d.dq, d.dv = B, H, L, D, dq, dv
   d.C, d.nb, d.na, d.nh = C, nb, na, nh
@@ -111,4 +111,5 @@ def make_dims(B, H, L, D, dq, dv, C, nb, na, nh, factors, causal, masked, act_dt
   for i, f in enumerate(factors):
     d.factors[i] = int(f)
   d.causal, d.masked, d.act_dtype = int(bool(causal)), int(bool(masked)), act_dtype
+  d.separate_k = int(bool(separate_k))
   return d

@@ -45,9 +45,9 @@ size_t attend_bwd_workspace_bytes(const LshAttnDims &);
 int attend_bwd_run(const LshAttnDims &, const void *, const int32_t *, const uint8_t *, const void *, const float *,
                    const void *, const float *, const int32_t *, const int32_t *, const AttnKeep *, void *, void *, size_t,
                    cudaStream_t);
-int pack_weights_run(const LshAttnDims &, const float *, const float *, const float *, void *, void *, cudaStream_t);
+int pack_weights_run(const LshAttnDims &, const float *, const float *, const float *, const float *, void *, void *, cudaStream_t);
 int f32_to_bf16_run(const float *, void *, int64_t, cudaStream_t);
-int unpack_dwqv_run(const LshAttnDims &, const float *, float *, float *, cudaStream_t);
+int unpack_dwqv_run(const LshAttnDims &, const float *, float *, float *, float *, cudaStream_t);
 int make_rotations_run(const LshAttnDims &, const uint32_t *, uint32_t *, float *, cudaStream_t);
 int layernorm_fwd_run(int64_t, int, int, const void *, const float *, const float *, void *, float2 *, float, cudaStream_t);
 int layernorm_bwd_run(int64_t, int, int, const void *, const void *, const void *, const float2 *, const float *, void *, float *,
@@ -77,6 +77,7 @@ static int check_dims(const LshAttnDims *dp, bool need_bwd) {
     if (d.factors[i] < 2 || (d.factors[i] & 1)) return set_error("hash factor %d must be even (EA:80, 87)", d.factors[i]);
   if (d.D % 8 != 0) return set_error("d_model=%d must be a multiple of 8", d.D);
   if (d.act_dtype != LSH_DTYPE_F32 && d.act_dtype != LSH_DTYPE_BF16) return set_error("bad act_dtype");
+  if (d.separate_k && d.nh != 1) return set_error("separate_k (SelfAttention(share_qk=False)) has no hashing: n_hashes must be 1");
   // int32 sort key of EA:1947 must not wrap: max key = L*(nh*n_buckets - 1) + L - 1
   const int64_t maxkey = static_cast<int64_t>(d.L) * d.nh * dr.n_buckets - 1;
   if (maxkey >= (1ll << 31))
@@ -201,7 +202,7 @@ static LayerWs carve(const LshAttnDims &d, void *ws, bool with_grad) {
 
 // Forward up to o_comb (EA:1923-1992 for all units).  Returns xb (bf16 view of x).
 static int forward_core(const LshAttnDims &d, const LayerWs &w, const void *x, const float *w_q, const float *w_v,
-                        const float *w_o, const float *rotations, const uint8_t *mask, const AttnKeep *keep, int32_t *buckets,
+                        const float *w_o, const float *w_k, const float *rotations, const uint8_t *mask, const AttnKeep *keep, int32_t *buckets,
                         int64_t bstride, bool need_lse_tot, const void **xb_out, cudaStream_t s, bool weights_packed = false) {
   Derived dr = derive(d);
   const int64_t BL = static_cast<int64_t>(d.B) * d.L;
@@ -212,7 +213,7 @@ static int forward_core(const LshAttnDims &d, const LayerWs &w, const void *x, c
     xb = w.xb;
   }
   *xb_out = xb;
-  if (!weights_packed && (rc = pack_weights_run(d, w_q, w_v, w_o, w.wqv, w.wo, s))) return rc;
+  if (!weights_packed && (rc = pack_weights_run(d, w_q, w_v, w_o, w_k, w.wqv, w.wo, s))) return rc;
   const int64_t NQV = static_cast<int64_t>(d.H) * dr.QV;
   if ((rc = gemm_rm(false, false, BL, NQV, d.D, xb, d.D, w.wqv, NQV, w.qv, NQV, false, w.cublas, s))) return rc;
   bool scales_done = false;
@@ -260,17 +261,17 @@ int64_t lsh_attn_launch_count(int reset) {
 
 int lsh_attn_check_dims(const LshAttnDims *dims) { return check_dims(dims, false); }
 
-int lsh_pack_weights(const LshAttnDims *dims, const float *w_q, const float *w_v, const float *w_o, void *wqv,
-                     void *wo, void *stream) {
+int lsh_pack_weights(const LshAttnDims *dims, const float *w_q, const float *w_v, const float *w_o, const float *w_k,
+                     void *wqv, void *wo, void *stream) {
   if (int rc = check_dims(dims, false)) return rc;
-  return pack_weights_run(*dims, w_q, w_v, w_o, wqv, wo, static_cast<cudaStream_t>(stream));
+  return pack_weights_run(*dims, w_q, w_v, w_o, w_k, wqv, wo, static_cast<cudaStream_t>(stream));
 }
 
 int lsh_project_qv(const LshAttnDims *dims, const void *x_bf16, const void *wqv, void *qv, void *ws, size_t ws_bytes,
                    void *stream) {
   if (int rc = check_dims(dims, false)) return rc;
   const LshAttnDims &d = *dims;
-  const int64_t BL = static_cast<int64_t>(d.B) * d.L, NQV = static_cast<int64_t>(d.H) * (d.dq + d.dv);
+  const int64_t BL = static_cast<int64_t>(d.B) * d.L, NQV = static_cast<int64_t>(d.H) * derive(d).QV;
   return gemm_rm(false, false, BL, NQV, d.D, x_bf16, d.D, wqv, NQV, qv, NQV, false,
                  ws_bytes >= kCublasWs ? ws : nullptr, static_cast<cudaStream_t>(stream));
 }
@@ -357,18 +358,19 @@ size_t lsh_layer_workspace_bytes(const LshAttnDims *dims, int with_grad) {
 }
 
 int lsh_layer_fwd(const LshAttnDims *dims, const void *x, const float *w_q, const float *w_v, const float *w_o,
-                  const float *rotations, const uint8_t *mask, const float *attn_keep, int32_t *buckets,
+                  const float *w_k, const float *rotations, const uint8_t *mask, const float *attn_keep, int32_t *buckets,
                   int64_t buckets_stride, void *out, void *ws, size_t ws_bytes, void *stream) {
   if (int rc = check_dims(dims, false)) return rc;
   const LshAttnDims &d = *dims;
   if (!x || !w_q || !w_v || !w_o || !buckets || !out || !ws) return set_error("lsh_layer_fwd: NULL argument");
+  if ((d.separate_k != 0) != (w_k != nullptr)) return set_error("lsh_layer_fwd: w_k must be given exactly when dims.separate_k is set");
   LayerWs w = carve(d, ws, false);
   if (ws_bytes < w.total) return set_error("lsh_layer_fwd: workspace too small (%zu < %zu)", ws_bytes, w.total);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const void *xb;
   AttnKeep keep;
   if (int rc = attn_keep_prepare(d, attn_keep, w.keep_ws, &keep, s)) return rc;
-  if (int rc = forward_core(d, w, x, w_q, w_v, w_o, rotations, mask, attn_keep ? &keep : nullptr, buckets, buckets_stride, false,
+  if (int rc = forward_core(d, w, x, w_q, w_v, w_o, w_k, rotations, mask, attn_keep ? &keep : nullptr, buckets, buckets_stride, false,
                             &xb, s))
     return rc;
   const int64_t BL = static_cast<int64_t>(d.B) * d.L, KO = static_cast<int64_t>(d.H) * d.dv;
@@ -376,13 +378,15 @@ int lsh_layer_fwd(const LshAttnDims *dims, const void *x, const float *w_q, cons
 }
 
 int lsh_layer_bwd(const LshAttnDims *dims, const void *x, const float *w_q, const float *w_v, const float *w_o,
-                  const uint8_t *mask, const float *attn_keep, const int32_t *buckets, int64_t buckets_stride,
-                  const void *dout, void *out, void *dx, float *dw_q, float *dw_v, float *dw_o, void *ws, size_t ws_bytes,
+                  const float *w_k, const uint8_t *mask, const float *attn_keep, const int32_t *buckets, int64_t buckets_stride,
+                  const void *dout, void *out, void *dx, float *dw_q, float *dw_v, float *dw_o, float *dw_k, void *ws, size_t ws_bytes,
                   void *ev_dwo_ready, void *ev_dwqv_ready, void *stream) {
   if (int rc = check_dims(dims, true)) return rc;
   const LshAttnDims &d = *dims;
   if (!x || !w_q || !w_v || !w_o || !buckets || !dout || !dx || !dw_q || !dw_v || !dw_o || !ws)
     return set_error("lsh_layer_bwd: NULL argument");
+  if ((d.separate_k != 0) != (w_k != nullptr) || (d.separate_k != 0) != (dw_k != nullptr))
+    return set_error("lsh_layer_bwd: w_k / dw_k must be given exactly when dims.separate_k is set");
   Derived dr = derive(d);
   LayerWs w = carve(d, ws, true);
   if (ws_bytes < w.total) return set_error("lsh_layer_bwd: workspace too small (%zu < %zu)", ws_bytes, w.total);
@@ -393,7 +397,7 @@ int lsh_layer_bwd(const LshAttnDims *dims, const void *x, const float *w_q, cons
   const int64_t NQV = static_cast<int64_t>(d.H) * dr.QV;
   const bool f32 = d.act_dtype == LSH_DTYPE_F32;
   // B1 (first half) on the side stream: do = dout·w_o^T
-  if ((rc = pack_weights_run(d, w_q, w_v, w_o, w.wqv, w.wo, s))) return rc;
+  if ((rc = pack_weights_run(d, w_q, w_v, w_o, w_k, w.wqv, w.wo, s))) return rc;
   SideStream *side = side_stream();
   if (!side) return set_error("lsh_layer_bwd: could not create the internal stream");
   LSH_CUDA_OK(cudaEventRecord(side->fork, s));
@@ -409,7 +413,7 @@ int lsh_layer_bwd(const LshAttnDims *dims, const void *x, const float *w_q, cons
   AttnKeep keep;
   if ((rc = attn_keep_prepare(d, attn_keep, w.keep_ws, &keep, s))) return rc;
   const AttnKeep *kp = attn_keep ? &keep : nullptr;
-  if ((rc = forward_core(d, w, x, w_q, w_v, w_o, nullptr, mask, kp, const_cast<int32_t *>(buckets), buckets_stride, true,
+  if ((rc = forward_core(d, w, x, w_q, w_v, w_o, w_k, nullptr, mask, kp, const_cast<int32_t *>(buckets), buckets_stride, true,
                          &xb, s, /*weights_packed=*/true)))
     return rc;
   if (out) {
@@ -424,7 +428,7 @@ int lsh_layer_bwd(const LshAttnDims *dims, const void *x, const float *w_q, cons
     return rc;
   // B7: dW_q|dW_v = x^T·dqv ; dx = dqv·wqv^T
   if ((rc = gemm_rm(true, false, d.D, NQV, BL, xb, d.D, w.dqv, NQV, w.dwqv, NQV, true, w.cublas, s))) return rc;
-  if ((rc = unpack_dwqv_run(d, w.dwqv, dw_q, dw_v, s))) return rc;
+  if ((rc = unpack_dwqv_run(d, w.dwqv, dw_q, dw_v, dw_k, s))) return rc;
   if (ev_dwqv_ready) LSH_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(ev_dwqv_ready), s));
   return gemm_rm(false, true, BL, d.D, NQV, w.dqv, NQV, w.wqv, NQV, dx, d.D, f32, w.cublas, s);
 }

@@ -34,6 +34,7 @@ struct AttendBwdParams {
   const uint32_t *keep_bits_t;   // attention dropout: (W, C / 32) bit rows by window column (null = none), see AttnKeep
   const float *keep_scale;
   int L, H, N, n_chunks, nb, nwin, causal, masked;
+  int row, ksep;                 // see AttendFwdParams
 };
 
 constexpr int QB = 64;   // queries per sub-block
@@ -78,7 +79,8 @@ __global__ void __launch_bounds__(2 * C, 1) attend_bwd_kernel(const AttendBwdPar
   __syncthreads();
   for (int i = tid; i < C * 16; i += NT) {
     const int j = i >> 4, ch = i & 15;
-    const __nv_bfloat16 *src = p.qv + ((static_cast<int64_t>(b) * p.L + kpos[j]) * p.H + h) * 128 + ch * 8;
+    // key rows: the q columns (shared-QK) or the k columns (separate keys); value rows: the v columns
+    const __nv_bfloat16 *src = p.qv + ((static_cast<int64_t>(b) * p.L + kpos[j]) * p.H + h) * p.row + ch * 8 + ((p.ksep && ch < 8) ? 128 : 0);
     cp_async16((ch < 8) ? ks_base + swz(j, ch) : vs_base + swz(j, ch - 8), src);
   }
   cp_async_commit();
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(2 * C, 1) attend_bwd_kernel(const AttendBwdPar
     ss += __shfl_xor_sync(0xffffffffu, ss, 1);
     ss += __shfl_xor_sync(0xffffffffu, ss, 2);
     ss += __shfl_xor_sync(0xffffffffu, ss, 4);
-    if (ch == 0) rnorm[j] = sqrtf(ss * (1.0f / 64) + 1e-6f);
+    if (ch == 0) rnorm[j] = p.ksep ? 1.f : sqrtf(ss * (1.0f / 64) + 1e-6f);   // separate keys are not normalised (EA:229-232)
   }
   __syncthreads();
 
@@ -137,7 +139,7 @@ __global__ void __launch_bounds__(2 * C, 1) attend_bwd_kernel(const AttendBwdPar
       for (int i = tid; i < QB * 16; i += NT) {
         const int j = i >> 4, ch = i & 15;
         const int64_t tokrow = (static_cast<int64_t>(b) * p.L + qpos[j]) * p.H + h;
-        if (ch < 8) cp_async16(qs_base + swz(j, ch), p.qv + tokrow * 128 + ch * 8);
+        if (ch < 8) cp_async16(qs_base + swz(j, ch), p.qv + tokrow * p.row + ch * 8);
         else cp_async16(ds_base + swz(j, ch - 8), p.do_comb + tokrow * 64 + (ch - 8) * 8);
       }
       cp_async_commit();
@@ -183,7 +185,7 @@ __global__ void __launch_bounds__(2 * C, 1) attend_bwd_kernel(const AttendBwdPar
           const float ki = (e < 2) ? ki0 : ki1;
           float v = s[nt][e] * ((e < 2) ? ksc0 : ksc1);
           if (p.causal && qi < ki) v = v - 1e9f;
-          if (qi == ki) v = v - 1e5f;
+          if (!p.ksep && qi == ki) v = v - 1e5f;           // exclude_self = share_qk (EA:1175-1178)
           if (p.masked && ki < 0.f) v = v - 1e9f;
           const float pt = exp2f((v - qlse[col]) * kLog2e);
           const float mk = (((e < 2 ? kw0 : kw1) >> (e & 1)) & 1u) ? kscale_m : 0.f;
@@ -265,7 +267,8 @@ __global__ void __launch_bounds__(2 * C, 1) attend_bwd_kernel(const AttendBwdPar
     const float rr0 = rnorm[r0], rr1 = rnorm[r1];
     // dq_key = dk^/(r*sqrt(dq)) - q * (dk^·q) / (dq * r^3 * sqrt(dq)),  dq = 64
     const float a0 = 0.125f / rr0, a1 = 0.125f / rr1;
-    const float c0 = dot0 * 0.125f / (64.f * rr0 * rr0 * rr0), c1 = dot1 * 0.125f / (64.f * rr1 * rr1 * rr1);
+    // (separate keys: k = x w_k / sqrt(dq) only, so the key-side cotangent is dk^ / sqrt(dq) — no normalisation term)
+    const float c0 = p.ksep ? 0.f : dot0 * 0.125f / (64.f * rr0 * rr0 * rr0), c1 = p.ksep ? 0.f : dot1 * 0.125f / (64.f * rr1 * rr1 * rr1);
     __nv_bfloat16 *oq = p.dq_part + static_cast<int64_t>(p.nwin) * p.kind_stride + static_cast<int64_t>(u) * p.N * 64;
     __nv_bfloat16 *ov = p.dv_part + static_cast<int64_t>(u) * p.N * 64;
     const int64_t t0 = ktk[r0], t1 = ktk[r1];
@@ -337,7 +340,7 @@ int attend_bwd_run(const LshAttnDims &d, const void *qv, const int32_t *sticker,
   // tcgen05 path for the long-sequence shape; LSH_ATTN_BWD=mma forces the mma.sync path
   static const bool force_mma = [] { const char *e = getenv("LSH_ATTN_BWD"); return e && strcmp(e, "mma") == 0; }();
   const bool dropout = keep && keep->bits_t;   // the tcgen05 backward works on position-sorted tiles; the keep matrix is in slot order
-  if (d.C == 128 && d.nb == 1 && d.na == 0 && d.causal && !d.masked && d.L % 128 == 0 && !force_mma && !dropout) {
+  if (d.C == 128 && d.nb == 1 && d.na == 0 && d.causal && !d.masked && d.L % 128 == 0 && !force_mma && !dropout && !d.separate_k) {
     const float *qscale = qscale_in;
     const bool prep = g_bwd_parts & 1;
     if (!qscale) {
@@ -368,6 +371,7 @@ int attend_bwd_run(const LshAttnDims &d, const void *qv, const int32_t *sticker,
   p.dq_part = dq_part; p.dv_part = dv_part; p.kind_stride = static_cast<int64_t>(rows) * 64;
   p.L = d.L; p.H = d.H; p.N = dr.N; p.n_chunks = dr.n_chunks; p.nb = d.nb; p.nwin = dr.nwin;
   p.causal = d.causal; p.masked = d.masked;
+  p.row = dr.QV; p.ksep = d.separate_k ? 1 : 0;
   p.keep_bits_t = dropout ? keep->bits_t : nullptr; p.keep_scale = dropout ? keep->scale : nullptr;
   if (g_bwd_parts & 2) switch (d.C) {
     case 64: rc = launch_attend_bwd<64>(p, dr.BH, stream); break;

@@ -19,7 +19,7 @@ template <int C>
 __global__ void __launch_bounds__(2 * C) attend_fwd_kernel(const AttendFwdParams p) {
   constexpr int NT = 2 * C;            // threads
   constexpr int D = 64;                // dq == dv == 64
-  constexpr int QVROW = 128;           // elements per (token, head) row of qv
+  const int QVROW = p.row;             // elements per (token, head) row of qv: q | v (| k)
   extern __shared__ __align__(1024) uint8_t smem[];
   const int W = C * p.nwin;
   uint8_t *Ks = smem;                                  // [W][64] bf16 swizzled (raw q rows: queries AND keys)
@@ -28,6 +28,7 @@ __global__ void __launch_bounds__(2 * C) attend_fwd_kernel(const AttendFwdParams
   int *spos = kinfo + W;                               // [W] 0-based positions
   int *tkq = spos + W;                                 // [C] ticker of the query rows
   float *kscale = reinterpret_cast<float *>(tkq + C);  // [W] 1 / (sqrt(mean(q^2)+eps) * sqrt(dq)) per key row
+  uint8_t *Qs = reinterpret_cast<uint8_t *>(kscale + W);   // [C][64] bf16 swizzled: the chunk's queries (separate keys only)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int u = blockIdx.x / p.n_chunks, c = blockIdx.x % p.n_chunks;
@@ -54,10 +55,18 @@ __global__ void __launch_bounds__(2 * C) attend_fwd_kernel(const AttendFwdParams
     const uint32_t ks_base = smem_u32(Ks), vs_base = smem_u32(Vs);
     for (int i = tid; i < W * 16; i += NT) {
       const int j = i >> 4, ch = i & 15;
+      // shared-QK: the q half is query AND key; separate keys (EA:1160-1162): the key tile comes from the k columns
       const __nv_bfloat16 *src =
-          p.qv + ((static_cast<int64_t>(b) * p.L + spos[j]) * p.H + h) * QVROW + ch * 8;
+          p.qv + ((static_cast<int64_t>(b) * p.L + spos[j]) * p.H + h) * QVROW + ch * 8 + ((p.ksep && ch < 8) ? 128 : 0);
       const uint32_t dst = (ch < 8) ? ks_base + swz(j, ch) : vs_base + swz(j, ch - 8);
       cp_async16(dst, src);
+    }
+    if (p.ksep) {
+      const uint32_t qs_base = smem_u32(Qs);
+      for (int i = tid; i < C * 8; i += NT) {
+        const int j = i >> 3, ch = i & 7;
+        cp_async16(qs_base + swz(j, ch), p.qv + ((static_cast<int64_t>(b) * p.L + spos[p.nb * C + j]) * p.H + h) * QVROW + ch * 8);
+      }
     }
     cp_async_commit();
     cp_async_wait<0>();
@@ -68,12 +77,12 @@ __global__ void __launch_bounds__(2 * C) attend_fwd_kernel(const AttendFwdParams
   const int qrow0 = p.nb * C + warp * 16;
   uint32_t qa[4][4];
   {
-    const uint32_t ks_base = smem_u32(Ks);
+    const uint32_t q_base = p.ksep ? smem_u32(Qs) : smem_u32(Ks);
     const int mi = lane >> 3;
-    const int row = qrow0 + (lane & 7) + 8 * (mi & 1);
+    const int row = (p.ksep ? warp * 16 : qrow0) + (lane & 7) + 8 * (mi & 1);
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks)
-      ldmatrix_x4(ks_base + swz(row, ks * 2 + (mi >> 1)), qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
+      ldmatrix_x4(q_base + swz(row, ks * 2 + (mi >> 1)), qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
   }
 
   // ---- keys: k = q / sqrt(mean(q^2) + 1e-6) / sqrt(dq)  (EA:54-57, 229-231) -------------------------
@@ -88,7 +97,8 @@ __global__ void __launch_bounds__(2 * C) attend_fwd_kernel(const AttendFwdParams
     ss += __shfl_xor_sync(0xffffffffu, ss, 1);
     ss += __shfl_xor_sync(0xffffffffu, ss, 2);
     ss += __shfl_xor_sync(0xffffffffu, ss, 4);
-    if (ch == 0) kscale[j] = 0.125f / sqrtf(ss * (1.0f / D) + 1e-6f);   // 1/sqrt(64) = 0.125
+    // separate keys are not length-normalised (EA:229-231 apply to shared-QK only), just divided by sqrt(dq) (EA:232)
+    if (ch == 0) kscale[j] = p.ksep ? 0.125f : 0.125f / sqrtf(ss * (1.0f / D) + 1e-6f);   // 1/sqrt(64) = 0.125
   }
   __syncthreads();
 
@@ -132,7 +142,7 @@ __global__ void __launch_bounds__(2 * C) attend_fwd_kernel(const AttendFwdParams
         const float qi = (e < 2) ? qi0 : qi1;
         float v = s[nt][e] * kscale[col];
         if (p.causal && qi < ki) v = v - 1e9f;
-        if (qi == ki) v = v - 1e5f;
+        if (!p.ksep && qi == ki) v = v - 1e5f;             // exclude_self = share_qk (EA:1175-1178)
         if (p.masked && ki < 0.f) v = v - 1e9f;
         s[nt][e] = v;
         if (e < 2) mx0 = fmaxf(mx0, v); else mx1 = fmaxf(mx1, v);
@@ -210,7 +220,7 @@ __global__ void __launch_bounds__(2 * C) attend_fwd_kernel(const AttendFwdParams
 template <int C>
 static int launch_attend_fwd(const AttendFwdParams &p, int BH, cudaStream_t stream) {
   const int W = C * p.nwin;
-  size_t smem = static_cast<size_t>(W) * 256 + static_cast<size_t>(W) * 12 + C * 4;
+  size_t smem = static_cast<size_t>(W) * 256 + static_cast<size_t>(W) * 12 + C * 4 + (p.ksep ? C * 128 : 0);
   if (smem > 227 * 1024) return set_error("attend_fwd: window of %d keys needs %zu B shared memory", W, smem);
   LSH_OPT_IN_SMEM(attend_fwd_kernel<C>);
   attend_fwd_kernel<C><<<BH * p.n_chunks, 2 * C, smem, stream>>>(p);
@@ -225,7 +235,9 @@ static bool force_mma_fwd() {
 // tcgen05 path for the long-sequence shape (chunk 128, 2-chunk window); LSH_ATTN_FWD=mma forces the mma.sync path
 // (L % 128 == 0: every chunk lies inside one hash round, so positions inside a tile are unique — the position-sorted
 // interval masks rely on that; other lengths take the mma.sync path)
-bool attend_fwd_uses_tc(const LshAttnDims &d) { return d.C == 128 && 1 + d.nb + d.na == 2 && d.L % 128 == 0 && !force_mma_fwd(); }
+bool attend_fwd_uses_tc(const LshAttnDims &d) {
+  return d.C == 128 && 1 + d.nb + d.na == 2 && d.L % 128 == 0 && !d.separate_k && !force_mma_fwd();
+}
 
 bool attend_fwd_tc_uses_bounds();
 bool attend_bwd_tc_uses_bounds();
@@ -258,7 +270,8 @@ FwdAux fwd_aux_carve(const LshAttnDims &d, void *ws) {
 int fwd_aux_prepare(const LshAttnDims &d, const void *qv, const int32_t *sticker, const FwdAux &aux, cudaStream_t stream,
                     bool scales_done) {
   const bool tc = attend_fwd_uses_tc(d);
-  if (!scales_done) {     // (a forward call that hashes gets them from the hash kernel, which already holds q)
+  if (!scales_done && !d.separate_k) {     // (a forward call that hashes gets them from the hash kernel, which already holds q;
+                                           //  separate keys are not normalised: no per-token scales at all)
     if (int rc = qscale_run(d, qv, aux.qscale, tc ? aux.rowmeta : nullptr, tc ? aux.qhat : nullptr, stream)) return rc;
   }
   if (tc && sticker) return chunk_possort_run(d, sticker, aux.sticker2, attend_tc_uses_bounds() ? aux.bounds : nullptr, stream);
@@ -282,6 +295,7 @@ int attend_fwd_run(const LshAttnDims &d, const void *qv, const int32_t *sticker,
   p.keep_bits = keep ? keep->bits : nullptr; p.keep_scale = keep ? keep->scale : nullptr;
   p.L = d.L; p.H = d.H; p.N = dr.N; p.n_chunks = dr.n_chunks; p.nb = d.nb; p.nwin = dr.nwin;
   p.causal = d.causal; p.masked = d.masked;
+  p.row = dr.QV; p.ksep = d.separate_k ? 1 : 0;
   if (d.masked && !mask) return set_error("attend_fwd: dims.masked set but mask == NULL");
   if (attend_fwd_uses_tc(d)) {
     if (!aux) return set_error("attend_fwd: the tcgen05 path needs the auxiliary workspace");

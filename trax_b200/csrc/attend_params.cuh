@@ -21,6 +21,8 @@ struct AttendFwdParams {
   int *redo;                    // tcgen05 path: [0] = number of queued rows, [2 + 2 i], [3 + 2 i] = {unit * n_chunks + chunk, ticker}
   long long *trace;             // debug: per-phase clock64 stamps of CTA 0 (null = off)
   int L, H, N, n_chunks, nb, nwin, causal, masked;
+  int row;                      // elements per (token, head) row of qv: 128 (q | v) or 192 (q | v | k, separate keys)
+  int ksep;                     // separate, un-normalised keys, self-attention allowed (SelfAttention(share_qk=False), EA:1133-1197)
 };
 
 int attend_fwd_tc_run(const AttendFwdParams &p, int BH, cudaStream_t stream);

@@ -247,7 +247,7 @@ int qscale_run(const LshAttnDims &d, const void *qv, float *qscale, float2 *rowm
 __global__ void __launch_bounds__(ROW_THREADS) sum_rounds_kernel(
     const __nv_bfloat16 *__restrict__ dq_part, const __nv_bfloat16 *__restrict__ dv_part,
     __nv_bfloat16 *__restrict__ dqv, int L, int H, int nh, int n_kinds, int64_t kind_stride,
-    int64_t total_rows) {
+    int64_t total_rows, int row_elems, int ksep) {
   const int64_t row = (static_cast<int64_t>(blockIdx.x) * ROW_THREADS + threadIdx.x) >> 3;   // (u, t)
   const int ch = threadIdx.x & 7;
   if (row >= total_rows) return;
@@ -255,6 +255,7 @@ __global__ void __launch_bounds__(ROW_THREADS) sum_rounds_kernel(
   const int t = static_cast<int>(row - u * L);
   const int64_t b = static_cast<uint32_t>(u) / static_cast<uint32_t>(H), h = u - b * H;
   float aq[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, av[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float ak[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // separate keys: the key-side kind is the cotangent of k, not of q
   if (n_kinds == 1 && nh <= 8) {
     // tcgen05 path: one dq and one dv row per round — all 2 * nh loads of the token in flight at once
     uint4 vq[8], vv[8];
@@ -284,17 +285,23 @@ __global__ void __launch_bounds__(ROW_THREADS) sum_rounds_kernel(
       float f[8];
       for (int k = 0; k < n_kinds; ++k) {
         bf16x8_to_f32(__ldg(reinterpret_cast<const uint4 *>(dq_part + k * kind_stride + off) + ch), f);
+        if (ksep && k == n_kinds - 1) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) aq[i] += f[i];
+          for (int i = 0; i < 8; ++i) ak[i] += f[i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) aq[i] += f[i];
+        }
       }
       bf16x8_to_f32(__ldg(reinterpret_cast<const uint4 *>(dv_part + off) + ch), f);
 #pragma unroll
       for (int i = 0; i < 8; ++i) av[i] += f[i];
     }
   }
-  __nv_bfloat16 *dst = dqv + ((b * L + t) * H + h) * 128;
+  __nv_bfloat16 *dst = dqv + ((b * L + t) * H + h) * row_elems;
   *(reinterpret_cast<uint4 *>(dst) + ch) = f32_to_bf16x8(aq);
   *(reinterpret_cast<uint4 *>(dst + 64) + ch) = f32_to_bf16x8(av);
+  if (ksep) *(reinterpret_cast<uint4 *>(dst + 128) + ch) = f32_to_bf16x8(ak);
 }
 
 int sum_rounds_run(const LshAttnDims &d, const void *dq_part, const void *dv_part, void *dqv,
@@ -305,7 +312,7 @@ int sum_rounds_run(const LshAttnDims &d, const void *dq_part, const void *dv_par
   sum_rounds_kernel<<<static_cast<unsigned>(blocks), ROW_THREADS, 0, stream>>>(
       static_cast<const __nv_bfloat16 *>(dq_part), static_cast<const __nv_bfloat16 *>(dv_part),
       static_cast<__nv_bfloat16 *>(dqv), d.L, d.H, d.nh, n_kinds,
-      static_cast<int64_t>(dr.BH) * dr.N * 64, rows);
+      static_cast<int64_t>(dr.BH) * dr.N * 64, rows, dr.QV, d.separate_k ? 1 : 0);
   LSH_CHECK_LAUNCH("sum_rounds_kernel");
   return 0;
 }

@@ -23,7 +23,7 @@ inline Derived derive(const LshAttnDims &d) {
   r.n_chunks = d.C > 0 ? r.N / d.C : 0;
   r.nwin = 1 + d.nb + d.na;
   r.W = d.C * r.nwin;
-  r.QV = d.dq + d.dv;
+  r.QV = d.dq + d.dv + (d.separate_k ? d.dq : 0);   // q | v (| k): columns of one (token, head) row
   r.R = 0;
   r.n_buckets = 1;
   for (int i = 0; i < d.n_factors && i < 4; ++i) {

@@ -3,10 +3,10 @@
 
 namespace lsh {
 
-// w_q (H, D, dq) f32, w_v (H, D, dv) f32 -> wqv (D, H, dq+dv) bf16 ; w_o (H, dv, D) f32 -> bf16 same layout
-__global__ void pack_wqv_kernel(const float *__restrict__ w_q, const float *__restrict__ w_v,
+// w_q (H, D, dq) f32, w_v (H, D, dv) f32 [, w_k (H, D, dq)] -> wqv (D, H, dq+dv[+dq]) bf16 ; w_o (H, dv, D) f32 -> bf16 same layout
+__global__ void pack_wqv_kernel(const float *__restrict__ w_q, const float *__restrict__ w_v, const float *__restrict__ w_k,
                                 __nv_bfloat16 *__restrict__ wqv, int H, int D, int dq, int dv) {
-  const int QV = dq + dv;
+  const int QV = dq + dv + (w_k ? dq : 0);
   const int64_t n = static_cast<int64_t>(D) * H * QV;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -14,7 +14,8 @@ __global__ void pack_wqv_kernel(const float *__restrict__ w_q, const float *__re
     const int h = static_cast<int>((i / QV) % H);
     const int dm = static_cast<int>(i / (static_cast<int64_t>(QV) * H));
     const float v = (c < dq) ? w_q[(static_cast<int64_t>(h) * D + dm) * dq + c]
-                             : w_v[(static_cast<int64_t>(h) * D + dm) * dv + (c - dq)];
+                    : (c < dq + dv) ? w_v[(static_cast<int64_t>(h) * D + dm) * dv + (c - dq)]
+                                    : w_k[(static_cast<int64_t>(h) * D + dm) * dq + (c - dq - dv)];
     wqv[i] = __float2bfloat16_rn(v);
   }
 }
@@ -32,10 +33,10 @@ __global__ void f32_to_bf16_kernel(const float *__restrict__ src, __nv_bfloat16 
     dst[i] = __float2bfloat16_rn(src[i]);
 }
 
-// dwqv (D, H, dq+dv) f32 -> dw_q (H, D, dq), dw_v (H, D, dv) f32
+// dwqv (D, H, dq+dv[+dq]) f32 -> dw_q (H, D, dq), dw_v (H, D, dv) [, dw_k (H, D, dq)] f32
 __global__ void unpack_dwqv_kernel(const float *__restrict__ dwqv, float *__restrict__ dw_q,
-                                   float *__restrict__ dw_v, int H, int D, int dq, int dv) {
-  const int QV = dq + dv;
+                                   float *__restrict__ dw_v, float *__restrict__ dw_k, int H, int D, int dq, int dv) {
+  const int QV = dq + dv + (dw_k ? dq : 0);
   const int64_t n = static_cast<int64_t>(D) * H * QV;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -43,7 +44,8 @@ __global__ void unpack_dwqv_kernel(const float *__restrict__ dwqv, float *__rest
     const int h = static_cast<int>((i / QV) % H);
     const int dm = static_cast<int>(i / (static_cast<int64_t>(QV) * H));
     if (c < dq) dw_q[(static_cast<int64_t>(h) * D + dm) * dq + c] = dwqv[i];
-    else dw_v[(static_cast<int64_t>(h) * D + dm) * dv + (c - dq)] = dwqv[i];
+    else if (c < dq + dv) dw_v[(static_cast<int64_t>(h) * D + dm) * dv + (c - dq)] = dwqv[i];
+    else dw_k[(static_cast<int64_t>(h) * D + dm) * dq + (c - dq - dv)] = dwqv[i];
   }
 }
 
@@ -105,10 +107,11 @@ static unsigned grid_for(int64_t n, int threads) {
   return static_cast<unsigned>(b);
 }
 
-int pack_weights_run(const LshAttnDims &d, const float *w_q, const float *w_v, const float *w_o,
+int pack_weights_run(const LshAttnDims &d, const float *w_q, const float *w_v, const float *w_o, const float *w_k,
                      void *wqv, void *wo, cudaStream_t stream) {
-  const int64_t n = static_cast<int64_t>(d.D) * d.H * (d.dq + d.dv);
-  pack_wqv_kernel<<<grid_for(n, 256), 256, 0, stream>>>(w_q, w_v, static_cast<__nv_bfloat16 *>(wqv), d.H,
+  if ((d.separate_k != 0) != (w_k != nullptr)) return set_error("pack_weights: w_k must be given exactly when dims.separate_k is set");
+  const int64_t n = static_cast<int64_t>(d.D) * d.H * derive(d).QV;
+  pack_wqv_kernel<<<grid_for(n, 256), 256, 0, stream>>>(w_q, w_v, w_k, static_cast<__nv_bfloat16 *>(wqv), d.H,
                                                         d.D, d.dq, d.dv);
   LSH_CHECK_LAUNCH("pack_wqv_kernel");
   const int64_t no = static_cast<int64_t>(d.H) * d.dv * d.D;
@@ -123,9 +126,10 @@ int f32_to_bf16_run(const float *src, void *dst, int64_t n, cudaStream_t stream)
   return 0;
 }
 
-int unpack_dwqv_run(const LshAttnDims &d, const float *dwqv, float *dw_q, float *dw_v, cudaStream_t stream) {
-  const int64_t n = static_cast<int64_t>(d.D) * d.H * (d.dq + d.dv);
-  unpack_dwqv_kernel<<<grid_for(n, 256), 256, 0, stream>>>(dwqv, dw_q, dw_v, d.H, d.D, d.dq, d.dv);
+int unpack_dwqv_run(const LshAttnDims &d, const float *dwqv, float *dw_q, float *dw_v, float *dw_k, cudaStream_t stream) {
+  if ((d.separate_k != 0) != (dw_k != nullptr)) return set_error("unpack_dwqv: dw_k must be given exactly when dims.separate_k is set");
+  const int64_t n = static_cast<int64_t>(d.D) * d.H * derive(d).QV;
+  unpack_dwqv_kernel<<<grid_for(n, 256), 256, 0, stream>>>(dwqv, dw_q, dw_v, dw_k, d.H, d.D, d.dq, d.dv);
   LSH_CHECK_LAUNCH("unpack_dwqv_kernel");
   return 0;
 }

@@ -250,6 +250,7 @@ class LSHSelfAttention:
     self._weights = ()
     self._state = ()
     self._rng = None
+    self._separate_k = False            # SelfAttention(share_qk=False) sets it: weights (w_q, w_k, w_v, w_o), EA:1112-1128
     self._x_stash = None                # (weakref to a host x, its _version, device copy): forward -> matching backward
     self._rotations_override = None     # tests / a JAX host inject explicit rotations here
     self._out_keep_override = None      # likewise an explicit (d_model,) bool keep-mask for output dropout
@@ -383,20 +384,20 @@ class LSHSelfAttention:
     class _Fn(torch.autograd.Function):
 
       @staticmethod
-      def forward(ctx, x0, w_q, w_v, w_o):
+      def forward(ctx, x0, *ws):
         inputs = x0 if have_single_input else (x0,) + xs[1:]
         out, new_state, _, _ = layer._forward_and_or_backward(
-            inputs, (w_q, w_v, w_o), state, rng, compute_output=True, update_state=True, _stash='store')
-        ctx.save_for_backward(x0, w_q, w_v, w_o)
+            inputs, tuple(ws), state, rng, compute_output=True, update_state=True, _stash='store')
+        ctx.save_for_backward(x0, *ws)
         holder['new_state'] = new_state                             # residual (base.py:659)
         return out
 
       @staticmethod
       def backward(ctx, grad):
-        x0, w_q, w_v, w_o = ctx.saved_tensors
+        x0, ws = ctx.saved_tensors[0], tuple(ctx.saved_tensors[1:])
         inputs = x0 if have_single_input else (x0,) + xs[1:]
         inputs_grad, weights_grad = layer.backward(
-            inputs, None, grad.contiguous(), (w_q, w_v, w_o), state, holder['new_state'], rng)
+            inputs, None, grad.contiguous(), ws, state, holder['new_state'], rng)
         gx = inputs_grad if have_single_input else inputs_grad[0]
         return (gx,) + tuple(weights_grad)
 
@@ -445,7 +446,7 @@ class LSHSelfAttention:
     factors = ops.bucket_factors(self._n_buckets, seqlen, self._chunk_len)     # EA:1890-1902
     return _lib.make_dims(batch_size, self._n_heads, seqlen, d_model, self._d_qk, self._d_v,
                           self._chunk_len, self._n_chunks_before, self._n_chunks_after, self._n_hashes,
-                          factors, self._causal, self._masked, act_dtype)
+                          factors, self._causal, self._masked, act_dtype, separate_k=self._separate_k)
 
   def forward_and_or_backward(self, inputs, weights, state, rng, output_grad=None,
                               compute_output=True, update_state=True):
@@ -496,7 +497,13 @@ class LSHSelfAttention:
     mask_d = None
     if self._masked:
       mask_d = to_dev(inputs[1]).to(torch.uint8).contiguous()
-    w_q, w_v, w_o = (to_dev(w).to(torch.float32).contiguous() for w in weights)
+    if len(weights) != (4 if self._separate_k else 3):
+      raise ValueError('expected %d weight tensors, got %d' % (4 if self._separate_k else 3, len(weights)))
+    w_k = None
+    if self._separate_k:                                            # (w_q, w_k, w_v, w_o), EA:1126-1128
+      w_q, w_k, w_v, w_o = (to_dev(w).to(torch.float32).contiguous() for w in weights)
+    else:
+      w_q, w_v, w_o = (to_dev(w).to(torch.float32).contiguous() for w in weights)
     out_mult = self._output_multiplier(rng, int(x_d.shape[2]), dev)
     attn_keep = self._attention_multiplier(rng, dev)
     if out_mult is not None:
@@ -544,14 +551,14 @@ class LSHSelfAttention:
     inputs_grad = weights_grad = None
     if not compute_grad:
       _lib.check(lib.lsh_layer_fwd(
-          ctypes.byref(dims), ops._ptr(x_d), ops._ptr(w_q), ops._ptr(w_v), ops._ptr(w_o), ops._ptr(rotations),
+          ctypes.byref(dims), ops._ptr(x_d), ops._ptr(w_q), ops._ptr(w_v), ops._ptr(w_o), ops._ptr(w_k), ops._ptr(rotations),
           ops._ptr(mask_d), ops._ptr(attn_keep), ops._ptr(buckets_d), buckets_d.stride(0), ops._ptr(out_d), ops._ptr(ws),
           ws.numel(), stream), 'lsh_layer_fwd')
     else:
       if update_state:
         # EA allows update_state together with output_grad; the hash must then run first.
         _lib.check(lib.lsh_layer_fwd(
-            ctypes.byref(dims), ops._ptr(x_d), ops._ptr(w_q), ops._ptr(w_v), ops._ptr(w_o), ops._ptr(rotations),
+            ctypes.byref(dims), ops._ptr(x_d), ops._ptr(w_q), ops._ptr(w_v), ops._ptr(w_o), ops._ptr(w_k), ops._ptr(rotations),
             ops._ptr(mask_d), ops._ptr(attn_keep), ops._ptr(buckets_d), buckets_d.stride(0),
             ops._ptr(out_d if out_d is not None else torch.empty_like(x_d)), ops._ptr(ws), ws.numel(), stream),
             'lsh_layer_fwd')
@@ -560,9 +567,10 @@ class LSHSelfAttention:
         raise ValueError('output_grad shape %s != input shape %s' % (tuple(g_d.shape), tuple(x_d.shape)))
       dx = torch.empty_like(x_d)
       # one contiguous gradient buffer (dw_q | dw_v | dw_o): the data-parallel mean below reduces slices of it in place
-      n_q, n_v, n_o = w_q.numel(), w_v.numel(), w_o.numel()
+      n_q, n_v, n_o = w_q.numel() + (w_k.numel() if w_k is not None else 0), w_v.numel(), w_o.numel()
       dw_flat = torch.empty(n_q + n_v + n_o, dtype=torch.float32, device=dev)
-      dw_q, dw_v = dw_flat[:n_q].view_as(w_q), dw_flat[n_q:n_q + n_v].view_as(w_v)
+      dw_q, dw_v = dw_flat[:w_q.numel()].view_as(w_q), dw_flat[n_q:n_q + n_v].view_as(w_v)
+      dw_k = dw_flat[w_q.numel():n_q].view_as(w_k) if w_k is not None else None
       dw_o = dw_flat[n_q + n_v:].view_as(w_o)
       overlap = None
       if _GRAD_ALLREDUCE['on']:
@@ -570,9 +578,9 @@ class LSHSelfAttention:
         overlap = dp.GradOverlap.get(dev)         # None without an initialised NCCL group of more than one rank
       ev_o, ev_qv = (overlap.events() if overlap is not None else (None, None))
       _lib.check(lib.lsh_layer_bwd(
-          ctypes.byref(dims), ops._ptr(x_d), ops._ptr(w_q), ops._ptr(w_v), ops._ptr(w_o), ops._ptr(mask_d),
+          ctypes.byref(dims), ops._ptr(x_d), ops._ptr(w_q), ops._ptr(w_v), ops._ptr(w_o), ops._ptr(w_k), ops._ptr(mask_d),
           ops._ptr(attn_keep), ops._ptr(buckets_d), buckets_d.stride(0), ops._ptr(g_d), ops._ptr(out_d), ops._ptr(dx), ops._ptr(dw_q),
-          ops._ptr(dw_v), ops._ptr(dw_o), ops._ptr(ws), ws.numel(),
+          ops._ptr(dw_v), ops._ptr(dw_o), ops._ptr(dw_k), ops._ptr(ws), ws.numel(),
           ev_o.cuda_event if ev_o is not None and out_mult is None else None,
           ev_qv.cuda_event if ev_qv is not None else None, stream), 'lsh_layer_bwd')
       if out_mult is not None:
@@ -586,8 +594,10 @@ class LSHSelfAttention:
         dp.allreduce_mean_((dw_q, dw_v, dw_o))
       if host_io:
         dx, dw_q, dw_v, dw_o = (io.download(t, r) for t, r in ((dx, 'dx'), (dw_q, 'dw_q'), (dw_v, 'dw_v'), (dw_o, 'dw_o')))
+        if dw_k is not None:
+          dw_k = io.download(dw_k, 'dw_k')
       inputs_grad = dx if have_single_input else (dx,) + (None,) * (len(inputs) - 1)
-      weights_grad = (dw_q, dw_v, dw_o)
+      weights_grad = (dw_q, dw_k, dw_v, dw_o) if dw_k is not None else (dw_q, dw_v, dw_o)
     if update_state:
       new_state = (buckets_d, new_rng)    # state stays on the device, like a jitted Trax layer's
     if compute_output and host_io:

@@ -59,19 +59,24 @@ def workspace(device, nbytes):
   return buf
 
 
-def pack_weights(dims, w_q, w_v, w_o):
+def _row_width(dims):
+  """Columns of one (token, head) row of the packed projections: q | v, plus k with separate keys."""
+  return dims.dq + dims.dv + (dims.dq if dims.separate_k else 0)
+
+
+def pack_weights(dims, w_q, w_v, w_o, w_k=None):
   lib = _lib.load()
   dev = w_q.device
-  wqv = torch.empty((dims.D, dims.H, dims.dq + dims.dv), dtype=torch.bfloat16, device=dev)
+  wqv = torch.empty((dims.D, dims.H, _row_width(dims)), dtype=torch.bfloat16, device=dev)
   wo = torch.empty((dims.H * dims.dv, dims.D), dtype=torch.bfloat16, device=dev)
-  _lib.check(lib.lsh_pack_weights(ctypes.byref(dims), _ptr(w_q), _ptr(w_v), _ptr(w_o), _ptr(wqv), _ptr(wo),
+  _lib.check(lib.lsh_pack_weights(ctypes.byref(dims), _ptr(w_q), _ptr(w_v), _ptr(w_o), _ptr(w_k), _ptr(wqv), _ptr(wo),
                                   _stream()), 'lsh_pack_weights')
   return wqv, wo
 
 
 def project_qv(dims, x_bf16, wqv):
   lib = _lib.load()
-  qv = torch.empty((dims.B, dims.L, dims.H, dims.dq + dims.dv), dtype=torch.bfloat16, device=x_bf16.device)
+  qv = torch.empty((dims.B, dims.L, dims.H, _row_width(dims)), dtype=torch.bfloat16, device=x_bf16.device)
   ws = workspace(x_bf16.device, 32 << 20)
   _lib.check(lib.lsh_project_qv(ctypes.byref(dims), _ptr(x_bf16), _ptr(wqv), _ptr(qv), _ptr(ws), ws.numel(),
                                 _stream()), 'lsh_project_qv')

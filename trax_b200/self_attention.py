@@ -1,16 +1,21 @@
 """`trax.layers.research.efficient_attention.SelfAttention` (EA:936-1726) — the chunked local attention ReformerLM
-interleaves with the LSH layer — for the configuration the existing kernels cover: `share_qk=True` with a `chunk_len`.
+interleaves with the LSH layer (`reformer_enwik8.gin:23-28`: 3 of 4 layers) — for every `share_qk` with a `chunk_len`.
 
 With shared queries and keys, `SelfAttention.forward_unbatched` (EA:1136-1197) is `LSHSelfAttention.forward_unbatched`
 with ONE hash round and the identity permutation: `attend` gets `q_info = arange(seqlen)`, keys are the length-normalised
 queries, a token does not attend to itself (EA:1175-1178), look-back / look-ahead chunks wrap around (EA:122-142), the
 padding mask flips the sign of `kv_info` (EA:1185-1186).  Sorting all-zero bucket ids by `seqlen * bucket + position`
 (EA:1946-1947) IS the identity, so the layer runs the LSH core — same CUDA kernels, no hashing — on constant buckets.
-The default `share_qk=False` (separate key projection, no key normalisation, self-attention allowed) needs a separate-K
-variant of the attend kernels and raises; its oracle (`oracle/self_attention_oracle.py`) is already pinned to the reference.
+The default `share_qk=False` (EA:1133-1197) has a key projection of its own, `k = x w_k` (EA:1160-1162), which is NOT
+length-normalised (EA:229-231 apply to shared-QK only; the keys are only divided by sqrt(d_qk), EA:232), and a token may
+attend to itself (`exclude_self=self._share_qk`, EA:1175-1178).  The kernels take it as `LshAttnDims.separate_k`: the
+projections are ONE GEMM onto q | v | k rows, the attention kernels read their key tiles from the k columns with a constant
+scale and without the self mask, and the key-side cotangent goes to `dw_k` instead of `dw_q` (no normalisation VJP).
 
-Interface kept: the constructor keywords (EA:939-953), weights `(w_q, w_v, w_o)` for `share_qk` (EA:1126), state `()`
-(EA:1130-1131), `forward`, `backward`, `forward_and_or_backward` → `(output, new_state, inputs_grad, weights_grad)`.
+Interface kept: the constructor keywords (EA:939-953), weights `(w_q, w_v, w_o)` for `share_qk`, `(w_q, w_k, w_v, w_o)`
+otherwise (EA:1112-1128), state `()` (EA:1130-1131), `forward`, `backward`, `forward_and_or_backward` →
+`(output, new_state, inputs_grad, weights_grad)`.  `chunk_len=None` (one dense window over the whole sequence) and
+`mode='predict'` are not built and raise.
 """
 import torch
 
@@ -25,9 +30,6 @@ class SelfAttention(LSHSelfAttention):
                attention_dropout=0.0, output_dropout=0.0, n_parallel_heads=None, use_python_loop=False,
                use_reference_code=False):
     del predict_mem_len, predict_drop_len
-    if not share_qk:
-      raise NotImplementedError('SelfAttention(share_qk=False) needs attend kernels with a separate key projection, without '
-                                'key normalisation and self-exclusion (EA:1160-1162, 230, 1175-1178); only share_qk=True is built')
     if chunk_len is None:
       raise NotImplementedError('SelfAttention(chunk_len=None) is dense attention over the whole sequence; the kernels are '
                                 'chunked (chunk_len 32 / 64 / 128 / 256)')
@@ -36,9 +38,20 @@ class SelfAttention(LSHSelfAttention):
                      attention_dropout=attention_dropout, output_dropout=output_dropout, bias=bias,
                      n_parallel_heads=n_parallel_heads, use_python_loop=use_python_loop,
                      use_reference_code=use_reference_code)
+    self._share_qk = bool(share_qk)
+    self._separate_k = not share_qk
 
   def init_weights_and_state(self, input_signature, device=None):
     super().init_weights_and_state(input_signature, device=device)   # same (w_q, w_v, w_o) shapes and init (EA:1061-1066)
+    if self._separate_k:                                             # (w_q, w_k, w_v, w_o), EA:1112-1128
+      import numpy as np
+      from trax_b200.lsh_attention import _split_host
+      w_q, w_v, w_o = self.weights
+      d_model = int(w_q.shape[1])
+      keys = _split_host(np.asarray(self.rng, np.uint32) ^ np.uint32(0x6b657973), self._n_heads)     # 'keys'
+      w_k = np.stack([self._kernel_initializer((d_model, self._d_qk), np.random.Generator(np.random.Philox(
+          key=int(k[0]) << 32 | int(k[1])))) for k in keys])
+      self.weights = (w_q, torch.from_numpy(np.ascontiguousarray(w_k)).to(w_q.device), w_v, w_o)
     self.state = ()                                                  # EA:1130-1131
 
   def forward(self, inputs):
