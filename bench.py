@@ -170,11 +170,11 @@ def run_reference(args, wl, name):
   print(json.dumps(line))
 
 
-def _config(name, wl, world):
+def _config(name, wl, world, head_reduce='all'):
   """Same dict (same keys, same workload string) for both arms."""
   if wl.get('shard') == 'heads':
-    par = 'heads sharded over %d GPU(s) (%d per GPU), all-reduce of the head-summed output and input gradient inside the step' % (
-        world, wl['H'] // world)
+    par = 'heads sharded over %d GPU(s) (%d per GPU), %s of the head-summed output and input gradient inside the step' % (
+        world, wl['H'] // world, 'reduce-scatter (over the sequence)' if head_reduce == 'scatter' else 'all-reduce')
   elif world > 1:
     par = 'dp%d over batch, NCCL all-reduce of dW inside the step' % world
   else:
@@ -244,7 +244,7 @@ def run_ours(args, wl, name):
     # the full 16-head layer's weights (same rng on every rank; drawn on the host), this rank's heads taken out of them
     full = trax_b200.LSHSelfAttention(n_heads=H, **layer_kw)
     full.init_weights_and_state(trax_b200.ShapeDtype((B, L, D)), device='cpu')
-    layer = dp.HeadShardedLSHSelfAttention(trax_b200.LSHSelfAttention(n_heads=H_local, **layer_kw), H)
+    layer = dp.HeadShardedLSHSelfAttention(trax_b200.LSHSelfAttention(n_heads=H_local, **layer_kw), H, reduce=args.head_reduce)
     layer.load_full(full.weights, full.state)
     layer.local.weights = tuple(w.to(dev) for w in layer.local.weights)
     layer.local.state = tuple(s.to(dev) for s in layer.local.state)
@@ -338,7 +338,7 @@ def run_ours(args, wl, name):
   line = dict(metric='LSH-attn fwd+bwd tokens/sec', value=tok_s, unit='tokens/s', n_gpus=world, steps=args.steps,
               warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling='strong' if head_sharded else 'weak',
               vs_baseline=None, dtype='bf16' if dtype == torch.bfloat16 else 'f32 I/O, bf16 tensor-core operands',
-              data='synthetic', config=_config(name, wl, world), clocks=clocks, e2e=e2e, gpu_launches=launches)
+              data='synthetic', config=_config(name, wl, world, args.head_reduce), clocks=clocks, e2e=e2e, gpu_launches=launches)
   if head_sharded and world > 1:
     # out and dx, all-reduced once each per step (counted by the layer from the tensors it reduced)
     line['collective_bytes_per_step'] = layer.comm_bytes // max(1, layer.n_calls // 2)
@@ -501,6 +501,8 @@ def main():
   ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
   ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
   ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--head-reduce', default='all', choices=['all', 'scatter'],
+                  help='config 5: all-reduce the head sums, or reduce-scatter them over the sequence (sequence-parallel consumer)')
   args = ap.parse_args()
   wl = WORKLOADS[args.workload]
   if args.impl == 'reference':

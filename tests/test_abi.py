@@ -108,3 +108,30 @@ def test_layer_init_layout_and_no_cpu_fallback():
   if not torch.cuda.is_available():
     with pytest.raises(_lib.LshAttnError):
       layer.forward(torch.zeros(2, 2048, 1024))
+
+
+def test_jax_ffi_shim_translation_unit_compiles_and_is_guarded(tmp_path):
+  """csrc/jax_ffi_shim.cc (the `jax.ffi` handlers over the C ABI) is real code behind
+  `__has_include("xla/ffi/api/ffi.h")`: without jaxlib's headers it must still compile and say so; its handler bodies call
+  the entry points with the argument counts the header declares (checked textually against SIGNATURES)."""
+  import re
+  import subprocess
+  src = os.path.join(ROOT, 'trax_b200', 'csrc', 'jax_ffi_shim.cc')
+  obj = str(tmp_path / 'shim.so')
+  subprocess.check_call(['g++', '-std=c++17', '-shared', '-fPIC', src, '-o', obj])
+  lib = ctypes.CDLL(obj)
+  assert lib.lsh_attn_jax_ffi_available() == 0          # no XLA headers in this image
+  text = open(src).read()
+  assert '__has_include("xla/ffi/api/ffi.h")' in text and 'XLA_FFI_DEFINE_HANDLER_SYMBOL' in text
+  from trax_b200 import _lib
+  for fn in ('lsh_layer_fwd', 'lsh_layer_bwd'):
+    m = re.search(fn + r'\((.*?)\)\);', text, re.S)
+    assert m, fn
+    depth, n_args = 0, 1
+    for ch in m.group(1):
+      depth += ch in '([{'
+      depth -= ch in ')]}'
+      n_args += (ch == ',' and depth == 0)
+    assert n_args == len(_lib.SIGNATURES[fn][1]), (fn, n_args, len(_lib.SIGNATURES[fn][1]))
+  with pytest.raises(ImportError):
+    import trax_b200.jax_binding  # noqa: F401  (no jax in this image)
