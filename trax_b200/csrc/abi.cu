@@ -10,6 +10,7 @@
 #include <mutex>
 
 #include "attend_params.cuh"
+#include "tc_common.cuh"
 
 namespace lsh {
 
@@ -475,3 +476,31 @@ int lsh_make_rotations(const LshAttnDims *dims, const uint32_t *keys, uint32_t *
 }
 
 }  // extern "C"
+
+// ---- TMA descriptor encoder (driver entry point fetched through the runtime: no link-time dependency on libcuda) ------
+namespace lsh {
+int make_row_gather_map(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes, uint32_t box_cols) {
+  using EncodeFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = [] {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      fn = nullptr;
+    return reinterpret_cast<EncodeFn>(fn);
+  }();
+  if (!encode) return set_error("cuTensorMapEncodeTiled is not available from this driver");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (pitch_bytes & 15)) return set_error("TMA: base / pitch must be 16-byte aligned");
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {pitch_bytes};
+  const cuuint32_t box[2] = {box_cols, 1};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
+  return 0;
+}
+}  // namespace lsh

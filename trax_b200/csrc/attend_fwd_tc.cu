@@ -37,6 +37,12 @@
 #ifndef TC_FWD_REDO
 #define TC_FWD_REDO 1
 #endif
+// TC_FWD_TMA 1: the producers fetch the tile rows with TMA (cp.async.bulk.tensor ... tile::gather4: four gathered rows per
+// instruction, written by the async proxy straight into the SWIZZLE_128B atoms, completion counted in bytes on the tile's
+// mbarrier) — 2 instructions per lane and tile; 0: 32 cp.async (16 bytes each) per lane and tile (round 1).
+#ifndef TC_FWD_TMA
+#define TC_FWD_TMA 1
+#endif
 
 namespace lsh {
 
@@ -156,7 +162,7 @@ __device__ __forceinline__ void softmax_block_generic(const uint32_t (&r)[32], c
 // !SORTED: the reference's masks evaluated per element from the keys' kv_info.  Two instantiations keep each one's code
 // (instruction-cache footprint) small.
 template <bool SORTED>
-__global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const AttendFwdParams p, int total_chunks) {
+__global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const __grid_constant__ AttendFwdParams p, int total_chunks) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t *tiles = smem;                                    // [TC_NST][K 16 KB | V 16 KB]
@@ -169,6 +175,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
   const int g1 = static_cast<int>(static_cast<int64_t>(total_chunks) * (blockIdx.x + 1) / gridDim.x);
 
   if (warp == 14) tmem_alloc(&sh.tmem_base, 512);
+#if TC_FWD_TMA
+  if (tid == 12 * 32) { tma_prefetch_desc(&p.tm_k); tma_prefetch_desc(&p.tm_v); }
+#endif
   if (tid == 0) {
     // full: per producer thread one arrival by its copies (cp.async ... noinc) and one ordinary arrival that releases its
     // plain metadata stores
@@ -259,6 +268,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
         }
         if (lane == 0) { mt.vmin[pw] = mn; mt.vmax[pw] = mx; }
       }
+#if TC_FWD_TMA
+      // TMA row gather: lanes 0-15 fetch the normalised keys qhat (BH, L, 64), lanes 16-31 the value halves of the qv rows,
+      // each lane the four ranks 4 q .. 4 q + 3 of this warp's 64 (q = 16 pw + lane % 16).  Rank r lives in tile row r ^ flip,
+      // so the four land in the aligned row group 4 G (G = q, or 31 - q for a flipped tile) — in reverse order when flipped.
+      {
+        const int l16 = lane & 15, isv = lane >> 4;
+        const int psel = l16 < 8 ? pa : pb;
+        int pr[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pr[j] = __shfl_sync(0xffffffffu, psel, (4 * l16 + j) & 31);
+        const int q = 16 * pw + l16, G = flip ? 31 - q : q;
+        const int i0 = flip ? pr[3] : pr[0], i1 = flip ? pr[2] : pr[1], i2 = flip ? pr[1] : pr[2], i3 = flip ? pr[0] : pr[3];
+        const uint32_t dst = tiles_u32 + slot * TC_TILE_BYTES + (isv ? TC_C * 128 : 0) + G * 512;
+        if (isv) {
+          const int rb = (b * p.L) * p.H + h;                   // row of (b, position 0, h) in the (B*L*H, 128) view of qv
+          tma_gather4(dst, &p.tm_v, &sh.full[slot], 64, rb + i0 * p.H, rb + i1 * p.H, rb + i2 * p.H, rb + i3 * p.H);
+        } else {
+          const int rb = u * p.L;
+          tma_gather4(dst, &p.tm_k, &sh.full[slot], 0, rb + i0, rb + i1, rb + i2, rb + i3);
+        }
+      }
+      // completion: the copies' bytes (16 KB per warp, expected by lane 0's arrival) + the rowmeta cp.async + one arrival
+      // per thread releasing its plain metadata stores
+      cp_async_mbar_arrive_noinc(&sh.full[slot]);
+      if (lane == 0) mbar_arrive_expect_tx(&sh.full[slot], 64 * 256);
+      else mbar_arrive(&sh.full[slot]);
+#else
       // 16-byte pieces 0-7 of a row: normalised key qhat (BH, L, 64); pieces 8-15: value, second half of the qv row.
       // Destination of rank R = 64 pw + 2 i + hi, piece c: tile + (X << 7) + (((c ^ X) & 7) << 4) with X = R ^ flip.  All
       // bit fields are disjoint, so this is  tile + (lane_tile_const ^ imm(i)):  one LOP3 + one IADD per copy.
@@ -281,6 +317,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const Atte
       // The ordinary arrival (release) publishes this thread's plain metadata stores.
       cp_async_mbar_arrive_noinc(&sh.full[slot]);
       mbar_arrive(&sh.full[slot]);
+#endif
     };
     TileReq r0, r1, r2;
     request(r0); request(r1); request(r2);
@@ -706,9 +743,17 @@ int attend_fwd_tc_run(const AttendFwdParams &p, int BH, cudaStream_t stream) {
     if (m > 0 && m < grid) grid = m;
   }
   if (!p.redo) return set_error("attend_fwd_tc: redo queue missing from the workspace");
+#if TC_FWD_TMA
+  AttendFwdParams pt = p;
+  const int64_t B = BH / p.H;
+  if (int rc = make_row_gather_map(&pt.tm_k, p.qhat, static_cast<uint64_t>(BH) * p.L, 64, 128, 64)) return rc;
+  if (int rc = make_row_gather_map(&pt.tm_v, p.qv, static_cast<uint64_t>(B) * p.L * p.H, 128, 256, 64)) return rc;
+#else
+  const AttendFwdParams &pt = p;
+#endif
   if (cudaMemsetAsync(p.redo, 0, 8, stream) != cudaSuccess) return set_error("attend_fwd_tc: cudaMemsetAsync failed");
-  if (sorted) attend_fwd_tc_kernel<true><<<grid, TC_THREADS, smem, stream>>>(p, total);
-  else attend_fwd_tc_kernel<false><<<grid, TC_THREADS, smem, stream>>>(p, total);
+  if (sorted) attend_fwd_tc_kernel<true><<<grid, TC_THREADS, smem, stream>>>(pt, total);
+  else attend_fwd_tc_kernel<false><<<grid, TC_THREADS, smem, stream>>>(pt, total);
   LSH_CHECK_LAUNCH("attend_fwd_tc_kernel");
   attend_fwd_redo_kernel<<<sms, 256, 0, stream>>>(p);
   LSH_CHECK_LAUNCH("attend_fwd_redo_kernel");

@@ -1,5 +1,7 @@
 // Parameter block shared by the two forward attention kernels (mma.sync path and tcgen05 path).
 #pragma once
+#include <cuda.h>   // CUtensorMap
+
 #include "common.cuh"
 
 namespace lsh {
@@ -21,6 +23,7 @@ struct AttendFwdParams {
   int *redo;                    // tcgen05 path: [0] = number of queued rows, [2 + 2 i], [3 + 2 i] = {unit * n_chunks + chunk, ticker}
   long long *trace;             // debug: per-phase clock64 stamps of CTA 0 (null = off)
   int L, H, N, n_chunks, nb, nwin, causal, masked;
+  CUtensorMap tm_k, tm_v;       // tcgen05 path: TMA row-gather descriptors of qhat (BH*L, 64) and of qv viewed as (B*L*H, row)
   int row;                      // elements per (token, head) row of qv: 128 (q | v) or 192 (q | v | k, separate keys)
   int ksep;                     // separate, un-normalised keys, self-attention allowed (SelfAttention(share_qk=False), EA:1133-1197)
 };

@@ -1,10 +1,38 @@
 // tcgen05 / TMEM / mbarrier primitives for sm_100a (inline PTX; encodings follow the PTX ISA as
 // exercised by CUTLASS's cute/arch/mma_sm100_desc.hpp, mma_sm100_umma.hpp, copy_sm100.hpp).
 #pragma once
+#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched from the driver at run time, no libcuda link)
+
 #include "common.cuh"
 
 namespace lsh {
+
+// ---- TMA descriptors (host) ---------------------------------------------------------------------------
+// 2-D bf16 tensor of `rows` rows x `cols` columns (row pitch `pitch_bytes`), box = `box_cols` columns x 1 row,
+// SWIZZLE_128B: the descriptor form `cp.async.bulk.tensor.2d ... tile::gather4` takes (four independent row
+// coordinates per instruction, rows land in consecutive 128-byte rows of the swizzle atom; CUTLASS builds the same map for
+// SM100_TMA_LOAD_2D_GATHER4, cute/atom/copy_traits_sm90_tma.hpp).
+int make_row_gather_map(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes, uint32_t box_cols);
+
 #ifdef __CUDACC__
+
+// ---- TMA (device) -------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
+  asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+// Four rows (r0..r3, any order) of a 2-D tensor, columns [c0, c0 + box_cols), into four consecutive 128-byte rows at
+// `dst` (swizzled by the shared-memory address like every SWIZZLE_128B tile); completion = bytes on the mbarrier.
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap *map, uint64_t *bar, int c0, int r0, int r1, int r2,
+                                            int r3) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
 
 // ---- mbarrier ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
