@@ -231,7 +231,10 @@ def run_ours(args, wl, name):
     os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
     if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
       os.environ['NCCL_DEBUG'] = 'WARN'          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
-    dist.init_process_group('nccl', device_id=dev)
+    # NCCL's kernels go on a high-priority stream: the weight-gradient all-reduce has to get SMs while the layer's last
+    # GEMMs still fill the machine (at default priority it started only when they were done: fully exposed)
+    opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True) if not os.environ.get('LSH_BENCH_NCCL_DEFAULT_PRIO') else None
+    dist.init_process_group('nccl', device_id=dev, pg_options=opts)
   dtype = torch.bfloat16 if wl['dtype'] == 'bf16' else torch.float32
   B, L, D, H = wl['B'], wl['L'], wl['D'], wl['H']
   head_sharded = wl.get('shard') == 'heads'

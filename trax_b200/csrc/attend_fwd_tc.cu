@@ -40,8 +40,11 @@
 // TC_FWD_TMA 1: the producers fetch the tile rows with TMA (cp.async.bulk.tensor ... tile::gather4: four gathered rows per
 // instruction, written by the async proxy straight into the SWIZZLE_128B atoms, completion counted in bytes on the tile's
 // mbarrier) — 2 instructions per lane and tile; 0: 32 cp.async (16 bytes each) per lane and tile (round 1).
+// Measured at config 2 (ncu, interleaved on one box, both parity-green over the whole GPU suite): cp.async 290.8-293.9 us,
+// TMA gather4 298.8-305.2 us (second box: 268-272 vs 278-280 us) — the row gather is 3.5 % SLOWER through the TMA unit
+// although the producers issue 16x fewer instructions, so cp.async stays the default and the TMA path the A/B variant.
 #ifndef TC_FWD_TMA
-#define TC_FWD_TMA 1
+#define TC_FWD_TMA 0
 #endif
 
 namespace lsh {
@@ -233,7 +236,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const __gr
       if (r.have) fetch_sticker(r.u, r.cc, r.tka, r.tkb, r.bda, r.bdb);
     };
     constexpr bool sorted_path = SORTED;
-    const int ch = lane & 15, hi = lane >> 4;              // 16-byte piece of the 256-byte row pair; row parity
+    [[maybe_unused]] const int ch = lane & 15, hi = lane >> 4;   // 16-byte piece of the 256-byte row pair; row parity
     auto issue = [&](const TileReq &r) {
       const int n = r.n, u = r.u, tka = r.tka, tkb = r.tkb;
       const uint32_t slot = slot_of(n);
@@ -274,10 +277,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const __gr
       // so the four land in the aligned row group 4 G (G = q, or 31 - q for a flipped tile) — in reverse order when flipped.
       {
         const int l16 = lane & 15, isv = lane >> 4;
-        const int psel = l16 < 8 ? pa : pb;
         int pr[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) pr[j] = __shfl_sync(0xffffffffu, psel, (4 * l16 + j) & 31);
+        for (int j = 0; j < 4; ++j) {                           // rank 4 l16 + j of the warp's 64: pa of that lane, or pb of lane - 32
+          const int va = __shfl_sync(0xffffffffu, pa, (4 * l16 + j) & 31), vb = __shfl_sync(0xffffffffu, pb, (4 * l16 + j) & 31);
+          pr[j] = l16 < 8 ? va : vb;
+        }
         const int q = 16 * pw + l16, G = flip ? 31 - q : q;
         const int i0 = flip ? pr[3] : pr[0], i1 = flip ? pr[2] : pr[1], i2 = flip ? pr[1] : pr[2], i3 = flip ? pr[0] : pr[3];
         const uint32_t dst = tiles_u32 + slot * TC_TILE_BYTES + (isv ? TC_C * 128 : 0) + G * 512;

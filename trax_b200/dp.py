@@ -30,7 +30,7 @@ class GradOverlap:
 
   def __init__(self, dev):
     self.dev = dev
-    self.comm = torch.cuda.Stream(device=dev)
+    self.comm = torch.cuda.Stream(device=dev, priority=-1)      # above the compute stream: collectives must not queue behind GEMMs
     self._events = None
 
   @classmethod
