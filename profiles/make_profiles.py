@@ -2,11 +2,12 @@
   gpurun_out/kernels_<tag>.csv   ncu --metrics gpu__time_duration.sum,dram__bytes_{read,write}.sum,...pipe/issue... of bench.py
   gpurun_out/prof_<tag>_{attend_bwd,attend_fwd,hash}.ncu-rep   ncu --set full of tests/prof_stage.py <stage>
   gpurun_out/bench_<tag>.json    the bench line of the same build
-Usage: python profiles/make_profiles.py <tag>"""
+Usage: python profiles/make_profiles.py <tag> [round prefix, e.g. r2]"""
 import collections, csv, io, json, re, shutil, subprocess, sys
 tag = sys.argv[1]
-shutil.copy('gpurun_out/bench_%s.json' % tag, 'profiles/r1_bench_line.json')
-shutil.copy('gpurun_out/kernels_%s.csv' % tag, 'profiles/r1_kernels_metrics.csv')
+rnd = sys.argv[2] if len(sys.argv) > 2 else 'r1'   # file-name prefix of the round
+shutil.copy('gpurun_out/bench_%s.json' % tag, 'profiles/%s_bench_line.json' % rnd)
+shutil.copy('gpurun_out/kernels_%s.csv' % tag, 'profiles/%s_kernels_metrics.csv' % rnd)
 rows = [r for r in csv.reader(open('gpurun_out/kernels_%s.csv' % tag)) if len(r) > 5]
 hdr = [r for r in rows if 'Kernel Name' in r][0]; ci = {h: i for i, h in enumerate(hdr)}
 byid = collections.OrderedDict()
@@ -42,9 +43,9 @@ for n, e in sorted(agg.items(), key=lambda kv: -kv[1]['t']):
       n, e['n'], t / 1e3, 100 * e['t'] / tot, e['rd'] / e['n'] / 1e6, e['wr'] / e['n'] / 1e6, (e['rd'] + e['wr']) / e['n'] / t,
       e['tp'] / e['n'], e['fma'] / e['n'], e['iss'] / e['n']))
 out.append('total %.1f us over %d launches' % (tot / 1e3, len(sel)))
-open('profiles/r1_kernel_table.txt', 'w').write('\n'.join(out) + '\n')
+open('profiles/%s_kernel_table.txt' % rnd, 'w').write('\n'.join(out) + '\n')
 # launch list in the older format (time only) for summarize_launches.py
-with open('profiles/r1_launches.csv', 'w') as f:
+with open('profiles/%s_launches.csv' % rnd, 'w') as f:
   w = csv.writer(f, quoting=csv.QUOTE_ALL); w.writerow(hdr)
   for r in rows:
     if r is not hdr and r[ci['Metric Name']] == 'gpu__time_duration.sum':
@@ -55,18 +56,18 @@ keys = ['dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__time_duration.sum
         'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
         'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed']
-full = []; traffic = {'_comment': 'dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` (profiles/r1_ncu_full_summary.txt), workload c2'}
-names = {'attend_bwd': 'attend_bwd(prep+bwd+sum_rounds)', 'attend_fwd': 'attend_fwd', 'hash': 'hash'}
+full = []; traffic = {'_comment': 'dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` (profiles/%s_ncu_full_summary.txt)' % rnd + ', workload c2'}
+names = {'attend_bwd': 'attend_bwd_tc_kernel', 'attend_fwd': 'attend_fwd_tc_kernel', 'hash': 'hash'}
 for st in ['attend_bwd', 'attend_fwd', 'hash']:
   raw = subprocess.run(['ncu', '-i', 'gpurun_out/prof_%s_%s.ncu-rep' % (tag, st), '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
   rr = list(csv.reader(io.StringIO(raw))); hh, uu, r = rr[0], rr[1], rr[2]
-  full.append('== prof_r1_%s   (ncu --set full --clock-control none --import-source on, one launch of the C2 workload; tests/prof_stage.py %s)' % (st, st))
+  full.append('== prof_%s_%s   (ncu --set full --clock-control none --import-source on, one launch of the C2 workload; tests/prof_stage.py %s)' % (rnd, st, st))
   full.append('%-70s %s' % ('Kernel Name', r[hh.index('Kernel Name')]))
   for k in keys:
     if k in hh: full.append('%-70s %-16s %s' % (k, uu[hh.index(k)], r[hh.index(k)]))
   def val(k):
     return float(r[hh.index(k)].replace(',', '')) * {'Mbyte': 1e6, 'Gbyte': 1e9, 'Kbyte': 1e3, 'byte': 1}.get(uu[hh.index(k)], 1)
   traffic[names[st]] = {'kernel': r[hh.index('Kernel Name')].split('(')[0], 'bytes': int(val('dram__bytes_read.sum') + val('dram__bytes_write.sum'))}
-open('profiles/r1_ncu_full_summary.txt', 'w').write('\n'.join(full) + '\n')
-json.dump(traffic, open('profiles/r1_traffic.json', 'w'), indent=1)
+open('profiles/%s_ncu_full_summary.txt' % rnd, 'w').write('\n'.join(full) + '\n')
+json.dump(traffic, open('profiles/%s_traffic.json' % rnd, 'w'), indent=1)
 print('\n'.join(out))

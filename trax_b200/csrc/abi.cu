@@ -116,6 +116,21 @@ static int gemm_rm(bool ta, bool tb, int64_t M, int64_t N, int64_t K, const void
   return 0;
 }
 
+// Activation x weight product C[M, N] = A[M, K] · W: the hand-written tensor-core kernel (gemm_tc.cu) when the weight is
+// at hand K-major (`w_k`: (N, K)) and the shape fits it, cuBLAS otherwise (`w_n`: the (K, N) copy, or w_k transposed).
+int gemm_tc_run(int64_t M, int64_t N, int64_t K, const void *A, int64_t lda, const void *B, int64_t ldb, void *C, int64_t ldc,
+                bool c_f32, cudaStream_t stream);
+int transpose_bf16_run(const void *src, void *dst, int R, int C, cudaStream_t stream);
+static int gemm_aw(int64_t M, int64_t N, int64_t K, const void *A, int64_t lda, const void *w_k, const void *w_n, void *C,
+                   int64_t ldc, bool c_f32, void *cws, cudaStream_t stream) {
+  if (w_k) {
+    const int rc = gemm_tc_run(M, N, K, A, lda, w_k, K, C, ldc, c_f32, stream);
+    if (rc >= 0) return rc;
+  }
+  if (w_n) return gemm_rm(false, false, M, N, K, A, lda, w_n, N, C, ldc, c_f32, cws, stream);
+  return gemm_rm(false, true, M, N, K, A, lda, w_k, K, C, ldc, c_f32, cws, stream);
+}
+
 // ---- side stream of lsh_layer_bwd -----------------------------------------------------------------------
 // do = dout·w_o^T depends only on the packed weights and on dout, not on the forward recompute: it runs on an internal
 // stream (fork / join by events, no host wait; legal inside a stream capture) beside the recompute's latency-bound
@@ -162,7 +177,7 @@ struct Bump {
 };
 
 struct LayerWs {
-  void *cublas, *cublas2, *xb, *wqv, *wo, *qv, *o_rounds, *o_comb, *sort_ws, *doutb, *do_comb, *dqv, *bwd_ws, *keep_ws;
+  void *cublas, *cublas2, *xb, *wqv, *wo, *wqv_t, *wo_t, *qv, *o_rounds, *o_comb, *sort_ws, *doutb, *do_comb, *dqv, *bwd_ws, *keep_ws;
   int32_t *sticker;
   float *logits, *lse_tot, *dwqv;
   FwdAux aux;
@@ -178,6 +193,8 @@ static LayerWs carve(const LshAttnDims &d, void *ws, bool with_grad) {
   w.xb = d.act_dtype == LSH_DTYPE_F32 ? b.take(BL * d.D * 2) : nullptr;
   w.wqv = b.take(static_cast<size_t>(d.D) * d.H * dr.QV * 2);
   w.wo = b.take(static_cast<size_t>(d.H) * d.dv * d.D * 2);
+  w.wqv_t = b.take(static_cast<size_t>(d.D) * d.H * dr.QV * 2);      // K-major copies for the forward projections (gemm_tc.cu)
+  w.wo_t = b.take(static_cast<size_t>(d.H) * d.dv * d.D * 2);
   w.qv = b.take(BL * d.H * dr.QV * 2);
   w.aux = fwd_aux_carve(d, b.take(fwd_aux_bytes(d)));
   w.keep_ws = b.take(attn_keep_bytes(d));
@@ -201,6 +218,16 @@ static LayerWs carve(const LshAttnDims &d, void *ws, bool with_grad) {
   return w;
 }
 
+// Packed bf16 weights in both orientations: (D, H*QV) / (H*dv, D) for the weight-gradient and cuBLAS paths, and their
+// transposes (K-major for x·wqv and o·w_o) for the tensor-core GEMM.
+static int pack_layer_weights(const LshAttnDims &d, const LayerWs &w, const float *w_q, const float *w_v, const float *w_o,
+                              const float *w_k, cudaStream_t s) {
+  Derived dr = derive(d);
+  if (int rc = pack_weights_run(d, w_q, w_v, w_o, w_k, w.wqv, w.wo, s)) return rc;
+  if (int rc = transpose_bf16_run(w.wqv, w.wqv_t, d.D, d.H * dr.QV, s)) return rc;
+  return transpose_bf16_run(w.wo, w.wo_t, d.H * d.dv, d.D, s);
+}
+
 // Forward up to o_comb (EA:1923-1992 for all units).  Returns xb (bf16 view of x).
 static int forward_core(const LshAttnDims &d, const LayerWs &w, const void *x, const float *w_q, const float *w_v,
                         const float *w_o, const float *w_k, const float *rotations, const uint8_t *mask, const AttnKeep *keep, int32_t *buckets,
@@ -214,9 +241,9 @@ static int forward_core(const LshAttnDims &d, const LayerWs &w, const void *x, c
     xb = w.xb;
   }
   *xb_out = xb;
-  if (!weights_packed && (rc = pack_weights_run(d, w_q, w_v, w_o, w_k, w.wqv, w.wo, s))) return rc;
+  if (!weights_packed && (rc = pack_layer_weights(d, w, w_q, w_v, w_o, w_k, s))) return rc;
   const int64_t NQV = static_cast<int64_t>(d.H) * dr.QV;
-  if ((rc = gemm_rm(false, false, BL, NQV, d.D, xb, d.D, w.wqv, NQV, w.qv, NQV, false, w.cublas, s))) return rc;
+  if ((rc = gemm_aw(BL, NQV, d.D, xb, d.D, w.wqv_t, w.wqv, w.qv, NQV, false, w.cublas, s))) return rc;
   bool scales_done = false;
   if (rotations) {
     if (attend_fwd_uses_tc(d) && hash_can_fuse_aux(d)) {
@@ -273,8 +300,15 @@ int lsh_project_qv(const LshAttnDims *dims, const void *x_bf16, const void *wqv,
   if (int rc = check_dims(dims, false)) return rc;
   const LshAttnDims &d = *dims;
   const int64_t BL = static_cast<int64_t>(d.B) * d.L, NQV = static_cast<int64_t>(d.H) * derive(d).QV;
-  return gemm_rm(false, false, BL, NQV, d.D, x_bf16, d.D, wqv, NQV, qv, NQV, false,
-                 ws_bytes >= kCublasWs ? ws : nullptr, static_cast<cudaStream_t>(stream));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const void *wt = nullptr;                                          // K-major copy in the workspace tail, if there is room
+  const size_t wbytes = static_cast<size_t>(d.D) * NQV * 2;
+  if (ws && ws_bytes >= kCublasWs + wbytes + 256) {
+    void *t = static_cast<char *>(ws) + kCublasWs;
+    if (int rc = transpose_bf16_run(wqv, t, d.D, static_cast<int>(NQV), s)) return rc;
+    wt = t;
+  }
+  return gemm_aw(BL, NQV, d.D, x_bf16, d.D, wt, wqv, qv, NQV, false, ws_bytes >= kCublasWs ? ws : nullptr, s);
 }
 
 int lsh_hash(const LshAttnDims *dims, const void *qv, const float *rotations, const uint8_t *mask, int32_t *buckets,
@@ -333,8 +367,15 @@ int lsh_project_out(const LshAttnDims *dims, const void *o_comb, const void *wo,
   if (int rc = check_dims(dims, false)) return rc;
   const LshAttnDims &d = *dims;
   const int64_t BL = static_cast<int64_t>(d.B) * d.L, KO = static_cast<int64_t>(d.H) * d.dv;
-  return gemm_rm(false, false, BL, d.D, KO, o_comb, KO, wo, d.D, out, d.D, d.act_dtype == LSH_DTYPE_F32,
-                 ws_bytes >= kCublasWs ? ws : nullptr, static_cast<cudaStream_t>(stream));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const void *wt = nullptr;
+  const size_t wbytes = static_cast<size_t>(KO) * d.D * 2;
+  if (ws && ws_bytes >= kCublasWs + wbytes + 256) {
+    void *t = static_cast<char *>(ws) + kCublasWs;
+    if (int rc = transpose_bf16_run(wo, t, static_cast<int>(KO), d.D, s)) return rc;
+    wt = t;
+  }
+  return gemm_aw(BL, d.D, KO, o_comb, KO, wt, wo, out, d.D, d.act_dtype == LSH_DTYPE_F32, ws_bytes >= kCublasWs ? ws : nullptr, s);
 }
 
 size_t lsh_attend_bwd_workspace_bytes(const LshAttnDims *dims) {
@@ -375,7 +416,7 @@ int lsh_layer_fwd(const LshAttnDims *dims, const void *x, const float *w_q, cons
                             &xb, s))
     return rc;
   const int64_t BL = static_cast<int64_t>(d.B) * d.L, KO = static_cast<int64_t>(d.H) * d.dv;
-  return gemm_rm(false, false, BL, d.D, KO, w.o_comb, KO, w.wo, d.D, out, d.D, d.act_dtype == LSH_DTYPE_F32, w.cublas, s);
+  return gemm_aw(BL, d.D, KO, w.o_comb, KO, w.wo_t, w.wo, out, d.D, d.act_dtype == LSH_DTYPE_F32, w.cublas, s);
 }
 
 int lsh_layer_bwd(const LshAttnDims *dims, const void *x, const float *w_q, const float *w_v, const float *w_o,
@@ -398,7 +439,7 @@ int lsh_layer_bwd(const LshAttnDims *dims, const void *x, const float *w_q, cons
   const int64_t NQV = static_cast<int64_t>(d.H) * dr.QV;
   const bool f32 = d.act_dtype == LSH_DTYPE_F32;
   // B1 (first half) on the side stream: do = dout·w_o^T
-  if ((rc = pack_weights_run(d, w_q, w_v, w_o, w_k, w.wqv, w.wo, s))) return rc;
+  if ((rc = pack_layer_weights(d, w, w_q, w_v, w_o, w_k, s))) return rc;
   SideStream *side = side_stream();
   if (!side) return set_error("lsh_layer_bwd: could not create the internal stream");
   LSH_CUDA_OK(cudaEventRecord(side->fork, s));
@@ -408,7 +449,7 @@ int lsh_layer_bwd(const LshAttnDims *dims, const void *x, const float *w_q, cons
     if ((rc = f32_to_bf16_run(static_cast<const float *>(dout), w.doutb, BL * d.D, side->stream))) return rc;
     doutb = w.doutb;
   }
-  if ((rc = gemm_rm(false, true, BL, KO, d.D, doutb, d.D, w.wo, d.D, w.do_comb, KO, false, w.cublas2, side->stream))) return rc;
+  if ((rc = gemm_aw(BL, KO, d.D, doutb, d.D, w.wo, nullptr, w.do_comb, KO, false, w.cublas2, side->stream))) return rc;
   LSH_CUDA_OK(cudaEventRecord(side->join, side->stream));
   // forward recompute on the caller's stream
   AttnKeep keep;
@@ -418,7 +459,7 @@ int lsh_layer_bwd(const LshAttnDims *dims, const void *x, const float *w_q, cons
                          &xb, s, /*weights_packed=*/true)))
     return rc;
   if (out) {
-    if ((rc = gemm_rm(false, false, BL, d.D, KO, w.o_comb, KO, w.wo, d.D, out, d.D, f32, w.cublas, s))) return rc;
+    if ((rc = gemm_aw(BL, d.D, KO, w.o_comb, KO, w.wo_t, w.wo, out, d.D, f32, w.cublas, s))) return rc;
   }
   LSH_CUDA_OK(cudaStreamWaitEvent(s, side->join, 0));
   // B1 (second half): dW_o = o^T·dout
@@ -431,7 +472,7 @@ int lsh_layer_bwd(const LshAttnDims *dims, const void *x, const float *w_q, cons
   if ((rc = gemm_rm(true, false, d.D, NQV, BL, xb, d.D, w.dqv, NQV, w.dwqv, NQV, true, w.cublas, s))) return rc;
   if ((rc = unpack_dwqv_run(d, w.dwqv, dw_q, dw_v, dw_k, s))) return rc;
   if (ev_dwqv_ready) LSH_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(ev_dwqv_ready), s));
-  return gemm_rm(false, true, BL, d.D, NQV, w.dqv, NQV, w.wqv, NQV, dx, d.D, f32, w.cublas, s);
+  return gemm_aw(BL, d.D, NQV, w.dqv, NQV, w.wqv, nullptr, dx, d.D, f32, w.cublas, s);
 }
 
 int lsh_layernorm_fwd(int64_t rows, int d_model, int act_dtype, const void *x, const float *scale, const float *bias, void *z,
@@ -479,7 +520,8 @@ int lsh_make_rotations(const LshAttnDims *dims, const uint32_t *keys, uint32_t *
 
 // ---- TMA descriptor encoder (driver entry point fetched through the runtime: no link-time dependency on libcuda) ------
 namespace lsh {
-int make_row_gather_map(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes, uint32_t box_cols) {
+int make_tile_map(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes, uint32_t box_cols,
+                  uint32_t box_rows) {
   using EncodeFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -495,7 +537,7 @@ int make_row_gather_map(CUtensorMap *map, const void *base, uint64_t rows, uint6
   if ((reinterpret_cast<uintptr_t>(base) & 15) || (pitch_bytes & 15)) return set_error("TMA: base / pitch must be 16-byte aligned");
   const cuuint64_t dims[2] = {cols, rows};
   const cuuint64_t strides[1] = {pitch_bytes};
-  const cuuint32_t box[2] = {box_cols, 1};
+  const cuuint32_t box[2] = {box_cols, box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -503,4 +545,14 @@ int make_row_gather_map(CUtensorMap *map, const void *base, uint64_t rows, uint6
   if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
   return 0;
 }
+int make_row_gather_map(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes, uint32_t box_cols) {
+  return make_tile_map(map, base, rows, cols, pitch_bytes, box_cols, 1);
+}
 }  // namespace lsh
+
+/* Test hook (not in the public header): the tensor-core GEMM of gemm_tc.cu on caller-supplied operands,
+ * C[M, N] = A[M, K] · B[N, K]^T (bf16 in, bf16 or f32 out).  Returns -1 when the kernel does not cover the shape. */
+extern "C" int lsh_debug_gemm_tc(int64_t M, int64_t N, int64_t K, const void *A, int64_t lda, const void *B, int64_t ldb, void *C,
+                                 int64_t ldc, int c_f32, void *stream) {
+  return lsh::gemm_tc_run(M, N, K, A, lda, B, ldb, C, ldc, c_f32 != 0, static_cast<cudaStream_t>(stream));
+}

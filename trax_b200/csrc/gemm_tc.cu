@@ -1,0 +1,260 @@
+// Dense projections of the layer on the 5th-generation tensor cores — C[M, N] = A[M, K] · B[N, K]^T, bf16 operands (both
+// K-major: rows of K contiguous elements), fp32 accumulation in TMEM, C bf16 or fp32 — for the activation x weight products
+// of the path:  q|v(|k) = x · wqv (EA:1923-1924),  out = o · w_o (EA:1995, heads summed by the contraction, EA:2426) and, in the
+// backward pass,  do = dout · w_o^T  and  dx = dqv · wqv^T  (the weight operand is packed K-major for each of them by
+// pack.cu, so one kernel serves all four).
+//
+// Persistent, warp-specialised, TMA-fed:
+//   warp 0   producer: one elected lane issues `cp.async.bulk.tensor.2d` tile loads (SWIZZLE_128B boxes of 64 K-elements x
+//            128 rows) into a 4-stage ring; completion = transaction bytes on the stage's `full` mbarrier.
+//   warp 1   MMA issuer: per K block of 64, four `tcgen05.mma.kind::f16` M128 x N{256,128} x K16 on shared-memory descriptors,
+//            accumulating into one of TWO TMEM accumulators (2 x N columns); `tcgen05.commit` frees the stage / hands the
+//            finished accumulator to the epilogue.
+//   warps 2-5 epilogue: TMEM -> registers (32 columns at a time, next load in flight) -> bf16 / fp32 rows in global memory,
+//            while the issuer is already accumulating the next tile in the other accumulator.
+// CLUSTER = 2: the two CTAs of a cluster compute vertically adjacent tiles (same n block) and SHARE the weight tile: each
+// loads half of it and multicasts it into both shared memories (`.multicast::cluster`), which halves the L2 -> SM traffic of
+// the B operand (a 1-CTA 128 x 256 tile needs 94 B/clk/SM from L2 against ~43 B/clk/SM available chip-wide,
+// B300_MICROARCH.md "LTS throughput cap"); a stage is refilled only after BOTH CTAs' MMAs have read it (commit multicast).
+// Shapes the kernel does not cover (N % 128, K % 64, unaligned pointers) are reported to the caller, which then uses cuBLAS.
+#include <stdlib.h>
+#include <string.h>
+
+#include "tc_common.cuh"
+
+namespace lsh {
+
+constexpr int GM_BM = 128, GM_BK = 64, GM_STAGES = 4, GM_THREADS = 192;
+
+struct GemmTcParams {
+  CUtensorMap tm_a, tm_b;
+  void *c;
+  int64_t ldc;
+  int M, N, K, c_f32, m_blocks, n_blocks;
+};
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;\n"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
+               ::"r"(smem_u32(bar)), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
+struct __align__(16) GemmShared {
+  uint64_t full[GM_STAGES], empty[GM_STAGES], acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+
+template <int BN, int CL>
+__global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int A_BYTES = GM_BM * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+  __shared__ GemmShared sh;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
+  const uint32_t smem_u = smem_u32(smem);
+
+  if (warp == 1) tmem_alloc(&sh.tmem_base, 512);
+  if (tid == 0) {
+    tma_prefetch_desc(&p.tm_a);
+    tma_prefetch_desc(&p.tm_b);
+    for (int i = 0; i < GM_STAGES; ++i) { mbar_init(&sh.full[i], 1); mbar_init(&sh.empty[i], CL); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sh.acc_full[i], 1); mbar_init(&sh.acc_empty[i], 4); }
+    fence_mbar_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (CL > 1) cluster_sync_all();          // the peer's barriers exist before anything is multicast to them
+  tc_fence_after();
+  const uint32_t tmem = sh.tmem_base;
+
+  const int n_clusters = gridDim.x / CL, cid = blockIdx.x / CL;
+  const int m_groups = (p.m_blocks + CL - 1) / CL, total = m_groups * p.n_blocks, kb_n = p.K / GM_BK;
+
+  if (warp == 0) {
+    // ================================ TMA producer ======================================================
+    int it = 0;                                                     // k-block counter across tiles (ring position)
+    for (int g = cid; g < total; g += n_clusters) {
+      const int n_blk = g % p.n_blocks, m_blk = (g / p.n_blocks) * CL + static_cast<int>(rank);
+      for (int kb = 0; kb < kb_n; ++kb, ++it) {
+        const int s = it % GM_STAGES;
+        mbar_wait(&sh.empty[s], ((it / GM_STAGES) & 1) ^ 1);
+        if (elect_one()) {
+          const uint32_t a_dst = smem_u + s * STAGE_BYTES, b_dst = a_dst + A_BYTES;
+          mbar_arrive_expect_tx(&sh.full[s], STAGE_BYTES);
+          tma_load_2d(a_dst, &p.tm_a, &sh.full[s], kb * GM_BK, m_blk * GM_BM);     // rows past M read as zeros
+          if (CL == 1) {
+            tma_load_2d(b_dst, &p.tm_b, &sh.full[s], kb * GM_BK, n_blk * BN);
+          } else {                                                   // my half of the weight tile, into both CTAs
+            tma_load_2d_mc(b_dst + rank * (B_BYTES / 2), &p.tm_b, &sh.full[s], kb * GM_BK, n_blk * BN + rank * (BN / 2),
+                           static_cast<uint16_t>((1u << CL) - 1));
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer =======================================================
+    constexpr uint32_t HI = desc_hi(1024);
+    constexpr uint32_t IDESC = make_idesc_bf16(GM_BM, BN, 0, 0);
+    int it = 0, t = 0;
+    for (int g = cid; g < total; g += n_clusters, ++t) {
+      const int acc = t & 1;
+      mbar_wait(&sh.acc_empty[acc], ((t >> 1) & 1) ^ 1);            // the epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_t = tmem + acc * BN;
+      for (int kb = 0; kb < kb_n; ++kb, ++it) {
+        const int s = it % GM_STAGES;
+        mbar_wait(&sh.full[s], (it / GM_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t a_lo = desc_lo(smem_u + s * STAGE_BYTES, 16), b_lo = desc_lo(smem_u + s * STAGE_BYTES + A_BYTES, 16);
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < GM_BK / 16; ++ks) umma_ss2(d_t, a_lo + ks * 2, HI, b_lo + ks * 2, HI, IDESC, (kb | ks) != 0);
+          if (CL == 1) umma_commit(&sh.empty[s]);
+          else umma_commit_mc(&sh.empty[s], static_cast<uint16_t>((1u << CL) - 1));
+          if (kb == kb_n - 1) umma_commit(&sh.acc_full[acc]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ================================ epilogue warps ====================================================
+    const int q = warp & 3;                                          // TMEM lane quarter of this warp
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>(q * 32) << 16);
+    int t = 0;
+    for (int g = cid; g < total; g += n_clusters, ++t) {
+      const int acc = t & 1;
+      const int n_blk = g % p.n_blocks, m_blk = (g / p.n_blocks) * CL + static_cast<int>(rank);
+      const int64_t row = static_cast<int64_t>(m_blk) * GM_BM + q * 32 + lane;
+      const bool live = row < p.M;
+      mbar_wait(&sh.acc_full[acc], (t >> 1) & 1);
+      tc_fence_after();
+      uint32_t ra[32], rb[32];
+      tmem_ld32(t_lane + acc * BN, ra);
+      auto store = [&](const uint32_t (&r)[32], int c) {
+        if (!live) return;
+        const int64_t col = static_cast<int64_t>(n_blk) * BN + c * 32;
+        if (p.c_f32) {
+          float4 *dst = reinterpret_cast<float4 *>(static_cast<float *>(p.c) + row * p.ldc + col);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                                 __uint_as_float(r[4 * i + 3]));
+        } else {
+          uint4 *dst = reinterpret_cast<uint4 *>(static_cast<__nv_bfloat16 *>(p.c) + row * p.ldc + col);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 v;
+            v.x = pack_bf16(__uint_as_float(r[8 * i]), __uint_as_float(r[8 * i + 1]));
+            v.y = pack_bf16(__uint_as_float(r[8 * i + 2]), __uint_as_float(r[8 * i + 3]));
+            v.z = pack_bf16(__uint_as_float(r[8 * i + 4]), __uint_as_float(r[8 * i + 5]));
+            v.w = pack_bf16(__uint_as_float(r[8 * i + 6]), __uint_as_float(r[8 * i + 7]));
+            dst[i] = v;
+          }
+        }
+      };
+#pragma unroll
+      for (int c = 0; c < BN / 32; c += 2) {
+        tmem_ld_wait_dep(ra);
+        tmem_ld32(t_lane + acc * BN + (c + 1) * 32, rb);
+        store(ra, c);
+        tmem_ld_wait_dep(rb);
+        if (c + 2 < BN / 32) tmem_ld32(t_lane + acc * BN + (c + 2) * 32, ra);
+        store(rb, c + 1);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh.acc_empty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (CL > 1) cluster_sync_all();          // no CTA leaves while its peer may still multicast into it
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+int make_tile_map(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes, uint32_t box_cols,
+                  uint32_t box_rows);
+
+template <int BN, int CL>
+static int gemm_tc_launch(const GemmTcParams &p, cudaStream_t stream) {
+  const size_t smem = static_cast<size_t>(GM_STAGES) * (GM_BM * 128 + BN * 128) + 1024;
+  auto kernel = gemm_tc_kernel<BN, CL>;
+  LSH_OPT_IN_SMEM(kernel);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int groups = ((p.m_blocks + CL - 1) / CL) * p.n_blocks;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  cfg.blockDim = dim3(GM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  int n_clusters = sms / CL;
+  if (CL > 1) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.gridDim = dim3(sms / CL * CL);
+    static thread_local int max_clusters[64] = {};
+    if (dev < 64 && max_clusters[dev] == 0) {
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = sms / CL / 2; }
+      max_clusters[dev] = n;
+    }
+    if (dev < 64 && max_clusters[dev] < n_clusters) n_clusters = max_clusters[dev];
+  }
+  if (groups < n_clusters) n_clusters = groups;
+  cfg.gridDim = dim3(n_clusters * CL);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, p);
+  if (e != cudaSuccess) return set_error("gemm_tc_kernel launch: %s", cudaGetErrorString(e));
+  count_launch();
+  return 0;
+}
+
+// A[M, K] (row pitch lda elements) · B[N, K]^T (row pitch ldb) -> C[M, N] (row pitch ldc), bf16 in, bf16 or f32 out.
+// Returns 0 on launch, > 0 on error, -1 when the shape is outside what the kernel covers (the caller falls back to cuBLAS).
+int gemm_tc_run(int64_t M, int64_t N, int64_t K, const void *A, int64_t lda, const void *B, int64_t ldb, void *C, int64_t ldc,
+                bool c_f32, cudaStream_t stream) {
+  static const int mode = [] {        // LSH_GEMM=cublas: library GEMMs everywhere; LSH_GEMM=cluster1: no weight-tile multicast
+    const char *e = getenv("LSH_GEMM");
+    if (!e) return 2;
+    if (strcmp(e, "cublas") == 0) return 0;
+    if (strcmp(e, "cluster1") == 0) return 1;
+    return 2;
+  }();
+  if (mode == 0) return -1;
+  if (N % 128 != 0 || K % GM_BK != 0 || M < 1 || M >= (1ll << 31) || lda % 8 != 0 || ldb % 8 != 0 || ldc % 8 != 0) return -1;
+  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C)) & 15) return -1;
+  const int bn = (N % 256 == 0) ? 256 : 128;
+  GemmTcParams p;
+  p.c = C; p.ldc = ldc; p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K); p.c_f32 = c_f32 ? 1 : 0;
+  p.m_blocks = static_cast<int>((M + GM_BM - 1) / GM_BM); p.n_blocks = static_cast<int>(N / bn);
+  const int cl = (mode == 2 && p.m_blocks >= 2) ? 2 : 1;
+  if (int rc = make_tile_map(&p.tm_a, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda) * 2, GM_BK, GM_BM)) return rc;
+  if (int rc = make_tile_map(&p.tm_b, B, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldb) * 2, GM_BK, bn / cl)) return rc;
+  if (bn == 256) return cl == 2 ? gemm_tc_launch<256, 2>(p, stream) : gemm_tc_launch<256, 1>(p, stream);
+  return cl == 2 ? gemm_tc_launch<128, 2>(p, stream) : gemm_tc_launch<128, 1>(p, stream);
+}
+
+}  // namespace lsh

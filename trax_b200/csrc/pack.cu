@@ -120,6 +120,25 @@ int pack_weights_run(const LshAttnDims &d, const float *w_q, const float *w_v, c
   return 0;
 }
 
+// src (R, C) bf16 -> dst (C, R) bf16: the K-major copy of a packed weight for the tensor-core GEMM (weights only: a few MB)
+__global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16 *__restrict__ src, __nv_bfloat16 *__restrict__ dst,
+                                                             int R, int C) {
+  __shared__ __nv_bfloat16 tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8)
+    if (r0 + i < R && c0 + tx < C) tile[i][tx] = src[static_cast<int64_t>(r0 + i) * C + c0 + tx];
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8)
+    if (c0 + i < C && r0 + tx < R) dst[static_cast<int64_t>(c0 + i) * R + r0 + tx] = tile[tx][i];
+}
+
+int transpose_bf16_run(const void *src, void *dst, int R, int C, cudaStream_t stream) {
+  dim3 grid((C + 31) / 32, (R + 31) / 32);
+  transpose_bf16_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(src), static_cast<__nv_bfloat16 *>(dst), R, C);
+  LSH_CHECK_LAUNCH("transpose_bf16_kernel");
+  return 0;
+}
+
 int f32_to_bf16_run(const float *src, void *dst, int64_t n, cudaStream_t stream) {
   f32_to_bf16_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, stream>>>(src, static_cast<__nv_bfloat16 *>(dst), n);
   LSH_CHECK_LAUNCH("f32_to_bf16_kernel");

@@ -77,7 +77,7 @@ def pack_weights(dims, w_q, w_v, w_o, w_k=None):
 def project_qv(dims, x_bf16, wqv):
   lib = _lib.load()
   qv = torch.empty((dims.B, dims.L, dims.H, _row_width(dims)), dtype=torch.bfloat16, device=x_bf16.device)
-  ws = workspace(x_bf16.device, 32 << 20)
+  ws = workspace(x_bf16.device, 64 << 20)     # cuBLAS scratch + the K-major weight copy of the tensor-core GEMM
   _lib.check(lib.lsh_project_qv(ctypes.byref(dims), _ptr(x_bf16), _ptr(wqv), _ptr(qv), _ptr(ws), ws.numel(),
                                 _stream()), 'lsh_project_qv')
   return qv
