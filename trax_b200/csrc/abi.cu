@@ -118,14 +118,16 @@ static int gemm_rm(bool ta, bool tb, int64_t M, int64_t N, int64_t K, const void
 
 // Activation x weight product C[M, N] = A[M, K] · W: the hand-written tensor-core kernel (gemm_tc.cu) when the weight is
 // at hand K-major (`w_k`: (N, K)) and the shape fits it, cuBLAS otherwise (`w_n`: the (K, N) copy, or w_k transposed).
-int gemm_tc_run(int64_t M, int64_t N, int64_t K, const void *A, int64_t lda, const void *B, int64_t ldb, void *C, int64_t ldc,
-                bool c_f32, cudaStream_t stream);
 int transpose_bf16_run(const void *src, void *dst, int R, int C, cudaStream_t stream);
 static int gemm_aw(int64_t M, int64_t N, int64_t K, const void *A, int64_t lda, const void *w_k, const void *w_n, void *C,
-                   int64_t ldc, bool c_f32, void *cws, cudaStream_t stream) {
+                   int64_t ldc, bool c_f32, void *cws, cudaStream_t stream, const GemmQStats *qs = nullptr, bool *qs_done = nullptr) {
+  if (qs_done) *qs_done = false;
   if (w_k) {
-    const int rc = gemm_tc_run(M, N, K, A, lda, w_k, K, C, ldc, c_f32, stream);
-    if (rc >= 0) return rc;
+    const int rc = gemm_tc_run(M, N, K, A, lda, w_k, K, C, ldc, c_f32, stream, qs);
+    if (rc >= 0) {
+      if (qs_done) *qs_done = rc == 0 && qs != nullptr;
+      return rc;
+    }
   }
   if (w_n) return gemm_rm(false, false, M, N, K, A, lda, w_n, N, C, ldc, c_f32, cws, stream);
   return gemm_rm(false, true, M, N, K, A, lda, w_k, K, C, ldc, c_f32, cws, stream);
@@ -243,10 +245,14 @@ static int forward_core(const LshAttnDims &d, const LayerWs &w, const void *x, c
   *xb_out = xb;
   if (!weights_packed && (rc = pack_layer_weights(d, w, w_q, w_v, w_o, w_k, s))) return rc;
   const int64_t NQV = static_cast<int64_t>(d.H) * dr.QV;
-  if ((rc = gemm_aw(BL, NQV, d.D, xb, d.D, w.wqv_t, w.wqv, w.qv, NQV, false, w.cublas, s))) return rc;
+  // tcgen05 attention path: the key scales / normalised keys come out of the projection's epilogue (fp32 accumulator ->
+  // bf16 q -> statistics, in the registers that already hold the row)
   bool scales_done = false;
+  GemmQStats qs = {w.aux.qscale, w.aux.rowmeta, w.aux.qhat, d.L, d.H};
+  const bool want_qs = attend_fwd_uses_tc(d) && !d.separate_k;
+  if ((rc = gemm_aw(BL, NQV, d.D, xb, d.D, w.wqv_t, w.wqv, w.qv, NQV, false, w.cublas, s, want_qs ? &qs : nullptr, &scales_done))) return rc;
   if (rotations) {
-    if (attend_fwd_uses_tc(d) && hash_can_fuse_aux(d)) {
+    if (!scales_done && attend_fwd_uses_tc(d) && hash_can_fuse_aux(d)) {
       if ((rc = hash_bf16_qv_aux(d, w.qv, rotations, mask, buckets, bstride, w.aux.qscale, w.aux.rowmeta, w.aux.qhat, s))) return rc;
       scales_done = true;
     } else if ((rc = hash_bf16_qv(d, w.qv, rotations, mask, buckets, bstride, s))) {

@@ -31,6 +31,13 @@ struct GemmTcParams {
   void *c;
   int64_t ldc;
   int M, N, K, c_f32, m_blocks, n_blocks;
+  // q|v projection only (all null otherwise): the per-token key normalisation of EA:229-231 straight from the epilogue — for
+  // every (token, head) whose 64 q columns this thread has just rounded to bf16: qscale = log2e / (8 r), the normalised key
+  // qhat = bf16(q / (8 r)) and rowmeta = {8 r log2e, that times |qhat|^2}, r = sqrt(mean(q^2) + 1e-6) (see qscale_kernel)
+  float *qscale;
+  float2 *rowmeta;
+  __nv_bfloat16 *qhat;
+  int L, H;
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
@@ -151,8 +158,52 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
       tc_fence_after();
       uint32_t ra[32], rb[32];
       tmem_ld32(t_lane + acc * BN, ra);
+      uint32_t qlo[16];                                              // first half of a head's q row, as stored (bf16 pairs)
+      float qss = 0.f;
+      // key normalisation of one head from the bf16 values just stored: `c` = chunk of 32 columns; a head owns 4 chunks,
+      // q | q | v | v (columns [128 h', 128 h' + 64) are its q)
+      auto q_stats = [&](const uint32_t (&r)[32], int c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          pk[i] = pack_bf16(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+          const float2 f = unpack_bf16(pk[i]);
+          qss = fmaf(f.x, f.x, qss); qss = fmaf(f.y, f.y, qss);
+        }
+        if ((c & 1) == 0) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) qlo[i] = pk[i];
+          return;
+        }
+        const float rr = sqrtf(qss * (1.0f / 64) + 1e-6f), sc = 0.125f / rr;
+        qss = 0.f;
+        const int h = n_blk * (BN / 128) + (c >> 2);
+        const int64_t b = row / p.L, ut = (b * p.H + h) * p.L + (row - b * p.L);
+        float s2 = 0.f;
+        uint4 *dst = reinterpret_cast<uint4 *>(p.qhat + ut * 64);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = unpack_bf16(half ? pk[4 * i + e] : qlo[4 * i + e]);
+              o[e] = pack_bf16(f.x * sc, f.y * sc);
+              const float2 g = unpack_bf16(o[e]);                     // |qhat|^2 of the rounded values the tensor cores see
+              s2 = fmaf(g.x, g.x, s2); s2 = fmaf(g.y, g.y, s2);
+            }
+            uint4 v; v.x = o[0]; v.y = o[1]; v.z = o[2]; v.w = o[3];
+            dst[half * 4 + i] = v;
+          }
+        }
+        p.qscale[ut] = 0.125f * kLog2e / rr;
+        const float am = 8.f * rr * kLog2e;
+        p.rowmeta[ut] = make_float2(am, am * s2);
+      };
       auto store = [&](const uint32_t (&r)[32], int c) {
         if (!live) return;
+        if (p.qhat != nullptr && (c & 2) == 0) q_stats(r, c);
         const int64_t col = static_cast<int64_t>(n_blk) * BN + c * 32;
         if (p.c_f32) {
           float4 *dst = reinterpret_cast<float4 *>(static_cast<float *>(p.c) + row * p.ldc + col);
@@ -235,7 +286,7 @@ static int gemm_tc_launch(const GemmTcParams &p, cudaStream_t stream) {
 // A[M, K] (row pitch lda elements) · B[N, K]^T (row pitch ldb) -> C[M, N] (row pitch ldc), bf16 in, bf16 or f32 out.
 // Returns 0 on launch, > 0 on error, -1 when the shape is outside what the kernel covers (the caller falls back to cuBLAS).
 int gemm_tc_run(int64_t M, int64_t N, int64_t K, const void *A, int64_t lda, const void *B, int64_t ldb, void *C, int64_t ldc,
-                bool c_f32, cudaStream_t stream) {
+                bool c_f32, cudaStream_t stream, const GemmQStats *qs) {
   static const int mode = [] {        // LSH_GEMM=cublas: library GEMMs everywhere; LSH_GEMM=cluster1: no weight-tile multicast
     const char *e = getenv("LSH_GEMM");
     if (!e) return 2;
@@ -250,6 +301,11 @@ int gemm_tc_run(int64_t M, int64_t N, int64_t K, const void *A, int64_t lda, con
   GemmTcParams p;
   p.c = C; p.ldc = ldc; p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K); p.c_f32 = c_f32 ? 1 : 0;
   p.m_blocks = static_cast<int>((M + GM_BM - 1) / GM_BM); p.n_blocks = static_cast<int>(N / bn);
+  p.qscale = nullptr; p.rowmeta = nullptr; p.qhat = nullptr; p.L = 1; p.H = 1;
+  if (qs) {           // fused key normalisation: rows are (b, t), columns (h, q | v) — needs bf16 output of 128-column heads
+    if (c_f32 || N != static_cast<int64_t>(qs->H) * 128) return set_error("gemm_tc: q statistics need the (B L, H 128) bf16 projection");
+    p.qscale = qs->qscale; p.rowmeta = qs->rowmeta; p.qhat = static_cast<__nv_bfloat16 *>(qs->qhat); p.L = qs->L; p.H = qs->H;
+  }
   const int cl = (mode == 2 && p.m_blocks >= 2) ? 2 : 1;
   if (int rc = make_tile_map(&p.tm_a, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda) * 2, GM_BK, GM_BM)) return rc;
   if (int rc = make_tile_map(&p.tm_b, B, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldb) * 2, GM_BK, bn / cl)) return rc;

@@ -14,6 +14,16 @@ namespace lsh {
 // SM100_TMA_LOAD_2D_GATHER4, cute/atom/copy_traits_sm90_tma.hpp).
 int make_row_gather_map(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes, uint32_t box_cols);
 
+// Optional epilogue of the q|v projection GEMM (gemm_tc.cu): per-token key scales / normalised keys, see GemmTcParams.
+struct GemmQStats {
+  float *qscale;
+  float2 *rowmeta;
+  void *qhat;
+  int L, H;
+};
+int gemm_tc_run(int64_t M, int64_t N, int64_t K, const void *A, int64_t lda, const void *B, int64_t ldb, void *C, int64_t ldc,
+                bool c_f32, cudaStream_t stream, const GemmQStats *qs = nullptr);
+
 #ifdef __CUDACC__
 
 // ---- TMA (device) -------------------------------------------------------------------------------------
