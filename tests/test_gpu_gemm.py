@@ -49,6 +49,36 @@ def test_gemm_tc_matches_fp32_matmul(M, N, K, out_dtype):
     torch.testing.assert_close(c.float(), want.bfloat16().float(), rtol=1.6e-2, atol=1e-2)   # one bf16 rounding apart
 
 
+@pytest.mark.parametrize('M,N,K', [
+    (128, 128, 64),              # one tile, one K block, no split
+    (256, 256, 4096),            # one cluster of tiles, K split over the machine
+    (512, 1024, 8192),           # dW_o shape (H d_v, d_model)
+    (1024, 1024, 4096),          # dW_q|v shape
+    (384, 384, 1024),            # odd row-block count (no cluster partner), 3 column blocks of 128
+])
+def test_gemm_tc_wgrad_matches_fp32_matmul(M, N, K):
+  """dW = act^T · cotangent (EA:2431 / the VJP of EA:1923-1924, 1995): MN-major operands, K split over the clusters, fp32
+  partial sums added in a fixed order."""
+  from trax_b200 import _lib, ops
+  lib = _lib.load()
+  fn = lib.lsh_debug_gemm_tc_wgrad
+  fn.restype = ctypes.c_int
+  fn.argtypes = [ctypes.c_int64] * 3 + [ctypes.c_void_p] * 4 + [ctypes.c_size_t, ctypes.c_void_p]
+  g = torch.Generator('cuda').manual_seed(M + N + K)
+  a = torch.randn((K, M), device='cuda', generator=g).bfloat16()
+  b = torch.randn((K, N), device='cuda', generator=g).bfloat16()
+  c = torch.full((M, N), float('nan'), dtype=torch.float32, device='cuda')
+  scratch = torch.empty(32 << 20, dtype=torch.uint8, device='cuda')
+  outs = []
+  for _ in range(2):
+    assert fn(M, N, K, a.data_ptr(), b.data_ptr(), c.data_ptr(), scratch.data_ptr(), scratch.numel(), ops._stream()) == 0
+    torch.cuda.synchronize()
+    outs.append(c.clone())
+  assert torch.equal(outs[0], outs[1])                               # deterministic (no atomics)
+  want = a.float().t() @ b.float()
+  torch.testing.assert_close(c, want, rtol=2e-4, atol=2e-2 * (K / 4096) ** 0.5)
+
+
 def test_gemm_tc_declines_shapes_it_does_not_cover():
   a = torch.zeros((128, 72), device='cuda', dtype=torch.bfloat16)
   b = torch.zeros((128, 72), device='cuda', dtype=torch.bfloat16)

@@ -133,6 +133,13 @@ static int gemm_aw(int64_t M, int64_t N, int64_t K, const void *A, int64_t lda, 
   return gemm_rm(false, true, M, N, K, A, lda, w_k, K, C, ldc, c_f32, cws, stream);
 }
 
+// Weight gradient C[M, N] (f32) = A^T · B, A (K, M), B (K, N) bf16: the split-K tensor-core kernel, else cuBLAS.
+static int gemm_wgrad(int64_t M, int64_t N, int64_t K, const void *A, const void *B, float *C, void *cws, cudaStream_t stream) {
+  const int rc = gemm_tc_wgrad_run(M, N, K, A, M, B, N, C, cws, cws ? kCublasWs : 0, stream);
+  if (rc >= 0) return rc;
+  return gemm_rm(true, false, M, N, K, A, M, B, N, C, N, true, cws, stream);
+}
+
 // ---- side stream of lsh_layer_bwd -----------------------------------------------------------------------
 // do = dout·w_o^T depends only on the packed weights and on dout, not on the forward recompute: it runs on an internal
 // stream (fork / join by events, no host wait; legal inside a stream capture) beside the recompute's latency-bound
@@ -469,13 +476,13 @@ int lsh_layer_bwd(const LshAttnDims *dims, const void *x, const float *w_q, cons
   }
   LSH_CUDA_OK(cudaStreamWaitEvent(s, side->join, 0));
   // B1 (second half): dW_o = o^T·dout
-  if ((rc = gemm_rm(true, false, KO, d.D, BL, w.o_comb, KO, doutb, d.D, dw_o, d.D, true, w.cublas, s))) return rc;
+  if ((rc = gemm_wgrad(KO, d.D, BL, w.o_comb, doutb, dw_o, w.cublas, s))) return rc;
   if (ev_dwo_ready) LSH_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(ev_dwo_ready), s));
   // B2-B6
   if ((rc = attend_bwd_run(d, w.qv, w.sticker, mask, w.o_comb, w.lse_tot, w.do_comb, w.aux.qscale, attend_fwd_uses_tc(d) ? w.aux.sticker2 : nullptr, attend_fwd_uses_tc(d) ? w.aux.bounds : nullptr, kp, w.dqv, w.bwd_ws, w.bwd_bytes, s)))
     return rc;
   // B7: dW_q|dW_v = x^T·dqv ; dx = dqv·wqv^T
-  if ((rc = gemm_rm(true, false, d.D, NQV, BL, xb, d.D, w.dqv, NQV, w.dwqv, NQV, true, w.cublas, s))) return rc;
+  if ((rc = gemm_wgrad(d.D, NQV, BL, xb, w.dqv, w.dwqv, w.cublas, s))) return rc;
   if ((rc = unpack_dwqv_run(d, w.dwqv, dw_q, dw_v, dw_k, s))) return rc;
   if (ev_dwqv_ready) LSH_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(ev_dwqv_ready), s));
   return gemm_aw(BL, d.D, NQV, w.dqv, NQV, w.wqv, nullptr, dx, d.D, f32, w.cublas, s);
@@ -558,6 +565,10 @@ int make_row_gather_map(CUtensorMap *map, const void *base, uint64_t rows, uint6
 
 /* Test hook (not in the public header): the tensor-core GEMM of gemm_tc.cu on caller-supplied operands,
  * C[M, N] = A[M, K] · B[N, K]^T (bf16 in, bf16 or f32 out).  Returns -1 when the kernel does not cover the shape. */
+extern "C" int lsh_debug_gemm_tc_wgrad(int64_t M, int64_t N, int64_t K, const void *A, const void *B, float *C, void *scratch,
+                                       size_t scratch_bytes, void *stream) {
+  return lsh::gemm_tc_wgrad_run(M, N, K, A, M, B, N, C, scratch, scratch_bytes, static_cast<cudaStream_t>(stream));
+}
 extern "C" int lsh_debug_gemm_tc(int64_t M, int64_t N, int64_t K, const void *A, int64_t lda, const void *B, int64_t ldb, void *C,
                                  int64_t ldc, int c_f32, void *stream) {
   return lsh::gemm_tc_run(M, N, K, A, lda, B, ldb, C, ldc, c_f32 != 0, static_cast<cudaStream_t>(stream));

@@ -31,6 +31,7 @@ struct GemmTcParams {
   void *c;
   int64_t ldc;
   int M, N, K, c_f32, m_blocks, n_blocks;
+  int splits;          // MN mode: the K range is cut into `splits` pieces, piece s writes its fp32 partial to c + s * M * ldc
   // q|v projection only (all null otherwise): the per-token key normalisation of EA:229-231 straight from the epilogue — for
   // every (token, head) whose 64 q columns this thread has just rounded to bf16: qscale = log2e / (8 r), the normalised key
   // qhat = bf16(q / (8 r)) and rowmeta = {8 r log2e, that times |qhat|^2}, r = sqrt(mean(q^2) + 1e-6) (see qscale_kernel)
@@ -70,7 +71,11 @@ struct __align__(16) GemmShared {
   uint32_t tmem_base;
 };
 
-template <int BN, int CL>
+// MN = false: A (M, K) and B (N, K), K contiguous (activation x weight).  MN = true: A (K, M) and B (K, N), M / N contiguous —
+// the weight-gradient products dW = act^T · cotangent, contraction over the B L token rows; tiles are boxes of 64 columns x 64
+// K-rows (MN-major SWIZZLE_128B operands, 8 KB per 64-wide group), K is split over the clusters (fp32 partials, summed by
+// sum_partials_kernel in a fixed order).
+template <int BN, int CL, bool MN>
 __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -95,25 +100,46 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
   const uint32_t tmem = sh.tmem_base;
 
   const int n_clusters = gridDim.x / CL, cid = blockIdx.x / CL;
-  const int m_groups = (p.m_blocks + CL - 1) / CL, total = m_groups * p.n_blocks, kb_n = p.K / GM_BK;
+  const int m_groups = (p.m_blocks + CL - 1) / CL, tiles = m_groups * p.n_blocks, total = tiles * p.splits, kb_all = p.K / GM_BK;
+  // work item g = (K piece, row-block group, column block), column block fastest; its K blocks are [kb0, kb1)
+  auto k_range = [&](int g, int &kb0, int &kb1) {
+    const int sp = g / tiles;
+    kb0 = static_cast<int>(static_cast<int64_t>(kb_all) * sp / p.splits);
+    kb1 = static_cast<int>(static_cast<int64_t>(kb_all) * (sp + 1) / p.splits);
+  };
 
   if (warp == 0) {
     // ================================ TMA producer ======================================================
     int it = 0;                                                     // k-block counter across tiles (ring position)
     for (int g = cid; g < total; g += n_clusters) {
-      const int n_blk = g % p.n_blocks, m_blk = (g / p.n_blocks) * CL + static_cast<int>(rank);
-      for (int kb = 0; kb < kb_n; ++kb, ++it) {
+      const int n_blk = g % p.n_blocks, m_blk = ((g % tiles) / p.n_blocks) * CL + static_cast<int>(rank);
+      int kb0, kb1;
+      k_range(g, kb0, kb1);
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int s = it % GM_STAGES;
         mbar_wait(&sh.empty[s], ((it / GM_STAGES) & 1) ^ 1);
         if (elect_one()) {
           const uint32_t a_dst = smem_u + s * STAGE_BYTES, b_dst = a_dst + A_BYTES;
+          constexpr uint16_t ALL = static_cast<uint16_t>((1u << CL) - 1);
           mbar_arrive_expect_tx(&sh.full[s], STAGE_BYTES);
-          tma_load_2d(a_dst, &p.tm_a, &sh.full[s], kb * GM_BK, m_blk * GM_BM);     // rows past M read as zeros
-          if (CL == 1) {
-            tma_load_2d(b_dst, &p.tm_b, &sh.full[s], kb * GM_BK, n_blk * BN);
-          } else {                                                   // my half of the weight tile, into both CTAs
-            tma_load_2d_mc(b_dst + rank * (B_BYTES / 2), &p.tm_b, &sh.full[s], kb * GM_BK, n_blk * BN + rank * (BN / 2),
-                           static_cast<uint16_t>((1u << CL) - 1));
+          if constexpr (!MN) {
+            tma_load_2d(a_dst, &p.tm_a, &sh.full[s], kb * GM_BK, m_blk * GM_BM);     // rows past M read as zeros
+            if (CL == 1) {
+              tma_load_2d(b_dst, &p.tm_b, &sh.full[s], kb * GM_BK, n_blk * BN);
+            } else {                                                   // my half of the weight tile, into both CTAs
+              tma_load_2d_mc(b_dst + rank * (B_BYTES / 2), &p.tm_b, &sh.full[s], kb * GM_BK, n_blk * BN + rank * (BN / 2), ALL);
+            }
+          } else {
+            // 64-column groups: 2 of A (mine), BN / 64 of B (CL = 2: half of them loaded here and multicast to the partner)
+#pragma unroll
+            for (int gq = 0; gq < GM_BM / 64; ++gq)
+              tma_load_2d(a_dst + gq * 8192, &p.tm_a, &sh.full[s], m_blk * GM_BM + gq * 64, kb * GM_BK);
+#pragma unroll
+            for (int gq = 0; gq < BN / 64 / CL; ++gq) {
+              const int grp = static_cast<int>(rank) * (BN / 64 / CL) + gq;
+              if (CL == 1) tma_load_2d(b_dst + grp * 8192, &p.tm_b, &sh.full[s], n_blk * BN + grp * 64, kb * GM_BK);
+              else tma_load_2d_mc(b_dst + grp * 8192, &p.tm_b, &sh.full[s], n_blk * BN + grp * 64, kb * GM_BK, ALL);
+            }
           }
         }
         __syncwarp();
@@ -122,24 +148,30 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
   } else if (warp == 1) {
     // ================================ MMA issuer =======================================================
     constexpr uint32_t HI = desc_hi(1024);
-    constexpr uint32_t IDESC = make_idesc_bf16(GM_BM, BN, 0, 0);
+    constexpr uint32_t IDESC = make_idesc_bf16(GM_BM, BN, MN ? 1 : 0, MN ? 1 : 0);
+    // K-major: 128-byte rows, next K16 step = +32 bytes inside the row.  MN-major: 64-wide groups 8 KB apart (LBO), next K16
+    // step = 16 K-rows = +2048 bytes
+    constexpr uint32_t LBO = MN ? 8192 : 16, KSTEP = MN ? 128 : 2;
     int it = 0, t = 0;
     for (int g = cid; g < total; g += n_clusters, ++t) {
       const int acc = t & 1;
+      int kb0, kb1;
+      k_range(g, kb0, kb1);
       mbar_wait(&sh.acc_empty[acc], ((t >> 1) & 1) ^ 1);            // the epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t d_t = tmem + acc * BN;
-      for (int kb = 0; kb < kb_n; ++kb, ++it) {
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int s = it % GM_STAGES;
         mbar_wait(&sh.full[s], (it / GM_STAGES) & 1);
         tc_fence_after();
-        const uint32_t a_lo = desc_lo(smem_u + s * STAGE_BYTES, 16), b_lo = desc_lo(smem_u + s * STAGE_BYTES + A_BYTES, 16);
+        const uint32_t a_lo = desc_lo(smem_u + s * STAGE_BYTES, LBO), b_lo = desc_lo(smem_u + s * STAGE_BYTES + A_BYTES, LBO);
         if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < GM_BK / 16; ++ks) umma_ss2(d_t, a_lo + ks * 2, HI, b_lo + ks * 2, HI, IDESC, (kb | ks) != 0);
+          for (int ks = 0; ks < GM_BK / 16; ++ks)
+            umma_ss2(d_t, a_lo + ks * KSTEP, HI, b_lo + ks * KSTEP, HI, IDESC, (kb > kb0 || ks > 0) ? 1u : 0u);
           if (CL == 1) umma_commit(&sh.empty[s]);
           else umma_commit_mc(&sh.empty[s], static_cast<uint16_t>((1u << CL) - 1));
-          if (kb == kb_n - 1) umma_commit(&sh.acc_full[acc]);
+          if (kb == kb1 - 1) umma_commit(&sh.acc_full[acc]);
         }
         __syncwarp();
       }
@@ -151,9 +183,10 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
     int t = 0;
     for (int g = cid; g < total; g += n_clusters, ++t) {
       const int acc = t & 1;
-      const int n_blk = g % p.n_blocks, m_blk = (g / p.n_blocks) * CL + static_cast<int>(rank);
+      const int n_blk = g % p.n_blocks, m_blk = ((g % tiles) / p.n_blocks) * CL + static_cast<int>(rank);
       const int64_t row = static_cast<int64_t>(m_blk) * GM_BM + q * 32 + lane;
       const bool live = row < p.M;
+      const int64_t crow = row + static_cast<int64_t>(g / tiles) * p.M;   // (MN mode: the K piece's slice of the partial buffer)
       mbar_wait(&sh.acc_full[acc], (t >> 1) & 1);
       tc_fence_after();
       uint32_t ra[32], rb[32];
@@ -206,13 +239,13 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
         if (p.qhat != nullptr && (c & 2) == 0) q_stats(r, c);
         const int64_t col = static_cast<int64_t>(n_blk) * BN + c * 32;
         if (p.c_f32) {
-          float4 *dst = reinterpret_cast<float4 *>(static_cast<float *>(p.c) + row * p.ldc + col);
+          float4 *dst = reinterpret_cast<float4 *>(static_cast<float *>(p.c) + crow * p.ldc + col);
 #pragma unroll
           for (int i = 0; i < 8; ++i)
             dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
                                  __uint_as_float(r[4 * i + 3]));
         } else {
-          uint4 *dst = reinterpret_cast<uint4 *>(static_cast<__nv_bfloat16 *>(p.c) + row * p.ldc + col);
+          uint4 *dst = reinterpret_cast<uint4 *>(static_cast<__nv_bfloat16 *>(p.c) + crow * p.ldc + col);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             uint4 v;
@@ -247,15 +280,15 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
 int make_tile_map(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes, uint32_t box_cols,
                   uint32_t box_rows);
 
-template <int BN, int CL>
+template <int BN, int CL, bool MN>
 static int gemm_tc_launch(const GemmTcParams &p, cudaStream_t stream) {
   const size_t smem = static_cast<size_t>(GM_STAGES) * (GM_BM * 128 + BN * 128) + 1024;
-  auto kernel = gemm_tc_kernel<BN, CL>;
+  auto kernel = gemm_tc_kernel<BN, CL, MN>;
   LSH_OPT_IN_SMEM(kernel);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int groups = ((p.m_blocks + CL - 1) / CL) * p.n_blocks;
+  const int groups = ((p.m_blocks + CL - 1) / CL) * p.n_blocks * p.splits;
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
   cfg.blockDim = dim3(GM_THREADS);
@@ -301,6 +334,7 @@ int gemm_tc_run(int64_t M, int64_t N, int64_t K, const void *A, int64_t lda, con
   GemmTcParams p;
   p.c = C; p.ldc = ldc; p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K); p.c_f32 = c_f32 ? 1 : 0;
   p.m_blocks = static_cast<int>((M + GM_BM - 1) / GM_BM); p.n_blocks = static_cast<int>(N / bn);
+  p.splits = 1;
   p.qscale = nullptr; p.rowmeta = nullptr; p.qhat = nullptr; p.L = 1; p.H = 1;
   if (qs) {           // fused key normalisation: rows are (b, t), columns (h, q | v) — needs bf16 output of 128-column heads
     if (c_f32 || N != static_cast<int64_t>(qs->H) * 128) return set_error("gemm_tc: q statistics need the (B L, H 128) bf16 projection");
@@ -309,8 +343,66 @@ int gemm_tc_run(int64_t M, int64_t N, int64_t K, const void *A, int64_t lda, con
   const int cl = (mode == 2 && p.m_blocks >= 2) ? 2 : 1;
   if (int rc = make_tile_map(&p.tm_a, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda) * 2, GM_BK, GM_BM)) return rc;
   if (int rc = make_tile_map(&p.tm_b, B, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldb) * 2, GM_BK, bn / cl)) return rc;
-  if (bn == 256) return cl == 2 ? gemm_tc_launch<256, 2>(p, stream) : gemm_tc_launch<256, 1>(p, stream);
-  return cl == 2 ? gemm_tc_launch<128, 2>(p, stream) : gemm_tc_launch<128, 1>(p, stream);
+  if (bn == 256) return cl == 2 ? gemm_tc_launch<256, 2, false>(p, stream) : gemm_tc_launch<256, 1, false>(p, stream);
+  return cl == 2 ? gemm_tc_launch<128, 2, false>(p, stream) : gemm_tc_launch<128, 1, false>(p, stream);
+}
+
+// fp32 partial sums of the K pieces, added in piece order (deterministic): dst[i] = sum_s part[s * n + i]
+__global__ void __launch_bounds__(256) sum_partials_kernel(const float4 *__restrict__ part, float4 *__restrict__ dst, int64_t n4, int splits) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float4 a = part[i];
+    for (int s = 1; s < splits; ++s) {
+      const float4 b = part[s * n4 + i];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    dst[i] = a;
+  }
+}
+
+// Weight gradient C[M, N] (f32, row pitch N) = A^T · B with A (K, M) (row pitch lda) and B (K, N) (row pitch ldb), bf16, the
+// contraction running over the K = B L token rows (EA:2431 sums examples: they are rows of the same product).  `scratch`
+// holds the split-K partials.  Returns like gemm_tc_run (-1: shape not covered).
+int gemm_tc_wgrad_run(int64_t M, int64_t N, int64_t K, const void *A, int64_t lda, const void *B, int64_t ldb, float *C,
+                      void *scratch, size_t scratch_bytes, cudaStream_t stream) {
+  static const int mode = [] {
+    const char *e = getenv("LSH_GEMM");
+    if (!e) return 2;
+    if (strcmp(e, "cublas") == 0 || strcmp(e, "cublas_wgrad") == 0) return 0;
+    if (strcmp(e, "cluster1") == 0) return 1;
+    return 2;
+  }();
+  if (mode == 0) return -1;
+  if (M % 128 != 0 || N % 128 != 0 || K % GM_BK != 0 || K >= (1ll << 31) || lda % 8 != 0 || ldb % 8 != 0) return -1;
+  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C) | reinterpret_cast<uintptr_t>(scratch)) & 15) return -1;
+  const int bn = (N % 256 == 0) ? 256 : 128;
+  GemmTcParams p;
+  p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K); p.c_f32 = 1; p.ldc = N;
+  p.m_blocks = static_cast<int>(M / GM_BM); p.n_blocks = static_cast<int>(N / bn);
+  p.qscale = nullptr; p.rowmeta = nullptr; p.qhat = nullptr; p.L = 1; p.H = 1;
+  const int cl = (mode == 2 && p.m_blocks % 2 == 0) ? 2 : 1;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles = (p.m_blocks / cl) * p.n_blocks;
+  int64_t splits = (sms / cl) / tiles;                       // one wave of clusters
+  const int64_t kb_all = K / GM_BK, fit = static_cast<int64_t>(scratch_bytes / (static_cast<size_t>(M) * N * 4));
+  if (splits > kb_all) splits = kb_all;
+  if (splits > fit) splits = fit;
+  if (splits < 1) splits = 1;
+  p.splits = static_cast<int>(splits);
+  p.c = splits > 1 ? scratch : static_cast<void *>(C);
+  if (splits > 1 && !scratch) return -1;
+  if (int rc = make_tile_map(&p.tm_a, A, static_cast<uint64_t>(K), static_cast<uint64_t>(M), static_cast<uint64_t>(lda) * 2, 64, GM_BK)) return rc;
+  if (int rc = make_tile_map(&p.tm_b, B, static_cast<uint64_t>(K), static_cast<uint64_t>(N), static_cast<uint64_t>(ldb) * 2, 64, GM_BK)) return rc;
+  int rc;
+  if (bn == 256) rc = cl == 2 ? gemm_tc_launch<256, 2, true>(p, stream) : gemm_tc_launch<256, 1, true>(p, stream);
+  else rc = cl == 2 ? gemm_tc_launch<128, 2, true>(p, stream) : gemm_tc_launch<128, 1, true>(p, stream);
+  if (rc || splits == 1) return rc;
+  const int64_t n4 = M * N / 4;
+  sum_partials_kernel<<<static_cast<unsigned>((n4 + 255) / 256 < 148 * 8 ? (n4 + 255) / 256 : 148 * 8), 256, 0, stream>>>(
+      static_cast<const float4 *>(scratch), reinterpret_cast<float4 *>(C), n4, static_cast<int>(splits));
+  LSH_CHECK_LAUNCH("sum_partials_kernel");
+  return 0;
 }
 
 }  // namespace lsh

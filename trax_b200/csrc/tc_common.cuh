@@ -23,6 +23,8 @@ struct GemmQStats {
 };
 int gemm_tc_run(int64_t M, int64_t N, int64_t K, const void *A, int64_t lda, const void *B, int64_t ldb, void *C, int64_t ldc,
                 bool c_f32, cudaStream_t stream, const GemmQStats *qs = nullptr);
+int gemm_tc_wgrad_run(int64_t M, int64_t N, int64_t K, const void *A, int64_t lda, const void *B, int64_t ldb, float *C,
+                      void *scratch, size_t scratch_bytes, cudaStream_t stream);
 
 #ifdef __CUDACC__
 
