@@ -10,8 +10,9 @@
 //   warp 1   MMA issuer: per K block of 64, four `tcgen05.mma.kind::f16` M128 x N{256,128} x K16 on shared-memory descriptors,
 //            accumulating into one of TWO TMEM accumulators (2 x N columns); `tcgen05.commit` frees the stage / hands the
 //            finished accumulator to the epilogue.
-//   warps 2-5 epilogue: TMEM -> registers (32 columns at a time, next load in flight) -> bf16 / fp32 rows in global memory,
-//            while the issuer is already accumulating the next tile in the other accumulator.
+//   warps 2-9 epilogue (two warpgroups, each owns half of the tile's columns; a warp reads the TMEM lane quarter warp % 4):
+//            TMEM -> registers (32 columns at a time, next load in flight) -> per-warp staging tile -> bf16 / fp32 row
+//            segments in global memory, while the issuer is already accumulating the next tile in the other accumulator.
 // CLUSTER = 2: the two CTAs of a cluster compute vertically adjacent tiles (same n block) and SHARE the weight tile: each
 // loads half of it and multicasts it into both shared memories (`.multicast::cluster`), which halves the L2 -> SM traffic of
 // the B operand (a 1-CTA 128 x 256 tile needs 94 B/clk/SM from L2 against ~43 B/clk/SM available chip-wide,
@@ -24,7 +25,9 @@
 
 namespace lsh {
 
-constexpr int GM_BM = 128, GM_BK = 64, GM_STAGES = 4, GM_THREADS = 192;
+constexpr int GM_BM = 128, GM_BK = 64, GM_STAGES = 4;
+constexpr int GM_EPI_WARPS = 8;                     // two warpgroups, each drains half of the tile's columns
+constexpr int GM_THREADS = 64 + 32 * GM_EPI_WARPS;
 
 struct GemmTcParams {
   CUtensorMap tm_a, tm_b;
@@ -84,13 +87,14 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
   const uint32_t smem_u = smem_u32(smem);
+  const uint32_t stage_u = smem_u + GM_STAGES * STAGE_BYTES;          // epilogue staging: GM_EPI_WARPS x 4 KB
 
   if (warp == 1) tmem_alloc(&sh.tmem_base, 512);
   if (tid == 0) {
     tma_prefetch_desc(&p.tm_a);
     tma_prefetch_desc(&p.tm_b);
     for (int i = 0; i < GM_STAGES; ++i) { mbar_init(&sh.full[i], 1); mbar_init(&sh.empty[i], CL); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&sh.acc_full[i], 1); mbar_init(&sh.acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sh.acc_full[i], 1); mbar_init(&sh.acc_empty[i], GM_EPI_WARPS); }
     fence_mbar_init();
   }
   tc_fence_before();
@@ -179,6 +183,8 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
   } else {
     // ================================ epilogue warps ====================================================
     const int q = warp & 3;                                          // TMEM lane quarter of this warp
+    constexpr int CPG = BN / 32 / (GM_EPI_WARPS / 4);                // 32-column chunks per warpgroup (even: heads stay whole or q | v)
+    const int c_first = ((warp - 2) >> 2) * CPG;
     const uint32_t t_lane = tmem + (static_cast<uint32_t>(q * 32) << 16);
     int t = 0;
     for (int g = cid; g < total; g += n_clusters, ++t) {
@@ -186,11 +192,10 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
       const int n_blk = g % p.n_blocks, m_blk = ((g % tiles) / p.n_blocks) * CL + static_cast<int>(rank);
       const int64_t row = static_cast<int64_t>(m_blk) * GM_BM + q * 32 + lane;
       const bool live = row < p.M;
-      const int64_t crow = row + static_cast<int64_t>(g / tiles) * p.M;   // (MN mode: the K piece's slice of the partial buffer)
       mbar_wait(&sh.acc_full[acc], (t >> 1) & 1);
       tc_fence_after();
       uint32_t ra[32], rb[32];
-      tmem_ld32(t_lane + acc * BN, ra);
+      tmem_ld32(t_lane + acc * BN + c_first * 32, ra);
       uint32_t qlo[16];                                              // first half of a head's q row, as stored (bf16 pairs)
       float qss = 0.f;
       // key normalisation of one head from the bf16 values just stored: `c` = chunk of 32 columns; a head owns 4 chunks,
@@ -234,36 +239,54 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
         const float am = 8.f * rr * kLog2e;
         p.rowmeta[ut] = make_float2(am, am * s2);
       };
+      // Rows leave through a per-warp staging tile (32 rows x 128 bytes, 16-byte pieces XOR-swizzled by the row): a thread
+      // owns a ROW of the accumulator, but a store instruction should cover contiguous bytes — after the transpose 8 lanes
+      // write one 128-byte row segment (4 rows per instruction) instead of 32 lanes writing 16 bytes of 32 different rows.
+      // One round = 32 fp32 columns, or 64 bf16 columns (two accumulator chunks).
+      const uint32_t stg = stage_u + (warp - 2) * 4096;
+      auto put = [&](int piece, uint32_t a, uint32_t b, uint32_t c2, uint32_t d) {
+        sts128(stg + lane * 128 + ((static_cast<uint32_t>(piece) ^ (lane & 7)) << 4), a, b, c2, d);
+      };
+      auto flush = [&](int64_t col_bytes) {                          // col_bytes: byte offset of the round inside the C row
+        __syncwarp();
+        const int piece = lane & 7;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = 4 * i + (lane >> 3);
+          const int64_t grow = static_cast<int64_t>(m_blk) * GM_BM + q * 32 + r;
+          const uint4 v = lds128u(stg + r * 128 + ((static_cast<uint32_t>(piece) ^ (r & 7)) << 4));
+          if (grow < p.M) {
+            char *dst = static_cast<char *>(p.c) + (grow + static_cast<int64_t>(g / tiles) * p.M) * p.ldc * (p.c_f32 ? 4 : 2) + col_bytes;
+            *reinterpret_cast<uint4 *>(dst + piece * 16) = v;
+          }
+        }
+        __syncwarp();
+      };
       auto store = [&](const uint32_t (&r)[32], int c) {
-        if (!live) return;
-        if (p.qhat != nullptr && (c & 2) == 0) q_stats(r, c);
+        if (live && p.qhat != nullptr && (c & 2) == 0) q_stats(r, c);
         const int64_t col = static_cast<int64_t>(n_blk) * BN + c * 32;
         if (p.c_f32) {
-          float4 *dst = reinterpret_cast<float4 *>(static_cast<float *>(p.c) + crow * p.ldc + col);
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
-                                 __uint_as_float(r[4 * i + 3]));
+          for (int i = 0; i < 8; ++i) put(i, r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+          flush(col * 4);
         } else {
-          uint4 *dst = reinterpret_cast<uint4 *>(static_cast<__nv_bfloat16 *>(p.c) + crow * p.ldc + col);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 v;
-            v.x = pack_bf16(__uint_as_float(r[8 * i]), __uint_as_float(r[8 * i + 1]));
-            v.y = pack_bf16(__uint_as_float(r[8 * i + 2]), __uint_as_float(r[8 * i + 3]));
-            v.z = pack_bf16(__uint_as_float(r[8 * i + 4]), __uint_as_float(r[8 * i + 5]));
-            v.w = pack_bf16(__uint_as_float(r[8 * i + 6]), __uint_as_float(r[8 * i + 7]));
-            dst[i] = v;
-          }
+          for (int i = 0; i < 4; ++i)
+            put((c & 1) * 4 + i, pack_bf16(__uint_as_float(r[8 * i]), __uint_as_float(r[8 * i + 1])),
+                pack_bf16(__uint_as_float(r[8 * i + 2]), __uint_as_float(r[8 * i + 3])),
+                pack_bf16(__uint_as_float(r[8 * i + 4]), __uint_as_float(r[8 * i + 5])),
+                pack_bf16(__uint_as_float(r[8 * i + 6]), __uint_as_float(r[8 * i + 7])));
+          if (c & 1) flush((col - 32) * 2);
         }
       };
 #pragma unroll
-      for (int c = 0; c < BN / 32; c += 2) {
+      for (int cc = 0; cc < CPG; cc += 2) {
+        const int c = c_first + cc;
         tmem_ld_wait_dep(ra);
         tmem_ld32(t_lane + acc * BN + (c + 1) * 32, rb);
         store(ra, c);
         tmem_ld_wait_dep(rb);
-        if (c + 2 < BN / 32) tmem_ld32(t_lane + acc * BN + (c + 2) * 32, ra);
+        if (cc + 2 < CPG) tmem_ld32(t_lane + acc * BN + (c + 2) * 32, ra);
         store(rb, c + 1);
       }
       tc_fence_before();
@@ -282,7 +305,7 @@ int make_tile_map(CUtensorMap *map, const void *base, uint64_t rows, uint64_t co
 
 template <int BN, int CL, bool MN>
 static int gemm_tc_launch(const GemmTcParams &p, cudaStream_t stream) {
-  const size_t smem = static_cast<size_t>(GM_STAGES) * (GM_BM * 128 + BN * 128) + 1024;
+  const size_t smem = static_cast<size_t>(GM_STAGES) * (GM_BM * 128 + BN * 128) + GM_EPI_WARPS * 4096 + 1024;
   auto kernel = gemm_tc_kernel<BN, CL, MN>;
   LSH_OPT_IN_SMEM(kernel);
   int dev = 0, sms = 148;
