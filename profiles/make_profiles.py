@@ -1,4 +1,4 @@
-"""Regenerates the committed round-1 evidence from one gpurun capture (see the commands in each output's header):
+"""Regenerates the committed per-round evidence from one gpurun capture (see the commands in each output's header):
   gpurun_out/kernels_<tag>.csv   ncu --metrics gpu__time_duration.sum,dram__bytes_{read,write}.sum,...pipe/issue... of bench.py
   gpurun_out/prof_<tag>_{attend_bwd,attend_fwd,hash}.ncu-rep   ncu --set full of tests/prof_stage.py <stage>
   gpurun_out/bench_<tag>.json    the bench line of the same build
@@ -21,8 +21,12 @@ for r in rows:
   if u == 'ms': v *= 1e6
   d[r[ci['Metric Name']]] = v
 ids = list(byid)
-h = [i for i in ids if 'hash_' in byid[i]['name']]
-a, b = h[1] - 5, h[2] - 5            # one full step: a forward call starts 5 launches before its hash kernel
+h = [i for i in ids if 'make_rotations' in byid[i]['name']]
+if len(h) >= 3:
+  a, b = h[1], h[2]                  # one full step: every forward call starts by drawing its rotations
+else:                                # (round-1 builds: rotations came from the host; 5 launches precede the hash kernel)
+  h = [i for i in ids if 'hash_' in byid[i]['name']]
+  a, b = h[1] - 5, h[2] - 5
 sel = [i for i in ids if a <= i < b]
 agg = collections.OrderedDict()
 for i in sel:
@@ -35,7 +39,7 @@ tot = sum(e['t'] for e in agg.values())
 out = ['Per-kernel counters of ONE fwd+bwd step of bench.py (workload c2) under ncu (--clock-control none; cold-cache, serialised:',
        'compare shares and per-launch DRAM bytes, not absolute times).  HBM peak measured on this pool: 6546.6 GB/s (MEASURED_PEAKS.json).',
        'Command: ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active...,',
-       '         sm__pipe_fma_cycles_active...,smsp__issue_active... --clock-control none -c 150 python bench.py --steps 2 --warmup 3',
+       '         sm__pipe_fma_cycles_active...,smsp__issue_active... --clock-control none -c 260 python bench.py --steps 2 --warmup 3',
        '%-58s %3s %9s %6s %9s %9s %8s %7s %6s %6s' % ('kernel', 'x', 'us/launch', 'share', 'rd MB', 'wr MB', 'GB/s', 'tensor%', 'fma%', 'issue%')]
 for n, e in sorted(agg.items(), key=lambda kv: -kv[1]['t']):
   t = e['t'] / e['n']

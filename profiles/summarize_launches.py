@@ -14,7 +14,7 @@ data = [r for r in rows if r is not hdr and r[ci['Metric Name']] == 'gpu__time_d
 names = [re.sub(r'\(.*', '', r[ci['Kernel Name']])[:64] for r in data]
 vals = [float(r[ci['Metric Value']].replace(',', '')) / 1e3 for r in data]   # ns -> us
 h = [i for i, n in enumerate(names) if 'hash_' in n and 'kernel' in n]
-a, b = h[3] - 5, h[4] - 5            # one full step (forward call starts 5 launches before its hash kernel)
+a, b = h[3] - 7, h[4] - 7            # one full step (round 2: a forward call starts 7 launches before its hash kernel; round 1: 5)
 agg, cnt = collections.OrderedDict(), collections.Counter()
 for n, v in zip(names[a:b], vals[a:b]):
   agg[n] = agg.get(n, 0.0) + v
