@@ -1,9 +1,9 @@
-"""Writes profiles/r1_sass_summary.txt from the built library (no GPU needed): per kernel, registers / shared memory
+"""Writes profiles/<round>_sass_summary.txt (round prefix = first argument, default r2) from the built library (no GPU needed): per kernel, registers / shared memory
 (`cuobjdump -res-usage`) and counts of the SASS mnemonics that show which hardware path it uses
 (B200_PROFILING.md: UTCHMMA = tcgen05.mma, LDTM/STTM = tcgen05.ld/st, UTCBAR = tcgen05.commit, SYNCS = mbarrier,
-LDGSTS = cp.async, HMMA = mma.sync, MUFU.EX2, FFMA2 = packed fp32).
+LDGSTS = cp.async, UTMALDG / UTMASTG = TMA tensor loads / stores, UBLKCP = cp.async.bulk, HMMA = mma.sync, MUFU.EX2, FFMA2 = packed fp32).
 
-    python profiles/make_sass_summary.py
+    python profiles/make_sass_summary.py r2
 """
 import collections
 import os
@@ -12,7 +12,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(os.path.dirname(HERE), 'trax_b200', 'liblsh_attn_b200.so')
-PATTERNS = ['UTCHMMA', 'UTCBAR', 'LDTM', 'STTM', 'SYNCS', 'LDGSTS', 'UBLKCP', 'HMMA', 'MUFU.EX2', 'FFMA2', 'FADD2', 'FMUL2',
+PATTERNS = ['UTCHMMA', 'UTCBAR', 'LDTM', 'STTM', 'SYNCS', 'LDGSTS', 'UTMALDG', 'UTMASTG', 'UBLKCP', 'HMMA', 'MUFU.EX2', 'FFMA2', 'FADD2', 'FMUL2',
             'ELECT', 'NANOSLEEP', 'RED', 'ATOM', 'BAR.SYNC', 'STL', 'LDL']
 
 
@@ -64,7 +64,8 @@ def main():
     regs, smem = usage.get(fn, (0, 0))
     c = ' '.join('%s=%d' % (p, counts[fn][p]) for p in PATTERNS if counts[fn][p])
     lines.append('%-58s %5d %7d %6d  %s' % (short[:58], regs, smem, size[fn], c))
-  out = os.path.join(HERE, 'r1_sass_summary.txt')
+  import sys
+  out = os.path.join(HERE, '%s_sass_summary.txt' % (sys.argv[1] if len(sys.argv) > 1 else 'r2'))
   open(out, 'w').write('\n'.join(lines) + '\n')
   print('\n'.join(lines))
 
