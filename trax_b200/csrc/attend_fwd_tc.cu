@@ -437,6 +437,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const __gr
       const TcTileMeta &mq = p.nb ? m1 : m0;
       const TcTileMeta &mk = wg ? m1 : m0;                          // the tile whose keys this warpgroup scores
       const int mypos = mq.pos[row];
+      const int my_tk = mq.tk[row];                                 // (read here: a load in the hand-off tail sits behind the P stores)
       const float qi = static_cast<float>(mypos + 1);               // q_info = pos + 1 (EA:201)
       const float2 am = mq.am[row];                                  // query-side scale a_i, self score m_i (log2 domain)
       const float a_i = am.x;
@@ -579,7 +580,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const __gr
       sh.row_l[ob][wg][row] = l;
       if (wg == 1) {
         sh.row_m2[ob][row] = m2; sh.row_off[ob][row] = lse_off;
-        sh.row_tk[ob][row] = mq.tk[row];
+        sh.row_tk[ob][row] = my_tk;
       }
       tmem_st_wait();
       tc_fence_before();
