@@ -417,3 +417,29 @@ def test_layer_with_attention_and_output_dropout(B, L, D, dtype, cfg):
   want_plain, _, _, _ = O.forward_and_or_backward(cfg, x, weights, buckets=buckets, update_state=False)
   got_plain, _, _, _ = ev.forward_and_or_backward(x_d, w_d, state, None, compute_output=True, update_state=False)
   util.assert_close_layer(got_plain.float().cpu().numpy(), want_plain, 'eval-mode out')
+
+
+def test_concurrent_streams_get_their_own_scratch_and_agree():
+  """Two calls on different streams must not share the library's scratch buffer (ops.workspace is keyed by device AND
+  stream): run the same forward on two side streams at once and compare with the default-stream result."""
+  import trax_b200
+  from trax_b200 import ops
+  cfg = util.make_cfg(H=4, C=128, nh=2, n_buckets=None)
+  layer = _layer(cfg)
+  layer.init(trax_b200.ShapeDtype((1, 2048, 256)))
+  g = torch.Generator('cuda').manual_seed(11)
+  xs = [torch.randn(1, 2048, 256, device='cuda', generator=g).bfloat16() for _ in range(2)]
+  layer.forward(xs[0])                       # fills the bucket state; any valid permutation serves both inputs below
+  state = layer.state
+  want = [layer.forward_and_or_backward(x, layer.weights, state, None, update_state=False)[0] for x in xs]
+  torch.cuda.synchronize()
+  streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+  got, bufs = [], []
+  for x, st in zip(xs, streams):
+    with torch.cuda.stream(st):
+      got.append(layer.forward_and_or_backward(x, layer.weights, state, None, update_state=False)[0])
+      bufs.append(ops.workspace(x.device, 1).data_ptr())
+  torch.cuda.synchronize()
+  assert bufs[0] != bufs[1]
+  for a, b in zip(got, want):
+    assert torch.equal(a, b)

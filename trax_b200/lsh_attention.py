@@ -474,6 +474,11 @@ class LSHSelfAttention:
       raise ValueError('inputs[0] must have shape (batch, seqlen, d_model)')
     if not torch.cuda.is_available():
       raise _lib.LshAttnError('trax_b200.LSHSelfAttention needs a CUDA device (no CPU fallback)')
+    if x.is_cuda and x.device.index != torch.cuda.current_device():
+      # kernels, streams and the scratch buffer belong to the tensors' device, whatever the caller's current device is
+      with torch.cuda.device(x.device):
+        return self._forward_and_or_backward(inputs if not have_single_input else inputs[0], weights, state, rng, output_grad,
+                                             compute_output, update_state, _stash)
     lib = _lib.load()
     host_io = not x.is_cuda
     dev = torch.device('cuda', torch.cuda.current_device()) if host_io else x.device

@@ -50,8 +50,9 @@ _WS = {}
 
 
 def workspace(device, nbytes):
-  """One cached scratch buffer per device (grown on demand); the library never allocates."""
-  key = (device.type, device.index)
+  """One cached scratch buffer per (device, current stream), grown on demand; the library never allocates.  Keyed by
+  the stream as well: two layers running concurrently on different streams must not share scratch memory."""
+  key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
   buf = _WS.get(key)
   if buf is None or buf.numel() < nbytes:
     buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
