@@ -21,10 +21,14 @@ __device__ __forceinline__ uint4 f32_to_bf16x8(const float (&f)[8]) {
 }
 
 // o_rounds (BH, nh, L, 64) bf16, logits (BH, nh, L) f32 -> o_comb (B, L, H, 64) bf16, lse_tot (BH, L)
+// NH > 0: the round count is a compile-time constant (1, 2, 4, 8: every BASELINE config) — all rows of the token are in
+// flight at once (one 16-byte load per round per lane) and no predicated-off round is issued; NH = 0: any round count.
+template <int NH>
 __global__ void __launch_bounds__(ROW_THREADS) combine_fwd_kernel(
     const __nv_bfloat16 *__restrict__ o_rounds, const float *__restrict__ logits,
-    __nv_bfloat16 *__restrict__ o_comb, float *__restrict__ lse_tot, int L, int H, int nh,
+    __nv_bfloat16 *__restrict__ o_comb, float *__restrict__ lse_tot, int L, int H, int nh_rt,
     int64_t total_rows) {
+  const int nh = NH > 0 ? NH : nh_rt;
   const int64_t row = (static_cast<int64_t>(blockIdx.x) * ROW_THREADS + threadIdx.x) >> 3;   // (u, t)
   const int ch = threadIdx.x & 7;
   if (row >= total_rows) return;
@@ -34,34 +38,29 @@ __global__ void __launch_bounds__(ROW_THREADS) combine_fwd_kernel(
   const float *lg = logits + u * nh * L + t;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   float lse;
-  if (nh <= 8) {
-    // all rows of the token in flight at once (one 16-byte load per round per lane)
-    float lgv[8];
-    uint4 ov[8];
+  if constexpr (NH > 0) {
+    float lgv[NH];
+    uint4 ov[NH];
+    const uint4 *src = reinterpret_cast<const uint4 *>(o_rounds + (u * NH * L + t) * 64) + ch;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      if (r < nh) {
-        lgv[r] = __ldg(lg + static_cast<int64_t>(r) * L);
-        ov[r] = __ldg(reinterpret_cast<const uint4 *>(o_rounds + ((u * nh + r) * L + t) * 64) + ch);
-      }
+    for (int r = 0; r < NH; ++r) {
+      lgv[r] = __ldg(lg + static_cast<int64_t>(r) * L);
+      ov[r] = __ldg(src + static_cast<int64_t>(r) * L * 8);
     }
-    float mx = -INFINITY;
+    float mx = lgv[0];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) if (r < nh) mx = fmaxf(mx, lgv[r]);
+    for (int r = 1; r < NH; ++r) mx = fmaxf(mx, lgv[r]);
     float den = 0.f;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) if (r < nh) den += __expf(lgv[r] - mx);
-    lse = mx + __logf(den);                                           // logsumexp over rounds (EA:1991); MUFU-based
-                                                                      // exp / log (2 ulp): the kernel is issue-bound
+    for (int r = 0; r < NH; ++r) den += __expf(lgv[r] - mx);
+    lse = mx + __logf(den);                                           // logsumexp over rounds (EA:1991); MUFU-based exp / log (2 ulp)
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      if (r < nh) {
-        const float w = __expf(lgv[r] - lse);
-        float f[8];
-        bf16x8_to_f32(ov[r], f);
+    for (int r = 0; r < NH; ++r) {
+      const float w = __expf(lgv[r] - lse);
+      float f[8];
+      bf16x8_to_f32(ov[r], f);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fmaf(w, f[i], acc[i]);
-      }
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(w, f[i], acc[i]);
     }
   } else {
     float mx = -INFINITY;
@@ -86,10 +85,16 @@ int combine_fwd_run(const LshAttnDims &d, const void *o_rounds, const float *log
                     float *lse_tot, cudaStream_t stream) {
   Derived dr = derive(d);
   const int64_t rows = static_cast<int64_t>(dr.BH) * d.L;
-  const int64_t blocks = (rows * 8 + ROW_THREADS - 1) / ROW_THREADS;
-  combine_fwd_kernel<<<static_cast<unsigned>(blocks), ROW_THREADS, 0, stream>>>(
-      static_cast<const __nv_bfloat16 *>(o_rounds), logits, static_cast<__nv_bfloat16 *>(o_comb),
-      lse_tot, d.L, d.H, d.nh, rows);
+  const unsigned blocks = static_cast<unsigned>((rows * 8 + ROW_THREADS - 1) / ROW_THREADS);
+  const __nv_bfloat16 *o = static_cast<const __nv_bfloat16 *>(o_rounds);
+  __nv_bfloat16 *oc = static_cast<__nv_bfloat16 *>(o_comb);
+  switch (d.nh) {
+    case 1: combine_fwd_kernel<1><<<blocks, ROW_THREADS, 0, stream>>>(o, logits, oc, lse_tot, d.L, d.H, d.nh, rows); break;
+    case 2: combine_fwd_kernel<2><<<blocks, ROW_THREADS, 0, stream>>>(o, logits, oc, lse_tot, d.L, d.H, d.nh, rows); break;
+    case 4: combine_fwd_kernel<4><<<blocks, ROW_THREADS, 0, stream>>>(o, logits, oc, lse_tot, d.L, d.H, d.nh, rows); break;
+    case 8: combine_fwd_kernel<8><<<blocks, ROW_THREADS, 0, stream>>>(o, logits, oc, lse_tot, d.L, d.H, d.nh, rows); break;
+    default: combine_fwd_kernel<0><<<blocks, ROW_THREADS, 0, stream>>>(o, logits, oc, lse_tot, d.L, d.H, d.nh, rows); break;
+  }
   LSH_CHECK_LAUNCH("combine_fwd_kernel");
   return 0;
 }
@@ -244,6 +249,8 @@ int qscale_run(const LshAttnDims &d, const void *qv, float *qscale, float2 *rowm
 
 // dqv[b,t,h,0:64]   = sum_r sum_kind dq_part[kind][u][r*L+t][:]
 // dqv[b,t,h,64:128] = sum_r dv_part[u][r*L+t][:]
+// NH > 0: tcgen05 path with a compile-time round count (one dq and one dv row per round, all 2 NH loads in flight).
+template <int NH>
 __global__ void __launch_bounds__(ROW_THREADS) sum_rounds_kernel(
     const __nv_bfloat16 *__restrict__ dq_part, const __nv_bfloat16 *__restrict__ dv_part,
     __nv_bfloat16 *__restrict__ dqv, int L, int H, int nh, int n_kinds, int64_t kind_stride,
@@ -256,28 +263,23 @@ __global__ void __launch_bounds__(ROW_THREADS) sum_rounds_kernel(
   const int64_t b = static_cast<uint32_t>(u) / static_cast<uint32_t>(H), h = u - b * H;
   float aq[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, av[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   float ak[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // separate keys: the key-side kind is the cotangent of k, not of q
-  if (n_kinds == 1 && nh <= 8) {
-    // tcgen05 path: one dq and one dv row per round — all 2 * nh loads of the token in flight at once
-    uint4 vq[8], vv[8];
+  if constexpr (NH > 0) {
+    uint4 vq[NH], vv[NH];
+    const int64_t off0 = (u * NH * L + t) * 64;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      if (r < nh) {
-        const int64_t off = ((u * nh + r) * L + t) * 64;
-        vq[r] = __ldg(reinterpret_cast<const uint4 *>(dq_part + off) + ch);
-        vv[r] = __ldg(reinterpret_cast<const uint4 *>(dv_part + off) + ch);
-      }
+    for (int r = 0; r < NH; ++r) {
+      vq[r] = __ldg(reinterpret_cast<const uint4 *>(dq_part + off0) + static_cast<int64_t>(r) * L * 8 + ch);
+      vv[r] = __ldg(reinterpret_cast<const uint4 *>(dv_part + off0) + static_cast<int64_t>(r) * L * 8 + ch);
     }
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      if (r < nh) {
-        float f[8];
-        bf16x8_to_f32(vq[r], f);
+    for (int r = 0; r < NH; ++r) {
+      float f[8];
+      bf16x8_to_f32(vq[r], f);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) aq[i] += f[i];
-        bf16x8_to_f32(vv[r], f);
+      for (int i = 0; i < 8; ++i) aq[i] += f[i];
+      bf16x8_to_f32(vv[r], f);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) av[i] += f[i];
-      }
+      for (int i = 0; i < 8; ++i) av[i] += f[i];
     }
   } else {
     for (int r = 0; r < nh; ++r) {
@@ -309,10 +311,21 @@ int sum_rounds_run(const LshAttnDims &d, const void *dq_part, const void *dv_par
   Derived dr = derive(d);
   const int64_t rows = static_cast<int64_t>(dr.BH) * d.L;
   const int64_t blocks = (rows * 8 + ROW_THREADS - 1) / ROW_THREADS;
-  sum_rounds_kernel<<<static_cast<unsigned>(blocks), ROW_THREADS, 0, stream>>>(
-      static_cast<const __nv_bfloat16 *>(dq_part), static_cast<const __nv_bfloat16 *>(dv_part),
-      static_cast<__nv_bfloat16 *>(dqv), d.L, d.H, d.nh, n_kinds,
-      static_cast<int64_t>(dr.BH) * dr.N * 64, rows, dr.QV, d.separate_k ? 1 : 0);
+  const unsigned nb = static_cast<unsigned>(blocks);
+  const __nv_bfloat16 *dq = static_cast<const __nv_bfloat16 *>(dq_part), *dv = static_cast<const __nv_bfloat16 *>(dv_part);
+  __nv_bfloat16 *out = static_cast<__nv_bfloat16 *>(dqv);
+  const int64_t kstride = static_cast<int64_t>(dr.BH) * dr.N * 64;
+  const int ksep = d.separate_k ? 1 : 0;
+  const int fast = (n_kinds == 1) ? d.nh : 0;
+#define LSH_SUM_ROUNDS(NH_) sum_rounds_kernel<NH_><<<nb, ROW_THREADS, 0, stream>>>(dq, dv, out, d.L, d.H, d.nh, n_kinds, kstride, rows, dr.QV, ksep)
+  switch (fast) {
+    case 1: LSH_SUM_ROUNDS(1); break;
+    case 2: LSH_SUM_ROUNDS(2); break;
+    case 4: LSH_SUM_ROUNDS(4); break;
+    case 8: LSH_SUM_ROUNDS(8); break;
+    default: LSH_SUM_ROUNDS(0); break;
+  }
+#undef LSH_SUM_ROUNDS
   LSH_CHECK_LAUNCH("sum_rounds_kernel");
   return 0;
 }
