@@ -13,10 +13,13 @@
 //   warps 2-9 epilogue (two warpgroups, each owns half of the tile's columns; a warp reads the TMEM lane quarter warp % 4):
 //            TMEM -> registers (32 columns at a time, next load in flight) -> per-warp staging tile -> bf16 / fp32 row
 //            segments in global memory, while the issuer is already accumulating the next tile in the other accumulator.
-// CLUSTER = 2: the two CTAs of a cluster compute vertically adjacent tiles (same n block) and SHARE the weight tile: each
-// loads half of it and multicasts it into both shared memories (`.multicast::cluster`), which halves the L2 -> SM traffic of
-// the B operand (a 1-CTA 128 x 256 tile needs 94 B/clk/SM from L2 against ~43 B/clk/SM available chip-wide,
-// B300_MICROARCH.md "LTS throughput cap"); a stage is refilled only after BOTH CTAs' MMAs have read it (commit multicast).
+// CLUSTER = 2: the two CTAs of a cluster form ONE `cta_group::2` tensor-core pair computing a 256 x BN tile: each CTA loads
+// its own 128 rows of A and HALF of the weight tile (B rows [rank BN/2, +BN/2)) — `cp.async.bulk.tensor ... cta_group::2`
+// signals the LEADER's (rank 0) barrier from both CTAs — and the leader's issuer alone issues `tcgen05.mma.cta_group::2`
+// (M 256: the hardware reads A / B halves from both shared memories and accumulates 128 rows in each CTA's TMEM); stages and
+// accumulators are handed back with multicast commits.  Per CTA and K block this moves 16 + 16 KB through shared memory
+// instead of 16 + 32 KB (the 1-CTA form, and the round-2 multicast form, are bound by the 128 B/clk shared-memory port: 48 KB
+// written by TMA + 48 KB read by the MMAs per 512 tensor cycles), and halves the L2 -> SM traffic of B.
 // Shapes the kernel does not cover (N % 128, K % 64, unaligned pointers) are reported to the caller, which then uses cuBLAS.
 #include <stdlib.h>
 #include <string.h>
@@ -25,7 +28,7 @@
 
 namespace lsh {
 
-constexpr int GM_BM = 128, GM_BK = 64, GM_STAGES = 4;
+constexpr int GM_BM = 128, GM_BK = 64;
 constexpr int GM_EPI_WARPS = 8;                     // two warpgroups, each drains half of the tile's columns
 constexpr int GM_THREADS = 64 + 32 * GM_EPI_WARPS;
 
@@ -49,16 +52,50 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
                ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
                : "memory");
 }
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, uint16_t mask) {
+// shared::cluster address of the same shared-memory offset in the LEADER CTA (cluster rank 0) of the pair
+__device__ __forceinline__ uint32_t leader_addr(const void *p) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;\n" : "=r"(r) : "r"(smem_u32(p)));
+  return r;
+}
+// cta_group::2 forms: the load's completion bytes go to the LEADER CTA's barrier, whichever CTA of the pair issues it
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap *map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void umma_ss2_2sm(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                             uint32_t idesc, uint32_t accum) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;\n"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1)
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum)
       : "memory");
 }
-__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
+// arrives (once all MMAs issued so far have completed) on the barrier at this offset in EVERY CTA of `mask`
+__device__ __forceinline__ void umma_commit_2sm_mc(uint64_t *bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
                ::"r"(smem_u32(bar)), "h"(mask)
                : "memory");
+}
+// ordinary arrival on the LEADER CTA's barrier at this offset (from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) {
+  // (default semantics, as CUTLASS's umma_arrive_2x1SM_sm0: a `.release.cluster` arrive compiles to ERRBAR + a cluster-scope
+  // fence that waits for the warp's outstanding global stores of the C tile — measured: ~40 % of the epilogue's samples.  What
+  // the issuer needs ordered before this arrival are the TMEM reads: tcgen05.wait::ld + tcgen05.fence::before_thread_sync.)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(leader_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t *dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(dst_smem)), "r"(ncols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::);
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols));
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -69,8 +106,9 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
 
+constexpr int GM_MAX_STAGES = 6;
 struct __align__(16) GemmShared {
-  uint64_t full[GM_STAGES], empty[GM_STAGES], acc_full[2], acc_empty[2];
+  uint64_t full[GM_MAX_STAGES], empty[GM_MAX_STAGES], acc_full[2], acc_empty[2];
   uint32_t tmem_base;
 };
 
@@ -78,23 +116,28 @@ struct __align__(16) GemmShared {
 // the weight-gradient products dW = act^T · cotangent, contraction over the B L token rows; tiles are boxes of 64 columns x 64
 // K-rows (MN-major SWIZZLE_128B operands, 8 KB per 64-wide group), K is split over the clusters (fp32 partials, summed by
 // sum_partials_kernel in a fixed order).
+__host__ __device__ constexpr int gemm_stages(int cl) { return cl == 2 ? 6 : 4; }
+
 template <int BN, int CL, bool MN>
 __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int A_BYTES = GM_BM * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int A_BYTES = GM_BM * 128, B_BYTES = (BN / CL) * 128, STAGE_BYTES = A_BYTES + B_BYTES;   // per CTA
+  constexpr int GM_STAGES = gemm_stages(CL);
   __shared__ GemmShared sh;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
   const uint32_t smem_u = smem_u32(smem);
   const uint32_t stage_u = smem_u + GM_STAGES * STAGE_BYTES;          // epilogue staging: GM_EPI_WARPS x 4 KB
 
-  if (warp == 1) tmem_alloc(&sh.tmem_base, 512);
+  if (warp == 1) { if (CL == 2) tmem_alloc_2sm(&sh.tmem_base, 512); else tmem_alloc(&sh.tmem_base, 512); }
   if (tid == 0) {
     tma_prefetch_desc(&p.tm_a);
     tma_prefetch_desc(&p.tm_b);
-    for (int i = 0; i < GM_STAGES; ++i) { mbar_init(&sh.full[i], 1); mbar_init(&sh.empty[i], CL); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&sh.acc_full[i], 1); mbar_init(&sh.acc_empty[i], GM_EPI_WARPS); }
+    // CL = 2: `full` and `acc_empty` are used in the leader CTA only (both CTAs' loads / epilogue warps arrive there);
+    // `empty` and `acc_full` receive one multicast commit per phase in each CTA
+    for (int i = 0; i < GM_STAGES; ++i) { mbar_init(&sh.full[i], 1); mbar_init(&sh.empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sh.acc_full[i], 1); mbar_init(&sh.acc_empty[i], CL * GM_EPI_WARPS); }
     fence_mbar_init();
   }
   tc_fence_before();
@@ -124,25 +167,28 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
         mbar_wait(&sh.empty[s], ((it / GM_STAGES) & 1) ^ 1);
         if (elect_one()) {
           const uint32_t a_dst = smem_u + s * STAGE_BYTES, b_dst = a_dst + A_BYTES;
-          constexpr uint16_t ALL = static_cast<uint16_t>((1u << CL) - 1);
-          mbar_arrive_expect_tx(&sh.full[s], STAGE_BYTES);
+          if (CL == 1) mbar_arrive_expect_tx(&sh.full[s], STAGE_BYTES);
+          else if (rank == 0) mbar_arrive_expect_tx(&sh.full[s], 2 * STAGE_BYTES);      // both CTAs' bytes land on the leader's barrier
           if constexpr (!MN) {
-            tma_load_2d(a_dst, &p.tm_a, &sh.full[s], kb * GM_BK, m_blk * GM_BM);     // rows past M read as zeros
             if (CL == 1) {
+              tma_load_2d(a_dst, &p.tm_a, &sh.full[s], kb * GM_BK, m_blk * GM_BM);     // rows past M read as zeros
               tma_load_2d(b_dst, &p.tm_b, &sh.full[s], kb * GM_BK, n_blk * BN);
-            } else {                                                   // my half of the weight tile, into both CTAs
-              tma_load_2d_mc(b_dst + rank * (B_BYTES / 2), &p.tm_b, &sh.full[s], kb * GM_BK, n_blk * BN + rank * (BN / 2), ALL);
+            } else {                                                   // my rows of A, my half of the weight tile
+              tma_load_2d_2sm(a_dst, &p.tm_a, leader_addr(&sh.full[s]), kb * GM_BK, m_blk * GM_BM);
+              tma_load_2d_2sm(b_dst, &p.tm_b, leader_addr(&sh.full[s]), kb * GM_BK, n_blk * BN + static_cast<int>(rank) * (BN / 2));
             }
           } else {
-            // 64-column groups: 2 of A (mine), BN / 64 of B (CL = 2: half of them loaded here and multicast to the partner)
+            // 64-column groups: 2 of A (mine), BN / 64 / CL of B (CL = 2: my half of the tile's column groups)
 #pragma unroll
-            for (int gq = 0; gq < GM_BM / 64; ++gq)
-              tma_load_2d(a_dst + gq * 8192, &p.tm_a, &sh.full[s], m_blk * GM_BM + gq * 64, kb * GM_BK);
+            for (int gq = 0; gq < GM_BM / 64; ++gq) {
+              if (CL == 1) tma_load_2d(a_dst + gq * 8192, &p.tm_a, &sh.full[s], m_blk * GM_BM + gq * 64, kb * GM_BK);
+              else tma_load_2d_2sm(a_dst + gq * 8192, &p.tm_a, leader_addr(&sh.full[s]), m_blk * GM_BM + gq * 64, kb * GM_BK);
+            }
 #pragma unroll
             for (int gq = 0; gq < BN / 64 / CL; ++gq) {
               const int grp = static_cast<int>(rank) * (BN / 64 / CL) + gq;
-              if (CL == 1) tma_load_2d(b_dst + grp * 8192, &p.tm_b, &sh.full[s], n_blk * BN + grp * 64, kb * GM_BK);
-              else tma_load_2d_mc(b_dst + grp * 8192, &p.tm_b, &sh.full[s], n_blk * BN + grp * 64, kb * GM_BK, ALL);
+              if (CL == 1) tma_load_2d(b_dst + gq * 8192, &p.tm_b, &sh.full[s], n_blk * BN + grp * 64, kb * GM_BK);
+              else tma_load_2d_2sm(b_dst + gq * 8192, &p.tm_b, leader_addr(&sh.full[s]), n_blk * BN + grp * 64, kb * GM_BK);
             }
           }
         }
@@ -150,9 +196,10 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
       }
     }
   } else if (warp == 1) {
-    // ================================ MMA issuer =======================================================
+    // ================================ MMA issuer (CL = 2: the leader CTA's, for the pair) ==================
     constexpr uint32_t HI = desc_hi(1024);
-    constexpr uint32_t IDESC = make_idesc_bf16(GM_BM, BN, MN ? 1 : 0, MN ? 1 : 0);
+    constexpr uint32_t IDESC = make_idesc_bf16(GM_BM * CL, BN, MN ? 1 : 0, MN ? 1 : 0);
+    if (CL == 1 || rank == 0) {
     // K-major: 128-byte rows, next K16 step = +32 bytes inside the row.  MN-major: 64-wide groups 8 KB apart (LBO), next K16
     // step = 16 K-rows = +2048 bytes
     constexpr uint32_t LBO = MN ? 8192 : 16, KSTEP = MN ? 128 : 2;
@@ -170,15 +217,23 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
         tc_fence_after();
         const uint32_t a_lo = desc_lo(smem_u + s * STAGE_BYTES, LBO), b_lo = desc_lo(smem_u + s * STAGE_BYTES + A_BYTES, LBO);
         if (elect_one()) {
+          if (CL == 1) {
 #pragma unroll
-          for (int ks = 0; ks < GM_BK / 16; ++ks)
-            umma_ss2(d_t, a_lo + ks * KSTEP, HI, b_lo + ks * KSTEP, HI, IDESC, (kb > kb0 || ks > 0) ? 1u : 0u);
-          if (CL == 1) umma_commit(&sh.empty[s]);
-          else umma_commit_mc(&sh.empty[s], static_cast<uint16_t>((1u << CL) - 1));
-          if (kb == kb1 - 1) umma_commit(&sh.acc_full[acc]);
+            for (int ks = 0; ks < GM_BK / 16; ++ks)
+              umma_ss2(d_t, a_lo + ks * KSTEP, HI, b_lo + ks * KSTEP, HI, IDESC, (kb > kb0 || ks > 0) ? 1u : 0u);
+            umma_commit(&sh.empty[s]);
+            if (kb == kb1 - 1) umma_commit(&sh.acc_full[acc]);
+          } else {
+#pragma unroll
+            for (int ks = 0; ks < GM_BK / 16; ++ks)
+              umma_ss2_2sm(d_t, a_lo + ks * KSTEP, HI, b_lo + ks * KSTEP, HI, IDESC, (kb > kb0 || ks > 0) ? 1u : 0u);
+            umma_commit_2sm_mc(&sh.empty[s], 3);                       // the stage is free in both CTAs
+            if (kb == kb1 - 1) umma_commit_2sm_mc(&sh.acc_full[acc], 3);   // both CTAs' epilogues drain their 128 rows
+          }
         }
         __syncwarp();
       }
+    }
     }
   } else {
     // ================================ epilogue warps ====================================================
@@ -291,13 +346,13 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sh.acc_empty[acc]);
+      if (lane == 0) { if (CL == 1) mbar_arrive(&sh.acc_empty[acc]); else mbar_arrive_leader(&sh.acc_empty[acc]); }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (CL > 1) cluster_sync_all();          // no CTA leaves while its peer may still multicast into it
-  if (warp == 1) tmem_dealloc(tmem, 512);
+  if (warp == 1) { if (CL == 2) tmem_dealloc_2sm(tmem, 512); else tmem_dealloc(tmem, 512); }
 }
 
 int make_tile_map(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes, uint32_t box_cols,
@@ -305,7 +360,7 @@ int make_tile_map(CUtensorMap *map, const void *base, uint64_t rows, uint64_t co
 
 template <int BN, int CL, bool MN>
 static int gemm_tc_launch(const GemmTcParams &p, cudaStream_t stream) {
-  const size_t smem = static_cast<size_t>(GM_STAGES) * (GM_BM * 128 + BN * 128) + GM_EPI_WARPS * 4096 + 1024;
+  const size_t smem = static_cast<size_t>(gemm_stages(CL)) * (GM_BM * 128 + (BN / CL) * 128) + GM_EPI_WARPS * 4096 + 1024;
   auto kernel = gemm_tc_kernel<BN, CL, MN>;
   LSH_OPT_IN_SMEM(kernel);
   int dev = 0, sms = 148;
