@@ -47,6 +47,7 @@ int attend_bwd_run(const LshAttnDims &, const void *, const int32_t *, const uin
                    const void *, const float *, const int32_t *, const int32_t *, const AttnKeep *, void *, void *, size_t,
                    cudaStream_t);
 int pack_weights_run(const LshAttnDims &, const float *, const float *, const float *, const float *, void *, void *, cudaStream_t);
+int pack_all_run(const LshAttnDims &, const float *, const float *, const float *, const float *, void *, void *, void *, void *, cudaStream_t);
 int f32_to_bf16_run(const float *, void *, int64_t, cudaStream_t);
 int unpack_dwqv_run(const LshAttnDims &, const float *, float *, float *, float *, cudaStream_t);
 int make_rotations_run(const LshAttnDims &, const uint32_t *, uint32_t *, float *, cudaStream_t);
@@ -134,8 +135,10 @@ static int gemm_aw(int64_t M, int64_t N, int64_t K, const void *A, int64_t lda, 
 }
 
 // Weight gradient C[M, N] (f32) = A^T · B, A (K, M), B (K, N) bf16: the split-K tensor-core kernel, else cuBLAS.
-static int gemm_wgrad(int64_t M, int64_t N, int64_t K, const void *A, const void *B, float *C, void *cws, cudaStream_t stream) {
-  const int rc = gemm_tc_wgrad_run(M, N, K, A, M, B, N, C, cws, cws ? kCublasWs : 0, stream);
+static int gemm_wgrad(int64_t M, int64_t N, int64_t K, const void *A, const void *B, float *C, void *cws, cudaStream_t stream,
+                      const WgradUnpack *up = nullptr, bool *unpacked = nullptr) {
+  if (unpacked) *unpacked = false;
+  const int rc = gemm_tc_wgrad_run(M, N, K, A, M, B, N, C, cws, cws ? kCublasWs : 0, stream, up, unpacked);
   if (rc >= 0) return rc;
   return gemm_rm(true, false, M, N, K, A, M, B, N, C, N, true, cws, stream);
 }
@@ -232,6 +235,8 @@ static LayerWs carve(const LshAttnDims &d, void *ws, bool with_grad) {
 static int pack_layer_weights(const LshAttnDims &d, const LayerWs &w, const float *w_q, const float *w_v, const float *w_o,
                               const float *w_k, cudaStream_t s) {
   Derived dr = derive(d);
+  const int rc1 = pack_all_run(d, w_q, w_v, w_o, w_k, w.wqv, w.wqv_t, w.wo, w.wo_t, s);   // one launch for all four layouts
+  if (rc1 >= 0) return rc1;
   if (int rc = pack_weights_run(d, w_q, w_v, w_o, w_k, w.wqv, w.wo, s)) return rc;
   if (int rc = transpose_bf16_run(w.wqv, w.wqv_t, d.D, d.H * dr.QV, s)) return rc;
   return transpose_bf16_run(w.wo, w.wo_t, d.H * d.dv, d.D, s);
@@ -482,8 +487,10 @@ int lsh_layer_bwd(const LshAttnDims *dims, const void *x, const float *w_q, cons
   if ((rc = attend_bwd_run(d, w.qv, w.sticker, mask, w.o_comb, w.lse_tot, w.do_comb, w.aux.qscale, attend_fwd_uses_tc(d) ? w.aux.sticker2 : nullptr, attend_fwd_uses_tc(d) ? w.aux.bounds : nullptr, kp, w.dqv, w.bwd_ws, w.bwd_bytes, s)))
     return rc;
   // B7: dW_q|dW_v = x^T·dqv ; dx = dqv·wqv^T
-  if ((rc = gemm_wgrad(d.D, NQV, BL, xb, w.dqv, w.dwqv, w.cublas, s))) return rc;
-  if ((rc = unpack_dwqv_run(d, w.dwqv, dw_q, dw_v, dw_k, s))) return rc;
+  const WgradUnpack up = {dw_q, dw_v, dw_k, d.H, d.D, d.dq, d.dv};
+  bool unpacked = false;
+  if ((rc = gemm_wgrad(d.D, NQV, BL, xb, w.dqv, w.dwqv, w.cublas, s, &up, &unpacked))) return rc;
+  if (!unpacked && (rc = unpack_dwqv_run(d, w.dwqv, dw_q, dw_v, dw_k, s))) return rc;
   if (ev_dwqv_ready) LSH_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(ev_dwqv_ready), s));
   return gemm_aw(BL, d.D, NQV, w.dqv, NQV, w.wqv, nullptr, dx, d.D, f32, w.cublas, s);
 }

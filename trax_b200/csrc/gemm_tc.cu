@@ -437,11 +437,33 @@ __global__ void __launch_bounds__(256) sum_partials_kernel(const float4 *__restr
   }
 }
 
+// Same sum, but of the (D, H, dq | dv (| dq)) weight gradient of the q|v(|k) projection, written straight into the reference's
+// per-head layouts dw_q (H, D, dq), dw_v (H, D, dv) (, dw_k (H, D, dq)): the separate unpack kernel's launch and its 2 x 4 MB
+// of traffic are folded into the pass that reads the partials anyway.
+__global__ void __launch_bounds__(256) sum_partials_unpack_kernel(const float4 *__restrict__ part, int64_t n4, int splits, WgradUnpack up) {
+  const int QV = up.dq + up.dv + (up.dw_k ? up.dq : 0), NQV = up.H * QV;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float4 a = part[i];
+    for (int s = 1; s < splits; ++s) {
+      const float4 b = part[s * n4 + i];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    const int64_t e = i * 4;                                        // element (dm, h, c), four consecutive c (dq, dv multiples of 4)
+    const int dm = static_cast<int>(e / NQV), col = static_cast<int>(e - static_cast<int64_t>(dm) * NQV);
+    const int h = col / QV, c = col - h * QV;
+    float *dst = c < up.dq ? up.dw_q + (static_cast<int64_t>(h) * up.D + dm) * up.dq + c
+                 : c < up.dq + up.dv ? up.dw_v + (static_cast<int64_t>(h) * up.D + dm) * up.dv + (c - up.dq)
+                                     : up.dw_k + (static_cast<int64_t>(h) * up.D + dm) * up.dq + (c - up.dq - up.dv);
+    *reinterpret_cast<float4 *>(dst) = a;
+  }
+}
+
 // Weight gradient C[M, N] (f32, row pitch N) = A^T · B with A (K, M) (row pitch lda) and B (K, N) (row pitch ldb), bf16, the
 // contraction running over the K = B L token rows (EA:2431 sums examples: they are rows of the same product).  `scratch`
 // holds the split-K partials.  Returns like gemm_tc_run (-1: shape not covered).
 int gemm_tc_wgrad_run(int64_t M, int64_t N, int64_t K, const void *A, int64_t lda, const void *B, int64_t ldb, float *C,
-                      void *scratch, size_t scratch_bytes, cudaStream_t stream) {
+                      void *scratch, size_t scratch_bytes, cudaStream_t stream, const WgradUnpack *up, bool *unpacked) {
+  if (unpacked) *unpacked = false;
   static const int mode = [] {
     const char *e = getenv("LSH_GEMM");
     if (!e) return 2;
@@ -477,8 +499,15 @@ int gemm_tc_wgrad_run(int64_t M, int64_t N, int64_t K, const void *A, int64_t ld
   else rc = cl == 2 ? gemm_tc_launch<128, 2, true>(p, stream) : gemm_tc_launch<128, 1, true>(p, stream);
   if (rc || splits == 1) return rc;
   const int64_t n4 = M * N / 4;
-  sum_partials_kernel<<<static_cast<unsigned>((n4 + 255) / 256 < 148 * 8 ? (n4 + 255) / 256 : 148 * 8), 256, 0, stream>>>(
-      static_cast<const float4 *>(scratch), reinterpret_cast<float4 *>(C), n4, static_cast<int>(splits));
+  const unsigned nb = static_cast<unsigned>((n4 + 255) / 256 < 148 * 8 ? (n4 + 255) / 256 : 148 * 8);
+  if (up && unpacked && up->dq % 4 == 0 && up->dv % 4 == 0 && M == up->D &&
+      N == static_cast<int64_t>(up->H) * (up->dq + up->dv + (up->dw_k ? up->dq : 0))) {
+    sum_partials_unpack_kernel<<<nb, 256, 0, stream>>>(static_cast<const float4 *>(scratch), n4, static_cast<int>(splits), *up);
+    LSH_CHECK_LAUNCH("sum_partials_unpack_kernel");
+    *unpacked = true;
+    return 0;
+  }
+  sum_partials_kernel<<<nb, 256, 0, stream>>>(static_cast<const float4 *>(scratch), reinterpret_cast<float4 *>(C), n4, static_cast<int>(splits));
   LSH_CHECK_LAUNCH("sum_partials_kernel");
   return 0;
 }

@@ -120,6 +120,66 @@ int pack_weights_run(const LshAttnDims &d, const float *w_q, const float *w_v, c
   return 0;
 }
 
+// All four packed bf16 weight layouts of a layer call in ONE launch (the separate pack / convert / two transposes cost four
+// latency-bound launches, ~28 us per call at config 2, for 6 MB of weights):
+//   wqv   (D, H*QV)   = [w_q | w_v (| w_k)] per head, row = model dimension       (weight-gradient layout; B operand of dx)
+//   wqv_t (H*QV, D)   = its transpose                                              (B operand of the q|v projection)
+//   wo    (H*dv, D)   = w_o                                                        (B operand of do = dout w_o^T)
+//   wo_t  (D, H*dv)   = its transpose                                              (B operand of the output projection)
+// One CTA = one 32 x 32 tile of one head's matrix; blockIdx.x enumerates the w_q | w_v | w_k tiles, then the w_o tiles.
+__global__ void __launch_bounds__(256) pack_all_kernel(const float *__restrict__ w_q, const float *__restrict__ w_v,
+                                                       const float *__restrict__ w_k, const float *__restrict__ w_o,
+                                                       __nv_bfloat16 *__restrict__ wqv, __nv_bfloat16 *__restrict__ wqv_t,
+                                                       __nv_bfloat16 *__restrict__ wo, __nv_bfloat16 *__restrict__ wo_t,
+                                                       int H, int D, int dq, int dv, int n_qv_tiles) {
+  __shared__ __nv_bfloat16 tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int QV = dq + dv + (w_k ? dq : 0), NQV = H * QV, KO = H * dv;
+  int t = blockIdx.x;
+  if (t < n_qv_tiles) {
+    // tile (h, dm0, c0) of the (D, QV) matrix of head h
+    const int ct = QV / 32, dt = D / 32;
+    const int c0 = (t % ct) * 32, dm0 = ((t / ct) % dt) * 32, h = t / (ct * dt);
+    const float *src; int cs, width;
+    if (c0 < dq) { src = w_q; cs = c0; width = dq; }
+    else if (c0 < dq + dv) { src = w_v; cs = c0 - dq; width = dv; }
+    else { src = w_k; cs = c0 - dq - dv; width = dq; }
+    for (int i = ty; i < 32; i += 8) {
+      const __nv_bfloat16 v = __float2bfloat16_rn(src[(static_cast<int64_t>(h) * D + dm0 + i) * width + cs + tx]);
+      tile[i][tx] = v;
+      wqv[static_cast<int64_t>(dm0 + i) * NQV + h * QV + c0 + tx] = v;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) wqv_t[static_cast<int64_t>(h * QV + c0 + i) * D + dm0 + tx] = tile[tx][i];
+  } else {
+    t -= n_qv_tiles;
+    // tile (h, e0, dm0) of the (dv, D) matrix of head h
+    const int dt = D / 32, et = dv / 32;
+    const int dm0 = (t % dt) * 32, e0 = ((t / dt) % et) * 32, h = t / (dt * et);
+    for (int i = ty; i < 32; i += 8) {
+      const __nv_bfloat16 v = __float2bfloat16_rn(w_o[(static_cast<int64_t>(h) * dv + e0 + i) * D + dm0 + tx]);
+      tile[i][tx] = v;
+      wo[static_cast<int64_t>(h * dv + e0 + i) * D + dm0 + tx] = v;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) wo_t[static_cast<int64_t>(dm0 + i) * KO + h * dv + e0 + tx] = tile[tx][i];
+  }
+}
+
+// Returns -1 when the shape is outside the fused kernel's tiling (the caller then runs the separate kernels).
+int pack_all_run(const LshAttnDims &d, const float *w_q, const float *w_v, const float *w_o, const float *w_k, void *wqv,
+                 void *wqv_t, void *wo, void *wo_t, cudaStream_t stream) {
+  if ((d.separate_k != 0) != (w_k != nullptr)) return set_error("pack_weights: w_k must be given exactly when dims.separate_k is set");
+  if (d.D % 32 != 0 || d.dq % 32 != 0 || d.dv % 32 != 0) return -1;
+  const int QV = derive(d).QV;
+  const int n_qv = d.H * (d.D / 32) * (QV / 32), n_o = d.H * (d.dv / 32) * (d.D / 32);
+  pack_all_kernel<<<n_qv + n_o, 256, 0, stream>>>(w_q, w_v, w_k, w_o, static_cast<__nv_bfloat16 *>(wqv),
+                                                  static_cast<__nv_bfloat16 *>(wqv_t), static_cast<__nv_bfloat16 *>(wo),
+                                                  static_cast<__nv_bfloat16 *>(wo_t), d.H, d.D, d.dq, d.dv, n_qv);
+  LSH_CHECK_LAUNCH("pack_all_kernel");
+  return 0;
+}
+
 // src (R, C) bf16 -> dst (C, R) bf16: the K-major copy of a packed weight for the tensor-core GEMM (weights only: a few MB)
 __global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16 *__restrict__ src, __nv_bfloat16 *__restrict__ dst,
                                                              int R, int C) {

@@ -23,8 +23,14 @@ struct GemmQStats {
 };
 int gemm_tc_run(int64_t M, int64_t N, int64_t K, const void *A, int64_t lda, const void *B, int64_t ldb, void *C, int64_t ldc,
                 bool c_f32, cudaStream_t stream, const GemmQStats *qs = nullptr);
+// Optional destination of the q|v(|k) weight gradient in the reference's per-head layouts (see sum_partials_unpack_kernel).
+struct WgradUnpack {
+  float *dw_q, *dw_v, *dw_k;
+  int H, D, dq, dv;
+};
 int gemm_tc_wgrad_run(int64_t M, int64_t N, int64_t K, const void *A, int64_t lda, const void *B, int64_t ldb, float *C,
-                      void *scratch, size_t scratch_bytes, cudaStream_t stream);
+                      void *scratch, size_t scratch_bytes, cudaStream_t stream, const WgradUnpack *up = nullptr,
+                      bool *unpacked = nullptr);
 
 #ifdef __CUDACC__
 
