@@ -537,7 +537,9 @@ class LSHSelfAttention:
         keys = to_dev(_to_int32_bits(hash_rng)).contiguous()
         rotations, new_keys = ops.make_rotations(dims, keys)        # split + normal (EA:1928, 92)
         new_rng = new_keys.view(torch.uint32) if hasattr(torch, 'uint32') else new_keys
-      buckets_d = torch.zeros((bh, max(length, self._n_hashes * seqlen)), dtype=torch.int32, device=dev)
+      # the hash kernel writes every (round, position) entry; only the padding up to max_length_for_buckets needs zeros
+      alloc = torch.zeros if length > self._n_hashes * seqlen else torch.empty
+      buckets_d = alloc((bh, max(length, self._n_hashes * seqlen)), dtype=torch.int32, device=dev)
     else:                                                           # EA:1939-1941
       buckets_d = to_dev(buckets)
       if buckets_d.dtype != torch.int32 or buckets_d.dim() != 2 or buckets_d.shape[0] != bh \
