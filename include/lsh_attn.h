@@ -162,6 +162,14 @@ int lsh_residual_sub(int64_t n, int act_dtype, const void *a, const void *b, voi
 /* reversible.py:318 output = accumulator + residual. */
 int lsh_residual_add(int64_t n, int act_dtype, const void *a, const void *b, void *out, void *stream);
 
+/* Head layout plumbing of the weight-less core, PureLSHSelfAttention (EA:2564; inputs (batch*heads, seqlen, d_head),
+ * EA:3052-3070):  a (BH, L, da) [, b (BH, L, db), or NULL with db = 0] in act_dtype  ->  dst (B, L, H, da + db) bf16, the
+ * (token, head) row layout `lsh_hash` / `lsh_attend_fwd` / `lsh_attend_bwd` read ([qk | v] side by side).  Widths % 8 == 0. */
+int lsh_pack_heads(int B, int H, int L, int act_dtype, const void *a, int da, const void *b, int db, void *dst, void *stream);
+/* src (B, L, H, d_total) bf16, columns [col0, col0 + d)  ->  dst (BH, L, d) in act_dtype: the core's output (from o_comb) and
+ * its input cotangents (dqk, dv from dqv), EA:3245-3265. */
+int lsh_unpack_heads(int B, int H, int L, int act_dtype, const void *src, int d_total, int col0, int d, void *dst, void *stream);
+
 /* ---- layer-level entry points (EA:2261-2561 forward_and_or_backward) -------------------------- */
 
 size_t lsh_layer_workspace_bytes(const LshAttnDims *dims, int with_grad);

@@ -134,3 +134,22 @@ def test_pure_lsh_wrapper_matches_oracle(num_weights, bias, rotary, dtype):
       util.assert_close_layer(got.float().cpu().numpy(), want, 'wrapper d_qkv[%d]' % i)
   for got, want in zip(leaves(dw[3]), leaves(want_ddense)):
     util.assert_close_layer(got.float().cpu().numpy(), want, 'wrapper d_dense')
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_head_pack_and_unpack_kernels_match_the_torch_layout_ops(dtype):
+  """`lsh_pack_heads` / `lsh_unpack_heads` against the cat / permute / cast they replace on the core's path (EA:3052-3070,
+  3245-3265): bit-exact in both directions, both dtypes, ragged widths."""
+  from trax_b200 import ops
+  B, H, L = 2, 3, 257
+  g = torch.Generator('cuda').manual_seed(3)
+  qk = torch.randn(B * H, L, 64, device='cuda', generator=g).to(dtype)
+  v = torch.randn(B * H, L, 40, device='cuda', generator=g).to(dtype)
+  got = ops.pack_heads(qk, v, H)
+  want = torch.cat([qk.view(B, H, L, 64), v.view(B, H, L, 40)], dim=3).permute(0, 2, 1, 3).to(torch.bfloat16).contiguous()
+  assert got.shape == want.shape and torch.equal(got, want)
+  single = ops.pack_heads(v, None, H)
+  assert torch.equal(single, v.view(B, H, L, 40).permute(0, 2, 1, 3).to(torch.bfloat16).contiguous())
+  back_q = ops.unpack_heads(got, 0, 64, dtype)
+  back_v = ops.unpack_heads(got, 64, 40, dtype)
+  assert torch.equal(back_q, qk.to(torch.bfloat16).to(dtype)) and torch.equal(back_v, v.to(torch.bfloat16).to(dtype))

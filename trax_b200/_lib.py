@@ -53,6 +53,8 @@ SIGNATURES = {
     'lsh_layernorm_bwd': (_I, [_I64, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'lsh_residual_sub': (_I, [_I64, _I, _P, _P, _P, _P]),
     'lsh_residual_add': (_I, [_I64, _I, _P, _P, _P, _P]),
+    'lsh_pack_heads': (_I, [_I, _I, _I, _I, _P, _I, _P, _I, _P, _P]),
+    'lsh_unpack_heads': (_I, [_I, _I, _I, _I, _P, _I, _I, _I, _P, _P]),
     'lsh_attn_launch_count': (_I64, [_I]),
 }
 

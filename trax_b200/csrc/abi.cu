@@ -50,6 +50,8 @@ int pack_weights_run(const LshAttnDims &, const float *, const float *, const fl
 int pack_all_run(const LshAttnDims &, const float *, const float *, const float *, const float *, void *, void *, void *, void *, cudaStream_t);
 int f32_to_bf16_run(const float *, void *, int64_t, cudaStream_t);
 int unpack_dwqv_run(const LshAttnDims &, const float *, float *, float *, float *, cudaStream_t);
+int pack_heads_run(int, int, int, int, const void *, int, const void *, int, void *, cudaStream_t);
+int unpack_heads_run(int, int, int, int, const void *, int, int, int, void *, cudaStream_t);
 int make_rotations_run(const LshAttnDims &, const uint32_t *, uint32_t *, float *, cudaStream_t);
 int layernorm_fwd_run(int64_t, int, int, const void *, const float *, const float *, void *, float2 *, float, cudaStream_t);
 int layernorm_bwd_run(int64_t, int, int, const void *, const void *, const void *, const float2 *, const float *, void *, float *,
@@ -521,6 +523,18 @@ int lsh_residual_add(int64_t n, int act_dtype, const void *a, const void *b, voi
   if (!a || !b || !out) return set_error("lsh_residual_add: NULL argument");
   if (act_dtype != LSH_DTYPE_F32 && act_dtype != LSH_DTYPE_BF16) return set_error("lsh_residual_add: bad act_dtype");
   return residual_sub_run(n, act_dtype, a, b, out, 1.f, static_cast<cudaStream_t>(stream));
+}
+
+int lsh_pack_heads(int B, int H, int L, int act_dtype, const void *a, int da, const void *b, int db, void *dst, void *stream) {
+  if (!a || !dst) return set_error("lsh_pack_heads: NULL argument");
+  if (act_dtype != LSH_DTYPE_F32 && act_dtype != LSH_DTYPE_BF16) return set_error("lsh_pack_heads: bad act_dtype");
+  return pack_heads_run(B, H, L, act_dtype, a, da, b, db, dst, static_cast<cudaStream_t>(stream));
+}
+
+int lsh_unpack_heads(int B, int H, int L, int act_dtype, const void *src, int d_total, int col0, int d, void *dst, void *stream) {
+  if (!src || !dst) return set_error("lsh_unpack_heads: NULL argument");
+  if (act_dtype != LSH_DTYPE_F32 && act_dtype != LSH_DTYPE_BF16) return set_error("lsh_unpack_heads: bad act_dtype");
+  return unpack_heads_run(B, H, L, act_dtype, src, d_total, col0, d, dst, static_cast<cudaStream_t>(stream));
 }
 
 /* Debug aid (not in the public header): device buffer receiving per-phase clock stamps of CTA 0. */

@@ -213,6 +213,83 @@ int unpack_dwqv_run(const LshAttnDims &d, const float *dwqv, float *dw_q, float 
   return 0;
 }
 
+// ---- head layout plumbing of the weight-less core (EA:2564 PureLSHSelfAttention: inputs (batch*heads, seqlen, d_head)) ------
+// a (BH, L, da) [, b (BH, L, db)] in f32 or bf16  ->  dst (B, L, H, da + db) bf16: the (token, head) row layout every kernel
+// gathers from ([qk | v] side by side).  One thread = 8 consecutive elements (16 bytes of bf16).
+template <typename T>
+__global__ void __launch_bounds__(256) pack_heads_kernel(const T *__restrict__ a, int da, const T *__restrict__ b, int db,
+                                                         __nv_bfloat16 *__restrict__ dst, int H, int L, int64_t n_chunks) {
+  const int cpr = (da + db) >> 3;                                    // 16-byte chunks per destination row
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_chunks; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % cpr);
+    const int64_t row = i / cpr;                                     // (b, t, h)
+    const int h = static_cast<int>(row % H);
+    const int64_t bt = row / H, bb = bt / L, t = bt - bb * L;
+    const int64_t srow = (bb * H + h) * L + t;                       // (b h, t)
+    const int col = c * 8;
+    const T *src = col < da ? a + srow * da + col : b + srow * db + (col - da);
+    uint4 o;
+    if constexpr (sizeof(T) == 4) {
+      const float4 v0 = __ldg(reinterpret_cast<const float4 *>(src)), v1 = __ldg(reinterpret_cast<const float4 *>(src) + 1);
+      o.x = pack_bf16(v0.x, v0.y); o.y = pack_bf16(v0.z, v0.w); o.z = pack_bf16(v1.x, v1.y); o.w = pack_bf16(v1.z, v1.w);
+    } else {
+      o = __ldg(reinterpret_cast<const uint4 *>(src));
+    }
+    *reinterpret_cast<uint4 *>(dst + row * (da + db) + col) = o;
+  }
+}
+
+// src (B, L, H, d_total) bf16, columns [col0, col0 + d)  ->  dst (BH, L, d) in f32 or bf16 (the core's outputs / cotangents)
+template <typename T>
+__global__ void __launch_bounds__(256) unpack_heads_kernel(const __nv_bfloat16 *__restrict__ src, int d_total, int col0, int d,
+                                                           T *__restrict__ dst, int H, int L, int64_t n_chunks) {
+  const int cpr = d >> 3;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_chunks; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % cpr);
+    const int64_t drow = i / cpr;                                    // (b h, t)
+    const int64_t t = drow % L, bh = drow / L, bb = bh / H, h = bh - bb * H;
+    const int64_t srow = (bb * L + t) * H + h;
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + srow * d_total + col0 + c * 8));
+    if constexpr (sizeof(T) == 4) {
+      const float2 f0 = unpack_bf16(v.x), f1 = unpack_bf16(v.y), f2 = unpack_bf16(v.z), f3 = unpack_bf16(v.w);
+      float4 *o = reinterpret_cast<float4 *>(dst + drow * d + c * 8);
+      o[0] = make_float4(f0.x, f0.y, f1.x, f1.y);
+      o[1] = make_float4(f2.x, f2.y, f3.x, f3.y);
+    } else {
+      *reinterpret_cast<uint4 *>(dst + drow * d + c * 8) = v;
+    }
+  }
+}
+
+int pack_heads_run(int B, int H, int L, int act_dtype, const void *a, int da, const void *b, int db, void *dst, cudaStream_t stream) {
+  if (B < 1 || H < 1 || L < 1 || da < 8 || da % 8 != 0 || db < 0 || db % 8 != 0 || (db > 0) != (b != nullptr))
+    return set_error("lsh_pack_heads: widths must be multiples of 8 (da=%d, db=%d)", da, db);
+  const int64_t n = static_cast<int64_t>(B) * L * H * ((da + db) >> 3);
+  const unsigned grid = grid_for(n, 256);
+  if (act_dtype == LSH_DTYPE_F32)
+    pack_heads_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float *>(a), da, static_cast<const float *>(b), db,
+                                                       static_cast<__nv_bfloat16 *>(dst), H, L, n);
+  else
+    pack_heads_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(a), da, static_cast<const __nv_bfloat16 *>(b), db,
+                                                               static_cast<__nv_bfloat16 *>(dst), H, L, n);
+  LSH_CHECK_LAUNCH("pack_heads_kernel");
+  return 0;
+}
+
+int unpack_heads_run(int B, int H, int L, int act_dtype, const void *src, int d_total, int col0, int d, void *dst, cudaStream_t stream) {
+  if (B < 1 || H < 1 || L < 1 || d < 8 || d % 8 != 0 || col0 < 0 || col0 % 8 != 0 || d_total % 8 != 0 || col0 + d > d_total)
+    return set_error("lsh_unpack_heads: column range [%d, %d) of %d must be multiples of 8", col0, col0 + d, d_total);
+  const int64_t n = static_cast<int64_t>(B) * L * H * (d >> 3);
+  const unsigned grid = grid_for(n, 256);
+  if (act_dtype == LSH_DTYPE_F32)
+    unpack_heads_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(src), d_total, col0, d, static_cast<float *>(dst), H, L, n);
+  else
+    unpack_heads_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(src), d_total, col0, d,
+                                                                 static_cast<__nv_bfloat16 *>(dst), H, L, n);
+  LSH_CHECK_LAUNCH("unpack_heads_kernel");
+  return 0;
+}
+
 // ---- rotations: counter-based N(0,1) (stands in for jax.random.normal at EA:92) ---------------------
 __device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
 

@@ -168,3 +168,27 @@ def make_rotations(dims, keys):
 
 def launch_count(reset=False):
   return int(_lib.load().lsh_attn_launch_count(1 if reset else 0))
+
+
+def pack_heads(a, b, n_heads):
+  """(B*H, L, da) [, (B*H, L, db)] f32 / bf16 -> (B, L, H, da + db) bf16: the row layout of the core (one kernel, no torch glue)."""
+  lib = _lib.load()
+  bh, L, da = (int(v) for v in a.shape)
+  db = int(b.shape[2]) if b is not None else 0
+  if b is not None and (b.dtype != a.dtype or tuple(b.shape[:2]) != (bh, L)):
+    raise ValueError('pack_heads: operands must agree in dtype and leading shape')
+  B = bh // n_heads
+  dst = torch.empty((B, L, n_heads, da + db), dtype=torch.bfloat16, device=a.device)
+  _lib.check(lib.lsh_pack_heads(B, n_heads, L, _act_dtype(a), _ptr(a), da, _ptr(b), db, _ptr(dst), _stream()), 'lsh_pack_heads')
+  return dst
+
+
+def unpack_heads(src, col0, d, dtype):
+  """(B, L, H, d_total) bf16, columns [col0, col0 + d) -> (B*H, L, d) in `dtype` (f32 or bf16)."""
+  lib = _lib.load()
+  B, L, H, d_total = (int(v) for v in src.shape)
+  if src.dtype != torch.bfloat16:
+    raise ValueError('unpack_heads: source must be bf16')
+  dst = torch.empty((B * H, L, d), dtype=dtype, device=src.device)
+  _lib.check(lib.lsh_unpack_heads(B, H, L, _act_dtype(dst), _ptr(src), d_total, col0, d, _ptr(dst), _stream()), 'lsh_unpack_heads')
+  return dst

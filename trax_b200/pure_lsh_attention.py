@@ -93,8 +93,8 @@ class PureLSHSelfAttention(LSHSelfAttention):
     _lib.check(_lib.load().lsh_attn_check_dims(ctypes.byref(dims)), 'PureLSHSelfAttention')
     attn_keep = self._attention_multiplier(rng, dev)                # EA:254-262 keep matrix (None without dropout)
     # (B*H, L, d) x 2  ->  (B, L, H, [q | v]) bf16: the row layout every kernel gathers from
-    qv = torch.cat([qk.view(batch, self._n_heads, seqlen, self._d_qk), v.view(batch, self._n_heads, seqlen, self._d_v)],
-                   dim=3).permute(0, 2, 1, 3).to(torch.bfloat16).contiguous()
+    io_dtype = qk.dtype if qk.dtype in (torch.float32, torch.bfloat16) else torch.float32
+    qv = ops.pack_heads(qk.to(io_dtype).contiguous(), v.to(device=dev, dtype=io_dtype).contiguous(), self._n_heads)
     mask_d = inputs[2].to(device=dev, dtype=torch.uint8).contiguous() if self._masked else None
     buckets, hash_rng = state
     length = self._n_hashes * (self._max_length_for_buckets or seqlen)
@@ -122,14 +122,14 @@ class PureLSHSelfAttention(LSHSelfAttention):
     o_rounds, logits = ops.attend_fwd(dims, qv, sticker, mask=mask_d, attn_keep=attn_keep)   # EA:2780-2808 (un-sorted rows)
     o_comb, lse_tot = ops.combine_fwd(dims, o_rounds, logits)       # EA:2810-2814
 
-    def unpack(t, d):                                               # (B, L, H, d) -> (B*H, L, d) in the input dtype
-      return t.permute(0, 2, 1, 3).reshape(bh, seqlen, d).to(qk.dtype)
-    output = unpack(o_comb, self._d_v) if compute_output else None
+    def unpack(t, col0, d):                                         # (B, L, H, :) columns -> (B*H, L, d) in the input dtype
+      return ops.unpack_heads(t, col0, d, io_dtype).to(qk.dtype)
+    output = unpack(o_comb, 0, self._d_v) if compute_output else None
     inputs_grad = None
     if compute_grad:
-      do = output_grad.to(dev).view(batch, self._n_heads, seqlen, self._d_v).permute(0, 2, 1, 3).to(torch.bfloat16).contiguous()
+      do = ops.pack_heads(output_grad.to(device=dev, dtype=io_dtype).contiguous(), None, self._n_heads)
       dqv = ops.attend_bwd(dims, qv, sticker, o_comb, lse_tot, do, mask=mask_d, attn_keep=attn_keep)
-      inputs_grad = (unpack(dqv[..., :self._d_qk], self._d_qk), unpack(dqv[..., self._d_qk:], self._d_v))
+      inputs_grad = (unpack(dqv, 0, self._d_qk), unpack(dqv, self._d_qk, self._d_v))
       if self._masked:
         inputs_grad = inputs_grad + (None,)
     return output, new_state, inputs_grad
