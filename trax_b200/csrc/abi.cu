@@ -40,12 +40,14 @@ size_t sort_workspace_bytes(const LshAttnDims &);
 int sort_run(const LshAttnDims &, const int32_t *, int64_t, int32_t *, int32_t *, void *, size_t, cudaStream_t);
 int attend_fwd_run(const LshAttnDims &, const void *, const int32_t *, const uint8_t *, void *, int64_t, int64_t,
                    int64_t, int64_t, float *, const FwdAux *, const AttnKeep *, cudaStream_t);
-int combine_fwd_run(const LshAttnDims &, const void *, const float *, void *, float *, cudaStream_t);
+int combine_fwd_run(const LshAttnDims &, const void *, const float *, void *, float *, cudaStream_t, const BwdPrepOut * = nullptr);
+bool attend_bwd_uses_tc(const LshAttnDims &, const AttnKeep *);
+int attend_bwd_prep_target(const LshAttnDims &, void *, size_t, const void *, BwdPrepOut *);
 int chunk_possort_run(const LshAttnDims &, const int32_t *, int32_t *, int32_t *, cudaStream_t);
 size_t attend_bwd_workspace_bytes(const LshAttnDims &);
 int attend_bwd_run(const LshAttnDims &, const void *, const int32_t *, const uint8_t *, const void *, const float *,
                    const void *, const float *, const int32_t *, const int32_t *, const AttnKeep *, void *, void *, size_t,
-                   cudaStream_t);
+                   cudaStream_t, bool prep_done = false);
 int pack_weights_run(const LshAttnDims &, const float *, const float *, const float *, const float *, void *, void *, cudaStream_t);
 int pack_all_run(const LshAttnDims &, const float *, const float *, const float *, const float *, void *, void *, void *, void *, cudaStream_t);
 int f32_to_bf16_run(const float *, void *, int64_t, cudaStream_t);
@@ -247,7 +249,8 @@ static int pack_layer_weights(const LshAttnDims &d, const LayerWs &w, const floa
 // Forward up to o_comb (EA:1923-1992 for all units).  Returns xb (bf16 view of x).
 static int forward_core(const LshAttnDims &d, const LayerWs &w, const void *x, const float *w_q, const float *w_v,
                         const float *w_o, const float *w_k, const float *rotations, const uint8_t *mask, const AttnKeep *keep, int32_t *buckets,
-                        int64_t bstride, bool need_lse_tot, const void **xb_out, cudaStream_t s, bool weights_packed = false) {
+                        int64_t bstride, bool need_lse_tot, const void **xb_out, cudaStream_t s, bool weights_packed = false,
+                        const BwdPrepOut *prep = nullptr, cudaEvent_t prep_wait = nullptr) {
   Derived dr = derive(d);
   const int64_t BL = static_cast<int64_t>(d.B) * d.L;
   int rc;
@@ -279,7 +282,10 @@ static int forward_core(const LshAttnDims &d, const LayerWs &w, const void *x, c
     if ((rc = attend_fwd_run(d, w.qv, w.sticker, mask, w.o_rounds, static_cast<int64_t>(d.H) * dr.N * 64,
                              static_cast<int64_t>(dr.N) * 64, static_cast<int64_t>(d.L) * 64, 64, w.logits, &w.aux, keep, s)))
       return rc;
-    if ((rc = combine_fwd_run(d, w.o_rounds, w.logits, w.o_comb, need_lse_tot ? w.lse_tot : nullptr, s))) return rc;
+    // backward call: the combine also leaves the gradient kernel's per-token inputs (needs do_comb: wait for the helper
+    // stream's GEMM here, long after it has finished, instead of before the first kernel of the recompute)
+    if (prep && prep_wait) LSH_CUDA_OK(cudaStreamWaitEvent(s, prep_wait, 0));
+    if ((rc = combine_fwd_run(d, w.o_rounds, w.logits, w.o_comb, need_lse_tot ? w.lse_tot : nullptr, s, prep))) return rc;
   } else {
     // single round: rows land directly in the (B, L, H, dv) layout, logits == lse_tot
     if ((rc = attend_fwd_run(d, w.qv, w.sticker, mask, w.o_comb, static_cast<int64_t>(d.L) * d.H * 64, 64, 0,
@@ -475,8 +481,11 @@ int lsh_layer_bwd(const LshAttnDims *dims, const void *x, const float *w_q, cons
   AttnKeep keep;
   if ((rc = attn_keep_prepare(d, attn_keep, w.keep_ws, &keep, s))) return rc;
   const AttnKeep *kp = attn_keep ? &keep : nullptr;
+  BwdPrepOut prep;
+  const bool fuse_prep = d.nh > 1 && attend_bwd_uses_tc(d, kp);
+  if (fuse_prep && (rc = attend_bwd_prep_target(d, w.bwd_ws, w.bwd_bytes, w.do_comb, &prep))) return rc;
   if ((rc = forward_core(d, w, x, w_q, w_v, w_o, w_k, nullptr, mask, kp, const_cast<int32_t *>(buckets), buckets_stride, true,
-                         &xb, s, /*weights_packed=*/true)))
+                         &xb, s, /*weights_packed=*/true, fuse_prep ? &prep : nullptr, side->join)))
     return rc;
   if (out) {
     if ((rc = gemm_aw(BL, d.D, KO, w.o_comb, KO, w.wo_t, w.wo, out, d.D, f32, w.cublas, s))) return rc;
@@ -486,7 +495,7 @@ int lsh_layer_bwd(const LshAttnDims *dims, const void *x, const float *w_q, cons
   if ((rc = gemm_wgrad(KO, d.D, BL, w.o_comb, doutb, dw_o, w.cublas, s))) return rc;
   if (ev_dwo_ready) LSH_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(ev_dwo_ready), s));
   // B2-B6
-  if ((rc = attend_bwd_run(d, w.qv, w.sticker, mask, w.o_comb, w.lse_tot, w.do_comb, w.aux.qscale, attend_fwd_uses_tc(d) ? w.aux.sticker2 : nullptr, attend_fwd_uses_tc(d) ? w.aux.bounds : nullptr, kp, w.dqv, w.bwd_ws, w.bwd_bytes, s)))
+  if ((rc = attend_bwd_run(d, w.qv, w.sticker, mask, w.o_comb, w.lse_tot, w.do_comb, w.aux.qscale, attend_fwd_uses_tc(d) ? w.aux.sticker2 : nullptr, attend_fwd_uses_tc(d) ? w.aux.bounds : nullptr, kp, w.dqv, w.bwd_ws, w.bwd_bytes, s, fuse_prep)))
     return rc;
   // B7: dW_q|dW_v = x^T·dqv ; dx = dqv·wqv^T
   const WgradUnpack up = {dw_q, dw_v, dw_k, d.H, d.D, d.dq, d.dv};

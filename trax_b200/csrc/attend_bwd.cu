@@ -317,10 +317,45 @@ bool attend_tc_uses_bounds();
 // a part that is skipped leaves the workspace of an earlier full call in place, so one part can be timed alone.
 int g_bwd_parts = 7;
 
+static bool force_mma_bwd() {
+  static const bool f = [] { const char *e = getenv("LSH_ATTN_BWD"); return e && strcmp(e, "mma") == 0; }();
+  return f;
+}
+
+// Whether attend_bwd_run takes the tcgen05 path for this call (long-sequence shape, no dropout / separate keys).
+bool attend_bwd_uses_tc(const LshAttnDims &d, const AttnKeep *keep) {
+  const bool dropout = keep && keep->bits_t;   // the tcgen05 backward works on position-sorted tiles; the keep matrix is in slot order
+  return d.C == 128 && d.nb == 1 && d.na == 0 && d.causal && !d.masked && d.L % 128 == 0 && !force_mma_bwd() && !dropout && !d.separate_k;
+}
+
+// The per-token scalar buffers inside the stage workspace (same carve-up as attend_bwd_run below).
+static void bwd_token_buffers(const LshAttnDims &d, void *ws, float **dvec, float **lse2, float **qcmp, float **qscale_ws) {
+  Derived dr = derive(d);
+  const size_t rows = static_cast<size_t>(dr.BH) * dr.N;
+  char *w = static_cast<char *>(ws);
+  w += rows * 64 * 2 * (dr.nwin + 1);
+  w += rows * 64 * 2;
+  w = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(w) + 255) / 256 * 256);
+  const size_t tok = (static_cast<size_t>(dr.BH) * d.L * 4 + 255) / 256 * 256;
+  *dvec = reinterpret_cast<float *>(w);
+  *lse2 = reinterpret_cast<float *>(w + tok);
+  *qcmp = reinterpret_cast<float *>(w + 2 * tok);
+  *qscale_ws = reinterpret_cast<float *>(w + 3 * tok);
+}
+
+// For the layer's backward call: where the combine of the recompute should leave dvec / lse2 / qcmp (see BwdPrepOut).
+int attend_bwd_prep_target(const LshAttnDims &d, void *ws, size_t ws_bytes, const void *do_comb, BwdPrepOut *out) {
+  if (ws_bytes < attend_bwd_workspace_bytes(d)) return set_error("lsh_attend_bwd: workspace too small");
+  float *qs;
+  out->do_comb = do_comb;
+  bwd_token_buffers(d, ws, &out->dvec, &out->lse2, &out->qcmp, &qs);
+  return 0;
+}
+
 int attend_bwd_run(const LshAttnDims &d, const void *qv, const int32_t *sticker, const uint8_t *mask,
                    const void *o_comb, const float *lse_tot, const void *do_comb, const float *qscale_in,
                    const int32_t *sticker2_in, const int32_t *bounds_in, const AttnKeep *keep, void *dqv, void *ws, size_t ws_bytes,
-                   cudaStream_t stream) {
+                   cudaStream_t stream, bool prep_done) {
   Derived dr = derive(d);
   if (ws_bytes < attend_bwd_workspace_bytes(d))
     return set_error("lsh_attend_bwd: workspace too small (%zu < %zu)", ws_bytes, attend_bwd_workspace_bytes(d));
@@ -331,23 +366,19 @@ int attend_bwd_run(const LshAttnDims &d, const void *qv, const int32_t *sticker,
   w += rows * 64 * 2 * (dr.nwin + 1);
   __nv_bfloat16 *dv_part = reinterpret_cast<__nv_bfloat16 *>(w);
   w += rows * 64 * 2;
-  w = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(w) + 255) / 256 * 256);
-  float *dvec = reinterpret_cast<float *>(w);
-  const size_t tok = (static_cast<size_t>(dr.BH) * d.L * 4 + 255) / 256 * 256;
-  float *lse2 = reinterpret_cast<float *>(w + tok), *qcmp = reinterpret_cast<float *>(w + 2 * tok);
-  float *qscale_ws = reinterpret_cast<float *>(w + 3 * tok);
+  float *dvec, *lse2, *qcmp, *qscale_ws;
+  bwd_token_buffers(d, ws, &dvec, &lse2, &qcmp, &qscale_ws);
   int rc;
   // tcgen05 path for the long-sequence shape; LSH_ATTN_BWD=mma forces the mma.sync path
-  static const bool force_mma = [] { const char *e = getenv("LSH_ATTN_BWD"); return e && strcmp(e, "mma") == 0; }();
-  const bool dropout = keep && keep->bits_t;   // the tcgen05 backward works on position-sorted tiles; the keep matrix is in slot order
-  if (d.C == 128 && d.nb == 1 && d.na == 0 && d.causal && !d.masked && d.L % 128 == 0 && !force_mma && !dropout && !d.separate_k) {
+  const bool dropout = keep && keep->bits_t;
+  if (attend_bwd_uses_tc(d, keep)) {
     const float *qscale = qscale_in;
     const bool prep = g_bwd_parts & 1;
     if (!qscale) {
       if (prep && (rc = qscale_run(d, qv, qscale_ws, nullptr, nullptr, stream))) return rc;
       qscale = qscale_ws;
     }
-    if (prep && (rc = bwd_prep_tc_run(d, do_comb, o_comb, lse_tot, dvec, lse2, qcmp, stream))) return rc;
+    if (prep && !prep_done && (rc = bwd_prep_tc_run(d, do_comb, o_comb, lse_tot, dvec, lse2, qcmp, stream))) return rc;
     // position-sorted chunks: from the forward pass of the same layer call if it made them, else into the (unused on this
     // path) second partial-dq area of the workspace
     const int32_t *sticker2 = sticker2_in, *bounds = bounds_in;

@@ -27,11 +27,11 @@ template <int NH>
 __global__ void __launch_bounds__(ROW_THREADS) combine_fwd_kernel(
     const __nv_bfloat16 *__restrict__ o_rounds, const float *__restrict__ logits,
     __nv_bfloat16 *__restrict__ o_comb, float *__restrict__ lse_tot, int L, int H, int nh_rt,
-    int64_t total_rows) {
+    int64_t total_rows, BwdPrepOut prep) {
   const int nh = NH > 0 ? NH : nh_rt;
   const int64_t row = (static_cast<int64_t>(blockIdx.x) * ROW_THREADS + threadIdx.x) >> 3;   // (u, t)
   const int ch = threadIdx.x & 7;
-  if (row >= total_rows) return;
+  if (row >= total_rows) return;                    // (whole warps: total_rows * 8 is a multiple of 32 whenever prep is set)
   const int64_t u = static_cast<uint32_t>(row) / static_cast<uint32_t>(L);   // rows < 2^31 (checked on the host): 32-bit divide
   const int t = static_cast<int>(row - u * L);
   const int64_t b = static_cast<uint32_t>(u) / static_cast<uint32_t>(H), h = u - b * H;
@@ -77,23 +77,49 @@ __global__ void __launch_bounds__(ROW_THREADS) combine_fwd_kernel(
       for (int i = 0; i < 8; ++i) acc[i] = fmaf(w, f[i], acc[i]);
     }
   }
-  *(reinterpret_cast<uint4 *>(o_comb + ((b * L + t) * H + h) * 64) + ch) = f32_to_bf16x8(acc);
+  const uint4 packed = f32_to_bf16x8(acc);
+  *(reinterpret_cast<uint4 *>(o_comb + ((b * L + t) * H + h) * 64) + ch) = packed;
   if (lse_tot != nullptr && ch == 0) lse_tot[u * L + t] = lse;
+  if (prep.do_comb != nullptr) {
+    // backward call: D = do . o of the row just combined (the bf16 values that were stored, same operation order as
+    // bwd_prep_tc_kernel) and the other two per-token inputs of the gradient kernel — no second pass over o_comb
+    float a[8], c[8];
+    bf16x8_to_f32(__ldg(reinterpret_cast<const uint4 *>(static_cast<const __nv_bfloat16 *>(prep.do_comb) + ((b * L + t) * H + h) * 64) + ch), a);
+    bf16x8_to_f32(packed, c);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s = fmaf(a[i], c[i], s);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (ch == 0) {
+      const int64_t o = u * L + t;
+      const bool self_only = lse < -5e4f;
+      prep.dvec[o] = -s;
+      prep.lse2[o] = -(lse * kLog2e + (self_only ? 1e5f * kLog2e : 0.f));
+      prep.qcmp[o] = static_cast<float>(t + 1) + (self_only ? 0.5f : 0.f);
+    }
+  }
 }
 
 int combine_fwd_run(const LshAttnDims &d, const void *o_rounds, const float *logits, void *o_comb,
-                    float *lse_tot, cudaStream_t stream) {
+                    float *lse_tot, cudaStream_t stream, const BwdPrepOut *prep_in) {
   Derived dr = derive(d);
   const int64_t rows = static_cast<int64_t>(dr.BH) * d.L;
+  BwdPrepOut prep = {nullptr, nullptr, nullptr, nullptr};
+  if (prep_in) {
+    if ((rows * 8) % 32 != 0) return set_error("combine_fwd: fused backward preparation needs whole warps");
+    prep = *prep_in;
+  }
   const unsigned blocks = static_cast<unsigned>((rows * 8 + ROW_THREADS - 1) / ROW_THREADS);
   const __nv_bfloat16 *o = static_cast<const __nv_bfloat16 *>(o_rounds);
   __nv_bfloat16 *oc = static_cast<__nv_bfloat16 *>(o_comb);
   switch (d.nh) {
-    case 1: combine_fwd_kernel<1><<<blocks, ROW_THREADS, 0, stream>>>(o, logits, oc, lse_tot, d.L, d.H, d.nh, rows); break;
-    case 2: combine_fwd_kernel<2><<<blocks, ROW_THREADS, 0, stream>>>(o, logits, oc, lse_tot, d.L, d.H, d.nh, rows); break;
-    case 4: combine_fwd_kernel<4><<<blocks, ROW_THREADS, 0, stream>>>(o, logits, oc, lse_tot, d.L, d.H, d.nh, rows); break;
-    case 8: combine_fwd_kernel<8><<<blocks, ROW_THREADS, 0, stream>>>(o, logits, oc, lse_tot, d.L, d.H, d.nh, rows); break;
-    default: combine_fwd_kernel<0><<<blocks, ROW_THREADS, 0, stream>>>(o, logits, oc, lse_tot, d.L, d.H, d.nh, rows); break;
+    case 1: combine_fwd_kernel<1><<<blocks, ROW_THREADS, 0, stream>>>(o, logits, oc, lse_tot, d.L, d.H, d.nh, rows, prep); break;
+    case 2: combine_fwd_kernel<2><<<blocks, ROW_THREADS, 0, stream>>>(o, logits, oc, lse_tot, d.L, d.H, d.nh, rows, prep); break;
+    case 4: combine_fwd_kernel<4><<<blocks, ROW_THREADS, 0, stream>>>(o, logits, oc, lse_tot, d.L, d.H, d.nh, rows, prep); break;
+    case 8: combine_fwd_kernel<8><<<blocks, ROW_THREADS, 0, stream>>>(o, logits, oc, lse_tot, d.L, d.H, d.nh, rows, prep); break;
+    default: combine_fwd_kernel<0><<<blocks, ROW_THREADS, 0, stream>>>(o, logits, oc, lse_tot, d.L, d.H, d.nh, rows, prep); break;
   }
   LSH_CHECK_LAUNCH("combine_fwd_kernel");
   return 0;

@@ -16,6 +16,14 @@ struct Derived {
   int BH, N, n_chunks, W, QV, R, n_buckets, nwin;
 };
 
+// Token-level inputs of the tcgen05 backward kernel, written by the multi-round combine of the backward call's recompute
+// when it already has the token's output row in registers (see combine_fwd_kernel): do_comb (B, L, H, 64) bf16 in,
+// dvec / lse2 / qcmp (BH, L) f32 out (same values as bwd_prep_tc_kernel).
+struct BwdPrepOut {
+  const void *do_comb;
+  float *dvec, *lse2, *qcmp;
+};
+
 inline Derived derive(const LshAttnDims &d) {
   Derived r;
   r.BH = d.B * d.H;
