@@ -196,6 +196,20 @@ int lsh_layer_bwd(const LshAttnDims *dims, const void *x, const float *w_q, cons
                   float *dw_v, float *dw_o, float *dw_k, void *ws, size_t ws_bytes, void *ev_dwo_ready,
                   void *ev_dwqv_ready, void *stream);
 
+/* The same two calls with the residual of the enclosing reversible block fused into the output projection's epilogue
+ * (layers/reversible.py:318  output = accumulator + residual;  :400  reconstructed_x = accumulator_output - residual):
+ * out = residual + acc_sign * attention_output, `residual` (B, L, D) in act_dtype (may alias `out`), acc_sign = +1 / -1.
+ * residual == NULL gives the plain calls above. */
+int lsh_layer_fwd_res(const LshAttnDims *dims, const void *x, const float *w_q, const float *w_v,
+                      const float *w_o, const float *w_k, const float *rotations, const uint8_t *mask, const float *attn_keep,
+                      int32_t *buckets, int64_t buckets_stride, void *out, const void *residual, float acc_sign,
+                      void *ws, size_t ws_bytes, void *stream);
+int lsh_layer_bwd_res(const LshAttnDims *dims, const void *x, const float *w_q, const float *w_v,
+                      const float *w_o, const float *w_k, const uint8_t *mask, const float *attn_keep,
+                      const int32_t *buckets, int64_t buckets_stride, const void *dout, void *out, void *dx,
+                      float *dw_q, float *dw_v, float *dw_o, float *dw_k, void *ws, size_t ws_bytes,
+                      void *ev_dwo_ready, void *ev_dwqv_ready, const void *residual, float acc_sign, void *stream);
+
 /* ---- helpers ---------------------------------------------------------------------------------- */
 
 /* Counter-based N(0,1) draws for the rotations (stands in for fastmath.random.normal at EA:92;

@@ -156,3 +156,26 @@ def test_reversible_half_with_output_dropout_uses_one_mask_in_both_passes():
   assert np.abs(bad.cpu().numpy() - x1).max() > 1e-2
   with pytest.raises(ValueError):
     block.reverse_and_grad((y1, ctx), (cu(ct_y1), cu(ct_x2)), block.weights, None, block.state, None)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_residual_fused_into_the_output_projection_matches_the_separate_pass(dtype):
+  """`lsh_layer_fwd_res` / `lsh_layer_bwd_res`: out = residual + sign * attention_output from the GEMM epilogue
+  (reversible.py:318, 400) against the plain call followed by the add / subtract; the gradients must not change."""
+  import trax_b200
+  layer = trax_b200.LSHSelfAttention(n_heads=4, causal=True, chunk_len=128, n_hashes=2, n_buckets=None)
+  layer.init(trax_b200.ShapeDtype((2, 1024, 256)))
+  g = torch.Generator('cuda').manual_seed(21)
+  x = torch.randn(2, 1024, 256, device='cuda', generator=g).to(dtype)
+  acc = torch.randn(2, 1024, 256, device='cuda', generator=g).to(dtype)
+  ct = torch.randn(2, 1024, 256, device='cuda', generator=g).to(dtype)
+  plain, state, _, _ = layer.forward_and_or_backward(x, layer.weights, layer.state, None)
+  fused, _, _, _ = layer._forward_and_or_backward(x, layer.weights, state, None, update_state=False, _residual=(acc, 1.0))
+  want = acc.float() + plain.float()
+  tol = 1e-5 if dtype == torch.float32 else 2 ** -7 * float(want.abs().max())
+  assert float((fused.float() - want).abs().max()) <= tol
+  out0, _, dx0, dw0 = layer.forward_and_or_backward(x, layer.weights, state, None, output_grad=ct, update_state=False)
+  out1, _, dx1, dw1 = layer._forward_and_or_backward(x, layer.weights, state, None, output_grad=ct, update_state=False,
+                                                     _residual=(acc, -1.0))
+  assert float((out1.float() - (acc.float() - out0.float())).abs().max()) <= tol
+  assert torch.equal(dx0, dx1) and all(torch.equal(a, b) for a, b in zip(dw0, dw1))

@@ -48,6 +48,8 @@ SIGNATURES = {
     'lsh_layer_workspace_bytes': (_SZ, [_D, _I]),
     'lsh_layer_fwd': (_I, [_D, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _SZ, _P]),
     'lsh_layer_bwd': (_I, [_D, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P, _P, _P]),
+    'lsh_layer_fwd_res': (_I, [_D, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, ctypes.c_float, _P, _SZ, _P]),
+    'lsh_layer_bwd_res': (_I, [_D, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P, _P, _P, ctypes.c_float, _P]),
     'lsh_make_rotations': (_I, [_D, _P, _P, _P, _P]),
     'lsh_layernorm_fwd': (_I, [_I64, _I, _I, _P, _P, _P, _P, _P, ctypes.c_float, _P]),
     'lsh_layernorm_bwd': (_I, [_I64, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

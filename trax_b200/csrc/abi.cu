@@ -125,17 +125,24 @@ static int gemm_rm(bool ta, bool tb, int64_t M, int64_t N, int64_t K, const void
 // at hand K-major (`w_k`: (N, K)) and the shape fits it, cuBLAS otherwise (`w_n`: the (K, N) copy, or w_k transposed).
 int transpose_bf16_run(const void *src, void *dst, int R, int C, cudaStream_t stream);
 static int gemm_aw(int64_t M, int64_t N, int64_t K, const void *A, int64_t lda, const void *w_k, const void *w_n, void *C,
-                   int64_t ldc, bool c_f32, void *cws, cudaStream_t stream, const GemmQStats *qs = nullptr, bool *qs_done = nullptr) {
+                   int64_t ldc, bool c_f32, void *cws, cudaStream_t stream, const GemmQStats *qs = nullptr, bool *qs_done = nullptr,
+                   const GemmResidual *res = nullptr) {
   if (qs_done) *qs_done = false;
+  if (res && !res->resid) res = nullptr;
   if (w_k) {
-    const int rc = gemm_tc_run(M, N, K, A, lda, w_k, K, C, ldc, c_f32, stream, qs);
+    const int rc = gemm_tc_run(M, N, K, A, lda, w_k, K, C, ldc, c_f32, stream, qs, res);
     if (rc >= 0) {
       if (qs_done) *qs_done = rc == 0 && qs != nullptr;
       return rc;
     }
   }
-  if (w_n) return gemm_rm(false, false, M, N, K, A, lda, w_n, N, C, ldc, c_f32, cws, stream);
-  return gemm_rm(false, true, M, N, K, A, lda, w_k, K, C, ldc, c_f32, cws, stream);
+  int rc;
+  if (w_n) rc = gemm_rm(false, false, M, N, K, A, lda, w_n, N, C, ldc, c_f32, cws, stream);
+  else rc = gemm_rm(false, true, M, N, K, A, lda, w_k, K, C, ldc, c_f32, cws, stream);
+  if (rc || !res) return rc;
+  // library-GEMM fallback: the residual as a separate pass, C = resid + sign * C
+  if (ldc != N || (M * N) % 8 != 0) return set_error("residual epilogue: unsupported output pitch / size on the fallback path");
+  return residual_sub_run(M * N, c_f32 ? LSH_DTYPE_F32 : LSH_DTYPE_BF16, res->resid, C, C, res->acc_sign, stream);
 }
 
 // Weight gradient C[M, N] (f32) = A^T · B, A (K, M), B (K, N) bf16: the split-K tensor-core kernel, else cuBLAS.
@@ -425,9 +432,9 @@ size_t lsh_layer_workspace_bytes(const LshAttnDims *dims, int with_grad) {
   return carve(*dims, nullptr, with_grad != 0).total;
 }
 
-int lsh_layer_fwd(const LshAttnDims *dims, const void *x, const float *w_q, const float *w_v, const float *w_o,
+int lsh_layer_fwd_res(const LshAttnDims *dims, const void *x, const float *w_q, const float *w_v, const float *w_o,
                   const float *w_k, const float *rotations, const uint8_t *mask, const float *attn_keep, int32_t *buckets,
-                  int64_t buckets_stride, void *out, void *ws, size_t ws_bytes, void *stream) {
+                  int64_t buckets_stride, void *out, const void *residual, float acc_sign, void *ws, size_t ws_bytes, void *stream) {
   if (int rc = check_dims(dims, false)) return rc;
   const LshAttnDims &d = *dims;
   if (!x || !w_q || !w_v || !w_o || !buckets || !out || !ws) return set_error("lsh_layer_fwd: NULL argument");
@@ -442,13 +449,21 @@ int lsh_layer_fwd(const LshAttnDims *dims, const void *x, const float *w_q, cons
                             &xb, s))
     return rc;
   const int64_t BL = static_cast<int64_t>(d.B) * d.L, KO = static_cast<int64_t>(d.H) * d.dv;
-  return gemm_aw(BL, d.D, KO, w.o_comb, KO, w.wo_t, w.wo, out, d.D, d.act_dtype == LSH_DTYPE_F32, w.cublas, s);
+  const GemmResidual res = {residual, acc_sign};
+  return gemm_aw(BL, d.D, KO, w.o_comb, KO, w.wo_t, w.wo, out, d.D, d.act_dtype == LSH_DTYPE_F32, w.cublas, s, nullptr, nullptr, &res);
 }
 
-int lsh_layer_bwd(const LshAttnDims *dims, const void *x, const float *w_q, const float *w_v, const float *w_o,
+int lsh_layer_fwd(const LshAttnDims *dims, const void *x, const float *w_q, const float *w_v, const float *w_o,
+                  const float *w_k, const float *rotations, const uint8_t *mask, const float *attn_keep, int32_t *buckets,
+                  int64_t buckets_stride, void *out, void *ws, size_t ws_bytes, void *stream) {
+  return lsh_layer_fwd_res(dims, x, w_q, w_v, w_o, w_k, rotations, mask, attn_keep, buckets, buckets_stride, out, nullptr, 1.f, ws,
+                           ws_bytes, stream);
+}
+
+int lsh_layer_bwd_res(const LshAttnDims *dims, const void *x, const float *w_q, const float *w_v, const float *w_o,
                   const float *w_k, const uint8_t *mask, const float *attn_keep, const int32_t *buckets, int64_t buckets_stride,
                   const void *dout, void *out, void *dx, float *dw_q, float *dw_v, float *dw_o, float *dw_k, void *ws, size_t ws_bytes,
-                  void *ev_dwo_ready, void *ev_dwqv_ready, void *stream) {
+                  void *ev_dwo_ready, void *ev_dwqv_ready, const void *residual, float acc_sign, void *stream) {
   if (int rc = check_dims(dims, true)) return rc;
   const LshAttnDims &d = *dims;
   if (!x || !w_q || !w_v || !w_o || !buckets || !dout || !dx || !dw_q || !dw_v || !dw_o || !ws)
@@ -488,7 +503,8 @@ int lsh_layer_bwd(const LshAttnDims *dims, const void *x, const float *w_q, cons
                          &xb, s, /*weights_packed=*/true, fuse_prep ? &prep : nullptr, side->join)))
     return rc;
   if (out) {
-    if ((rc = gemm_aw(BL, d.D, KO, w.o_comb, KO, w.wo_t, w.wo, out, d.D, f32, w.cublas, s))) return rc;
+    const GemmResidual res = {residual, acc_sign};
+    if ((rc = gemm_aw(BL, d.D, KO, w.o_comb, KO, w.wo_t, w.wo, out, d.D, f32, w.cublas, s, nullptr, nullptr, &res))) return rc;
   }
   LSH_CUDA_OK(cudaStreamWaitEvent(s, side->join, 0));
   // B1 (second half): dW_o = o^T·dout
@@ -504,6 +520,14 @@ int lsh_layer_bwd(const LshAttnDims *dims, const void *x, const float *w_q, cons
   if (!unpacked && (rc = unpack_dwqv_run(d, w.dwqv, dw_q, dw_v, dw_k, s))) return rc;
   if (ev_dwqv_ready) LSH_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(ev_dwqv_ready), s));
   return gemm_aw(BL, d.D, NQV, w.dqv, NQV, w.wqv, nullptr, dx, d.D, f32, w.cublas, s);
+}
+
+int lsh_layer_bwd(const LshAttnDims *dims, const void *x, const float *w_q, const float *w_v, const float *w_o,
+                  const float *w_k, const uint8_t *mask, const float *attn_keep, const int32_t *buckets, int64_t buckets_stride,
+                  const void *dout, void *out, void *dx, float *dw_q, float *dw_v, float *dw_o, float *dw_k, void *ws, size_t ws_bytes,
+                  void *ev_dwo_ready, void *ev_dwqv_ready, void *stream) {
+  return lsh_layer_bwd_res(dims, x, w_q, w_v, w_o, w_k, mask, attn_keep, buckets, buckets_stride, dout, out, dx, dw_q, dw_v, dw_o, dw_k,
+                           ws, ws_bytes, ev_dwo_ready, ev_dwqv_ready, nullptr, 1.f, stream);
 }
 
 int lsh_layernorm_fwd(int64_t rows, int d_model, int act_dtype, const void *x, const float *scale, const float *bias, void *z,

@@ -45,6 +45,9 @@ struct GemmTcParams {
   float2 *rowmeta;
   __nv_bfloat16 *qhat;
   int L, H;
+  // residual epilogue: C = resid + acc_sign * acc (null = plain product); same pitch and element type as C
+  const void *resid;
+  float acc_sign;
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
@@ -309,10 +312,26 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
         for (int i = 0; i < 8; ++i) {
           const int r = 4 * i + (lane >> 3);
           const int64_t grow = static_cast<int64_t>(m_blk) * GM_BM + q * 32 + r;
-          const uint4 v = lds128u(stg + r * 128 + ((static_cast<uint32_t>(piece) ^ (r & 7)) << 4));
+          uint4 v = lds128u(stg + r * 128 + ((static_cast<uint32_t>(piece) ^ (r & 7)) << 4));
           if (grow < p.M) {
-            char *dst = static_cast<char *>(p.c) + (grow + static_cast<int64_t>(g / tiles) * p.M) * p.ldc * (p.c_f32 ? 4 : 2) + col_bytes;
-            *reinterpret_cast<uint4 *>(dst + piece * 16) = v;
+            const int64_t off = (grow + static_cast<int64_t>(g / tiles) * p.M) * p.ldc * (p.c_f32 ? 4 : 2) + col_bytes + piece * 16;
+            if (p.resid != nullptr) {                                  // y = x + attn / x = y - attn of the reversible block
+              const uint4 rv = *reinterpret_cast<const uint4 *>(static_cast<const char *>(p.resid) + off);
+              const float sg = p.acc_sign;
+              if (p.c_f32) {
+                v.x = __float_as_uint(fmaf(sg, __uint_as_float(v.x), __uint_as_float(rv.x)));
+                v.y = __float_as_uint(fmaf(sg, __uint_as_float(v.y), __uint_as_float(rv.y)));
+                v.z = __float_as_uint(fmaf(sg, __uint_as_float(v.z), __uint_as_float(rv.z)));
+                v.w = __float_as_uint(fmaf(sg, __uint_as_float(v.w), __uint_as_float(rv.w)));
+              } else {
+                auto mix = [&](uint32_t a, uint32_t b) {
+                  const float2 fa = unpack_bf16(a), fb = unpack_bf16(b);
+                  return pack_bf16(fmaf(sg, fa.x, fb.x), fmaf(sg, fa.y, fb.y));
+                };
+                v.x = mix(v.x, rv.x); v.y = mix(v.y, rv.y); v.z = mix(v.z, rv.z); v.w = mix(v.w, rv.w);
+              }
+            }
+            *reinterpret_cast<uint4 *>(static_cast<char *>(p.c) + off) = v;
           }
         }
         __syncwarp();
@@ -397,7 +416,7 @@ static int gemm_tc_launch(const GemmTcParams &p, cudaStream_t stream) {
 // A[M, K] (row pitch lda elements) · B[N, K]^T (row pitch ldb) -> C[M, N] (row pitch ldc), bf16 in, bf16 or f32 out.
 // Returns 0 on launch, > 0 on error, -1 when the shape is outside what the kernel covers (the caller falls back to cuBLAS).
 int gemm_tc_run(int64_t M, int64_t N, int64_t K, const void *A, int64_t lda, const void *B, int64_t ldb, void *C, int64_t ldc,
-                bool c_f32, cudaStream_t stream, const GemmQStats *qs) {
+                bool c_f32, cudaStream_t stream, const GemmQStats *qs, const GemmResidual *res) {
   static const int mode = [] {        // LSH_GEMM=cublas: library GEMMs everywhere; LSH_GEMM=cluster1: no weight-tile multicast
     const char *e = getenv("LSH_GEMM");
     if (!e) return 2;
@@ -414,6 +433,8 @@ int gemm_tc_run(int64_t M, int64_t N, int64_t K, const void *A, int64_t lda, con
   p.m_blocks = static_cast<int>((M + GM_BM - 1) / GM_BM); p.n_blocks = static_cast<int>(N / bn);
   p.splits = 1;
   p.qscale = nullptr; p.rowmeta = nullptr; p.qhat = nullptr; p.L = 1; p.H = 1;
+  p.resid = res ? res->resid : nullptr; p.acc_sign = res ? res->acc_sign : 1.f;
+  if (res && res->resid && (reinterpret_cast<uintptr_t>(res->resid) & 15)) return -1;
   if (qs) {           // fused key normalisation: rows are (b, t), columns (h, q | v) — needs bf16 output of 128-column heads
     if (c_f32 || N != static_cast<int64_t>(qs->H) * 128) return set_error("gemm_tc: q statistics need the (B L, H 128) bf16 projection");
     p.qscale = qs->qscale; p.rowmeta = qs->rowmeta; p.qhat = static_cast<__nv_bfloat16 *>(qs->qhat); p.L = qs->L; p.H = qs->H;
@@ -478,7 +499,7 @@ int gemm_tc_wgrad_run(int64_t M, int64_t N, int64_t K, const void *A, int64_t ld
   GemmTcParams p;
   p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K); p.c_f32 = 1; p.ldc = N;
   p.m_blocks = static_cast<int>(M / GM_BM); p.n_blocks = static_cast<int>(N / bn);
-  p.qscale = nullptr; p.rowmeta = nullptr; p.qhat = nullptr; p.L = 1; p.H = 1;
+  p.qscale = nullptr; p.rowmeta = nullptr; p.qhat = nullptr; p.L = 1; p.H = 1; p.resid = nullptr; p.acc_sign = 1.f;
   const int cl = (mode == 2 && p.m_blocks % 2 == 0) ? 2 : 1;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

@@ -21,8 +21,14 @@ struct GemmQStats {
   void *qhat;
   int L, H;
 };
+// Optional residual epilogue (layers/reversible.py:318, 400): C = resid + acc_sign * (A B^T), `resid` laid out and typed like C
+// (it may BE C: every element is read and written by the same thread).
+struct GemmResidual {
+  const void *resid;
+  float acc_sign;
+};
 int gemm_tc_run(int64_t M, int64_t N, int64_t K, const void *A, int64_t lda, const void *B, int64_t ldb, void *C, int64_t ldc,
-                bool c_f32, cudaStream_t stream, const GemmQStats *qs = nullptr);
+                bool c_f32, cudaStream_t stream, const GemmQStats *qs = nullptr, const GemmResidual *res = nullptr);
 // Optional destination of the q|v(|k) weight gradient in the reference's per-head layouts (see sum_partials_unpack_kernel).
 struct WgradUnpack {
   float *dw_q, *dw_v, *dw_k;

@@ -454,7 +454,7 @@ class LSHSelfAttention:
     return self._forward_and_or_backward(inputs, weights, state, rng, output_grad, compute_output, update_state)
 
   def _forward_and_or_backward(self, inputs, weights, state, rng, output_grad=None,
-                               compute_output=True, update_state=True, _stash=None):
+                               compute_output=True, update_state=True, _stash=None, _residual=None):
     """Performs batched forward and/or backward passes (EA:2261-2289).
 
     Returns (output, new_state, inputs_grad, weights_grad):
@@ -478,7 +478,7 @@ class LSHSelfAttention:
       # kernels, streams and the scratch buffer belong to the tensors' device, whatever the caller's current device is
       with torch.cuda.device(x.device):
         return self._forward_and_or_backward(inputs if not have_single_input else inputs[0], weights, state, rng, output_grad,
-                                             compute_output, update_state, _stash)
+                                             compute_output, update_state, _stash, _residual)
     lib = _lib.load()
     host_io = not x.is_cuda
     dev = torch.device('cuda', torch.cuda.current_device()) if host_io else x.device
@@ -555,12 +555,19 @@ class LSHSelfAttention:
     out_d = None
     if compute_output:
       out_d = torch.empty_like(x_d)                                 # dtype of inputs[0], EA:2529-2530
+    # residual of the enclosing reversible block, fused into the output projection's epilogue (reversible.py:318, 400):
+    # out = residual + sign * attention_output
+    res_d, res_sign = None, 1.0
+    if _residual is not None and compute_output:
+      res_d, res_sign = _residual
+      if not res_d.is_cuda or res_d.shape != x_d.shape or res_d.dtype != x_d.dtype or not res_d.is_contiguous():
+        raise ValueError('fused residual must be a contiguous device tensor shaped and typed like the input')
     inputs_grad = weights_grad = None
     if not compute_grad:
-      _lib.check(lib.lsh_layer_fwd(
+      _lib.check(lib.lsh_layer_fwd_res(
           ctypes.byref(dims), ops._ptr(x_d), ops._ptr(w_q), ops._ptr(w_v), ops._ptr(w_o), ops._ptr(w_k), ops._ptr(rotations),
-          ops._ptr(mask_d), ops._ptr(attn_keep), ops._ptr(buckets_d), buckets_d.stride(0), ops._ptr(out_d), ops._ptr(ws),
-          ws.numel(), stream), 'lsh_layer_fwd')
+          ops._ptr(mask_d), ops._ptr(attn_keep), ops._ptr(buckets_d), buckets_d.stride(0), ops._ptr(out_d), ops._ptr(res_d),
+          ctypes.c_float(res_sign), ops._ptr(ws), ws.numel(), stream), 'lsh_layer_fwd')
     else:
       if update_state:
         # EA allows update_state together with output_grad; the hash must then run first.
@@ -584,12 +591,12 @@ class LSHSelfAttention:
         from trax_b200 import dp
         overlap = dp.GradOverlap.get(dev)         # None without an initialised NCCL group of more than one rank
       ev_o, ev_qv = (overlap.events() if overlap is not None else (None, None))
-      _lib.check(lib.lsh_layer_bwd(
+      _lib.check(lib.lsh_layer_bwd_res(
           ctypes.byref(dims), ops._ptr(x_d), ops._ptr(w_q), ops._ptr(w_v), ops._ptr(w_o), ops._ptr(w_k), ops._ptr(mask_d),
           ops._ptr(attn_keep), ops._ptr(buckets_d), buckets_d.stride(0), ops._ptr(g_d), ops._ptr(out_d), ops._ptr(dx), ops._ptr(dw_q),
           ops._ptr(dw_v), ops._ptr(dw_o), ops._ptr(dw_k), ops._ptr(ws), ws.numel(),
           ev_o.cuda_event if ev_o is not None and out_mult is None else None,
-          ev_qv.cuda_event if ev_qv is not None else None, stream), 'lsh_layer_bwd')
+          ev_qv.cuda_event if ev_qv is not None else None, ops._ptr(res_d), ctypes.c_float(res_sign), stream), 'lsh_layer_bwd')
       if out_mult is not None:
         dw_o.mul_(out_mult)
       if overlap is not None:

@@ -126,9 +126,21 @@ class ReversibleHalfResidual:
     z, _ = layernorm_fwd(context, scale, bias, self._epsilon)
     attn = self._attention_layer
     with torch.no_grad():
+      if self._fused(accumulator, z):
+        # output = accumulator + residual (reversible.py:318) leaves the output projection's epilogue: no separate pass
+        out, new_state, _, _ = attn._forward_and_or_backward(z, attn.weights, attn.state, rngs[1], compute_output=True,
+                                                             update_state=True, _residual=(accumulator.contiguous(), +1.0))
+        attn.state = new_state
+        return out, context
       residual, new_state = attn.pure_fn(z, attn.weights, attn.state, rngs[1])     # reversible.py:308
     attn.state = new_state                                                 # buckets of this step, read back by reverse_and_grad
     return _residual(accumulator, residual, +1.0), context
+
+  def _fused(self, accumulator, z):
+    """The residual add / subtract can ride in the attention layer's output-projection epilogue (device tensors only)."""
+    from trax_b200.lsh_attention import LSHSelfAttention
+    return (isinstance(self._attention_layer, LSHSelfAttention) and accumulator.is_cuda and z.is_cuda
+            and accumulator.shape == z.shape and accumulator.dtype == z.dtype)
 
   def reverse(self, output, weights=(), state=(), new_state=(), rng=None):
     raise NotImplementedError('Only reverse_and_grad is actually used.')     # reversible.py:323-324
@@ -142,8 +154,15 @@ class ReversibleHalfResidual:
     attn_state = (new_state if new_state else self.state)[1]
     rngs = _split_rngs(rng, 2)                                             # reversible.py:328: same split as forward
     z, stats = layernorm_fwd(context, scale, bias, self._epsilon)
-    residual, _, dz, attn_weights_ct = self._attention_layer.forward_and_or_backward(
-        z, attn_weights, attn_state, rngs[1], output_grad=accumulator_output_ct, compute_output=True, update_state=False)
-    context_ct_new, d_scale, d_bias = layernorm_bwd(context, dz, context_ct, stats, scale)
-    reconstructed_x = _residual(accumulator_output, residual, -1.0)
+    if self._fused(accumulator_output, z):
+      # reconstructed_x = accumulator_output - residual (reversible.py:400), again in the epilogue of the same GEMM
+      reconstructed_x, _, dz, attn_weights_ct = self._attention_layer._forward_and_or_backward(
+          z, attn_weights, attn_state, rngs[1], output_grad=accumulator_output_ct, compute_output=True, update_state=False,
+          _residual=(accumulator_output.contiguous(), -1.0))
+      context_ct_new, d_scale, d_bias = layernorm_bwd(context, dz, context_ct, stats, scale)
+    else:
+      residual, _, dz, attn_weights_ct = self._attention_layer.forward_and_or_backward(
+          z, attn_weights, attn_state, rngs[1], output_grad=accumulator_output_ct, compute_output=True, update_state=False)
+      context_ct_new, d_scale, d_bias = layernorm_bwd(context, dz, context_ct, stats, scale)
+      reconstructed_x = _residual(accumulator_output, residual, -1.0)
     return (reconstructed_x, context), ((accumulator_output_ct, context_ct_new), ((d_scale, d_bias), attn_weights_ct))
