@@ -324,8 +324,8 @@ static bool force_mma_bwd() {
 
 // Whether attend_bwd_run takes the tcgen05 path for this call (long-sequence shape, no dropout / separate keys).
 bool attend_bwd_uses_tc(const LshAttnDims &d, const AttnKeep *keep) {
-  const bool dropout = keep && keep->bits_t;   // the tcgen05 backward works on position-sorted tiles; the keep matrix is in slot order
-  return d.C == 128 && d.nb == 1 && d.na == 0 && d.causal && !d.masked && d.L % 128 == 0 && !force_mma_bwd() && !dropout && !d.separate_k;
+  (void)keep;   // dropout runs on this path too: slot-ordered tiles, keep bits by window column (AttendBwdTcParams::slot_order)
+  return d.C == 128 && d.nb == 1 && d.na == 0 && d.causal && !d.masked && d.L % 128 == 0 && !force_mma_bwd() && !d.separate_k;
 }
 
 // The per-token scalar buffers inside the stage workspace (same carve-up as attend_bwd_run below).
@@ -382,7 +382,9 @@ int attend_bwd_run(const LshAttnDims &d, const void *qv, const int32_t *sticker,
     // position-sorted chunks: from the forward pass of the same layer call if it made them, else into the (unused on this
     // path) second partial-dq area of the workspace
     const int32_t *sticker2 = sticker2_in, *bounds = bounds_in;
-    if (!sticker2 || (!bounds && attend_tc_uses_bounds())) {
+    if (dropout) {                       // the keep matrix is indexed by slot: tiles stay in the reference's order
+      sticker2 = sticker; bounds = nullptr;
+    } else if (!sticker2 || (!bounds && attend_tc_uses_bounds())) {
       int32_t *s2 = reinterpret_cast<int32_t *>(dq_part + rows * 64), *bd = attend_tc_uses_bounds() ? s2 + rows : nullptr;
       if (prep && (rc = chunk_possort_run(d, sticker, s2, bd, stream))) return rc;
       sticker2 = s2; bounds = bd;
@@ -390,6 +392,7 @@ int attend_bwd_run(const LshAttnDims &d, const void *qv, const int32_t *sticker,
     AttendBwdTcParams t;
     t.qv = static_cast<const __nv_bfloat16 *>(qv); t.sticker = sticker; t.sticker2 = sticker2; t.bounds = bounds;
     t.do_comb = static_cast<const __nv_bfloat16 *>(do_comb); t.qscale = qscale; t.lse2 = lse2; t.dvec = dvec; t.qcmp = qcmp;
+    t.keep_bits_t = dropout ? keep->bits_t : nullptr; t.keep_scale = dropout ? keep->scale : nullptr; t.slot_order = dropout ? 1 : 0;
     t.trace = g_fwd_trace; t.dq_out = dq_part; t.dv_out = dv_part; t.L = d.L; t.H = d.H; t.N = dr.N; t.n_chunks = dr.n_chunks;
     if ((g_bwd_parts & 2) && (rc = attend_bwd_tc_run(t, dr.BH, stream))) return rc;
     return (g_bwd_parts & 4) ? sum_rounds_run(d, dq_part, dv_part, dqv, 1, stream) : 0;

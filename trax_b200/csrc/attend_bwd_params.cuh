@@ -17,6 +17,12 @@ struct AttendBwdTcParams {
   __nv_bfloat16 *dq_out;          // (BH, N, 64) ticker order: dq_query + dq_key of every token copy
   __nv_bfloat16 *dv_out;          // (BH, N, 64)
   int L, H, N, n_chunks;
+  // Attention dropout (EA:254-262): keep bits by window column (AttnKeep::bits_t, (2 C, C / 32)) and the 1 / (1 - rate)
+  // multiplier; null = none.  Dropout calls pass `sticker` (slot order) as sticker2: the keep matrix is indexed by slot, so
+  // tiles are NOT re-ordered by position and every block takes the per-element position compare (no block skipping).
+  const uint32_t *keep_bits_t;
+  const float *keep_scale;
+  int slot_order;
   long long *trace;               // debug: per-phase clock64 stamps of CTA 0 (null = off)
 };
 

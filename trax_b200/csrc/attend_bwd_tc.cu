@@ -130,6 +130,9 @@ struct BtWalk {
 __device__ __forceinline__ uint32_t bt_slot(int seq) { return static_cast<uint32_t>(seq % BT_NST); }
 __device__ __forceinline__ uint32_t bt_phase(int seq) { return static_cast<uint32_t>((seq / BT_NST) & 1); }
 
+// DROPOUT: slot-ordered tiles + keep bits (see AttendBwdTcParams); its own instantiation, so that the plain kernel's code —
+// register allocation, instruction-cache footprint — is exactly the one without it (measured: +2.5 % otherwise).
+template <bool DROPOUT>
 __global__ void __launch_bounds__(BT_THREADS, 1) attend_bwd_tc_kernel(const AttendBwdTcParams p, int total_chunks) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -385,7 +388,17 @@ BT_ISSUE_UNROLL
         lo_j = blo;
         hi_j = blo + ((blo < 128 && mq.kinfo[blo & 127] == ki_j) ? 1 : 0);
       }
+      if (DROPOUT) { lo_j = 0; hi_j = BT_C; }                // tiles in slot order (dropout): every block with the compare
       const int min_lo = __reduce_min_sync(0xffffffffu, lo_j), max_hi = __reduce_max_sync(0xffffffffu, hi_j);
+      // dropout: my key's row of the transposed keep matrix — bit i = query slot i keeps this key (window column = my slot in
+      // the look-back part, C + my slot in the own part); all ones and scale 1 without dropout
+      uint32_t kw0 = 0xffffffffu, kw1 = 0xffffffffu;
+      float kscale = 1.f;
+      if (DROPOUT) {
+        const uint4 kw = __ldg(reinterpret_cast<const uint4 *>(p.keep_bits_t) + ((it.seq_q == it.seq_k ? BT_C : 0) + row));
+        kw0 = h ? kw.z : kw.x; kw1 = h ? kw.w : kw.y;
+        kscale = __ldg(p.keep_scale);
+      }
       mbar_wait(&sh.st_full[h], it.n & 1);
       mbar_wait(&sh.dsm_free[it.n & 1], ((it.n >> 1) & 1) ^ 1);
       tc_fence_after();
@@ -393,6 +406,7 @@ BT_ISSUE_UNROLL
 #pragma unroll 1
       for (int cc = 0; cc < 64; cc += 32) {
         const int c0 = 64 * h + cc;
+        const uint32_t kwb = cc ? kw1 : kw0;                  // keep bits of this block's 32 queries
 #ifdef LSH_TRACE_WARP
         if (cc == 32 && warp == LSH_TRACE_WARP && lane == 0) BT_TRACE(it.n, 31);
 #endif
@@ -434,10 +448,20 @@ BT_ISSUE_UNROLL
               const uint64_t t01 = ffma2(pk2u(s[c4 + 0], s[c4 + 1]), ksc2, ls.x), t23 = ffma2(pk2u(s[c4 + 2], s[c4 + 3]), ksc2, ls.y);
               const uint64_t p01 = pk2(fast_exp2(ki_j < qc.x ? lo32(t01) : -INFINITY), fast_exp2(ki_j < qc.y ? hi32(t01) : -INFINITY));
               const uint64_t p23 = pk2(fast_exp2(ki_j < qc.z ? lo32(t23) : -INFINITY), fast_exp2(ki_j < qc.w ? hi32(t23) : -INFINITY));
-              const uint64_t d01 = fmul2(p01, fadd2(pk2u(dp[c4 + 0], dp[c4 + 1]), dv.x));
-              const uint64_t d23 = fmul2(p23, fadd2(pk2u(dp[c4 + 2], dp[c4 + 3]), dv.y));
+              // keep multipliers m of the four (query, key) pairs: dV takes P∘m, dS = P∘(m∘dP - D)
+              uint64_t d01, d23, pm01 = p01, pm23 = p23;
+              if (DROPOUT) {
+                const uint64_t m01 = pk2((kwb >> (c4 + 0)) & 1u ? kscale : 0.f, (kwb >> (c4 + 1)) & 1u ? kscale : 0.f);
+                const uint64_t m23 = pk2((kwb >> (c4 + 2)) & 1u ? kscale : 0.f, (kwb >> (c4 + 3)) & 1u ? kscale : 0.f);
+                d01 = fmul2(p01, ffma2(pk2u(dp[c4 + 0], dp[c4 + 1]), m01, dv.x));
+                d23 = fmul2(p23, ffma2(pk2u(dp[c4 + 2], dp[c4 + 3]), m23, dv.y));
+                pm01 = fmul2(p01, m01); pm23 = fmul2(p23, m23);
+              } else {
+                d01 = fmul2(p01, fadd2(pk2u(dp[c4 + 0], dp[c4 + 1]), dv.x));
+                d23 = fmul2(p23, fadd2(pk2u(dp[c4 + 2], dp[c4 + 3]), dv.y));
+              }
               const uint64_t g01 = fmul2(d01, kst2), g23 = fmul2(d23, kst2);
-              pk_p[c4 >> 1] = pack_bf16(lo32(p01), hi32(p01));  pk_p[(c4 >> 1) + 1] = pack_bf16(lo32(p23), hi32(p23));
+              pk_p[c4 >> 1] = pack_bf16(lo32(pm01), hi32(pm01));  pk_p[(c4 >> 1) + 1] = pack_bf16(lo32(pm23), hi32(pm23));
               pk_ds[c4 >> 1] = pack_bf16(lo32(d01), hi32(d01)); pk_ds[(c4 >> 1) + 1] = pack_bf16(lo32(d23), hi32(d23));
               // reuse s[] as the staging copy (dS * key scale) for dQ
               s[c4 >> 1] = pack_bf16(lo32(g01), hi32(g01));
@@ -583,7 +607,7 @@ bool attend_bwd_tc_uses_bounds() { return false; }
 
 int attend_bwd_tc_run(const AttendBwdTcParams &p, int BH, cudaStream_t stream) {
   const size_t smem = static_cast<size_t>(BT_NST) * BT_TILE_BYTES + 2 * BT_DS_BYTES + 1024;
-  LSH_OPT_IN_SMEM(attend_bwd_tc_kernel);
+  LSH_OPT_IN_SMEM(attend_bwd_tc_kernel<false>);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -593,7 +617,12 @@ int attend_bwd_tc_run(const AttendBwdTcParams &p, int BH, cudaStream_t stream) {
     const int m = atoi(e);
     if (m > 0 && m < grid) grid = m;
   }
-  attend_bwd_tc_kernel<<<grid, BT_THREADS, smem, stream>>>(p, total);
+  if (p.keep_bits_t != nullptr) {
+    LSH_OPT_IN_SMEM(attend_bwd_tc_kernel<true>);
+    attend_bwd_tc_kernel<true><<<grid, BT_THREADS, smem, stream>>>(p, total);
+  } else {
+    attend_bwd_tc_kernel<false><<<grid, BT_THREADS, smem, stream>>>(p, total);
+  }
   LSH_CHECK_LAUNCH("attend_bwd_tc_kernel");
   return 0;
 }
