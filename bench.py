@@ -243,6 +243,8 @@ def run_ours(args, wl, name):
   H_local = H // world if head_sharded else H
 
   layer_kw = dict(d_qk=64, d_v=64, causal=True, chunk_len=wl['C'], n_hashes=wl['nh'], n_buckets=wl['n_buckets'], mode='train')
+  if args.attention_dropout > 0.0:     # the reference's training configs (reformer_enwik8.gin:94, reformer_imagenet64.gin:69: 0.2)
+    layer_kw['attention_dropout'] = args.attention_dropout
   if head_sharded:
     # the full 16-head layer's weights (same rng on every rank; drawn on the host), this rank's heads taken out of them
     full = trax_b200.LSHSelfAttention(n_heads=H, **layer_kw)
@@ -265,9 +267,11 @@ def run_ours(args, wl, name):
   # underneath the call's remaining kernels (trax_b200.dp.GradOverlap)
   trax_b200.set_weight_grad_allreduce(world > 1 and not head_sharded)
 
+  # the dropout masks are a function of the rng: the backward call gets the one the forward call used
+  bwd_rng = getattr(layer, 'rng', np.array([0, 0], np.uint32)) if args.attention_dropout > 0.0 else None
   def step(xi, gi):
     out = layer.forward(xi)                                                                   # forward call
-    dx, dw = layer.backward(xi, out, gi, layer.weights, None, layer.state, None)              # backward call (+ collectives)
+    dx, dw = layer.backward(xi, out, gi, layer.weights, None, layer.state, bwd_rng)           # backward call (+ collectives)
     return out, dx, dw
 
   def sync():
@@ -342,6 +346,8 @@ def run_ours(args, wl, name):
               warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling='strong' if head_sharded else 'weak',
               vs_baseline=None, dtype='bf16' if dtype == torch.bfloat16 else 'f32 I/O, bf16 tensor-core operands',
               data='synthetic', config=_config(name, wl, world, args.head_reduce), clocks=clocks, e2e=e2e, gpu_launches=launches)
+  if args.attention_dropout > 0.0:
+    line['config']['attention_dropout'] = args.attention_dropout    # (not a BASELINE config: the reference gins' training setting)
   if head_sharded and world > 1:
     # out and dx, all-reduced once each per step (counted by the layer from the tensors it reduced)
     line['collective_bytes_per_step'] = layer.comm_bytes // max(1, layer.n_calls // 2)
@@ -504,6 +510,8 @@ def main():
   ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
   ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
   ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--attention-dropout', type=float, default=0.0,
+                  help='attention dropout rate of the layer (default 0: the BASELINE configs; the reference gins train with 0.2)')
   ap.add_argument('--head-reduce', default='all', choices=['all', 'scatter'],
                   help='config 5: all-reduce the head sums, or reduce-scatter them over the sequence (sequence-parallel consumer)')
   args = ap.parse_args()

@@ -161,6 +161,27 @@ __device__ __forceinline__ void softmax_block_generic(const uint32_t (&r)[32], c
   tmem_st16(t_dst, pk);
 }
 
+// Slot-ordered tiles, causal, no padding mask (the attention-dropout calls of the long-sequence configs): ONE compare per
+// element — key position + 1 against qcmp = q_info, or q_info + 0.5 for a row that sees no earlier key and therefore keeps
+// exactly its own "-1e5" class (EA:150-155; the caller moves that -1e5 into the reported log-sum-exp) — packed math as in
+// the position-sorted routine, and the keep bits applied to P after the row sum.
+__device__ __forceinline__ void softmax_block_causal_keep(const uint32_t (&r)[32], const float *kin, float qcmp, uint64_t a2,
+                                                          uint64_t mm2, uint32_t keep, uint32_t t_dst, uint64_t &l2) {
+  uint32_t pk[16];
+#pragma unroll
+  for (int c4 = 0; c4 < 32; c4 += 4) {
+    const float4 ki = *reinterpret_cast<const float4 *>(kin + c4);
+    const uint64_t t01 = ffma2(pk2u(r[c4], r[c4 + 1]), a2, mm2), t23 = ffma2(pk2u(r[c4 + 2], r[c4 + 3]), a2, mm2);
+    const float p0 = fast_exp2(ki.x < qcmp ? lo32(t01) : -INFINITY), p1 = fast_exp2(ki.y < qcmp ? hi32(t01) : -INFINITY);
+    const float p2 = fast_exp2(ki.z < qcmp ? lo32(t23) : -INFINITY), p3 = fast_exp2(ki.w < qcmp ? hi32(t23) : -INFINITY);
+    l2 = fadd2(l2, fadd2(pk2(p0, p1), pk2(p2, p3)));
+    const uint32_t kq = keep >> c4;
+    pk[c4 >> 1] = pack_bf16((kq & 1u) ? p0 : 0.f, (kq & 2u) ? p1 : 0.f);
+    pk[(c4 >> 1) + 1] = pack_bf16((kq & 4u) ? p2 : 0.f, (kq & 8u) ? p3 : 0.f);
+  }
+  tmem_st16(t_dst, pk);
+}
+
 // SORTED: causal, no padding mask, look-back window (every long-sequence config) — interval masks on position-sorted tiles.
 // !SORTED: the reference's masks evaluated per element from the keys' kv_info.  Two instantiations keep each one's code
 // (instruction-cache footprint) small.
@@ -442,6 +463,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const __gr
       const float2 am = mq.am[row];                                  // query-side scale a_i, self score m_i (log2 domain)
       const float a_i = am.x;
       float m2 = am.y, lse_off = 0.f;
+      [[maybe_unused]] float qcmp = qi;                              // (slot-ordered causal routine)
       uint32_t need = 0xfu;                                          // 32-column blocks of my tile any row of this warp sees
       int lo = 0, hi = 128;                                          // visible column interval in my tile
       uint32_t keep4[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};   // dropout keep bits per 32-column block
@@ -503,8 +525,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const __gr
         const float wmin = fminf(fminf(m0.vmin[0], m0.vmin[1]), fminf(m1.vmin[0], m1.vmin[1]));
         const float wmax = fmaxf(fmaxf(m0.vmax[0], m0.vmax[1]), fmaxf(m1.vmax[0], m1.vmax[1]));
         const bool visible = p.causal ? (wmin < qi) : !(wmin == qi && wmax == qi);
-        if (!visible) m2 -= kSelf;                                    // only the "-1e5" class is left: shift by it
-        if (p.masked && own_ki < 0.f) m2 = -kBig;                     // padding query: any finite result
+        if (p.causal && !p.masked) {
+          // fast causal routine (softmax_block_causal_keep): a row without any earlier key keeps exactly its "-1e5" class
+          qcmp = visible ? qi : qi + 0.5f;
+          if (!visible) lse_off = -1e5f;
+        } else {
+          if (!visible) m2 -= kSelf;                                  // only the "-1e5" class is left: shift by it
+          if (p.masked && own_ki < 0.f) m2 = -kBig;                   // padding query: any finite result
+        }
       }
       const uint64_t a2 = pk2(a_i, a_i), mm2 = pk2(-m2, -m2);
       if (warp == 0 && lane == 0) TC_TRACE(wk.k, 6);
@@ -527,7 +555,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attend_fwd_tc_kernel(const __gr
           softmax_block_mask(r, a2, mm2, below_hi & ~below_lo, t_p + bq * 16, l2);
         } else {
           const uint32_t kpw = bq == 0 ? keep4[0] : (bq == 1 ? keep4[1] : (bq == 2 ? keep4[2] : keep4[3]));
-          softmax_block_generic(r, mk.kinfo + bq * 32, qi, a_i, m2, p.causal, p.masked, kpw, t_p + bq * 16, l);
+          if (p.causal && !p.masked) softmax_block_causal_keep(r, mk.kinfo + bq * 32, qcmp, a2, mm2, kpw, t_p + bq * 16, l2);
+          else softmax_block_generic(r, mk.kinfo + bq * 32, qi, a_i, m2, p.causal, p.masked, kpw, t_p + bq * 16, l);
         }
       };
       auto zero_until = [&](int from, int to) {                       // zero P for the skipped blocks in [from, to)

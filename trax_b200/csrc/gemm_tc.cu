@@ -121,7 +121,8 @@ struct __align__(16) GemmShared {
 // sum_partials_kernel in a fixed order).
 __host__ __device__ constexpr int gemm_stages(int cl) { return cl == 2 ? 6 : 4; }
 
-template <int BN, int CL, bool MN>
+// RES: residual epilogue (its own instantiations: the plain products keep the code they were tuned with)
+template <int BN, int CL, bool MN, bool RES = false>
 __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -315,7 +316,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
           uint4 v = lds128u(stg + r * 128 + ((static_cast<uint32_t>(piece) ^ (r & 7)) << 4));
           if (grow < p.M) {
             const int64_t off = (grow + static_cast<int64_t>(g / tiles) * p.M) * p.ldc * (p.c_f32 ? 4 : 2) + col_bytes + piece * 16;
-            if (p.resid != nullptr) {                                  // y = x + attn / x = y - attn of the reversible block
+            if constexpr (RES) {                                       // y = x + attn / x = y - attn of the reversible block
               const uint4 rv = *reinterpret_cast<const uint4 *>(static_cast<const char *>(p.resid) + off);
               const float sg = p.acc_sign;
               if (p.c_f32) {
@@ -377,10 +378,10 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
 int make_tile_map(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes, uint32_t box_cols,
                   uint32_t box_rows);
 
-template <int BN, int CL, bool MN>
+template <int BN, int CL, bool MN, bool RES = false>
 static int gemm_tc_launch(const GemmTcParams &p, cudaStream_t stream) {
   const size_t smem = static_cast<size_t>(gemm_stages(CL)) * (GM_BM * 128 + (BN / CL) * 128) + GM_EPI_WARPS * 4096 + 1024;
-  auto kernel = gemm_tc_kernel<BN, CL, MN>;
+  auto kernel = gemm_tc_kernel<BN, CL, MN, RES>;
   LSH_OPT_IN_SMEM(kernel);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -442,6 +443,10 @@ int gemm_tc_run(int64_t M, int64_t N, int64_t K, const void *A, int64_t lda, con
   const int cl = (mode == 2 && p.m_blocks >= 2) ? 2 : 1;
   if (int rc = make_tile_map(&p.tm_a, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda) * 2, GM_BK, GM_BM)) return rc;
   if (int rc = make_tile_map(&p.tm_b, B, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldb) * 2, GM_BK, bn / cl)) return rc;
+  if (p.resid != nullptr) {
+    if (bn == 256) return cl == 2 ? gemm_tc_launch<256, 2, false, true>(p, stream) : gemm_tc_launch<256, 1, false, true>(p, stream);
+    return cl == 2 ? gemm_tc_launch<128, 2, false, true>(p, stream) : gemm_tc_launch<128, 1, false, true>(p, stream);
+  }
   if (bn == 256) return cl == 2 ? gemm_tc_launch<256, 2, false>(p, stream) : gemm_tc_launch<256, 1, false>(p, stream);
   return cl == 2 ? gemm_tc_launch<128, 2, false>(p, stream) : gemm_tc_launch<128, 1, false>(p, stream);
 }
