@@ -120,12 +120,34 @@ constexpr float kRedoBelow = 1e-30f, kRedoAbove = 1e30f;       // row sums outsi
 // per-ROW registers (no loads); bit c of `vis` says whether column c is visible.  ONE code copy serves interior blocks
 // (all ones) and boundary blocks: fewer instructions for the former were measured to be worth less than the
 // instruction-cache footprint of separate variants (A/B on one box: 0.329 vs 0.337 ms per launch + auxiliaries).
+// 2^x on the FMA / ALU pipes (Cody-Waite split + degree-3 minimax polynomial, max relative error 7.5e-5 — P is rounded to
+// bf16, 4e-3, right after): every TC_FWD_POLY-th column pair of a block takes this instead of MUFU.EX2, which two softmax
+// warps of one sub-partition otherwise keep ~85 % busy.  0 = off.
+#ifndef TC_FWD_POLY
+#define TC_FWD_POLY 0
+#endif
+__device__ __forceinline__ float poly_exp2(float x) {
+  x = fmaxf(x, -125.f);                                    // (masked / far-away scores: 2^-125, rounds to 0 in bf16)
+  const float y = x + 12582912.f;                          // 1.5 * 2^23: round-to-nearest integer part in the low mantissa bits
+  const float f = x - (y - 12582912.f);                    // in [-0.5, 0.5]
+  float p = fmaf(f, 0.05517132f, 0.24261054f);
+  p = fmaf(p, f, 0.69326097f);
+  p = fmaf(p, f, 0.9999281f);
+  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(y) << 23));
+}
 __device__ __forceinline__ void softmax_block_mask(const uint32_t (&r)[32], uint64_t a2, uint64_t mm2, uint32_t vis, uint32_t t_dst,
                                                    uint64_t &l2) {
   uint32_t pk[16];
 #pragma unroll
   for (int c2 = 0; c2 < 32; c2 += 2) {
     const uint64_t t = ffma2(pk2u(r[c2], r[c2 + 1]), a2, mm2);
+    if (TC_FWD_POLY > 0 && ((c2 >> 1) % (TC_FWD_POLY > 0 ? TC_FWD_POLY : 1)) == 0) {
+      const float q0 = poly_exp2(lo32(t)), q1 = poly_exp2(hi32(t));
+      const float p0 = (vis & (1u << c2)) ? q0 : 0.f, p1 = (vis & (2u << c2)) ? q1 : 0.f;
+      l2 = fadd2(l2, pk2(p0, p1));
+      pk[c2 >> 1] = pack_bf16(p0, p1);
+      continue;
+    }
     const float p0 = fast_exp2((vis & (1u << c2)) ? lo32(t) : -INFINITY);
     const float p1 = fast_exp2((vis & (2u << c2)) ? hi32(t) : -INFINITY);
     l2 = fadd2(l2, pk2(p0, p1));
