@@ -42,7 +42,9 @@
 extern "C" {
 #endif
 
-#define LSH_ATTN_ABI_VERSION 3
+/* 4: + lsh_layer_fwd_res / lsh_layer_bwd_res (residual epilogue), lsh_pack_heads / lsh_unpack_heads, lsh_layernorm_fwd_bf16,
+ *    LshAttnDims.x_bf16 (was reserved[0]; 0 keeps the v3 behaviour).  v3 entry points are unchanged. */
+#define LSH_ATTN_ABI_VERSION 4
 
 enum { LSH_DTYPE_F32 = 0, LSH_DTYPE_BF16 = 1 };
 
@@ -61,7 +63,9 @@ typedef struct LshAttnDims {
                             * 1: SelfAttention(share_qk=False) (EA:1133-1197): keys have their own projection w_k, are NOT
                             * normalised (only divided by sqrt(d_qk), EA:232) and self-attention is allowed (EA:1175-1178);
                             * every "qv" buffer then has dq+dv+dq columns per head: q | v | k.  n_hashes must be 1. */
-  int32_t reserved[2];
+  int32_t x_bf16;          /* layer calls with act_dtype = F32 only: 1 = the INPUT x is already bf16 (the caller's LayerNorm wrote
+                            * it that way, lsh_layernorm_fwd_bf16): no conversion pass; out / dout / dx stay f32. */
+  int32_t reserved[1];
 } LshAttnDims;
 
 int lsh_attn_abi_version(void);
@@ -150,6 +154,11 @@ int lsh_attend_bwd(const LshAttnDims *dims, const void *qv_bf16, const int32_t *
  * stats (rows, 2) f32 receives {mean, 1/sqrt(var + epsilon)} for the backward (may be NULL). */
 int lsh_layernorm_fwd(int64_t rows, int d_model, int act_dtype, const void *x, const float *scale,
                       const float *bias, void *z, float *stats, float epsilon, void *stream);
+
+/* The same normalisation for f32 activations with z written as bf16 — what the attention layer makes of its input anyway
+ * (same values: one rounding of the same fp32 number) — for layer calls with dims.x_bf16 = 1. */
+int lsh_layernorm_fwd_bf16(int64_t rows, int d_model, const float *x, const float *scale, const float *bias,
+                           void *z_bf16, float *stats, float epsilon, void *stream);
 
 /* VJP of the above: ct_out = (ct_in ? ct_in : 0) + dx (reversible.py:397-398 adds it to the context cotangent);
  * d_scale, d_bias (d_model) f32 are overwritten. */

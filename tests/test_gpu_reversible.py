@@ -179,3 +179,27 @@ def test_residual_fused_into_the_output_projection_matches_the_separate_pass(dty
                                                      _residual=(acc, -1.0))
   assert float((out1.float() - (acc.float() - out0.float())).abs().max()) <= tol
   assert torch.equal(dx0, dx1) and all(torch.equal(a, b) for a, b in zip(dw0, dw1))
+
+
+def test_layernorm_bf16_output_feeds_the_layer_without_a_conversion_pass():
+  """f32 activations: `lsh_layernorm_fwd_bf16` + a layer call with dims.x_bf16 must give exactly what the f32 LayerNorm output
+  followed by the layer's own f32 -> bf16 conversion gives (one rounding of the same fp32 number either way)."""
+  import trax_b200
+  from trax_b200 import reversible as R
+  layer = trax_b200.LSHSelfAttention(n_heads=4, causal=True, chunk_len=128, n_hashes=2, n_buckets=None)
+  layer.init(trax_b200.ShapeDtype((2, 1024, 256)))
+  g = torch.Generator('cuda').manual_seed(33)
+  ctx = torch.randn(2, 1024, 256, device='cuda', generator=g)
+  ct = torch.randn(2, 1024, 256, device='cuda', generator=g)
+  scale = torch.rand(256, device='cuda', generator=g) + 0.5
+  bias = torch.randn(256, device='cuda', generator=g)
+  z32, st32 = R.layernorm_fwd(ctx, scale, bias)
+  z16, st16 = R.layernorm_fwd(ctx, scale, bias, z_bf16=True)
+  assert z16.dtype == torch.bfloat16 and torch.equal(z16, z32.to(torch.bfloat16)) and torch.equal(st16, st32)
+  out0, state, _, _ = layer.forward_and_or_backward(z32, layer.weights, layer.state, None)
+  out1, _, dx1, dw1 = layer._forward_and_or_backward(z16, layer.weights, state, None, output_grad=ct, update_state=False,
+                                                     _io_dtype=torch.float32)
+  out2, _, dx2, dw2 = layer.forward_and_or_backward(z32, layer.weights, state, None, output_grad=ct, update_state=False)
+  assert out1.dtype == torch.float32 and dx1.dtype == torch.float32
+  assert torch.equal(out1, out2) and torch.equal(out0, out2) and torch.equal(dx1, dx2)
+  assert all(torch.equal(a, b) for a, b in zip(dw1, dw2))

@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('LSH_ATTN_LIB') or os.path.join(_HERE, 'liblsh_attn_b200.so')   # override: kernel experiments
 
 LSH_DTYPE_F32, LSH_DTYPE_BF16 = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class LshAttnDims(ctypes.Structure):
@@ -20,7 +20,7 @@ class LshAttnDims(ctypes.Structure):
       ('C', ctypes.c_int32), ('nb', ctypes.c_int32), ('na', ctypes.c_int32), ('nh', ctypes.c_int32),
       ('n_factors', ctypes.c_int32), ('factors', ctypes.c_int32 * 4),
       ('causal', ctypes.c_int32), ('masked', ctypes.c_int32),
-      ('act_dtype', ctypes.c_int32), ('separate_k', ctypes.c_int32), ('reserved', ctypes.c_int32 * 2),
+      ('act_dtype', ctypes.c_int32), ('separate_k', ctypes.c_int32), ('x_bf16', ctypes.c_int32), ('reserved', ctypes.c_int32 * 1),
   ]
 
 
@@ -52,6 +52,7 @@ SIGNATURES = {
     'lsh_layer_bwd_res': (_I, [_D, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P, _P, _P, ctypes.c_float, _P]),
     'lsh_make_rotations': (_I, [_D, _P, _P, _P, _P]),
     'lsh_layernorm_fwd': (_I, [_I64, _I, _I, _P, _P, _P, _P, _P, ctypes.c_float, _P]),
+    'lsh_layernorm_fwd_bf16': (_I, [_I64, _I, _P, _P, _P, _P, _P, ctypes.c_float, _P]),
     'lsh_layernorm_bwd': (_I, [_I64, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'lsh_residual_sub': (_I, [_I64, _I, _P, _P, _P, _P]),
     'lsh_residual_add': (_I, [_I64, _I, _P, _P, _P, _P]),

@@ -55,7 +55,7 @@ int unpack_dwqv_run(const LshAttnDims &, const float *, float *, float *, float 
 int pack_heads_run(int, int, int, int, const void *, int, const void *, int, void *, cudaStream_t);
 int unpack_heads_run(int, int, int, int, const void *, int, int, int, void *, cudaStream_t);
 int make_rotations_run(const LshAttnDims &, const uint32_t *, uint32_t *, float *, cudaStream_t);
-int layernorm_fwd_run(int64_t, int, int, const void *, const float *, const float *, void *, float2 *, float, cudaStream_t);
+int layernorm_fwd_run(int64_t, int, int, const void *, const float *, const float *, void *, float2 *, float, cudaStream_t, bool z_bf16 = false);
 int layernorm_bwd_run(int64_t, int, int, const void *, const void *, const void *, const float2 *, const float *, void *, float *,
                       float *, cudaStream_t);
 int residual_sub_run(int64_t, int, const void *, const void *, void *, float, cudaStream_t);
@@ -262,7 +262,7 @@ static int forward_core(const LshAttnDims &d, const LayerWs &w, const void *x, c
   const int64_t BL = static_cast<int64_t>(d.B) * d.L;
   int rc;
   const void *xb = x;
-  if (d.act_dtype == LSH_DTYPE_F32) {
+  if (d.act_dtype == LSH_DTYPE_F32 && !d.x_bf16) {        // (x_bf16: f32 activations whose layer input already is bf16, see lsh_attn.h)
     if ((rc = f32_to_bf16_run(static_cast<const float *>(x), w.xb, BL * d.D, s))) return rc;
     xb = w.xb;
   }
@@ -536,6 +536,13 @@ int lsh_layernorm_fwd(int64_t rows, int d_model, int act_dtype, const void *x, c
   if (act_dtype != LSH_DTYPE_F32 && act_dtype != LSH_DTYPE_BF16) return set_error("lsh_layernorm_fwd: bad act_dtype");
   return layernorm_fwd_run(rows, d_model, act_dtype, x, scale, bias, z, reinterpret_cast<float2 *>(stats), epsilon,
                            static_cast<cudaStream_t>(stream));
+}
+
+int lsh_layernorm_fwd_bf16(int64_t rows, int d_model, const float *x, const float *scale, const float *bias, void *z_bf16,
+                           float *stats, float epsilon, void *stream) {
+  if (!x || !scale || !bias || !z_bf16) return set_error("lsh_layernorm_fwd_bf16: NULL argument");
+  return layernorm_fwd_run(rows, d_model, LSH_DTYPE_F32, x, scale, bias, z_bf16, reinterpret_cast<float2 *>(stats), epsilon,
+                           static_cast<cudaStream_t>(stream), true);
 }
 
 int lsh_layernorm_bwd(int64_t rows, int d_model, int act_dtype, const void *x, const void *dz, const void *ct_in,

@@ -46,9 +46,11 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // Reads x (row), writes z (row) and {mean, rstd} (8 bytes per row).
-template <typename T, int NV>
+// TZ: type of z — T, or bf16 for f32 activations when the consumer is the attention layer (which rounds its input to bf16
+// anyway: the same values, half the bytes, and no separate conversion pass in the layer).
+template <typename T, int NV, typename TZ = T>
 __global__ void __launch_bounds__(LN_THREADS) layernorm_fwd_kernel(const T *__restrict__ x, const float *__restrict__ scale,
-                                                                 const float *__restrict__ bias, T *__restrict__ z,
+                                                                 const float *__restrict__ bias, TZ *__restrict__ z,
                                                                  float2 *__restrict__ stats, int64_t rows, int D, float eps) {
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * (LN_THREADS / 32) + (threadIdx.x >> 5);
@@ -81,7 +83,7 @@ __global__ void __launch_bounds__(LN_THREADS) layernorm_fwd_kernel(const T *__re
       load8<float>(bias + (i * 32 + lane) * 8, bi);
 #pragma unroll
       for (int e = 0; e < 8; ++e) o[e] = fmaf(v[i][e] * rstd, sc[e], bi[e]);
-      store8<T>(z + row * D + (i * 32 + lane) * 8, o);
+      store8<TZ>(z + row * D + (i * 32 + lane) * 8, o);
     }
   }
   if (lane == 0 && stats != nullptr) stats[row] = make_float2(mean, rstd);
@@ -184,10 +186,13 @@ static int check_ln(int64_t rows, int D) {
   }
 
 int layernorm_fwd_run(int64_t rows, int D, int dtype, const void *x, const float *scale, const float *bias, void *z,
-                      float2 *stats, float eps, cudaStream_t stream) {
+                      float2 *stats, float eps, cudaStream_t stream, bool z_bf16) {
   if (int rc = check_ln(rows, D)) return rc;
   const unsigned grid = static_cast<unsigned>((rows + LN_THREADS / 32 - 1) / (LN_THREADS / 32));
-  if (dtype == LSH_DTYPE_F32) {
+  if (dtype == LSH_DTYPE_F32 && z_bf16) {
+    LN_DISPATCH_NV(D, (layernorm_fwd_kernel<float, NV, __nv_bfloat16><<<grid, LN_THREADS, 0, stream>>>(
+        static_cast<const float *>(x), scale, bias, static_cast<__nv_bfloat16 *>(z), stats, rows, D, eps)));
+  } else if (dtype == LSH_DTYPE_F32) {
     LN_DISPATCH_NV(D, (layernorm_fwd_kernel<float, NV><<<grid, LN_THREADS, 0, stream>>>(
         static_cast<const float *>(x), scale, bias, static_cast<float *>(z), stats, rows, D, eps)));
   } else {

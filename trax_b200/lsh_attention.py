@@ -454,7 +454,7 @@ class LSHSelfAttention:
     return self._forward_and_or_backward(inputs, weights, state, rng, output_grad, compute_output, update_state)
 
   def _forward_and_or_backward(self, inputs, weights, state, rng, output_grad=None,
-                               compute_output=True, update_state=True, _stash=None, _residual=None):
+                               compute_output=True, update_state=True, _stash=None, _residual=None, _io_dtype=None):
     """Performs batched forward and/or backward passes (EA:2261-2289).
 
     Returns (output, new_state, inputs_grad, weights_grad):
@@ -478,7 +478,7 @@ class LSHSelfAttention:
       # kernels, streams and the scratch buffer belong to the tensors' device, whatever the caller's current device is
       with torch.cuda.device(x.device):
         return self._forward_and_or_backward(inputs if not have_single_input else inputs[0], weights, state, rng, output_grad,
-                                             compute_output, update_state, _stash, _residual)
+                                             compute_output, update_state, _stash, _residual, _io_dtype)
     lib = _lib.load()
     host_io = not x.is_cuda
     dev = torch.device('cuda', torch.cuda.current_device()) if host_io else x.device
@@ -521,7 +521,15 @@ class LSHSelfAttention:
     if tuple(w_q.shape) != (self._n_heads, d_model, self._d_qk) or tuple(w_o.shape) != (self._n_heads, self._d_v, d_model):
       raise ValueError('weights do not match (n_heads, d_model, d_head) layout: %s %s %s'
                        % (tuple(w_q.shape), tuple(w_v.shape), tuple(w_o.shape)))
-    dims = self._dims(batch_size, seqlen, d_model, ops._act_dtype(x_d))
+    # _io_dtype (ReversibleHalfResidual with f32 activations): the input arrives as bf16 straight from the LayerNorm kernel,
+    # outputs and cotangents are f32 (dims.x_bf16, include/lsh_attn.h)
+    io_dtype = x_d.dtype
+    if _io_dtype is not None and _io_dtype != x_d.dtype:
+      if not (x_d.dtype == torch.bfloat16 and _io_dtype == torch.float32):
+        raise ValueError('_io_dtype: only bf16 input with f32 outputs is supported')
+      io_dtype = torch.float32
+    dims = self._dims(batch_size, seqlen, d_model, _lib.LSH_DTYPE_F32 if io_dtype == torch.float32 else _lib.LSH_DTYPE_BF16)
+    dims.x_bf16 = 1 if io_dtype != x_d.dtype else 0
     _lib.check(lib.lsh_attn_check_dims(ctypes.byref(dims)), 'LSHSelfAttention')
     bh = batch_size * self._n_heads
     length = self._n_hashes * (self._max_length_for_buckets or seqlen)
@@ -554,13 +562,13 @@ class LSHSelfAttention:
 
     out_d = None
     if compute_output:
-      out_d = torch.empty_like(x_d)                                 # dtype of inputs[0], EA:2529-2530
+      out_d = torch.empty(x_d.shape, dtype=io_dtype, device=dev)    # dtype of inputs[0], EA:2529-2530
     # residual of the enclosing reversible block, fused into the output projection's epilogue (reversible.py:318, 400):
     # out = residual + sign * attention_output
     res_d, res_sign = None, 1.0
     if _residual is not None and compute_output:
       res_d, res_sign = _residual
-      if not res_d.is_cuda or res_d.shape != x_d.shape or res_d.dtype != x_d.dtype or not res_d.is_contiguous():
+      if not res_d.is_cuda or res_d.shape != x_d.shape or res_d.dtype != io_dtype or not res_d.is_contiguous():
         raise ValueError('fused residual must be a contiguous device tensor shaped and typed like the input')
     inputs_grad = weights_grad = None
     if not compute_grad:
@@ -574,12 +582,12 @@ class LSHSelfAttention:
         _lib.check(lib.lsh_layer_fwd(
             ctypes.byref(dims), ops._ptr(x_d), ops._ptr(w_q), ops._ptr(w_v), ops._ptr(w_o), ops._ptr(w_k), ops._ptr(rotations),
             ops._ptr(mask_d), ops._ptr(attn_keep), ops._ptr(buckets_d), buckets_d.stride(0),
-            ops._ptr(out_d if out_d is not None else torch.empty_like(x_d)), ops._ptr(ws), ws.numel(), stream),
+            ops._ptr(out_d if out_d is not None else torch.empty(x_d.shape, dtype=io_dtype, device=dev)), ops._ptr(ws), ws.numel(), stream),
             'lsh_layer_fwd')
-      g_d = to_dev(output_grad).to(x_d.dtype).contiguous()
+      g_d = to_dev(output_grad).to(io_dtype).contiguous()
       if g_d.shape != x_d.shape:
         raise ValueError('output_grad shape %s != input shape %s' % (tuple(g_d.shape), tuple(x_d.shape)))
-      dx = torch.empty_like(x_d)
+      dx = torch.empty(x_d.shape, dtype=io_dtype, device=dev)
       # one contiguous gradient buffer (dw_q | dw_v | dw_o): the data-parallel mean below reduces slices of it in place
       n_q, n_v, n_o = w_q.numel() + (w_k.numel() if w_k is not None else 0), w_v.numel(), w_o.numel()
       dw_flat = torch.empty(n_q + n_v + n_o, dtype=torch.float32, device=dev)

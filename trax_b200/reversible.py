@@ -26,13 +26,20 @@ def _rows(x):
   return int(x.numel() // x.shape[-1]), int(x.shape[-1])
 
 
-def layernorm_fwd(x, scale, bias, epsilon=1e-6):
-  """trax/layers/normalization.py:129-136.  Returns (z, stats (rows, 2) f32 = {mean, rstd})."""
+def layernorm_fwd(x, scale, bias, epsilon=1e-6, z_bf16=False):
+  """trax/layers/normalization.py:129-136.  Returns (z, stats (rows, 2) f32 = {mean, rstd}).  z_bf16 (f32 activations
+  only): z is written as bf16 — the rounding the attention layer applies to its input anyway — for layer calls with
+  `_io_dtype=torch.float32` (no f32 z round trip, no conversion pass)."""
   lib = _lib.load()
   x = x.contiguous()
   rows, d = _rows(x)
-  z = torch.empty_like(x)
   stats = torch.empty((rows, 2), dtype=torch.float32, device=x.device)
+  if z_bf16 and x.dtype == torch.float32:
+    z = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    _lib.check(lib.lsh_layernorm_fwd_bf16(rows, d, ops._ptr(x), ops._ptr(scale), ops._ptr(bias), ops._ptr(z), ops._ptr(stats),
+                                          ctypes.c_float(epsilon), ops._stream()), 'lsh_layernorm_fwd_bf16')
+    return z, stats
+  z = torch.empty_like(x)
   _lib.check(lib.lsh_layernorm_fwd(rows, d, ops._act_dtype(x), ops._ptr(x), ops._ptr(scale), ops._ptr(bias), ops._ptr(z),
                                    ops._ptr(stats), ctypes.c_float(epsilon), ops._stream()), 'lsh_layernorm_fwd')
   return z, stats
@@ -123,13 +130,16 @@ class ReversibleHalfResidual:
     accumulator, context = xs
     scale, bias = self._ln_weights
     rngs = _split_rngs(self.rng, 2)                                        # reversible.py:297: (LayerNorm, attention)
-    z, _ = layernorm_fwd(context, scale, bias, self._epsilon)
+    fused = self._fused(accumulator, context)
+    z, _ = layernorm_fwd(context, scale, bias, self._epsilon, z_bf16=fused)
     attn = self._attention_layer
     with torch.no_grad():
-      if self._fused(accumulator, z):
-        # output = accumulator + residual (reversible.py:318) leaves the output projection's epilogue: no separate pass
+      if fused:
+        # output = accumulator + residual (reversible.py:318) leaves the output projection's epilogue: no separate pass;
+        # with f32 activations the LayerNorm hands its result over as bf16 (what the layer makes of its input anyway)
         out, new_state, _, _ = attn._forward_and_or_backward(z, attn.weights, attn.state, rngs[1], compute_output=True,
-                                                             update_state=True, _residual=(accumulator.contiguous(), +1.0))
+                                                             update_state=True, _residual=(accumulator.contiguous(), +1.0),
+                                                             _io_dtype=context.dtype)
         attn.state = new_state
         return out, context
       residual, new_state = attn.pure_fn(z, attn.weights, attn.state, rngs[1])     # reversible.py:308
@@ -153,12 +163,13 @@ class ReversibleHalfResidual:
     (scale, bias), attn_weights = weights if weights else self.weights
     attn_state = (new_state if new_state else self.state)[1]
     rngs = _split_rngs(rng, 2)                                             # reversible.py:328: same split as forward
-    z, stats = layernorm_fwd(context, scale, bias, self._epsilon)
-    if self._fused(accumulator_output, z):
+    fused = self._fused(accumulator_output, context)
+    z, stats = layernorm_fwd(context, scale, bias, self._epsilon, z_bf16=fused)
+    if fused:
       # reconstructed_x = accumulator_output - residual (reversible.py:400), again in the epilogue of the same GEMM
       reconstructed_x, _, dz, attn_weights_ct = self._attention_layer._forward_and_or_backward(
           z, attn_weights, attn_state, rngs[1], output_grad=accumulator_output_ct, compute_output=True, update_state=False,
-          _residual=(accumulator_output.contiguous(), -1.0))
+          _residual=(accumulator_output.contiguous(), -1.0), _io_dtype=context.dtype)
       context_ct_new, d_scale, d_bias = layernorm_bwd(context, dz, context_ct, stats, scale)
     else:
       residual, _, dz, attn_weights_ct = self._attention_layer.forward_and_or_backward(

@@ -60,7 +60,7 @@ class SelfAttention(LSHSelfAttention):
     return output
 
   def _forward_and_or_backward(self, inputs, weights, state, rng, output_grad=None, compute_output=True, update_state=True,
-                               _stash=None, _residual=None):
+                               _stash=None, _residual=None, _io_dtype=None):
     x = inputs[0] if isinstance(inputs, (tuple, list)) else inputs
     if not torch.cuda.is_available():
       from trax_b200 import _lib
@@ -70,5 +70,5 @@ class SelfAttention(LSHSelfAttention):
     buckets = torch.zeros((int(x.shape[0]) * self._n_heads, int(x.shape[1])), dtype=torch.int32, device=dev)
     out, _, inputs_grad, weights_grad = super()._forward_and_or_backward(
         inputs, weights, (buckets, None), rng, output_grad=output_grad, compute_output=compute_output, update_state=False,
-        _stash=_stash, _residual=_residual)
+        _stash=_stash, _residual=_residual, _io_dtype=_io_dtype)
     return out, (state if update_state else None), inputs_grad, weights_grad
