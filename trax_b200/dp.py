@@ -5,6 +5,8 @@ every device owns B/n examples with all heads and replicated weights.  The analo
 GPU (`torch.distributed`, NCCL over NVLink on the GPU box, gloo in CPU tests): `shard_batch` picks a rank's
 examples, `allreduce_mean_` averages the weight gradients.  Units (example, head) never exchange data.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -30,7 +32,8 @@ class GradOverlap:
 
   def __init__(self, dev):
     self.dev = dev
-    self.comm = torch.cuda.Stream(device=dev, priority=-1)      # above the compute stream: collectives must not queue behind GEMMs
+    # above the compute stream by default: collectives must not queue behind GEMMs (LSH_COMM_STREAM_PRIORITY=0: same priority)
+    self.comm = torch.cuda.Stream(device=dev, priority=int(os.environ.get('LSH_COMM_STREAM_PRIORITY', '-1')))
     self._events = None
 
   @classmethod
