@@ -263,9 +263,11 @@ def run_ours(args, wl, name):
   dout = torch.randn((B, L, D), generator=g, device=dev, dtype=torch.float32).to(dtype)
   x_host, dout_host = x.cpu().pin_memory(), dout.cpu().pin_memory()
 
-  # psum/n of the weight gradients (trainer.py:194-199) runs inside the backward call, on a communication stream
-  # underneath the call's remaining kernels (trax_b200.dp.GradOverlap)
-  trax_b200.set_weight_grad_allreduce(world > 1 and not head_sharded)
+  # psum/n of the weight gradients (trainer.py:194-199) runs inside the backward call: one in-place all-reduce of the
+  # contiguous gradient buffer after the call's last kernel
+  # (--grad-allreduce overlap: the slices travel on a communication stream underneath the call's remaining kernels instead;
+  # measured 2.56 vs 2.50 ms at 2 GPUs, but 2.9-3.0 vs 2.52 ms at 8 GPUs on one box — DESIGN.md section 7)
+  trax_b200.set_weight_grad_allreduce(args.grad_allreduce if (world > 1 and not head_sharded) else False)
 
   # the dropout masks are a function of the rng: the backward call gets the one the forward call used
   bwd_rng = getattr(layer, 'rng', np.array([0, 0], np.uint32)) if args.attention_dropout > 0.0 else None
@@ -510,6 +512,9 @@ def main():
   ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
   ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
   ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--grad-allreduce', default='flat', choices=['flat', 'overlap'],
+                  help='data-parallel weight-gradient mean inside the backward call: one flat all-reduce after the last kernel '
+                       '(default) or two slices overlapped with the rest of the call')
   ap.add_argument('--attention-dropout', type=float, default=0.0,
                   help='attention dropout rate of the layer (default 0: the BASELINE configs; the reference gins train with 0.2)')
   ap.add_argument('--head-reduce', default='all', choices=['all', 'scatter'],

@@ -75,6 +75,20 @@ class GradOverlap:
     main.wait_event(done)
 
 
+def allreduce_mean_flat_(flat, group=None):
+  """In-place mean of ONE contiguous gradient buffer over the process group, on the caller's stream, after the call's last
+  kernel (no concatenation, no copy back; NCCL divides itself).  The robust data-parallel default: its cost is the
+  collective's own duration (6.3 MB at config 2/3) and nothing it does can take SMs from the layer's persistent kernels."""
+  if not dist.is_initialized() or dist.get_world_size(group) == 1:
+    return flat
+  if dist.get_backend(group) == 'nccl':
+    dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
+  else:
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat /= dist.get_world_size(group)
+  return flat
+
+
 def allreduce_mean_(grads, group=None):
   """In-place mean of a tuple of gradient tensors over the process group, as ONE flat all-reduce
   (6.3 MB at config 2/3: latency-bound, so a single bucket)."""

@@ -171,8 +171,14 @@ _GRAD_ALLREDUCE = {'on': False}
 def set_weight_grad_allreduce(flag):
   """Data-parallel training: average (dw_q, dw_v, dw_o) over the default process group INSIDE the backward call, on
   the device, before they are returned / downloaded — the analogue of `psum(grads) / n` inside Trax's pmapped step
-  (`trax/optimizers/trainer.py:172-199`).  Off by default (the caller then reduces the returned gradients itself)."""
-  _GRAD_ALLREDUCE['on'] = bool(flag)
+  (`trax/optimizers/trainer.py:172-199`).  Off by default (the caller then reduces the returned gradients itself).
+  True / 'flat': one in-place all-reduce of the contiguous gradient buffer on the caller's stream after the call's last
+  kernel.  'overlap': the two slices are reduced on a communication stream as soon as each is final
+  (`dp.GradOverlap`) — underneath the remaining kernels; faster when the ranks run in step, but the collective's CTAs
+  displace CTAs of the layer's persistent kernels for as long as they wait for the slowest rank."""
+  if flag not in (False, True, None, 0, 1, 'flat', 'overlap'):
+    raise ValueError("set_weight_grad_allreduce: False, True / 'flat' or 'overlap'")
+  _GRAD_ALLREDUCE['on'] = 'overlap' if flag == 'overlap' else ('flat' if flag else False)
 
 
 def synchronize():
@@ -597,6 +603,7 @@ class LSHSelfAttention:
       overlap = None
       if _GRAD_ALLREDUCE['on']:
         from trax_b200 import dp
+      if _GRAD_ALLREDUCE['on'] == 'overlap':
         overlap = dp.GradOverlap.get(dev)         # None without an initialised NCCL group of more than one rank
       ev_o, ev_qv = (overlap.events() if overlap is not None else (None, None))
       _lib.check(lib.lsh_layer_bwd_res(
@@ -613,7 +620,7 @@ class LSHSelfAttention:
         # dw_q|dw_v under the dx GEMM.  (With output dropout dw_o is rescaled after the call, so it goes last.)
         overlap.reduce(dw_flat, n_q + n_v, ev_o if out_mult is None else None, ev_qv)
       elif _GRAD_ALLREDUCE['on']:
-        dp.allreduce_mean_((dw_q, dw_v, dw_o))
+        dp.allreduce_mean_flat_(dw_flat)          # (dw_q | dw_k | dw_v | dw_o are views of this buffer)
       if host_io:
         dx, dw_q, dw_v, dw_o = (io.download(t, r) for t, r in ((dx, 'dx'), (dw_q, 'dw_q'), (dw_v, 'dw_v'), (dw_o, 'dw_o')))
         if dw_k is not None:
