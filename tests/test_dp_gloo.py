@@ -26,6 +26,11 @@ def _worker(rank, world, port, out):
   dp.allreduce_mean_(g)
   want0 = x.sum(dim=(0, 1)) / world
   ok = torch.allclose(g[0], want0) and torch.allclose(g[1], torch.full((2, 5), 1.5)) and torch.allclose(g[2], torch.ones(3) * 5.5)
+  # the layer's default: ONE contiguous buffer (dw_q | dw_v | dw_o are views of it), reduced in place
+  flat = torch.arange(10, dtype=torch.float32) * (rank + 1)
+  view = flat[4:]
+  same = dp.allreduce_mean_flat_(flat)
+  ok = ok and same is flat and torch.allclose(flat, torch.arange(10, dtype=torch.float32) * 1.5) and torch.allclose(view, flat[4:])
   out[rank] = bool(ok)
   dist.barrier()
   dist.destroy_process_group()
@@ -44,6 +49,8 @@ def test_allreduce_is_identity_without_process_group():
   from trax_b200 import dp
   g = (torch.ones(3), torch.zeros(2, 2))
   assert dp.allreduce_mean_(g) is g and torch.equal(g[0], torch.ones(3))
+  f = torch.ones(4)
+  assert dp.allreduce_mean_flat_(f) is f and torch.equal(f, torch.ones(4))
 
 
 # ---- head sharding (BASELINE config 5): the head sums of EA:2426 / EA:2430 across ranks ------------------------------------
