@@ -146,3 +146,15 @@ def test_randomised_sweep_against_the_live_reference():
                      capture_output=True, text=True)
   assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
   assert r.stdout.count('\nok') + r.stdout.startswith('ok') == 32
+
+
+@pytest.mark.skipif(not ref_live.available(), reason='the reference checkout exists only in the build container')
+def test_predict_mode_sweep_against_the_live_reference():
+  """oracle/ref_live_predict.py: `oracle/predict_oracle.py` vs the reference's own `mode='predict'` code (LSHSelfAttention
+  EA:1999-2109, 2174-2244 and SelfAttention EA:1200-1268), call by call: prefixes shorter / equal / longer than the memory,
+  then single tokens until the memory has rolled twice; outputs to 1e-11, memory / bucket memory / counters exact."""
+  repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  r = subprocess.run([sys.executable, os.path.join(repo, 'oracle', 'ref_live_predict.py'), '16', '3'], cwd=repo, timeout=900,
+                     capture_output=True, text=True)
+  assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+  assert r.stdout.count('\nok') + r.stdout.startswith('ok') == 16
