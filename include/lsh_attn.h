@@ -44,7 +44,8 @@ extern "C" {
 
 /* 4: + lsh_layer_fwd_res / lsh_layer_bwd_res (residual epilogue), lsh_pack_heads / lsh_unpack_heads, lsh_layernorm_fwd_bf16,
  *    LshAttnDims.x_bf16 (was reserved[0]; 0 keeps the v3 behaviour).  v3 entry points are unchanged. */
-#define LSH_ATTN_ABI_VERSION 4
+/* 5: + lsh_predict_step / lsh_predict_workspace_bytes (fast inference, mode='predict').  v4 entry points are unchanged. */
+#define LSH_ATTN_ABI_VERSION 5
 
 enum { LSH_DTYPE_F32 = 0, LSH_DTYPE_BF16 = 1 };
 
@@ -218,6 +219,26 @@ int lsh_layer_bwd_res(const LshAttnDims *dims, const void *x, const float *w_q, 
                       const int32_t *buckets, int64_t buckets_stride, const void *dout, void *out, void *dx,
                       float *dw_q, float *dw_v, float *dw_o, float *dw_k, void *ws, size_t ws_bytes,
                       void *ev_dwo_ready, void *ev_dwqv_ready, const void *residual, float acc_sign, void *stream);
+
+/* ---- fast inference, mode='predict' (EA:1999-2109, 1200-1268) --------------------------------- */
+
+/* ONE new token per example against the layer's input memory — the single-token branch of
+ * `LSHSelfAttention._incremental_forward_unbatched` (EA:2032-2109) for every unit at once, and with rotations == buckets ==
+ * NULL the q_len == 1 case of `SelfAttention._incremental_forward_unbatched` (EA:1200-1268; dims.separate_k / dims.causal as
+ * in the layer calls).  dims.L is the MEMORY length (`predict_mem_len`), dims.factors the bucket list of THIS step (EA:2066
+ * hashes two rows, so `n_buckets=None` resolves to [2], EA:1893-1902).
+ *   mem      (B, M, D) act_dtype: the input memory AFTER `_use_predict_mem` (EA:2174-2207) stored the new token at q_start
+ *   buckets  (B*H, buckets_stride) int32, rows (nh, M): the bucket memory AFTER the caller's roll (EA:2036-2053); the call
+ *            writes the new token's ids into column q_start (EA:2069-2071) — in place
+ *   rotations (B*H, dq, nh, R) f32: drawn from the state's hash key itself, not from a split of it (EA:2066)
+ *   out      (B, 1, D) act_dtype
+ * Attended slots: the n_hashes * chunk_len * (1 + n_chunks_before) memory slots of highest priority (same-bucket slots first,
+ * then the most recent ones, EA:2073-2084) under the causal and self masks of EA:2091-2092.  The memory roll, `mem_end` and
+ * `buckets_idx` are host bookkeeping (trax_b200/predict.py).  Prefixes (q_len > 1, EA:2004-2030) are lsh_layer_fwd calls. */
+size_t lsh_predict_workspace_bytes(const LshAttnDims *dims);
+int lsh_predict_step(const LshAttnDims *dims, const void *mem, const float *w_q, const float *w_v, const float *w_o,
+                     const float *w_k, const float *rotations, int32_t *buckets, int64_t buckets_stride, int32_t q_start,
+                     void *out, void *ws, size_t ws_bytes, void *stream);
 
 /* ---- helpers ---------------------------------------------------------------------------------- */
 

@@ -86,9 +86,11 @@ def use_predict_mem(pcfg: PredictConfig, x, mem_end: int, mem):
 
 
 def incremental_forward_unit(cfg: O.LSHConfig, pcfg: PredictConfig, x, q_start: int, q_len: int, w_q, w_v, w_o, buckets,
-                             buckets_idx: int, rotations_fn):
+                             buckets_idx: int, rotations_fn, new_ids=None):
   """EA:1999-2109 for one (example, head).  `rotations_fn(n_rows)` returns the (dq, nh, R) rotations `hash_vectors` would
   draw for `n_rows` hashed rows (the shape depends on n_rows only through `n_buckets=None`, EA:1893-1902).
+  `new_ids` (GPU parity tests): bucket ids to use instead of hashing here — (nh * padded_len,) for a prefix, (nh,) for one
+  token — so that a comparison downstream of the hash does not hinge on fp32-vs-bf16 argmax near-ties.
   Returns (out (q_len, D), new_buckets, new_buckets_idx)."""
   nh, m = cfg.n_hashes, pcfg.predict_mem_len
   x = np.asarray(x, np.float64)
@@ -99,7 +101,10 @@ def incremental_forward_unit(cfg: O.LSHConfig, pcfg: PredictConfig, x, q_start: 
     else:
       x_padded = x
     q = x_padded @ w_q
-    buckets_update = O.hash_vectors(cfg, q.astype(np.float32), rotations_fn(x_padded.shape[0]))      # EA:2014
+    if new_ids is None:
+      buckets_update = O.hash_vectors(cfg, q.astype(np.float32), rotations_fn(x_padded.shape[0]))    # EA:2014
+    else:
+      buckets_update = np.asarray(new_ids, np.int32).reshape(-1)
     res = O.forward_unit(cfg, x_padded, w_q, w_v, w_o, buckets=buckets_update)                        # EA:2016-2018
     out = res.out[:q_len]
     buckets = np.reshape(buckets, (nh, -1))
@@ -114,8 +119,11 @@ def incremental_forward_unit(cfg: O.LSHConfig, pcfg: PredictConfig, x, q_start: 
     b2 = np.concatenate([b2, np.zeros((nh, pcfg.predict_drop_len), b2.dtype)], axis=1)
     buckets = np.reshape(_dynamic_slice(b2, buckets_idx - q_start, m, axis=1), (-1,))
   q = np.concatenate([x[q_start:q_start + 1]] * 2, 0) @ w_q          # EA:2064 (the duplicated row)
-  q_buckets = O.hash_vectors(cfg, q.astype(np.float32), rotations_fn(2))                              # EA:2066
-  q_buckets = np.reshape(q_buckets, (nh, 2))[:, :1]
+  if new_ids is None:
+    q_buckets = O.hash_vectors(cfg, q.astype(np.float32), rotations_fn(2))                            # EA:2066
+    q_buckets = np.reshape(q_buckets, (nh, 2))[:, :1]
+  else:
+    q_buckets = np.asarray(new_ids, np.int32).reshape(nh, 1)
   unflattened = _dynamic_update_slice(np.reshape(buckets, (nh, -1)), q_buckets, q_start, axis=1)      # EA:2069-2071
   buckets = np.reshape(unflattened, (-1,))
   is_valid_target = np.any(unflattened == q_buckets, axis=0)         # EA:2073
@@ -139,8 +147,9 @@ def incremental_forward_unit(cfg: O.LSHConfig, pcfg: PredictConfig, x, q_start: 
   return out[:1], buckets, q_start + q_len                           # EA:2104-2109
 
 
-def predict_forward(cfg: O.LSHConfig, pcfg: PredictConfig, x, weights, state, rotations_fn):
-  """One call of the layer in predict mode (EA:2127-2170): x (B, seqlen, D); `rotations_fn(unit, n_rows)` as above.
+def predict_forward(cfg: O.LSHConfig, pcfg: PredictConfig, x, weights, state, rotations_fn, new_ids_fn=None):
+  """One call of the layer in predict mode (EA:2127-2170): x (B, seqlen, D); `rotations_fn(unit, n_rows)` as above;
+  `new_ids_fn(unit)` optionally supplies the call's bucket ids (see incremental_forward_unit).
   Returns (output (B, seqlen, D), new_state)."""
   mem_end, mem, (buckets, buckets_idx) = state
   w_q, w_v, w_o = weights
@@ -151,7 +160,8 @@ def predict_forward(cfg: O.LSHConfig, pcfg: PredictConfig, x, weights, state, ro
   for idx in range(bsz * cfg.n_heads):
     b, h = idx // cfg.n_heads, idx % cfg.n_heads
     o, nb[idx], ni[idx] = incremental_forward_unit(cfg, pcfg, inputs[b], q_start, seqlen, w_q[h], w_v[h], w_o[h], buckets[idx],
-                                                   int(buckets_idx[idx]), lambda n, _u=idx: rotations_fn(_u, n))
+                                                   int(buckets_idx[idx]), lambda n, _u=idx: rotations_fn(_u, n),
+                                                   None if new_ids_fn is None else new_ids_fn(idx))
     out[b] += o
   return out, (new_mem_end, new_mem, (nb, ni))
 

@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('LSH_ATTN_LIB') or os.path.join(_HERE, 'liblsh_attn_b200.so')   # override: kernel experiments
 
 LSH_DTYPE_F32, LSH_DTYPE_BF16 = 0, 1
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class LshAttnDims(ctypes.Structure):
@@ -58,6 +58,8 @@ SIGNATURES = {
     'lsh_residual_add': (_I, [_I64, _I, _P, _P, _P, _P]),
     'lsh_pack_heads': (_I, [_I, _I, _I, _I, _P, _I, _P, _I, _P, _P]),
     'lsh_unpack_heads': (_I, [_I, _I, _I, _I, _P, _I, _I, _I, _P, _P]),
+    'lsh_predict_workspace_bytes': (_SZ, [_D]),
+    'lsh_predict_step': (_I, [_D, _P, _P, _P, _P, _P, _P, _P, _I64, ctypes.c_int32, _P, _P, _SZ, _P]),
     'lsh_attn_launch_count': (_I64, [_I]),
 }
 

@@ -59,6 +59,8 @@ int layernorm_fwd_run(int64_t, int, int, const void *, const float *, const floa
 int layernorm_bwd_run(int64_t, int, int, const void *, const void *, const void *, const float2 *, const float *, void *, float *,
                       float *, cudaStream_t);
 int residual_sub_run(int64_t, int, const void *, const void *, void *, float, cudaStream_t);
+int predict_attend_run(const LshAttnDims &, const void *, int32_t *, int64_t, const int32_t *, int, float *, cudaStream_t);
+int predict_out_run(const LshAttnDims &, const float *, const float *, void *, cudaStream_t);
 
 // ---- dims ------------------------------------------------------------------------------------------
 static int check_dims(const LshAttnDims *dp, bool need_bwd) {
@@ -300,6 +302,32 @@ static int forward_core(const LshAttnDims &d, const LayerWs &w, const void *x, c
       return rc;
   }
   return 0;
+}
+
+// ---- fast inference (mode='predict'): scratch of one single-token step ---------------------------------------------
+struct PredictWs {
+  LayerWs lw;               // cublas, xb, wqv, wo, wqv_t, wo_t, qv (the fields pack_layer_weights / gemm_aw use)
+  int32_t *hashed;
+  float *o;
+  size_t total;
+};
+
+static PredictWs carve_predict(const LshAttnDims &d, void *ws) {
+  Derived dr = derive(d);
+  PredictWs p{};
+  Bump b(ws);
+  const size_t BM = static_cast<size_t>(d.B) * d.L;
+  p.lw.cublas = b.take(kCublasWs);
+  p.lw.xb = d.act_dtype == LSH_DTYPE_F32 ? b.take(BM * d.D * 2) : nullptr;
+  p.lw.wqv = b.take(static_cast<size_t>(d.D) * d.H * dr.QV * 2);
+  p.lw.wo = b.take(static_cast<size_t>(d.H) * d.dv * d.D * 2);
+  p.lw.wqv_t = b.take(static_cast<size_t>(d.D) * d.H * dr.QV * 2);
+  p.lw.wo_t = b.take(static_cast<size_t>(d.H) * d.dv * d.D * 2);
+  p.lw.qv = b.take(BM * d.H * dr.QV * 2);
+  p.hashed = static_cast<int32_t *>(b.take(static_cast<size_t>(dr.BH) * dr.N * 4));
+  p.o = static_cast<float *>(b.take(static_cast<size_t>(dr.BH) * 64 * 4));
+  p.total = b.off + 256;
+  return p;
 }
 
 }  // namespace lsh
@@ -575,6 +603,44 @@ int lsh_unpack_heads(int B, int H, int L, int act_dtype, const void *src, int d_
   if (!src || !dst) return set_error("lsh_unpack_heads: NULL argument");
   if (act_dtype != LSH_DTYPE_F32 && act_dtype != LSH_DTYPE_BF16) return set_error("lsh_unpack_heads: bad act_dtype");
   return unpack_heads_run(B, H, L, act_dtype, src, d_total, col0, d, dst, static_cast<cudaStream_t>(stream));
+}
+
+size_t lsh_predict_workspace_bytes(const LshAttnDims *dims) {
+  if (check_dims(dims, false)) return 0;
+  return carve_predict(*dims, nullptr).total;
+}
+
+int lsh_predict_step(const LshAttnDims *dims, const void *mem, const float *w_q, const float *w_v, const float *w_o, const float *w_k,
+                     const float *rotations, int32_t *buckets, int64_t buckets_stride, int32_t q_start, void *out, void *ws,
+                     size_t ws_bytes, void *stream) {
+  if (int rc = check_dims(dims, false)) return rc;
+  const LshAttnDims &d = *dims;
+  if (!mem || !w_q || !w_v || !w_o || !out || !ws) return set_error("lsh_predict_step: NULL argument");
+  if ((d.separate_k != 0) != (w_k != nullptr)) return set_error("lsh_predict_step: w_k must be given exactly when dims.separate_k is set");
+  if ((rotations != nullptr) != (buckets != nullptr)) return set_error("lsh_predict_step: rotations and buckets go together (LSH) or are both NULL");
+  if (rotations && d.separate_k) return set_error("lsh_predict_step: hashing needs shared-QK");
+  if (d.masked || d.na != 0) return set_error("lsh_predict_step: masked / n_chunks_after are not part of fast inference (EA:2085)");
+  Derived dr = derive(d);
+  if (buckets && buckets_stride < dr.N) return set_error("lsh_predict_step: buckets_stride %lld < n_hashes * memory length %d", (long long)buckets_stride, dr.N);
+  PredictWs p = carve_predict(d, ws);
+  if (ws_bytes < p.total) return set_error("lsh_predict_step: workspace too small (%zu < %zu)", ws_bytes, p.total);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t BM = static_cast<int64_t>(d.B) * d.L, NQV = static_cast<int64_t>(d.H) * dr.QV;
+  int rc;
+  const void *xb = mem;
+  if (d.act_dtype == LSH_DTYPE_F32) {
+    if ((rc = f32_to_bf16_run(static_cast<const float *>(mem), p.lw.xb, BM * d.D, s))) return rc;
+    xb = p.lw.xb;
+  }
+  if ((rc = pack_layer_weights(d, p.lw, w_q, w_v, w_o, w_k, s))) return rc;
+  // EA:2064, 2087-2089: q of the new token, k and v of the attended slots — here: of every memory slot, one GEMM
+  if ((rc = gemm_aw(BM, NQV, d.D, xb, d.D, p.lw.wqv_t, p.lw.wqv, p.lw.qv, NQV, false, p.lw.cublas, s))) return rc;
+  if (rotations) {
+    // EA:2066: the bit-exact hash of the training path over the memory's rows (only the new token's column is consumed)
+    if ((rc = hash_bf16_qv(d, p.lw.qv, rotations, nullptr, p.hashed, dr.N, s))) return rc;
+  }
+  if ((rc = predict_attend_run(d, p.lw.qv, buckets, buckets_stride, rotations ? p.hashed : nullptr, q_start, p.o, s))) return rc;
+  return predict_out_run(d, p.o, w_o, out, s);
 }
 
 /* Debug aid (not in the public header): device buffer receiving per-phase clock stamps of CTA 0. */

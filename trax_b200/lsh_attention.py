@@ -12,9 +12,10 @@ Kept from the reference (names, argument meaning, error behaviour):
     `forward_and_or_backward`, `pure_fn`, `__call__` with the semantics of `trax/layers/base.py:265`,
     `:541`, `:644` and EA:2111-2126, 2246-2561; only `weights`, `state`, `rng` are settable public
     attributes (base.py:675-706).
-Not provided (raise, never silently differ): mode='predict' (EA:1999-2109, out of scope for this
-tier), `use_reference_code=True` (would be a CPU path), `bias=True` (broken in the reference too:
-EA:1921 unpacks exactly three weights).  attention_dropout (the (chunk_len, window) keep matrix of EA:254-262, applied inside
+  * mode='predict' (fast inference, EA:1999-2109, 2174-2244): state `(mem_end, (mem,), (buckets, buckets_idx, rng))`
+    (EA:1833-1841, 1883-1887), forward-only — trax_b200/predict.py.
+Not provided (raise, never silently differ): `use_reference_code=True` (would be a CPU path), `bias=True` (broken in the
+reference too: EA:1921 unpacks exactly three weights).  attention_dropout (the (chunk_len, window) keep matrix of EA:254-262, applied inside
 the attention kernels) and output_dropout (a column scaling of w_o) are supported; their masks are functions of `rng`, not
 jax.random's bits, and can be supplied explicitly.
 
@@ -216,7 +217,7 @@ class LSHSelfAttention:
                use_python_loop=False,
                use_reference_code=False,
               ):
-    del share_qk, predict_mem_len, predict_drop_len
+    del share_qk
     self._n_in = 2 if masked else 1                                 # EA:1750
     self._n_out = 1
     self._n_heads = n_heads
@@ -228,9 +229,14 @@ class LSHSelfAttention:
     # reference's memory use (EA:2297-2321) and do not change results.
     self._n_parallel_heads = n_parallel_heads or None
     self._use_python_loop = use_python_loop
-    if mode == 'predict':
-      raise NotImplementedError(
-          "LSHSelfAttention(mode='predict') (EA:1999-2109, 2174-2244) is outside this build's scope")
+    self._incremental = (mode == 'predict')                         # EA:1762-1766
+    self._predict_hashes = True         # the predict state carries a bucket memory (SelfAttention: it does not)
+    self._predict_mem_len, self._predict_drop_len = predict_mem_len, predict_drop_len
+    if self._incremental:
+      if masked or n_chunks_after:
+        raise NotImplementedError("mode='predict' takes one input and no look-ahead (EA:1999-2001, 2085)")
+      if not (isinstance(predict_mem_len, int) and isinstance(predict_drop_len, int) and 0 < predict_drop_len < predict_mem_len):
+        raise ValueError("mode='predict' needs 0 < predict_drop_len < predict_mem_len")
     if use_reference_code:
       raise NotImplementedError('use_reference_code=True is a CPU loop in the reference; this build has no CPU path')
     if bias:
@@ -341,6 +347,11 @@ class LSHSelfAttention:
       rng_state = rng_state.view(torch.uint32)
     self.weights = tuple(torch.from_numpy(np.ascontiguousarray(np.stack(w))).to(device) for w in (w_q, w_v, w_o))
     self.state = (buckets, rng_state)
+    if self._incremental:                                           # EA:1833-1841, 1883-1887
+      from trax_b200 import predict
+      dtype = getattr(input_signature[0], 'dtype', torch.float32)
+      self.state = predict.init_state(self, batch_size, d_model, dtype if isinstance(dtype, torch.dtype) else torch.float32,
+                                      device, rng_state, self._predict_hashes)
 
   # ---- forward / backward (EA:2111-2126, 2251-2259) ------------------------------------------------
   def forward(self, inputs):
@@ -460,14 +471,20 @@ class LSHSelfAttention:
     return self._forward_and_or_backward(inputs, weights, state, rng, output_grad, compute_output, update_state)
 
   def _forward_and_or_backward(self, inputs, weights, state, rng, output_grad=None,
-                               compute_output=True, update_state=True, _stash=None, _residual=None, _io_dtype=None):
+                               compute_output=True, update_state=True, _stash=None, _residual=None, _io_dtype=None,
+                               _raw=False):
     """Performs batched forward and/or backward passes (EA:2261-2289).
 
     Returns (output, new_state, inputs_grad, weights_grad):
       output is not None iff compute_output; new_state iff update_state; grads iff output_grad given.
     Tensors may live on the GPU (no copies) or on the host (pinned or pageable): host inputs are
     copied to cuda:current, results copied back — the e2e path bench.py times.
+    In predict mode the call goes to trax_b200/predict.py (EA:2336-2350); `_raw` is that module's way back to the
+    training-path kernels for a prefix.
     """
+    if self._incremental and not _raw:
+      from trax_b200 import predict
+      return predict.forward_and_or_backward(self, inputs, weights, state, rng, output_grad, compute_output, update_state)
     have_single_input = not isinstance(inputs, (tuple, list))
     if have_single_input:
       inputs = (inputs,)
@@ -484,7 +501,7 @@ class LSHSelfAttention:
       # kernels, streams and the scratch buffer belong to the tensors' device, whatever the caller's current device is
       with torch.cuda.device(x.device):
         return self._forward_and_or_backward(inputs if not have_single_input else inputs[0], weights, state, rng, output_grad,
-                                             compute_output, update_state, _stash, _residual, _io_dtype)
+                                             compute_output, update_state, _stash, _residual, _io_dtype, _raw)
     lib = _lib.load()
     host_io = not x.is_cuda
     dev = torch.device('cuda', torch.cuda.current_device()) if host_io else x.device

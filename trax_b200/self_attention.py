@@ -14,8 +14,8 @@ scale and without the self mask, and the key-side cotangent goes to `dw_k` inste
 
 Interface kept: the constructor keywords (EA:939-953), weights `(w_q, w_v, w_o)` for `share_qk`, `(w_q, w_k, w_v, w_o)`
 otherwise (EA:1112-1128), state `()` (EA:1130-1131), `forward`, `backward`, `forward_and_or_backward` →
-`(output, new_state, inputs_grad, weights_grad)`.  `chunk_len=None` (one dense window over the whole sequence) and
-`mode='predict'` are not built and raise.
+`(output, new_state, inputs_grad, weights_grad)`.  `mode='predict'` (EA:1200-1268; state `(mem_end, (mem,), ())`) runs
+through trax_b200/predict.py.  `chunk_len=None` (one dense window over the whole sequence) is not built and raises.
 """
 import torch
 
@@ -29,17 +29,17 @@ class SelfAttention(LSHSelfAttention):
                n_chunks_before=0, n_chunks_after=0, bias=False, mode='train', predict_mem_len=None, predict_drop_len=None,
                attention_dropout=0.0, output_dropout=0.0, n_parallel_heads=None, use_python_loop=False,
                use_reference_code=False):
-    del predict_mem_len, predict_drop_len
     if chunk_len is None:
       raise NotImplementedError('SelfAttention(chunk_len=None) is dense attention over the whole sequence; the kernels are '
                                 'chunked (chunk_len 32 / 64 / 128 / 256)')
     super().__init__(n_heads=n_heads, d_qk=d_qk, d_v=d_v, causal=causal, masked=masked, chunk_len=chunk_len,
                      n_chunks_before=n_chunks_before, n_chunks_after=n_chunks_after, n_hashes=1, n_buckets=2, mode=mode,
-                     attention_dropout=attention_dropout, output_dropout=output_dropout, bias=bias,
+                     predict_mem_len=predict_mem_len, predict_drop_len=predict_drop_len, attention_dropout=attention_dropout, output_dropout=output_dropout, bias=bias,
                      n_parallel_heads=n_parallel_heads, use_python_loop=use_python_loop,
                      use_reference_code=use_reference_code)
     self._share_qk = bool(share_qk)
     self._separate_k = not share_qk
+    self._predict_hashes = False
 
   def init_weights_and_state(self, input_signature, device=None):
     super().init_weights_and_state(input_signature, device=device)   # same (w_q, w_v, w_o) shapes and init (EA:1061-1066)
@@ -52,15 +52,21 @@ class SelfAttention(LSHSelfAttention):
       w_k = np.stack([self._kernel_initializer((d_model, self._d_qk), np.random.Generator(np.random.Philox(
           key=int(k[0]) << 32 | int(k[1])))) for k in keys])
       self.weights = (w_q, torch.from_numpy(np.ascontiguousarray(w_k)).to(w_q.device), w_v, w_o)
-    self.state = ()                                                  # EA:1130-1131
+    if not self._incremental:
+      self.state = ()                                                # EA:1130-1131 (predict mode: (mem_end, (mem,), ()), EA:1093-1101)
 
   def forward(self, inputs):
-    output, _, _, _ = self.forward_and_or_backward(inputs, self.weights, self.state, self.rng, compute_output=True,
-                                                   update_state=True)
+    output, new_state, _, _ = self.forward_and_or_backward(inputs, self.weights, self.state, self.rng, compute_output=True,
+                                                           update_state=True)
+    if self._incremental:
+      self.state = new_state
     return output
 
   def _forward_and_or_backward(self, inputs, weights, state, rng, output_grad=None, compute_output=True, update_state=True,
-                               _stash=None, _residual=None, _io_dtype=None):
+                               _stash=None, _residual=None, _io_dtype=None, _raw=False):
+    if self._incremental and not _raw:
+      from trax_b200 import predict
+      return predict.forward_and_or_backward(self, inputs, weights, state, rng, output_grad, compute_output, update_state)
     x = inputs[0] if isinstance(inputs, (tuple, list)) else inputs
     if not torch.cuda.is_available():
       from trax_b200 import _lib
@@ -70,5 +76,5 @@ class SelfAttention(LSHSelfAttention):
     buckets = torch.zeros((int(x.shape[0]) * self._n_heads, int(x.shape[1])), dtype=torch.int32, device=dev)
     out, _, inputs_grad, weights_grad = super()._forward_and_or_backward(
         inputs, weights, (buckets, None), rng, output_grad=output_grad, compute_output=compute_output, update_state=False,
-        _stash=_stash, _residual=_residual, _io_dtype=_io_dtype)
+        _stash=_stash, _residual=_residual, _io_dtype=_io_dtype, _raw=True)
     return out, (state if update_state else None), inputs_grad, weights_grad
