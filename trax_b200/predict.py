@@ -190,6 +190,8 @@ def _run(layer, x_d, weights, mem_end, mem, inner, rng, step=None, train=None):
         att_in = torch.cat([att_in, att_in.new_zeros((att_in.shape[0], pad, att_in.shape[2]))], dim=1)
       out, (buckets_update, _), _, _ = train(att_in, weights, (None, hash_rng))                      # EA:2012-2018
       out = out[:, :seqlen].contiguous()
+      # (a training-path bucket row may be longer than n_hashes * rows: `max_length_for_buckets`, EA:1880)
+      buckets_update = buckets_update[:, :layer._n_hashes * int(att_in.shape[1])].contiguous()
       new_buckets = store_prefix_buckets(buckets, buckets_update, seqlen, layer._n_hashes, m)
       new_inner = (new_buckets, buckets_idx + seqlen, hash_rng)                                       # EA:2030
     elif seqlen > layer._chunk_len:                                # EA:1250-1261: whole chunks of the prefix itself
