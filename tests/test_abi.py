@@ -124,7 +124,7 @@ def test_jax_ffi_shim_translation_unit_compiles_and_is_guarded(tmp_path):
   text = open(src).read()
   assert '__has_include("xla/ffi/api/ffi.h")' in text and 'XLA_FFI_DEFINE_HANDLER_SYMBOL' in text
   from trax_b200 import _lib
-  for fn in ('lsh_layer_fwd', 'lsh_layer_bwd'):
+  for fn in ('lsh_layer_fwd', 'lsh_layer_bwd', 'lsh_predict_step'):
     m = re.search(fn + r'\((.*?)\)\);', text, re.S)
     assert m, fn
     depth, n_args = 0, 1

@@ -158,3 +158,52 @@ def test_predict_mode_sweep_against_the_live_reference():
                      capture_output=True, text=True)
   assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
   assert r.stdout.count('\nok') + r.stdout.startswith('ok') == 16
+
+
+PREDICT_FIXTURE = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_predict.npz')
+
+
+@pytest.mark.parametrize('name', ['lsh', 'self'])
+def test_predict_oracle_matches_the_committed_reference_outputs(name):
+  """tests/golden/reference_predict.npz holds what the reference's own `mode='predict'` code returned (a prefix, then single
+  tokens until the memory rolled twice; tests/golden/make_predict_golden.py): the oracle must reproduce the outputs (stored
+  as float32) and the final state exactly — this runs wherever the fixture travels, /root/reference or not."""
+  from oracle import predict_oracle as P
+  from oracle import self_attention_oracle as SA
+  from tests.golden import make_predict_golden as G
+  g, c = np.load(PREDICT_FIXTURE), G.CASES[name]
+  w, xs = G.inputs(name)
+  pcfg = P.PredictConfig(predict_mem_len=G.M, predict_drop_len=G.DROP)
+  outs, t0 = [], 0
+  if name == 'lsh':
+    cfg = O.LSHConfig(**c['kw'])
+    state = P.init_state(cfg, pcfg, G.B, G.D)
+  else:
+    cfg = SA.SelfAttentionConfig(**c['kw'])
+    state = (0, np.zeros((G.B, G.M, G.D)))
+  for n in G.calls(c):
+    x = xs[:, t0:t0 + n]
+    t0 += n
+    if name == 'lsh':
+      out, state = P.predict_forward(cfg, pcfg, x, w, state, lambda u, n_rows: g['lsh/rot'][u])
+    else:
+      out, state = P.self_attention_predict_forward(cfg, pcfg, x, w, state)
+    outs.append(out)
+  np.testing.assert_allclose(np.concatenate(outs, axis=1), g[name + '/out'], rtol=1e-5, atol=1e-6)
+  assert state[0] == int(g[name + '/mem_end'])
+  np.testing.assert_array_equal(state[1].astype(np.float32), g[name + '/mem'])
+  if name == 'lsh':
+    np.testing.assert_array_equal(state[2][0], g['lsh/buckets'])
+    np.testing.assert_array_equal(state[2][1], g['lsh/buckets_idx'])
+
+
+@pytest.mark.skipif(not ref_live.available(), reason='the reference checkout exists only in the build container')
+def test_predict_fixture_regenerates_from_the_live_reference(tmp_path):
+  repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  out = str(tmp_path / 'regen.npz')
+  subprocess.run([sys.executable, os.path.join(repo, 'tests', 'golden', 'make_predict_golden.py'), '--out', out], cwd=repo,
+                 timeout=900, check=True, capture_output=True)
+  a, b = np.load(PREDICT_FIXTURE), np.load(out)
+  assert sorted(a.files) == sorted(b.files)
+  for k in a.files:
+    np.testing.assert_array_equal(a[k], b[k], err_msg=k)

@@ -189,3 +189,36 @@ def test_lsh_predict_layer_prefix_then_tokens(prefix_len, dtype):
     assert out.dtype == dtype and tuple(out.shape) == (B, n, D)
     util.assert_close_layer(out.float().cpu().numpy(), want, 'out after %d tokens' % t0)
   assert int(layer.state[0]) < t0                                    # the memory did roll
+
+
+@pytest.mark.parametrize('name', ['lsh', 'self'])
+def test_predict_layers_against_the_reference_own_outputs(name):
+  """tests/golden/reference_predict.npz: outputs of the REFERENCE's own predict-mode code (make_predict_golden.py) for a
+  prefix followed by single tokens through two rolls of the memory.  The LSH case is sized so that every earlier slot is
+  attended (n_hashes * chunk_len * 2 == predict_mem_len): its output does not depend on the bucket ids, so the device's
+  output is compared with the reference's directly; the bucket memory (the device hashes bf16 projections, the reference
+  fp64 ones) may differ at near-ties of the argmax, bounded here at 5 % like tests/test_gpu_golden.py does for the layer."""
+  import os
+  import trax_b200
+  from tests.golden import make_predict_golden as G
+  g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_predict.npz'))
+  c = G.CASES[name]
+  w, xs = G.inputs(name)
+  cls = trax_b200.LSHSelfAttention if name == 'lsh' else trax_b200.SelfAttention
+  layer = cls(mode='predict', predict_mem_len=G.M, predict_drop_len=G.DROP, **c['kw'])
+  layer.init(trax_b200.ShapeDtype((G.B, 1, G.D)))
+  layer.weights = tuple(torch.from_numpy(a.astype(np.float32)).cuda() for a in w)
+  if name == 'lsh':
+    layer._rotations_override = torch.from_numpy(g['lsh/rot'])
+  outs, t0 = [], 0
+  for n in G.calls(c):
+    outs.append(layer.forward(torch.from_numpy(xs[:, t0:t0 + n].astype(np.float32)).cuda()))
+    t0 += n
+  out = torch.cat(outs, dim=1).cpu().numpy()
+  util.assert_close_layer(out, g[name + '/out'], 'out')
+  assert int(layer.state[0]) == int(g[name + '/mem_end'])
+  np.testing.assert_array_equal(layer.state[1][0].cpu().numpy(), g[name + '/mem'])
+  if name == 'lsh':
+    got_b = layer.state[2][0].cpu().numpy()
+    assert (got_b != g['lsh/buckets']).mean() <= 0.05
+    np.testing.assert_array_equal(layer.state[2][1].cpu().numpy(), g['lsh/buckets_idx'])

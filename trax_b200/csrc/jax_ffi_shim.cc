@@ -116,7 +116,54 @@ ffi::Error LayerBwdImpl(cudaStream_t stream, ffi::ScratchAllocator scratch, ffi:
                               /*ev_dwqv_ready=*/nullptr, stream));
 }
 
+// One fast-inference step (mode='predict', EA:2032-2109): `mem` is the input memory with the new token already stored at
+// q_start, `buckets_in` the bucket memory after the host-side roll (EA:2036-2053); -> (output (B, 1, D), bucket memory with
+// the new token's ids in column q_start).  rotations / buckets_in empty: SelfAttention (EA:1200-1268).
+ffi::Error PredictStepImpl(cudaStream_t stream, ffi::ScratchAllocator scratch, ffi::AnyBuffer mem, ffi::Buffer<ffi::F32> w_q,
+                           ffi::Buffer<ffi::F32> w_v, ffi::Buffer<ffi::F32> w_o, ffi::Buffer<ffi::F32> w_k,
+                           ffi::Buffer<ffi::F32> rotations, ffi::Buffer<ffi::S32> buckets_in,
+                           ffi::Result<ffi::Buffer<ffi::S32>> buckets, ffi::Result<ffi::AnyBuffer> out, int32_t chunk_len,
+                           int32_t n_chunks_before, int32_t n_hashes, ffi::Span<const int32_t> factors, bool causal,
+                           bool separate_k, int32_t q_start) {
+  auto dims = MakeDims(mem, w_q, w_v, chunk_len, n_chunks_before, /*n_chunks_after=*/0, n_hashes, factors, causal, /*masked=*/false,
+                       separate_k);
+  if (dims.has_error()) return dims.error();
+  LshAttnDims d = dims.value();
+  const size_t ws_bytes = lsh_predict_workspace_bytes(&d);
+  auto ws = scratch.Allocate(ws_bytes);
+  if (!ws.has_value()) return ffi::Error(ffi::ErrorCode::kResourceExhausted, "lsh_attn: workspace allocation failed");
+  const bool hashed = rotations.element_count() != 0;
+  if (hashed && cudaMemcpyAsync(buckets->typed_data(), buckets_in.typed_data(), buckets_in.size_bytes(), cudaMemcpyDeviceToDevice,
+                                stream) != cudaSuccess)
+    return ffi::Error(ffi::ErrorCode::kInternal, "lsh_attn: bucket copy failed");
+  return Status(lsh_predict_step(&d, mem.untyped_data(), w_q.typed_data(), w_v.typed_data(), w_o.typed_data(), OrNull(w_k),
+                                 OrNull(rotations), hashed ? buckets->typed_data() : nullptr,
+                                 hashed ? buckets->dimensions()[1] : 0, q_start, out->untyped_data(), *ws, ws_bytes, stream));
+}
+
 }  // namespace
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(
+    LshPredictStep, PredictStepImpl,
+    ffi::Ffi::Bind()
+        .Ctx<ffi::PlatformStream<cudaStream_t>>()
+        .Ctx<ffi::ScratchAllocator>()
+        .Arg<ffi::AnyBuffer>()            // mem (B, M, D)
+        .Arg<ffi::Buffer<ffi::F32>>()     // w_q
+        .Arg<ffi::Buffer<ffi::F32>>()     // w_v
+        .Arg<ffi::Buffer<ffi::F32>>()     // w_o
+        .Arg<ffi::Buffer<ffi::F32>>()     // w_k           (empty unless separate_k)
+        .Arg<ffi::Buffer<ffi::F32>>()     // rotations     (empty: no hashing, SelfAttention)
+        .Arg<ffi::Buffer<ffi::S32>>()     // buckets_in    (bucket memory; empty likewise)
+        .Ret<ffi::Buffer<ffi::S32>>()     // buckets
+        .Ret<ffi::AnyBuffer>()            // out (B, 1, D)
+        .Attr<int32_t>("chunk_len")
+        .Attr<int32_t>("n_chunks_before")
+        .Attr<int32_t>("n_hashes")
+        .Attr<ffi::Span<const int32_t>>("factors")
+        .Attr<bool>("causal")
+        .Attr<bool>("separate_k")
+        .Attr<int32_t>("q_start"));
 
 XLA_FFI_DEFINE_HANDLER_SYMBOL(
     LshLayerFwd, LayerFwdImpl,

@@ -43,6 +43,7 @@ def build_shim(out=None):
 def register(lib):
   jax.ffi.register_ffi_target('lsh_layer_fwd', jax.ffi.pycapsule(lib.LshLayerFwd), platform='CUDA')
   jax.ffi.register_ffi_target('lsh_layer_bwd', jax.ffi.pycapsule(lib.LshLayerBwd), platform='CUDA')
+  jax.ffi.register_ffi_target('lsh_predict_step', jax.ffi.pycapsule(lib.LshPredictStep), platform='CUDA')
 
 
 def _bucket_factors(n_buckets, seqlen, chunk_len):
