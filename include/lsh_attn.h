@@ -44,7 +44,8 @@ extern "C" {
 
 /* 4: + lsh_layer_fwd_res / lsh_layer_bwd_res (residual epilogue), lsh_pack_heads / lsh_unpack_heads, lsh_layernorm_fwd_bf16,
  *    LshAttnDims.x_bf16 (was reserved[0]; 0 keeps the v3 behaviour).  v3 entry points are unchanged. */
-/* 5: + lsh_predict_step / lsh_predict_workspace_bytes (fast inference, mode='predict').  v4 entry points are unchanged. */
+/* 5: + lsh_predict_step / lsh_predict_attend (+ their *_workspace_bytes): fast inference, mode='predict'.  v4 entry points
+ *    are unchanged. */
 #define LSH_ATTN_ABI_VERSION 5
 
 enum { LSH_DTYPE_F32 = 0, LSH_DTYPE_BF16 = 1 };
@@ -239,6 +240,14 @@ size_t lsh_predict_workspace_bytes(const LshAttnDims *dims);
 int lsh_predict_step(const LshAttnDims *dims, const void *mem, const float *w_q, const float *w_v, const float *w_o,
                      const float *w_k, const float *rotations, int32_t *buckets, int64_t buckets_stride, int32_t q_start,
                      void *out, void *ws, size_t ws_bytes, void *stream);
+
+/* The same step on caller-supplied projections — `PureLSHSelfAttention._incremental_forward_unbatched` (EA:2858-2932), whose
+ * memory holds qk and v themselves: qv (B, M, H, dq+dv) bf16 is that memory in the kernels' row layout (lsh_pack_heads) with
+ * the new token stored at q_start; o (B*H, dv) f32 receives the attention output of the new token (there is no output
+ * projection, EA:2928).  buckets / rotations / q_start as above. */
+size_t lsh_predict_attend_workspace_bytes(const LshAttnDims *dims);
+int lsh_predict_attend(const LshAttnDims *dims, const void *qv_bf16, const float *rotations, int32_t *buckets,
+                       int64_t buckets_stride, int32_t q_start, float *o, void *ws, size_t ws_bytes, void *stream);
 
 /* ---- helpers ---------------------------------------------------------------------------------- */
 

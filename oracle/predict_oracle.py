@@ -166,6 +166,30 @@ def predict_forward(cfg: O.LSHConfig, pcfg: PredictConfig, x, weights, state, ro
   return out, (new_mem_end, new_mem, (nb, ni))
 
 
+# ---- PureLSHSelfAttention (EA:2823-2932, 2955-3033, 3122-3146) ---------------------------------------------------------------
+def pure_predict_forward(cfg: O.LSHConfig, pcfg: PredictConfig, qk, v, state, rotations_fn, new_ids_fn=None):
+  """One call of the weight-less core in predict mode: inputs qk (B*H, seqlen, d_qk), v (B*H, seqlen, d_v); state
+  (mem_end, (qk_mem, v_mem), (buckets, buckets_idx)).  EA:2823-2932 is EA:1999-2109 with the projections taken out — the
+  memory holds qk and v themselves — so this is `incremental_forward_unit` on x = [qk | v] with selector weights
+  (w_q = [I; 0], w_v = [0; I], w_o = I), one "head" per leading row.  Returns (output (B*H, seqlen, d_v), new_state)."""
+  mem_end, (qk_mem, v_mem), (buckets, buckets_idx) = state
+  dq, dv = qk.shape[-1], v.shape[-1]
+  w_q = np.concatenate([np.eye(dq), np.zeros((dv, dq))], axis=0)
+  w_v = np.concatenate([np.zeros((dq, dv)), np.eye(dv)], axis=0)
+  w_o = np.eye(dv)
+  x = np.concatenate([np.asarray(qk, np.float64), np.asarray(v, np.float64)], axis=-1)
+  mem = np.concatenate([qk_mem, v_mem], axis=-1)
+  seqlen = x.shape[1]
+  inputs, q_start, new_mem, new_mem_end = use_predict_mem(pcfg, x, int(mem_end), mem)
+  out = np.zeros((x.shape[0], seqlen, dv))
+  nb, ni = np.array(buckets, copy=True), np.array(buckets_idx, copy=True)
+  for u in range(x.shape[0]):
+    out[u], nb[u], ni[u] = incremental_forward_unit(cfg, pcfg, inputs[u], q_start, seqlen, w_q, w_v, w_o, buckets[u],
+                                                    int(buckets_idx[u]), lambda n, _u=u: rotations_fn(_u, n),
+                                                    None if new_ids_fn is None else new_ids_fn(u))
+  return out, (new_mem_end, (new_mem[..., :dq], new_mem[..., dq:]), (nb, ni))
+
+
 # ---- SelfAttention (EA:1200-1268) -------------------------------------------------------------------------------------
 def self_attention_incremental_unit(cfg: SA.SelfAttentionConfig, x, q_start: int, q_len: int, weights):
   """EA:1200-1268 for one (example, head), no input mask.  Returns out (q_len, D)."""

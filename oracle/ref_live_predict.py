@@ -52,6 +52,11 @@ def draw_case(rng, i):
   M = C * int(rng.choice([2, 4, 6]))
   drop = int(rng.choice([d for d in (1, 2, C, 2 * C) if d < M]))
   prefix = str(rng.choice(['none', 'append', 'short', 'full', 'long']))
+  if i % 4 == 2:
+    kind = rng.choice(['int', 'list', 'none'])
+    d_head = int(rng.choice([4, 6]))                                 # the batched driver sizes its output by d_qk (EA:3128, 3239)
+    return dict(kind='pure', B=int(rng.choice([1, 2])), H=int(rng.choice([1, 2])), D=0, dq=d_head, dv=d_head, C=C, nb=int(rng.choice([0, 1])), nh=int(rng.choice([1, 2])),
+                n_buckets={'int': int(rng.choice([2, 4])), 'list': [2, 2], 'none': None}[str(kind)], M=M, drop=drop, prefix=prefix)
   if i % 4 == 3:
     return dict(kind='self', B=int(rng.choice([1, 2])), H=int(rng.choice([1, 2])), D=int(rng.choice([8, 12])),
                 dq=int(rng.choice([4, 6])), dv=int(rng.choice([4, 5])), C=C, nb=int(rng.choice([0, 1])), M=M, drop=drop,
@@ -87,9 +92,11 @@ def run_case(R, c, rng):
   B, H, D, M, drop = c['B'], c['H'], c['D'], c['M'], c['drop']
   pcfg = P.PredictConfig(predict_mem_len=M, predict_drop_len=drop)
   calls = schedule(c, rng)
+  seed = int(rng.integers(1 << 30))
+  if c['kind'] == 'pure':
+    return run_pure_case(R, c, rng, calls, pcfg, seed)
   xs = rng.standard_normal((B, sum(calls), D))
   sig = R.shapes.ShapeDtype((B, 1, D), np.float64)
-  seed = int(rng.integers(1 << 30))
   if c['kind'] == 'lsh':
     kw = dict(n_heads=H, d_qk=c['dq'], d_v=c['dv'], causal=True, chunk_len=c['C'], n_chunks_before=c['nb'],
               n_hashes=c['nh'], n_buckets=c['n_buckets'])
@@ -133,6 +140,39 @@ def run_case(R, c, rng):
     err = np.abs(out - y)
     worst = max(worst, float(np.nanmax(err)) if np.isfinite(y).any() else 0.0)
     n_state_diff += int((np.isnan(out) != np.isnan(y)).sum())
+  return worst, n_state_diff, len(calls), calls[0]
+
+
+def run_pure_case(R, c, rng, calls, pcfg, seed):
+  """`PureLSHSelfAttention(mode='predict')` has no `use_reference_code` loop (EA:2946-2948): it runs through its batched
+  driver in Python-loop mode (EA:3052-3265, `use_python_loop=True, n_parallel_heads=1`)."""
+  BH, M = c['B'] * c['H'], c['M']
+  kw = dict(n_heads=c['H'], d_qk=c['dq'], d_v=c['dv'], causal=True, chunk_len=c['C'], n_chunks_before=c['nb'],
+            n_hashes=c['nh'], n_buckets=c['n_buckets'])
+  layer = R.EA.PureLSHSelfAttention(mode='predict', predict_mem_len=M, predict_drop_len=c['drop'], use_python_loop=True,
+                                    n_parallel_heads=1, **kw)
+  layer.init((R.shapes.ShapeDtype((BH, 1, c['dq']), np.float64), R.shapes.ShapeDtype((BH, 1, c['dv']), np.float64)))
+  cfg = O.LSHConfig(**kw)
+  qks, vs = rng.standard_normal((BH, sum(calls), c['dq'])), rng.standard_normal((BH, sum(calls), c['dv']))
+  state = (0, (np.zeros((BH, M, c['dq'])), np.zeros((BH, M, c['dv']))),
+           (np.zeros((BH, c['nh'] * M), np.int32), np.zeros((BH,), np.int32)))
+  worst, n_state_diff, t0 = 0.0, 0, 0
+  for n in calls:
+    qk, v = qks[:, t0:t0 + n], vs[:, t0:t0 + n]
+    t0 += n
+    np.random.seed(seed)
+    y = np.asarray(layer((qk, v)))
+    ref_state = layer.state
+
+    def rotations_fn(unit, n_rows):
+      np.random.seed(seed)
+      shape = O.rotations_shape(cfg, n_rows)
+      return [np.random.normal(size=shape).astype(np.float64).astype(np.float32) for _ in range(unit + 1)][unit]
+    out, state = P.pure_predict_forward(cfg, pcfg, qk, v, state, rotations_fn)
+    worst = max(worst, float(np.abs(out - y).max()))
+    n_state_diff += int(int(ref_state[0]) != int(state[0]))
+    n_state_diff += int((np.asarray(ref_state[1][0]) != state[1][0]).sum()) + int((np.asarray(ref_state[1][1]) != state[1][1]).sum())
+    n_state_diff += int((np.asarray(ref_state[2][0]) != state[2][0]).sum()) + int((np.asarray(ref_state[2][1]) != state[2][1]).sum())
   return worst, n_state_diff, len(calls), calls[0]
 
 

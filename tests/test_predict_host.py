@@ -189,3 +189,61 @@ def test_predict_mode_rejections():
                                                             torch.zeros((2,), dtype=torch.int32), None), None)
   with pytest.raises(NotImplementedError):                           # EA:2002-2003
     predict.forward_and_or_backward(layer, torch.zeros((1, 1, 8)), (), (), None, output_grad=torch.zeros((1, 1, 8)))
+
+
+def _selector_weights(dq, dv):
+  """x = [qk | v]: w_q picks qk, w_v picks v, w_o is the identity — the oracle's unit then is the weight-less core."""
+  return (np.concatenate([np.eye(dq), np.zeros((dv, dq))]), np.concatenate([np.zeros((dq, dv)), np.eye(dv)]), np.eye(dv))
+
+
+@pytest.mark.parametrize('prefix', ['none', 'append', 'short', 'full', 'long'])
+def test_pure_core_predict_host_logic_matches_the_oracle(prefix):
+  """`predict._run_pure` (PureLSHSelfAttention, EA:2823-3033) with `lsh_predict_attend` and the training-path core replaced
+  by the oracle: outputs and every state leaf vs `oracle.predict_oracle.pure_predict_forward` (pinned against the live
+  reference's batched driver)."""
+  import trax_b200
+  from trax_b200 import predict
+  rng = np.random.default_rng(3 + len(prefix))
+  B, H, C, nh, M, drop, d = 2, 2, 4, 2, 16, 4, 6
+  BH = B * H
+  kw = dict(n_heads=H, d_qk=d, d_v=d, causal=True, chunk_len=C, n_chunks_before=1, n_hashes=nh, n_buckets=4)
+  cfg, pcfg = O.LSHConfig(**kw), P.PredictConfig(predict_mem_len=M, predict_drop_len=drop)
+  cfg1 = cfg
+  layer = trax_b200.PureLSHSelfAttention(mode='predict', predict_mem_len=M, predict_drop_len=drop, **kw)
+  rot = rng.standard_normal((BH,) + O.rotations_shape(cfg, 2)).astype(np.float32)
+  layer._rotations_override = torch.from_numpy(rot)
+  w_q, w_v, w_o = _selector_weights(d, d)
+
+  def fake_step(layer_, qk_mem, v_mem, q_start, buckets, rotations):
+    out = np.zeros((BH, 1, d))
+    x = np.concatenate([qk_mem.numpy(), v_mem.numpy()], axis=-1)
+    for u in range(BH):
+      out[u], nb, _ = P.incremental_forward_unit(cfg, pcfg, x[u], q_start, 1, w_q, w_v, w_o, buckets[u].numpy(), q_start,
+                                                 lambda n, _u=u: rotations[_u].numpy())
+      buckets[u] = torch.from_numpy(nb)
+    return torch.from_numpy(out)
+
+  def fake_train(inputs, state):
+    x = np.concatenate([inputs[0].numpy(), inputs[1].numpy()], axis=-1)
+    res = [O.forward_unit(cfg1, x[u], w_q, w_v, w_o, rotations=rot[u]) for u in range(BH)]
+    return (torch.from_numpy(np.stack([r.out for r in res])),
+            (torch.from_numpy(np.stack([r.buckets for r in res])), state[1]), None)
+
+  calls = _schedule(prefix, M, drop, C, rng)
+  qks, vs = rng.standard_normal((BH, sum(calls), d)), rng.standard_normal((BH, sum(calls), d))
+  ostate = (0, (np.zeros((BH, M, d)), np.zeros((BH, M, d))), (np.zeros((BH, nh * M), np.int32), np.zeros((BH,), np.int32)))
+  mem_end, mems = 0, (torch.zeros((BH, M, d), dtype=torch.float64), torch.zeros((BH, M, d), dtype=torch.float64))
+  inner = (torch.zeros((BH, nh * M), dtype=torch.int32), torch.zeros((BH,), dtype=torch.int32), None)
+  t0 = 0
+  for n in calls:
+    qk, v = qks[:, t0:t0 + n], vs[:, t0:t0 + n]
+    t0 += n
+    want, ostate = P.pure_predict_forward(cfg, pcfg, qk, v, ostate, lambda u, n_rows: rot[u])
+    out, (mem_end, mems, inner) = predict._run_pure(layer, torch.from_numpy(qk), torch.from_numpy(v), mem_end, mems, inner, None,
+                                                    step=fake_step, train=fake_train)
+    np.testing.assert_allclose(out.numpy(), want, rtol=1e-12, atol=1e-12)
+    assert mem_end == ostate[0]
+    np.testing.assert_array_equal(mems[0].numpy(), ostate[1][0])
+    np.testing.assert_array_equal(mems[1].numpy(), ostate[1][1])
+    np.testing.assert_array_equal(inner[0].numpy(), ostate[2][0])
+    np.testing.assert_array_equal(inner[1].numpy(), ostate[2][1])

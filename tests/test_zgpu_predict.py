@@ -222,3 +222,131 @@ def test_predict_layers_against_the_reference_own_outputs(name):
     got_b = layer.state[2][0].cpu().numpy()
     assert (got_b != g['lsh/buckets']).mean() <= 0.05
     np.testing.assert_array_equal(layer.state[2][1].cpu().numpy(), g['lsh/buckets_idx'])
+
+
+# ---- the weight-less core and its wrapper (EA:2823-3033, 3493-3620) ----------------------------------------------------
+def _selector_weights():
+  return util.core_identity_weights()                                # x = [qk | v]: w_q / w_v pick the halves, w_o = I
+
+
+@pytest.mark.parametrize('M,C,nb,nh,n_buckets,q_start,dtype', [
+    (512, 64, 0, 2, 8, 0, torch.float32),
+    (512, 64, 0, 2, 8, 300, torch.float32),
+    (256, 128, 1, 1, [4, 2], 255, torch.bfloat16),
+])
+def test_pure_core_predict_step_matches_oracle(M, C, nb, nh, n_buckets, q_start, dtype):
+  """`lsh_predict_attend` (the step of `PureLSHSelfAttention`, EA:2858-2932): bucket ids bit-exact vs the oracle's hash of
+  the (bf16-rounded) qk row, bucket memory, output."""
+  import trax_b200
+  from trax_b200 import predict
+  rng = np.random.default_rng(31 + q_start)
+  B, H = 2, 2
+  BH = B * H
+  kw = dict(n_heads=H, d_qk=64, d_v=64, causal=True, chunk_len=C, n_chunks_before=nb, n_hashes=nh, n_buckets=n_buckets)
+  cfg, pcfg = O.LSHConfig(**kw), P.PredictConfig(predict_mem_len=M, predict_drop_len=C)
+  layer = trax_b200.PureLSHSelfAttention(mode='predict', predict_mem_len=M, predict_drop_len=C, **kw)
+  qk_mem, v_mem = util.bf16_round(rng.standard_normal((BH, M, 64))), util.bf16_round(rng.standard_normal((BH, M, 64)))
+  qk_mem[:, q_start + 1:] = 0
+  v_mem[:, q_start + 1:] = 0
+  nbk = int(np.prod(O.bucket_factors(n_buckets, 2, C)))
+  buckets = util.random_valid_buckets(rng, BH, nh, M, nbk).reshape(BH, nh, M)
+  buckets[:, :, q_start:] = 0
+  buckets = buckets.reshape(BH, nh * M)
+  rot = rng.standard_normal((BH,) + O.rotations_shape(cfg, 2)).astype(np.float32)
+  buckets_d = torch.from_numpy(buckets.copy()).cuda()
+  out_d = predict._pure_step(layer, torch.from_numpy(qk_mem).cuda().to(dtype), torch.from_numpy(v_mem).cuda().to(dtype), q_start,
+                             buckets_d, torch.from_numpy(rot).cuda())
+  got_b = buckets_d.cpu().numpy()
+  new_ids = got_b.reshape(BH, nh, M)[:, :, q_start]
+  w_q, w_v, w_o = _selector_weights()
+  want = np.zeros((BH, 1, 64))
+  for u in range(BH):
+    q_row = qk_mem[u, q_start].astype(np.float32)
+    want_ids = O.hash_vectors(cfg, np.stack([q_row, q_row]), rot[u]).reshape(nh, 2)[:, 0]
+    np.testing.assert_array_equal(new_ids[u], want_ids, err_msg='unit %d' % u)
+    x = np.concatenate([qk_mem[u], v_mem[u]], axis=-1)
+    want[u], nb_u, _ = P.incremental_forward_unit(cfg, pcfg, x, q_start, 1, w_q, w_v, w_o, buckets[u], q_start, None,
+                                                  new_ids=new_ids[u])
+    np.testing.assert_array_equal(nb_u, got_b[u])
+  assert out_d.dtype == dtype and tuple(out_d.shape) == (BH, 1, 64)
+  util.assert_close(out_d.float().cpu().numpy(), want, 'out')
+
+
+def test_pure_core_predict_layer_prefix_then_tokens():
+  """`PureLSHSelfAttention(mode='predict')` through `pure_fn`: a prefix that needs padding, then single tokens through two
+  rolls; output and state leaves vs the oracle on the device's bucket ids."""
+  import trax_b200
+  rng = np.random.default_rng(37)
+  B, H, C, nh, M, drop = 2, 2, 64, 2, 256, 64
+  BH = B * H
+  kw = dict(n_heads=H, d_qk=64, d_v=64, causal=True, chunk_len=C, n_chunks_before=0, n_hashes=nh, n_buckets=8)
+  cfg, pcfg = O.LSHConfig(**kw), P.PredictConfig(predict_mem_len=M, predict_drop_len=drop)
+  layer = trax_b200.PureLSHSelfAttention(mode='predict', predict_mem_len=M, predict_drop_len=drop, **kw)
+  _, state = layer.init((trax_b200.ShapeDtype((BH, 1, 64)), trax_b200.ShapeDtype((BH, 1, 64))))
+  rot = rng.standard_normal((BH,) + O.rotations_shape(cfg, 2)).astype(np.float32)
+  layer._rotations_override = torch.from_numpy(rot)
+  prefix_len = 100
+  calls = [prefix_len] + [1] * (M - prefix_len + 2 * drop + 3)
+  qks, vs = util.bf16_round(rng.standard_normal((BH, sum(calls), 64))), util.bf16_round(rng.standard_normal((BH, sum(calls), 64)))
+  ostate = (0, (np.zeros((BH, M, 64)), np.zeros((BH, M, 64))), (np.zeros((BH, nh * M), np.int32), np.zeros((BH,), np.int32)))
+  t0 = 0
+  for n in calls:
+    qk, v = qks[:, t0:t0 + n], vs[:, t0:t0 + n]
+    t0 += n
+    out, state = layer.pure_fn((torch.from_numpy(qk).cuda(), torch.from_numpy(v).cuda()), (), state, None)
+    mem_end, (qk_mem, v_mem), (buckets, buckets_idx, _) = state
+    got_b = buckets.cpu().numpy().reshape(BH, nh, M)
+    if n > 1:
+      padded = -(-n // C) * C
+
+      def new_ids_fn(u):
+        ids = np.zeros((nh, padded), np.int32)
+        ids[:, :n] = got_b[u, :, :n]
+        ids[:, n:] = (np.arange(nh) * 8)[:, None]                    # zero pad rows hash to bucket 0 of their round
+        return ids.reshape(-1)
+    else:
+      def new_ids_fn(u, _q=int(mem_end) - 1):
+        return got_b[u, :, _q]
+    want, ostate = P.pure_predict_forward(cfg, pcfg, qk, v, ostate, None, new_ids_fn=new_ids_fn)
+    assert int(mem_end) == ostate[0]
+    np.testing.assert_array_equal(qk_mem.cpu().numpy(), ostate[1][0].astype(np.float32))
+    np.testing.assert_array_equal(v_mem.cpu().numpy(), ostate[1][1].astype(np.float32))
+    np.testing.assert_array_equal(got_b.reshape(BH, nh * M), ostate[2][0])
+    np.testing.assert_array_equal(buckets_idx.cpu().numpy(), ostate[2][1])
+    assert tuple(out.shape) == (BH, n, 64)
+    util.assert_close(out.float().cpu().numpy(), want, 'out after %d tokens' % t0)
+  assert int(state[0]) < t0
+
+
+def test_pure_lsh_wrapper_predict_token_by_token():
+  """`PureLSHSelfAttentionWrapper(mode='predict')` (EA:3493-3540: Dense projections of the NEW tokens, the core's predict
+  mode, head merge, output Dense): a prefix, then single tokens; vs the same composition around the oracle's core."""
+  import trax_b200
+  rng = np.random.default_rng(41)
+  B, H, C, nh, M, drop = 2, 2, 64, 1, 128, 32
+  D = 64 * H
+  kw = dict(n_heads=H, d_qk=64, d_v=64, causal=True, chunk_len=C, n_chunks_before=1, n_hashes=nh, n_buckets=4)
+  cfg, pcfg = O.LSHConfig(**kw), P.PredictConfig(predict_mem_len=M, predict_drop_len=drop)
+  layer = trax_b200.PureLSHSelfAttentionWrapper(mode='predict', predict_mem_len=M, predict_drop_len=drop, bias=False,
+                                                num_weights=2, **kw)
+  weights, state = layer.init(trax_b200.ShapeDtype((B, 1, D)))
+  rot = rng.standard_normal((B * H,) + O.rotations_shape(cfg, 2)).astype(np.float32)
+  layer.sublayers[1]._rotations_override = torch.from_numpy(rot)
+  w_qk, w_v = (w.cpu().numpy().astype(np.float64) for w in weights[0])
+  w_out = weights[3].cpu().numpy().astype(np.float64)
+  calls = [M] + [1] * (2 * drop + 3)                                # a prefix that fills the memory (two chunks), then two rolls
+  xs = util.bf16_round(rng.standard_normal((B, sum(calls), D)))
+  ostate = (0, (np.zeros((B * H, M, 64)), np.zeros((B * H, M, 64))), (np.zeros((B * H, nh * M), np.int32), np.zeros((B * H,), np.int32)))
+
+  def split(t):                                                      # attention.py:347-364
+    return t.reshape(B, -1, H, 64).transpose(0, 2, 1, 3).reshape(B * H, -1, 64)
+  t0 = 0
+  for n in calls:
+    x = xs[:, t0:t0 + n]
+    t0 += n
+    out, state = layer.pure_fn(torch.from_numpy(x).cuda(), weights, state, None)
+    want_core, ostate = P.pure_predict_forward(cfg, pcfg, split(x @ w_qk), split(x @ w_v), ostate, lambda u, n_rows: rot[u])
+    want = want_core.reshape(B, H, n, 64).transpose(0, 2, 1, 3).reshape(B, n, D) @ w_out
+    # every earlier slot is attended (n_hashes * chunk_len * 2 == predict_mem_len), so the output does not hinge on bucket ids
+    util.assert_close_layer(out.float().cpu().numpy(), want, 'out after %d tokens' % t0)
+    assert int(state[1][0]) == ostate[0]

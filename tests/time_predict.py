@@ -5,8 +5,10 @@
 
 Prints ms per `lsh_predict_step` call (C-ABI level, memory already updated) and per `layer.forward` call (with the memory /
 bucket-memory bookkeeping).  NOT yet run on a GPU: round 2's GPU minutes ended before it could be."""
+import os
 import sys
 
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 
@@ -35,7 +37,7 @@ def main(steps=200):
     torch.cuda.synchronize()
     api_ms = e0.elapsed_time(e1) / steps
     mem_end, (mem,), inner = layer.state
-    rot = predict._step_rotations(layer, mem, inner[2]) if name == 'lsh' else None
+    rot = predict._step_rotations(layer, B, mem.device, inner[2]) if name == 'lsh' else None
     buckets = inner[0].clone() if name == 'lsh' else None
     q_start = int(mem_end) - 1
     for _ in range(10):

@@ -60,6 +60,8 @@ SIGNATURES = {
     'lsh_unpack_heads': (_I, [_I, _I, _I, _I, _P, _I, _I, _I, _P, _P]),
     'lsh_predict_workspace_bytes': (_SZ, [_D]),
     'lsh_predict_step': (_I, [_D, _P, _P, _P, _P, _P, _P, _P, _I64, ctypes.c_int32, _P, _P, _SZ, _P]),
+    'lsh_predict_attend_workspace_bytes': (_SZ, [_D]),
+    'lsh_predict_attend': (_I, [_D, _P, _P, _P, _I64, ctypes.c_int32, _P, _P, _SZ, _P]),
     'lsh_attn_launch_count': (_I64, [_I]),
 }
 

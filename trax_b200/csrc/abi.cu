@@ -643,6 +643,26 @@ int lsh_predict_step(const LshAttnDims *dims, const void *mem, const float *w_q,
   return predict_out_run(d, p.o, w_o, out, s);
 }
 
+size_t lsh_predict_attend_workspace_bytes(const LshAttnDims *dims) {
+  if (check_dims(dims, false)) return 0;
+  return static_cast<size_t>(derive(*dims).BH) * derive(*dims).N * 4 + 512;
+}
+
+int lsh_predict_attend(const LshAttnDims *dims, const void *qv, const float *rotations, int32_t *buckets, int64_t buckets_stride,
+                       int32_t q_start, float *o, void *ws, size_t ws_bytes, void *stream) {
+  if (int rc = check_dims(dims, false)) return rc;
+  const LshAttnDims &d = *dims;
+  if (!qv || !rotations || !buckets || !o || !ws) return set_error("lsh_predict_attend: NULL argument");
+  if (d.separate_k || d.masked || d.na != 0) return set_error("lsh_predict_attend: shared-QK, unmasked, no look-ahead (EA:2823-2932)");
+  Derived dr = derive(d);
+  if (buckets_stride < dr.N) return set_error("lsh_predict_attend: buckets_stride %lld < n_hashes * memory length %d", (long long)buckets_stride, dr.N);
+  if (ws_bytes < lsh_predict_attend_workspace_bytes(dims)) return set_error("lsh_predict_attend: workspace too small");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int32_t *hashed = reinterpret_cast<int32_t *>((reinterpret_cast<uintptr_t>(ws) + 255) / 256 * 256);
+  if (int rc = hash_bf16_qv(d, qv, rotations, nullptr, hashed, dr.N, s)) return rc;      // EA:2890
+  return predict_attend_run(d, qv, buckets, buckets_stride, hashed, q_start, o, s);
+}
+
 /* Debug aid (not in the public header): device buffer receiving per-phase clock stamps of CTA 0. */
 int lsh_debug_set_trace(void *dev_ptr) { lsh::g_fwd_trace = static_cast<long long *>(dev_ptr); return 0; }
 

@@ -142,18 +142,40 @@ def _step(layer, mem, weights, q_start, buckets, rotations, causal):
   return out
 
 
-def _step_rotations(layer, mem, hash_rng):
+def _step_rotations(layer, batch_size, device, hash_rng):
   """The rotations `hash_vectors(q, hash_rng)` draws at a single-token step (EA:2066): a function of the state's key and of
   the shape (d_qk, n_hashes, R) only — the same at every step, and the same as the prefix call's when `n_buckets` is given."""
   if layer._rotations_override is not None:
-    return layer._rotations_override.to(mem.device).to(torch.float32).contiguous()
+    return layer._rotations_override.to(device).to(torch.float32).contiguous()
   from trax_b200.lsh_attention import _to_int32_bits
-  batch_size, m, d_model = (int(s) for s in mem.shape)
   factors = ops.bucket_factors(layer._n_buckets, 2, layer._chunk_len)
-  dims = _lib.make_dims(batch_size, layer._n_heads, m, d_model, layer._d_qk, layer._d_v, layer._chunk_len,
-                        layer._n_chunks_before, 0, layer._n_hashes, factors, True, False, ops._act_dtype(mem))
-  keys = _to_int32_bits(hash_rng).to(mem.device).contiguous()
+  dims = _lib.make_dims(batch_size, layer._n_heads, layer._predict_mem_len, 64, layer._d_qk, layer._d_v, layer._chunk_len,
+                        layer._n_chunks_before, 0, layer._n_hashes, factors, True, False, _lib.LSH_DTYPE_BF16)
+  keys = _to_int32_bits(hash_rng).to(device).contiguous()
   return ops.make_rotations(dims, keys)[0]
+
+
+def _pure_step(layer, qk_mem, v_mem, q_start, buckets, rotations):
+  """One `lsh_predict_attend` call for the weight-less core (EA:2858-2932): qk_mem / v_mem (B*H, M, d_head) with the new
+  token stored at q_start; buckets (BH, nh*M) updated IN PLACE.  Returns out (B*H, 1, d_v) in the memory's dtype."""
+  lib = _lib.load()
+  dev = qk_mem.device
+  bh, m = int(qk_mem.shape[0]), int(qk_mem.shape[1])
+  io_dtype = qk_mem.dtype if qk_mem.dtype in (torch.float32, torch.bfloat16) else torch.float32
+  # (B*H, M, d) x 2 -> (B, M, H, [qk | v]) bf16, the row layout the kernels read (one launch)
+  qv = ops.pack_heads(qk_mem.to(io_dtype).contiguous(), v_mem.to(io_dtype).contiguous(), layer._n_heads)
+  factors = ops.bucket_factors(layer._n_buckets, 2, layer._chunk_len)                                # EA:2886-2890: 2 rows
+  dims = _lib.make_dims(bh // layer._n_heads, layer._n_heads, m, 64, layer._d_qk, layer._d_v, layer._chunk_len,
+                        layer._n_chunks_before, 0, layer._n_hashes, factors, True, False, _lib.LSH_DTYPE_BF16)
+  nbytes = lib.lsh_predict_attend_workspace_bytes(ctypes.byref(dims))
+  if nbytes == 0:
+    _lib.check(1, 'lsh_predict_attend_workspace_bytes')
+  ws = ops.workspace(dev, nbytes)
+  o = torch.empty((bh, layer._d_v), dtype=torch.float32, device=dev)
+  _lib.check(lib.lsh_predict_attend(ctypes.byref(dims), ops._ptr(qv), ops._ptr(rotations), ops._ptr(buckets), buckets.stride(0),
+                                    ctypes.c_int32(q_start), ops._ptr(o), ops._ptr(ws), ws.numel(), ops._stream()),
+             'lsh_predict_attend')
+  return o.view(bh, 1, layer._d_v).to(qk_mem.dtype)
 
 
 def _run(layer, x_d, weights, mem_end, mem, inner, rng, step=None, train=None):
@@ -173,7 +195,7 @@ def _run(layer, x_d, weights, mem_end, mem, inner, rng, step=None, train=None):
   if seqlen == 1:
     if with_buckets:
       new_buckets = roll_buckets(buckets, idx0, q_start, layer._n_hashes, m, drop)
-      out = step(layer, new_mem, weights, q_start, new_buckets, _step_rotations(layer, new_mem, hash_rng), True)
+      out = step(layer, new_mem, weights, q_start, new_buckets, _step_rotations(layer, int(new_mem.shape[0]), new_mem.device, hash_rng), True)
       new_inner = (new_buckets, torch.full_like(buckets_idx, q_start + 1), hash_rng)                 # EA:2108
     else:
       out = step(layer, new_mem, weights, q_start, None, None, layer._causal)
@@ -230,10 +252,72 @@ def forward_and_or_backward(layer, inputs, weights, state, rng, output_grad=None
   return (out if compute_output else None), new_state, None, None
 
 
+def _run_pure(layer, qk, v, mem_end, mems, inner, rng, step=None, train=None):
+  """`_run` for the weight-less core (EA:3122-3146 + 2823-2932): the memory is the pair (qk_mem, v_mem), both rolled and
+  updated alike (EA:2955-3033).  Returns (output (B*H, seqlen, d_v), (new_mem_end, (qk_mem, v_mem), new_inner))."""
+  step = step or _pure_step
+  train = train or (lambda inputs, st: layer.forward_and_or_backward(inputs, st, rng, compute_output=True, update_state=True,
+                                                                     _raw=True))
+  seqlen = int(qk.shape[1])
+  m, drop = layer._predict_mem_len, layer._predict_drop_len
+  att_qk, q_start, new_qk_mem, new_mem_end = use_predict_mem(qk, mem_end, mems[0], m, drop)
+  att_v, _, new_v_mem, _ = use_predict_mem(v, mem_end, mems[1], m, drop)
+  buckets, buckets_idx, hash_rng = inner
+  idx0 = int(buckets_idx.reshape(-1)[0]) if buckets_idx.numel() else 0
+  if seqlen == 1:
+    new_buckets = roll_buckets(buckets, idx0, q_start, layer._n_hashes, m, drop)
+    rotations = _step_rotations(layer, int(qk.shape[0]) // layer._n_heads, new_qk_mem.device, hash_rng)
+    out = step(layer, new_qk_mem, new_v_mem, q_start, new_buckets, rotations)
+    new_inner = (new_buckets, torch.full_like(buckets_idx, q_start + 1), hash_rng)                   # EA:2931
+  else:
+    if q_start != 0:                                               # EA:2831-2832
+      raise ValueError('predict mode: more than one token at a time only works at the start of a sequence '
+                       '(the memory already holds %d)' % q_start)
+    rows = int(att_qk.shape[1])
+    pad = (-rows) % layer._chunk_len                               # EA:2833-2838
+    if pad:
+      att_qk = torch.cat([att_qk, att_qk.new_zeros((att_qk.shape[0], pad, att_qk.shape[2]))], dim=1)
+      att_v = torch.cat([att_v, att_v.new_zeros((att_v.shape[0], pad, att_v.shape[2]))], dim=1)
+    out, (buckets_update, _), _ = train((att_qk.contiguous(), att_v.contiguous()), (None, hash_rng))  # EA:2839-2845
+    out = out[:, :seqlen].contiguous()
+    buckets_update = buckets_update[:, :layer._n_hashes * int(att_qk.shape[1])].contiguous()
+    new_buckets = store_prefix_buckets(buckets, buckets_update, seqlen, layer._n_hashes, m)
+    new_inner = (new_buckets, buckets_idx + seqlen, hash_rng)                                         # EA:2857
+  return out.to(qk.dtype), (new_mem_end, (new_qk_mem, new_v_mem), new_inner)
+
+
+def pure_init_state(layer, batch_x_heads, d_qk, d_v, dtype, device, rng_state):
+  """EA:2677-2686, 2700-2708: memories for qk and v, bucket memory, counters."""
+  m = layer._predict_mem_len
+  mems = (torch.zeros((batch_x_heads, m, d_qk), dtype=dtype, device=device),
+          torch.zeros((batch_x_heads, m, d_v), dtype=dtype, device=device))
+  buckets = torch.zeros((batch_x_heads, layer._n_hashes * m), dtype=torch.int32, device=device)
+  return (torch.zeros((), dtype=torch.int32), mems, (buckets, torch.zeros((batch_x_heads,), dtype=torch.int32), rng_state))
+
+
+def pure_forward_and_or_backward(layer, inputs, state, rng, output_grad=None, compute_output=True, update_state=True):
+  """`PureLSHSelfAttention.forward_and_or_backward` in predict mode (EA:3122-3146).  Returns (output, new_state, None)."""
+  if output_grad is not None or not update_state:
+    raise NotImplementedError('predict mode is forward-only with update_state=True (EA:2828-2829, 3125)')
+  qk, v = inputs[0], inputs[1]
+  if not isinstance(state, (tuple, list)) or len(state) != 3 or len(state[1]) != 2 or len(state[2]) != 3:
+    raise ValueError("predict mode: state must be (mem_end, (qk_mem, v_mem), (buckets, buckets_idx, rng)) (EA:2677-2686)")
+  if not qk.is_cuda:
+    raise ValueError('PureLSHSelfAttention takes device tensors (its caller holds the projections on the device)')
+  mem_end, mems, inner = state
+  dev = qk.device
+  with torch.cuda.device(dev):
+    out, (new_mem_end, new_mems, new_inner) = _run_pure(
+        layer, qk, v.to(dev), int(mem_end), (mems[0].to(dev), mems[1].to(dev)), (inner[0].to(dev), inner[1], inner[2]), rng)
+  new_state = (torch.tensor(new_mem_end, dtype=torch.int32), new_mems, new_inner)
+  return (out if compute_output else None), new_state, None
+
+
 def rotations_shape(layer, n_rows):
   """(d_qk, n_hashes, R) of the rotations a call that hashes `n_rows` rows draws (EA:79-91, 1893-1902)."""
   return (layer._d_qk, layer._n_hashes, sum(ops.bucket_factors(layer._n_buckets, n_rows, layer._chunk_len)) // 2)
 
 
-__all__ = ['use_predict_mem', 'roll_buckets', 'store_prefix_buckets', 'init_state', 'forward_and_or_backward', 'rotations_shape']
+__all__ = ['use_predict_mem', 'roll_buckets', 'store_prefix_buckets', 'init_state', 'pure_init_state', 'forward_and_or_backward',
+           'pure_forward_and_or_backward', 'rotations_shape']
 del np

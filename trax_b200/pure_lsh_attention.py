@@ -50,6 +50,11 @@ class PureLSHSelfAttention(LSHSelfAttention):
       rng_state = rng_state.view(torch.uint32)
     self.weights = ()                                               # EA:2689
     self.state = (buckets, rng_state)
+    if self._incremental:                                           # EA:2677-2686
+      from trax_b200 import predict
+      dtype = getattr(input_signature[0], 'dtype', torch.float32)
+      self.state = predict.pure_init_state(self, batch_x_heads, int(shape[2]), int(tuple(input_signature[1].shape)[2]),
+                                           dtype if isinstance(dtype, torch.dtype) else torch.float32, device, rng_state)
 
   # ---- forward / backward (EA:2935-2953, 3035-3050) --------------------------------------------------
   def forward(self, inputs):
@@ -70,11 +75,17 @@ class PureLSHSelfAttention(LSHSelfAttention):
     return out, new_state
 
   # ---- the batched driver (EA:3052-3265) -------------------------------------------------------------
-  def forward_and_or_backward(self, inputs, state, rng, output_grad=None, compute_output=True, update_state=True):
+  def forward_and_or_backward(self, inputs, state, rng, output_grad=None, compute_output=True, update_state=True, _raw=False):
     """Returns (output, new_state, inputs_grad): output iff compute_output, new_state iff update_state,
-    inputs_grad = (dqk, dv[, None for the mask]) iff output_grad is given."""
+    inputs_grad = (dqk, dv[, None for the mask]) iff output_grad is given.  In predict mode (EA:3122-3146) the call goes
+    to trax_b200/predict.py; `_raw` is that module's way back to the training-path kernels for a prefix."""
     if not isinstance(inputs, (tuple, list)) or len(inputs) != self._n_in:
       raise ValueError('PureLSHSelfAttention(masked=%s) takes %d inputs' % (self._masked, self._n_in))
+    if self._incremental and not _raw:
+      if not torch.cuda.is_available():
+        raise _lib.LshAttnError('trax_b200.PureLSHSelfAttention needs a CUDA device (no CPU fallback)')
+      from trax_b200 import predict
+      return predict.pure_forward_and_or_backward(self, inputs, state, rng, output_grad, compute_output, update_state)
     compute_grad = output_grad is not None
     assert compute_output or compute_grad, 'No work to perform!'
     if not torch.cuda.is_available():
