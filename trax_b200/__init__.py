@@ -3,7 +3,9 @@
 
 Layout: csrc/ (CUDA kernels + C ABI, built to liblsh_attn_b200.so), _lib.py (ctypes binding),
 ops.py (stage-level wrappers), lsh_attention.py (the layer with the reference's interface),
-pure_lsh_attention.py (its weight-less core, `PureLSHSelfAttention`, and `PureLSHSelfAttentionWrapper` around it), self_attention.py (`SelfAttention` with share_qk=True on the same core).
+pure_lsh_attention.py (its weight-less core, `PureLSHSelfAttention`, and `PureLSHSelfAttentionWrapper` around it),
+self_attention.py (`SelfAttention`, both `share_qk` settings, on the same core), predict.py (fast inference, `mode='predict'`, of
+all four), reversible.py (`ReversibleHalfResidual` around the layer), dp.py (multi-GPU drivers).
 Importing the package does not need a GPU; calling anything does, and raises otherwise.
 """
 from trax_b200.lsh_attention import (LSHSelfAttention, ShapeDtype, host_io_bytes,  # noqa: F401
