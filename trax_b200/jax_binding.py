@@ -112,3 +112,22 @@ def forward_and_or_backward(layer, inputs, weights, state, rng, output_grad=None
   if not compute_output:
     out = None
   return out, new_state, dx, dw
+
+
+def predict_step(layer, mem, weights, buckets, hash_rng, q_start):
+  """One fast-inference step (EA:2032-2109) on the `lsh_predict_step` custom call: `mem` (B, M, D) is the input memory with the
+  new token stored at `q_start` (`_use_predict_mem`, EA:2174-2207, stays JAX code), `buckets` (B*H, n_hashes*M) the bucket
+  memory after `roll_buckets` (EA:2036-2053).  The rotations are drawn from the state's key itself — predict mode does not
+  split it (EA:2066).  Returns (output (B, 1, D), new bucket memory)."""
+  import numpy as np
+  w_q, w_v, w_o = weights
+  nh, cl = layer._n_hashes, layer._chunk_len                           # pylint: disable=protected-access
+  factors = _bucket_factors(layer._n_buckets, 2, cl)                   # pylint: disable=protected-access  (EA:2064: two rows)
+  rotations = jax.vmap(lambda k: jax.random.normal(k, (layer._d_qk, nh, sum(factors) // 2)))(hash_rng).astype(jnp.float32)
+  new_buckets, out = jax.ffi.ffi_call(
+      'lsh_predict_step', (jax.ShapeDtypeStruct(buckets.shape, jnp.int32),
+                           jax.ShapeDtypeStruct((mem.shape[0], 1, mem.shape[2]), mem.dtype)))(
+                               mem, w_q, w_v, w_o, jnp.zeros((0,), jnp.float32), rotations, buckets,
+                               chunk_len=np.int32(cl), n_chunks_before=np.int32(layer._n_chunks_before), n_hashes=np.int32(nh),
+                               factors=np.asarray(factors, np.int32), causal=True, separate_k=False, q_start=np.int32(q_start))
+  return out, new_buckets
