@@ -135,3 +135,39 @@ def test_jax_ffi_shim_translation_unit_compiles_and_is_guarded(tmp_path):
     assert n_args == len(_lib.SIGNATURES[fn][1]), (fn, n_args, len(_lib.SIGNATURES[fn][1]))
   with pytest.raises(ImportError):
     import trax_b200.jax_binding  # noqa: F401  (no jax in this image)
+
+
+def test_predict_entry_points_validate_their_arguments_without_a_gpu():
+  """`lsh_predict_step` / `lsh_predict_attend` (fast inference, ABI v5): workspace queries answer and argument errors come
+  back as status + message before any CUDA call; the predict-mode state layout of the layers (EA:1833-1841, 1883-1887,
+  2677-2686) is the reference's."""
+  import torch
+  import trax_b200
+  from trax_b200 import _lib
+  lib = _lib.load()
+  assert lib.lsh_attn_abi_version() == 5
+  d = _lib.make_dims(1, 8, 2048, 1024, 64, 64, 128, 1, 0, 4, [64], True, False, _lib.LSH_DTYPE_BF16)
+  assert lib.lsh_predict_workspace_bytes(ctypes.byref(d)) > 2048 * 8 * 128 * 2          # at least the projected memory
+  assert lib.lsh_predict_attend_workspace_bytes(ctypes.byref(d)) >= 8 * 4 * 2048 * 4    # the step's hash of every slot
+  assert lib.lsh_predict_step(ctypes.byref(d), None, None, None, None, None, None, None, 0, 0, None, None, 0, None) != 0
+  assert b'NULL' in lib.lsh_attn_last_error()
+  assert lib.lsh_predict_attend(ctypes.byref(d), None, None, None, 0, 0, None, None, 0, None) != 0
+  assert b'NULL' in lib.lsh_attn_last_error()
+  bad = _lib.make_dims(1, 8, 2048, 1024, 7, 17, 128, 1, 0, 4, [64], True, False, _lib.LSH_DTYPE_BF16)
+  assert lib.lsh_predict_workspace_bytes(ctypes.byref(bad)) == 0 and b'd_qk=7' in lib.lsh_attn_last_error()
+  layer = trax_b200.LSHSelfAttention(n_heads=8, causal=True, n_hashes=4, n_buckets=64, mode='predict')
+  layer.init_weights_and_state(trax_b200.ShapeDtype((2, 1, 1024), torch.bfloat16), device='cpu')
+  mem_end, (mem,), (buckets, buckets_idx, rng) = layer.state
+  assert int(mem_end) == 0 and tuple(mem.shape) == (2, 2048, 1024) and mem.dtype == torch.bfloat16
+  assert tuple(buckets.shape) == (16, 4 * 2048) and buckets.dtype == torch.int32 and tuple(buckets_idx.shape) == (16,)
+  assert tuple(rng.shape) == (16, 2)
+  core = trax_b200.PureLSHSelfAttention(n_heads=8, causal=True, n_hashes=4, n_buckets=64, mode='predict')
+  core.init_weights_and_state((trax_b200.ShapeDtype((16, 1, 64)),) * 2, device='cpu')
+  assert [tuple(t.shape) for t in core.state[1]] == [(16, 2048, 64)] * 2 and core.weights == ()
+  sa = trax_b200.SelfAttention(n_heads=8, causal=True, chunk_len=128, n_chunks_before=1, mode='predict', predict_mem_len=2048,
+                               predict_drop_len=256)
+  sa.init_weights_and_state(trax_b200.ShapeDtype((2, 1, 1024)), device='cpu')
+  assert len(sa.weights) == 4 and sa.state[2] == () and tuple(sa.state[1][0].shape) == (2, 2048, 1024)
+  if not torch.cuda.is_available():
+    with pytest.raises(_lib.LshAttnError):
+      layer.forward(torch.zeros(2, 1, 1024))

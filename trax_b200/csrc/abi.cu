@@ -1,8 +1,9 @@
 // extern "C" surface of liblsh_attn_b200.so (see include/lsh_attn.h) + the layer-level orchestration
 // that mirrors LSHSelfAttention.forward_and_or_backward (EA:2261-2561) for every unit at once.
 //
-// The D-contractions (x·w_q|w_v EA:1923-1924, o·w_o EA:1995 and their VJPs) are plain dense GEMMs and
-// go to cuBLAS (bf16 operands, fp32 accumulation); everything between them is hand-written CUDA.
+// The D-contractions (x·w_q|w_v EA:1923-1924, o·w_o EA:1995 and their VJPs) run on the hand-written tcgen05 + TMA GEMM of
+// gemm_tc.cu (bf16 operands, fp32 accumulation); cuBLAS is only the fallback for shapes outside that kernel's tiling
+// (N % 128 != 0 or K % 64 != 0 — none of the BASELINE configs) and the A/B reference (LSH_GEMM=cublas).
 #include <cublas_v2.h>
 #include <stdarg.h>
 #include <stdio.h>
