@@ -1,8 +1,8 @@
 """Helper (not a test, not collected): dry run of tests/test_zgpu_predict.py's LAYER-level tests on the CPU — torch.cuda
 patched to no-ops, the CUDA entry points (`predict._step`, `predict._pure_step`, the layers' training-path forward) replaced by
 the oracle — so that the test logic and `trax_b200/predict.py`'s plumbing can be exercised where there is no GPU.  It proves
-nothing about the kernels (the step-level GPU tests do); it was how the layer-level tests were debugged after round 2's GPU
-minutes had run out.        python tests/dry_run_predict_gpu_tests.py"""
+nothing about the kernels (the GPU tests do); it is how the layer-level tests were debugged while no GPU was at hand — they
+then passed on a B200 at the first attempt (profiles/r2_gputest_predict_layers.log).        python tests/dry_run_predict_gpu_tests.py"""
 import contextlib, sys
 import numpy as np, torch
 import os
