@@ -247,3 +247,28 @@ def test_pure_core_predict_host_logic_matches_the_oracle(prefix):
     np.testing.assert_array_equal(mems[1].numpy(), ostate[1][1])
     np.testing.assert_array_equal(inner[0].numpy(), ostate[2][0])
     np.testing.assert_array_equal(inner[1].numpy(), ostate[2][1])
+
+
+def test_kernel_key_selection_edge_cases(select_lib):
+  """Largest memory the kernel takes (32 768 slots), many hash rounds, every slot valid / no slot valid, K below and above
+  the number of candidates."""
+  rng = np.random.default_rng(99)
+  cases = []
+  for M, nh in ((32768, 8), (4096, 64), (33, 1)):
+    for fill in ('random', 'all_valid', 'none_valid'):
+      for q_start in (0, M // 3, M - 1):
+        for k_sel in (2, 300, 2 * M):
+          cases.append((M, nh, fill, q_start, k_sel))
+  for M, nh, fill, q_start, k_sel in cases:
+    qb = (np.arange(nh) * 4 + rng.integers(0, 4, nh)).astype(np.int32)
+    if fill == 'random':
+      buckets = (rng.integers(0, 4, (nh, M)) + 4 * np.arange(nh)[:, None]).astype(np.int32)
+    elif fill == 'all_valid':
+      buckets = np.repeat(qb[:, None], M, axis=1).astype(np.int32)
+    else:
+      buckets = np.repeat(((qb + 1) % 4 + 4 * np.arange(nh))[:, None], M, axis=1).astype(np.int32)
+    buckets[:, q_start] = qb
+    flags = np.zeros(M, np.uint8)
+    select_lib.predict_select_host(buckets.ctypes.data, qb.ctypes.data, M, nh, q_start, k_sel, flags.ctypes.data)
+    want = _reference_selection(buckets.reshape(-1), qb, M, nh, q_start, k_sel)
+    np.testing.assert_array_equal(flags[:q_start + 1] == 1, want[:q_start + 1], err_msg=str((M, nh, fill, q_start, k_sel)))
