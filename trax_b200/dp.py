@@ -157,6 +157,8 @@ class HeadShardedLSHSelfAttention:
   def __init__(self, local_layer, n_heads, group=None, reduce='all'):
     if reduce not in ('all', 'scatter'):
       raise ValueError("reduce must be 'all' or 'scatter'")
+    if getattr(local_layer, '_incremental', False):
+      raise NotImplementedError("head sharding is built for the training path; a mode='predict' layer is not sharded")
     self._local = local_layer
     self._n_heads = n_heads
     self._group = group
