@@ -272,3 +272,17 @@ def test_kernel_key_selection_edge_cases(select_lib):
     select_lib.predict_select_host(buckets.ctypes.data, qb.ctypes.data, M, nh, q_start, k_sel, flags.ctypes.data)
     want = _reference_selection(buckets.reshape(-1), qb, M, nh, q_start, k_sel)
     np.testing.assert_array_equal(flags[:q_start + 1] == 1, want[:q_start + 1], err_msg=str((M, nh, fill, q_start, k_sel)))
+
+
+def test_reversible_block_does_not_fuse_the_residual_into_a_predict_mode_layer():
+  """`ReversibleHalfResidual` folds `x1 + Attn(...)` into the training path's output-projection epilogue; the decode step has
+  no such epilogue, so a predict-mode attention layer must take the separate-add path (the fused call would drop the
+  residual silently)."""
+  import trax_b200
+  train = trax_b200.ReversibleHalfResidual(trax_b200.LSHSelfAttention(causal=True))
+  pred = trax_b200.ReversibleHalfResidual(trax_b200.LSHSelfAttention(causal=True, mode='predict'))
+
+  class _Dev(torch.Tensor):                                          # a CPU tensor that claims to live on the device
+    is_cuda = True
+  a = torch.zeros((1, 4, 8)).as_subclass(_Dev)
+  assert train._fused(a, a) and not pred._fused(a, a)

@@ -149,7 +149,8 @@ class ReversibleHalfResidual:
   def _fused(self, accumulator, z):
     """The residual add / subtract can ride in the attention layer's output-projection epilogue (device tensors only)."""
     from trax_b200.lsh_attention import LSHSelfAttention
-    return (isinstance(self._attention_layer, LSHSelfAttention) and accumulator.is_cuda and z.is_cuda
+    return (isinstance(self._attention_layer, LSHSelfAttention) and not self._attention_layer._incremental   # (predict mode:
+            and accumulator.is_cuda and z.is_cuda                                           # the decode step has no epilogue)
             and accumulator.shape == z.shape and accumulator.dtype == z.dtype)
 
   def reverse(self, output, weights=(), state=(), new_state=(), rng=None):
