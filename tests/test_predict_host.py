@@ -286,3 +286,39 @@ def test_reversible_block_does_not_fuse_the_residual_into_a_predict_mode_layer()
     is_cuda = True
   a = torch.zeros((1, 4, 8)).as_subclass(_Dev)
   assert train._fused(a, a) and not pred._fused(a, a)
+
+
+def test_self_attention_without_chunks_decodes_in_predict_mode_only():
+  """`SelfAttention(chunk_len=None)` — the reference's default — is dense attention; the training kernels are chunked, but a
+  decode step attends over the whole memory whatever the chunk length (EA:1262-1267), and with `chunk_len=None` a prefix is
+  never chunked either (EA:1250): token-by-token steps.  Control flow vs the oracle, CUDA step swapped for the oracle's."""
+  import trax_b200
+  from trax_b200 import predict
+  with pytest.raises(NotImplementedError):
+    trax_b200.SelfAttention(causal=True)
+  rng = np.random.default_rng(17)
+  B, H, D, M, drop, dq, dv = 1, 2, 12, 16, 4, 6, 5
+  kw = dict(n_heads=H, d_qk=dq, d_v=dv, share_qk=False, causal=True, chunk_len=None)
+  cfg, pcfg = SA.SelfAttentionConfig(**kw), P.PredictConfig(predict_mem_len=M, predict_drop_len=drop)
+  layer = trax_b200.SelfAttention(mode='predict', predict_mem_len=M, predict_drop_len=drop, **kw)
+  w = tuple(rng.standard_normal(s) / 3 for s in ((H, D, dq), (H, D, dq), (H, D, dv), (H, dv, D)))
+
+  def fake_step(layer_, mem, weights, q_start, buckets, rotations, causal):
+    out = np.zeros((B, 1, D))
+    for u in range(B * H):
+      out[u // H] += P.self_attention_incremental_unit(cfg, mem[u // H].numpy(), q_start, 1, tuple(a[u % H] for a in w))
+    return torch.from_numpy(out)
+
+  def no_train(*a):
+    raise AssertionError('a dense prefix must not reach the chunked training path')
+  calls = [9] + [1] * 14                                             # a prefix longer than the stand-in chunk length would be
+  xs = rng.standard_normal((B, sum(calls), D))
+  ostate, mem_end, mem, t0 = (0, np.zeros((B, M, D))), 0, torch.zeros((B, M, D), dtype=torch.float64), 0
+  layer._chunk_len = 4                                               # (the stand-in only sizes the C ABI's dims)
+  for n in calls:
+    x = xs[:, t0:t0 + n]
+    t0 += n
+    want, ostate = P.self_attention_predict_forward(cfg, pcfg, x, w, ostate)
+    out, (mem_end, mem, _) = predict._run(layer, torch.from_numpy(x), w, mem_end, mem, (), None, step=fake_step, train=no_train)
+    np.testing.assert_allclose(out.numpy(), want, rtol=1e-12, atol=1e-12)
+    assert mem_end == ostate[0]

@@ -216,7 +216,7 @@ def _run(layer, x_d, weights, mem_end, mem, inner, rng, step=None, train=None):
       buckets_update = buckets_update[:, :layer._n_hashes * int(att_in.shape[1])].contiguous()
       new_buckets = store_prefix_buckets(buckets, buckets_update, seqlen, layer._n_hashes, m)
       new_inner = (new_buckets, buckets_idx + seqlen, hash_rng)                                       # EA:2030
-    elif seqlen > layer._chunk_len:                                # EA:1250-1261: whole chunks of the prefix itself
+    elif seqlen > layer._chunk_len and not getattr(layer, '_dense', False):   # EA:1250-1261: whole chunks of the prefix itself
       if seqlen % layer._chunk_len or rows != seqlen:
         raise ValueError('predict mode: a prefix longer than chunk_len must be a multiple of it and longer than '
                          'predict_drop_len (EA:1250-1252, 2209)')

@@ -15,7 +15,8 @@ scale and without the self mask, and the key-side cotangent goes to `dw_k` inste
 Interface kept: the constructor keywords (EA:939-953), weights `(w_q, w_v, w_o)` for `share_qk`, `(w_q, w_k, w_v, w_o)`
 otherwise (EA:1112-1128), state `()` (EA:1130-1131), `forward`, `backward`, `forward_and_or_backward` →
 `(output, new_state, inputs_grad, weights_grad)`.  `mode='predict'` (EA:1200-1268; state `(mem_end, (mem,), ())`) runs
-through trax_b200/predict.py.  `chunk_len=None` (one dense window over the whole sequence) is not built and raises.
+through trax_b200/predict.py.  `chunk_len=None` (one dense window over the whole sequence) is built for predict mode only
+(a decode step attends over the whole memory whatever the chunk length, EA:1262-1267); in the other modes it raises.
 """
 import torch
 
@@ -29,10 +30,12 @@ class SelfAttention(LSHSelfAttention):
                n_chunks_before=0, n_chunks_after=0, bias=False, mode='train', predict_mem_len=None, predict_drop_len=None,
                attention_dropout=0.0, output_dropout=0.0, n_parallel_heads=None, use_python_loop=False,
                use_reference_code=False):
-    if chunk_len is None:
-      raise NotImplementedError('SelfAttention(chunk_len=None) is dense attention over the whole sequence; the kernels are '
-                                'chunked (chunk_len 32 / 64 / 128 / 256)')
-    super().__init__(n_heads=n_heads, d_qk=d_qk, d_v=d_v, causal=causal, masked=masked, chunk_len=chunk_len,
+    dense = chunk_len is None
+    if dense and mode != 'predict':
+      raise NotImplementedError('SelfAttention(chunk_len=None) is dense attention over the whole sequence; the training '
+                                'kernels are chunked (chunk_len 32 / 64 / 128 / 256).  In predict mode it is built: every '
+                                'decode step attends over the whole memory anyway (EA:1262-1267)')
+    super().__init__(n_heads=n_heads, d_qk=d_qk, d_v=d_v, causal=causal, masked=masked, chunk_len=64 if dense else chunk_len,
                      n_chunks_before=n_chunks_before, n_chunks_after=n_chunks_after, n_hashes=1, n_buckets=2, mode=mode,
                      predict_mem_len=predict_mem_len, predict_drop_len=predict_drop_len, attention_dropout=attention_dropout, output_dropout=output_dropout, bias=bias,
                      n_parallel_heads=n_parallel_heads, use_python_loop=use_python_loop,
@@ -40,6 +43,7 @@ class SelfAttention(LSHSelfAttention):
     self._share_qk = bool(share_qk)
     self._separate_k = not share_qk
     self._predict_hashes = False
+    self._dense = dense                 # chunk_len=None (predict mode only): prefixes are never chunked (EA:1250)
 
   def init_weights_and_state(self, input_signature, device=None):
     super().init_weights_and_state(input_signature, device=device)   # same (w_q, w_v, w_o) shapes and init (EA:1061-1066)
