@@ -218,8 +218,8 @@ def test_unsupported_shapes_are_rejected():
   layer.init(trax_b200.ShapeDtype((2, 10, 13)))
   with pytest.raises(_lib.LshAttnError):
     layer.forward(torch.zeros(2, 10, 13, device='cuda'))
-  with pytest.raises(NotImplementedError):
-    trax_b200.LSHSelfAttention(mode='predict', causal=True)
+  with pytest.raises(NotImplementedError):                          # predict mode is built (tests/test_zgpu_predict.py) but takes
+    trax_b200.LSHSelfAttention(mode='predict', causal=True, masked=True)   # one input (EA:1999-2001)
   with pytest.raises(ValueError):
     trax_b200.LSHSelfAttention(attention_dropout=1.0)
   with pytest.raises(ValueError):

@@ -102,9 +102,14 @@ def test_self_attention_autograd_with_separate_keys():
 def test_self_attention_rejects_what_is_not_built():
   import trax_b200
   with pytest.raises(NotImplementedError):
-    trax_b200.SelfAttention(n_heads=2, share_qk=True, causal=True)                              # chunk_len=None
-  with pytest.raises(NotImplementedError):
+    trax_b200.SelfAttention(n_heads=2, share_qk=True, causal=True)                              # chunk_len=None outside predict mode
+  with pytest.raises(ValueError):                                   # predict mode (tests/test_zgpu_predict.py) needs its memory sizes
     trax_b200.SelfAttention(n_heads=2, causal=True, chunk_len=128, mode='predict')
+  with pytest.raises(NotImplementedError):                          # ... and is forward-only (EA:2002-2003)
+    sa = trax_b200.SelfAttention(n_heads=2, causal=True, chunk_len=64, mode='predict', predict_mem_len=128, predict_drop_len=64)
+    _, st = sa.init(trax_b200.ShapeDtype((1, 1, 64)))
+    sa.forward_and_or_backward(torch.zeros((1, 1, 64), device='cuda'), sa.weights, st, None,
+                               output_grad=torch.zeros((1, 1, 64), device='cuda'))
   layer = trax_b200.SelfAttention(n_heads=2, causal=True, chunk_len=64)
   layer.init(trax_b200.ShapeDtype((1, 128, 64)))
   with pytest.raises(ValueError):                                   # share_qk=False takes four weights
