@@ -37,9 +37,9 @@ class SelfAttention(LSHSelfAttention):
                                 'decode step attends over the whole memory anyway (EA:1262-1267)')
     super().__init__(n_heads=n_heads, d_qk=d_qk, d_v=d_v, causal=causal, masked=masked, chunk_len=64 if dense else chunk_len,
                      n_chunks_before=n_chunks_before, n_chunks_after=n_chunks_after, n_hashes=1, n_buckets=2, mode=mode,
-                     predict_mem_len=predict_mem_len, predict_drop_len=predict_drop_len, attention_dropout=attention_dropout, output_dropout=output_dropout, bias=bias,
-                     n_parallel_heads=n_parallel_heads, use_python_loop=use_python_loop,
-                     use_reference_code=use_reference_code)
+                     predict_mem_len=predict_mem_len, predict_drop_len=predict_drop_len, attention_dropout=attention_dropout,
+                     output_dropout=output_dropout, bias=bias, n_parallel_heads=n_parallel_heads,
+                     use_python_loop=use_python_loop, use_reference_code=use_reference_code)
     self._share_qk = bool(share_qk)
     self._separate_k = not share_qk
     self._predict_hashes = False
